@@ -1,0 +1,172 @@
+/* odecol.h -- C ABI of the B200-native fused integrator for the ODE-Column hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces a piece of the
+ * reference's Python call stack; the citation after each declaration names what it replaces
+ * (paths relative to the reference repository, ccnmaastricht/ODE-Column).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers to float32 (int32 / uint8 where declared), caller-owned,
+ *     never retained past the call; the library performs no hidden allocation -- scratch memory is a
+ *     caller-provided workspace sized by odecol_workspace_bytes();
+ *   - calls are asynchronous with respect to the host and ordered on `stream` (a cudaStream_t passed as
+ *     void* so that the header needs no CUDA include);
+ *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
+ *   - re-entrant across streams, no global mutable state, one GPU per call (multi-GPU orchestration is
+ *     the caller's: shard trials, then all-reduce grad_W_aug);
+ *   - there is NO CPU implementation behind this ABI.
+ *
+ * The problem integrated (all three reference networks reduce to it):
+ *
+ *     r      = phi(V - A)                                  src/utils.py:13-28
+ *     I      = W r + U s(t) + bias  =  W_aug . [r ; s(t) ; 1]
+ *     dV/dt  = (-V + I * tau_s * R) / tau_m                src/coupled_columns.py:225-229, 402/431, 746-749/777
+ *     dA/dt  = (-A + kappa * r) / tau_a                    :230-231, 433-434, 779-780
+ *     dF/dt  = (-F + r) / tau_s                            :232-233, 437-438, 783-784
+ *     g      = sigma (per state component, scalar noise)   :239-249, 444-454, 790-800
+ *
+ * State layout: y[b] = [ V(0..N) | A(0..N) | F(0..N) ], trajectories are (T, B, 3N) row-major, exactly
+ * the (len(t), batch, d) tensors torchdiffeq / torchsde return.
+ */
+#ifndef ODECOL_H
+#define ODECOL_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODECOL_ABI_VERSION 1
+
+enum {
+    ODECOL_OK = 0,
+    ODECOL_E_NULL = -1,        /* required pointer is NULL                              */
+    ODECOL_E_SHAPE = -2,       /* N, B, T, K, n_in or ld_w out of range                 */
+    ODECOL_E_UNSUPPORTED = -3, /* valid request the library has no kernel for           */
+    ODECOL_E_WORKSPACE = -4,   /* workspace missing or smaller than workspace_bytes()   */
+    ODECOL_E_CUDA = -5,        /* a CUDA runtime call or launch failed                  */
+    ODECOL_E_ALIGN = -6        /* a pointer violates the 16-byte alignment contract     */
+};
+
+/* per-trial solver status written by the adaptive entry points */
+enum {
+    ODECOL_ST_OK = 0,
+    ODECOL_ST_NONFINITE = 1,   /* state became inf/NaN (phi has a pole at V-A = 981/48) */
+    ODECOL_ST_MAXSTEPS = 2,    /* step budget exhausted before t[T-1]                   */
+    ODECOL_ST_UNDERFLOW = 3    /* t + dt == t                                           */
+};
+
+/* operations, for odecol_workspace_bytes() */
+enum {
+    ODECOL_OP_RHS = 0,
+    ODECOL_OP_RK4_FWD = 1,
+    ODECOL_OP_RK4_BWD = 2,
+    ODECOL_OP_DOPRI5_FWD = 3,
+    ODECOL_OP_EM_FWD = 4,
+    ODECOL_OP_EM_BWD = 5
+};
+
+/* The column network in linear form plus the stimulus of every trial.
+ * Replaces the nn.Module attributes the reference solvers read through func(t, y):
+ *   recurrent / lateral / feedforward / input weights   src/coupled_columns.py:183, 318-341, 601, 631, 665-668
+ *   background_weights * background_drive               :222, 398, 743
+ *   adaptation_strength (kappa), time constants, R      :28-37, 50
+ *   network.time_vec / network.stim                     scripts/wta_ode.py:154,171  xor_ode.py:112,156  parity_ode.py:181,231
+ */
+typedef struct odecol_problem {
+    int32_t N;            /* populations (8 per column)                                      */
+    int32_t n_in;         /* stimulus channels                                               */
+    int32_t B;            /* trials (independent solves; the reference loops over them)      */
+    int32_t K;            /* stimulus knots per trial (>= 2)                                 */
+    int32_t ld_w;         /* floats per row of W_aug, >= N + n_in + 1, multiple of 4         */
+    int32_t reserved0;
+    const float* W_aug;   /* [N][ld_w]: columns [0,N) = W (row target, col source),
+                             [N, N+n_in) = U, column N+n_in = bias, rest zero                */
+    const float* kappa;   /* [N]                                                             */
+    const float* sigma;   /* [3N] diffusion per state component, may be NULL (treated as 0)  */
+    const float* knot_t;  /* [K] strictly increasing knot times (the reference's time_vec)   */
+    const float* knot_u;  /* [B][K][n_in] stimulus values at the knots; piecewise-linear in
+                             between, held beyond the ends (src/utils.py:31-46)              */
+    int64_t knot_stride_b;/* floats between consecutive trials in knot_u (0 = shared)        */
+    float tau_s, tau_m, tau_a, resistance;
+} odecol_problem;
+
+int odecol_abi_version(void);
+const char* odecol_strerror(int code);
+
+/* Scratch requirement of `op` on this problem with T output times (bytes, 0 if none). */
+size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T);
+
+/* f = forward(t, y) for a batch: t[B] (one time per trial), y[B][3N] -> f[B][3N].
+ * Replaces ColumnAreaWTA.forward / ColumnNetworkXOR.forward / ColumnNetwork.forward
+ * (src/coupled_columns.py:204-237, 407-442, 753-788) incl. compute_firing_rate and torch_interp
+ * (src/utils.py:13-46). */
+int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f, void* stream);
+
+/* Fixed-grid RK4 (3/8 rule) on the grid t[0..T): y_out[0] = y0, y_out[j] = y(t[j]).
+ * Replaces torchdiffeq.odeint(func, y0, t, method='rk4') plus the per-trial Python loop
+ * (scripts/xor_ode.py:104-117, scripts/parity_ode.py:223-236, scripts/wta_ode.py:167-176).
+ * y_out may be strided in time: y_out[j] is written iff j % out_every == 0 or j == T-1; row index j / out_every
+ * (last row = ceil((T-1)/out_every)).  out_every = 1 gives the torchdiffeq result (T, B, 3N). */
+int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0,
+                   float* y_out, int32_t out_every, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact discrete adjoint of odecol_rk4_fwd (discretise-then-optimise: what loss.backward() through
+ * torchdiffeq's unrolled steps computes; scripts/xor_ode.py:177, scripts/parity_ode.py:250).
+ *   y_traj      (T, B, 3N) the forward result with out_every = 1
+ *   grad_y      (T, B, G)  dL/dy_out restricted to the state components sel[0..G); sel == NULL means
+ *                          G = 3N, all components in order
+ *   grad_y0     (B, 3N)    out, may be NULL
+ *   grad_W_aug  (N, ld_w)  out, OVERWRITTEN with sum over trials of dL/dW_aug (dW | dU | dbias) */
+int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const float* y_traj,
+                   const float* grad_y, const int32_t* sel, int32_t G,
+                   float* grad_y0, float* grad_W_aug,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adaptive Dormand-Prince 5(4) with per-trial step control and 4th-order dense output at t[0..T).
+ * Replaces torchdiffeq.odeint(func, y0, t) with its default method (what the reference scripts get,
+ * scripts/xor_ode.py:114, scripts/parity_ode.py:233; rtol 1e-7, atol 1e-9 are torchdiffeq's defaults).
+ * n_accept / n_reject / status are per trial, any of them may be NULL. */
+int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
+                      float rtol, float atol, int32_t max_steps,
+                      int32_t* n_accept, int32_t* n_reject, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Euler-Maruyama in torchsde's integrate loop (scalar noise, Ito): steps of `dt` from ts[0], the last
+ * one clipped to ts[T-1], outputs by linear interpolation between the two solver states around ts[j].
+ * Replaces torchsde.sdeint(sde, y0, ts, names={'drift':'forward','diffusion':'diffusion'}, method='euler',
+ * dt=, adaptive=, rtol=, atol=, dt_min=) (call sites scripts/wta_ode.py:174,200).
+ *   dW       (n_steps, B) host-supplied Brownian increments in step order (bit-parity mode, fixed step
+ *            only; n_steps = odecol_em_num_steps()), or NULL: increments come from the in-kernel Philox4x32-10
+ *            virtual Brownian tree keyed by (seed, trial_offset + b)
+ *   adaptive 0 = fixed step; 1 = step doubling with torchsde's controller, per trial
+ *   y_steps  optional (n_steps+1, B, 3N): every solver state (needed by odecol_em_bwd), fixed step only */
+int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out,
+                  const float* dW, uint64_t seed, int64_t trial_offset,
+                  float dt, int32_t adaptive, float rtol, float atol, float dt_min,
+                  int32_t* n_accept, int32_t* n_reject, int32_t* status, float* y_steps,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of fixed steps odecol_em_fwd takes for (ts, dt): the float32 time loop is data independent.
+ * ts is a HOST pointer here. */
+int64_t odecol_em_num_steps(const float* ts_host, int32_t T, float dt);
+
+/* Discrete adjoint of the fixed-step Euler-Maruyama solve (additive noise: dW does not enter the Jacobian).
+ *   y_steps (n_steps+1, B, 3N) from odecol_em_fwd, grad_y (T, B, G) as in odecol_rk4_bwd. */
+int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps,
+                  const float* grad_y, const int32_t* sel, int32_t G, float dt,
+                  float* grad_y0, float* grad_W_aug,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Which kernel family a call would use: 0 = persistent on-chip ("small", W row in registers),
+ * 1 = staged FP32-FFMA contraction, 2 = staged 3xTF32 tcgen05 contraction.  Diagnostic only. */
+int odecol_kernel_family(const odecol_problem* p, int op);
+
+/* Number of kernel launches the last call of `op` on this thread enqueued (for bench bookkeeping). */
+int64_t odecol_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODECOL_H */

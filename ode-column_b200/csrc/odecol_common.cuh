@@ -1,0 +1,121 @@
+// Device helpers shared by every kernel family: transfer function, stimulus lookup, Philox noise.
+// Arithmetic follows the reference's operation order with explicit round-to-nearest intrinsics (no FMA
+// contraction) wherever the reference computes elementwise in fp32, so that the only differences to the
+// CPU path are the summation order of W.r and the last-ulp behaviour of tanhf/expf.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/odecol.h"
+
+namespace odecol {
+
+#define ODECOL_DEVINL __device__ __forceinline__
+
+struct Consts {
+    float tau_s, tau_m, tau_a, R;
+};
+
+// ---- phi and its derivative ---------------------------------------------------------------------------------
+// reference src/utils.py:13-28: x_nom = a x - b; z = 80 tanh(-d x_nom / 80); r = x_nom / (1 - exp(z)).
+ODECOL_DEVINL float phi(float x) {
+    const float x_nom = __fsub_rn(__fmul_rn(48.0f, x), 981.0f);
+    float z = __fmul_rn(-0.0089f, x_nom);
+    z = __fmul_rn(80.0f, tanhf(__fdiv_rn(z, 80.0f)));
+    const float den = __fsub_rn(1.0f, expf(z));
+    return __fdiv_rn(x_nom, den);
+}
+
+// r = phi(x) and dr/dx in one pass (what autograd assembles from the pieces above).
+ODECOL_DEVINL void phi_dphi(float x, float& r, float& dr) {
+    const float x_nom = __fsub_rn(__fmul_rn(48.0f, x), 981.0f);
+    const float z = __fmul_rn(-0.0089f, x_nom);
+    const float th = tanhf(__fdiv_rn(z, 80.0f));
+    const float e = expf(__fmul_rn(80.0f, th));
+    const float den = __fsub_rn(1.0f, e);
+    const float inv = __fdiv_rn(1.0f, den);
+    r = __fdiv_rn(x_nom, den);
+    // d r / d x_nom = 1/den + x_nom/den^2 * e * dz'/dx_nom,  dz'/dx_nom = (1 - th^2) * (-d)
+    const float dzp = (1.0f - th * th) * (-0.0089f);
+    dr = 48.0f * (inv + r * inv * e * dzp);
+}
+
+// ---- stimulus lookup (reference src/utils.py:31-46) ------------------------------------------------------------
+// Finds idx in [1, K-1] with searchsorted(right=True) semantics starting from a hint; returns clamped time.
+ODECOL_DEVINL float knot_locate(const float* __restrict__ kt, int K, float t, int& idx) {
+    const float tc = fminf(fmaxf(t, __ldg(kt)), __ldg(kt + K - 1));
+    int i = idx;
+    i = i < 1 ? 1 : (i > K - 1 ? K - 1 : i);
+    while (i > 1 && __ldg(kt + i - 1) > tc) --i;        // want kt[i-1] <= tc
+    while (i < K - 1 && __ldg(kt + i) <= tc) ++i;       // want kt[i] > tc (or i == K-1)
+    idx = i;
+    return tc;
+}
+
+ODECOL_DEVINL float knot_value(const float* __restrict__ kt, const float* __restrict__ ku_trial, int n_in,
+                               int idx, float tc, int c) {
+    const float x0 = __ldg(kt + idx - 1), x1 = __ldg(kt + idx);
+    const float y0 = __ldg(ku_trial + (size_t)(idx - 1) * n_in + c);
+    const float y1 = __ldg(ku_trial + (size_t)idx * n_in + c);
+    const float slope = __fdiv_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+    return __fadd_rn(y0, __fmul_rn(slope, __fsub_rn(tc, x0)));
+}
+
+// ---- elementwise drift given the total synaptic input ------------------------------------------------------------
+// total = (ff + bias + rec); reference: coupled_columns.py:225-233.
+ODECOL_DEVINL void drift(const Consts& c, float V, float A, float F, float r, float kappa, float total_raw,
+                         float& dV, float& dA, float& dF) {
+    const float total = __fmul_rn(total_raw, c.tau_s);
+    dV = __fdiv_rn(__fadd_rn(-V, __fmul_rn(total, c.R)), c.tau_m);
+    dA = __fdiv_rn(__fadd_rn(-A, __fmul_rn(kappa, r)), c.tau_a);
+    dF = __fdiv_rn(__fadd_rn(-F, r), c.tau_s);
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    ODECOL_DEVINL Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    ODECOL_DEVINL uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+// one standard normal from two 32-bit words (Box-Muller, u1 in (0,1])
+ODECOL_DEVINL float normal_from_bits(uint32_t a, uint32_t b) {
+    const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// Virtual Brownian tree: W(t) on [T0, T0 + span] for one trial, bisection to `depth` levels, linear inside
+// the leaf.  Deterministic in (seed, trial, t) so that W(a,c) = W(a,b) + W(b,c) under step rejection.
+constexpr int kBrownianDepth = 24;
+ODECOL_DEVINL float brownian_tree(const Philox& px, uint64_t trial, float T0, float span, float t) {
+    float a = T0, b = T0 + span;
+    float wa = 0.0f;
+    const uint4 root = px((uint32_t)trial, (uint32_t)(trial >> 32), 0xFFFFFFFFu, 0u);
+    float wb = sqrtf(span) * normal_from_bits(root.x, root.y);
+    uint32_t index = 0;
+    float width = span;
+#pragma unroll 1
+    for (int level = 0; level < kBrownianDepth; ++level) {
+        const float m = 0.5f * (a + b);
+        const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)level, index);
+        const float wm = 0.5f * (wa + wb) + 0.5f * sqrtf(width) * normal_from_bits(bits.x, bits.y);
+        index <<= 1;
+        if (t >= m) { a = m; wa = wm; index |= 1u; } else { b = m; wb = wm; }
+        width *= 0.5f;
+    }
+    const float w = (b > a) ? (t - a) / (b - a) : 0.0f;
+    return wa + fminf(fmaxf(w, 0.0f), 1.0f) * (wb - wa);
+}
+
+}  // namespace odecol
