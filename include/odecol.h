@@ -57,6 +57,12 @@ enum {
     ODECOL_ST_UNDERFLOW = 3    /* t + dt == t                                           */
 };
 
+/* odecol_problem.flags */
+enum {
+    ODECOL_FLAG_FORCE_STAGED = 1   /* use the staged (global-state) kernel family even when the problem
+                                      fits the persistent on-chip family; for testing and measurement   */
+};
+
 /* operations, for odecol_workspace_bytes() */
 enum {
     ODECOL_OP_RHS = 0,
@@ -80,7 +86,7 @@ typedef struct odecol_problem {
     int32_t B;            /* trials (independent solves; the reference loops over them)      */
     int32_t K;            /* stimulus knots per trial (>= 2)                                 */
     int32_t ld_w;         /* floats per row of W_aug, >= N + n_in + 1, multiple of 4         */
-    int32_t reserved0;
+    int32_t flags;        /* ODECOL_FLAG_* (0 = let the library pick the kernel family)              */
     const float* W_aug;   /* [N][ld_w]: columns [0,N) = W (row target, col source),
                              [N, N+n_in) = U, column N+n_in = bias, rest zero                */
     const float* kappa;   /* [N]                                                             */
@@ -95,8 +101,9 @@ typedef struct odecol_problem {
 int odecol_abi_version(void);
 const char* odecol_strerror(int code);
 
-/* Scratch requirement of `op` on this problem with T output times (bytes, 0 if none). */
-size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T);
+/* Scratch requirement of `op` on this problem with T output times (bytes, 0 if none).  n_steps is the number
+ * of Euler-Maruyama steps (odecol_em_num_steps) and is ignored by the other operations. */
+size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_t n_steps);
 
 /* f = forward(t, y) for a batch: t[B] (one time per trial), y[B][3N] -> f[B][3N].
  * Replaces ColumnAreaWTA.forward / ColumnNetworkXOR.forward / ColumnNetwork.forward
@@ -154,7 +161,7 @@ int64_t odecol_em_num_steps(const float* ts_host, int32_t T, float dt);
 
 /* Discrete adjoint of the fixed-step Euler-Maruyama solve (additive noise: dW does not enter the Jacobian).
  *   y_steps (n_steps+1, B, 3N) from odecol_em_fwd, grad_y (T, B, G) as in odecol_rk4_bwd. */
-int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps,
+int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
                   const float* grad_y, const int32_t* sel, int32_t G, float dt,
                   float* grad_y0, float* grad_W_aug,
                   void* workspace, size_t workspace_bytes, void* stream);

@@ -1,0 +1,26 @@
+"""odecol -- B200-native fused integrator for the ODE-Column hot path (package directory ``ode-column_b200``).
+
+Drop-in surface (reference src/coupled_columns.py, src/utils.py; torchdiffeq / torchsde call shapes):
+
+    ColumnArea, ColumnAreaWTA, ColumnNetworkXOR, ColumnNetwork, load_config,
+    compute_firing_rate, soft_clamp, torch_interp, min_max, fr_to_binary, huber_loss_wta,
+    odeint, odeint_adjoint, sdeint
+
+The solvers run only on CUDA through the C ABI in ``include/odecol.h``; importing the package does not need a GPU.
+"""
+from .model import (ColumnArea, ColumnAreaWTA, ColumnNetwork, ColumnNetworkXOR, LinearForm, compute_firing_rate,
+                    load_config, pack_w_aug, soft_clamp, torch_interp)
+from .losses import fr_to_binary, huber_loss_wta, min_max, parity_readout, xor_readout
+from .solvers import odeint, odeint_adjoint, sdeint
+from .stimulus import compress_knots, step_knots
+from .synthetic import SyntheticColumnSheet
+from . import distributed
+from . import _native
+
+__all__ = [
+    "ColumnArea", "ColumnAreaWTA", "ColumnNetwork", "ColumnNetworkXOR", "SyntheticColumnSheet", "LinearForm",
+    "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug",
+    "min_max", "fr_to_binary", "huber_loss_wta", "xor_readout", "parity_readout",
+    "odeint", "odeint_adjoint", "sdeint", "compress_knots", "step_knots", "distributed",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,203 @@
+// C-ABI shim (include/odecol.h): validates arguments, picks the kernel family, launches on the caller's stream.
+// No allocation, no synchronisation, no global mutable state (the launch counter is thread local).
+#include <cstring>
+#include <cmath>
+#include "odecol_internal.h"
+
+namespace odecol {
+
+static thread_local int64_t g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+
+static int to_dev(const odecol_problem* p, DevProblem& d) {
+    if (!p || !p->W_aug || !p->kappa || !p->knot_t || !p->knot_u) return ODECOL_E_NULL;
+    if (p->N <= 0 || p->B <= 0 || p->n_in < 0 || p->K < 2) return ODECOL_E_SHAPE;
+    if (p->ld_w < p->N + p->n_in + 1 || (p->ld_w & 3)) return ODECOL_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(p->W_aug) & 15) || (reinterpret_cast<uintptr_t>(p->kappa) & 15)) return ODECOL_E_ALIGN;
+    d.N = p->N; d.n_in = p->n_in; d.B = p->B; d.K = p->K; d.ld_w = p->ld_w;
+    d.W_aug = p->W_aug; d.kappa = p->kappa; d.sigma = p->sigma; d.knot_t = p->knot_t; d.knot_u = p->knot_u;
+    d.knot_stride_b = p->knot_stride_b;
+    d.c.tau_s = p->tau_s; d.c.tau_m = p->tau_m; d.c.tau_a = p->tau_a; d.c.R = p->resistance;
+    return ODECOL_OK;
+}
+
+static bool use_small(const odecol_problem* p, const DevProblem& d) {
+    return !(p->flags & ODECOL_FLAG_FORCE_STAGED) && small_kp(d) != 0;
+}
+
+static inline bool misaligned(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) != 0; }
+
+struct EmScheduleLayout { size_t off_step, off_w, off_tk, total; };
+static EmScheduleLayout em_schedule_layout(int T, int64_t n_steps) {
+    EmScheduleLayout L;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    L.off_step = 0;
+    L.off_w = up(sizeof(int) * (size_t)(T + 1));
+    L.off_tk = L.off_w + up(sizeof(float) * 2 * (size_t)T);
+    L.total = L.off_tk + up(sizeof(float) * (size_t)(n_steps + 1));
+    return L;
+}
+
+}  // namespace odecol
+
+using namespace odecol;
+
+extern "C" {
+
+int odecol_abi_version(void) { return ODECOL_ABI_VERSION; }
+
+const char* odecol_strerror(int code) {
+    switch (code) {
+        case ODECOL_OK: return "ok";
+        case ODECOL_E_NULL: return "required pointer is NULL";
+        case ODECOL_E_SHAPE: return "N, B, T, K, n_in or ld_w out of range";
+        case ODECOL_E_UNSUPPORTED: return "no kernel for this request";
+        case ODECOL_E_WORKSPACE: return "workspace missing or too small";
+        case ODECOL_E_CUDA: return "CUDA launch failed";
+        case ODECOL_E_ALIGN: return "pointer not 16-byte aligned";
+        default: return "unknown odecol error";
+    }
+}
+
+int64_t odecol_last_launch_count(void) { return g_launches; }
+
+int odecol_kernel_family(const odecol_problem* p, int op) {
+    DevProblem d;
+    if (to_dev(p, d) != ODECOL_OK) return -1;
+    (void)op;
+    return use_small(p, d) ? 0 : 1;
+}
+
+size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_t n_steps) {
+    DevProblem d;
+    if (to_dev(p, d) != ODECOL_OK) return 0;
+    const bool small = use_small(p, d);
+    switch (op) {
+        case ODECOL_OP_RK4_FWD: return small ? 0 : stage_rk4_fwd_workspace_bytes(d, T);
+        case ODECOL_OP_RK4_BWD: return small ? 0 : stage_rk4_bwd_workspace_bytes(d, T);
+        case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
+        case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
+        default: return 0;
+    }
+}
+
+int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y || !f) return ODECOL_E_NULL;
+    g_launches = 0;
+    return launch_rhs_generic(d, t, y, f, static_cast<cudaStream_t>(stream));
+}
+
+int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
+                   int32_t out_every, void* workspace, size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y0 || !y_out) return ODECOL_E_NULL;
+    if (T < 2 || out_every < 1) return ODECOL_E_SHAPE;
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_small(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
+    if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
+    return stage_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
+}
+
+int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const float* y_traj, const float* grad_y,
+                   const int32_t* sel, int32_t G, float* grad_y0, float* grad_W_aug, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y_traj || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
+    if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (use_small(p, d)) return launch_rk4_bwd_small(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, s);
+    if (misaligned(y_traj) || misaligned(workspace) || misaligned(grad_W_aug)) return ODECOL_E_ALIGN;
+    return stage_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
+}
+
+int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out, float rtol,
+                      float atol, int32_t max_steps, int32_t* n_accept, int32_t* n_reject, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y0 || !y_out) return ODECOL_E_NULL;
+    if (T < 2 || max_steps < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
+    g_launches = 0;
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;   // per-trial dopri5 exists in the on-chip family only
+    return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int64_t odecol_em_num_steps(const float* ts, int32_t T, float dt) {
+    if (!ts || T < 2 || !(dt > 0.f)) return -1;
+    // the float32 loop of torchsde's integrate(): curr_t += dt, clipped to ts[T-1]
+    volatile float curr = ts[0];
+    const float t_end = ts[T - 1];
+    int64_t k = 0;
+    for (int j = 1; j < T; ++j) {
+        const float out_t = ts[j];
+        while (curr < out_t) {
+            volatile float nxt = curr + dt;
+            curr = nxt < t_end ? nxt : t_end;
+            ++k;
+            if (k > (int64_t)1 << 40) return -1;
+        }
+    }
+    return k;
+}
+
+int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out, const float* dW,
+                  uint64_t seed, int64_t trial_offset, float dt, int32_t adaptive, float rtol, float atol,
+                  float dt_min, int32_t* n_accept, int32_t* n_reject, int32_t* status, float* y_steps,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
+    if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
+    if (adaptive && (dW || y_steps || !(dt_min > 0.f))) return ODECOL_E_UNSUPPORTED;
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_small(p, d)) {
+        // attempts are bounded: a step at dt_min is always accepted
+        const long long cap = adaptive ? (1LL << 34) : (1LL << 40);
+        return launch_em_fwd_small(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min,
+                                   n_accept, n_reject, status, y_steps, cap, s);
+    }
+    if (y_steps) return ODECOL_E_UNSUPPORTED;
+    if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
+    return stage_em_fwd(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min, n_accept, n_reject,
+                        status, workspace, workspace_bytes, s);
+}
+
+int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
+                  const float* grad_y, const int32_t* sel, int32_t G, float dt, float* grad_y0, float* grad_W_aug,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
+    if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    const EmScheduleLayout L = em_schedule_layout(T, n_steps);
+    if (!workspace || workspace_bytes < L.total) return ODECOL_E_WORKSPACE;
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    int* step_of = reinterpret_cast<int*>(w + L.off_step);
+    float* wts = reinterpret_cast<float*>(w + L.off_w);
+    float* tk = reinterpret_cast<float*>(w + L.off_tk);
+    if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+    int r2 = launch_em_schedule(ts, T, dt, step_of, wts, tk, s);
+    if (r2) return r2;
+    return launch_em_bwd_small(d, ts, T, y_steps, grad_y, sel, G, grad_y0, grad_W_aug, step_of, wts, tk, s);
+}
+
+}  // extern "C"

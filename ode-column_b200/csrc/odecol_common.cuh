@@ -5,15 +5,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "../../include/odecol.h"
+#include "odecol_internal.h"
 
 namespace odecol {
 
 #define ODECOL_DEVINL __device__ __forceinline__
-
-struct Consts {
-    float tau_s, tau_m, tau_a, R;
-};
 
 // ---- phi and its derivative ---------------------------------------------------------------------------------
 // reference src/utils.py:13-28: x_nom = a x - b; z = 80 tanh(-d x_nom / 80); r = x_nom / (1 - exp(z)).
@@ -95,27 +91,51 @@ ODECOL_DEVINL float normal_from_bits(uint32_t a, uint32_t b) {
     return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
-// Virtual Brownian tree: W(t) on [T0, T0 + span] for one trial, bisection to `depth` levels, linear inside
-// the leaf.  Deterministic in (seed, trial, t) so that W(a,c) = W(a,b) + W(b,c) under step rejection.
+// Virtual Brownian tree: W(t) on [T0, T0 + span] for one trial.  The query time is quantised to
+// q / 2^24 of the span (integer path, so every kernel family walks the same nodes), bisection over 24 levels
+// with Brownian-bridge midpoints, linear inside the leaf.  Deterministic in (seed, trial, t), hence
+// W(a,c) = W(a,b) + W(b,c) under step rejection and results do not depend on sharding or kernel family.
 constexpr int kBrownianDepth = 24;
-ODECOL_DEVINL float brownian_tree(const Philox& px, uint64_t trial, float T0, float span, float t) {
-    float a = T0, b = T0 + span;
-    float wa = 0.0f;
-    const uint4 root = px((uint32_t)trial, (uint32_t)(trial >> 32), 0xFFFFFFFFu, 0u);
-    float wb = sqrtf(span) * normal_from_bits(root.x, root.y);
-    uint32_t index = 0;
-    float width = span;
+constexpr uint32_t kBrownianRootLevel = 0xFFFFFFFFu;
+
+ODECOL_DEVINL void brownian_path(float T0, float span, float t, uint32_t& q, float& frac) {
+    float u = (t - T0) / span;
+    u = fminf(fmaxf(u, 0.0f), 1.0f) * 16777216.0f;
+    float fl = floorf(u);
+    if (fl > 16777215.0f) fl = 16777215.0f;
+    q = (uint32_t)fl;
+    frac = fminf(u - fl, 1.0f);
+}
+
+// normal deviate of tree node (level, index-within-level); level == kBrownianRootLevel is W(T0+span)/sqrt(span)
+ODECOL_DEVINL float brownian_node(const Philox& px, uint64_t trial, uint32_t level, uint32_t index) {
+    const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), level, index);
+    return normal_from_bits(bits.x, bits.y);
+}
+
+// combine: z[l] is the deviate of the node visited at level l, zroot the root deviate
+template <typename ZF>
+ODECOL_DEVINL float brownian_combine(float span, uint32_t q, float frac, float zroot, ZF z) {
+    float wa = 0.0f, wb = sqrtf(span) * zroot;
+    float half_sd = 0.5f * sqrtf(span);            // 0.5*sqrt(width), width halves per level
 #pragma unroll 1
     for (int level = 0; level < kBrownianDepth; ++level) {
-        const float m = 0.5f * (a + b);
-        const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)level, index);
-        const float wm = 0.5f * (wa + wb) + 0.5f * sqrtf(width) * normal_from_bits(bits.x, bits.y);
-        index <<= 1;
-        if (t >= m) { a = m; wa = wm; index |= 1u; } else { b = m; wb = wm; }
-        width *= 0.5f;
+        const float wm = 0.5f * (wa + wb) + half_sd * z(level);
+        if ((q >> (kBrownianDepth - 1 - level)) & 1u) wa = wm; else wb = wm;
+        half_sd *= 0.70710678118654752f;
     }
-    const float w = (b > a) ? (t - a) / (b - a) : 0.0f;
-    return wa + fminf(fmaxf(w, 0.0f), 1.0f) * (wb - wa);
+    return wa + frac * (wb - wa);
+}
+
+// sequential version (one thread per trial)
+ODECOL_DEVINL float brownian_tree(const Philox& px, uint64_t trial, float T0, float span, float t) {
+    uint32_t q; float frac;
+    brownian_path(T0, span, t, q, frac);
+    const float zroot = brownian_node(px, trial, kBrownianRootLevel, 0u);
+    return brownian_combine(span, q, frac, zroot, [&](int level) {
+        const uint32_t index = level == 0 ? 0u : (q >> (kBrownianDepth - level));
+        return brownian_node(px, trial, (uint32_t)level, index);
+    });
 }
 
 }  // namespace odecol

@@ -1,0 +1,62 @@
+// Internal declarations shared by the kernel translation units and the C-ABI shim.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/odecol.h"
+
+namespace odecol {
+
+struct Consts {
+    float tau_s, tau_m, tau_a, R;
+};
+
+// device-side copy of odecol_problem (passed by value to kernels)
+struct DevProblem {
+    int N, n_in, B, K, ld_w;
+    const float* W_aug;
+    const float* kappa;
+    const float* sigma;
+    const float* knot_t;
+    const float* knot_u;
+    long long knot_stride_b;
+    Consts c;
+};
+
+// thread-local launch counter (odecol_last_launch_count)
+void count_launch(int n = 1);
+
+// ---- family S (small_kernels.cu) ---------------------------------------------------------------------------
+int small_kp(const DevProblem& p);                 // 0 if the problem does not fit family S
+size_t small_bwd_smem_bytes(int N, int KP);
+int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, float* f, cudaStream_t s);
+int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
+                         cudaStream_t s);
+int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float* y_traj, const float* grad_y,
+                         const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s);
+int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, float rtol,
+                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, cudaStream_t s);
+int launch_em_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
+                        uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol,
+                        float dt_min, int* n_accept, int* n_reject, int* status, float* y_steps,
+                        long long max_attempts, cudaStream_t s);
+// schedule: step_of[T+1] (last entry = n_steps), w[2T], tk[n_steps+1]
+int launch_em_schedule(const float* ts, int T, float dt, int* step_of, float* w, float* tk, cudaStream_t s);
+int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float* y_steps, const float* grad_y,
+                        const int* sel, int G, float* grad_y0, float* grad_W, const int* step_of, const float* w,
+                        const float* tk, cudaStream_t s);
+
+// ---- family L (stage_kernels.cu): state in global memory, one fused contraction + epilogue per RK stage ------
+struct StageWorkspace;   // carved from the caller's workspace
+size_t stage_rk4_fwd_workspace_bytes(const DevProblem& p, int T);
+size_t stage_rk4_bwd_workspace_bytes(const DevProblem& p, int T);
+size_t stage_em_fwd_workspace_bytes(const DevProblem& p, int T);
+int stage_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
+                  void* ws, size_t ws_bytes, cudaStream_t s);
+int stage_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y,
+                  const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
+int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                 uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
+                 int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
+
+}  // namespace odecol

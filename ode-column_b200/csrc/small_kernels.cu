@@ -1,0 +1,851 @@
+// Kernel family S ("small"): one persistent CTA integrates ONE trial through the whole time loop.
+//
+//   * thread i owns population i: V_i, A_i, F_i and every Runge-Kutta stage value live in registers;
+//   * row i of W_aug = [W | U | bias] lives in registers too (KP floats, compile-time padded), so the
+//     recurrent + feedforward + background input is one fully unrolled FFMA dot product against the
+//     trial's r_aug = [phi(V-A) ; s(t) ; 1] vector, which is exchanged through (double-buffered) shared
+//     memory with ONE barrier per right-hand-side evaluation;
+//   * adaptive solvers (dopri5, step-doubling Euler-Maruyama) take their accept/reject decision per trial
+//     from a warp-shuffle + shared-memory reduction, exactly like the reference, which solves trials
+//     one at a time (scripts/xor_ode.py:104-117);
+//   * many such CTAs share an SM (32..128 threads each), trials never communicate.
+//
+// Used when N <= 128 and N + n_in + 1 <= 128 (the reference's WTA / XOR / parity networks).
+// Replaces the Python stepping loops of torchdiffeq / torchsde around ColumnArea*.forward
+// (reference src/coupled_columns.py:204-237, 407-442, 753-788).
+#include "odecol_common.cuh"
+
+namespace odecol {
+
+constexpr float kOneThird = 0.3333333333333333f;   // float32(1/3), as torch scalar math
+constexpr float kTwoThirds = 0.6666666666666666f;
+
+// ---------------------------------------------------------------------------------------------------------------
+// block reductions (all threads return the same value)
+// ---------------------------------------------------------------------------------------------------------------
+ODECOL_DEVINL double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int nw = blockDim.x >> 5;
+    if (nw == 1) return v;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+ODECOL_DEVINL bool block_any(bool flag) { return __syncthreads_or(flag ? 1 : 0) != 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-thread right-hand side with the weight row in registers
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+struct RowRhs {
+    float w[KP];
+    float kappa;
+    float* ra;            // shared [2][KP]
+    const float* ku;      // this trial's knots
+    int idx, buf;
+    int N, n_in, K;
+    const float* kt;
+    Consts c;
+    bool act;
+
+    ODECOL_DEVINL void init(const DevProblem& p, float* ra_smem, int b) {
+        const int i = threadIdx.x;
+        N = p.N; n_in = p.n_in; K = p.K; kt = p.knot_t; c = p.c;
+        act = i < N;
+        ra = ra_smem;
+        ku = p.knot_u + (size_t)b * p.knot_stride_b;
+        idx = 1; buf = 0;
+        const int Kaug = p.N + p.n_in + 1;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) w[k] = (act && k < Kaug) ? __ldg(p.W_aug + (size_t)i * p.ld_w + k) : 0.0f;
+        kappa = act ? __ldg(p.kappa + i) : 0.0f;
+        for (int k = i; k < 2 * KP; k += blockDim.x) ra[k] = 0.0f;
+        __syncthreads();
+        if (i == 0) { ra[Kaug - 1] = 1.0f; ra[KP + Kaug - 1] = 1.0f; }
+        __syncthreads();
+    }
+
+    // publishes r_aug(t, V-A) and returns the total synaptic input of population i; one barrier
+    ODECOL_DEVINL float input(float t, float r) {
+        buf ^= 1;
+        float* cur = ra + buf * KP;
+        if (act) cur[threadIdx.x] = r;
+        if ((int)threadIdx.x < n_in) {
+            const float tc = knot_locate(kt, K, t, idx);
+            for (int ch = threadIdx.x; ch < n_in; ch += blockDim.x) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+        }
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float4* r4 = reinterpret_cast<const float4*>(cur);
+#pragma unroll
+        for (int k = 0; k < KP / 4; ++k) {
+            const float4 v = r4[k];
+            a0 = fmaf(w[4 * k + 0], v.x, a0);
+            a1 = fmaf(w[4 * k + 1], v.y, a1);
+            a2 = fmaf(w[4 * k + 2], v.z, a2);
+            a3 = fmaf(w[4 * k + 3], v.w, a3);
+        }
+        return (a0 + a1) + (a2 + a3);
+    }
+
+    ODECOL_DEVINL void eval(float t, float V, float A, float F, float& dV, float& dA, float& dF) {
+        const float r = phi(__fsub_rn(V, A));
+        const float tot = input(t, r);
+        drift(c, V, A, F, r, kappa, tot, dV, dA, dF);
+    }
+};
+
+struct Y3 { float V, A, F; };
+ODECOL_DEVINL Y3 ld3(const float* base, int N, int i) { return {base[i], base[N + i], base[2 * N + i]}; }
+ODECOL_DEVINL void st3(float* base, int N, int i, float V, float A, float F) { base[i] = V; base[N + i] = A; base[2 * N + i] = F; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// single RHS evaluation (module.forward parity); generic in N: CTA per trial, r_aug in dynamic smem
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_rhs_generic(DevProblem p, const float* __restrict__ t, const float* __restrict__ y,
+                              float* __restrict__ f) {
+    extern __shared__ float ra[];
+    const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
+    const float* yb = y + (size_t)b * 3 * N;
+    const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
+    const float tb = t[b];
+    int idx = 1;
+    const float tc = knot_locate(p.knot_t, p.K, tb, idx);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ra[i] = phi(__fsub_rn(yb[i], yb[N + i]));
+    for (int ch = threadIdx.x; ch < p.n_in; ch += blockDim.x) ra[N + ch] = knot_value(p.knot_t, ku, p.n_in, idx, tc, ch);
+    if (threadIdx.x == 0) ra[Kaug - 1] = 1.0f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float* wr = p.W_aug + (size_t)i * p.ld_w;
+        float acc = 0.f;
+        for (int k = 0; k < Kaug; ++k) acc = fmaf(__ldg(wr + k), ra[k], acc);
+        float dV, dA, dF;
+        drift(p.c, yb[i], yb[N + i], yb[2 * N + i], ra[i], __ldg(p.kappa + i), acc, dV, dA, dF);
+        st3(f + (size_t)b * 3 * N, N, i, dV, dA, dF);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RK4 (3/8 rule) forward
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) k_rk4_fwd_small(DevProblem p, const float* __restrict__ t, int T,
+                                                       const float* __restrict__ y0, float* __restrict__ y_out,
+                                                       int out_every) {
+    __shared__ __align__(16) float ra[2 * KP];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N;
+    RowRhs<KP> f;
+    f.init(p, ra, b);
+    const size_t row = (size_t)3 * N;
+    float V = 0.f, A = 0.f, F = 0.f;
+    if (f.act) {
+        const Y3 s = ld3(y0 + b * row, N, i);
+        V = s.V; A = s.A; F = s.F;
+        st3(y_out + b * row, N, i, V, A, F);
+    }
+    for (int n = 0; n < T - 1; ++n) {
+        const float t0 = __ldg(t + n), t1 = __ldg(t + n + 1);
+        const float dt = __fsub_rn(t1, t0);
+        float k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F, k4V, k4A, k4F;
+        f.eval(t0, V, A, F, k1V, k1A, k1F);
+        // Y2 = y0 + dt*k1*(1/3)
+        f.eval(__fadd_rn(t0, __fmul_rn(dt, kOneThird)),
+               __fadd_rn(V, __fmul_rn(__fmul_rn(dt, k1V), kOneThird)),
+               __fadd_rn(A, __fmul_rn(__fmul_rn(dt, k1A), kOneThird)),
+               __fadd_rn(F, __fmul_rn(__fmul_rn(dt, k1F), kOneThird)), k2V, k2A, k2F);
+        // Y3 = y0 + dt*(k2 - k1*(1/3))
+        f.eval(__fadd_rn(t0, __fmul_rn(dt, kTwoThirds)),
+               __fadd_rn(V, __fmul_rn(dt, __fsub_rn(k2V, __fmul_rn(k1V, kOneThird)))),
+               __fadd_rn(A, __fmul_rn(dt, __fsub_rn(k2A, __fmul_rn(k1A, kOneThird)))),
+               __fadd_rn(F, __fmul_rn(dt, __fsub_rn(k2F, __fmul_rn(k1F, kOneThird)))), k3V, k3A, k3F);
+        // Y4 = y0 + dt*(k1 - k2 + k3)
+        f.eval(t1,
+               __fadd_rn(V, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V, k2V), k3V))),
+               __fadd_rn(A, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A, k2A), k3A))),
+               __fadd_rn(F, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1F, k2F), k3F))), k4V, k4A, k4F);
+        // y1 = y0 + (k1 + 3*(k2+k3) + k4)*dt*0.125
+        V = __fadd_rn(V, __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1V, __fmul_rn(3.f, __fadd_rn(k2V, k3V))), k4V), dt), 0.125f));
+        A = __fadd_rn(A, __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1A, __fmul_rn(3.f, __fadd_rn(k2A, k3A))), k4A), dt), 0.125f));
+        F = __fadd_rn(F, __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F, __fmul_rn(3.f, __fadd_rn(k2F, k3F))), k4F), dt), 0.125f));
+        const int j = n + 1;
+        if (f.act && (j % out_every == 0 || j == T - 1)) {
+            const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
+            st3(y_out + (r * p.B + b) * row, N, i, V, A, F);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RK4 discrete adjoint (reverse sweep over the saved trajectory; stages recomputed per step)
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+struct BwdShared {
+    float* Ws;     // [N][KP+1]   padded rows: row access (thread = row) and column access (thread = col) conflict free
+    float* ra;     // [4][KP]     r_aug of the four stages
+    float* av;     // [2][NP]
+    int* inv;      // [3N]        state component -> column of grad_y, or -1
+};
+
+template <int KP>
+ODECOL_DEVINL BwdShared<KP> carve_bwd(float* sm, int N, int NP) {
+    BwdShared<KP> s;
+    s.ra = sm;                                   // 16-byte aligned
+    s.av = s.ra + 4 * KP;
+    s.Ws = s.av + 2 * NP;
+    s.inv = reinterpret_cast<int*>(s.Ws + (size_t)N * (KP + 1));
+    return s;
+}
+
+size_t small_bwd_smem_bytes(int N, int KP) {
+    const int NP = (N + 31) / 32 * 32;
+    return sizeof(float) * ((size_t)4 * KP + 2 * NP + (size_t)N * (KP + 1) + 3 * N);
+}
+
+template <int KP>
+struct BwdCtx {
+    BwdShared<KP> s;
+    float dw[KP];
+    float kappa, gamma, inv_tau_m, inv_tau_a, inv_tau_s;
+    const float* ku;
+    const float* kt;
+    int idx, abuf, N, n_in, K, NP;
+    Consts c;
+    bool act;
+
+    ODECOL_DEVINL void init(const DevProblem& p, float* sm, int b) {
+        const int i = threadIdx.x;
+        N = p.N; n_in = p.n_in; K = p.K; kt = p.knot_t; c = p.c;
+        NP = blockDim.x;
+        act = i < N;
+        s = carve_bwd<KP>(sm, N, NP);
+        ku = p.knot_u + (size_t)b * p.knot_stride_b;
+        idx = 1; abuf = 0;
+        const int Kaug = N + n_in + 1;
+        for (int e = i; e < N * KP; e += blockDim.x) {
+            const int r = e / KP, k = e % KP;
+            s.Ws[r * (KP + 1) + k] = k < Kaug ? __ldg(p.W_aug + (size_t)r * p.ld_w + k) : 0.0f;
+        }
+        for (int e = i; e < 4 * KP; e += blockDim.x) s.ra[e] = (e % KP == Kaug - 1) ? 1.0f : 0.0f;
+        for (int e = i; e < 2 * NP; e += blockDim.x) s.av[e] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) dw[k] = 0.0f;
+        kappa = act ? __ldg(p.kappa + i) : 0.0f;
+        gamma = c.tau_s * c.R / c.tau_m;
+        inv_tau_m = 1.0f / c.tau_m; inv_tau_a = 1.0f / c.tau_a; inv_tau_s = 1.0f / c.tau_s;
+        __syncthreads();
+    }
+
+    // forward stage: publishes r_aug into ra[stage], returns total input (needs_dot) ; r, dr out
+    ODECOL_DEVINL float stage_fwd(int stage, float t, float V, float A, float& r, float& dr, bool needs_dot) {
+        phi_dphi(__fsub_rn(V, A), r, dr);
+        float* cur = s.ra + stage * KP;
+        if (act) cur[threadIdx.x] = r;
+        if ((int)threadIdx.x < n_in) {
+            const float tc = knot_locate(kt, K, t, idx);
+            for (int ch = threadIdx.x; ch < n_in; ch += blockDim.x) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+        }
+        __syncthreads();
+        float acc = 0.f;
+        if (needs_dot && act) {
+            const float* wr = s.Ws + threadIdx.x * (KP + 1);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < KP; k += 2) { a0 = fmaf(wr[k], cur[k], a0); a1 = fmaf(wr[k + 1], cur[k + 1], a1); }
+            acc = a0 + a1;
+        }
+        return acc;
+    }
+
+    // (Yb) = J(stage)^T (aV, aA, aF);  accumulates dW_aug row
+    ODECOL_DEVINL void stage_bwd(int stage, float dr, float aV, float aA, float aF, float& bV, float& bA, float& bF) {
+        abuf ^= 1;
+        float* a = s.av + abuf * NP;
+        const float ga = gamma * aV;
+        a[threadIdx.x] = act ? ga : 0.0f;
+        __syncthreads();
+        float g = 0.f;
+        if (act) {
+            const float* wc = s.Ws + threadIdx.x;
+            float g0 = 0.f, g1 = 0.f;
+            int r = 0;
+            for (; r + 1 < N; r += 2) { g0 = fmaf(wc[r * (KP + 1)], a[r], g0); g1 = fmaf(wc[(r + 1) * (KP + 1)], a[r + 1], g1); }
+            if (r < N) g0 = fmaf(wc[r * (KP + 1)], a[r], g0);
+            g = g0 + g1 + kappa * aA * inv_tau_a + aF * inv_tau_s;
+        }
+        const float4* r4 = reinterpret_cast<const float4*>(s.ra + stage * KP);
+#pragma unroll
+        for (int k = 0; k < KP / 4; ++k) {
+            const float4 v = r4[k];
+            dw[4 * k + 0] = fmaf(ga, v.x, dw[4 * k + 0]);
+            dw[4 * k + 1] = fmaf(ga, v.y, dw[4 * k + 1]);
+            dw[4 * k + 2] = fmaf(ga, v.z, dw[4 * k + 2]);
+            dw[4 * k + 3] = fmaf(ga, v.w, dw[4 * k + 3]);
+        }
+        bV = -aV * inv_tau_m + dr * g;
+        bA = -aA * inv_tau_a - dr * g;
+        bF = -aF * inv_tau_s;
+    }
+
+    ODECOL_DEVINL void flush_dw(const DevProblem& p, float* grad_W) {
+        if (!act) return;
+        const int Kaug = N + n_in + 1;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < Kaug) atomicAdd(grad_W + (size_t)threadIdx.x * p.ld_w + k, dw[k]);
+    }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
+                                                       const float* __restrict__ y_traj,
+                                                       const float* __restrict__ grad_y, const int* __restrict__ sel,
+                                                       int G, float* __restrict__ grad_y0, float* __restrict__ grad_W) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    BwdCtx<KP> cx;
+    cx.init(p, sm, b);
+    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    __syncthreads();
+    const int gV = cx.act ? cx.s.inv[i] : -1, gA = cx.act ? cx.s.inv[N + i] : -1, gF = cx.act ? cx.s.inv[2 * N + i] : -1;
+    const size_t row = (size_t)3 * N;
+    auto add_grad = [&](int n, float& lV, float& lA, float& lF) {
+        const float* g = grad_y + ((size_t)n * B + b) * G;
+        if (gV >= 0) lV += g[gV];
+        if (gA >= 0) lA += g[gA];
+        if (gF >= 0) lF += g[gF];
+    };
+    float lV = 0.f, lA = 0.f, lF = 0.f;
+    add_grad(T - 1, lV, lA, lF);
+    for (int n = T - 2; n >= 0; --n) {
+        const float t0 = __ldg(t + n), t1 = __ldg(t + n + 1);
+        const float dt = __fsub_rn(t1, t0);
+        float V = 0.f, A = 0.f, F = 0.f;
+        if (cx.act) { const Y3 s = ld3(y_traj + ((size_t)n * B + b) * row, N, i); V = s.V; A = s.A; F = s.F; }
+        // ---- recompute the stages (same arithmetic as the forward kernel)
+        float r, d1, d2, d3, d4, tot, k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+        tot = cx.stage_fwd(0, t0, V, A, r, d1, true);
+        drift(cx.c, V, A, F, r, cx.kappa, tot, k1V, k1A, k1F);
+        float sV = __fadd_rn(V, __fmul_rn(__fmul_rn(dt, k1V), kOneThird));
+        float sA = __fadd_rn(A, __fmul_rn(__fmul_rn(dt, k1A), kOneThird));
+        float sF = __fadd_rn(F, __fmul_rn(__fmul_rn(dt, k1F), kOneThird));
+        tot = cx.stage_fwd(1, __fadd_rn(t0, __fmul_rn(dt, kOneThird)), sV, sA, r, d2, true);
+        drift(cx.c, sV, sA, sF, r, cx.kappa, tot, k2V, k2A, k2F);
+        sV = __fadd_rn(V, __fmul_rn(dt, __fsub_rn(k2V, __fmul_rn(k1V, kOneThird))));
+        sA = __fadd_rn(A, __fmul_rn(dt, __fsub_rn(k2A, __fmul_rn(k1A, kOneThird))));
+        sF = __fadd_rn(F, __fmul_rn(dt, __fsub_rn(k2F, __fmul_rn(k1F, kOneThird))));
+        tot = cx.stage_fwd(2, __fadd_rn(t0, __fmul_rn(dt, kTwoThirds)), sV, sA, r, d3, true);
+        drift(cx.c, sV, sA, sF, r, cx.kappa, tot, k3V, k3A, k3F);
+        sV = __fadd_rn(V, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V, k2V), k3V)));
+        sA = __fadd_rn(A, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A, k2A), k3A)));
+        (void)cx.stage_fwd(3, t1, sV, sA, r, d4, false);
+        // ---- reverse sweep.  y1 = y0 + dt/8 (k1 + 3k2 + 3k3 + k4)
+        const float h8 = dt * 0.125f, h38 = 3.0f * h8, h3 = dt * kOneThird;
+        float b4V, b4A, b4F, b3V, b3A, b3F, b2V, b2A, b2F, b1V, b1A, b1F;
+        cx.stage_bwd(3, d4, h8 * lV, h8 * lA, h8 * lF, b4V, b4A, b4F);
+        cx.stage_bwd(2, d3, h38 * lV + dt * b4V, h38 * lA + dt * b4A, h38 * lF + dt * b4F, b3V, b3A, b3F);
+        cx.stage_bwd(1, d2, h38 * lV - dt * b4V + dt * b3V, h38 * lA - dt * b4A + dt * b3A,
+                     h38 * lF - dt * b4F + dt * b3F, b2V, b2A, b2F);
+        cx.stage_bwd(0, d1, h8 * lV + dt * b4V - h3 * b3V + h3 * b2V, h8 * lA + dt * b4A - h3 * b3A + h3 * b2A,
+                     h8 * lF + dt * b4F - h3 * b3F + h3 * b2F, b1V, b1A, b1F);
+        lV += b4V + b3V + b2V + b1V;
+        lA += b4A + b3A + b2A + b1A;
+        lF += b4F + b3F + b2F + b1F;
+        add_grad(n, lV, lA, lF);
+        __syncthreads();    // ra[] of this step fully consumed before the next step overwrites it
+    }
+    if (grad_y0 && cx.act) st3(grad_y0 + b * row, N, i, lV, lA, lF);
+    cx.flush_dw(p, grad_W);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dopri5 forward with per-trial control and dense output
+// ---------------------------------------------------------------------------------------------------------------
+struct DP {
+    // float32(coefficient), as torchdiffeq casts its float64 tableau to y0.dtype
+    static constexpr float a1 = (float)(1.0 / 5), a2 = (float)(3.0 / 10), a3 = (float)(4.0 / 5), a4 = (float)(8.0 / 9);
+    static constexpr float b10 = (float)(1.0 / 5);
+    static constexpr float b20 = (float)(3.0 / 40), b21 = (float)(9.0 / 40);
+    static constexpr float b30 = (float)(44.0 / 45), b31 = (float)(-56.0 / 15), b32 = (float)(32.0 / 9);
+    static constexpr float b40 = (float)(19372.0 / 6561), b41 = (float)(-25360.0 / 2187), b42 = (float)(64448.0 / 6561),
+                           b43 = (float)(-212.0 / 729);
+    static constexpr float b50 = (float)(9017.0 / 3168), b51 = (float)(-355.0 / 33), b52 = (float)(46732.0 / 5247),
+                           b53 = (float)(49.0 / 176), b54 = (float)(-5103.0 / 18656);
+    static constexpr float b60 = (float)(35.0 / 384), b62 = (float)(500.0 / 1113), b63 = (float)(125.0 / 192),
+                           b64 = (float)(-2187.0 / 6784), b65 = (float)(11.0 / 84);
+    static constexpr float e0 = (float)(35.0 / 384 - 1951.0 / 21600), e2 = (float)(500.0 / 1113 - 22642.0 / 50085),
+                           e3 = (float)(125.0 / 192 - 451.0 / 720), e4 = (float)(-2187.0 / 6784 + 12231.0 / 42400),
+                           e5 = (float)(11.0 / 84 - 649.0 / 6300), e6 = (float)(-1.0 / 60);
+    static constexpr float m0 = (float)(6025192743.0 / 30085553152.0 / 2), m2 = (float)(51252292925.0 / 65400821598.0 / 2),
+                           m3 = (float)(-2691868925.0 / 45128329728.0 / 2), m4 = (float)(187940372067.0 / 1594534317056.0 / 2),
+                           m5 = (float)(-1776094331.0 / 19743644256.0 / 2), m6 = (float)(11237099.0 / 235043384.0 / 2);
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128) k_dopri5_fwd_small(DevProblem p, const float* __restrict__ t, int T,
+                                                          const float* __restrict__ y0, float* __restrict__ y_out,
+                                                          float rtol, float atol, int max_steps,
+                                                          int* __restrict__ n_accept, int* __restrict__ n_reject,
+                                                          int* __restrict__ status) {
+    __shared__ __align__(16) float ra[2 * KP];
+    __shared__ double red[4];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N;
+    RowRhs<KP> f;
+    f.init(p, ra, b);
+    const size_t row = (size_t)3 * N;
+    const double cnt = 3.0 * N;
+    float y[3] = {0.f, 0.f, 0.f};
+    if (f.act) {
+        const Y3 s = ld3(y0 + b * row, N, i);
+        y[0] = s.V; y[1] = s.A; y[2] = s.F;
+        st3(y_out + b * row, N, i, y[0], y[1], y[2]);
+    }
+    float k[7][3];
+    auto rms3 = [&](float a0, float a1, float a2) -> float {
+        double s = f.act ? ((double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2) : 0.0;
+        s = block_sum(s, red);
+        return (float)sqrt(s / cnt);
+    };
+    // ---- before integrate: f0 and Hairer's initial step (order 4 -> exponent 1/5)
+    double tc0 = (double)__ldg(t);
+    f.eval((float)tc0, y[0], y[1], y[2], k[0][0], k[0][1], k[0][2]);
+    double dt;
+    {
+        float sc[3], q0[3], q1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sc[c] = __fadd_rn(atol, __fmul_rn(fabsf(y[c]), rtol));
+            q0[c] = __fdiv_rn(y[c], sc[c]);
+            q1[c] = __fdiv_rn(k[0][c], sc[c]);
+        }
+        const float d0 = rms3(q0[0], q0[1], q0[2]);
+        const float d1 = rms3(q1[0], q1[1], q1[2]);
+        float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : __fdiv_rn(__fmul_rn(0.01f, d0), d1);
+        h0 = fabsf(h0);
+        float y1[3], f1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) y1[c] = __fadd_rn(y[c], __fmul_rn(h0, k[0][c]));
+        f.eval((float)(tc0 + (double)h0), y1[0], y1[1], y1[2], f1[0], f1[1], f1[2]);
+        const float d2 = fabsf(__fdiv_rn(rms3(__fdiv_rn(__fsub_rn(f1[0], k[0][0]), sc[0]), __fdiv_rn(__fsub_rn(f1[1], k[0][1]), sc[1]),
+                                              __fdiv_rn(__fsub_rn(f1[2], k[0][2]), sc[2])), h0));
+        float h1;
+        if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
+        else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 0.2f);
+        dt = (double)fminf(__fmul_rn(100.f, h0), fabsf(h1));
+    }
+    double st_t0 = tc0, st_t1 = tc0;
+    float ce[3], cd[3], cc[3], cb[3], ca[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ce[c] = cd[c] = cc[c] = cb[c] = ca[c] = y[c];
+    int nacc = 0, nrej = 0, st = ODECOL_ST_OK;
+    int j = 1;
+    for (; j < T && st == ODECOL_ST_OK; ++j) {
+        const double next_t = (double)__ldg(t + j);
+        while (next_t > st_t1) {
+            if (nacc + nrej >= max_steps) { st = ODECOL_ST_MAXSTEPS; break; }
+            const double t0 = st_t1, t1 = t0 + dt;
+            if (!(t0 + dt > t0)) { st = ODECOL_ST_UNDERFLOW; break; }
+            if (block_any(f.act && !(isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2])))) { st = ODECOL_ST_NONFINITE; break; }
+            const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
+            float ys[3];
+#define ODECOL_STAGE(expr, tt, ko)                                                                   \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) ys[c] = __fadd_rn(y[c], (expr));                   \
+    f.eval((tt), ys[0], ys[1], ys[2], k[ko][0], k[ko][1], k[ko][2]);
+            ODECOL_STAGE(k[0][c] * (DP::b10 * dtf), __fadd_rn(t0f, __fmul_rn(DP::a1, dtf)), 1)
+            ODECOL_STAGE(fmaf(k[1][c], DP::b21 * dtf, k[0][c] * (DP::b20 * dtf)), __fadd_rn(t0f, __fmul_rn(DP::a2, dtf)), 2)
+            ODECOL_STAGE(fmaf(k[2][c], DP::b32 * dtf, fmaf(k[1][c], DP::b31 * dtf, k[0][c] * (DP::b30 * dtf))),
+                         __fadd_rn(t0f, __fmul_rn(DP::a3, dtf)), 3)
+            ODECOL_STAGE(fmaf(k[3][c], DP::b43 * dtf, fmaf(k[2][c], DP::b42 * dtf, fmaf(k[1][c], DP::b41 * dtf, k[0][c] * (DP::b40 * dtf)))),
+                         __fadd_rn(t0f, __fmul_rn(DP::a4, dtf)), 4)
+            ODECOL_STAGE(fmaf(k[4][c], DP::b54 * dtf, fmaf(k[3][c], DP::b53 * dtf, fmaf(k[2][c], DP::b52 * dtf,
+                              fmaf(k[1][c], DP::b51 * dtf, k[0][c] * (DP::b50 * dtf))))), t1f, 5)
+            ODECOL_STAGE(fmaf(k[5][c], DP::b65 * dtf, fmaf(k[4][c], DP::b64 * dtf, fmaf(k[3][c], DP::b63 * dtf,
+                              fmaf(k[2][c], DP::b62 * dtf, k[0][c] * (DP::b60 * dtf))))), t1f, 6)
+#undef ODECOL_STAGE
+            // ys is y1 (FSAL), k[6] is f1
+            float q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float err = fmaf(k[6][c], DP::e6 * dtf, fmaf(k[5][c], DP::e5 * dtf, fmaf(k[4][c], DP::e4 * dtf,
+                                  fmaf(k[3][c], DP::e3 * dtf, fmaf(k[2][c], DP::e2 * dtf, k[0][c] * (DP::e0 * dtf))))));
+                const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y[c]), fabsf(ys[c]))));
+                q[c] = __fdiv_rn(err, tol);
+            }
+            const float ratio = rms3(q[0], q[1], q[2]);
+            const bool accept = ratio <= 1.0f;
+            if (accept) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float ymid = __fadd_rn(y[c], fmaf(k[6][c], DP::m6 * dtf, fmaf(k[5][c], DP::m5 * dtf, fmaf(k[4][c], DP::m4 * dtf,
+                                       fmaf(k[3][c], DP::m3 * dtf, fmaf(k[2][c], DP::m2 * dtf, k[0][c] * (DP::m0 * dtf)))))));
+                    const float f0 = k[0][c], f1 = k[6][c], y0c = y[c], y1c = ys[c];
+                    ca[c] = 2.f * dtf * (f1 - f0) - 8.f * (y1c + y0c) + 16.f * ymid;
+                    cb[c] = dtf * (5.f * f0 - 3.f * f1) + 18.f * y0c + 14.f * y1c - 32.f * ymid;
+                    cc[c] = dtf * (f1 - 4.f * f0) - 11.f * y0c - 5.f * y1c + 16.f * ymid;
+                    cd[c] = dtf * f0;
+                    ce[c] = y0c;
+                    y[c] = y1c;
+                    k[0][c] = f1;
+                }
+                st_t0 = t0; st_t1 = t1;
+                ++nacc;
+            } else {
+                ++nrej;
+            }
+            // controller in float64 (torchdiffeq keeps dt in float64)
+            const double r64 = (double)ratio;
+            if (r64 == 0.0) dt = dt * 10.0;
+            else {
+                const double df = r64 < 1.0 ? 1.0 : 0.2;
+                dt = dt * fmin(10.0, fmax(0.9 / pow(r64, 0.2), df));
+            }
+            if (!(ratio == ratio)) { st = ODECOL_ST_NONFINITE; break; }
+        }
+        if (st != ODECOL_ST_OK) break;
+        const float x = (float)((next_t - st_t0) / (st_t1 - st_t0));
+        if (f.act) {
+            float o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float tot = __fadd_rn(ce[c], __fmul_rn(x, cd[c]));
+                float xp = __fmul_rn(x, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, cc[c]));
+                xp = __fmul_rn(xp, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, cb[c]));
+                xp = __fmul_rn(xp, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, ca[c]));
+                o[c] = tot;
+            }
+            st3(y_out + ((size_t)j * p.B + b) * row, N, i, o[0], o[1], o[2]);
+        }
+    }
+    if (st != ODECOL_ST_OK && f.act) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int jj = j; jj < T; ++jj) st3(y_out + ((size_t)jj * p.B + b) * row, N, i, qnan, qnan, qnan);
+    }
+    if (i == 0) {
+        if (n_accept) n_accept[b] = nacc;
+        if (n_reject) n_reject[b] = nrej;
+        if (status) status[b] = st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Euler-Maruyama in torchsde's integrate loop: fixed step (host increments or Philox) and step doubling
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) k_em_fwd_small(DevProblem p, const float* __restrict__ ts, int T,
+                                                      const float* __restrict__ y0, float* __restrict__ y_out,
+                                                      const float* __restrict__ dWs, unsigned long long seed,
+                                                      long long trial_offset, float dt0, int adaptive,
+                                                      float rtol, float atol, float dt_min,
+                                                      int* __restrict__ n_accept, int* __restrict__ n_reject,
+                                                      int* __restrict__ status, float* __restrict__ y_steps,
+                                                      long long max_attempts) {
+    __shared__ __align__(16) float ra[2 * KP];
+    __shared__ double red[4];
+    __shared__ float zs[2][kBrownianDepth + 1];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    RowRhs<KP> f;
+    f.init(p, ra, b);
+    const size_t row = (size_t)3 * N;
+    const double cnt = 3.0 * N;
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    float sg[3] = {0.f, 0.f, 0.f};
+    float y[3] = {0.f, 0.f, 0.f};
+    if (f.act) {
+        const Y3 s = ld3(y0 + b * row, N, i);
+        y[0] = s.V; y[1] = s.A; y[2] = s.F;
+        st3(y_out + b * row, N, i, y[0], y[1], y[2]);
+        if (y_steps) st3(y_steps + b * row, N, i, y[0], y[1], y[2]);
+        if (p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+    }
+    const float t_begin = __ldg(ts), t_end = __ldg(ts + T - 1);
+    const float span = t_end - t_begin;
+    float curr_t = t_begin, prev_t = t_begin;
+    float py[3] = {y[0], y[1], y[2]};
+    double step = (double)dt0, prev_ratio = 0.0;
+    bool has_prev = false;
+    long long kstep = 0, attempts = 0;
+    int nacc = 0, nrej = 0, st = ODECOL_ST_OK;
+    float w_curr = 0.0f;                        // W(curr_t) on the virtual tree (adaptive mode)
+    // two tree queries per attempt, computed cooperatively: lanes 0..24 of warp 0 draw the node deviates
+    auto tree2 = [&](float ta, float tb, float& wa, float& wb) {
+        uint32_t qa, qb; float fa, fb;
+        brownian_path(t_begin, span, ta, qa, fa);
+        brownian_path(t_begin, span, tb, qb, fb);
+        if (i <= kBrownianDepth) {
+            const uint32_t lvl = i == kBrownianDepth ? kBrownianRootLevel : (uint32_t)i;
+            zs[0][i] = brownian_node(px, trial, lvl, i == kBrownianDepth ? 0u : (qa >> (kBrownianDepth - i)));
+            zs[1][i] = brownian_node(px, trial, lvl, i == kBrownianDepth ? 0u : (qb >> (kBrownianDepth - i)));
+        }
+        __syncthreads();
+        wa = brownian_combine(span, qa, fa, zs[0][kBrownianDepth], [&](int l) { return zs[0][l]; });
+        wb = brownian_combine(span, qb, fb, zs[1][kBrownianDepth], [&](int l) { return zs[1][l]; });
+        __syncthreads();
+    };
+    int j = 1;
+    for (; j < T && st == ODECOL_ST_OK; ++j) {
+        const float out_t = __ldg(ts + j);
+        while (curr_t < out_t) {
+            if (++attempts > max_attempts) { st = ODECOL_ST_MAXSTEPS; break; }
+            const float next_t = fminf(__fadd_rn(curr_t, (float)step), t_end);
+            float fv[3];
+            f.eval(curr_t, y[0], y[1], y[2], fv[0], fv[1], fv[2]);
+            if (!adaptive) {
+                const float h = __fsub_rn(next_t, curr_t);
+                float dw;
+                if (dWs) dw = __ldg(dWs + (size_t)kstep * B + b);
+                else {
+                    const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)kstep, 0x80000000u | (uint32_t)(kstep >> 32));
+                    dw = sqrtf(h) * normal_from_bits(bits.x, bits.y);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    py[c] = y[c];
+                    y[c] = __fadd_rn(__fadd_rn(y[c], __fmul_rn(fv[c], h)), __fmul_rn(sg[c], dw));
+                }
+                prev_t = curr_t; curr_t = next_t;
+                ++kstep; ++nacc;
+                if (y_steps && f.act) st3(y_steps + ((size_t)kstep * B + b) * row, N, i, y[0], y[1], y[2]);
+            } else {
+                const float mid_t = __fmul_rn(0.5f, __fadd_rn(curr_t, next_t));
+                float w_mid, w_next;
+                tree2(mid_t, next_t, w_mid, w_next);
+                const float h = __fsub_rn(next_t, curr_t), h1 = __fsub_rn(mid_t, curr_t), h2 = __fsub_rn(next_t, mid_t);
+                float yf[3], ym[3], yh[3], fm[3], q[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    yf[c] = __fadd_rn(__fadd_rn(y[c], __fmul_rn(fv[c], h)), __fmul_rn(sg[c], w_next - w_curr));
+                    ym[c] = __fadd_rn(__fadd_rn(y[c], __fmul_rn(fv[c], h1)), __fmul_rn(sg[c], w_mid - w_curr));
+                }
+                f.eval(mid_t, ym[0], ym[1], ym[2], fm[0], fm[1], fm[2]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    yh[c] = __fadd_rn(__fadd_rn(ym[c], __fmul_rn(fm[c], h2)), __fmul_rn(sg[c], w_next - w_mid));
+                    const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf[c]), fabsf(yh[c]))));
+                    q[c] = __fdiv_rn(__fsub_rn(yf[c], yh[c]), tol);
+                }
+                double s = f.act ? ((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]) : 0.0;
+                s = block_sum(s, red);
+                const double err = (double)(float)sqrt(s / cnt);
+                if (!(err == err)) { st = ODECOL_ST_NONFINITE; break; }
+                // torchsde adaptive_stepping.update_step_size
+                {
+                    const double pfac = err > 1.0 ? 0.0 : 0.13, ifac = err > 1.0 ? 1.0 / 1.5 : 1.0 / 4.5;
+                    const double ratio = 0.9 / err;
+                    const double pr = has_prev ? prev_ratio : ratio;
+                    double factor = pow(ratio, ifac) * pow(ratio / pr, pfac);
+                    double facmin = 0.2;
+                    if (err <= 1.0) { prev_ratio = ratio; has_prev = true; facmin = 1.0; }
+                    factor = fmin(1.4, fmax(facmin, factor));
+                    step = step * factor;
+                }
+                if (step < (double)dt_min) { step = (double)dt_min; has_prev = false; }
+                if (err <= 1.0 || step <= (double)dt_min) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { py[c] = y[c]; y[c] = yh[c]; }
+                    prev_t = curr_t; curr_t = next_t; w_curr = w_next;
+                    ++nacc;
+                } else {
+                    ++nrej;
+                }
+            }
+        }
+        if (st != ODECOL_ST_OK) break;
+        if (f.act) {
+            const float spn = __fsub_rn(curr_t, prev_t);
+            const float w0 = __fdiv_rn(__fsub_rn(curr_t, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, prev_t), spn);
+            st3(y_out + ((size_t)j * B + b) * row, N, i,
+                __fadd_rn(__fmul_rn(w0, py[0]), __fmul_rn(w1, y[0])),
+                __fadd_rn(__fmul_rn(w0, py[1]), __fmul_rn(w1, y[1])),
+                __fadd_rn(__fmul_rn(w0, py[2]), __fmul_rn(w1, y[2])));
+        }
+    }
+    if (st != ODECOL_ST_OK && f.act) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int jj = j; jj < T; ++jj) st3(y_out + ((size_t)jj * B + b) * row, N, i, qnan, qnan, qnan);
+    }
+    if (i == 0) {
+        if (n_accept) n_accept[b] = nacc;
+        if (n_reject) n_reject[b] = nrej;
+        if (status) status[b] = st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Euler-Maruyama discrete adjoint (fixed step).  k_em_schedule replays the data-independent float32 time loop
+// once: for every output j the solver state index it ends on and the two interpolation weights, and the start
+// time of every step.  k_em_bwd_small then sweeps the steps in reverse.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_em_schedule(const float* __restrict__ ts, int T, float dt0, int* __restrict__ step_of,
+                              float* __restrict__ w, float* __restrict__ tk) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float t_end = ts[T - 1];
+    float curr_t = ts[0], prev_t = ts[0];
+    int k = 0;
+    step_of[0] = 0; w[0] = 0.f; w[1] = 1.f;
+    tk[0] = curr_t;
+    for (int j = 1; j < T; ++j) {
+        const float out_t = ts[j];
+        while (curr_t < out_t) {
+            const float next_t = fminf(__fadd_rn(curr_t, dt0), t_end);
+            prev_t = curr_t; curr_t = next_t;
+            tk[++k] = curr_t;
+        }
+        const float spn = __fsub_rn(curr_t, prev_t);
+        step_of[j] = k;
+        w[2 * j] = __fdiv_rn(__fsub_rn(curr_t, out_t), spn);
+        w[2 * j + 1] = __fdiv_rn(__fsub_rn(out_t, prev_t), spn);
+    }
+    step_of[T] = k;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) k_em_bwd_small(DevProblem p, int T, const float* __restrict__ y_steps,
+                                                      const float* __restrict__ grad_y, const int* __restrict__ sel,
+                                                      int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
+                                                      const int* __restrict__ step_of, const float* __restrict__ w,
+                                                      const float* __restrict__ tk) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    BwdCtx<KP> cx;
+    cx.init(p, sm, b);
+    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    __syncthreads();
+    const int gV = cx.act ? cx.s.inv[i] : -1, gA = cx.act ? cx.s.inv[N + i] : -1, gF = cx.act ? cx.s.inv[2 * N + i] : -1;
+    const size_t row = (size_t)3 * N;
+    const int nsteps = step_of[T];
+    auto gcomp = [&](int j, int g) -> float { return g >= 0 ? grad_y[((size_t)j * B + b) * G + g] : 0.f; };
+    float lV = 0.f, lA = 0.f, lF = 0.f;      // adjoint of solver state k+1 while processing step k
+    float pV = 0.f, pA = 0.f, pF = 0.f;      // contributions destined for state k (from interpolated outputs)
+    int j = T - 1;
+    for (int k = nsteps - 1; k >= 0; --k) {
+        lV += pV; lA += pA; lF += pF;
+        pV = pA = pF = 0.f;
+        while (j >= 1 && step_of[j] == k + 1) {           // outputs whose "curr" state is k+1, "prev" is k
+            const float w0 = w[2 * j], w1 = w[2 * j + 1];
+            const float a = gcomp(j, gV), c2 = gcomp(j, gA), d = gcomp(j, gF);
+            lV += w1 * a; lA += w1 * c2; lF += w1 * d;
+            pV += w0 * a; pA += w0 * c2; pF += w0 * d;
+            --j;
+        }
+        const float t0 = tk[k], h = __fsub_rn(tk[k + 1], tk[k]);
+        float V = 0.f, A = 0.f;
+        if (cx.act) { const float* yk = y_steps + ((size_t)k * B + b) * row; V = yk[i]; A = yk[N + i]; }
+        float r, dr, bV, bA, bF;
+        (void)cx.stage_fwd(0, t0, V, A, r, dr, false);
+        cx.stage_bwd(0, dr, h * lV, h * lA, h * lF, bV, bA, bF);
+        lV += bV; lA += bA; lF += bF;
+        __syncthreads();
+    }
+    lV += pV; lA += pA; lF += pF;
+    if (j >= 0) { lV += gcomp(0, gV); lA += gcomp(0, gA); lF += gcomp(0, gF); }   // output 0 is y0 itself
+    if (grad_y0 && cx.act) st3(grad_y0 + b * row, N, i, lV, lA, lF);
+    cx.flush_dw(p, grad_W);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------------------------
+static inline int small_threads(int N) { return (N + 31) / 32 * 32; }
+
+int small_kp(const DevProblem& p) {
+    const int Kaug = p.N + p.n_in + 1;
+    if (p.N > 128 || Kaug > 128) return 0;
+    if (Kaug <= 40) return 40;
+    if (Kaug <= 64) return 64;
+    if (Kaug <= 96) return 96;
+    return 128;
+}
+
+#define ODECOL_KP_SWITCH(kp, ...)                                  \
+    switch (kp) {                                                  \
+        case 40: { constexpr int KP = 40; __VA_ARGS__; } break;    \
+        case 64: { constexpr int KP = 64; __VA_ARGS__; } break;    \
+        case 96: { constexpr int KP = 96; __VA_ARGS__; } break;    \
+        case 128: { constexpr int KP = 128; __VA_ARGS__; } break;  \
+        default: return ODECOL_E_UNSUPPORTED;                      \
+    }
+
+int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, float* f, cudaStream_t s) {
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t smem = sizeof(float) * Kaug;
+    if (smem > 200 * 1024) return ODECOL_E_UNSUPPORTED;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rhs_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_rhs_generic<<<p.B, 256, smem, s>>>(p, t, y, f);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
+                         cudaStream_t s) {
+    const int kp = small_kp(p);
+    ODECOL_KP_SWITCH(kp, (k_rk4_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, out_every)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float* y_traj, const float* grad_y,
+                         const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s) {
+    const int kp = small_kp(p);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    ODECOL_KP_SWITCH(kp, {
+        cudaFuncSetAttribute(k_rk4_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_rk4_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W);
+    });
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, float rtol,
+                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, cudaStream_t s) {
+    const int kp = small_kp(p);
+    ODECOL_KP_SWITCH(kp, (k_dopri5_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, rtol, atol, max_steps,
+                                                                                   n_accept, n_reject, status)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_em_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
+                        uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol,
+                        float dt_min, int* n_accept, int* n_reject, int* status, float* y_steps,
+                        long long max_attempts, cudaStream_t s) {
+    const int kp = small_kp(p);
+    ODECOL_KP_SWITCH(kp, (k_em_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(
+                             p, ts, T, y0, y_out, dW, (unsigned long long)seed, (long long)trial_offset, dt, adaptive, rtol,
+                             atol, dt_min, n_accept, n_reject, status, y_steps, max_attempts)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_em_schedule(const float* ts, int T, float dt, int* step_of, float* w, float* tk, cudaStream_t s) {
+    k_em_schedule<<<1, 32, 0, s>>>(ts, T, dt, step_of, w, tk);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float* y_steps, const float* grad_y,
+                        const int* sel, int G, float* grad_y0, float* grad_W, const int* step_of, const float* w,
+                        const float* tk, cudaStream_t s) {
+    (void)ts;
+    const int kp = small_kp(p);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    ODECOL_KP_SWITCH(kp, {
+        cudaFuncSetAttribute(k_em_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_em_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, y_steps, grad_y, sel, G, grad_y0, grad_W, step_of, w, tk);
+    });
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+}  // namespace odecol

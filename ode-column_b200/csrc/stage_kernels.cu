@@ -1,0 +1,335 @@
+// Kernel family L ("staged"): N too large for one CTA's registers.  The state of every trial lives in HBM/L2
+// and each Runge-Kutta stage is ONE fused launch:
+//
+//     C[i][b] = sum_k W_aug[i][k] * R_aug[b][k]            (128 x 128 x 16 FFMA tiles, register-prefetched)
+//     epilogue: drift -> k_s -> next stage state -> phi -> R_aug of the next stage (written K-major so that it is
+//               directly the B operand of the next launch), stimulus columns refreshed by the first row of CTAs
+//
+// so the only HBM traffic is the per-element RK bookkeeping (about 46 floats per population-step) and
+// W_aug / R_aug stream from L2.  The reverse sweep reuses the same contraction core with W^T for J^T lambda and
+// a split-K (over trials) contraction with atomics for dW_aug.
+//
+// Replaces the Python stepping loop of torchdiffeq's rk4 around ColumnNetwork.forward for networks beyond the
+// reference's sizes (BASELINE.json configs 4 and 5); same arithmetic as family S.
+#include "odecol_common.cuh"
+
+namespace odecol {
+
+constexpr float kOneThirdL = 0.3333333333333333f;
+constexpr float kTwoThirdsL = 0.6666666666666666f;
+
+constexpr int TM = 128, TN = 128, TK = 16;     // CTA tile: TM rows of W (populations) x TN trials x TK
+constexpr int kGemmThreads = 256;
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// contraction core: acc[8][8] per thread.  A rows = populations (ldA floats, K contiguous), B rows = trials.
+// thread (tx = tid % 16, ty = tid / 16): rows {4tx..4tx+3} u {64+4tx..}, cols {4ty..4ty+3} u {64+4ty..}
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmSmem {
+    float A[2][TK][TM];
+    float B[2][TK][TN];
+};
+
+ODECOL_DEVINL void gemm_nt_core(const float* __restrict__ Ag, int ldA, const float* __restrict__ Bg, int ldB, int Kdim,
+                                GemmSmem& sm, float (&acc)[8][8]) {
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    // loader mapping: float4 index f = tid + 256*m (m = 0,1): row = f % 128, kq = f / 128
+    const int lrow = tid & 127, lkq = tid >> 7;       // lkq in {0,1}; second float4 uses kq + 2
+    const float4* a_src0 = reinterpret_cast<const float4*>(Ag + (size_t)lrow * ldA) + lkq;
+    const float4* b_src0 = reinterpret_cast<const float4*>(Bg + (size_t)lrow * ldB) + lkq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 ra0 = __ldg(a_src0), ra1 = __ldg(a_src0 + 2), rb0 = __ldg(b_src0), rb1 = __ldg(b_src0 + 2);
+    const int nk = Kdim / TK;
+    int buf = 0;
+    auto stash = [&](int bf) {
+        const int k0 = 4 * lkq, k1 = 4 * (lkq + 2);
+        sm.A[bf][k0 + 0][lrow] = ra0.x; sm.A[bf][k0 + 1][lrow] = ra0.y; sm.A[bf][k0 + 2][lrow] = ra0.z; sm.A[bf][k0 + 3][lrow] = ra0.w;
+        sm.A[bf][k1 + 0][lrow] = ra1.x; sm.A[bf][k1 + 1][lrow] = ra1.y; sm.A[bf][k1 + 2][lrow] = ra1.z; sm.A[bf][k1 + 3][lrow] = ra1.w;
+        sm.B[bf][k0 + 0][lrow] = rb0.x; sm.B[bf][k0 + 1][lrow] = rb0.y; sm.B[bf][k0 + 2][lrow] = rb0.z; sm.B[bf][k0 + 3][lrow] = rb0.w;
+        sm.B[bf][k1 + 0][lrow] = rb1.x; sm.B[bf][k1 + 1][lrow] = rb1.y; sm.B[bf][k1 + 2][lrow] = rb1.z; sm.B[bf][k1 + 3][lrow] = rb1.w;
+    };
+    stash(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        if (kt + 1 < nk) {
+            const int off = (kt + 1) * (TK / 4);
+            ra0 = __ldg(a_src0 + off); ra1 = __ldg(a_src0 + off + 2);
+            rb0 = __ldg(b_src0 + off); rb1 = __ldg(b_src0 + off + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sm.A[buf][k][4 * tx]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sm.A[buf][k][64 + 4 * tx]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sm.B[buf][k][4 * ty]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sm.B[buf][k][64 + 4 * ty]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward stage epilogues
+// ---------------------------------------------------------------------------------------------------------------
+struct FwdStageArgs {
+    DevProblem p;
+    const float* Wp;       // [Np][KPa]
+    const float* Ra_cur;   // [Bp][KPa]
+    float* Ra_nxt;         // [Bp][KPa]
+    const float* y0;       // [B][3N] state at the start of the step
+    float* k1;             // [B][3N]
+    float* k2;
+    float* k3;
+    float* y1;             // [B][3N] state at the end of the step (stage 4)
+    float* y_out_row;      // optional second destination of y1 (trajectory row), may be NULL
+    const float* t;        // device time grid
+    int n;                 // step index: t0 = t[n], t1 = t[n+1]
+    int KPa;
+};
+
+ODECOL_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+ODECOL_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// one state component of 4 consecutive populations
+struct C4 { float v[4]; };
+ODECOL_DEVINL C4 ldc(const float* p) { const float4 q = ld4(p); return {{q.x, q.y, q.z, q.w}}; }
+ODECOL_DEVINL void stc(float* p, const C4& c) { st4(p, make_float4(c.v[0], c.v[1], c.v[2], c.v[3])); }
+
+template <int S>
+ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const float (&tot)[4], float dt) {
+    const int N = a.p.N;
+    const size_t base = (size_t)b * 3 * N + i;
+    const C4 V0 = ldc(a.y0 + base), A0 = ldc(a.y0 + base + N), F0 = ldc(a.y0 + base + 2 * N);
+    const C4 rs = ldc(a.Ra_cur + (size_t)b * a.KPa + i);
+    const C4 kap = ldc(a.p.kappa + i);
+    C4 k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+    if (S >= 2) { k1V = ldc(a.k1 + base); k1A = ldc(a.k1 + base + N); k1F = ldc(a.k1 + base + 2 * N); }
+    if (S >= 3) { k2V = ldc(a.k2 + base); k2A = ldc(a.k2 + base + N); k2F = ldc(a.k2 + base + 2 * N); }
+    if (S >= 4) { k3V = ldc(a.k3 + base); k3A = ldc(a.k3 + base + N); k3F = ldc(a.k3 + base + 2 * N); }
+    C4 oV, oA, oF, oR, kV, kA, kF;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        // the stage state this launch's contraction belongs to (same expressions as family S)
+        float V, A, F;
+        if (S == 1) { V = V0.v[e]; A = A0.v[e]; F = F0.v[e]; }
+        if (S == 2) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, k1V.v[e]), kOneThirdL));
+            A = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, k1A.v[e]), kOneThirdL));
+            F = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(dt, k1F.v[e]), kOneThirdL));
+        }
+        if (S == 3) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(k2V.v[e], __fmul_rn(k1V.v[e], kOneThirdL))));
+            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(k2A.v[e], __fmul_rn(k1A.v[e], kOneThirdL))));
+            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fsub_rn(k2F.v[e], __fmul_rn(k1F.v[e], kOneThirdL))));
+        }
+        if (S == 4) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), k3V.v[e])));
+            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), k3A.v[e])));
+            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1F.v[e], k2F.v[e]), k3F.v[e])));
+        }
+        float dV, dA, dF;
+        drift(a.p.c, V, A, F, rs.v[e], kap.v[e], tot[e], dV, dA, dF);
+        kV.v[e] = dV; kA.v[e] = dA; kF.v[e] = dF;
+        // next stage state
+        float nV, nA, nF;
+        if (S == 1) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, dV), kOneThirdL));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, dA), kOneThirdL));
+            nF = 0.f;
+        }
+        if (S == 2) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(dV, __fmul_rn(k1V.v[e], kOneThirdL))));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(dA, __fmul_rn(k1A.v[e], kOneThirdL))));
+            nF = 0.f;
+        }
+        if (S == 3) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), dV)));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), dA)));
+            nF = 0.f;
+        }
+        if (S == 4) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1V.v[e], __fmul_rn(3.f, __fadd_rn(k2V.v[e], k3V.v[e]))), dV), dt), 0.125f));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1A.v[e], __fmul_rn(3.f, __fadd_rn(k2A.v[e], k3A.v[e]))), dA), dt), 0.125f));
+            nF = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F.v[e], __fmul_rn(3.f, __fadd_rn(k2F.v[e], k3F.v[e]))), dF), dt), 0.125f));
+        }
+        oV.v[e] = nV; oA.v[e] = nA; oF.v[e] = nF;
+        oR.v[e] = phi(__fsub_rn(nV, nA));
+    }
+    if (S == 1) { stc(a.k1 + base, kV); stc(a.k1 + base + N, kA); stc(a.k1 + base + 2 * N, kF); }
+    if (S == 2) { stc(a.k2 + base, kV); stc(a.k2 + base + N, kA); stc(a.k2 + base + 2 * N, kF); }
+    if (S == 3) { stc(a.k3 + base, kV); stc(a.k3 + base + N, kA); stc(a.k3 + base + 2 * N, kF); }
+    if (S == 4) {
+        stc(a.y1 + base, oV); stc(a.y1 + base + N, oA); stc(a.y1 + base + 2 * N, oF);
+        if (a.y_out_row) { stc(a.y_out_row + base, oV); stc(a.y_out_row + base + N, oA); stc(a.y_out_row + base + 2 * N, oF); }
+    }
+    stc(a.Ra_nxt + (size_t)b * a.KPa + i, oR);
+}
+
+template <int S>
+__global__ void __launch_bounds__(kGemmThreads, 2) k_fwd_stage(FwdStageArgs a) {
+    __shared__ __align__(16) GemmSmem sm;
+    const int i0 = blockIdx.x * TM, b0 = blockIdx.y * TN;
+    float acc[8][8];
+    gemm_nt_core(a.Wp + (size_t)i0 * a.KPa, a.KPa, a.Ra_cur + (size_t)b0 * a.KPa, a.KPa, a.KPa, sm, acc);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int N = a.p.N, B = a.p.B;
+    const float t0 = __ldg(a.t + a.n), t1 = __ldg(a.t + a.n + 1);
+    const float dt = __fsub_rn(t1, t0);
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int b = b0 + jh * 64 + 4 * ty + jj;
+            if (b >= B) continue;
+#pragma unroll
+            for (int ih = 0; ih < 2; ++ih) {
+                const int i = i0 + ih * 64 + 4 * tx;
+                if (i >= N) continue;
+                const float tot[4] = {acc[ih * 4 + 0][jh * 4 + jj], acc[ih * 4 + 1][jh * 4 + jj], acc[ih * 4 + 2][jh * 4 + jj],
+                                      acc[ih * 4 + 3][jh * 4 + jj]};
+                fwd_stage_epilogue<S>(a, i, b, tot, dt);
+            }
+        }
+    // stimulus columns of the next stage's operand: written by the first row of CTAs
+    if (blockIdx.x == 0 && a.p.n_in > 0) {
+        const float tn = S == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : S == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
+        int idx = 1;
+        const float tc = knot_locate(a.p.knot_t, a.p.K, tn, idx);
+        const int n_in = a.p.n_in;
+        for (int e = tid; e < TN * n_in; e += kGemmThreads) {
+            const int bl = e / n_in, ch = e % n_in, b = b0 + bl;
+            if (b < B)
+                a.Ra_nxt[(size_t)b * a.KPa + N + ch] = knot_value(a.p.knot_t, a.p.knot_u + (size_t)b * a.p.knot_stride_b, n_in, idx, tc, ch);
+        }
+    }
+}
+
+// operand initialisation: Wp (padded copy), Ra[0] = r_aug(t[0], y0), constant-one column in both buffers
+__global__ void k_pad_weights(const float* __restrict__ W_aug, int N, int ld_w, int Kaug, float* __restrict__ Wp, int Np, int KPa) {
+    const size_t total = (size_t)Np * KPa;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / KPa), k = (int)(e % KPa);
+        Wp[e] = (i < N && k < Kaug) ? W_aug[(size_t)i * ld_w + k] : 0.0f;
+    }
+}
+
+__global__ void k_init_operand(DevProblem p, const float* y, const float* t_dev, float* Ra0, float* Ra1, int KPa, int Bp) {
+    // one CTA per trial row (padding rows become zero); stimulus taken at t_dev[0]
+    const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
+    const float tq = __ldg(t_dev);
+    float* r0 = Ra0 + (size_t)b * KPa;
+    float* r1 = Ra1 ? Ra1 + (size_t)b * KPa : nullptr;
+    if (b >= p.B) {
+        for (int k = threadIdx.x; k < KPa; k += blockDim.x) { r0[k] = 0.f; if (r1) r1[k] = 0.f; }
+        return;
+    }
+    const float* yb = y + (size_t)b * 3 * N;
+    int idx = 1;
+    const float tc = knot_locate(p.knot_t, p.K, tq, idx);
+    const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
+    for (int k = threadIdx.x; k < KPa; k += blockDim.x) {
+        float v = 0.f, v1 = 0.f;
+        if (k < N) v = phi(__fsub_rn(yb[k], yb[N + k]));
+        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tc, k - N);
+        else if (k == Kaug - 1) { v = 1.f; v1 = 1.f; }
+        r0[k] = v;
+        if (r1) r1[k] = v1;
+    }
+}
+
+__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x)
+        reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward driver
+// ---------------------------------------------------------------------------------------------------------------
+struct FwdLayout {
+    int Np, Bp, KPa;
+    size_t off_Wp, off_Ra0, off_Ra1, off_k1, off_k2, off_k3, off_ya, off_yb, total;
+};
+
+static FwdLayout fwd_layout(const DevProblem& p) {
+    FwdLayout L;
+    const int Kaug = p.N + p.n_in + 1;
+    L.Np = round_up(p.N, TM);
+    L.Bp = round_up(p.B, TN);
+    L.KPa = round_up(Kaug, TK);
+    size_t o = 0;
+    auto take = [&](size_t floats) { const size_t r = o; o += (floats * sizeof(float) + 255) / 256 * 256; return r; };
+    L.off_Wp = take((size_t)L.Np * L.KPa);
+    L.off_Ra0 = take((size_t)L.Bp * L.KPa);
+    L.off_Ra1 = take((size_t)L.Bp * L.KPa);
+    const size_t st = (size_t)p.B * 3 * p.N;
+    L.off_k1 = take(st); L.off_k2 = take(st); L.off_k3 = take(st);
+    L.off_ya = take(st); L.off_yb = take(st);
+    L.total = o;
+    return L;
+}
+
+size_t stage_rk4_fwd_workspace_bytes(const DevProblem& p, int) { return fwd_layout(p).total; }
+
+int stage_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
+                  void* ws, size_t ws_bytes, cudaStream_t s) {
+    const FwdLayout L = fwd_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    float* Wp = reinterpret_cast<float*>(w + L.off_Wp);
+    float* Ra[2] = {reinterpret_cast<float*>(w + L.off_Ra0), reinterpret_cast<float*>(w + L.off_Ra1)};
+    float* k1 = reinterpret_cast<float*>(w + L.off_k1);
+    float* k2 = reinterpret_cast<float*>(w + L.off_k2);
+    float* k3 = reinterpret_cast<float*>(w + L.off_k3);
+    float* ybuf[2] = {reinterpret_cast<float*>(w + L.off_ya), reinterpret_cast<float*>(w + L.off_yb)};
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+
+    k_pad_weights<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, Kaug, Wp, L.Np, L.KPa);
+    k_init_operand<<<L.Bp, 128, 0, s>>>(p, y0, t_dev, Ra[0], Ra[1], L.KPa, L.Bp);
+    k_copy<<<296, 256, 0, s>>>(y0, y_out, st / 4);
+    count_launch(3);
+    const dim3 grid(L.Np / TM, L.Bp / TN);
+    const float* ycur = y0;
+    int cur = 0;
+    for (int n = 0; n < T - 1; ++n) {
+        const int j = n + 1;
+        const bool emit = (j % out_every == 0) || (j == T - 1);
+        const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
+        float* ynext = emit ? y_out + r * st : ybuf[n & 1];
+        FwdStageArgs a;
+        a.p = p; a.Wp = Wp; a.y0 = ycur; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.y1 = ynext; a.y_out_row = nullptr;
+        a.t = t_dev; a.n = n; a.KPa = L.KPa;
+        a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
+        k_fwd_stage<1><<<grid, kGemmThreads, 0, s>>>(a);
+        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
+        k_fwd_stage<2><<<grid, kGemmThreads, 0, s>>>(a);
+        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
+        k_fwd_stage<3><<<grid, kGemmThreads, 0, s>>>(a);
+        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
+        k_fwd_stage<4><<<grid, kGemmThreads, 0, s>>>(a);
+        cur ^= 1;
+        ycur = ynext;
+        count_launch(4);
+    }
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// backward and Euler-Maruyama drivers of family L live in stage_bwd.cu / stage_em.cu
+
+}  // namespace odecol

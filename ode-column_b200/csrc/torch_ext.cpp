@@ -1,0 +1,232 @@
+// PyTorch C++ extension over the C ABI (include/odecol.h).  Torch is plumbing here: it owns the device memory
+// (outputs and workspaces come from its caching allocator) and names the stream; every computation happens behind
+// the extern "C" entry points of libodecol.so.  Nothing in this file has a CPU path: tensors must be CUDA.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <optional>
+#include <string>
+#include "../../include/odecol.h"
+
+namespace {
+
+void check(int rc, const char* what) {
+    TORCH_CHECK(rc == ODECOL_OK, "odecol ", what, " failed: ", odecol_strerror(rc), " (", rc, ")");
+}
+
+void want(const torch::Tensor& t, const char* name, c10::ScalarType dt = torch::kFloat32) {
+    TORCH_CHECK(t.is_cuda(), "odecol: ", name, " must be a CUDA tensor (there is no CPU path)");
+    TORCH_CHECK(t.scalar_type() == dt, "odecol: ", name, " has the wrong dtype");
+    TORCH_CHECK(t.is_contiguous(), "odecol: ", name, " must be contiguous");
+}
+
+struct Problem {
+    torch::Tensor W_aug, kappa, sigma, knot_t, knot_u;
+    bool has_sigma = false;
+    odecol_problem p{};
+
+    Problem(torch::Tensor W_aug_, torch::Tensor kappa_, std::optional<torch::Tensor> sigma_, torch::Tensor knot_t_,
+            torch::Tensor knot_u_, int64_t n_in, int64_t B, double tau_s, double tau_m, double tau_a, double R,
+            int64_t flags)
+        : W_aug(std::move(W_aug_)), kappa(std::move(kappa_)), knot_t(std::move(knot_t_)), knot_u(std::move(knot_u_)) {
+        want(W_aug, "W_aug"); want(kappa, "kappa"); want(knot_t, "knot_t"); want(knot_u, "knot_u");
+        TORCH_CHECK(W_aug.dim() == 2 && kappa.dim() == 1 && knot_t.dim() == 1 && knot_u.dim() == 3, "odecol: bad ranks");
+        const int64_t N = W_aug.size(0);
+        TORCH_CHECK(kappa.size(0) == N, "odecol: kappa must have N entries");
+        TORCH_CHECK(W_aug.size(1) >= N + n_in + 1 && W_aug.size(1) % 4 == 0, "odecol: W_aug needs >= N+n_in+1 columns, multiple of 4");
+        TORCH_CHECK(knot_u.size(1) == knot_t.size(0) && knot_u.size(2) == n_in, "odecol: knot_u must be (B or 1, K, n_in)");
+        TORCH_CHECK(knot_u.size(0) == B || knot_u.size(0) == 1, "odecol: knot_u batch must be B or 1");
+        if (sigma_.has_value()) {
+            sigma = *sigma_;
+            want(sigma, "sigma");
+            TORCH_CHECK(sigma.numel() == 3 * N, "odecol: sigma must have 3N entries");
+            has_sigma = true;
+        }
+        p.N = (int32_t)N; p.n_in = (int32_t)n_in; p.B = (int32_t)B; p.K = (int32_t)knot_t.size(0);
+        p.ld_w = (int32_t)W_aug.size(1); p.flags = (int32_t)flags;
+        p.W_aug = W_aug.data_ptr<float>(); p.kappa = kappa.data_ptr<float>();
+        p.sigma = has_sigma ? sigma.data_ptr<float>() : nullptr;
+        p.knot_t = knot_t.data_ptr<float>(); p.knot_u = knot_u.data_ptr<float>();
+        p.knot_stride_b = knot_u.size(0) == 1 ? 0 : knot_u.size(1) * knot_u.size(2);
+        p.tau_s = (float)tau_s; p.tau_m = (float)tau_m; p.tau_a = (float)tau_a; p.resistance = (float)R;
+    }
+
+    torch::TensorOptions fopts() const { return W_aug.options(); }
+    torch::TensorOptions iopts() const { return W_aug.options().dtype(torch::kInt32); }
+    int64_t N() const { return p.N; }
+    int64_t B() const { return p.B; }
+
+    torch::Tensor workspace(int op, int64_t T, int64_t n_steps = 0) const {
+        const size_t bytes = odecol_workspace_bytes(&p, op, (int32_t)T, n_steps);
+        return torch::empty({(int64_t)((bytes + 15) / 16 * 16)}, W_aug.options().dtype(torch::kUInt8));
+    }
+    void* stream() const { return at::cuda::getCurrentCUDAStream(W_aug.device().index()).stream(); }
+};
+
+void check_state(const Problem& pr, const torch::Tensor& y, const char* name) {
+    want(y, name);
+    TORCH_CHECK(y.dim() == 2 && y.size(0) == pr.B() && y.size(1) == 3 * pr.N(), "odecol: ", name, " must be (B, 3N)");
+}
+
+torch::Tensor rhs(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y, "y");
+    want(t, "t");
+    TORCH_CHECK(t.numel() == pr.B(), "odecol: t must have one entry per trial");
+    auto f = torch::empty_like(y);
+    check(odecol_rhs(&pr.p, t.data_ptr<float>(), y.data_ptr<float>(), f.data_ptr<float>(), pr.stream()), "rhs");
+    return f;
+}
+
+torch::Tensor rk4_fwd(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0, int64_t out_every) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(t, "t");
+    const int64_t T = t.numel();
+    TORCH_CHECK(T >= 2 && out_every >= 1, "odecol: need at least two time points");
+    const int64_t rows = (T - 2) / out_every + 2;
+    auto y = torch::empty({rows, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto ws = pr.workspace(ODECOL_OP_RK4_FWD, T);
+    check(odecol_rk4_fwd(&pr.p, t.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(),
+                         (int32_t)out_every, ws.data_ptr(), (size_t)ws.numel(), pr.stream()), "rk4_fwd");
+    return y;
+}
+
+std::vector<torch::Tensor> rk4_bwd(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y_traj,
+                                   const torch::Tensor& grad_y, std::optional<torch::Tensor> sel) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    want(t, "t"); want(y_traj, "y_traj"); want(grad_y, "grad_y");
+    const int64_t T = t.numel();
+    TORCH_CHECK(y_traj.dim() == 3 && y_traj.size(0) == T && y_traj.size(1) == pr.B() && y_traj.size(2) == 3 * pr.N(),
+                "odecol: y_traj must be (T, B, 3N)");
+    TORCH_CHECK(grad_y.dim() == 3 && grad_y.size(0) == T && grad_y.size(1) == pr.B(), "odecol: grad_y must be (T, B, G)");
+    const int64_t G = grad_y.size(2);
+    const int32_t* selp = nullptr;
+    if (sel.has_value()) {
+        want(*sel, "sel", torch::kInt32);
+        TORCH_CHECK(sel->numel() == G, "odecol: sel must have G entries");
+        selp = sel->data_ptr<int32_t>();
+    } else {
+        TORCH_CHECK(G == 3 * pr.N(), "odecol: dense grad_y must have 3N components");
+    }
+    auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
+    auto gW = torch::empty_like(pr.W_aug);
+    auto ws = pr.workspace(ODECOL_OP_RK4_BWD, T);
+    check(odecol_rk4_bwd(&pr.p, t.data_ptr<float>(), (int32_t)T, y_traj.data_ptr<float>(), grad_y.data_ptr<float>(), selp,
+                         (int32_t)G, gy0.data_ptr<float>(), gW.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(),
+                         pr.stream()), "rk4_bwd");
+    return {gy0, gW};
+}
+
+std::vector<torch::Tensor> dopri5_fwd(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0, double rtol,
+                                      double atol, int64_t max_steps) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(t, "t");
+    const int64_t T = t.numel();
+    auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto na = torch::zeros({pr.B()}, pr.iopts()), nr = torch::zeros({pr.B()}, pr.iopts()), st = torch::zeros({pr.B()}, pr.iopts());
+    auto ws = pr.workspace(ODECOL_OP_DOPRI5_FWD, T);
+    check(odecol_dopri5_fwd(&pr.p, t.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), (float)rtol,
+                            (float)atol, (int32_t)std::min<int64_t>(max_steps, INT32_MAX), na.data_ptr<int32_t>(),
+                            nr.data_ptr<int32_t>(), st.data_ptr<int32_t>(), ws.data_ptr(), (size_t)ws.numel(), pr.stream()),
+          "dopri5_fwd");
+    return {y, na, nr, st};
+}
+
+int64_t em_num_steps(const torch::Tensor& ts_cpu, double dt) {
+    TORCH_CHECK(!ts_cpu.is_cuda() && ts_cpu.scalar_type() == torch::kFloat32 && ts_cpu.is_contiguous(),
+                "odecol: em_num_steps wants a contiguous float32 CPU tensor");
+    return odecol_em_num_steps(ts_cpu.data_ptr<float>(), (int32_t)ts_cpu.numel(), (float)dt);
+}
+
+std::vector<torch::Tensor> em_fwd(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y0,
+                                  std::optional<torch::Tensor> dW, int64_t seed, int64_t trial_offset, double dt,
+                                  bool adaptive, double rtol, double atol, double dt_min, int64_t save_steps) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(ts, "ts");
+    const int64_t T = ts.numel();
+    const float* dWp = nullptr;
+    if (dW.has_value()) {
+        want(*dW, "dW");
+        TORCH_CHECK(dW->dim() == 2 && dW->size(1) == pr.B(), "odecol: dW must be (n_steps, B)");
+        dWp = dW->data_ptr<float>();
+    }
+    auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto na = torch::zeros({pr.B()}, pr.iopts()), nr = torch::zeros({pr.B()}, pr.iopts()), st = torch::zeros({pr.B()}, pr.iopts());
+    torch::Tensor ysteps;
+    float* ysp = nullptr;
+    if (save_steps > 0) {
+        ysteps = torch::empty({save_steps + 1, pr.B(), 3 * pr.N()}, pr.fopts());
+        ysp = ysteps.data_ptr<float>();
+    } else {
+        ysteps = torch::empty({0}, pr.fopts());
+    }
+    auto ws = pr.workspace(ODECOL_OP_EM_FWD, T);
+    check(odecol_em_fwd(&pr.p, ts.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), dWp,
+                        (uint64_t)seed, trial_offset, (float)dt, adaptive ? 1 : 0, (float)rtol, (float)atol, (float)dt_min,
+                        na.data_ptr<int32_t>(), nr.data_ptr<int32_t>(), st.data_ptr<int32_t>(), ysp, ws.data_ptr(),
+                        (size_t)ws.numel(), pr.stream()), "em_fwd");
+    return {y, na, nr, st, ysteps};
+}
+
+std::vector<torch::Tensor> em_bwd(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y_steps,
+                                  const torch::Tensor& grad_y, std::optional<torch::Tensor> sel, double dt) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    want(ts, "ts"); want(y_steps, "y_steps"); want(grad_y, "grad_y");
+    const int64_t T = ts.numel();
+    TORCH_CHECK(y_steps.dim() == 3 && y_steps.size(1) == pr.B() && y_steps.size(2) == 3 * pr.N(), "odecol: y_steps must be (n_steps+1, B, 3N)");
+    const int64_t n_steps = y_steps.size(0) - 1;
+    TORCH_CHECK(grad_y.dim() == 3 && grad_y.size(0) == T && grad_y.size(1) == pr.B(), "odecol: grad_y must be (T, B, G)");
+    const int64_t G = grad_y.size(2);
+    const int32_t* selp = nullptr;
+    if (sel.has_value()) {
+        want(*sel, "sel", torch::kInt32);
+        TORCH_CHECK(sel->numel() == G, "odecol: sel must have G entries");
+        selp = sel->data_ptr<int32_t>();
+    } else {
+        TORCH_CHECK(G == 3 * pr.N(), "odecol: dense grad_y must have 3N components");
+    }
+    auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
+    auto gW = torch::empty_like(pr.W_aug);
+    auto ws = pr.workspace(ODECOL_OP_EM_BWD, T, n_steps);
+    check(odecol_em_bwd(&pr.p, ts.data_ptr<float>(), (int32_t)T, y_steps.data_ptr<float>(), n_steps, grad_y.data_ptr<float>(),
+                        selp, (int32_t)G, (float)dt, gy0.data_ptr<float>(), gW.data_ptr<float>(), ws.data_ptr(),
+                        (size_t)ws.numel(), pr.stream()), "em_bwd");
+    return {gy0, gW};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "odecol: PyTorch binding of the sm_100a fused column-ODE integrator (C ABI in include/odecol.h)";
+    py::class_<Problem>(m, "Problem")
+        .def(py::init<torch::Tensor, torch::Tensor, std::optional<torch::Tensor>, torch::Tensor, torch::Tensor, int64_t,
+                      int64_t, double, double, double, double, int64_t>(),
+             py::arg("W_aug"), py::arg("kappa"), py::arg("sigma"), py::arg("knot_t"), py::arg("knot_u"), py::arg("n_in"),
+             py::arg("B"), py::arg("tau_s"), py::arg("tau_m"), py::arg("tau_a"), py::arg("resistance"), py::arg("flags") = 0)
+        .def_property_readonly("N", &Problem::N)
+        .def_property_readonly("B", &Problem::B)
+        .def("kernel_family", [](const Problem& pr, int op) { return odecol_kernel_family(&pr.p, op); })
+        .def("workspace_bytes", [](const Problem& pr, int op, int64_t T, int64_t n_steps) {
+            return (int64_t)odecol_workspace_bytes(&pr.p, op, (int32_t)T, n_steps);
+        });
+    m.def("abi_version", &odecol_abi_version);
+    m.def("strerror", [](int c) { return std::string(odecol_strerror(c)); });
+    m.def("last_launch_count", &odecol_last_launch_count);
+    m.def("rhs", &rhs);
+    m.def("rk4_fwd", &rk4_fwd);
+    m.def("rk4_bwd", &rk4_bwd);
+    m.def("dopri5_fwd", &dopri5_fwd);
+    m.def("em_num_steps", &em_num_steps);
+    m.def("em_fwd", &em_fwd);
+    m.def("em_bwd", &em_bwd);
+    m.attr("OP_RHS") = (int)ODECOL_OP_RHS;
+    m.attr("OP_RK4_FWD") = (int)ODECOL_OP_RK4_FWD;
+    m.attr("OP_RK4_BWD") = (int)ODECOL_OP_RK4_BWD;
+    m.attr("OP_DOPRI5_FWD") = (int)ODECOL_OP_DOPRI5_FWD;
+    m.attr("OP_EM_FWD") = (int)ODECOL_OP_EM_FWD;
+    m.attr("OP_EM_BWD") = (int)ODECOL_OP_EM_BWD;
+    m.attr("FLAG_FORCE_STAGED") = (int)ODECOL_FLAG_FORCE_STAGED;
+}

@@ -1,0 +1,217 @@
+"""odeint / odeint_adjoint / sdeint-compatible entry points that run FUSED on the GPU.
+
+They keep the call shapes of the third-party functions the reference uses
+
+    torchdiffeq.odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None)
+        call sites: reference scripts/xor_ode.py:114, scripts/parity_ode.py:233, scripts/plotting_results.py:131
+    torchsde.sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5, atol=1e-4, dt_min=1e-5,
+                    options=None, names=None, ...)
+        call sites: reference scripts/wta_ode.py:174,200
+
+but ``func`` / ``sde`` must be one of this package's column networks (anything with ``export_linear_form()`` and
+``stimulus_channels()``): the whole time loop then runs inside the sm_100a kernels behind ``include/odecol.h``.
+There is no generic-function path, no CPU path and no multi-backend dispatch -- other inputs raise.
+
+Batching: where the reference loops over trials with B = 1 solves, pass y0 of shape (B, 3N) and a stimulus with a
+leading trial dimension; the result is (T, B, 3N).
+
+Gradients: ``method='rk4'`` and fixed-step Euler-Maruyama are differentiable w.r.t. every module parameter that enters
+W_aug = [W | U | bias] and w.r.t. y0, through hand-written exact discrete adjoints (what ``loss.backward()`` through
+the reference's unrolled solver computes).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence, Union
+
+import torch
+
+from . import _native
+from .stimulus import compress_knots
+
+_DEFAULT_MAX_STEPS = 4_000_000
+
+
+def _require_linear_form(func):
+    if not (hasattr(func, "export_linear_form") and hasattr(func, "stimulus_channels")):
+        raise TypeError(
+            "odecol solvers integrate column networks exposing export_linear_form()/stimulus_channels(); got "
+            f"{type(func).__name__}. There is no generic-function or CPU fallback.")
+
+
+class _Setup:
+    """Everything a solve needs besides the differentiable tensors (kept out of autograd's way)."""
+
+    def __init__(self, func, y0: torch.Tensor, t: torch.Tensor, family: Optional[str]):
+        _require_linear_form(func)
+        if not y0.is_cuda:
+            raise RuntimeError("odecol: y0 must live on a CUDA device (no CPU path); move the module and state to cuda")
+        if y0.dim() != 2:
+            raise ValueError("odecol: y0 must be (B, 3N)")
+        self.ext = _native.ext()
+        dev = y0.device
+        self.lf = func.export_linear_form()
+        if y0.shape[1] != 3 * self.lf.N:
+            raise ValueError(f"odecol: y0 has {y0.shape[1]} components, the network needs {3 * self.lf.N}")
+        self.B = y0.shape[0]
+        self.t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        table = func.stimulus_channels().detach().to(device=dev, dtype=torch.float32)
+        if table.shape[0] not in (1, self.B):
+            raise ValueError(f"odecol: stimulus has {table.shape[0]} trials, y0 has {self.B}")
+        time_vec = func.time_vec.detach().to(device=dev, dtype=torch.float32)
+        self.knot_t, self.knot_u = compress_knots(time_vec, table)
+        self.flags = self.ext.FLAG_FORCE_STAGED if family == "staged" else 0
+        self.kappa = self.lf.kappa.detach().to(dev, torch.float32).contiguous()
+        self.sigma = self.lf.sigma.detach().to(dev, torch.float32).contiguous()
+
+    def problem(self, W_aug: torch.Tensor):
+        lf = self.lf
+        return self.ext.Problem(W_aug.detach().to(torch.float32).contiguous(), self.kappa, self.sigma, self.knot_t,
+                                self.knot_u, lf.n_in, self.B, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, self.flags)
+
+
+def _sel_tensors(components, N3, device):
+    if components is None:
+        return None, None
+    idx = torch.as_tensor(components, dtype=torch.int64, device=device).flatten()
+    if idx.numel() == 0 or int(idx.min()) < 0 or int(idx.max()) >= N3:
+        raise ValueError("odecol: components out of range")
+    return idx, idx.to(torch.int32).contiguous()
+
+
+class _RK4Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, W_aug, setup: _Setup, sel_long, sel_i32):
+        prob = setup.problem(W_aug)
+        y = setup.ext.rk4_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), 1)
+        ctx.setup, ctx.prob, ctx.sel_i32 = setup, prob, sel_i32
+        ctx.save_for_backward(y)
+        return y if sel_long is None else y.index_select(2, sel_long)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (y,) = ctx.saved_tensors
+        gy0, gW = ctx.setup.ext.rk4_bwd(ctx.prob, ctx.setup.t, y, grad.to(torch.float32).contiguous(), ctx.sel_i32)
+        return gy0, gW, None, None, None
+
+
+class _EMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, W_aug, setup: _Setup, dW, seed, trial_offset, dt, n_steps, sel_long, sel_i32, stats):
+        prob = setup.problem(W_aug)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        y, na, nr, st, ysteps = setup.ext.em_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), dW, seed,
+                                                 trial_offset, dt, False, 0.0, 0.0, 0.0, n_steps if need_grad else 0)
+        if stats is not None:
+            stats.update(n_accept=na, n_reject=nr, status=st)
+        ctx.setup, ctx.prob, ctx.sel_i32, ctx.dt = setup, prob, sel_i32, dt
+        ctx.save_for_backward(ysteps)
+        return y if sel_long is None else y.index_select(2, sel_long)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ysteps,) = ctx.saved_tensors
+        gy0, gW = ctx.setup.ext.em_bwd(ctx.prob, ctx.setup.t, ysteps, grad.to(torch.float32).contiguous(), ctx.sel_i32, ctx.dt)
+        return (gy0, gW) + (None,) * 9
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+           components=None, stats: Optional[Dict] = None):
+    """Fused replacement of ``torchdiffeq.odeint``.  ``method``: None/'dopri5' (adaptive, per-trial control, the
+    default the reference scripts get) or 'rk4' (3/8 rule on the grid ``t``).  Extras beyond torchdiffeq:
+    ``components`` restricts the returned trajectory to those state components (T, B, len(components));
+    ``stats`` (a dict) receives per-trial n_accept / n_reject / status tensors; ``options['family']='staged'`` forces
+    the global-state kernel family, ``options['max_num_steps']`` bounds dopri5."""
+    if event_fn is not None:
+        raise NotImplementedError("odecol: event handling is not part of the fused path")
+    options = dict(options or {})
+    method = method or "dopri5"
+    setup = _Setup(func, y0, t, options.pop("family", None))
+    sel_long, sel_i32 = _sel_tensors(components, 3 * setup.lf.N, y0.device)
+    if method == "rk4":
+        if options.get("step_size") is not None:
+            raise NotImplementedError("odecol rk4 integrates on the grid `t` (the reference passes no step_size)")
+        return _RK4Function.apply(y0, setup.lf.W_aug, setup, sel_long, sel_i32)
+    if method == "dopri5":
+        if torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad):
+            from .dopri5_adjoint import dopri5_with_grad   # discrete adjoint through the accepted steps
+            return dopri5_with_grad(setup, y0, rtol, atol, options, sel_long, sel_i32, stats)
+        prob = setup.problem(setup.lf.W_aug)
+        y, na, nr, st = setup.ext.dopri5_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), float(rtol),
+                                             float(atol), int(options.get("max_num_steps", _DEFAULT_MAX_STEPS)))
+        if stats is not None:
+            stats.update(n_accept=na, n_reject=nr, status=st)
+        return y if sel_long is None else y.index_select(2, sel_long)
+    raise ValueError(f"odecol: method {method!r} is not fused (have 'rk4', 'dopri5')")
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None, components=None, stats=None):
+    """Signature of ``torchdiffeq.odeint_adjoint`` (imported but never called by the reference).  The fused solvers
+    already run their backward pass inside a kernel from O(T) saved states, so this is ``odeint``; the adjoint_*
+    arguments are accepted for compatibility."""
+    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options, event_fn=event_fn,
+                  components=components, stats=stats)
+
+
+def _tabulate_bm(bm, ts_cpu: torch.Tensor, dt: float, B: int, device) -> torch.Tensor:
+    """Increments of a torchsde-style Brownian object along the fixed-step schedule (float32 time loop)."""
+    out = []
+    curr = ts_cpu[0].clone()
+    t_end = ts_cpu[-1]
+    for out_t in ts_cpu[1:]:
+        while curr < out_t:
+            nxt = torch.minimum(curr + dt, t_end)
+            w = torch.as_tensor(bm(curr, nxt), dtype=torch.float32).reshape(-1)
+            out.append(w.expand(B) if w.numel() == 1 else w)
+            curr = nxt
+    return torch.stack(out).to(device).contiguous()
+
+
+def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5, atol=1e-4, dt_min=1e-5,
+           options=None, names=None, logqp=False, extra=False, extra_solver_state=None,
+           seed: Optional[int] = None, trial_offset: int = 0, components=None, stats: Optional[Dict] = None):
+    """Fused replacement of ``torchsde.sdeint`` for scalar-noise Ito SDEs integrated with Euler-Maruyama.
+
+    ``bm``: None -> in-kernel Philox4x32-10 noise keyed by (seed, trial_offset + trial index); a tensor (n_steps, B)
+    or (n_steps, B, 1) of increments in step order (bit-parity mode, fixed step); or a torchsde-style callable
+    ``bm(t0, t1)``, tabulated along the step schedule.  ``adaptive=True`` uses step doubling with torchsde's controller,
+    per trial, on a virtual Brownian tree (Philox only).  ``method='srk'`` (what the reference scripts name) is not
+    fused yet."""
+    if logqp or extra or extra_solver_state is not None:
+        raise NotImplementedError("odecol: logqp / extra solver state are not part of the fused path")
+    method = method or "euler"
+    if method != "euler":
+        raise NotImplementedError(f"odecol: sdeint method {method!r} is not fused (have 'euler'); see DESIGN.md, next rows")
+    if getattr(sde, "noise_type", "scalar") != "scalar" or getattr(sde, "sde_type", "ito") != "ito":
+        raise ValueError("odecol: only scalar-noise Ito SDEs (what the reference declares) are supported")
+    options = dict(options or {})
+    setup = _Setup(sde, y0, ts, options.pop("family", None))
+    sel_long, sel_i32 = _sel_tensors(components, 3 * setup.lf.N, y0.device)
+    ext = setup.ext
+    if seed is None:
+        seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+    dt = float(dt)
+    if adaptive:
+        if bm is not None:
+            raise NotImplementedError("odecol: adaptive stepping draws from the in-kernel Brownian tree; pass bm=None")
+        prob = setup.problem(setup.lf.W_aug)
+        y, na, nr, st, _ = ext.em_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), None, seed,
+                                      int(trial_offset), dt, True, float(rtol), float(atol), float(dt_min), 0)
+        if stats is not None:
+            stats.update(n_accept=na, n_reject=nr, status=st)
+        return y if sel_long is None else y.index_select(2, sel_long)
+    ts_cpu = setup.t.cpu()
+    n_steps = int(ext.em_num_steps(ts_cpu, dt))
+    dW = None
+    if bm is not None:
+        if torch.is_tensor(bm):
+            dW = bm.detach().to(y0.device, torch.float32).reshape(bm.shape[0], -1)
+            if dW.shape[1] == 1 and setup.B > 1:
+                dW = dW.expand(-1, setup.B)
+            dW = dW.contiguous()
+        else:
+            dW = _tabulate_bm(bm, ts_cpu, dt, setup.B, y0.device)
+        if dW.shape != (n_steps, setup.B):
+            raise ValueError(f"odecol: need Brownian increments of shape ({n_steps}, {setup.B}), got {tuple(dW.shape)}")
+    return _EMFunction.apply(y0, setup.lf.W_aug, setup, dW, seed, int(trial_offset), dt, n_steps, sel_long, sel_i32, stats)

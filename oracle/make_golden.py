@@ -64,6 +64,7 @@ def make_wta(cc, ru, cfg):
     out = {}
     ys, ts, f = _rhs_samples(net, tv, 16, gen)
     out.update(rhs_y=_np(ys), rhs_t=_np(ts), rhs_f=_np(f), rhs_g=_np(net.diffusion(ts[0], ys[:1])))
+    out.update(orig_weights=extract_orig_weights())
     out.update(recurrent_weights=_np(net.recurrent_weights), feedforward_weights=_np(net.feedforward_weights),
                background_weights=_np(net.background_weights), adaptation_strength=_np(net.adaptation_strength),
                lat_in_mask=_np(net.lat_in_mask), time_vec=_np(tv), stim=_np(stim))
@@ -236,7 +237,27 @@ def make_parity(cc, ru, cfg):
     return out
 
 
+def extract_orig_weights() -> np.ndarray:
+    """The one numeric fixture the reference holds for this path: the hard-coded 16x16 ``orig_weights`` literal of
+    scripts/plotting_results.py:36-99 (units are 1000x today's; six entries are stale).  Parsed
+    from the source text (the script itself cannot be imported: matplotlib is missing)."""
+    import ast
+    import re
+    src = open(os.path.join(REF, "scripts", "plotting_results.py")).read()
+    m = re.search(r"orig_weights\s*=\s*torch\.tensor\((\[\[.*?\]\])\)", src, flags=re.S)
+    mat = np.asarray(ast.literal_eval(m.group(1)), dtype=np.float64)
+    assert mat.shape == (16, 16)
+    return mat
+
+
 def main():
+    if "--orig-weights-only" in sys.argv:      # cheap refresh of one key without re-running the solvers
+        path = os.path.join(OUT, "wta.npz")
+        data = dict(np.load(path))
+        data["orig_weights"] = extract_orig_weights()
+        np.savez_compressed(path, **data)
+        print("updated", path)
+        return
     cc, ru = _import_reference()
     cfg = ru.load_config(os.path.join(REF, "config", "model.toml"))
     os.makedirs(OUT, exist_ok=True)

@@ -1,0 +1,154 @@
+"""Host side of the boundary on the CPU: drop-in modules (names, shapes, seed-for-seed initial parameters), their
+torch forward against the reference's golden RHS, the linear form against the oracle's, knot compression."""
+import io
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import odecol
+from oracle import rhs as orhs
+from helpers import PARITY_DICT, XOR_DICT, oracle_form, product_network, stim_table
+
+NAMES = ("wta", "xor", "parity")
+
+
+def test_seed_for_seed_initial_parameters(cfg, golden):
+    torch.manual_seed(0)
+    w = odecol.ColumnAreaWTA(cfg, "mt")
+    assert np.array_equal(w.recurrent_weights.detach().numpy(), golden["wta"]["recurrent_weights"])
+    torch.manual_seed(0)
+    x = odecol.ColumnNetworkXOR(cfg, XOR_DICT)
+    for a in "01":
+        for i in range(2):
+            assert np.array_equal(x.feedforward_target_weights[a][i].detach().numpy(), golden["xor"][f"ffw_{a}_{i}"])
+    torch.manual_seed(0)
+    p = odecol.ColumnNetwork(cfg, PARITY_DICT, torch.device("cpu"))
+    g = golden["parity"]
+    for k in "012":
+        assert np.array_equal(p.areas[k].lateral_weights.detach().numpy(), g[f"lateral_{k}"])
+        assert np.array_equal(p.areas[k].lateral_mask.numpy(), g[f"lateral_mask_{k}"])
+    for k in "12":
+        assert np.array_equal(p.areas[k].feedforward_weights.detach().numpy(), g[f"feedforward_{k}"])
+        assert np.array_equal(p.areas[k].feedforward_mask.numpy(), g[f"feedforward_mask_{k}"])
+    assert np.array_equal(p.areas["0"].input_weights.detach().numpy(), g["input_weights"])
+    assert np.array_equal(p.areas["0"].input_mask.numpy(), g["input_mask"])
+    assert np.array_equal(p.output_weights.detach().numpy(), g["output_weights"])
+
+
+def test_parameter_names_match_the_reference(cfg):
+    torch.manual_seed(1)
+    assert [n for n, _ in odecol.ColumnAreaWTA(cfg, "mt").named_parameters()] == ["recurrent_weights"]
+    x = odecol.ColumnNetworkXOR(cfg, XOR_DICT)
+    assert [n for n, _ in x.named_parameters()] == [f"feedforward_target_weights.{a}.{i}" for a in "01" for i in "01"]
+    p = odecol.ColumnNetwork(cfg, PARITY_DICT, torch.device("cpu"))
+    names = {n: q.requires_grad for n, q in p.named_parameters()}
+    assert names == {"output_weights": True, "areas.0.lateral_weights": True, "areas.0.input_weights": True,
+                     "areas.1.lateral_weights": True, "areas.1.feedforward_weights": True,
+                     "areas.2.lateral_weights": False, "areas.2.feedforward_weights": True}
+    for attr in ("lat_in_mask", "output_weights", "noise_type", "sde_type", "set_stim", "set_time_vec"):
+        assert hasattr(odecol.ColumnAreaWTA(cfg, "mt"), attr)
+    assert x.network_as_area.num_populations == 24 and p.nr_areas == 3 and p.output_scale == 1.0
+    assert x.noise_type == "scalar" and p.sde_type == "ito"
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_forward_and_diffusion_match_reference(name, cfg, golden):
+    g = golden[name]
+    net = product_network(name, cfg, g)
+    net.stim = torch.tensor(g["stim"] if name == "wta" else g["rhs_stim"])
+    ys, ts, f = (torch.tensor(g[k]) for k in ("rhs_y", "rhs_t", "rhs_f"))
+    out = torch.stack([net.forward(ts[i], ys[i:i + 1])[0] for i in range(len(ts))])
+    assert out.shape == f.shape
+    assert float((out - f).abs().max()) <= 2e-7 * float(f.abs().max())
+    gd = net.diffusion(ts[0], ys[:1])
+    assert gd.shape == (1, ys.shape[1], 1) and np.array_equal(gd.numpy(), g["rhs_g"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_linear_form_equals_oracle(name, cfg, golden):
+    g = golden[name]
+    net = product_network(name, cfg, g)
+    lf, lo = net.export_linear_form(), oracle_form(name, cfg, g)
+    N, n_in = lo.n, lo.n_in
+    Wa = lf.W_aug.detach().numpy()
+    assert lf.n_in == n_in and Wa.shape[1] % 4 == 0 and Wa.shape[1] >= N + n_in + 1
+    assert np.array_equal(Wa[:, :N], lo.W) and np.array_equal(Wa[:, N:N + n_in], lo.U)
+    assert np.array_equal(Wa[:, N + n_in], lo.bias) and not Wa[:, N + n_in + 1:].any()
+    assert np.array_equal(lf.kappa.numpy(), lo.kappa) and np.array_equal(lf.sigma.numpy(), lo.sigma)
+    assert (lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance) == (lo.tau_s, lo.tau_m, lo.tau_a, lo.resistance)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_linear_form_is_differentiable_in_the_reference_parameters(name, cfg, golden):
+    net = product_network(name, cfg, golden[name])
+    lf = net.export_linear_form()
+    lf.W_aug.sum().backward()
+    got = {n for n, p in net.named_parameters() if p.grad is not None and p.grad.abs().sum() > 0}
+    want = {n for n, p in net.named_parameters() if p.requires_grad and n != "output_weights"}
+    assert got == want
+
+
+def test_batched_forward_equals_per_trial_forward(cfg, golden):
+    g = golden["xor"]
+    net = product_network("xor", cfg, g)
+    stims = torch.tensor(g["stims"])                      # (4,T,2,16)
+    y = torch.tensor(g["rhs_y"][:4])
+    t = torch.tensor(0.7312)
+    net.stim = stims
+    batched = net.forward(t, y)
+    for b in range(4):
+        net.stim = stims[b]
+        assert torch.allclose(batched[b], net.forward(t, y[b:b + 1])[0], rtol=1e-6, atol=1e-3)
+
+
+def test_modules_pickle(cfg, golden):
+    for name in NAMES:
+        net = product_network(name, cfg, golden[name])
+        clone = pickle.loads(pickle.dumps(net))
+        for (n1, p1), (n2, p2) in zip(net.named_parameters(), clone.named_parameters()):
+            assert n1 == n2 and torch.equal(p1, p2)
+
+
+def test_compress_knots_is_exact(cfg, golden):
+    from oracle.rhs import interp_knots
+    for name in NAMES:
+        g = golden[name]
+        tv = torch.tensor(g["time_vec"])
+        table = stim_table(name, g["stims"] if name != "wta" else g["stim"]).float()
+        kt, ku = odecol.compress_knots(tv, table)
+        assert 2 <= len(kt) <= 8 and ku.shape == (table.shape[0], len(kt), table.shape[2])
+        gen = torch.Generator().manual_seed(3)
+        probe = torch.cat((tv[::37], tv[len(tv) // 2 - 2:len(tv) // 2 + 2], tv[len(tv) // 3 - 2:len(tv) // 3 + 2],
+                           torch.rand(300, generator=gen) * float(tv[-1]) * 1.2 - 0.1 * float(tv[-1])))
+        for t in probe:
+            assert torch.equal(interp_knots(t, tv, table), interp_knots(t, kt, ku))
+    # a smooth stimulus keeps every knot
+    tv = torch.linspace(0, 1, 50)
+    kt, ku = odecol.compress_knots(tv, torch.sin(tv)[None, :, None])
+    assert len(kt) == 50
+
+
+def test_solvers_refuse_cpu_and_foreign_functions(cfg, golden):
+    net = product_network("wta", cfg, golden["wta"])
+    net.stim = torch.tensor(golden["wta"]["stim"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        odecol.odeint(net, torch.zeros(1, 48), net.time_vec, method="rk4")
+    with pytest.raises(TypeError, match="fallback"):
+        odecol.odeint(lambda t, y: -y, torch.zeros(1, 48), net.time_vec)
+    with pytest.raises(NotImplementedError):
+        odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="srk")
+
+
+def test_synthetic_sheet_matches_oracle_structure(cfg):
+    sheet = odecol.SyntheticColumnSheet(cfg, 4, seed=0)
+    lf = sheet.export_linear_form()
+    assert lf.N == 32 and lf.n_in == 4
+    W = lf.W_aug.detach()[:, :32]
+    from oracle.column_model import area_constants
+    one = area_constants(cfg, "mt", 1)
+    for c in range(4):
+        assert np.array_equal(W[8 * c:8 * c + 8, 8 * c:8 * c + 8].numpy(), one.recurrent_weights)
+    off = W[0:8, 8:16]
+    assert (off[0, 1] < 0) and (off[4, 5] < 0) and int((off != 0).sum()) == 2
