@@ -11,77 +11,9 @@
 //
 // Replaces the Python stepping loop of torchdiffeq's rk4 around ColumnNetwork.forward for networks beyond the
 // reference's sizes (BASELINE.json configs 4 and 5); same arithmetic as family S.
-#include "odecol_common.cuh"
+#include "stage_common.cuh"
 
 namespace odecol {
-
-constexpr float kOneThirdL = 0.3333333333333333f;
-constexpr float kTwoThirdsL = 0.6666666666666666f;
-
-constexpr int TM = 128, TN = 128, TK = 16;     // CTA tile: TM rows of W (populations) x TN trials x TK
-constexpr int kGemmThreads = 256;
-
-static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-// ---------------------------------------------------------------------------------------------------------------
-// contraction core: acc[8][8] per thread.  A rows = populations (ldA floats, K contiguous), B rows = trials.
-// thread (tx = tid % 16, ty = tid / 16): rows {4tx..4tx+3} u {64+4tx..}, cols {4ty..4ty+3} u {64+4ty..}
-// ---------------------------------------------------------------------------------------------------------------
-struct GemmSmem {
-    float A[2][TK][TM];
-    float B[2][TK][TN];
-};
-
-ODECOL_DEVINL void gemm_nt_core(const float* __restrict__ Ag, int ldA, const float* __restrict__ Bg, int ldB, int Kdim,
-                                GemmSmem& sm, float (&acc)[8][8]) {
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    // loader mapping: float4 index f = tid + 256*m (m = 0,1): row = f % 128, kq = f / 128
-    const int lrow = tid & 127, lkq = tid >> 7;       // lkq in {0,1}; second float4 uses kq + 2
-    const float4* a_src0 = reinterpret_cast<const float4*>(Ag + (size_t)lrow * ldA) + lkq;
-    const float4* b_src0 = reinterpret_cast<const float4*>(Bg + (size_t)lrow * ldB) + lkq;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float4 ra0 = __ldg(a_src0), ra1 = __ldg(a_src0 + 2), rb0 = __ldg(b_src0), rb1 = __ldg(b_src0 + 2);
-    const int nk = Kdim / TK;
-    int buf = 0;
-    auto stash = [&](int bf) {
-        const int k0 = 4 * lkq, k1 = 4 * (lkq + 2);
-        sm.A[bf][k0 + 0][lrow] = ra0.x; sm.A[bf][k0 + 1][lrow] = ra0.y; sm.A[bf][k0 + 2][lrow] = ra0.z; sm.A[bf][k0 + 3][lrow] = ra0.w;
-        sm.A[bf][k1 + 0][lrow] = ra1.x; sm.A[bf][k1 + 1][lrow] = ra1.y; sm.A[bf][k1 + 2][lrow] = ra1.z; sm.A[bf][k1 + 3][lrow] = ra1.w;
-        sm.B[bf][k0 + 0][lrow] = rb0.x; sm.B[bf][k0 + 1][lrow] = rb0.y; sm.B[bf][k0 + 2][lrow] = rb0.z; sm.B[bf][k0 + 3][lrow] = rb0.w;
-        sm.B[bf][k1 + 0][lrow] = rb1.x; sm.B[bf][k1 + 1][lrow] = rb1.y; sm.B[bf][k1 + 2][lrow] = rb1.z; sm.B[bf][k1 + 3][lrow] = rb1.w;
-    };
-    stash(0);
-    __syncthreads();
-    for (int kt = 0; kt < nk; ++kt) {
-        if (kt + 1 < nk) {
-            const int off = (kt + 1) * (TK / 4);
-            ra0 = __ldg(a_src0 + off); ra1 = __ldg(a_src0 + off + 2);
-            rb0 = __ldg(b_src0 + off); rb1 = __ldg(b_src0 + off + 2);
-        }
-#pragma unroll
-        for (int k = 0; k < TK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&sm.A[buf][k][4 * tx]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&sm.A[buf][k][64 + 4 * tx]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&sm.B[buf][k][4 * ty]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&sm.B[buf][k][64 + 4 * ty]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        if (kt + 1 < nk) {
-            stash(buf ^ 1);
-            __syncthreads();
-            buf ^= 1;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward stage epilogues
@@ -101,14 +33,6 @@ struct FwdStageArgs {
     int n;                 // step index: t0 = t[n], t1 = t[n+1]
     int KPa;
 };
-
-ODECOL_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-ODECOL_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-
-// one state component of 4 consecutive populations
-struct C4 { float v[4]; };
-ODECOL_DEVINL C4 ldc(const float* p) { const float4 q = ld4(p); return {{q.x, q.y, q.z, q.w}}; }
-ODECOL_DEVINL void stc(float* p, const C4& c) { st4(p, make_float4(c.v[0], c.v[1], c.v[2], c.v[3])); }
 
 template <int S>
 ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const float (&tot)[4], float dt) {

@@ -250,7 +250,75 @@ def extract_orig_weights() -> np.ndarray:
     return mat
 
 
+def add_fp64_gradients():
+    """float64 'truth' for the three gradient fixtures: the oracle's unified form (validated against the reference's
+    forward to 1e-7) integrated and differentiated in float64 with the scripts' losses.  Two float32 evaluations of
+    these gradients (the reference's autograd and any other summation order) differ from each other by up to 5e-4
+    relative on the ill-conditioned final-time XOR loss, so the tests measure the CUDA result against this truth and
+    against the reference's own float32 error."""
+    import tomllib
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    from oracle import column_model as cm, rhs as orhs, solvers
+    cfg = tomllib.load(open(os.path.join(os.path.dirname(os.path.dirname(OUT)), "config", "model.toml"), "rb"))
+    f64 = torch.float64
+
+    def solve(lf, tv, table, N):
+        ode = orhs.UnifiedColumnODE(lf, tv, table, dtype=f64, requires_grad=True)
+        y = solvers.odeint_rk4(ode, torch.zeros(table.shape[0], 3 * N, dtype=f64), torch.tensor(tv, dtype=f64))
+        return ode, y
+
+    # wta
+    path = os.path.join(OUT, "wta.npz")
+    g = dict(np.load(path))
+    lf = cm.wta_linear_form(cfg, g["recurrent_weights"])
+    ode, y = solve(lf, g["time_vec"], g["stim"][None], 16)
+    r = orhs.phi(y[:, 0, :16] - y[:, 0, 16:32])
+    both = torch.stack((r[:, 0], r[:, 8]), dim=1)[None]
+    loss = torch.nn.functional.smooth_l1_loss(both, torch.tensor(g["rk4_target"], dtype=f64), beta=1.0)
+    loss.backward()
+    g["rk4_grad64_recurrent_weights"] = _np(ode.W.grad)
+    np.savez_compressed(path, **g)
+    print("wta fp64 loss", float(loss), "vs fp32", float(g["rk4_loss"]))
+    # xor
+    path = os.path.join(OUT, "xor.npz")
+    g = dict(np.load(path))
+    lf = cm.xor_linear_form(cfg, [[g["ffw_0_0"], g["ffw_0_1"]], [g["ffw_1_0"], g["ffw_1_1"]]])
+    ode, y = solve(lf, g["time_vec"], g["stims"].reshape(4, 1000, 32), 24)
+    fc = orhs.phi(y[-1, :, 16:24] - y[-1, :, 40:48])[:, 0]
+    loss = torch.mean(abs(fc - torch.tensor([1.0, 1.0, 0.25, 0.25], dtype=f64)))
+    loss.backward()
+    for i in range(2):
+        g[f"rk4_grad64_ffw_0_{i}"] = _np(torch.diagonal(ode.U.grad[:16, 16 * i:16 * (i + 1)]))
+        g[f"rk4_grad64_ffw_1_{i}"] = _np(10.0 * ode.W.grad[16:24, 8 * i])
+    np.savez_compressed(path, **g)
+    print("xor fp64 loss", float(loss), "vs fp32", float(g["rk4_loss"]))
+    # parity
+    path = os.path.join(OUT, "parity.npz")
+    g = dict(np.load(path))
+    lf = cm.parity_linear_form(cfg, [g[f"lateral_{k}"] for k in range(3)], {1: g["feedforward_1"], 2: g["feedforward_2"]},
+                               g["input_weights"])
+    ode, y = solve(lf, g["time_vec"], g["stims"], 104)
+    N = 104
+    r = orhs.phi(y[-100:, :, N - 8:N] - y[-100:, :, 2 * N - 8:2 * N])
+    ow = torch.tensor(g["output_weights"], dtype=f64, requires_grad=True)
+    summed = (r.mean(0) * ow).sum(-1)
+    loss = torch.mean(abs(summed - torch.tensor(g["rk4_targets"], dtype=f64)))
+    loss.backward()
+    gW, gU = ode.W.grad, ode.U.grad
+    g["rk4_grad64_output_weights"] = _np(ow.grad)
+    g["rk4_grad64_areas_0_lateral_weights"] = _np(gW[0:64, 0:64])
+    g["rk4_grad64_areas_1_lateral_weights"] = _np(gW[64:96, 64:96])
+    g["rk4_grad64_areas_1_feedforward_weights"] = _np(gW[64:96, 0:64])
+    g["rk4_grad64_areas_2_feedforward_weights"] = _np(gW[96:104, 64:96])
+    g["rk4_grad64_areas_0_input_weights"] = _np(gU[0:64, :])
+    np.savez_compressed(path, **g)
+    print("parity fp64 loss", float(loss), "vs fp32", float(g["rk4_loss"]))
+
+
 def main():
+    if "--fp64-only" in sys.argv:
+        add_fp64_gradients()
+        return
     if "--orig-weights-only" in sys.argv:      # cheap refresh of one key without re-running the solvers
         path = os.path.join(OUT, "wta.npz")
         data = dict(np.load(path))
@@ -268,6 +336,7 @@ def main():
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in data.items()})
         print(f"  wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+    add_fp64_gradients()
 
 
 if __name__ == "__main__":
