@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: population-steps/s of the fused column-ODE solver, forward + adjoint (BASELINE.json metric).
+
+Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): synthetic 64-column network (N = 512 populations, dense
+W), rk4 (3/8 rule) on T = 1500 grid points (dt = 1e-4), 8192 trials per GPU (65,536 at 8 GPUs, weak scaling), per-trial
+three-phase stimuli, Huber loss on the L2/3e rates over the whole trajectory, exact discrete adjoint -> dW_aug, and for
+N > 1 one NCCL all-reduce of the parameter gradients per step.  One "step" = one such forward + adjoint pass.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU under torchrun)
+  python bench.py --impl reference [...]                          the CPU path (oracle port, all host threads), same metric
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how every field is computed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "population_steps_per_sec_fwd_adjoint"
+UNIT = "population-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--columns", type=int, default=64)
+    ap.add_argument("--trials-per-gpu", type=int, default=8192)
+    ap.add_argument("--time-points", type=int, default=1500)
+    ap.add_argument("--dt", type=float, default=1e-4)
+    ap.add_argument("--cpu-trials", type=int, default=1024, help="trials of the bounded CPU sample")
+    ap.add_argument("--cpu-time-points", type=int, default=41, help="grid points of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--family", default=None, help="force a kernel family (staged)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload construction (shared by both arms; everything seeded, nothing read from disk but config/model.toml)
+# ----------------------------------------------------------------------------------------------------------------------
+def make_stimulus(torch, B, columns, T, dt, trial0, device):
+    """Three-phase stimulus (off / on / off, thirds of the window) with per-trial, per-column amplitudes U(0, 30) Hz,
+    as knots; amplitudes are keyed by the GLOBAL trial index so that results do not depend on the sharding."""
+    import odecol
+    g = torch.Generator(device="cpu").manual_seed(1000 + trial0)
+    amp = torch.rand(B, columns, generator=g) * 30.0
+    t_end = T * dt
+    grid = t_end / (T - 1)
+    on, off = (T // 3) * grid, (2 * (T // 3)) * grid
+    kt, ku = odecol.step_knots(on, off, t_end, amp, grid)
+    return kt.to(device), ku.to(device), amp
+
+
+def loss_components(torch, columns):
+    n = 8 * columns
+    v = torch.arange(columns) * 8                       # L2/3e of every column: V and A components
+    return torch.cat((v, v + n)).to(torch.int64)
+
+
+def huber_on_rates(torch, odecol, sel_traj, target, columns):
+    rate = odecol.compute_firing_rate(sel_traj[:, :, :columns] - sel_traj[:, :, columns:])
+    return torch.nn.functional.smooth_l1_loss(rate, target.expand_as(rate), beta=1.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_sample(args, threads=None):
+    """The oracle port of the SAME workload on the host cores: batched unified form (torch CPU), restated rk4, autograd
+    backward.  Bounded sample: --cpu-trials trials x (--cpu-time-points - 1) steps of the N = 8*columns network."""
+    import torch
+    import odecol
+    from oracle import rhs as orhs, solvers as S
+    from oracle.column_model import LinearForm
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
+    sheet = odecol.SyntheticColumnSheet(cfg, args.columns, seed=0)
+    n = 8 * args.columns
+    lfp = sheet.export_linear_form()
+    Wa = lfp.W_aug.detach().numpy()
+    lf = LinearForm(W=Wa[:, :n], U=Wa[:, n:n + args.columns], bias=Wa[:, n + args.columns], kappa=lfp.kappa.numpy(),
+                    sigma=lfp.sigma.numpy(), tau_s=lfp.tau_s, tau_m=lfp.tau_m, tau_a=lfp.tau_a, resistance=lfp.resistance)
+    B, T = args.cpu_trials, args.cpu_time_points
+    kt, ku, _ = make_stimulus(torch, B, args.columns, args.time_points, args.dt, 0, "cpu")
+    tv = torch.linspace(0.0, args.time_points * args.dt, args.time_points)[:T]
+    sel = loss_components(torch, args.columns)
+    target = torch.full((1, 1, args.columns), 0.5)
+
+    def one_pass():
+        ode = orhs.UnifiedColumnODE(lf, kt, ku, requires_grad=True)
+        y = S.odeint_rk4(ode, torch.zeros(B, 3 * n), tv)
+        loss = huber_on_rates(torch, odecol, y[:, :, sel], target, args.columns)
+        loss.backward()
+        return float(loss.detach())
+
+    return one_pass, n * B * (T - 1), threads, f"{B} trials x {T - 1} rk4 steps, N={n}, forward + autograd backward"
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    one_pass, pop_steps, threads, sample = cpu_sample(args)
+    for _ in range(min(args.warmup, 1)):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+    el = time.perf_counter() - t0
+    value = pop_steps * args.steps / el
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "reference CPU path = oracle port (the reference is pure "
+                   "Python driving third-party solvers that are not installable offline); bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(args):
+    return (f"C4: synthetic {args.columns}-column network (N={8 * args.columns}), rk4 forward + discrete adjoint dW, "
+            f"T={args.time_points} grid points, {args.trials_per_gpu} trials/GPU (x{args.gpus} GPUs = {args.trials_per_gpu * args.gpus})")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import odecol
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ext = odecol._native.ext()
+
+    cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
+    columns, B, T = args.columns, args.trials_per_gpu, args.time_points
+    n = 8 * columns
+    net = odecol.SyntheticColumnSheet(cfg, columns, seed=0, device=dev)
+    params = [net.recurrent_weights, net.input_weights]
+    trial0 = rank * B
+    kt, ku, _ = make_stimulus(torch, B, columns, T, args.dt, trial0, "cpu")
+    tv = torch.linspace(0.0, T * args.dt, T, device=dev)
+    sel = loss_components(torch, columns).to(dev)
+    target = torch.full((1, 1, columns), 0.5, device=dev)
+    y0_host = torch.zeros(B, 3 * n).pin_memory()
+    ku_host = ku.pin_memory()
+    kt_dev = kt.to(dev)
+    options = {"family": args.family} if args.family else None
+    launches = {"n": 0}
+
+    def step(from_host: bool):
+        """One forward + adjoint pass through the public API.  from_host: inputs come from pinned host memory and the
+        loss + dW go back to the host inside the pass (the e2e leg)."""
+        if from_host:
+            y0 = y0_host.to(dev, non_blocking=True)
+            ku_d = ku_host.to(dev, non_blocking=True)
+        else:
+            y0, ku_d = step.y0_dev, step.ku_dev
+        net.set_knots(kt_dev, ku_d)
+        for p in params:
+            p.grad = None
+        traj = odecol.odeint(net, y0, tv, method="rk4", components=sel, options=options)
+        launches["n"] += ext.last_launch_count()
+        loss = huber_on_rates(torch, odecol, traj, target, columns)
+        loss.backward()
+        launches["n"] += ext.last_launch_count()
+        if world > 1:
+            odecol.distributed.allreduce_gradients(params)
+        if from_host:
+            return loss.detach().cpu(), net.recurrent_weights.grad.cpu()
+        return loss.detach(), None
+
+    step.y0_dev = y0_host.to(dev)
+    step.ku_dev = ku_host.to(dev)
+
+    def timed(n_steps, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(n_steps):
+            out = step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms) / 1e3, out
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    sec, (loss, _) = timed(args.steps, False)
+    n_launch = launches["n"]
+    clocks = sampler.stop() if rank == 0 else None
+    pop_steps_job = n * B * world * (T - 1)
+    value = pop_steps_job * args.steps / sec
+
+    # e2e leg: same pass, inputs from pinned host memory, loss and dW read back every step
+    step(True)
+    sec_e2e, (loss_h, gW_h) = timed(max(1, min(args.steps, 2)), True)
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_value = pop_steps_job * e2e_steps / sec_e2e
+    h2d = y0_host.numel() * 4 + ku_host.numel() * 4
+    d2h = gW_h.numel() * 4 + 4
+
+    # roofline of the dominant kernel (the fused forward stage contraction): forward-only solve, CUDA events around it
+    net.set_knots(kt_dev, step.ku_dev)
+    with torch.no_grad():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        odecol.odeint(net, step.y0_dev, tv, method="rk4", components=sel, options=options)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd_sec = e0.elapsed_time(e1) / 1e3
+        fwd_launches = ext.last_launch_count()
+    kaug = n + columns + 1
+    flops_per_launch = 2.0 * n * kaug * B                       # algorithmic: one W_aug . r_aug contraction of all trials
+    stage_launches = 4 * (T - 1)
+    avg_launch = fwd_sec / stage_launches
+    achieved_tflops = flops_per_launch / avg_launch / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    tensor_peak = bf16 / 2.0 / 3.0                               # TF32 dense = bf16/2; 3xTF32 split keeps fp32 accuracy
+    sm_max = peaks.get("sm_max_mhz", 1965.0)
+    ffma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    family = net_family(ext, odecol, net, step.y0_dev, tv, args)
+    roofline = {
+        "bound": "tensor", "kernel": "k_fwd_stage (fused W_aug.r_aug contraction + RK stage epilogue)",
+        "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tflops / tensor_peak,
+        "traffic": None,
+        "peak_source": ("measured bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split) from MEASURED_PEAKS.json" if peaks else
+                        "fallback 1.4 PFLOP/s bf16 sustained /6"),
+        "flops_per_launch": flops_per_launch, "avg_launch_ms": 1e3 * avg_launch, "kernel_family": family,
+        "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": achieved_tflops / ffma_peak,
+        "forward_only_pop_steps_per_sec": n * B * (T - 1) / fwd_sec,
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        one_pass, ps, threads, sample = cpu_sample(args)
+        one_pass()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            one_pass()
+        cpu = {"value": ps * reps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "populations": n, "trials_per_gpu": B, "time_points": T,
+                       "solver": "rk4 (3/8 rule) + exact discrete adjoint", "l2": "inputs (75 GB trajectory per pass) larger than L2",
+                       "parallelism": f"trial-parallel x{world}, allreduce(dW) per step" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": n_launch,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "loss": float(loss),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def net_family(ext, odecol, net, y0, tv, args):
+    lf = net.export_linear_form()
+    return "staged FP32-FFMA" if lf.N > 128 or args.family == "staged" else "persistent on-chip"
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,4 +81,30 @@ ODECOL_DEVINL C4 ldc(const float* p) { const float4 q = ld4(p); return {{q.x, q.
 ODECOL_DEVINL void stc(float* p, const C4& c) { st4(p, make_float4(c.v[0], c.v[1], c.v[2], c.v[3])); }
 
 
+// ---- forward stage launch arguments (stage_kernels.cu) ---------------------------------------------------------
+struct FwdStageArgs {
+    DevProblem p;
+    const float* Wp;       // [Np][KPa]
+    const float* Ra_cur;   // [Bp][KPa]
+    float* Ra_nxt;         // [Bp][KPa]
+    const float* y0;       // [B][3N] state at the start of the step
+    float* k1;             // [B][3N]
+    float* k2;
+    float* k3;
+    float* y1;             // [B][3N] state at the end of the step (stage 4)
+    float* y_out_row;      // optional second destination of y1 (trajectory row), may be NULL
+    float* DR_nxt;         // optional [B][N]: phi'(x) of the NEXT stage state (reverse sweep recompute)
+    const float* t;        // device time grid
+    int n;                 // step index: t0 = t[n], t1 = t[n+1]
+    int KPa;
+};
+
+// launchers defined in stage_kernels.cu (kernels cannot be launched across translation units)
+void launch_pad_weights(const float* W_aug, int N, int ld_w, int Kaug, float* Wp, int Np, int KPa, cudaStream_t s);
+void launch_pad_transpose(const float* W_aug, int N, int ld_w, float* WT, int Np, int NPk, cudaStream_t s);
+// Ra = r_aug(t_ptr[0], y) (+ phi' into DR if given); Ra_extra (optional) gets the constant-one column and zero padding
+void launch_init_operand(const DevProblem& p, const float* y, const float* t_ptr, float* Ra, float* Ra_extra, float* DR,
+                         int KPa, int Bp, cudaStream_t s);
+void launch_fwd_stage(int S, const FwdStageArgs& a, dim3 grid, cudaStream_t s);
+
 }  // namespace odecol

@@ -18,21 +18,6 @@ namespace odecol {
 // ---------------------------------------------------------------------------------------------------------------
 // forward stage epilogues
 // ---------------------------------------------------------------------------------------------------------------
-struct FwdStageArgs {
-    DevProblem p;
-    const float* Wp;       // [Np][KPa]
-    const float* Ra_cur;   // [Bp][KPa]
-    float* Ra_nxt;         // [Bp][KPa]
-    const float* y0;       // [B][3N] state at the start of the step
-    float* k1;             // [B][3N]
-    float* k2;
-    float* k3;
-    float* y1;             // [B][3N] state at the end of the step (stage 4)
-    float* y_out_row;      // optional second destination of y1 (trajectory row), may be NULL
-    const float* t;        // device time grid
-    int n;                 // step index: t0 = t[n], t1 = t[n+1]
-    int KPa;
-};
 
 template <int S>
 ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const float (&tot)[4], float dt) {
@@ -45,7 +30,7 @@ ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const
     if (S >= 2) { k1V = ldc(a.k1 + base); k1A = ldc(a.k1 + base + N); k1F = ldc(a.k1 + base + 2 * N); }
     if (S >= 3) { k2V = ldc(a.k2 + base); k2A = ldc(a.k2 + base + N); k2F = ldc(a.k2 + base + 2 * N); }
     if (S >= 4) { k3V = ldc(a.k3 + base); k3A = ldc(a.k3 + base + N); k3F = ldc(a.k3 + base + 2 * N); }
-    C4 oV, oA, oF, oR, kV, kA, kF;
+    C4 oV, oA, oF, oR, oD, kV, kA, kF;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         // the stage state this launch's contraction belongs to (same expressions as family S)
@@ -92,8 +77,10 @@ ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const
             nF = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F.v[e], __fmul_rn(3.f, __fadd_rn(k2F.v[e], k3F.v[e]))), dF), dt), 0.125f));
         }
         oV.v[e] = nV; oA.v[e] = nA; oF.v[e] = nF;
-        oR.v[e] = phi(__fsub_rn(nV, nA));
+        if (a.DR_nxt) phi_dphi(__fsub_rn(nV, nA), oR.v[e], oD.v[e]);
+        else oR.v[e] = phi(__fsub_rn(nV, nA));
     }
+    if (a.DR_nxt) stc(a.DR_nxt + (size_t)b * N + i, oD);
     if (S == 1) { stc(a.k1 + base, kV); stc(a.k1 + base + N, kA); stc(a.k1 + base + 2 * N, kF); }
     if (S == 2) { stc(a.k2 + base, kV); stc(a.k2 + base + N, kA); stc(a.k2 + base + 2 * N, kF); }
     if (S == 3) { stc(a.k3 + base, kV); stc(a.k3 + base + N, kA); stc(a.k3 + base + 2 * N, kF); }
@@ -152,10 +139,19 @@ __global__ void k_pad_weights(const float* __restrict__ W_aug, int N, int ld_w, 
     }
 }
 
-__global__ void k_init_operand(DevProblem p, const float* y, const float* t_dev, float* Ra0, float* Ra1, int KPa, int Bp) {
-    // one CTA per trial row (padding rows become zero); stimulus taken at t_dev[0]
+__global__ void k_pad_transpose(const float* __restrict__ W_aug, int N, int ld_w, float* __restrict__ WT, int Np, int NPk) {
+    const size_t total = (size_t)Np * NPk;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e / NPk), i = (int)(e % NPk);
+        WT[e] = (i < N && j < N) ? W_aug[(size_t)i * ld_w + j] : 0.0f;
+    }
+}
+
+__global__ void k_init_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_ptr,
+                               float* __restrict__ Ra0, float* __restrict__ Ra1, float* __restrict__ DR, int KPa, int Bp) {
+    // one CTA per trial row (padding rows become zero); stimulus taken at t_ptr[0]
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
-    const float tq = __ldg(t_dev);
+    const float tq = __ldg(t_ptr);
     float* r0 = Ra0 + (size_t)b * KPa;
     float* r1 = Ra1 ? Ra1 + (size_t)b * KPa : nullptr;
     if (b >= p.B) {
@@ -168,17 +164,43 @@ __global__ void k_init_operand(DevProblem p, const float* y, const float* t_dev,
     const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
     for (int k = threadIdx.x; k < KPa; k += blockDim.x) {
         float v = 0.f, v1 = 0.f;
-        if (k < N) v = phi(__fsub_rn(yb[k], yb[N + k]));
-        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tc, k - N);
+        if (k < N) {
+            if (DR) { float d; phi_dphi(__fsub_rn(yb[k], yb[N + k]), v, d); DR[(size_t)b * N + k] = d; }
+            else v = phi(__fsub_rn(yb[k], yb[N + k]));
+        } else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tc, k - N);
         else if (k == Kaug - 1) { v = 1.f; v1 = 1.f; }
         r0[k] = v;
         if (r1) r1[k] = v1;
     }
 }
 
+void launch_pad_weights(const float* W_aug, int N, int ld_w, int Kaug, float* Wp, int Np, int KPa, cudaStream_t s) {
+    k_pad_weights<<<296, 256, 0, s>>>(W_aug, N, ld_w, Kaug, Wp, Np, KPa);
+    count_launch();
+}
+void launch_pad_transpose(const float* W_aug, int N, int ld_w, float* WT, int Np, int NPk, cudaStream_t s) {
+    k_pad_transpose<<<296, 256, 0, s>>>(W_aug, N, ld_w, WT, Np, NPk);
+    count_launch();
+}
+void launch_init_operand(const DevProblem& p, const float* y, const float* t_ptr, float* Ra, float* Ra_extra, float* DR,
+                         int KPa, int Bp, cudaStream_t s) {
+    k_init_operand<<<Bp, 128, 0, s>>>(p, y, t_ptr, Ra, Ra_extra, DR, KPa, Bp);
+    count_launch();
+}
+
 __global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x)
         reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+}
+
+void launch_fwd_stage(int S, const FwdStageArgs& a, dim3 grid, cudaStream_t s) {
+    switch (S) {
+        case 1: k_fwd_stage<1><<<grid, kGemmThreads, 0, s>>>(a); break;
+        case 2: k_fwd_stage<2><<<grid, kGemmThreads, 0, s>>>(a); break;
+        case 3: k_fwd_stage<3><<<grid, kGemmThreads, 0, s>>>(a); break;
+        default: k_fwd_stage<4><<<grid, kGemmThreads, 0, s>>>(a); break;
+    }
+    count_launch();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,10 +246,10 @@ int stage_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
 
-    k_pad_weights<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, Kaug, Wp, L.Np, L.KPa);
-    k_init_operand<<<L.Bp, 128, 0, s>>>(p, y0, t_dev, Ra[0], Ra[1], L.KPa, L.Bp);
+    launch_pad_weights(p.W_aug, p.N, p.ld_w, Kaug, Wp, L.Np, L.KPa, s);
+    launch_init_operand(p, y0, t_dev, Ra[0], Ra[1], nullptr, L.KPa, L.Bp, s);
     k_copy<<<296, 256, 0, s>>>(y0, y_out, st / 4);
-    count_launch(3);
+    count_launch();
     const dim3 grid(L.Np / TM, L.Bp / TN);
     const float* ycur = y0;
     int cur = 0;
@@ -237,19 +259,14 @@ int stage_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y
         const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
         float* ynext = emit ? y_out + r * st : ybuf[n & 1];
         FwdStageArgs a;
-        a.p = p; a.Wp = Wp; a.y0 = ycur; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.y1 = ynext; a.y_out_row = nullptr;
+        a.p = p; a.Wp = Wp; a.y0 = ycur; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.y1 = ynext; a.y_out_row = nullptr; a.DR_nxt = nullptr;
         a.t = t_dev; a.n = n; a.KPa = L.KPa;
         a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
-        k_fwd_stage<1><<<grid, kGemmThreads, 0, s>>>(a);
-        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
-        k_fwd_stage<2><<<grid, kGemmThreads, 0, s>>>(a);
-        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
-        k_fwd_stage<3><<<grid, kGemmThreads, 0, s>>>(a);
-        cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
-        k_fwd_stage<4><<<grid, kGemmThreads, 0, s>>>(a);
-        cur ^= 1;
+        for (int S = 1; S <= 4; ++S) {
+            launch_fwd_stage(S, a, grid, s);
+            cur ^= 1; a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
+        }
         ycur = ynext;
-        count_launch(4);
     }
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
