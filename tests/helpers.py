@@ -72,15 +72,18 @@ def stim_table(name, stim):
     return s
 
 
-def rel_err(a, b):
-    """Norm-relative error per state block (elementwise relative error is meaningless at zero
-    crossings of V)."""
+def block_errs(a, b):
+    """Norm-relative error of the V, A and F blocks (elementwise relative error is meaningless
+    at zero crossings of V)."""
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
-    n3 = a.shape[-1]
-    n = n3 // 3
+    n = a.shape[-1] // 3
     out = []
     for c in range(3):
         x, y = a[..., c * n:(c + 1) * n], b[..., c * n:(c + 1) * n]
         out.append(float((x - y).abs().max() / y.abs().max().clamp_min(1e-30)))
-    return max(out)
+    return out
+
+
+def rel_err(a, b):
+    return max(block_errs(a, b))
