@@ -293,7 +293,7 @@ def run_ours(args):
     ffma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     family = net_family(ext, odecol, net, step.y0_dev, tv, args)
     roofline = {
-        "bound": "tensor", "kernel": "k_fwd_stage (fused W_aug.r_aug contraction + RK stage epilogue)",
+        "bound": "tensor", "kernel": "forward stage kernel (fused W_aug.r_aug contraction + RK stage epilogue)",
         "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tflops / tensor_peak,
         "traffic": None,
         "peak_source": ("measured bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split) from MEASURED_PEAKS.json" if peaks else
@@ -333,8 +333,10 @@ def run_ours(args):
 
 
 def net_family(ext, odecol, net, y0, tv, args):
-    lf = net.export_linear_form()
-    return "staged FP32-FFMA" if lf.N > 128 or args.family == "staged" else "persistent on-chip"
+    from ode_column_b200.solvers import _Setup
+    setup = _Setup(net, y0, tv, args.family)
+    fam = setup.problem(setup.lf.W_aug).kernel_family(ext.OP_RK4_FWD)
+    return {0: "persistent on-chip (FP32 FFMA)", 1: "staged FP32-FFMA", 2: "staged tcgen05 3xTF32"}.get(fam, str(fam))
 
 
 def main():

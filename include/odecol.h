@@ -59,8 +59,9 @@ enum {
 
 /* odecol_problem.flags */
 enum {
-    ODECOL_FLAG_FORCE_STAGED = 1   /* use the staged (global-state) kernel family even when the problem
-                                      fits the persistent on-chip family; for testing and measurement   */
+    ODECOL_FLAG_FORCE_STAGED = 1,  /* use the staged (global-state) FP32-FFMA kernel family even when the
+                                      problem fits the persistent on-chip family; for testing and measurement */
+    ODECOL_FLAG_FORCE_TENSOR = 2   /* use the staged tcgen05 (3xTF32) family regardless of size               */
 };
 
 /* operations, for odecol_workspace_bytes() */
@@ -165,6 +166,13 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
                   const float* grad_y, const int32_t* sel, int32_t G, float dt,
                   float* grad_y0, float* grad_W_aug,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in
+ * tensor memory), C[n][m] = sum_k A[m][k] * B[n][k] for row-major A (M x K), B (N x K), C (N x M).  Lets the tests pin
+ * the accuracy of the split-precision contraction the staged solver uses for large networks. */
+size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int odecol_tc_contract(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Which kernel family a call would use: 0 = persistent on-chip ("small", W row in registers),
  * 1 = staged FP32-FFMA contraction, 2 = staged 3xTF32 tcgen05 contraction.  Diagnostic only. */

@@ -22,7 +22,14 @@ static int to_dev(const odecol_problem* p, DevProblem& d) {
 }
 
 static bool use_small(const odecol_problem* p, const DevProblem& d) {
-    return !(p->flags & ODECOL_FLAG_FORCE_STAGED) && small_kp(d) != 0;
+    return !(p->flags & (ODECOL_FLAG_FORCE_STAGED | ODECOL_FLAG_FORCE_TENSOR)) && small_kp(d) != 0;
+}
+
+// staged problems: the contraction runs on the tensor cores once it is a real dense one (N >= 256), or on request
+static bool use_tensor(const odecol_problem* p, const DevProblem& d) {
+    if (p->flags & ODECOL_FLAG_FORCE_TENSOR) return true;
+    if (p->flags & ODECOL_FLAG_FORCE_STAGED) return false;
+    return d.N >= 256;
 }
 
 static inline bool misaligned(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) != 0; }
@@ -65,7 +72,7 @@ int odecol_kernel_family(const odecol_problem* p, int op) {
     DevProblem d;
     if (to_dev(p, d) != ODECOL_OK) return -1;
     (void)op;
-    return use_small(p, d) ? 0 : 1;
+    return use_small(p, d) ? 0 : (use_tensor(p, d) && op == ODECOL_OP_RK4_FWD ? 2 : 1);
 }
 
 size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_t n_steps) {
@@ -73,7 +80,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
     if (to_dev(p, d) != ODECOL_OK) return 0;
     const bool small = use_small(p, d);
     switch (op) {
-        case ODECOL_OP_RK4_FWD: return small ? 0 : stage_rk4_fwd_workspace_bytes(d, T);
+        case ODECOL_OP_RK4_FWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
         case ODECOL_OP_RK4_BWD: return small ? 0 : stage_rk4_bwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
@@ -101,6 +108,7 @@ int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const flo
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_small(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
+    if (use_tensor(p, d)) return tc_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
     return stage_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
 }
 
@@ -198,6 +206,20 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     int r2 = launch_em_schedule(ts, T, dt, step_of, wts, tk, s);
     if (r2) return r2;
     return launch_em_bwd_small(d, ts, T, y_steps, grad_y, sel, G, grad_y0, grad_W_aug, step_of, wts, tk, s);
+}
+
+size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return tc_contract_workspace_bytes(M, N, K);
+}
+
+int odecol_tc_contract(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!A || !B || !C) return ODECOL_E_NULL;
+    if (M <= 0 || N <= 0 || K <= 0) return ODECOL_E_SHAPE;
+    if (misaligned(workspace)) return ODECOL_E_ALIGN;
+    g_launches = 0;
+    return tc_contract(A, B, C, M, N, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

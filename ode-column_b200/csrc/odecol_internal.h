@@ -59,4 +59,11 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
                  uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
                  int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// ---- family T (stage_tc.cu): the staged contraction on tcgen05 tensor cores (3xTF32) ------------------------------
+size_t tc_rk4_fwd_workspace_bytes(const DevProblem& p, int T);
+int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every, void* ws,
+               size_t ws_bytes, cudaStream_t s);
+size_t tc_contract_workspace_bytes(int M, int N, int K);
+int tc_contract(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace odecol

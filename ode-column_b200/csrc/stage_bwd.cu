@@ -272,7 +272,7 @@ int stage_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y
         launch_init_operand(p, yn, t_dev + n, Ra[0], nullptr, DR[0], L.KPa, L.Bp, s);
         FwdStageArgs f;
         f.p = p; f.Wp = Wp; f.y0 = yn; f.k1 = kk[0]; f.k2 = kk[1]; f.k3 = kk[2]; f.y1 = nullptr; f.y_out_row = nullptr;
-        f.t = t_dev; f.n = n; f.KPa = L.KPa;
+        f.t = t_dev; f.n = n; f.KPa = L.KPa; f.Ra_cur_lo = nullptr; f.Ra_nxt_lo = nullptr;
         for (int S = 1; S <= 3; ++S) {
             f.Ra_cur = Ra[S - 1]; f.Ra_nxt = Ra[S]; f.DR_nxt = DR[S];
             launch_fwd_stage(S, f, grid, s);

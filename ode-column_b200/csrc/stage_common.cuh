@@ -87,6 +87,8 @@ struct FwdStageArgs {
     const float* Wp;       // [Np][KPa]
     const float* Ra_cur;   // [Bp][KPa]
     float* Ra_nxt;         // [Bp][KPa]
+    const float* Ra_cur_lo; // tensor family only: low TF32 parts of the operands (else NULL)
+    float* Ra_nxt_lo;
     const float* y0;       // [B][3N] state at the start of the step
     float* k1;             // [B][3N]
     float* k2;
@@ -98,6 +100,117 @@ struct FwdStageArgs {
     int n;                 // step index: t0 = t[n], t1 = t[n+1]
     int KPa;
 };
+
+template <int VW> struct Pk { float v[VW]; };
+template <int VW> ODECOL_DEVINL Pk<VW> ldp(const float* p) {
+    Pk<VW> r;
+    if constexpr (VW == 4) { const float4 q = ld4(p); r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; }
+    else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) r.v[e] = p[e];
+    }
+    return r;
+}
+template <int VW> ODECOL_DEVINL void stp(float* p, const Pk<VW>& x) {
+    if constexpr (VW == 4) st4(p, make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
+    else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) p[e] = x.v[e];
+    }
+}
+ODECOL_DEVINL float tf32_round(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// fused epilogue of forward stage S (1..4) for VW consecutive populations of trial b, shared by the FFMA and the
+// tensor-core contraction kernels
+template <int S, int VW>
+ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const float (&tot)[VW], float dt) {
+    const int N = a.p.N;
+    const size_t base = (size_t)b * 3 * N + i;
+    const Pk<VW> V0 = ldp<VW>(a.y0 + base), A0 = ldp<VW>(a.y0 + base + N), F0 = ldp<VW>(a.y0 + base + 2 * N);
+    Pk<VW> rs = ldp<VW>(a.Ra_cur + (size_t)b * a.KPa + i);
+    if (a.Ra_cur_lo) {                       // tensor family: the operand is stored split, r = hi + lo
+        const Pk<VW> rl = ldp<VW>(a.Ra_cur_lo + (size_t)b * a.KPa + i);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) rs.v[e] += rl.v[e];
+    }
+    const Pk<VW> kap = ldp<VW>(a.p.kappa + i);
+    Pk<VW> k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+    if (S >= 2) { k1V = ldp<VW>(a.k1 + base); k1A = ldp<VW>(a.k1 + base + N); k1F = ldp<VW>(a.k1 + base + 2 * N); }
+    if (S >= 3) { k2V = ldp<VW>(a.k2 + base); k2A = ldp<VW>(a.k2 + base + N); k2F = ldp<VW>(a.k2 + base + 2 * N); }
+    if (S >= 4) { k3V = ldp<VW>(a.k3 + base); k3A = ldp<VW>(a.k3 + base + N); k3F = ldp<VW>(a.k3 + base + 2 * N); }
+    Pk<VW> oV, oA, oF, oR, oD, kV, kA, kF;
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+        // the stage state this launch's contraction belongs to (same expressions as family S)
+        float V, A, F;
+        if (S == 1) { V = V0.v[e]; A = A0.v[e]; F = F0.v[e]; }
+        if (S == 2) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, k1V.v[e]), kOneThirdL));
+            A = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, k1A.v[e]), kOneThirdL));
+            F = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(dt, k1F.v[e]), kOneThirdL));
+        }
+        if (S == 3) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(k2V.v[e], __fmul_rn(k1V.v[e], kOneThirdL))));
+            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(k2A.v[e], __fmul_rn(k1A.v[e], kOneThirdL))));
+            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fsub_rn(k2F.v[e], __fmul_rn(k1F.v[e], kOneThirdL))));
+        }
+        if (S == 4) {
+            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), k3V.v[e])));
+            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), k3A.v[e])));
+            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1F.v[e], k2F.v[e]), k3F.v[e])));
+        }
+        float dV, dA, dF;
+        drift(a.p.c, V, A, F, rs.v[e], kap.v[e], tot[e], dV, dA, dF);
+        kV.v[e] = dV; kA.v[e] = dA; kF.v[e] = dF;
+        // next stage state
+        float nV, nA, nF;
+        if (S == 1) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, dV), kOneThirdL));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, dA), kOneThirdL));
+            nF = 0.f;
+        }
+        if (S == 2) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(dV, __fmul_rn(k1V.v[e], kOneThirdL))));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(dA, __fmul_rn(k1A.v[e], kOneThirdL))));
+            nF = 0.f;
+        }
+        if (S == 3) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), dV)));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), dA)));
+            nF = 0.f;
+        }
+        if (S == 4) {
+            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1V.v[e], __fmul_rn(3.f, __fadd_rn(k2V.v[e], k3V.v[e]))), dV), dt), 0.125f));
+            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1A.v[e], __fmul_rn(3.f, __fadd_rn(k2A.v[e], k3A.v[e]))), dA), dt), 0.125f));
+            nF = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F.v[e], __fmul_rn(3.f, __fadd_rn(k2F.v[e], k3F.v[e]))), dF), dt), 0.125f));
+        }
+        oV.v[e] = nV; oA.v[e] = nA; oF.v[e] = nF;
+        if (a.DR_nxt) phi_dphi(__fsub_rn(nV, nA), oR.v[e], oD.v[e]);
+        else oR.v[e] = phi(__fsub_rn(nV, nA));
+    }
+    if (a.DR_nxt) stp<VW>(a.DR_nxt + (size_t)b * N + i, oD);
+    if (S == 1) { stp<VW>(a.k1 + base, kV); stp<VW>(a.k1 + base + N, kA); stp<VW>(a.k1 + base + 2 * N, kF); }
+    if (S == 2) { stp<VW>(a.k2 + base, kV); stp<VW>(a.k2 + base + N, kA); stp<VW>(a.k2 + base + 2 * N, kF); }
+    if (S == 3) { stp<VW>(a.k3 + base, kV); stp<VW>(a.k3 + base + N, kA); stp<VW>(a.k3 + base + 2 * N, kF); }
+    if (S == 4) {
+        stp<VW>(a.y1 + base, oV); stp<VW>(a.y1 + base + N, oA); stp<VW>(a.y1 + base + 2 * N, oF);
+        if (a.y_out_row) { stp<VW>(a.y_out_row + base, oV); stp<VW>(a.y_out_row + base + N, oA); stp<VW>(a.y_out_row + base + 2 * N, oF); }
+    }
+    if (a.Ra_nxt_lo) {
+        Pk<VW> oH, oL;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) { oH.v[e] = tf32_round(oR.v[e]); oL.v[e] = tf32_round(oR.v[e] - oH.v[e]); }
+        stp<VW>(a.Ra_nxt + (size_t)b * a.KPa + i, oH);
+        stp<VW>(a.Ra_nxt_lo + (size_t)b * a.KPa + i, oL);
+    } else {
+        stp<VW>(a.Ra_nxt + (size_t)b * a.KPa + i, oR);
+    }
+}
+
 
 // launchers defined in stage_kernels.cu (kernels cannot be launched across translation units)
 void launch_pad_weights(const float* W_aug, int N, int ld_w, int Kaug, float* Wp, int Np, int KPa, cudaStream_t s);

@@ -20,78 +20,6 @@ namespace odecol {
 // ---------------------------------------------------------------------------------------------------------------
 
 template <int S>
-ODECOL_DEVINL void fwd_stage_epilogue(const FwdStageArgs& a, int i, int b, const float (&tot)[4], float dt) {
-    const int N = a.p.N;
-    const size_t base = (size_t)b * 3 * N + i;
-    const C4 V0 = ldc(a.y0 + base), A0 = ldc(a.y0 + base + N), F0 = ldc(a.y0 + base + 2 * N);
-    const C4 rs = ldc(a.Ra_cur + (size_t)b * a.KPa + i);
-    const C4 kap = ldc(a.p.kappa + i);
-    C4 k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
-    if (S >= 2) { k1V = ldc(a.k1 + base); k1A = ldc(a.k1 + base + N); k1F = ldc(a.k1 + base + 2 * N); }
-    if (S >= 3) { k2V = ldc(a.k2 + base); k2A = ldc(a.k2 + base + N); k2F = ldc(a.k2 + base + 2 * N); }
-    if (S >= 4) { k3V = ldc(a.k3 + base); k3A = ldc(a.k3 + base + N); k3F = ldc(a.k3 + base + 2 * N); }
-    C4 oV, oA, oF, oR, oD, kV, kA, kF;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        // the stage state this launch's contraction belongs to (same expressions as family S)
-        float V, A, F;
-        if (S == 1) { V = V0.v[e]; A = A0.v[e]; F = F0.v[e]; }
-        if (S == 2) {
-            V = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, k1V.v[e]), kOneThirdL));
-            A = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, k1A.v[e]), kOneThirdL));
-            F = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(dt, k1F.v[e]), kOneThirdL));
-        }
-        if (S == 3) {
-            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(k2V.v[e], __fmul_rn(k1V.v[e], kOneThirdL))));
-            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(k2A.v[e], __fmul_rn(k1A.v[e], kOneThirdL))));
-            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fsub_rn(k2F.v[e], __fmul_rn(k1F.v[e], kOneThirdL))));
-        }
-        if (S == 4) {
-            V = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), k3V.v[e])));
-            A = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), k3A.v[e])));
-            F = __fadd_rn(F0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1F.v[e], k2F.v[e]), k3F.v[e])));
-        }
-        float dV, dA, dF;
-        drift(a.p.c, V, A, F, rs.v[e], kap.v[e], tot[e], dV, dA, dF);
-        kV.v[e] = dV; kA.v[e] = dA; kF.v[e] = dF;
-        // next stage state
-        float nV, nA, nF;
-        if (S == 1) {
-            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(dt, dV), kOneThirdL));
-            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(dt, dA), kOneThirdL));
-            nF = 0.f;
-        }
-        if (S == 2) {
-            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fsub_rn(dV, __fmul_rn(k1V.v[e], kOneThirdL))));
-            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fsub_rn(dA, __fmul_rn(k1A.v[e], kOneThirdL))));
-            nF = 0.f;
-        }
-        if (S == 3) {
-            nV = __fadd_rn(V0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1V.v[e], k2V.v[e]), dV)));
-            nA = __fadd_rn(A0.v[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1A.v[e], k2A.v[e]), dA)));
-            nF = 0.f;
-        }
-        if (S == 4) {
-            nV = __fadd_rn(V0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1V.v[e], __fmul_rn(3.f, __fadd_rn(k2V.v[e], k3V.v[e]))), dV), dt), 0.125f));
-            nA = __fadd_rn(A0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1A.v[e], __fmul_rn(3.f, __fadd_rn(k2A.v[e], k3A.v[e]))), dA), dt), 0.125f));
-            nF = __fadd_rn(F0.v[e], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F.v[e], __fmul_rn(3.f, __fadd_rn(k2F.v[e], k3F.v[e]))), dF), dt), 0.125f));
-        }
-        oV.v[e] = nV; oA.v[e] = nA; oF.v[e] = nF;
-        if (a.DR_nxt) phi_dphi(__fsub_rn(nV, nA), oR.v[e], oD.v[e]);
-        else oR.v[e] = phi(__fsub_rn(nV, nA));
-    }
-    if (a.DR_nxt) stc(a.DR_nxt + (size_t)b * N + i, oD);
-    if (S == 1) { stc(a.k1 + base, kV); stc(a.k1 + base + N, kA); stc(a.k1 + base + 2 * N, kF); }
-    if (S == 2) { stc(a.k2 + base, kV); stc(a.k2 + base + N, kA); stc(a.k2 + base + 2 * N, kF); }
-    if (S == 3) { stc(a.k3 + base, kV); stc(a.k3 + base + N, kA); stc(a.k3 + base + 2 * N, kF); }
-    if (S == 4) {
-        stc(a.y1 + base, oV); stc(a.y1 + base + N, oA); stc(a.y1 + base + 2 * N, oF);
-        if (a.y_out_row) { stc(a.y_out_row + base, oV); stc(a.y_out_row + base + N, oA); stc(a.y_out_row + base + 2 * N, oF); }
-    }
-    stc(a.Ra_nxt + (size_t)b * a.KPa + i, oR);
-}
-
-template <int S>
 __global__ void __launch_bounds__(kGemmThreads, 2) k_fwd_stage(FwdStageArgs a) {
     __shared__ __align__(16) GemmSmem sm;
     const int i0 = blockIdx.x * TM, b0 = blockIdx.y * TN;
@@ -113,7 +41,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) k_fwd_stage(FwdStageArgs a) {
                 if (i >= N) continue;
                 const float tot[4] = {acc[ih * 4 + 0][jh * 4 + jj], acc[ih * 4 + 1][jh * 4 + jj], acc[ih * 4 + 2][jh * 4 + jj],
                                       acc[ih * 4 + 3][jh * 4 + jj]};
-                fwd_stage_epilogue<S>(a, i, b, tot, dt);
+                fwd_stage_epilogue<S, 4>(a, i, b, tot, dt);
             }
         }
     // stimulus columns of the next stage's operand: written by the first row of CTAs
@@ -259,7 +187,7 @@ int stage_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y
         const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
         float* ynext = emit ? y_out + r * st : ybuf[n & 1];
         FwdStageArgs a;
-        a.p = p; a.Wp = Wp; a.y0 = ycur; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.y1 = ynext; a.y_out_row = nullptr; a.DR_nxt = nullptr;
+        a.p = p; a.Wp = Wp; a.y0 = ycur; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.y1 = ynext; a.y_out_row = nullptr; a.DR_nxt = nullptr; a.Ra_cur_lo = nullptr; a.Ra_nxt_lo = nullptr;
         a.t = t_dev; a.n = n; a.KPa = L.KPa;
         a.Ra_cur = Ra[cur]; a.Ra_nxt = Ra[cur ^ 1];
         for (int S = 1; S <= 4; ++S) {

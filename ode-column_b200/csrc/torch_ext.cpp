@@ -197,6 +197,19 @@ std::vector<torch::Tensor> em_bwd(const Problem& pr, const torch::Tensor& ts, co
     return {gy0, gW};
 }
 
+torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
+    c10::cuda::CUDAGuard g(A.device());
+    want(A, "A"); want(B, "B");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "odecol: tc_contract wants A (M,K), B (N,K)");
+    const int64_t M = A.size(0), N = B.size(0), K = A.size(1);
+    auto C = torch::empty({N, M}, A.options());
+    const size_t bytes = odecol_tc_contract_workspace_bytes((int32_t)M, (int32_t)N, (int32_t)K);
+    auto ws = torch::empty({(int64_t)bytes}, A.options().dtype(torch::kUInt8));
+    check(odecol_tc_contract(A.data_ptr<float>(), B.data_ptr<float>(), C.data_ptr<float>(), (int32_t)M, (int32_t)N, (int32_t)K,
+                             ws.data_ptr(), bytes, at::cuda::getCurrentCUDAStream(A.device().index()).stream()), "tc_contract");
+    return C;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -222,6 +235,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_num_steps", &em_num_steps);
     m.def("em_fwd", &em_fwd);
     m.def("em_bwd", &em_bwd);
+    m.def("tc_contract", &tc_contract);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;
     m.attr("OP_RK4_FWD") = (int)ODECOL_OP_RK4_FWD;
     m.attr("OP_RK4_BWD") = (int)ODECOL_OP_RK4_BWD;
@@ -229,4 +243,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.attr("OP_EM_FWD") = (int)ODECOL_OP_EM_FWD;
     m.attr("OP_EM_BWD") = (int)ODECOL_OP_EM_BWD;
     m.attr("FLAG_FORCE_STAGED") = (int)ODECOL_FLAG_FORCE_STAGED;
+    m.attr("FLAG_FORCE_TENSOR") = (int)ODECOL_FLAG_FORCE_TENSOR;
 }

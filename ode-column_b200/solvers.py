@@ -59,7 +59,9 @@ class _Setup:
             raise ValueError(f"odecol: stimulus has {table.shape[0]} trials, y0 has {self.B}")
         time_vec = func.time_vec.detach().to(device=dev, dtype=torch.float32)
         self.knot_t, self.knot_u = compress_knots(time_vec, table)
-        self.flags = self.ext.FLAG_FORCE_STAGED if family == "staged" else 0
+        if family not in (None, "staged", "tensor"):
+            raise ValueError("odecol: options['family'] must be None, 'staged' (FP32 FFMA) or 'tensor' (tcgen05 3xTF32)")
+        self.flags = {None: 0, "staged": self.ext.FLAG_FORCE_STAGED, "tensor": self.ext.FLAG_FORCE_TENSOR}[family]
         self.kappa = self.lf.kappa.detach().to(dev, torch.float32).contiguous()
         self.sigma = self.lf.sigma.detach().to(dev, torch.float32).contiguous()
 

@@ -1,0 +1,25 @@
+"""The tcgen05 (3xTF32) contraction core and the tensor-core staged solver against float64 / the other kernel families."""
+import numpy as np
+import pytest
+import torch
+
+import odecol
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (128, 128, 64), (512, 300, 577), (200, 1000, 130), (1024, 2368, 608)])
+def test_tc_contract_matches_float64(M, N, K):
+    ext = odecol._native.ext()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * torch.rand(M, K, generator=g) * 30).to(DEV)
+    B = (torch.randn(N, K, generator=g).abs() * 5).to(DEV)
+    C = ext.tc_contract(A, B)
+    torch.cuda.synchronize()
+    ref = B.double() @ A.double().T
+    mag = B.double().abs() @ A.double().abs().T                     # sum_k |a||b|: the natural error scale of a dot product
+    err = float(((C.double() - ref).abs() / mag).max())
+    fp32 = float((((B @ A.T).double() - ref).abs() / mag).max())
+    print(f"\ntc_contract {M}x{N}x{K}: max err / sum|a||b| = {err:.2e} (cuBLAS fp32: {fp32:.2e})")
+    assert err < 2e-6
