@@ -6,11 +6,14 @@
 // One persistent CTA per SM, warp specialised:
 //   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the four operand tiles of a 32-wide K block into
 //               a 3-stage shared-memory ring, completion on mbarriers
-//   warp 1      tcgen05.mma issuer (one elected thread; M = 128 populations x N = tile of trials x K = 8 per instruction),
-//               accumulators double-buffered in TMEM; tcgen05.commit releases ring slots and publishes finished tiles
-//   warps 2..9  epilogue: tcgen05.ld the accumulator rows (TMEM lane = population), then the same fused RK-stage epilogue
-//               as the FFMA family -- drift, next stage state, phi, next operand (already split into hi/lo) -- while
-//               warp 1 is contracting the next tile
+//   warp 1      tcgen05.mma issuer (one elected thread; M = 128 populations x N = tile of trials x K = 8 per instruction).
+//               The tensor core truncates (round-toward-zero) every accumulation into TMEM, which biases long sums of
+//               same-signed terms (measured: -3.8e-6 relative at K = 608).  So the Whi.Rhi products rotate over THREE
+//               accumulators (a third of the truncations each) and the two small cross terms go to a fourth; the epilogue
+//               adds the four in FP32 round-to-nearest.  tcgen05.commit releases ring slots and publishes finished tiles
+//   warps 2..17 epilogue: tcgen05.ld this thread's accumulator row segment (TMEM lane = population) into registers, hand
+//               TMEM back to warp 1 (which starts contracting the next tile), then the fused RK-stage epilogue -- drift,
+//               next stage state, phi, next operand already split into hi/lo -- on tile-major scratch (float4 along trials)
 // The trial tile is chosen so that the number of tiles is a multiple of the SM count (148) where possible.
 #include <cuda.h>
 #include "stage_common.cuh"
@@ -21,7 +24,8 @@ namespace tc {
 constexpr int BM = 128;          // populations per tile = TMEM lanes
 constexpr int BK = 32;           // floats per K block = one 128-byte swizzle row
 constexpr int STAGES = 3;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kMainAcc = 3;      // Whi.Rhi accumulators (rotated), plus one for the cross terms
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr uint32_t kSpinLimit = 1u << 24;
 
@@ -59,16 +63,11 @@ ODECOL_DEVINL void umma_commit(uint32_t bar) {
 }
 ODECOL_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 ODECOL_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-ODECOL_DEVINL void tmem_ld16(uint32_t taddr, float (&r)[16]) {
-    uint32_t u[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-                   "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+ODECOL_DEVINL void tmem_ld4_issue(uint32_t taddr, uint32_t (&u)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr));
 }
+ODECOL_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart
 ODECOL_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -95,30 +94,36 @@ struct TileShape {
     int MT, NT, TN, KB;      // m tiles, trial tiles, trials per tile (multiple of 16, <= 128), K blocks of 32
 };
 
+constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4 <= 32
+
 // ---------------------------------------------------------------------------------------------------------------
-// the persistent warp-specialised contraction; Epi supplies element(i, b, acc) and tile_done(m_tile, n0, tid, nthreads)
+// the persistent warp-specialised contraction.  Epi supplies
+//   prepare()                                             once per epilogue thread
+//   rows(m_tile, i, n0, nt, g, tot)                       population i, trials n0 + g*TN/4 + [0, TN/4): tot[] = W_aug.r_aug
+//   tile_done(m_tile, n0, tile_n, etid, nthreads)         per tile, all epilogue threads
 // ---------------------------------------------------------------------------------------------------------------
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
               const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TileShape ts, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)ts.TN * BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+    const uint32_t tfull = smem_u32(&bars[2 * STAGES]), tempty = smem_u32(&bars[2 * STAGES + 1]);
     const int tiles = ts.MT * ts.NT;
     const uint32_t acc_stride = (uint32_t)ts.TN;
     uint32_t ncols = 32;
-    while (ncols < 2 * acc_stride) ncols <<= 1;
+    while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiWarps); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -150,11 +155,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(ts.TN);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
+            int stage = 0; uint32_t phase = 0, tphase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                mbar_wait(tempty, tphase ^ 1);            // epilogue has drained the accumulators of the previous tile
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * acc_stride;
+                int j = 0;
                 for (int kb = 0; kb < ts.KB; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
@@ -162,42 +168,56 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
                     const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
+                    for (int k = 0; k < BK / 8; ++k, ++j) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 TF32 = 32 bytes along the swizzled row
-                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                        umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                        umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
                     }
                     umma_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                umma_commit(tfull);
+                tphase ^= 1;
             }
         }
     } else {
         const int ew = warp - 2;
         const int quarter = warp & 3;                 // a warp may only read TMEM lanes [32*(warpid%4), +32)
-        const int half = ew >> 2;
+        const int g = ew >> 2;                        // which quarter of the tile's trials this warp owns
         const int etid = ew * 32 + lane;
+        const int TNq = ts.TN >> 2;
         epi.prepare();
-        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t tphase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m_tile = tile % ts.MT, n0 = (tile / ts.MT) * ts.TN;
+            const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
             const int row = m_tile * BM + quarter * 32 + lane;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            float tot[kMaxQ];
+            mbar_wait(tfull, tphase);
             tc_fence_after();
-            for (int c = half; c < ts.TN / 16; c += 2) {
-                float r[16];
-                tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + c * 16, r);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) epi.element(row, n0 + c * 16 + j, r[j]);
+            for (int q = 0; q < kMaxQ / 4; ++q) {
+                if (4 * q < TNq) {
+                    uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                    for (int a = 0; a <= kMainAcc; ++a) tmem_ld4_issue(lane_base + a * acc_stride + 4 * q, u[a]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float sum = __uint_as_float(u[kMainAcc][e]);                 // cross terms first (small)
+#pragma unroll
+                        for (int a = 0; a < kMainAcc; ++a) sum += __uint_as_float(u[a][e]);
+                        tot[4 * q + e] = sum;
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) mbar_arrive(tempty);        // TMEM is free again: warp 1 may start the next tile
+            tphase ^= 1;
+            epi.rows(m_tile, row, n0, nt, g, TNq, tot);
             epi.tile_done(m_tile, n0, ts.TN, etid, kEpiWarps * 32);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -302,7 +322,14 @@ __global__ void k_split_pad(const float* __restrict__ src, int rows, int cols, i
 struct StoreEpi {
     float* C; int M, N, ldc;
     ODECOL_DEVINL void prepare() {}
-    ODECOL_DEVINL void element(int i, int b, float acc) const { if (i < M && b < N) C[(size_t)b * ldc + i] = acc; }
+    ODECOL_DEVINL void rows(int, int i, int n0, int, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (i >= M) return;
+#pragma unroll
+        for (int j = 0; j < kMaxQ; ++j) {
+            const int b = n0 + g * TNq + j;
+            if (j < TNq && b < N) C[(size_t)b * ldc + i] = tot[j];
+        }
+    }
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 
@@ -320,75 +347,210 @@ static ContractLayout contract_layout(int M, int N, int K) {
     return L;
 }
 
+}  // namespace tc
+
+namespace tc {
+
 // ---------------------------------------------------------------------------------------------------------------
-// forward RK4 stages on the tensor cores
+// fast, FP32-accurate (about 1e-7 relative) elementwise math for the tensor family's epilogue
 // ---------------------------------------------------------------------------------------------------------------
+ODECOL_DEVINL float exp_fast(float x) {            // |x| < 87
+    const float n = rintf(x * 1.4426950408889634f);
+    float f = fmaf(n, -0.693145751953125f, x);
+    f = fmaf(n, -1.42860682030941723212e-6f, f);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f * 1.4426950408889634f));
+    return p * __int_as_float(((int)n + 127) << 23);
+}
+ODECOL_DEVINL float tanh_small(float u) {          // Taylor through u^11: < 3e-8 relative for |u| <= 0.4
+    if (fabsf(u) > 0.4f) return tanhf(u);
+    const float s = u * u;
+    float p = fmaf(s, -8.8632355299021965e-3f, 2.1869488536155203e-2f);   // -1382/155925, 62/2835
+    p = fmaf(s, p, -5.3968253968253968e-2f);                               // -17/315
+    p = fmaf(s, p, 1.3333333333333333e-1f);                                // 2/15
+    p = fmaf(s, p, -3.3333333333333333e-1f);                               // -1/3
+    return fmaf(u * s, p, u);
+}
+ODECOL_DEVINL float phi_fast(float x) {
+    const float x_nom = fmaf(48.0f, x, -981.0f);
+    const float zc = 80.0f * tanh_small(x_nom * (-0.0089f / 80.0f));
+    return __fdividef(x_nom, 1.0f - exp_fast(zc));
+}
+
+// tile-major scratch: element (component c, population i, trial b) with b = nt*TN + g*TNq + 4q + e lives at
+//   c*plane + ((((nt*4 + g)*(TNq/4) + q)*Np + i)*4 + e
+// so the float4 a thread reads for (q, i) sits next to its lane neighbours' (i +- 1): every warp request is one fully
+// used 512-byte run and no sector is ever touched twice (the first layout, row-per-thread, re-read each sector 25 us
+// later and lost it from L2 in between: 6x the DRAM traffic, profiles/r1_tc_v2_ncu.txt).
+struct TileGeom {
+    int NT, Np, TN, TNq;
+    ODECOL_DEVINL size_t plane() const { return (size_t)NT * 4 * Np * TNq; }
+    ODECOL_DEVINL size_t off(int nt, int g, int q, int i) const {
+        return ((((size_t)nt * 4 + g) * (TNq >> 2) + q) * Np + i) * 4;
+    }
+};
+
 template <int S>
-struct FwdEpi {
-    FwdStageArgs a;
+struct FwdEpiT {
+    DevProblem p;
+    TileGeom tg;
+    const float* t;
+    int n, KPa;
+    const float* Y0T;      // [3 planes] state at the start of the step (tile-major)
+    float* Y1T;            // stage 4: state at the end of the step (tile-major)
+    float* traj_row;       // stage 4: (B, 3N) row of the trajectory, or NULL
+    float* K1T; float* K2T; float* K3T;     // [3 planes] each
+    const float* RT_cur;   // [1 plane] r of this stage
+    float* RT_nxt;         // r of the next stage
+    float* Rhi_nxt; float* Rlo_nxt;         // [Bp][KPa] operand of the next contraction
+    float inv_tm, inv_ta, inv_ts;
     float t0, t1, dt;
+
     ODECOL_DEVINL void prepare() {
-        t0 = __ldg(a.t + a.n); t1 = __ldg(a.t + a.n + 1);
+        t0 = __ldg(t + n); t1 = __ldg(t + n + 1);
         dt = __fsub_rn(t1, t0);
     }
-    ODECOL_DEVINL void element(int i, int b, float acc) const {
-        if (i < a.p.N && b < a.p.B) {
-            const float tot[1] = {acc};
-            fwd_stage_epilogue<S, 1>(a, i, b, tot, dt);
+
+    ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (i >= p.N) return;
+        const int N = p.N, B = p.B;
+        const float kap = __ldg(p.kappa + i);
+        const size_t pl = tg.plane();
+        const float third = kOneThirdL;
+#pragma unroll
+        for (int q = 0; q < kMaxQ / 4; ++q) {
+            if (4 * q >= TNq) break;
+            const size_t oq = tg.off(nt, g, q, i);
+            const float4 V0 = ld4(Y0T + oq), A0 = ld4(Y0T + pl + oq), F0 = ld4(Y0T + 2 * pl + oq);
+            const float4 R = ld4(RT_cur + oq);
+            float4 k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+            if (S >= 2) { k1V = ld4(K1T + oq); k1A = ld4(K1T + pl + oq); k1F = ld4(K1T + 2 * pl + oq); }
+            if (S >= 3) { k2V = ld4(K2T + oq); k2A = ld4(K2T + pl + oq); k2F = ld4(K2T + 2 * pl + oq); }
+            if (S >= 4) { k3V = ld4(K3T + oq); k3A = ld4(K3T + pl + oq); k3F = ld4(K3T + 2 * pl + oq); }
+            float oKV[4], oKA[4], oKF[4], oNV[4], oNA[4], oNF[4], oR[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v0 = (&V0.x)[e], a0 = (&A0.x)[e], f0 = (&F0.x)[e], r = (&R.x)[e];
+                float V, A, F;
+                if (S == 1) { V = v0; A = a0; F = f0; }
+                if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * (&k1A.x)[e] * third; F = f0 + dt * (&k1F.x)[e] * third; }
+                if (S == 3) {
+                    V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third);
+                    A = a0 + dt * ((&k2A.x)[e] - (&k1A.x)[e] * third);
+                    F = f0 + dt * ((&k2F.x)[e] - (&k1F.x)[e] * third);
+                }
+                if (S == 4) {
+                    V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]);
+                    A = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + (&k3A.x)[e]);
+                    F = f0 + dt * ((&k1F.x)[e] - (&k2F.x)[e] + (&k3F.x)[e]);
+                }
+                const float total = tot[4 * q + e] * p.c.tau_s;
+                const float dV = (total * p.c.R - V) * inv_tm;
+                const float dA = (kap * r - A) * inv_ta;
+                const float dF = (r - F) * inv_ts;
+                oKV[e] = dV; oKA[e] = dA; oKF[e] = dF;
+                float nV, nA, nF = 0.f;
+                if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
+                if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - (&k1A.x)[e] * third); }
+                if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + dA); }
+                if (S == 4) {
+                    nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
+                    nA = a0 + ((&k1A.x)[e] + 3.f * ((&k2A.x)[e] + (&k3A.x)[e]) + dA) * dt * 0.125f;
+                    nF = f0 + ((&k1F.x)[e] + 3.f * ((&k2F.x)[e] + (&k3F.x)[e]) + dF) * dt * 0.125f;
+                }
+                oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
+                oR[e] = phi_fast(nV - nA);
+            }
+            const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
+            const float4 kA4 = make_float4(oKA[0], oKA[1], oKA[2], oKA[3]);
+            const float4 kF4 = make_float4(oKF[0], oKF[1], oKF[2], oKF[3]);
+            if (S == 1) { st4(K1T + oq, kV4); st4(K1T + pl + oq, kA4); st4(K1T + 2 * pl + oq, kF4); }
+            if (S == 2) { st4(K2T + oq, kV4); st4(K2T + pl + oq, kA4); st4(K2T + 2 * pl + oq, kF4); }
+            if (S == 3) { st4(K3T + oq, kV4); st4(K3T + pl + oq, kA4); st4(K3T + 2 * pl + oq, kF4); }
+            if (S == 4) {
+                st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+                st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+                st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+            }
+            st4(RT_nxt + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = n0 + g * TNq + 4 * q + e;
+                if (b < B) {
+                    const float h = tf32_rna(oR[e]);
+                    Rhi_nxt[(size_t)b * KPa + i] = h;
+                    Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
+                    if (S == 4 && traj_row) {
+                        float* yr = traj_row + (size_t)b * 3 * N + i;
+                        yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
+                    }
+                }
+            }
         }
     }
+
     // stimulus columns of the next operand, written once per trial tile (by the CTA that owns population tile 0)
     ODECOL_DEVINL void tile_done(int m_tile, int n0, int tile_n, int etid, int nthr) const {
-        if (m_tile != 0 || a.p.n_in == 0) return;
+        if (m_tile != 0 || p.n_in == 0) return;
         const float tn = S == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : S == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
         int idx = 1;
-        const float tc = knot_locate(a.p.knot_t, a.p.K, tn, idx);
-        const int n_in = a.p.n_in, N = a.p.N;
+        const float tcl = knot_locate(p.knot_t, p.K, tn, idx);
+        const int n_in = p.n_in, N = p.N;
         for (int e = etid; e < tile_n * n_in; e += nthr) {
             const int b = n0 + e / n_in, ch = e % n_in;
-            if (b < a.p.B) {
-                const float v = knot_value(a.p.knot_t, a.p.knot_u + (size_t)b * a.p.knot_stride_b, n_in, idx, tc, ch);
+            if (b < p.B) {
+                const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
                 const float h = tf32_rna(v);
-                a.Ra_nxt[(size_t)b * a.KPa + N + ch] = h;
-                a.Ra_nxt_lo[(size_t)b * a.KPa + N + ch] = tf32_rna(v - h);
+                Rhi_nxt[(size_t)b * KPa + N + ch] = h;
+                Rlo_nxt[(size_t)b * KPa + N + ch] = tf32_rna(v - h);
             }
         }
     }
 };
 
-// r_aug(t_ptr[0], y) split into hi/lo for buffer 0; constant-one column + zero padding for buffer 1
-__global__ void k_init_operand_split(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_ptr,
-                                     float* __restrict__ hi0, float* __restrict__ lo0, float* __restrict__ hi1,
-                                     float* __restrict__ lo1, float* __restrict__ DR, int KPa) {
+// initial operand (r_aug at t_ptr[0], split hi/lo), constant-one column + zero padding of the second operand buffer,
+// and the tile-major copies of y0 and r.  One CTA per (padded) trial.
+__global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y, const float* __restrict__ t_ptr,
+                          float* __restrict__ hi0, float* __restrict__ lo0, float* __restrict__ hi1, float* __restrict__ lo1,
+                          float* __restrict__ Y0T, float* __restrict__ RT, int KPa) {
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
     const size_t ro = (size_t)b * KPa;
+    const int nt = b / tg.TN, g = (b % tg.TN) / tg.TNq, jq = (b % tg.TN) % tg.TNq;
+    const int q = jq >> 2, e4 = jq & 3;
+    const size_t pl = tg.plane();
     if (b >= p.B) {
-        for (int k = threadIdx.x; k < KPa; k += blockDim.x) {
-            hi0[ro + k] = 0.f; lo0[ro + k] = 0.f;
-            if (hi1) { hi1[ro + k] = 0.f; lo1[ro + k] = 0.f; }
+        for (int k = threadIdx.x; k < KPa; k += blockDim.x) { hi0[ro + k] = 0.f; lo0[ro + k] = 0.f; hi1[ro + k] = 0.f; lo1[ro + k] = 0.f; }
+        for (int i = threadIdx.x; i < tg.Np; i += blockDim.x) {
+            const size_t o = tg.off(nt, g, q, i) + e4;
+            Y0T[o] = 0.f; Y0T[pl + o] = 0.f; Y0T[2 * pl + o] = 0.f; RT[o] = 0.f;
         }
         return;
     }
     const float* yb = y + (size_t)b * 3 * N;
     int idx = 1;
-    const float tc = knot_locate(p.knot_t, p.K, __ldg(t_ptr), idx);
+    const float tcl = knot_locate(p.knot_t, p.K, __ldg(t_ptr), idx);
     const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
     for (int k = threadIdx.x; k < KPa; k += blockDim.x) {
         float v = 0.f, one = 0.f;
-        if (k < N) {
-            if (DR) { float d; phi_dphi(__fsub_rn(yb[k], yb[N + k]), v, d); DR[(size_t)b * N + k] = d; }
-            else v = phi(__fsub_rn(yb[k], yb[N + k]));
-        } else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tc, k - N);
+        if (k < N) v = phi_fast(yb[k] - yb[N + k]);
+        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N);
         else if (k == Kaug - 1) { v = 1.f; one = 1.f; }
         const float h = tf32_rna(v);
         hi0[ro + k] = h; lo0[ro + k] = tf32_rna(v - h);
-        if (hi1) { hi1[ro + k] = one; lo1[ro + k] = 0.f; }
+        hi1[ro + k] = one; lo1[ro + k] = 0.f;
+    }
+    for (int i = threadIdx.x; i < tg.Np; i += blockDim.x) {
+        const size_t o = tg.off(nt, g, q, i) + e4;
+        const bool in = i < N;
+        const float V = in ? yb[i] : 0.f, A = in ? yb[N + i] : 0.f, F = in ? yb[2 * N + i] : 0.f;
+        Y0T[o] = V; Y0T[pl + o] = A; Y0T[2 * pl + o] = F;
+        RT[o] = in ? phi_fast(V - A) : 0.f;
     }
 }
 
 struct TcFwdLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_k[3], off_y[2], total;
+    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[2], total;
 };
 
 static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
@@ -401,16 +563,12 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     auto take = [&](size_t floats) { const size_t r = o; o += (floats * 4 + 1023) / 1024 * 1024; return r; };
     L.off_Whi = take((size_t)L.Np * L.KPa); L.off_Wlo = take((size_t)L.Np * L.KPa);
     for (int i = 0; i < 2; ++i) { L.off_Rhi[i] = take((size_t)L.Bp * L.KPa); L.off_Rlo[i] = take((size_t)L.Bp * L.KPa); }
-    const size_t st = (size_t)p.B * 3 * p.N;
-    for (int i = 0; i < 3; ++i) L.off_k[i] = take(st);
-    for (int i = 0; i < 2; ++i) L.off_y[i] = take(st);
+    const size_t plane = (size_t)L.Np * L.Bp;
+    for (int i = 0; i < 3; ++i) L.off_K[i] = take(3 * plane);
+    for (int i = 0; i < 2; ++i) L.off_Y[i] = take(3 * plane);
+    for (int i = 0; i < 2; ++i) L.off_RT[i] = take(plane);
     L.total = o;
     return L;
-}
-
-__global__ void k_copy4(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x)
-        reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
 }
 
 }  // namespace tc
@@ -428,15 +586,17 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo);
     float* Rhi[2] = {F(L.off_Rhi[0]), F(L.off_Rhi[1])};
     float* Rlo[2] = {F(L.off_Rlo[0]), F(L.off_Rlo[1])};
-    float* kk[3] = {F(L.off_k[0]), F(L.off_k[1]), F(L.off_k[2])};
-    float* ybuf[2] = {F(L.off_y[0]), F(L.off_y[1])};
+    float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
+    float* YT[2] = {F(L.off_Y[0]), F(L.off_Y[1])};
+    float* RT[2] = {F(L.off_RT[0]), F(L.off_RT[1])};
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
+    const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
 
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    k_init_operand_split<<<L.Bp, 128, 0, s>>>(p, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], nullptr, L.KPa);
-    k_copy4<<<296, 256, 0, s>>>(y0, y_out, st / 4);
-    count_launch(3);
+    k_tc_init<<<L.Bp, 128, 0, s>>>(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], RT[0], L.KPa);
+    count_launch(2);
+    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi[2], mRlo[2];
     bool ok = make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) && make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM);
     for (int i = 0; i < 2; ++i)
@@ -444,32 +604,32 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     if (!ok) return ODECOL_E_CUDA;
     const TileShape ts{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK};
 
-    const float* ycur = y0;
     int cur = 0;
     for (int n = 0; n < T - 1; ++n) {
         const int j = n + 1;
         const bool emit = (j % out_every == 0) || (j == T - 1);
         const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
-        float* ynext = emit ? y_out + r * st : ybuf[n & 1];
-        FwdStageArgs a;
-        a.p = p; a.Wp = nullptr; a.y0 = ycur; a.k1 = kk[0]; a.k2 = kk[1]; a.k3 = kk[2]; a.y1 = ynext; a.y_out_row = nullptr;
-        a.DR_nxt = nullptr; a.t = t_dev; a.n = n; a.KPa = L.KPa;
+        auto fill = [&](auto& e) {
+            e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
+            e.Y0T = YT[n & 1]; e.Y1T = YT[(n + 1) & 1]; e.traj_row = emit ? y_out + r * st : nullptr;
+            e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
+            e.RT_cur = RT[cur]; e.RT_nxt = RT[cur ^ 1]; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1];
+            e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+            e.t0 = e.t1 = e.dt = 0.f;
+        };
         for (int S = 1; S <= 4; ++S) {
-            a.Ra_cur = Rhi[cur]; a.Ra_cur_lo = Rlo[cur]; a.Ra_nxt = Rhi[cur ^ 1]; a.Ra_nxt_lo = Rlo[cur ^ 1];
             int rc;
-            switch (S) {
-                case 1: rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, FwdEpi<1>{a}, s); break;
-                case 2: rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, FwdEpi<2>{a}, s); break;
-                case 3: rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, FwdEpi<3>{a}, s); break;
-                default: rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, FwdEpi<4>{a}, s); break;
-            }
+            if (S == 1) { FwdEpiT<1> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
+            else if (S == 2) { FwdEpiT<2> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
+            else if (S == 3) { FwdEpiT<3> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
+            else { FwdEpiT<4> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             if (rc != ODECOL_OK) return rc;
             cur ^= 1;
         }
-        ycur = ynext;
     }
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
+
 
 size_t tc_contract_workspace_bytes(int M, int N, int K) { return tc::contract_layout(M, N, K).total; }
 
