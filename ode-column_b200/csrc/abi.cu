@@ -72,7 +72,7 @@ int odecol_kernel_family(const odecol_problem* p, int op) {
     DevProblem d;
     if (to_dev(p, d) != ODECOL_OK) return -1;
     (void)op;
-    return use_small(p, d) ? 0 : (use_tensor(p, d) && op == ODECOL_OP_RK4_FWD ? 2 : 1);
+    return use_small(p, d) ? 0 : (use_tensor(p, d) && (op == ODECOL_OP_RK4_FWD || op == ODECOL_OP_RK4_BWD) ? 2 : 1);
 }
 
 size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_t n_steps) {
@@ -81,7 +81,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
     const bool small = use_small(p, d);
     switch (op) {
         case ODECOL_OP_RK4_FWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
-        case ODECOL_OP_RK4_BWD: return small ? 0 : stage_rk4_bwd_workspace_bytes(d, T);
+        case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
         default: return 0;
@@ -125,6 +125,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
     if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (use_small(p, d)) return launch_rk4_bwd_small(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, s);
     if (misaligned(y_traj) || misaligned(workspace) || misaligned(grad_W_aug)) return ODECOL_E_ALIGN;
+    if (use_tensor(p, d)) return tc_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
     return stage_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
 }
 

@@ -1,0 +1,492 @@
+// Kernel family T ("tensor"): the staged solver's contraction on the 5th-generation tensor cores.
+//
+//   C[i][b] = sum_k W_aug[i][k] * R_aug[b][k]   as   3xTF32:  W = Whi + Wlo, R = Rhi + Rlo (each rounded to TF32),
+//   C = Wlo.Rhi + Whi.Rlo + Whi.Rhi accumulated in FP32 in tensor memory -- FP32-level accuracy at tensor-core rate.
+//
+// One persistent CTA per SM, warp specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the four operand tiles of a 32-wide K block into
+//               a 3-stage shared-memory ring, completion on mbarriers
+//   warp 1      tcgen05.mma issuer (one elected thread; M = 128 populations x N = tile of trials x K = 8 per instruction).
+//               The tensor core truncates (round-toward-zero) every accumulation into TMEM, which biases long sums of
+//               same-signed terms (measured: -3.8e-6 relative at K = 608).  So the Whi.Rhi products rotate over THREE
+//               accumulators (a third of the truncations each) and the two small cross terms go to a fourth; the epilogue
+//               adds the four in FP32 round-to-nearest.  tcgen05.commit releases ring slots and publishes finished tiles
+//   warps 2..17 epilogue: tcgen05.ld this thread's accumulator row segment (TMEM lane = population) into registers, hand
+//               TMEM back to warp 1 (which starts contracting the next tile), then the fused RK-stage epilogue -- drift,
+//               next stage state, phi, next operand already split into hi/lo -- on tile-major scratch (float4 along trials)
+// The trial tile is chosen so that the number of tiles is a multiple of the SM count (148) where possible.
+#pragma once
+#include <cuda.h>
+#include "stage_common.cuh"
+
+namespace odecol {
+namespace tc {
+
+constexpr int BM = 128;          // populations per tile = TMEM lanes
+constexpr int BK = 32;           // floats per K block = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int kEpiWarps = 16;
+constexpr int kMainAcc = 3;      // Whi.Rhi accumulators (rotated), plus one for the cross terms
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+ODECOL_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+ODECOL_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+ODECOL_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+ODECOL_DEVINL void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must trap, never hang the GPU
+ODECOL_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+ODECOL_DEVINL void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+ODECOL_DEVINL void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+ODECOL_DEVINL void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+ODECOL_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+ODECOL_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+ODECOL_DEVINL void tmem_ld4_issue(uint32_t taddr, uint32_t (&u)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr));
+}
+ODECOL_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart
+ODECOL_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);     // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset      bits [16,30)  (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+ODECOL_DEVINL uint32_t make_idesc(int tile_n) {
+    // c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+ODECOL_DEVINL float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+struct TileShape {
+    int MT, NT, TN, KB;      // m tiles, trial tiles, trials per tile (multiple of 16, <= 128), K blocks of 32
+    int b_row0;              // first row of the B operand inside its tensor map (stacked per-stage operand buffers)
+};
+
+constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4 <= 32
+
+// ---------------------------------------------------------------------------------------------------------------
+// the persistent warp-specialised contraction.  Epi supplies
+//   prepare()                                             once per epilogue thread
+//   rows(m_tile, i, n0, nt, g, tot)                       population i, trials n0 + g*TN/4 + [0, TN/4): tot[] = W_aug.r_aug
+//   tile_done(m_tile, n0, tile_n, etid, nthreads)         per tile, all epilogue threads
+// ---------------------------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+              const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TileShape ts, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)ts.TN * BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * STAGES]), tempty = smem_u32(&bars[2 * STAGES + 1]);
+    const int tiles = ts.MT * ts.NT;
+    const uint32_t acc_stride = (uint32_t)ts.TN;
+    uint32_t ncols = 32;
+    while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile % ts.MT) * BM, n0 = (tile / ts.MT) * ts.TN;
+                for (int kb = 0; kb < ts.KB; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, stage_bytes);
+                    tma_load_2d(base, &mA_hi, fb, kb * BK, m0);
+                    tma_load_2d(base + a_bytes, &mA_lo, fb, kb * BK, m0);
+                    tma_load_2d(base + 2 * a_bytes, &mB_hi, fb, kb * BK, n0 + ts.b_row0);
+                    tma_load_2d(base + 2 * a_bytes + b_bytes, &mB_lo, fb, kb * BK, n0 + ts.b_row0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(ts.TN);
+            const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(tempty, tphase ^ 1);            // epilogue has drained the accumulators of the previous tile
+                tc_fence_after();
+                int j = 0;
+                for (int kb = 0; kb < ts.KB; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t base = ring + stage * stage_bytes;
+                    const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
+                    const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k, ++j) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 TF32 = 32 bytes along the swizzled row
+                        umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                        umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                 // a warp may only read TMEM lanes [32*(warpid%4), +32)
+        const int g = ew >> 2;                        // which quarter of the tile's trials this warp owns
+        const int etid = ew * 32 + lane;
+        const int TNq = ts.TN >> 2;
+        epi.prepare();
+        uint32_t tphase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
+            const int row = m_tile * BM + quarter * 32 + lane;
+            float tot[kMaxQ];
+            mbar_wait(tfull, tphase);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
+#pragma unroll
+            for (int q = 0; q < kMaxQ / 4; ++q) {
+                if (4 * q < TNq) {
+                    uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                    for (int a = 0; a <= kMainAcc; ++a) tmem_ld4_issue(lane_base + a * acc_stride + 4 * q, u[a]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float sum = __uint_as_float(u[kMainAcc][e]);                 // cross terms first (small)
+#pragma unroll
+                        for (int a = 0; a < kMainAcc; ++a) sum += __uint_as_float(u[a][e]);
+                        tot[4 * q + e] = sum;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);        // TMEM is free again: warp 1 may start the next tile
+            tphase ^= 1;
+            epi.rows(m_tile, row, n0, nt, g, TNq, tot);
+            epi.tile_done(m_tile, n0, ts.TN, etid, kEpiWarps * 32);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps, tile shape, launch
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// rows x cols float32 matrix, row-major with `ld` floats per row; box = box_rows x 32 floats, 128-byte swizzle
+inline bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * sizeof(float)};
+    const cuuint32_t box[2] = {BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// trials per tile: multiple of 16, <= 128, minimising (waves x per-tile cost) -- lands on a multiple of the SM count
+inline int pick_tile_n(int MT, int B) {
+    const int sms = num_sms();
+    int best = 16;
+    double best_cost = 1e30;
+    for (int tn = 16; tn <= 128; tn += 16) {
+        const int nt = (B + tn - 1) / tn;
+        const long tiles = (long)MT * nt;
+        const long waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (tn + 24.0);      // 24: per-tile fixed cost in "trial" units (pipeline fill)
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = tn; }
+    }
+    return best;
+}
+
+template <class Epi>
+static int launch_contract(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                           const TileShape& ts, const Epi& epi, cudaStream_t s) {
+    const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)ts.TN * BK * 4) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tc_contract<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return ODECOL_E_CUDA;
+        configured = true;
+    }
+    const int tiles = ts.MT * ts.NT;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    k_tc_contract<Epi><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void k_split_pad(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ hi,
+                            float* __restrict__ lo, int rows_p, int cols_p) {
+    const size_t total = (size_t)rows_p * cols_p;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols_p), c = (int)(e % cols_p);
+        const float x = (r < rows && c < cols) ? src[(size_t)r * ld + c] : 0.0f;
+        const float h = tf32_rna(x);
+        hi[e] = h;
+        lo[e] = tf32_rna(x - h);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fast, FP32-accurate (about 1e-7 relative) elementwise math for the tensor family's epilogue
+// ---------------------------------------------------------------------------------------------------------------
+ODECOL_DEVINL float exp_fast(float x) {            // |x| < 87
+    const float n = rintf(x * 1.4426950408889634f);
+    float f = fmaf(n, -0.693145751953125f, x);
+    f = fmaf(n, -1.42860682030941723212e-6f, f);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f * 1.4426950408889634f));
+    return p * __int_as_float(((int)n + 127) << 23);
+}
+ODECOL_DEVINL float tanh_small(float u) {          // Taylor through u^11: < 3e-8 relative for |u| <= 0.4
+    if (fabsf(u) > 0.4f) return tanhf(u);
+    const float s = u * u;
+    float p = fmaf(s, -8.8632355299021965e-3f, 2.1869488536155203e-2f);   // -1382/155925, 62/2835
+    p = fmaf(s, p, -5.3968253968253968e-2f);                               // -17/315
+    p = fmaf(s, p, 1.3333333333333333e-1f);                                // 2/15
+    p = fmaf(s, p, -3.3333333333333333e-1f);                               // -1/3
+    return fmaf(u * s, p, u);
+}
+ODECOL_DEVINL float phi_fast(float x) {
+    const float x_nom = fmaf(48.0f, x, -981.0f);
+    const float zc = 80.0f * tanh_small(x_nom * (-0.0089f / 80.0f));
+    return __fdividef(x_nom, 1.0f - exp_fast(zc));
+}
+
+ODECOL_DEVINL void phi_dphi_fast(float x, float& r, float& dr) {
+    const float x_nom = fmaf(48.0f, x, -981.0f);
+    const float th = tanh_small(x_nom * (-0.0089f / 80.0f));
+    const float e = exp_fast(80.0f * th);
+    const float inv = __fdividef(1.0f, 1.0f - e);
+    r = x_nom * inv;
+    dr = 48.0f * (inv + r * inv * e * (1.0f - th * th) * (-0.0089f));
+}
+
+// tile-major scratch: element (component c, population i, trial b) with b = nt*TN + g*TNq + 4q + e lives at
+//   c*plane + ((((nt*4 + g)*(TNq/4) + q)*Np + i)*4 + e
+// so the float4 a thread reads for (q, i) sits next to its lane neighbours' (i +- 1): every warp request is one fully
+// used 512-byte run and no sector is ever touched twice (the first layout, row-per-thread, re-read each sector 25 us
+// later and lost it from L2 in between: 6x the DRAM traffic, profiles/r1_tc_v2_ncu.txt).
+struct TileGeom {
+    int NT, Np, TN, TNq;
+    ODECOL_DEVINL size_t plane() const { return (size_t)NT * 4 * Np * TNq; }
+    ODECOL_DEVINL size_t off(int nt, int g, int q, int i) const {
+        return ((((size_t)nt * 4 + g) * (TNq >> 2) + q) * Np + i) * 4;
+    }
+};
+
+template <int S>
+struct FwdEpiT {
+    DevProblem p;
+    TileGeom tg;
+    const float* t;
+    int n, KPa;
+    const float* Y0T;      // [3 planes] state at the start of the step (tile-major)
+    float* Y1T;            // stage 4: state at the end of the step (tile-major)
+    float* traj_row;       // stage 4: (B, 3N) row of the trajectory, or NULL
+    float* K1T; float* K2T; float* K3T;     // [3 planes] each
+    const float* RT_cur;   // [1 plane] r of this stage
+    float* RT_nxt;         // r of the next stage
+    float* Rhi_nxt; float* Rlo_nxt;         // [Bp][KPa] operand of the next contraction
+    float* DRT_nxt;        // optional [1 plane]: phi'(x) of the next stage state (reverse-sweep recompute)
+    float inv_tm, inv_ta, inv_ts;
+    float t0, t1, dt;
+
+    ODECOL_DEVINL void prepare() {
+        t0 = __ldg(t + n); t1 = __ldg(t + n + 1);
+        dt = __fsub_rn(t1, t0);
+    }
+
+    ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (i >= p.N) return;
+        const int N = p.N, B = p.B;
+        const float kap = __ldg(p.kappa + i);
+        const size_t pl = tg.plane();
+        const float third = kOneThirdL;
+#pragma unroll
+        for (int q = 0; q < kMaxQ / 4; ++q) {
+            if (4 * q >= TNq) break;
+            const size_t oq = tg.off(nt, g, q, i);
+            const float4 V0 = ld4(Y0T + oq), A0 = ld4(Y0T + pl + oq), F0 = ld4(Y0T + 2 * pl + oq);
+            const float4 R = ld4(RT_cur + oq);
+            float4 k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+            if (S >= 2) { k1V = ld4(K1T + oq); k1A = ld4(K1T + pl + oq); k1F = ld4(K1T + 2 * pl + oq); }
+            if (S >= 3) { k2V = ld4(K2T + oq); k2A = ld4(K2T + pl + oq); k2F = ld4(K2T + 2 * pl + oq); }
+            if (S >= 4) { k3V = ld4(K3T + oq); k3A = ld4(K3T + pl + oq); k3F = ld4(K3T + 2 * pl + oq); }
+            float oKV[4], oKA[4], oKF[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v0 = (&V0.x)[e], a0 = (&A0.x)[e], f0 = (&F0.x)[e], r = (&R.x)[e];
+                float V, A, F;
+                if (S == 1) { V = v0; A = a0; F = f0; }
+                if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * (&k1A.x)[e] * third; F = f0 + dt * (&k1F.x)[e] * third; }
+                if (S == 3) {
+                    V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third);
+                    A = a0 + dt * ((&k2A.x)[e] - (&k1A.x)[e] * third);
+                    F = f0 + dt * ((&k2F.x)[e] - (&k1F.x)[e] * third);
+                }
+                if (S == 4) {
+                    V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]);
+                    A = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + (&k3A.x)[e]);
+                    F = f0 + dt * ((&k1F.x)[e] - (&k2F.x)[e] + (&k3F.x)[e]);
+                }
+                const float total = tot[4 * q + e] * p.c.tau_s;
+                const float dV = (total * p.c.R - V) * inv_tm;
+                const float dA = (kap * r - A) * inv_ta;
+                const float dF = (r - F) * inv_ts;
+                oKV[e] = dV; oKA[e] = dA; oKF[e] = dF;
+                float nV, nA, nF = 0.f;
+                if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
+                if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - (&k1A.x)[e] * third); }
+                if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + dA); }
+                if (S == 4) {
+                    nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
+                    nA = a0 + ((&k1A.x)[e] + 3.f * ((&k2A.x)[e] + (&k3A.x)[e]) + dA) * dt * 0.125f;
+                    nF = f0 + ((&k1F.x)[e] + 3.f * ((&k2F.x)[e] + (&k3F.x)[e]) + dF) * dt * 0.125f;
+                }
+                oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
+                if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
+                else oR[e] = phi_fast(nV - nA);
+            }
+            if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
+            const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
+            const float4 kA4 = make_float4(oKA[0], oKA[1], oKA[2], oKA[3]);
+            const float4 kF4 = make_float4(oKF[0], oKF[1], oKF[2], oKF[3]);
+            if (S == 1) { st4(K1T + oq, kV4); st4(K1T + pl + oq, kA4); st4(K1T + 2 * pl + oq, kF4); }
+            if (S == 2) { st4(K2T + oq, kV4); st4(K2T + pl + oq, kA4); st4(K2T + 2 * pl + oq, kF4); }
+            if (S == 3) { st4(K3T + oq, kV4); st4(K3T + pl + oq, kA4); st4(K3T + 2 * pl + oq, kF4); }
+            if (S == 4) {
+                st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+                st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+                st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+            }
+            st4(RT_nxt + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = n0 + g * TNq + 4 * q + e;
+                if (b < B) {
+                    const float h = tf32_rna(oR[e]);
+                    Rhi_nxt[(size_t)b * KPa + i] = h;
+                    Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
+                    if (S == 4 && traj_row) {
+                        float* yr = traj_row + (size_t)b * 3 * N + i;
+                        yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
+                    }
+                }
+            }
+        }
+    }
+
+    // stimulus columns of the next operand, written once per trial tile (by the CTA that owns population tile 0)
+    ODECOL_DEVINL void tile_done(int m_tile, int n0, int tile_n, int etid, int nthr) const {
+        if (m_tile != 0 || p.n_in == 0) return;
+        const float tn = S == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : S == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
+        int idx = 1;
+        const float tcl = knot_locate(p.knot_t, p.K, tn, idx);
+        const int n_in = p.n_in, N = p.N;
+        for (int e = etid; e < tile_n * n_in; e += nthr) {
+            const int b = n0 + e / n_in, ch = e % n_in;
+            if (b < p.B) {
+                const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
+                const float h = tf32_rna(v);
+                Rhi_nxt[(size_t)b * KPa + N + ch] = h;
+                Rlo_nxt[(size_t)b * KPa + N + ch] = tf32_rna(v - h);
+            }
+        }
+    }
+};
+
+
+}  // namespace tc
+}  // namespace odecol

@@ -1,0 +1,511 @@
+// Family T reverse sweep: the exact discrete adjoint of the staged RK4 solve with all three contractions on the
+// tensor cores (3xTF32, kernels of stage_tc.cuh):
+//   recompute  W_aug . r_aug           K-major operands, forward stage epilogue + phi'
+//   J^T kbar   W^T . (gamma kbar_V)    K-major operands, reverse stage epilogue (Butcher-tableau transposes of the 3/8 rule)
+//   dW_aug    += (gamma kbar_V)^T r_aug  over the four stages and all trials: both operands MN-major (the same buffers
+//              the other two contractions read K-major), split over trials, reduced with float atomics
+// All per-element bookkeeping lives in tile-major scratch (stage_tc.cuh), float4 along trials.
+#include "stage_tc.cuh"
+
+namespace odecol {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// reverse stage epilogue.  S = 4, 3, 2, 1: the stage whose Jacobian is applied (same algebra as stage_bwd.cu)
+// ---------------------------------------------------------------------------------------------------------------
+template <int S>
+struct BwdEpiT {
+    DevProblem p;
+    TileGeom tg;
+    const float* t;
+    int n, NPk, G;
+    float* acurT;          // [3 planes] kbar of this stage in, of the next reverse stage out
+    float* lamT;           // [3 planes]
+    float* b4T;            // [3 planes] Ybar_4, later Ybar_4 + Ybar_3 + Ybar_2
+    float* b3T;            // [3 planes]
+    const float* DRT;      // [1 plane] phi'(x_s)
+    float* AVhi_nxt; float* AVlo_nxt;   // [Bp][NPk] operand of the next reverse stage (and of dW)
+    const float* grad_y;   // (T, B, G)
+    const int* inv;        // [3N]
+    float gamma, inv_tm, inv_ta, inv_ts;
+    float dt, h8p;
+
+    ODECOL_DEVINL void prepare() {
+        dt = __fsub_rn(__ldg(t + n + 1), __ldg(t + n));
+        h8p = n > 0 ? __fsub_rn(__ldg(t + n), __ldg(t + n - 1)) * 0.125f : 0.f;
+    }
+
+    ODECOL_DEVINL void rows(int, int j, int n0, int nt, int g, int TNq, const float (&graw)[kMaxQ]) const {
+        if (j >= p.N) return;
+        const int N = p.N, B = p.B;
+        const float kap = __ldg(p.kappa + j);
+        const size_t pl = tg.plane();
+        const float h8 = dt * 0.125f, h38 = 3.0f * h8, h3 = dt * kOneThirdL;
+        int gV = -1, gA = -1, gF = -1;
+        if (S == 1) { gV = inv[j]; gA = inv[N + j]; gF = inv[2 * N + j]; }
+#pragma unroll
+        for (int q = 0; q < kMaxQ / 4; ++q) {
+            if (4 * q >= TNq) break;
+            const size_t oq = tg.off(nt, g, q, j);
+            const float4 aV = ld4(acurT + oq), aA = ld4(acurT + pl + oq), aF = ld4(acurT + 2 * pl + oq);
+            const float4 dr = ld4(DRT + oq);
+            const float4 lV = ld4(lamT + oq), lA = ld4(lamT + pl + oq), lF = ld4(lamT + 2 * pl + oq);
+            float4 p4V, p4A, p4F, p3V, p3A, p3F;
+            if (S <= 3) { p4V = ld4(b4T + oq); p4A = ld4(b4T + pl + oq); p4F = ld4(b4T + 2 * pl + oq); }
+            if (S == 2) { p3V = ld4(b3T + oq); p3A = ld4(b3T + pl + oq); p3F = ld4(b3T + 2 * pl + oq); }
+            float nV[4], nA[4], nF[4], sV[4], sA[4], sF[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float av = (&aV.x)[e], aa = (&aA.x)[e], af = (&aF.x)[e], d = (&dr.x)[e];
+                const float gg = graw[4 * q + e] + kap * aa * inv_ta + af * inv_ts;
+                const float bV = -av * inv_tm + d * gg;
+                const float bA = -aa * inv_ta - d * gg;
+                const float bF = -af * inv_ts;
+                if (S == 4) {
+                    sV[e] = bV; sA[e] = bA; sF[e] = bF;
+                    nV[e] = h38 * (&lV.x)[e] + dt * bV; nA[e] = h38 * (&lA.x)[e] + dt * bA; nF[e] = h38 * (&lF.x)[e] + dt * bF;
+                }
+                if (S == 3) {
+                    sV[e] = bV; sA[e] = bA; sF[e] = bF;
+                    nV[e] = h38 * (&lV.x)[e] - dt * (&p4V.x)[e] + dt * bV;
+                    nA[e] = h38 * (&lA.x)[e] - dt * (&p4A.x)[e] + dt * bA;
+                    nF[e] = h38 * (&lF.x)[e] - dt * (&p4F.x)[e] + dt * bF;
+                }
+                if (S == 2) {
+                    nV[e] = h8 * (&lV.x)[e] + dt * (&p4V.x)[e] - h3 * (&p3V.x)[e] + h3 * bV;
+                    nA[e] = h8 * (&lA.x)[e] + dt * (&p4A.x)[e] - h3 * (&p3A.x)[e] + h3 * bA;
+                    nF[e] = h8 * (&lF.x)[e] + dt * (&p4F.x)[e] - h3 * (&p3F.x)[e] + h3 * bF;
+                    sV[e] = (&p4V.x)[e] + (&p3V.x)[e] + bV; sA[e] = (&p4A.x)[e] + (&p3A.x)[e] + bA; sF[e] = (&p4F.x)[e] + (&p3F.x)[e] + bF;
+                }
+                if (S == 1) {
+                    const int b = n0 + g * TNq + 4 * q + e;
+                    float gv = 0.f, ga = 0.f, gf = 0.f;
+                    if (b < B) {
+                        const float* gy = grad_y + ((size_t)n * B + b) * G;
+                        if (gV >= 0) gv = gy[gV];
+                        if (gA >= 0) ga = gy[gA];
+                        if (gF >= 0) gf = gy[gF];
+                    }
+                    const float LV = (&lV.x)[e] + (&p4V.x)[e] + bV + gv;
+                    const float LA = (&lA.x)[e] + (&p4A.x)[e] + bA + ga;
+                    const float LF = (&lF.x)[e] + (&p4F.x)[e] + bF + gf;
+                    sV[e] = LV; sA[e] = LA; sF[e] = LF;
+                    nV[e] = h8p * LV; nA[e] = h8p * LA; nF[e] = h8p * LF;
+                }
+            }
+            float* sdst = S == 4 ? b4T : S == 3 ? b3T : S == 2 ? b4T : lamT;
+            st4(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
+            st4(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
+            st4(sdst + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
+            st4(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
+            st4(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
+            st4(acurT + 2 * pl + oq, make_float4(nF[0], nF[1], nF[2], nF[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = n0 + g * TNq + 4 * q + e;
+                if (b < B) {
+                    const float v = gamma * nV[e];
+                    const float h = tf32_rna(v);
+                    AVhi_nxt[(size_t)b * NPk + j] = h;
+                    AVlo_nxt[(size_t)b * NPk + j] = tf32_rna(v - h);
+                }
+            }
+        }
+    }
+    ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-step operand setup: y_traj[n] (API layout) -> tile-major Y0T, r / phi' of stage 1, split operand with stimulus
+// One CTA per group of four trials (one float4 of the tile-major layout), threads over populations.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_tc_step_begin(DevProblem p, TileGeom tg, const float* __restrict__ y, const float* __restrict__ t_ptr,
+                                float* __restrict__ hi0, float* __restrict__ lo0, float* __restrict__ Y0T,
+                                float* __restrict__ RT, float* __restrict__ DRT, int KPa) {
+    const int b4 = blockIdx.x * 4, N = p.N;
+    const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
+    const size_t pl = tg.plane();
+    for (int i = threadIdx.x; i < tg.Np; i += blockDim.x) {
+        float V[4], A[4], F[4], R[4], D[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int b = b4 + e;
+            const bool in = i < N && b < p.B;
+            const float* yb = y + (size_t)b * 3 * N;
+            V[e] = in ? yb[i] : 0.f; A[e] = in ? yb[N + i] : 0.f; F[e] = in ? yb[2 * N + i] : 0.f;
+            R[e] = 0.f; D[e] = 0.f;
+            if (in) {
+                phi_dphi_fast(V[e] - A[e], R[e], D[e]);
+                const float h = tf32_rna(R[e]);
+                hi0[(size_t)b * KPa + i] = h;
+                lo0[(size_t)b * KPa + i] = tf32_rna(R[e] - h);
+            }
+        }
+        const size_t o = tg.off(nt, g, q, i);
+        st4(Y0T + o, make_float4(V[0], V[1], V[2], V[3]));
+        st4(Y0T + pl + o, make_float4(A[0], A[1], A[2], A[3]));
+        st4(Y0T + 2 * pl + o, make_float4(F[0], F[1], F[2], F[3]));
+        st4(RT + o, make_float4(R[0], R[1], R[2], R[3]));
+        if (DRT) st4(DRT + o, make_float4(D[0], D[1], D[2], D[3]));
+    }
+    // stimulus channels, constant-one column
+    int idx = 1;
+    const float tcl = knot_locate(p.knot_t, p.K, __ldg(t_ptr), idx);
+    for (int e = threadIdx.x; e < 4 * (p.n_in + 1); e += blockDim.x) {
+        const int b = b4 + e / (p.n_in + 1), ch = e % (p.n_in + 1);
+        if (b >= p.B) continue;
+        float v = 1.0f;
+        if (ch < p.n_in) v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, p.n_in, idx, tcl, ch);
+        const float h = tf32_rna(v);
+        hi0[(size_t)b * KPa + N + ch] = h;
+        lo0[(size_t)b * KPa + N + ch] = tf32_rna(v - h);
+    }
+}
+
+// lam = dL/dy_out[T-1] (tile-major), kbar_4 of the last step, its operand
+__global__ void k_tc_bwd_begin(DevProblem p, TileGeom tg, const float* __restrict__ grad_y, const int* __restrict__ inv,
+                               int G, const float* __restrict__ t, int T, float gamma, float* __restrict__ lamT,
+                               float* __restrict__ acurT, float* __restrict__ AVhi, float* __restrict__ AVlo, int NPk) {
+    const int b4 = blockIdx.x * 4, N = p.N;
+    const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
+    const size_t pl = tg.plane();
+    const float h8 = __fsub_rn(__ldg(t + T - 1), __ldg(t + T - 2)) * 0.125f;
+    for (int i = threadIdx.x; i < tg.Np; i += blockDim.x) {
+        float L[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = b4 + e;
+                float v = 0.f;
+                if (i < N && b < p.B) {
+                    const int gi = inv[c * N + i];
+                    if (gi >= 0) v = grad_y[((size_t)(T - 1) * p.B + b) * G + gi];
+                }
+                L[c][e] = v;
+            }
+        const size_t o = tg.off(nt, g, q, i);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            st4(lamT + c * pl + o, make_float4(L[c][0], L[c][1], L[c][2], L[c][3]));
+            st4(acurT + c * pl + o, make_float4(h8 * L[c][0], h8 * L[c][1], h8 * L[c][2], h8 * L[c][3]));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int b = b4 + e;
+            if (i < N && b < p.B) {
+                const float v = gamma * h8 * L[0][e];
+                const float h = tf32_rna(v);
+                AVhi[(size_t)b * NPk + i] = h;
+                AVlo[(size_t)b * NPk + i] = tf32_rna(v - h);
+            }
+        }
+    }
+}
+
+// grad_y0 (API layout) from the tile-major adjoint
+__global__ void k_tc_untile(DevProblem p, TileGeom tg, const float* __restrict__ srcT, float* __restrict__ dst) {
+    const int b4 = blockIdx.x * 4, N = p.N;
+    const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
+    const size_t pl = tg.plane();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const size_t o = tg.off(nt, g, q, i);
+        for (int c = 0; c < 3; ++c) {
+            const float4 v = ld4(srcT + c * pl + o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (b4 + e < p.B) dst[(size_t)(b4 + e) * 3 * N + c * N + i] = (&v.x)[e];
+        }
+    }
+}
+
+// constant-one column (the bias input) of the four stacked operand buffers
+__global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, int col) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * B) return;
+    const int s = e / B, b = e % B;
+    Rhi[((size_t)s * Bp + b) * KPa + col] = 1.0f;
+}
+
+__global__ void k_tc_build_inv(const int* __restrict__ sel, int G, int n3, int* __restrict__ inv) {
+    for (int e = threadIdx.x; e < n3; e += blockDim.x) inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) inv[sel[g]] = g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW contraction: C[i][k] += sum_rows A[row][i] * B[row][k], rows = stacked (stage, trial); both operands MN-major.
+// Same warp roles as k_tc_contract; one output tile and one slice of the rows per CTA; epilogue = float atomics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_BK = 32;        // rows (trials) per K block = four 8-row swizzle atoms
+constexpr int DW_T = 128;        // output tile: 128 x 128
+
+ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((DW_BK * 128) >> 4) << 16;        // leading byte offset: next 32-wide block along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; };
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+        const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t box_bytes = DW_BK * 128;                 // 32 rows x 32 floats
+    constexpr uint32_t op_bytes = 4 * box_bytes;                // 128 columns
+    constexpr uint32_t stage_bytes = 4 * op_bytes;              // A hi, A lo, B hi, B lo
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+    constexpr uint32_t ncols = 512;
+    const int tile = blockIdx.x % (ds.MT * ds.NT), z = blockIdx.x / (ds.MT * ds.NT);
+    const int i0 = (tile % ds.MT) * DW_T, k0 = (tile / ds.MT) * DW_T;
+    const int r0 = z * ds.rows_per_split;
+    int r1 = r0 + ds.rows_per_split;
+    if (r1 > ds.total_rows) r1 = ds.total_rows;
+    const int KB = (r1 - r0) / DW_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
+                mbar_expect_tx(fb, stage_bytes);
+                const int row = r0 + kb * DW_BK;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    tma_load_2d(base + m * box_bytes, &mA_hi, fb, i0 + 32 * m, row);
+                    tma_load_2d(base + op_bytes + m * box_bytes, &mA_lo, fb, i0 + 32 * m, row);
+                    tma_load_2d(base + 2 * op_bytes + m * box_bytes, &mB_hi, fb, k0 + 32 * m, row);
+                    tma_load_2d(base + 3 * op_bytes + m * box_bytes, &mB_lo, fb, k0 + 32 * m, row);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // c=F32, a=b=TF32, both MN-major (bits 15, 16), N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(DW_T >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t d_small = tmem_base + kMainAcc * DW_T;
+            int stage = 0; uint32_t phase = 0;
+            int j = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t base = ring + stage * stage_bytes;
+                const uint64_t a_hi = make_smem_desc_mn(base), a_lo = make_smem_desc_mn(base + op_bytes);
+                const uint64_t b_hi = make_smem_desc_mn(base + 2 * op_bytes), b_lo = make_smem_desc_mn(base + 3 * op_bytes);
+#pragma unroll
+                for (int k = 0; k < DW_BK / 8; ++k, ++j) {
+                    const uint64_t adv = (uint64_t)(k * 1024 >> 4);     // next 8-row swizzle atom
+                    umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                    umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                }
+                umma_commit(empty0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (KB > 0) {
+        const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
+        const int i = i0 + quarter * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+            for (int a = 0; a <= kMainAcc; ++a) tmem_ld4_issue(lane_base + a * DW_T + 4 * q, u[a]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float sum = __uint_as_float(u[kMainAcc][e]);
+#pragma unroll
+                for (int a = 0; a < kMainAcc; ++a) sum += __uint_as_float(u[a][e]);
+                const int k = k0 + g * 32 + 4 * q + e;
+                if (i < ds.N && k < ds.Kaug) atomicAdd(ds.grad_W + (size_t)i * ds.ld_w + k, sum);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// rows x cols float32 matrix, box = box_rows x 32 floats (MN-major operand boxes reuse make_map with box_rows = 32)
+
+__global__ void k_split_pad_T(const float* __restrict__ src, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
+                              int rows_p, int cols_p) {
+    // hi/lo of the transpose of the leading n x n block
+    const size_t total = (size_t)rows_p * cols_p;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols_p), c = (int)(e % cols_p);
+        const float x = (r < n && c < n) ? src[(size_t)c * ld + r] : 0.0f;
+        const float h = tf32_rna(x);
+        hi[e] = h;
+        lo[e] = tf32_rna(x - h);
+    }
+}
+
+struct TcBwdLayout {
+    int Np, Bp, KPa, NPk, TN;
+    size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo;   // stacked x4 operand buffers
+    size_t off_K[3], off_Y, off_RT, off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, total;
+};
+
+static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
+    TcBwdLayout L;
+    L.Np = round_up(p.N, BM);
+    L.NPk = L.Np;
+    L.KPa = round_up(p.N + p.n_in + 1, BK);
+    L.TN = pick_tile_n(L.Np / BM, p.B);
+    L.Bp = round_up(p.B, L.TN);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
+    L.off_WThi = take(4ull * L.Np * L.NPk); L.off_WTlo = take(4ull * L.Np * L.NPk);
+    L.off_Rhi = take(16ull * L.Bp * L.KPa); L.off_Rlo = take(16ull * L.Bp * L.KPa);
+    L.off_AVhi = take(16ull * L.Bp * L.NPk); L.off_AVlo = take(16ull * L.Bp * L.NPk);
+    const size_t plane = 4ull * L.Np * L.Bp;
+    for (int i = 0; i < 3; ++i) L.off_K[i] = take(3 * plane);
+    L.off_Y = take(3 * plane);
+    L.off_RT = take(plane);
+    for (int i = 0; i < 4; ++i) L.off_DRT[i] = take(plane);
+    L.off_lam = take(3 * plane); L.off_b4 = take(3 * plane); L.off_b3 = take(3 * plane); L.off_acur = take(3 * plane);
+    L.off_inv = take(sizeof(int) * 3ull * p.N);
+    L.total = o;
+    return L;
+}
+
+}  // namespace tc
+
+size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_bwd_layout(p).total; }
+
+int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
+               int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const TcBwdLayout L = tc_bwd_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *WThi = F(L.off_WThi), *WTlo = F(L.off_WTlo);
+    float *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo), *AVhi = F(L.off_AVhi), *AVlo = F(L.off_AVlo);
+    float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
+    float *YT = F(L.off_Y), *RT = F(L.off_RT);
+    float* DRT[4] = {F(L.off_DRT[0]), F(L.off_DRT[1]), F(L.off_DRT[2]), F(L.off_DRT[3])};
+    float *lamT = F(L.off_lam), *b4T = F(L.off_b4), *b3T = F(L.off_b3), *acurT = F(L.off_acur);
+    int* inv = reinterpret_cast<int*>(w + L.off_inv);
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+    const float gamma = p.c.tau_s * p.c.R / p.c.tau_m;
+    const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
+    const size_t rstride = (size_t)L.Bp * L.KPa, astride = (size_t)L.Bp * L.NPk;
+
+    // zero the stacked operand buffers once: padding rows / columns must stay zero
+    if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_K[0] - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+    k_split_pad_T<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, WThi, WTlo, L.Np, L.NPk);
+    k_tc_set_one<<<(4 * p.B + 255) / 256, 256, 0, s>>>(Rhi, L.Bp, p.B, L.KPa, Kaug - 1);
+    k_tc_build_inv<<<1, 256, 0, s>>>(sel, G, 3 * p.N, inv);
+    k_tc_bwd_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, grad_y, inv, G, t_dev, T, gamma, lamT, acurT, AVhi + 3 * astride,
+                                           AVlo + 3 * astride, L.NPk);
+    count_launch(5);
+
+    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo, dAhi, dAlo, dBhi, dBlo;
+    bool ok = make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) && make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) &&
+              make_map(&mWThi, WThi, L.Np, L.NPk, L.NPk, BM) && make_map(&mWTlo, WTlo, L.Np, L.NPk, L.NPk, BM) &&
+              make_map(&mRhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, L.TN) &&
+              make_map(&mAVhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, L.TN) && make_map(&mAVlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, L.TN) &&
+              make_map(&dAhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, DW_BK) && make_map(&dAlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK) &&
+              make_map(&dBhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK) && make_map(&dBlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK);
+    if (!ok) return ODECOL_E_CUDA;
+
+    // dW launch shape: output tiles x splits of the stacked rows, about three waves of CTAs
+    DwShape ds;
+    ds.MT = L.Np / DW_T; ds.NT = (L.KPa + DW_T - 1) / DW_T;
+    ds.total_rows = 4 * L.Bp;
+    int z = (3 * num_sms()) / (ds.MT * ds.NT);
+    if (z < 1) z = 1;
+    int rows = (ds.total_rows / DW_BK + z - 1) / z * DW_BK;
+    if (rows < DW_BK) rows = DW_BK;
+    ds.rows_per_split = rows; ds.Z = (ds.total_rows + rows - 1) / rows;
+    ds.N = p.N; ds.Kaug = Kaug; ds.ld_w = p.ld_w; ds.grad_W = grad_W;
+    const size_t dw_smem = (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024;
+    static bool dw_configured = false;
+    if (!dw_configured) {
+        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
+        dw_configured = true;
+    }
+
+    const int MT = L.Np / BM, NT = L.Bp / L.TN;
+    for (int n = T - 2; n >= 0; --n) {
+        const float* yn = y_traj + (size_t)n * st;
+        k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT, DRT[0], L.KPa);
+        count_launch();
+        // recompute stages 1..3: operand s -> operand s+1, r and phi' of the next stage state
+        auto fill_f = [&](auto& e, int S) {
+            e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
+            e.Y0T = YT; e.Y1T = nullptr; e.traj_row = nullptr;
+            e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
+            e.RT_cur = RT; e.RT_nxt = RT;                       // in place: each element is read then written by its owner
+            e.Rhi_nxt = Rhi + S * rstride; e.Rlo_nxt = Rlo + S * rstride; e.DRT_nxt = DRT[S];
+            e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+            e.t0 = e.t1 = e.dt = 0.f;
+        };
+        int rc;
+        { FwdEpiT<1> e; fill_f(e, 1); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 0 * L.Bp}, e, s); if (rc) return rc; }
+        { FwdEpiT<2> e; fill_f(e, 2); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 1 * L.Bp}, e, s); if (rc) return rc; }
+        { FwdEpiT<3> e; fill_f(e, 3); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 2 * L.Bp}, e, s); if (rc) return rc; }
+        // reverse stages 4, 3, 2, then dW, then stage 1 (which overwrites the stage-4 operand for the next step)
+        auto fill_b = [&](auto& e, int S) {
+            e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
+            e.acurT = acurT; e.lamT = lamT; e.b4T = b4T; e.b3T = b3T; e.DRT = DRT[S - 1];
+            const int nxt = S == 1 ? 3 : S - 2;                 // operand buffer the epilogue writes
+            e.AVhi_nxt = AVhi + nxt * astride; e.AVlo_nxt = AVlo + nxt * astride;
+            e.grad_y = grad_y; e.inv = inv; e.gamma = gamma;
+            e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+            e.dt = e.h8p = 0.f;
+        };
+        { BwdEpiT<4> e; fill_b(e, 4); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 3 * L.Bp}, e, s); if (rc) return rc; }
+        { BwdEpiT<3> e; fill_b(e, 3); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 2 * L.Bp}, e, s); if (rc) return rc; }
+        { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 1 * L.Bp}, e, s); if (rc) return rc; }
+        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi, dAlo, dBhi, dBlo, ds);
+        count_launch();
+        { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 0 * L.Bp}, e, s); if (rc) return rc; }
+    }
+    if (grad_y0) {
+        k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);
+        count_launch();
+    }
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+}  // namespace odecol
