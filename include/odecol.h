@@ -174,6 +174,12 @@ size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K);
 int odecol_tc_contract(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: the MN-major variant used for the dW accumulation, C[m][n] = sum_k A[k][m] * B[k][n] for row-major
+ * A (K x M), B (K x N), C (M x N). */
+size_t odecol_tc_contract_tn_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int odecol_tc_contract_tn(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Which kernel family a call would use: 0 = persistent on-chip ("small", W row in registers),
  * 1 = staged FP32-FFMA contraction, 2 = staged 3xTF32 tcgen05 contraction.  Diagnostic only. */
 int odecol_kernel_family(const odecol_problem* p, int op);

@@ -223,4 +223,18 @@ int odecol_tc_contract(const float* A, const float* B, float* C, int32_t M, int3
     return tc_contract(A, B, C, M, N, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+size_t odecol_tc_contract_tn_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return tc_contract_tn_workspace_bytes(M, N, K);
+}
+
+int odecol_tc_contract_tn(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!A || !B || !C) return ODECOL_E_NULL;
+    if (M <= 0 || N <= 0 || K <= 0) return ODECOL_E_SHAPE;
+    if (misaligned(workspace)) return ODECOL_E_ALIGN;
+    g_launches = 0;
+    return tc_contract_tn(A, B, C, M, N, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

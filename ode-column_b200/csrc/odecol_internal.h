@@ -66,6 +66,8 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int T);
 int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
                int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t tc_contract_tn_workspace_bytes(int M, int N, int K);
+int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_contract_workspace_bytes(int M, int N, int K);
 int tc_contract(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s);
 

@@ -235,22 +235,26 @@ __global__ void k_tc_build_inv(const int* __restrict__ sel, int G, int n3, int* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // dW contraction: C[i][k] += sum_rows A[row][i] * B[row][k], rows = stacked (stage, trial); both operands MN-major.
+// For 32-bit operands the tensor core reads MN-major tiles only in the "128-byte swizzle with 32-byte atoms" layout:
+// TMA boxes of 32 rows x 32 floats with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; in the descriptor a K atom is 4 rows
+// (512 bytes, the stride byte offset), the next 32-wide block along M/N is one box further (leading byte offset),
+// and one tcgen05.mma (K = 8) consumes two atoms, i.e. 1024 bytes.
 // Same warp roles as k_tc_contract; one output tile and one slice of the rows per CTA; epilogue = float atomics.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DW_BK = 32;        // rows (trials) per K block = four 8-row swizzle atoms
 constexpr int DW_T = 128;        // output tile: 128 x 128
 
-ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((DW_BK * 128) >> 4) << 16;        // leading byte offset: next 32-wide block along M/N
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row group along K
+    d |= (uint64_t)(lbo >> 4) << 16;                  // leading byte offset: next 32-wide block along M/N
+    d |= (uint64_t)(sbo >> 4) << 32;                  // stride byte offset: next 8-row group along K
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B: the only MN-major layout for 32-bit operands
     return d;
 }
 
-struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; };
+struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv; };
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -307,7 +311,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
     } else if (warp == 1) {
         if (lane == 0) {
             // c=F32, a=b=TF32, both MN-major (bits 15, 16), N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
                                    ((uint32_t)(DW_T >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t d_small = tmem_base + kMainAcc * DW_T;
             int stage = 0; uint32_t phase = 0;
@@ -316,11 +320,11 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t base = ring + stage * stage_bytes;
-                const uint64_t a_hi = make_smem_desc_mn(base), a_lo = make_smem_desc_mn(base + op_bytes);
-                const uint64_t b_hi = make_smem_desc_mn(base + 2 * op_bytes), b_lo = make_smem_desc_mn(base + 3 * op_bytes);
+                const uint64_t a_hi = make_smem_desc_mn(base, ds.lbo, ds.sbo), a_lo = make_smem_desc_mn(base + op_bytes, ds.lbo, ds.sbo);
+                const uint64_t b_hi = make_smem_desc_mn(base + 2 * op_bytes, ds.lbo, ds.sbo), b_lo = make_smem_desc_mn(base + 3 * op_bytes, ds.lbo, ds.sbo);
 #pragma unroll
                 for (int k = 0; k < DW_BK / 8; ++k, ++j) {
-                    const uint64_t adv = (uint64_t)(k * 1024 >> 4);     // next 8-row swizzle atom
+                    const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);   // next 8-row swizzle atom
                     umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
                     umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
                     umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
@@ -406,6 +410,41 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
 
 }  // namespace tc
 
+// diagnostic: C[m][n] += sum_k A[k][m] * B[k][n] with the MN-major contraction the dW accumulation uses
+size_t tc_contract_tn_workspace_bytes(int M, int N, int K) {
+    const size_t Mp = round_up(M, 128), Np = round_up(N, 32), Kp = round_up(K, 64);
+    return 4 * (2 * Kp * Mp + 2 * Kp * Np) + 4096;
+}
+
+int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const int Mp = round_up(M, 128), Np = round_up(N, 32), Kp = round_up(K, 64);
+    if (!ws || ws_bytes < tc_contract_tn_workspace_bytes(M, N, K)) return ODECOL_E_WORKSPACE;
+    float* Ahi = static_cast<float*>(ws);
+    float* Alo = Ahi + (size_t)Kp * Mp;
+    float* Bhi = Alo + (size_t)Kp * Mp;
+    float* Blo = Bhi + (size_t)Kp * Np;
+    k_split_pad<<<296, 256, 0, s>>>(A, K, M, M, Ahi, Alo, Kp, Mp);
+    k_split_pad<<<296, 256, 0, s>>>(B, K, N, N, Bhi, Blo, Kp, Np);
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!make_map(&a_hi, Ahi, Kp, Mp, Mp, DW_BK, sw) || !make_map(&a_lo, Alo, Kp, Mp, Mp, DW_BK, sw) ||
+        !make_map(&b_hi, Bhi, Kp, Np, Np, DW_BK, sw) || !make_map(&b_lo, Blo, Kp, Np, Np, DW_BK, sw))
+        return ODECOL_E_CUDA;
+    DwShape ds;
+    ds.MT = Mp / DW_T; ds.NT = (Np + DW_T - 1) / DW_T; ds.total_rows = Kp;
+    int z = 2;
+    int rows = (Kp / DW_BK + z - 1) / z * DW_BK;
+    ds.rows_per_split = rows; ds.Z = (Kp + rows - 1) / rows;
+    ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C;
+    ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
+    if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+    count_launch(3);
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_bwd_layout(p).total; }
 
 int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
@@ -444,8 +483,10 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
               make_map(&mWThi, WThi, L.Np, L.NPk, L.NPk, BM) && make_map(&mWTlo, WTlo, L.Np, L.NPk, L.NPk, BM) &&
               make_map(&mRhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, L.TN) &&
               make_map(&mAVhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, L.TN) && make_map(&mAVlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, L.TN) &&
-              make_map(&dAhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, DW_BK) && make_map(&dAlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK) &&
-              make_map(&dBhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK) && make_map(&dBlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK);
+              make_map(&dAhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dAlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dBhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dBlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (!ok) return ODECOL_E_CUDA;
 
     // dW launch shape: output tiles x splits of the stacked rows, about three waves of CTAs
@@ -458,6 +499,7 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
     if (rows < DW_BK) rows = DW_BK;
     ds.rows_per_split = rows; ds.Z = (ds.total_rows + rows - 1) / rows;
     ds.N = p.N; ds.Kaug = Kaug; ds.ld_w = p.ld_w; ds.grad_W = grad_W;
+    ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
     const size_t dw_smem = (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024;
     static bool dw_configured = false;
     if (!dw_configured) {

@@ -210,6 +210,19 @@ torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
     return C;
 }
 
+torch::Tensor tc_contract_tn(const torch::Tensor& A, const torch::Tensor& B) {
+    c10::cuda::CUDAGuard g(A.device());
+    want(A, "A"); want(B, "B");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(0) == B.size(0), "odecol: tc_contract_tn wants A (K,M), B (K,N)");
+    const int64_t K = A.size(0), M = A.size(1), N = B.size(1);
+    auto C = torch::empty({M, N}, A.options());
+    const size_t bytes = odecol_tc_contract_tn_workspace_bytes((int32_t)M, (int32_t)N, (int32_t)K);
+    auto ws = torch::empty({(int64_t)bytes}, A.options().dtype(torch::kUInt8));
+    check(odecol_tc_contract_tn(A.data_ptr<float>(), B.data_ptr<float>(), C.data_ptr<float>(), (int32_t)M, (int32_t)N, (int32_t)K,
+                                ws.data_ptr(), bytes, at::cuda::getCurrentCUDAStream(A.device().index()).stream()), "tc_contract_tn");
+    return C;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -236,6 +249,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_fwd", &em_fwd);
     m.def("em_bwd", &em_bwd);
     m.def("tc_contract", &tc_contract);
+    m.def("tc_contract_tn", &tc_contract_tn);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;
     m.attr("OP_RK4_FWD") = (int)ODECOL_OP_RK4_FWD;
     m.attr("OP_RK4_BWD") = (int)ODECOL_OP_RK4_BWD;

@@ -23,3 +23,19 @@ def test_tc_contract_matches_float64(M, N, K):
     fp32 = float((((B @ A.T).double() - ref).abs() / mag).max())
     print(f"\ntc_contract {M}x{N}x{K}: max err / sum|a||b| = {err:.2e} (cuBLAS fp32: {fp32:.2e})")
     assert err < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 577, 1000), (200, 96, 4096)])
+def test_tc_contract_tn_matches_float64(M, N, K):
+    """The MN-major variant (both operands read along their contiguous dimension) used for dW_aug."""
+    ext = odecol._native.ext()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(K, M, generator=g) * 3).to(DEV)
+    B = (torch.randn(K, N, generator=g).abs() * 5).to(DEV)
+    C = ext.tc_contract_tn(A, B)
+    torch.cuda.synchronize()
+    ref = A.double().T @ B.double()
+    mag = A.double().abs().T @ B.double().abs()
+    err = float(((C.double() - ref).abs() / mag).max())
+    print(f"\ntc_contract_tn {M}x{N}x{K}: max err / sum|a||b| = {err:.2e}; |C|max {float(C.abs().max()):.3e} |ref|max {float(ref.abs().max()):.3e}")
+    assert err < 2e-6
