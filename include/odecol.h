@@ -11,7 +11,7 @@
  *   - calls are asynchronous with respect to the host and ordered on `stream` (a cudaStream_t passed as
  *     void* so that the header needs no CUDA include);
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
- *   - re-entrant across streams, no global mutable state, one GPU per call (multi-GPU orchestration is
+ *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
  *   - there is NO CPU implementation behind this ABI.
  *
@@ -184,7 +184,7 @@ int odecol_tc_contract_tn(const float* A, const float* B, float* C, int32_t M, i
  * 1 = staged FP32-FFMA contraction, 2 = staged 3xTF32 tcgen05 contraction.  Diagnostic only. */
 int odecol_kernel_family(const odecol_problem* p, int op);
 
-/* Number of kernel launches the last call of `op` on this thread enqueued (for bench bookkeeping). */
+/* Number of kernel launches the most recent entry-point call enqueued (process-wide, for bench bookkeeping). */
 int64_t odecol_last_launch_count(void);
 
 #ifdef __cplusplus

@@ -1,13 +1,16 @@
 // C-ABI shim (include/odecol.h): validates arguments, picks the kernel family, launches on the caller's stream.
-// No allocation, no synchronisation, no global mutable state (the launch counter is thread local).
+// No allocation, no synchronisation, no global state that affects results (one diagnostic launch counter).
+#include <atomic>
 #include <cstring>
 #include <cmath>
 #include "odecol_internal.h"
 
 namespace odecol {
 
-static thread_local int64_t g_launches = 0;
-void count_launch(int n) { g_launches += n; }
+// diagnostic only: kernels enqueued by the most recent call (autograd runs backward on its own thread, so this is a
+// process-wide relaxed atomic rather than a thread-local; it never influences a computation)
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int to_dev(const odecol_problem* p, DevProblem& d) {
     if (!p || !p->W_aug || !p->kappa || !p->knot_t || !p->knot_u) return ODECOL_E_NULL;
@@ -66,7 +69,7 @@ const char* odecol_strerror(int code) {
     }
 }
 
-int64_t odecol_last_launch_count(void) { return g_launches; }
+int64_t odecol_last_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int odecol_kernel_family(const odecol_problem* p, int op) {
     DevProblem d;
@@ -93,7 +96,7 @@ int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f
     const int rc = to_dev(p, d);
     if (rc) return rc;
     if (!t || !y || !f) return ODECOL_E_NULL;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     return launch_rhs_generic(d, t, y, f, static_cast<cudaStream_t>(stream));
 }
 
@@ -104,7 +107,7 @@ int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const flo
     if (rc) return rc;
     if (!t || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || out_every < 1) return ODECOL_E_SHAPE;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_small(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
@@ -120,7 +123,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
     if (rc) return rc;
     if (!t || !y_traj || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (use_small(p, d)) return launch_rk4_bwd_small(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, s);
@@ -138,7 +141,7 @@ int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const 
     if (rc) return rc;
     if (!t || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;   // per-trial dopri5 exists in the on-chip family only
     return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status,
                                    static_cast<cudaStream_t>(stream));
@@ -172,7 +175,7 @@ int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
     if (adaptive && (dW || y_steps || !(dt_min > 0.f))) return ODECOL_E_UNSUPPORTED;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_small(p, d)) {
         // attempts are bounded: a step at dt_min is always accepted
@@ -197,7 +200,7 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
     const EmScheduleLayout L = em_schedule_layout(T, n_steps);
     if (!workspace || workspace_bytes < L.total) return ODECOL_E_WORKSPACE;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* w = static_cast<char*>(workspace);
     int* step_of = reinterpret_cast<int*>(w + L.off_step);
@@ -219,7 +222,7 @@ int odecol_tc_contract(const float* A, const float* B, float* C, int32_t M, int3
     if (!A || !B || !C) return ODECOL_E_NULL;
     if (M <= 0 || N <= 0 || K <= 0) return ODECOL_E_SHAPE;
     if (misaligned(workspace)) return ODECOL_E_ALIGN;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     return tc_contract(A, B, C, M, N, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -233,7 +236,7 @@ int odecol_tc_contract_tn(const float* A, const float* B, float* C, int32_t M, i
     if (!A || !B || !C) return ODECOL_E_NULL;
     if (M <= 0 || N <= 0 || K <= 0) return ODECOL_E_SHAPE;
     if (misaligned(workspace)) return ODECOL_E_ALIGN;
-    g_launches = 0;
+    g_launches.store(0, std::memory_order_relaxed);
     return tc_contract_tn(A, B, C, M, N, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
