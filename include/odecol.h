@@ -141,6 +141,25 @@ int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const 
                       int32_t* n_accept, int32_t* n_reject, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training-mode variant of odecol_dopri5_fwd: additionally records every ACCEPTED step so that odecol_dopri5_bwd can
+ * differentiate through them (discretise-then-optimise, what loss.backward() through torchdiffeq's adaptive steps
+ * computes; reference scripts/xor_ode.py:114,177 -- rejected attempts and the step controller carry no gradient).
+ *   rec_y     (cap, B, 3N)  state at the start of accepted step n
+ *   rec_t0, rec_dt (B, cap) float64 start time and size of accepted step n
+ *   out_step, out_x (B, T)  for every output time the accepted step it lies in and the dense-output abscissa
+ * A trial that needs more than `cap` accepted steps stops with ODECOL_ST_MAXSTEPS (retry with a larger cap). */
+int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
+                             float rtol, float atol, int32_t max_steps,
+                             int32_t* n_accept, int32_t* n_reject, int32_t* status,
+                             float* rec_y, double* rec_t0, double* rec_dt, int32_t* out_step, float* out_x, int32_t cap,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse sweep over the recorded steps; grad_y / sel / G / grad_y0 / grad_W_aug as in odecol_rk4_bwd. */
+int odecol_dopri5_bwd(const odecol_problem* p, int32_t T, const float* rec_y, const double* rec_t0, const double* rec_dt,
+                      const int32_t* out_step, const float* out_x, int32_t cap, const int32_t* n_accept,
+                      const float* grad_y, const int32_t* sel, int32_t G, float* grad_y0, float* grad_W_aug,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Euler-Maruyama in torchsde's integrate loop (scalar noise, Ito): steps of `dt` from ts[0], the last
  * one clipped to ts[T-1], outputs by linear interpolation between the two solver states around ts[j].
  * Replaces torchsde.sdeint(sde, y0, ts, names={'drift':'forward','diffusion':'diffusion'}, method='euler',

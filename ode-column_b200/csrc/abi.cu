@@ -143,8 +143,45 @@ int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const 
     if (T < 2 || max_steps < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
     if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;   // per-trial dopri5 exists in the on-chip family only
-    return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status,
+    const Dopri5Record none{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, none,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out, float rtol,
+                             float atol, int32_t max_steps, int32_t* n_accept, int32_t* n_reject, int32_t* status,
+                             float* rec_y, double* rec_t0, double* rec_dt, int32_t* out_step, float* out_x, int32_t cap,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y0 || !y_out || !n_accept || !rec_y || !rec_t0 || !rec_dt || !out_step || !out_x) return ODECOL_E_NULL;
+    if (T < 2 || max_steps < 1 || cap < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
+    g_launches.store(0, std::memory_order_relaxed);
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    const Dopri5Record rec{rec_y, rec_t0, rec_dt, out_step, out_x, cap};
+    return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int odecol_dopri5_bwd(const odecol_problem* p, int32_t T, const float* rec_y, const double* rec_t0, const double* rec_dt,
+                      const int32_t* out_step, const float* out_x, int32_t cap, const int32_t* n_accept,
+                      const float* grad_y, const int32_t* sel, int32_t G, float* grad_y0, float* grad_W_aug,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!rec_y || !rec_t0 || !rec_dt || !out_step || !out_x || !n_accept || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
+    if (T < 2 || cap < 1 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    g_launches.store(0, std::memory_order_relaxed);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+    const Dopri5Record rec{const_cast<float*>(rec_y), const_cast<double*>(rec_t0), const_cast<double*>(rec_dt),
+                           const_cast<int*>(out_step), const_cast<float*>(out_x), cap};
+    return launch_dopri5_bwd_small(d, T, rec, n_accept, grad_y, sel, G, grad_y0, grad_W_aug, s);
 }
 
 int64_t odecol_em_num_steps(const float* ts, int32_t T, float dt) {

@@ -23,6 +23,17 @@ struct DevProblem {
     Consts c;
 };
 
+// optional recording of the accepted dopri5 steps (training mode): start state, t0, dt of every accepted step and, for
+// every output time, the step it was interpolated in and the abscissa
+struct Dopri5Record {
+    float* y;          // (cap, B, 3N) or NULL
+    double* t0;        // (B, cap)
+    double* dt;        // (B, cap)
+    int* out_step;     // (B, T)
+    float* out_x;      // (B, T)
+    int cap;
+};
+
 // thread-local launch counter (odecol_last_launch_count)
 void count_launch(int n = 1);
 
@@ -35,7 +46,10 @@ int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float
 int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float* y_traj, const float* grad_y,
                          const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s);
 int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, float rtol,
-                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, cudaStream_t s);
+                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec,
+                            cudaStream_t s);
+int launch_dopri5_bwd_small(const DevProblem& p, int T, const Dopri5Record& rec, const int* n_accept, const float* grad_y,
+                            const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s);
 int launch_em_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
                         uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol,
                         float dt_min, int* n_accept, int* n_reject, int* status, float* y_steps,

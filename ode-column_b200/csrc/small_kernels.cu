@@ -183,10 +183,12 @@ __global__ void __launch_bounds__(128) k_rk4_fwd_small(DevProblem p, const float
 // ---------------------------------------------------------------------------------------------------------------
 // RK4 discrete adjoint (reverse sweep over the saved trajectory; stages recomputed per step)
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kBwdSlots = 7;     // r_aug vectors kept per step: 4 RK4 stages, or the 7 Dormand-Prince stages
+
 template <int KP>
 struct BwdShared {
     float* Ws;     // [N][KP+1]   padded rows: row access (thread = row) and column access (thread = col) conflict free
-    float* ra;     // [4][KP]     r_aug of the four stages
+    float* ra;     // [kBwdSlots][KP] r_aug of the stages of one step
     float* av;     // [2][NP]
     int* inv;      // [3N]        state component -> column of grad_y, or -1
 };
@@ -195,7 +197,7 @@ template <int KP>
 ODECOL_DEVINL BwdShared<KP> carve_bwd(float* sm, int N, int NP) {
     BwdShared<KP> s;
     s.ra = sm;                                   // 16-byte aligned
-    s.av = s.ra + 4 * KP;
+    s.av = s.ra + kBwdSlots * KP;
     s.Ws = s.av + 2 * NP;
     s.inv = reinterpret_cast<int*>(s.Ws + (size_t)N * (KP + 1));
     return s;
@@ -203,7 +205,7 @@ ODECOL_DEVINL BwdShared<KP> carve_bwd(float* sm, int N, int NP) {
 
 size_t small_bwd_smem_bytes(int N, int KP) {
     const int NP = (N + 31) / 32 * 32;
-    return sizeof(float) * ((size_t)4 * KP + 2 * NP + (size_t)N * (KP + 1) + 3 * N);
+    return sizeof(float) * ((size_t)kBwdSlots * KP + 2 * NP + (size_t)N * (KP + 1) + 3 * N);
 }
 
 template <int KP>
@@ -230,7 +232,7 @@ struct BwdCtx {
             const int r = e / KP, k = e % KP;
             s.Ws[r * (KP + 1) + k] = k < Kaug ? __ldg(p.W_aug + (size_t)r * p.ld_w + k) : 0.0f;
         }
-        for (int e = i; e < 4 * KP; e += blockDim.x) s.ra[e] = (e % KP == Kaug - 1) ? 1.0f : 0.0f;
+        for (int e = i; e < kBwdSlots * KP; e += blockDim.x) s.ra[e] = (e % KP == Kaug - 1) ? 1.0f : 0.0f;
         for (int e = i; e < 2 * NP; e += blockDim.x) s.av[e] = 0.0f;
 #pragma unroll
         for (int k = 0; k < KP; ++k) dw[k] = 0.0f;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(128) k_dopri5_fwd_small(DevProblem p, const fl
                                                           const float* __restrict__ y0, float* __restrict__ y_out,
                                                           float rtol, float atol, int max_steps,
                                                           int* __restrict__ n_accept, int* __restrict__ n_reject,
-                                                          int* __restrict__ status) {
+                                                          int* __restrict__ status, Dopri5Record rec) {
     __shared__ __align__(16) float ra[2 * KP];
     __shared__ double red[4];
     const int b = blockIdx.x, i = threadIdx.x, N = p.N;
@@ -479,6 +481,11 @@ __global__ void __launch_bounds__(128) k_dopri5_fwd_small(DevProblem p, const fl
             }
             const float ratio = rms3(q[0], q[1], q[2]);
             const bool accept = ratio <= 1.0f;
+            if (accept && rec.y) {                 // training mode: remember the step (start state, t0, dt)
+                if (nacc >= rec.cap) { st = ODECOL_ST_MAXSTEPS; break; }
+                if (f.act) st3(rec.y + ((size_t)nacc * p.B + b) * row, N, i, y[0], y[1], y[2]);
+                if (i == 0) { rec.t0[(size_t)b * rec.cap + nacc] = t0; rec.dt[(size_t)b * rec.cap + nacc] = dt; }
+            }
             if (accept) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -509,6 +516,7 @@ __global__ void __launch_bounds__(128) k_dopri5_fwd_small(DevProblem p, const fl
         }
         if (st != ODECOL_ST_OK) break;
         const float x = (float)((next_t - st_t0) / (st_t1 - st_t0));
+        if (rec.y && i == 0) { rec.out_step[(size_t)b * T + j] = nacc - 1; rec.out_x[(size_t)b * T + j] = x; }
         if (f.act) {
             float o[3];
 #pragma unroll
@@ -534,6 +542,120 @@ __global__ void __launch_bounds__(128) k_dopri5_fwd_small(DevProblem p, const fl
         if (n_reject) n_reject[b] = nrej;
         if (status) status[b] = st;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dopri5 discrete adjoint: reverse sweep over the ACCEPTED steps recorded by the forward kernel (rejected attempts and
+// the step-size controller carry no gradient: torchdiffeq computes them under no_grad).  Per step the seven stages are
+// recomputed from the recorded start state, then the adjoint runs through the dense-output quartic (every requested
+// output is interpolated), the FSAL solution row and the six stage rows of the tableau.
+// What it replaces: loss.backward() through torchdiffeq's unrolled adaptive steps (reference scripts/xor_ode.py:177).
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) k_dopri5_bwd_small(DevProblem p, int T, Dopri5Record rec,
+                                                          const int* __restrict__ n_accept,
+                                                          const float* __restrict__ grad_y, const int* __restrict__ sel,
+                                                          int G, float* __restrict__ grad_y0, float* __restrict__ grad_W) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    BwdCtx<KP> cx;
+    cx.init(p, sm, b);
+    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    __syncthreads();
+    int gi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gi[c] = cx.act ? cx.s.inv[c * N + i] : -1;
+    const size_t row = (size_t)3 * N;
+    // tableau as float32, row r = coefficients of stage r+2 (last row = FSAL solution row)
+    const float beta[6][6] = {
+        {DP::b10, 0.f, 0.f, 0.f, 0.f, 0.f}, {DP::b20, DP::b21, 0.f, 0.f, 0.f, 0.f}, {DP::b30, DP::b31, DP::b32, 0.f, 0.f, 0.f},
+        {DP::b40, DP::b41, DP::b42, DP::b43, 0.f, 0.f}, {DP::b50, DP::b51, DP::b52, DP::b53, DP::b54, 0.f},
+        {DP::b60, 0.f, DP::b62, DP::b63, DP::b64, DP::b65}};
+    const float alpha[4] = {DP::a1, DP::a2, DP::a3, DP::a4};
+    const float cmid[7] = {DP::m0, 0.f, DP::m2, DP::m3, DP::m4, DP::m5, DP::m6};
+    const int nacc = n_accept[b];
+    float lam[3] = {0.f, 0.f, 0.f};        // adjoint of y1 of the step being processed
+    float carry[3] = {0.f, 0.f, 0.f};      // adjoint of f1 = k7 handed back by the following step (its k1)
+    int j = T - 1;
+    for (int n = nacc - 1; n >= 0; --n) {
+        const double t0 = rec.t0[(size_t)b * rec.cap + n], dtd = rec.dt[(size_t)b * rec.cap + n];
+        const float t0f = (float)t0, dtf = (float)dtd, t1f = (float)(t0 + dtd);
+        float y0[3] = {0.f, 0.f, 0.f};
+        if (cx.act) { const Y3 q = ld3(rec.y + ((size_t)n * B + b) * row, N, i); y0[0] = q.V; y0[1] = q.A; y0[2] = q.F; }
+        // ---- recompute the seven stages
+        float k[7][3], dph[7], ys[3] = {y0[0], y0[1], y0[2]};
+#pragma unroll
+        for (int st = 0; st < 7; ++st) {
+            if (st > 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float acc = k[0][c] * (beta[st - 1][0] * dtf);
+#pragma unroll
+                    for (int m = 1; m < 6; ++m)
+                        if (m < st) acc = fmaf(k[m][c], beta[st - 1][m] * dtf, acc);
+                    ys[c] = __fadd_rn(y0[c], acc);
+                }
+            }
+            const float ts = st == 0 ? t0f : (st <= 4 ? __fadd_rn(t0f, __fmul_rn(alpha[st - 1], dtf)) : t1f);
+            float r;
+            const float tot = cx.stage_fwd(st, ts, ys[0], ys[1], r, dph[st], true);
+            drift(cx.c, ys[0], ys[1], ys[2], r, cx.kappa, tot, k[st][0], k[st][1], k[st][2]);
+        }
+        // ys is y1 now.  ---- adjoint of the dense output for every output time inside this step
+        float ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0}, cc[3] = {0, 0, 0}, cd[3] = {0, 0, 0}, ce[3] = {0, 0, 0};
+        while (j >= 1 && rec.out_step[(size_t)b * T + j] == n) {
+            const float x = rec.out_x[(size_t)b * T + j];
+            const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float g = gi[c] >= 0 ? grad_y[((size_t)j * B + b) * G + gi[c]] : 0.f;
+                ce[c] += g; cd[c] += x * g; cc[c] += x2 * g; cb[c] += x3 * g; ca[c] += x4 * g;
+            }
+            --j;
+        }
+        float kb[7][3], yb0[3], yb1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float ymidb = 16.f * ca[c] - 32.f * cb[c] + 16.f * cc[c];
+            yb0[c] = ce[c] - 8.f * ca[c] + 18.f * cb[c] - 11.f * cc[c] + ymidb;
+            yb1[c] = lam[c] - 8.f * ca[c] + 14.f * cb[c] - 5.f * cc[c];
+#pragma unroll
+            for (int m = 0; m < 7; ++m) kb[m][c] = dtf * cmid[m] * ymidb;
+            kb[0][c] += dtf * (-2.f * ca[c] + 5.f * cb[c] - 4.f * cc[c] + cd[c]);     // f0 = k1
+            kb[6][c] += dtf * (2.f * ca[c] - 3.f * cb[c] + cc[c]) + carry[c];         // f1 = k7 (+ next step's k1)
+        }
+        // ---- stages 7 .. 2: Ybar_i = [i == 7] ybar1 + J(Y_i)^T kbar_i, then push through the tableau row
+#pragma unroll
+        for (int st = 6; st >= 1; --st) {
+            float bV, bA, bF;
+            cx.stage_bwd(st, dph[st], kb[st][0], kb[st][1], kb[st][2], bV, bA, bF);
+            float Yb[3] = {bV, bA, bF};
+            if (st == 6) { Yb[0] += yb1[0]; Yb[1] += yb1[1]; Yb[2] += yb1[2]; }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                yb0[c] += Yb[c];
+#pragma unroll
+                for (int m = 0; m < 6; ++m)
+                    if (m < st) kb[m][c] += dtf * beta[st - 1][m] * Yb[c];
+            }
+        }
+        if (n > 0) {
+            carry[0] = kb[0][0]; carry[1] = kb[0][1]; carry[2] = kb[0][2];
+        } else {                                   // first step: k1 = f(t[0], y0) was evaluated, not inherited
+            float bV, bA, bF;
+            cx.stage_bwd(0, dph[0], kb[0][0], kb[0][1], kb[0][2], bV, bA, bF);
+            yb0[0] += bV; yb0[1] += bA; yb0[2] += bF;
+        }
+        lam[0] = yb0[0]; lam[1] = yb0[1]; lam[2] = yb0[2];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if (gi[c] >= 0) lam[c] += grad_y[((size_t)0 * B + b) * G + gi[c]];        // output 0 is y0 itself
+    if (grad_y0 && cx.act) st3(grad_y0 + b * row, N, i, lam[0], lam[1], lam[2]);
+    cx.flush_dw(p, grad_W);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -808,10 +930,23 @@ int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float
 }
 
 int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, float rtol,
-                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, cudaStream_t s) {
+                            float atol, int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec,
+                            cudaStream_t s) {
     const int kp = small_kp(p);
     ODECOL_KP_SWITCH(kp, (k_dopri5_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, rtol, atol, max_steps,
-                                                                                   n_accept, n_reject, status)));
+                                                                                   n_accept, n_reject, status, rec)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_dopri5_bwd_small(const DevProblem& p, int T, const Dopri5Record& rec, const int* n_accept, const float* grad_y,
+                            const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s) {
+    const int kp = small_kp(p);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    ODECOL_KP_SWITCH(kp, {
+        cudaFuncSetAttribute(k_dopri5_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_dopri5_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, rec, n_accept, grad_y, sel, G, grad_y0, grad_W);
+    });
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }

@@ -134,6 +134,55 @@ std::vector<torch::Tensor> dopri5_fwd(const Problem& pr, const torch::Tensor& t,
     return {y, na, nr, st};
 }
 
+// training mode: (y, n_accept, n_reject, status, rec_y, rec_t0, rec_dt, out_step, out_x)
+std::vector<torch::Tensor> dopri5_fwd_record(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0, double rtol,
+                                             double atol, int64_t max_steps, int64_t cap) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(t, "t");
+    const int64_t T = t.numel();
+    auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto na = torch::zeros({pr.B()}, pr.iopts()), nr = torch::zeros({pr.B()}, pr.iopts()), st = torch::zeros({pr.B()}, pr.iopts());
+    auto rec_y = torch::empty({cap, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto rec_t0 = torch::zeros({pr.B(), cap}, pr.fopts().dtype(torch::kFloat64));
+    auto rec_dt = torch::zeros({pr.B(), cap}, pr.fopts().dtype(torch::kFloat64));
+    auto out_step = torch::zeros({pr.B(), T}, pr.iopts());
+    auto out_x = torch::zeros({pr.B(), T}, pr.fopts());
+    check(odecol_dopri5_fwd_record(&pr.p, t.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), (float)rtol,
+                                   (float)atol, (int32_t)std::min<int64_t>(max_steps, INT32_MAX), na.data_ptr<int32_t>(),
+                                   nr.data_ptr<int32_t>(), st.data_ptr<int32_t>(), rec_y.data_ptr<float>(),
+                                   rec_t0.data_ptr<double>(), rec_dt.data_ptr<double>(), out_step.data_ptr<int32_t>(),
+                                   out_x.data_ptr<float>(), (int32_t)cap, nullptr, 0, pr.stream()), "dopri5_fwd_record");
+    return {y, na, nr, st, rec_y, rec_t0, rec_dt, out_step, out_x};
+}
+
+std::vector<torch::Tensor> dopri5_bwd(const Problem& pr, int64_t T, const torch::Tensor& rec_y, const torch::Tensor& rec_t0,
+                                      const torch::Tensor& rec_dt, const torch::Tensor& out_step, const torch::Tensor& out_x,
+                                      const torch::Tensor& n_accept, const torch::Tensor& grad_y,
+                                      std::optional<torch::Tensor> sel) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    want(rec_y, "rec_y"); want(rec_t0, "rec_t0", torch::kFloat64); want(rec_dt, "rec_dt", torch::kFloat64);
+    want(out_step, "out_step", torch::kInt32); want(out_x, "out_x"); want(n_accept, "n_accept", torch::kInt32);
+    want(grad_y, "grad_y");
+    TORCH_CHECK(grad_y.dim() == 3 && grad_y.size(0) == T && grad_y.size(1) == pr.B(), "odecol: grad_y must be (T, B, G)");
+    const int64_t G = grad_y.size(2), cap = rec_y.size(0);
+    const int32_t* selp = nullptr;
+    if (sel.has_value()) {
+        want(*sel, "sel", torch::kInt32);
+        TORCH_CHECK(sel->numel() == G, "odecol: sel must have G entries");
+        selp = sel->data_ptr<int32_t>();
+    } else {
+        TORCH_CHECK(G == 3 * pr.N(), "odecol: dense grad_y must have 3N components");
+    }
+    auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
+    auto gW = torch::empty_like(pr.W_aug);
+    check(odecol_dopri5_bwd(&pr.p, (int32_t)T, rec_y.data_ptr<float>(), rec_t0.data_ptr<double>(), rec_dt.data_ptr<double>(),
+                            out_step.data_ptr<int32_t>(), out_x.data_ptr<float>(), (int32_t)cap, n_accept.data_ptr<int32_t>(),
+                            grad_y.data_ptr<float>(), selp, (int32_t)G, gy0.data_ptr<float>(), gW.data_ptr<float>(), nullptr, 0,
+                            pr.stream()), "dopri5_bwd");
+    return {gy0, gW};
+}
+
 int64_t em_num_steps(const torch::Tensor& ts_cpu, double dt) {
     TORCH_CHECK(!ts_cpu.is_cuda() && ts_cpu.scalar_type() == torch::kFloat32 && ts_cpu.is_contiguous(),
                 "odecol: em_num_steps wants a contiguous float32 CPU tensor");
@@ -245,6 +294,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rk4_fwd", &rk4_fwd);
     m.def("rk4_bwd", &rk4_bwd);
     m.def("dopri5_fwd", &dopri5_fwd);
+    m.def("dopri5_fwd_record", &dopri5_fwd_record);
+    m.def("dopri5_bwd", &dopri5_bwd);
     m.def("em_num_steps", &em_num_steps);
     m.def("em_fwd", &em_fwd);
     m.def("em_bwd", &em_bwd);
