@@ -15,7 +15,7 @@ There is no generic-function path, no CPU path and no multi-backend dispatch -- 
 Batching: where the reference loops over trials with B = 1 solves, pass y0 of shape (B, 3N) and a stimulus with a
 leading trial dimension; the result is (T, B, 3N).
 
-Gradients: ``method='rk4'`` and fixed-step Euler-Maruyama are differentiable w.r.t. every module parameter that enters
+Gradients: ``method='rk4'``, ``method='dopri5'`` and fixed-step Euler-Maruyama are differentiable w.r.t. every module parameter that enters
 W_aug = [W | U | bias] and w.r.t. y0, through hand-written exact discrete adjoints (what ``loss.backward()`` through
 the reference's unrolled solver computes).
 """
