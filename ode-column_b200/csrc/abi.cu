@@ -220,7 +220,7 @@ int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const flo
         return launch_em_fwd_small(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min,
                                    n_accept, n_reject, status, y_steps, cap, s);
     }
-    if (y_steps) return ODECOL_E_UNSUPPORTED;
+    if (y_steps) return ODECOL_E_UNSUPPORTED;          // no staged Euler-Maruyama adjoint yet
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
     return stage_em_fwd(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min, n_accept, n_reject,
                         status, workspace, workspace_bytes, s);

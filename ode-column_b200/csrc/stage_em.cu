@@ -1,13 +1,427 @@
-// Family L Euler-Maruyama (fixed step and per-trial step doubling with the state in global memory).
-#include "odecol_common.cuh"
+// Staged (large-N) Euler-Maruyama: the drift's contraction runs on the tensor cores (kernel of stage_tc.cuh with a
+// plain right-hand-side epilogue), the stepping logic in small elementwise kernels around it.  At N >= 256 the
+// contraction dominates (2 N^2 flops per trial and evaluation against ~60 bytes of bookkeeping), so the extra pass over
+// the state costs nothing measurable and keeps the torchsde loop semantics readable:
+//
+//   fixed step   per step:   f = drift(t_k, y)  [tensor]  ->  y += f h + sigma dW, outputs, next operand   [elementwise]
+//   adaptive     per round:  f0 [tensor] -> full step + first half step [elementwise] -> f(mid) [tensor]
+//                            -> second half step + per-trial error sums [elementwise] -> per-trial controller
+//                            (torchsde update_step_size, accept/reject, Brownian tree queries) -> commit [elementwise]
+// Every trial carries its own time and step size; finished trials idle.  Replaces torchsde.sdeint(method='euler') for
+// networks beyond the on-chip family (BASELINE.json config 5).
+//
+// Unlike the other entry points these two synchronise the stream: the fixed-step schedule is replayed on the host from
+// a copy of ts, and the adaptive loop polls an "all trials finished" flag every 16 rounds.
+#include <vector>
+#include "stage_tc.cuh"
 
 namespace odecol {
+namespace tc {
 
-size_t stage_em_fwd_workspace_bytes(const DevProblem&, int) { return 0; }
+// ---- tensor-core right-hand side: f[b] = drift(y[b], W_aug . r_aug[b]) -------------------------------------------------
+struct RhsEpi {
+    DevProblem p;
+    const float* y;        // (B, 3N)
+    const float* Rhi; const float* Rlo;   // operand of this evaluation (r = hi + lo)
+    float* f;              // (B, 3N)
+    int KPa;
+    float inv_tm, inv_ta, inv_ts;
+    ODECOL_DEVINL void prepare() {}
+    ODECOL_DEVINL void rows(int, int i, int n0, int, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (i >= p.N) return;
+        const int N = p.N;
+        const float kap = __ldg(p.kappa + i);
+#pragma unroll 4
+        for (int j = 0; j < kMaxQ; ++j) {
+            const int b = n0 + g * TNq + j;
+            if (j >= TNq || b >= p.B) break;
+            const float* yb = y + (size_t)b * 3 * N + i;
+            const float r = Rhi[(size_t)b * KPa + i] + Rlo[(size_t)b * KPa + i];
+            const float total = tot[j] * p.c.tau_s;
+            float* fb = f + (size_t)b * 3 * N + i;
+            fb[0] = (total * p.c.R - yb[0]) * inv_tm;
+            fb[N] = (kap * r - yb[N]) * inv_ta;
+            fb[2 * N] = (r - yb[2 * N]) * inv_ts;
+        }
+    }
+    ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
+};
 
-int stage_em_fwd(const DevProblem&, const float*, int, const float*, float*, const float*, uint64_t, int64_t, float, int,
-                 float, float, float, int*, int*, int*, void*, size_t, cudaStream_t) {
-    return ODECOL_E_UNSUPPORTED;
+// operand r_aug(t_b, y_b) split hi/lo; one CTA per trial, per-trial time (NULL -> shared time *t_shared)
+__global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
+                             float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa) {
+    const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
+    const size_t ro = (size_t)b * KPa;
+    const float* yb = y + (size_t)b * 3 * N;
+    const float tq = t_trial ? t_trial[b] : t_shared;
+    int idx = 1;
+    const float tcl = knot_locate(p.knot_t, p.K, tq, idx);
+    const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
+    for (int k = threadIdx.x; k < Kaug; k += blockDim.x) {
+        float v;
+        if (k < N) v = phi_fast(yb[k] - yb[N + k]);
+        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N);
+        else v = 1.0f;
+        const float h = tf32_rna(v);
+        hi[ro + k] = h;
+        lo[ro + k] = tf32_rna(v - h);
+    }
+}
+
+// ---- fixed step ---------------------------------------------------------------------------------------------------
+struct EmStepArgs {
+    DevProblem p;
+    float* y; const float* f; float* y_prev;      // y updated in place, previous state kept for the interpolation
+    const float* dW; unsigned long long seed; long long trial_offset; long long kstep;
+    float t0, t1;                                 // this step
+    float* y_out; int j_lo, j_hi;                 // outputs emitted after this step: ts[j], j in [j_lo, j_hi)
+    const float* ts;
+};
+
+__global__ void k_em_step(EmStepArgs a) {
+    const int N = a.p.N, B = a.p.B;
+    const size_t total = (size_t)B * 3 * N;
+    const float h = __fsub_rn(a.t1, a.t0);
+    const Philox px(a.seed);
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / (3 * N)), comp = (int)(e % (3 * N));
+        float dw;
+        if (a.dW) dw = a.dW[(size_t)a.kstep * B + b];
+        else {
+            const unsigned long long trial = (unsigned long long)(a.trial_offset + b);
+            const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)a.kstep, 0x80000000u | (uint32_t)(a.kstep >> 32));
+            dw = sqrtf(h) * normal_from_bits(bits.x, bits.y);
+        }
+        const float sg = a.p.sigma ? __ldg(a.p.sigma + comp) : 0.f;
+        const float y0 = a.y[e];
+        const float y1 = __fadd_rn(__fadd_rn(y0, __fmul_rn(a.f[e], h)), __fmul_rn(sg, dw));
+        a.y_prev[e] = y0;
+        a.y[e] = y1;
+        for (int j = a.j_lo; j < a.j_hi; ++j) {
+            const float out_t = __ldg(a.ts + j);
+            const float w0 = __fdiv_rn(__fsub_rn(a.t1, out_t), h), w1 = __fdiv_rn(__fsub_rn(out_t, a.t0), h);
+            a.y_out[(size_t)j * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
+        }
+    }
+}
+
+// ---- adaptive: per-trial controller state -------------------------------------------------------------------------------
+struct TrialState {
+    float* t_cur; float* t_prev; float* t_mid; float* t_next;   // (B)
+    double* step; double* prev_ratio; int* has_prev;
+    float* w_cur; float* dw_full; float* dw_1; float* dw_2;
+    double* err2;
+    int* next_out; int* n_acc; int* n_rej; int* status; int* active; int* accept;
+    int* n_active;          // single counter
+};
+
+__global__ void k_ad_init(DevProblem p, TrialState s, const float* __restrict__ ts, int T, float dt0, unsigned long long seed,
+                          long long trial_offset) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const float t_begin = ts[0], t_end = ts[T - 1];
+    s.t_cur[b] = t_begin; s.t_prev[b] = t_begin;
+    s.step[b] = (double)dt0; s.prev_ratio[b] = 0.0; s.has_prev[b] = 0;
+    s.w_cur[b] = 0.f; s.err2[b] = 0.0;
+    s.next_out[b] = 1; s.n_acc[b] = 0; s.n_rej[b] = 0; s.status[b] = ODECOL_ST_OK; s.active[b] = 1; s.accept[b] = 0;
+    // first attempt
+    const float next_t = fminf(__fadd_rn(t_begin, dt0), t_end);
+    const float mid_t = __fmul_rn(0.5f, __fadd_rn(t_begin, next_t));
+    s.t_next[b] = next_t; s.t_mid[b] = mid_t;
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    const float span = t_end - t_begin;
+    const float wm = brownian_tree(px, trial, t_begin, span, mid_t), wn = brownian_tree(px, trial, t_begin, span, next_t);
+    s.dw_full[b] = wn; s.dw_1[b] = wm; s.dw_2[b] = wn - wm;
+    if (b == 0) *s.n_active = p.B;
+}
+
+// full step and first half step from f0; writes y_full, y_mid
+__global__ void k_ad_half1(DevProblem p, TrialState s, const float* __restrict__ y, const float* __restrict__ f0,
+                           float* __restrict__ y_full, float* __restrict__ y_mid) {
+    const int N = p.N;
+    const size_t total = (size_t)p.B * 3 * N;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / (3 * N)), comp = (int)(e % (3 * N));
+        if (!s.active[b]) continue;
+        const float tc = s.t_cur[b], tm = s.t_mid[b], tn = s.t_next[b];
+        const float h = __fsub_rn(tn, tc), h1 = __fsub_rn(tm, tc);
+        const float sg = p.sigma ? __ldg(p.sigma + comp) : 0.f;
+        const float y0 = y[e], f = f0[e];
+        y_full[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, s.dw_full[b]));
+        y_mid[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, s.dw_1[b]));
+    }
+}
+
+// second half step from f(mid), error sums per trial
+__global__ void k_ad_half2(DevProblem p, TrialState s, const float* __restrict__ y_mid, const float* __restrict__ fm,
+                           const float* __restrict__ y_full, float* __restrict__ y_half, float rtol, float atol) {
+    const int N = p.N;
+    const int b = blockIdx.x;
+    if (!s.active[b]) return;
+    const float h2 = __fsub_rn(s.t_next[b], s.t_mid[b]);
+    const float dw2 = s.dw_2[b];
+    double acc = 0.0;
+    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
+        const size_t e = (size_t)b * 3 * N + comp;
+        const float sg = p.sigma ? __ldg(p.sigma + comp) : 0.f;
+        const float yh = __fadd_rn(__fadd_rn(y_mid[e], __fmul_rn(fm[e], h2)), __fmul_rn(sg, dw2));
+        y_half[e] = yh;
+        const float yf = y_full[e];
+        const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf), fabsf(yh))));
+        const float q = __fdiv_rn(__fsub_rn(yf, yh), tol);
+        acc += (double)q * q;
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        s.err2[b] = t;
+    }
+}
+
+// torchsde adaptive_stepping.update_step_size + accept/reject per trial, then the next attempt's times and increments
+__global__ void k_ad_control(DevProblem p, TrialState s, const float* __restrict__ ts, int T, float dt_min,
+                             unsigned long long seed, long long trial_offset, long long max_attempts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B || !s.active[b]) return;
+    const float t_begin = ts[0], t_end = ts[T - 1];
+    const double err = (double)(float)sqrt(s.err2[b] / (3.0 * p.N));
+    int acc = 0;
+    if (!(err == err)) {
+        s.status[b] = ODECOL_ST_NONFINITE; s.active[b] = 0; s.accept[b] = 0; atomicSub(s.n_active, 1);
+        return;
+    }
+    double step = s.step[b];
+    {
+        const double pfac = err > 1.0 ? 0.0 : 0.13, ifac = err > 1.0 ? 1.0 / 1.5 : 1.0 / 4.5;
+        const double ratio = 0.9 / err;
+        const double pr = s.has_prev[b] ? s.prev_ratio[b] : ratio;
+        double factor = pow(ratio, ifac) * pow(ratio / pr, pfac);
+        double facmin = 0.2;
+        if (err <= 1.0) { s.prev_ratio[b] = ratio; s.has_prev[b] = 1; facmin = 1.0; }
+        factor = fmin(1.4, fmax(facmin, factor));
+        step *= factor;
+    }
+    if (step < (double)dt_min) { step = (double)dt_min; s.has_prev[b] = 0; }
+    s.step[b] = step;
+    float t_cur = s.t_cur[b];
+    if (err <= 1.0 || step <= (double)dt_min) {
+        acc = 1;
+        s.t_prev[b] = t_cur;
+        t_cur = s.t_next[b];
+        s.t_cur[b] = t_cur;
+        s.w_cur[b] += s.dw_full[b];
+        s.n_acc[b] += 1;
+    } else {
+        s.n_rej[b] += 1;
+    }
+    s.accept[b] = acc;
+    if ((long long)s.n_acc[b] + s.n_rej[b] >= max_attempts) { s.status[b] = ODECOL_ST_MAXSTEPS; s.active[b] = 0; atomicSub(s.n_active, 1); return; }
+    // next attempt (also after the final accept: k_ad_commit decides whether the trial is finished)
+    const float next_t = fminf(__fadd_rn(t_cur, (float)step), t_end);
+    const float mid_t = __fmul_rn(0.5f, __fadd_rn(t_cur, next_t));
+    s.t_next[b] = next_t; s.t_mid[b] = mid_t;
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    const float span = t_end - t_begin;
+    const float w0 = s.w_cur[b];
+    const float wm = brownian_tree(px, trial, t_begin, span, mid_t), wn = brownian_tree(px, trial, t_begin, span, next_t);
+    s.dw_full[b] = wn - w0; s.dw_1[b] = wm - w0; s.dw_2[b] = wn - wm;
+}
+
+// commit accepted steps: state, outputs reached by the new time, finished trials
+__global__ void k_ad_commit(DevProblem p, TrialState s, const float* __restrict__ ts, int T, float* __restrict__ y,
+                            float* __restrict__ y_prev, const float* __restrict__ y_half, float* __restrict__ y_out) {
+    const int N = p.N, b = blockIdx.x;
+    if (!s.active[b] || !s.accept[b]) return;
+    const float t_prev = s.t_prev[b], t_cur = s.t_cur[b];
+    const float spn = __fsub_rn(t_cur, t_prev);
+    int j = s.next_out[b];
+    const size_t total = (size_t)p.B * 3 * N;
+    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
+        const size_t e = (size_t)b * 3 * N + comp;
+        const float y0 = y[e], y1 = y_half[e];
+        y_prev[e] = y0;
+        y[e] = y1;
+        for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
+            const float out_t = __ldg(ts + jj);
+            const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
+            y_out[(size_t)jj * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        while (j < T && ts[j] <= t_cur) ++j;
+        s.next_out[b] = j;
+        if (j >= T) { s.active[b] = 0; atomicSub(s.n_active, 1); }
+    }
+}
+
+__global__ void k_em_fill_nan(DevProblem p, const int* __restrict__ status, const int* __restrict__ next_out, int T,
+                              float* __restrict__ y_out) {
+    const int b = blockIdx.x, N = p.N;
+    if (status[b] == ODECOL_ST_OK) return;
+    const size_t total = (size_t)p.B * 3 * N;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int j = next_out[b]; j < T; ++j)
+        for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) y_out[(size_t)j * total + (size_t)b * 3 * N + comp] = qnan;
+}
+
+struct EmLayout {
+    int Np, Bp, KPa, TN;
+    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev, off_state, total;
+};
+
+static EmLayout em_layout(const DevProblem& p) {
+    EmLayout L;
+    L.Np = round_up(p.N, BM);
+    L.KPa = round_up(p.N + p.n_in + 1, BK);
+    L.TN = pick_tile_n(L.Np / BM, p.B);
+    L.Bp = round_up(p.B, L.TN);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
+    L.off_Rhi = take(4ull * L.Bp * L.KPa); L.off_Rlo = take(4ull * L.Bp * L.KPa);
+    const size_t st = 4ull * p.B * 3 * p.N;
+    L.off_f = take(st); L.off_fm = take(st); L.off_yfull = take(st); L.off_ymid = take(st); L.off_yhalf = take(st);
+    L.off_y = take(st); L.off_yprev = take(st);
+    L.off_state = take(128ull * p.B + 1024);
+    L.total = o;
+    return L;
+}
+
+}  // namespace tc
+
+size_t stage_em_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_layout(p).total; }
+
+int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                 uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
+                 int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const EmLayout L = em_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo);
+    float *f0 = F(L.off_f), *fm = F(L.off_fm), *yfull = F(L.off_yfull), *ymid = F(L.off_ymid), *yhalf = F(L.off_yhalf);
+    float *y = F(L.off_y), *yprev = F(L.off_yprev);
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+
+    if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+    count_launch();
+    if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(yprev, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    CUtensorMap mWhi, mWlo, mRhi, mRlo;
+    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+        return ODECOL_E_CUDA;
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0};
+    auto rhs = [&](const float* ysrc, float* fdst) {
+        RhsEpi e;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
+    };
+    const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
+
+    if (!adaptive) {
+        // replay the float32 time loop of torchsde's integrate() on the host (data independent)
+        std::vector<float> ts(T);
+        if (cudaMemcpyAsync(ts.data(), ts_dev, sizeof(float) * T, cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        volatile float curr = ts[0];
+        const float t_end = ts[T - 1];
+        long long k = 0;
+        int j = 1;
+        while (j < T) {
+            const float c0 = curr;
+            volatile float nx = c0 + dt;
+            const float next_t = nx < t_end ? nx : t_end;
+            int j_hi = j;
+            while (j_hi < T && ts[j_hi] <= next_t) ++j_hi;            // outputs the loop emits once curr_t >= ts[j]
+            k_em_operand<<<p.B, 128, 0, s>>>(p, y, nullptr, c0, Rhi, Rlo, L.KPa);
+            count_launch();
+            const int rc = rhs(y, f0);
+            if (rc != ODECOL_OK) return rc;
+            EmStepArgs a;
+            a.p = p; a.y = y; a.f = f0; a.y_prev = yprev; a.dW = dW; a.seed = seed; a.trial_offset = trial_offset; a.kstep = k;
+            a.t0 = c0; a.t1 = next_t; a.y_out = y_out; a.j_lo = j; a.j_hi = j_hi; a.ts = ts_dev;
+            k_em_step<<<ew_grid, 256, 0, s>>>(a);
+            count_launch();
+            curr = next_t;
+            j = j_hi;
+            ++k;
+            if (k > (1LL << 40)) return ODECOL_E_SHAPE;
+        }
+        if (n_accept || n_reject || status) {
+            std::vector<int> hk(p.B, (int)k), hz(p.B, 0);
+            if (n_accept && cudaMemcpyAsync(n_accept, hk.data(), sizeof(int) * p.B, cudaMemcpyHostToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (n_reject && cudaMemcpyAsync(n_reject, hz.data(), sizeof(int) * p.B, cudaMemcpyHostToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (status && cudaMemcpyAsync(status, hz.data(), sizeof(int) * p.B, cudaMemcpyHostToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;      // host vectors go out of scope
+        }
+        return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+    }
+
+    // ---- adaptive: per-trial controller state carved from the workspace
+    char* sb = w + L.off_state;
+    TrialState S;
+    const size_t B = p.B;
+    auto grab = [&](size_t bytes) { char* r = sb; sb += (bytes + 15) / 16 * 16; return r; };
+    S.step = reinterpret_cast<double*>(grab(8 * B)); S.prev_ratio = reinterpret_cast<double*>(grab(8 * B));
+    S.err2 = reinterpret_cast<double*>(grab(8 * B));
+    S.t_cur = reinterpret_cast<float*>(grab(4 * B)); S.t_prev = reinterpret_cast<float*>(grab(4 * B));
+    S.t_mid = reinterpret_cast<float*>(grab(4 * B)); S.t_next = reinterpret_cast<float*>(grab(4 * B));
+    S.w_cur = reinterpret_cast<float*>(grab(4 * B)); S.dw_full = reinterpret_cast<float*>(grab(4 * B));
+    S.dw_1 = reinterpret_cast<float*>(grab(4 * B)); S.dw_2 = reinterpret_cast<float*>(grab(4 * B));
+    S.has_prev = reinterpret_cast<int*>(grab(4 * B)); S.next_out = reinterpret_cast<int*>(grab(4 * B));
+    S.n_acc = reinterpret_cast<int*>(grab(4 * B)); S.n_rej = reinterpret_cast<int*>(grab(4 * B));
+    S.status = reinterpret_cast<int*>(grab(4 * B)); S.active = reinterpret_cast<int*>(grab(4 * B));
+    S.accept = reinterpret_cast<int*>(grab(4 * B));
+    S.n_active = reinterpret_cast<int*>(grab(16));
+
+    std::vector<float> tse(2);
+    if (cudaMemcpyAsync(&tse[0], ts_dev, sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(&tse[1], ts_dev + T - 1, sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+    const double span = (double)tse[1] - (double)tse[0];
+    const long long max_attempts = (long long)(4.0 * span / dt_min) + 4LL * T + 1024;
+    const int tb = (p.B + 127) / 128;
+    k_ad_init<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt, seed, trial_offset);
+    k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa);
+    count_launch(2);
+    int h_active = p.B;
+    for (long long round = 0; round < max_attempts && h_active > 0; ++round) {
+        int rc = rhs(y, f0);
+        if (rc != ODECOL_OK) return rc;
+        k_ad_half1<<<ew_grid, 256, 0, s>>>(p, S, y, f0, yfull, ymid);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa);
+        rc = rhs(ymid, fm);
+        if (rc != ODECOL_OK) return rc;
+        k_ad_half2<<<p.B, 256, 0, s>>>(p, S, ymid, fm, yfull, yhalf, rtol, atol);
+        k_ad_control<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt_min, seed, trial_offset, max_attempts);
+        k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa);
+        count_launch(6);
+        if ((round & 15) == 15) {
+            if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        }
+    }
+    k_em_fill_nan<<<p.B, 128, 0, s>>>(p, S.status, S.next_out, T, y_out);
+    count_launch();
+    if (n_accept && cudaMemcpyAsync(n_accept, S.n_acc, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (n_reject && cudaMemcpyAsync(n_reject, S.n_rej, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (status && cudaMemcpyAsync(status, S.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
 }  // namespace odecol
