@@ -43,7 +43,12 @@ def parse():
     ap.add_argument("--cpu-trials", type=int, default=1024, help="trials of the bounded CPU sample")
     ap.add_argument("--cpu-time-points", type=int, default=41, help="grid points of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--family", default=None, help="force a kernel family (staged)")
+    ap.add_argument("--family", default=None, help="force a kernel family (staged, tensor)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 (default, the headline): N=512 rk4 forward+adjoint; c5: N=8192 adaptive Euler-Maruyama sweep")
+    ap.add_argument("--c5-columns", type=int, default=1024)
+    ap.add_argument("--c5-trials", type=int, default=8192, help="sweep members in total (strong scaling over GPUs)")
+    ap.add_argument("--c5-horizon", type=float, default=0.004, help="simulated seconds per step of the c5 workload")
     return ap.parse_args()
 
 
@@ -332,6 +337,93 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """BASELINE.json configs[4]: 1,024-column network (N = 8192, dense W on the tensor cores), sweep of
+    8192 members differing in stimulus amplitude, stochastic adaptive Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3,
+    dt_min 1e-5, in-kernel Philox seed 0), members sharded over the GPUs (strong scaling, no collective).  One step =
+    one solve over --c5-horizon simulated seconds; the unit is one population advanced by one ATTEMPTED step."""
+    import torch
+    import torch.distributed as dist
+    import odecol
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ext = odecol._native.ext()
+    cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
+    cols, n = args.c5_columns, 8 * args.c5_columns
+    lo, hi = odecol.distributed.shard_bounds(args.c5_trials, rank, world)
+    B = hi - lo
+    net = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(2000)
+    amp = (torch.rand(args.c5_trials, 1, generator=g) * 30.0)[lo:hi].expand(B, cols).contiguous()
+    kt = torch.tensor([0.0, 1.0], device=dev)
+    ku = torch.stack((amp, amp), dim=1).to(dev)                  # constant stimulus, per-member amplitude
+    net.set_knots(kt, ku)
+    ts = torch.linspace(0.0, args.c5_horizon, 3, device=dev)
+    y0 = torch.zeros(B, 3 * n, device=dev)
+
+    def step():
+        st = {}
+        with torch.no_grad():
+            y = odecol.sdeint(net, y0, ts, method="euler", dt=1e-3, adaptive=True, rtol=1e-5, atol=1e-4, dt_min=1e-5,
+                              seed=0, trial_offset=lo, stats=st)
+        return y, st, ext.last_launch_count()
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    attempts = torch.zeros((), device=dev, dtype=torch.float64)
+    launches = 0
+    for _ in range(args.steps):
+        y, st, nl = step()
+        attempts += (st["n_accept"] + st["n_reject"]).double().sum()
+        launches += nl
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(attempts)
+    clocks = sampler.stop() if rank == 0 else None
+    sec = float(ms) / 1e3
+    rounds = int(st["n_accept"].max() + st["n_reject"].max())
+    value = n * float(attempts) / sec
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 6.0
+    kaug = n + cols + 1
+    rhs_launches = args.steps * 2 * rounds                        # two drift evaluations per round, all members
+    achieved = 2.0 * n * kaug * B * rhs_launches / sec / 1e12     # whole solve attributed to the contraction launches
+    if rank == 0:
+        print(json.dumps({
+            "metric": "population_steps_per_sec_adaptive_em", "value": value, "unit": "population-steps/s (attempted steps)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5: synthetic {cols}-column network (N={n}), sweep of {args.c5_trials} members, adaptive "
+                       f"Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3, dt_min 1e-5, Philox seed 0), {args.c5_horizon}s horizon",
+                       "l2": "W_aug hi+lo (539 MB) larger than L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "attempted_steps_per_member": float(attempts) / args.steps / args.c5_trials, "rounds_per_solve": rounds,
+            "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (3xTF32 tcgen05 drift evaluation)",
+                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                         "traffic": None, "note": "lower bound: the elementwise stepping kernels are inside the timed region"},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def net_family(ext, odecol, net, y0, tv, args):
     from ode_column_b200.solvers import _Setup
     setup = _Setup(net, y0, tv, args.family)
@@ -343,6 +435,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 
