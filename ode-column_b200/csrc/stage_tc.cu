@@ -1,4 +1,6 @@
 // Family T drivers: forward RK4 stages on the tensor cores and the diagnostic contraction (kernels in stage_tc.cuh).
+#include <cstdio>
+#include <cstdlib>
 #include "stage_tc.cuh"
 
 namespace odecol {
@@ -78,7 +80,7 @@ __global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y
 
 struct TcFwdLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[2], total;
+    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[2], off_done, total;
 };
 
 static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
@@ -95,11 +97,27 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     for (int i = 0; i < 3; ++i) L.off_K[i] = take(3 * plane);
     for (int i = 0; i < 2; ++i) L.off_Y[i] = take(3 * plane);
     for (int i = 0; i < 2; ++i) L.off_RT[i] = take(plane);
+    L.off_done = take((size_t)(L.Bp / L.TN) + 64);          // one uint32 per trial tile (floats == 4 bytes)
     L.total = o;
     return L;
 }
 
 }  // namespace tc
+
+void tc_launch_init(const DevProblem& p, const tc::TileGeom& tg, const float* y0, const float* t_dev, float* hi0, float* lo0,
+                    float* hi1, float* lo1, float* Y0T, float* RT, int KPa, int Bp, cudaStream_t s) {
+    tc::k_tc_init<<<Bp, 128, 0, s>>>(p, tg, y0, t_dev, hi0, lo0, hi1, lo1, Y0T, RT, KPa);
+}
+
+int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
+                          float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
+                          float* const YT[2], float* const RT[2], unsigned int* done, int Np, int Bp, int KPa, int TN,
+                          cudaStream_t s);
+
+static bool persistent_enabled() {
+    const char* v = getenv("ODECOL_PERSISTENT");
+    return v ? atoi(v) != 0 : true;
+}
 
 size_t tc_rk4_fwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_fwd_layout(p).total; }
 
@@ -120,6 +138,9 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
     const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
+    if (persistent_enabled())
+        return tc_rk4_fwd_persistent(p, t_dev, T, y0, y_out, out_every, Whi, Wlo, Rhi, Rlo, KT, YT, RT,
+                                     reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, s);
 
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
     k_tc_init<<<L.Bp, 128, 0, s>>>(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], RT[0], L.KPa);
@@ -130,7 +151,7 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     for (int i = 0; i < 2; ++i)
         ok = ok && make_map(&mRhi[i], Rhi[i], L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo[i], Rlo[i], L.Bp, L.KPa, L.KPa, L.TN);
     if (!ok) return ODECOL_E_CUDA;
-    const TileShape ts{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0};
+    const TileShape ts0{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
 
     int cur = 0;
     for (int n = 0; n < T - 1; ++n) {
@@ -141,17 +162,43 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
             e.Y0T = YT[n & 1]; e.Y1T = YT[(n + 1) & 1]; e.traj_row = emit ? y_out + r * st : nullptr;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
-            e.RT_cur = RT[cur]; e.RT_nxt = RT[cur ^ 1]; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1]; e.DRT_nxt = nullptr;
+            e.RT_cur = RT[cur]; e.RT_nxt = RT[cur ^ 1]; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1]; e.DRT_nxt = nullptr; e.dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.t0 = e.t1 = e.dt = 0.f;
         };
         for (int S = 1; S <= 4; ++S) {
             int rc;
+            TileShape ts = ts0;
+            unsigned long long* dbg = nullptr;
+            if (n == 2 && getenv("ODECOL_TIMELINE")) {          // diagnostics only: per-CTA timeline of one launch
+                cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 148);
+                cudaMemset(dbg, 0, sizeof(unsigned long long) * 8 * 148);
+                ts.dbg = dbg;
+            }
             if (S == 1) { FwdEpiT<1> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else if (S == 2) { FwdEpiT<2> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else if (S == 3) { FwdEpiT<3> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else { FwdEpiT<4> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             if (rc != ODECOL_OK) return rc;
+            if (dbg) {
+                cudaStreamSynchronize(s);
+                unsigned long long h[8 * 148];
+                cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+                cudaFree(dbg);
+                double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                int cnt = 0;
+                for (int c = 0; c < 148; ++c) {
+                    const unsigned long long* r = h + 8 * c;
+                    if (!r[0] || !r[6]) continue;
+                    ++cnt;
+                    acc[0] += (double)(r[1] - r[0]); acc[1] += (double)(r[2] - r[1]); acc[2] += (double)(r[3] - r[2]);
+                    acc[3] += (double)(r[4] - r[3]); acc[4] += (double)(r[5] - r[4]); acc[5] += (double)(r[6] - r[5]);
+                    acc[6] += (double)(r[6] - r[0]);
+                }
+                if (cnt) fprintf(stderr, "[odecol timeline] stage %d, %d CTAs, mean ns: mainloop1 %.0f | drain1 %.0f | epilogue1 %.0f | "
+                                 "wait2 %.0f | drain2 %.0f | epilogue2 %.0f | total %.0f\n", S, cnt, acc[0] / cnt, acc[1] / cnt,
+                                 acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt, acc[6] / cnt);
+            }
             cur ^= 1;
         }
     }
@@ -175,7 +222,7 @@ int tc_contract(const float* A, const float* B, float* C, int M, int N, int K, v
     if (!make_map(&ma_hi, Ahi, L.Mp, L.Kp, L.Kp, BM) || !make_map(&ma_lo, Alo, L.Mp, L.Kp, L.Kp, BM) ||
         !make_map(&mb_hi, Bhi, L.Np, L.Kp, L.Kp, L.TN) || !make_map(&mb_lo, Blo, L.Np, L.Kp, L.Kp, L.TN))
         return ODECOL_E_CUDA;
-    TileShape ts{L.Mp / BM, L.Np / L.TN, L.TN, L.Kp / BK, 0};
+    TileShape ts{L.Mp / BM, L.Np / L.TN, L.TN, L.Kp / BK, 0, nullptr};
     StoreEpi epi{C, M, N, M};
     return launch_contract(ma_hi, ma_lo, mb_hi, mb_lo, ts, epi, s);
 }

@@ -94,7 +94,14 @@ ODECOL_DEVINL float tf32_rna(float x) {
 struct TileShape {
     int MT, NT, TN, KB;      // m tiles, trial tiles, trials per tile (multiple of 16, <= 128), K blocks of 32
     int b_row0;              // first row of the B operand inside its tensor map (stacked per-stage operand buffers)
+    unsigned long long* dbg; // optional per-CTA timeline stamps (globaltimer ns): [cta][8], diagnostics only
 };
+
+ODECOL_DEVINL unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4 <= 32
 
@@ -136,6 +143,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (ts.dbg && threadIdx.x == 0) ts.dbg[blockIdx.x * 8 + 0] = gtimer();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -197,6 +205,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
             float tot[kMaxQ];
             mbar_wait(tfull, tphase);
             tc_fence_after();
+            const int tslot = (tile - blockIdx.x) / gridDim.x;
+            if (ts.dbg && etid == 0 && tslot < 2) ts.dbg[blockIdx.x * 8 + 1 + 3 * tslot] = gtimer();
             const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
 #pragma unroll
             for (int q = 0; q < kMaxQ / 4; ++q) {
@@ -218,8 +228,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);        // TMEM is free again: warp 1 may start the next tile
             tphase ^= 1;
+            if (ts.dbg && etid == 0 && tslot < 2) ts.dbg[blockIdx.x * 8 + 2 + 3 * tslot] = gtimer();
             epi.rows(m_tile, row, n0, nt, g, TNq, tot);
             epi.tile_done(m_tile, n0, ts.TN, etid, kEpiWarps * 32);
+            if (ts.dbg && etid == 0 && tslot < 2) ts.dbg[blockIdx.x * 8 + 3 + 3 * tslot] = gtimer();
         }
     }
     tc_fence_before();
@@ -381,6 +393,7 @@ struct FwdEpiT {
     float* RT_nxt;         // r of the next stage
     float* Rhi_nxt; float* Rlo_nxt;         // [Bp][KPa] operand of the next contraction
     float* DRT_nxt;        // optional [1 plane]: phi'(x) of the next stage state (reverse-sweep recompute)
+    int dbg_skip;          // diagnostics: 1 skip trajectory stores, 2 skip operand stores, 4 skip phi, 8 skip k stores
     float inv_tm, inv_ta, inv_ts;
     float t0, t1, dt;
 
@@ -389,83 +402,108 @@ struct FwdEpiT {
         dt = __fsub_rn(t1, t0);
     }
 
-    ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
-        if (i >= p.N) return;
+    // everything one float4 group (4 trials) of population i needs from the scratch planes
+    struct Loaded {
+        float4 V0, A0, F0, R, k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
+    };
+    ODECOL_DEVINL void load(size_t oq, size_t pl, Loaded& L) const {
+        L.V0 = ld4(Y0T + oq); L.A0 = ld4(Y0T + pl + oq); L.F0 = ld4(Y0T + 2 * pl + oq);
+        L.R = ld4(RT_cur + oq);
+        if (S >= 2) { L.k1V = ld4(K1T + oq); L.k1A = ld4(K1T + pl + oq); L.k1F = ld4(K1T + 2 * pl + oq); }
+        if (S >= 3) { L.k2V = ld4(K2T + oq); L.k2A = ld4(K2T + pl + oq); L.k2F = ld4(K2T + 2 * pl + oq); }
+        if (S >= 4) { L.k3V = ld4(K3T + oq); L.k3A = ld4(K3T + pl + oq); L.k3F = ld4(K3T + 2 * pl + oq); }
+    }
+
+    ODECOL_DEVINL void finish(const Loaded& L, size_t oq, size_t pl, int i, int b0, float kap, const float* tot4) const {
         const int N = p.N, B = p.B;
-        const float kap = __ldg(p.kappa + i);
-        const size_t pl = tg.plane();
         const float third = kOneThirdL;
+        const float4 &V0 = L.V0, &A0 = L.A0, &F0 = L.F0, &R = L.R;
+        const float4 &k1V = L.k1V, &k1A = L.k1A, &k1F = L.k1F, &k2V = L.k2V, &k2A = L.k2A, &k2F = L.k2F;
+        const float4 &k3V = L.k3V, &k3A = L.k3A, &k3F = L.k3F;
+        float oKV[4], oKA[4], oKF[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
 #pragma unroll
-        for (int q = 0; q < kMaxQ / 4; ++q) {
-            if (4 * q >= TNq) break;
-            const size_t oq = tg.off(nt, g, q, i);
-            const float4 V0 = ld4(Y0T + oq), A0 = ld4(Y0T + pl + oq), F0 = ld4(Y0T + 2 * pl + oq);
-            const float4 R = ld4(RT_cur + oq);
-            float4 k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
-            if (S >= 2) { k1V = ld4(K1T + oq); k1A = ld4(K1T + pl + oq); k1F = ld4(K1T + 2 * pl + oq); }
-            if (S >= 3) { k2V = ld4(K2T + oq); k2A = ld4(K2T + pl + oq); k2F = ld4(K2T + 2 * pl + oq); }
-            if (S >= 4) { k3V = ld4(K3T + oq); k3A = ld4(K3T + pl + oq); k3F = ld4(K3T + 2 * pl + oq); }
-            float oKV[4], oKA[4], oKF[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float v0 = (&V0.x)[e], a0 = (&A0.x)[e], f0 = (&F0.x)[e], r = (&R.x)[e];
-                float V, A, F;
-                if (S == 1) { V = v0; A = a0; F = f0; }
-                if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * (&k1A.x)[e] * third; F = f0 + dt * (&k1F.x)[e] * third; }
-                if (S == 3) {
-                    V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third);
-                    A = a0 + dt * ((&k2A.x)[e] - (&k1A.x)[e] * third);
-                    F = f0 + dt * ((&k2F.x)[e] - (&k1F.x)[e] * third);
-                }
-                if (S == 4) {
-                    V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]);
-                    A = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + (&k3A.x)[e]);
-                    F = f0 + dt * ((&k1F.x)[e] - (&k2F.x)[e] + (&k3F.x)[e]);
-                }
-                const float total = tot[4 * q + e] * p.c.tau_s;
-                const float dV = (total * p.c.R - V) * inv_tm;
-                const float dA = (kap * r - A) * inv_ta;
-                const float dF = (r - F) * inv_ts;
-                oKV[e] = dV; oKA[e] = dA; oKF[e] = dF;
-                float nV, nA, nF = 0.f;
-                if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
-                if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - (&k1A.x)[e] * third); }
-                if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + dA); }
-                if (S == 4) {
-                    nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
-                    nA = a0 + ((&k1A.x)[e] + 3.f * ((&k2A.x)[e] + (&k3A.x)[e]) + dA) * dt * 0.125f;
-                    nF = f0 + ((&k1F.x)[e] + 3.f * ((&k2F.x)[e] + (&k3F.x)[e]) + dF) * dt * 0.125f;
-                }
-                oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
-                if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
-                else oR[e] = phi_fast(nV - nA);
+        for (int e = 0; e < 4; ++e) {
+            const float v0 = (&V0.x)[e], a0 = (&A0.x)[e], f0 = (&F0.x)[e], r = (&R.x)[e];
+            float V, A, F;
+            if (S == 1) { V = v0; A = a0; F = f0; }
+            if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * (&k1A.x)[e] * third; F = f0 + dt * (&k1F.x)[e] * third; }
+            if (S == 3) {
+                V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third);
+                A = a0 + dt * ((&k2A.x)[e] - (&k1A.x)[e] * third);
+                F = f0 + dt * ((&k2F.x)[e] - (&k1F.x)[e] * third);
             }
-            if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
-            const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
-            const float4 kA4 = make_float4(oKA[0], oKA[1], oKA[2], oKA[3]);
-            const float4 kF4 = make_float4(oKF[0], oKF[1], oKF[2], oKF[3]);
-            if (S == 1) { st4(K1T + oq, kV4); st4(K1T + pl + oq, kA4); st4(K1T + 2 * pl + oq, kF4); }
-            if (S == 2) { st4(K2T + oq, kV4); st4(K2T + pl + oq, kA4); st4(K2T + 2 * pl + oq, kF4); }
-            if (S == 3) { st4(K3T + oq, kV4); st4(K3T + pl + oq, kA4); st4(K3T + 2 * pl + oq, kF4); }
             if (S == 4) {
-                st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
-                st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
-                st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+                V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]);
+                A = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + (&k3A.x)[e]);
+                F = f0 + dt * ((&k1F.x)[e] - (&k2F.x)[e] + (&k3F.x)[e]);
             }
-            st4(RT_nxt + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+            const float total = tot4[e] * p.c.tau_s;
+            const float dV = (total * p.c.R - V) * inv_tm;
+            const float dA = (kap * r - A) * inv_ta;
+            const float dF = (r - F) * inv_ts;
+            oKV[e] = dV; oKA[e] = dA; oKF[e] = dF;
+            float nV, nA, nF = 0.f;
+            if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
+            if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - (&k1A.x)[e] * third); }
+            if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + dA); }
+            if (S == 4) {
+                nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
+                nA = a0 + ((&k1A.x)[e] + 3.f * ((&k2A.x)[e] + (&k3A.x)[e]) + dA) * dt * 0.125f;
+                nF = f0 + ((&k1F.x)[e] + 3.f * ((&k2F.x)[e] + (&k3F.x)[e]) + dF) * dt * 0.125f;
+            }
+            oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
+            if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
+            else oR[e] = (dbg_skip & 4) ? (nV - nA) : phi_fast(nV - nA);
+        }
+        if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
+        const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
+        const float4 kA4 = make_float4(oKA[0], oKA[1], oKA[2], oKA[3]);
+        const float4 kF4 = make_float4(oKF[0], oKF[1], oKF[2], oKF[3]);
+        if (dbg_skip & 8) return;
+        if (S == 1) { st4(K1T + oq, kV4); st4(K1T + pl + oq, kA4); st4(K1T + 2 * pl + oq, kF4); }
+        if (S == 2) { st4(K2T + oq, kV4); st4(K2T + pl + oq, kA4); st4(K2T + 2 * pl + oq, kF4); }
+        if (S == 3) { st4(K3T + oq, kV4); st4(K3T + pl + oq, kA4); st4(K3T + 2 * pl + oq, kF4); }
+        if (S == 4) {
+            st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+            st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+            st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+        }
+        st4(RT_nxt + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int b = n0 + g * TNq + 4 * q + e;
-                if (b < B) {
-                    const float h = tf32_rna(oR[e]);
+        for (int e = 0; e < 4; ++e) {
+            const int b = b0 + e;
+            if (b < B) {
+                const float h = tf32_rna(oR[e]);
+                if (!(dbg_skip & 2)) {
                     Rhi_nxt[(size_t)b * KPa + i] = h;
                     Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
-                    if (S == 4 && traj_row) {
-                        float* yr = traj_row + (size_t)b * 3 * N + i;
-                        yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
-                    }
+                }
+                if (S == 4 && traj_row && !(dbg_skip & 1)) {
+                    float* yr = traj_row + (size_t)b * 3 * N + i;
+                    yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
                 }
             }
+        }
+    }
+
+    // The scratch loads of a float4 group cost a full DRAM round trip; the early stages read few planes, so U groups are
+    // loaded before any is processed to keep enough requests in flight (U = 3, 2, 1, 1 for stages 1..4: register budget).
+    ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (i >= p.N) return;
+        constexpr int U = S == 1 ? 3 : (S == 2 ? 2 : 1);
+        const float kap = __ldg(p.kappa + i);
+        const size_t pl = tg.plane();
+        const int nq = TNq >> 2;
+#pragma unroll
+        for (int q0 = 0; q0 < kMaxQ / 4; q0 += U) {
+            if (q0 >= nq) break;
+            Loaded L[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q0 + u < nq) load(tg.off(nt, g, q0 + u, i), pl, L[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q0 + u < nq) finish(L[u], tg.off(nt, g, q0 + u, i), pl, i, n0 + g * TNq + 4 * (q0 + u), kap, &tot[4 * (q0 + u)]);
         }
     }
 

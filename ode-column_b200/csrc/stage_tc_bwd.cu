@@ -518,14 +518,14 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
             e.Y0T = YT; e.Y1T = nullptr; e.traj_row = nullptr;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
             e.RT_cur = RT; e.RT_nxt = RT;                       // in place: each element is read then written by its owner
-            e.Rhi_nxt = Rhi + S * rstride; e.Rlo_nxt = Rlo + S * rstride; e.DRT_nxt = DRT[S];
+            e.Rhi_nxt = Rhi + S * rstride; e.Rlo_nxt = Rlo + S * rstride; e.DRT_nxt = DRT[S]; e.dbg_skip = 0;
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.t0 = e.t1 = e.dt = 0.f;
         };
         int rc;
-        { FwdEpiT<1> e; fill_f(e, 1); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 0 * L.Bp}, e, s); if (rc) return rc; }
-        { FwdEpiT<2> e; fill_f(e, 2); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 1 * L.Bp}, e, s); if (rc) return rc; }
-        { FwdEpiT<3> e; fill_f(e, 3); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 2 * L.Bp}, e, s); if (rc) return rc; }
+        { FwdEpiT<1> e; fill_f(e, 1); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        { FwdEpiT<2> e; fill_f(e, 2); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        { FwdEpiT<3> e; fill_f(e, 3); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         // reverse stages 4, 3, 2, then dW, then stage 1 (which overwrites the stage-4 operand for the next step)
         auto fill_b = [&](auto& e, int S) {
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
@@ -536,12 +536,12 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.dt = e.h8p = 0.f;
         };
-        { BwdEpiT<4> e; fill_b(e, 4); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 3 * L.Bp}, e, s); if (rc) return rc; }
-        { BwdEpiT<3> e; fill_b(e, 3); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 2 * L.Bp}, e, s); if (rc) return rc; }
-        { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 1 * L.Bp}, e, s); if (rc) return rc; }
+        { BwdEpiT<4> e; fill_b(e, 4); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 3 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        { BwdEpiT<3> e; fill_b(e, 3); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi, dAlo, dBhi, dBlo, ds);
         count_launch();
-        { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 0 * L.Bp}, e, s); if (rc) return rc; }
+        { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
     }
     if (grad_y0) {
         k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);

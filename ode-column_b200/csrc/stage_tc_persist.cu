@@ -1,0 +1,259 @@
+// Family T, persistent variant: ONE cooperative launch runs the whole rk4 time loop (all steps, all four stages).
+//
+// Each CTA keeps the (population tile, trial tile) pairs it owns for the entire solve.  Stage q+1 of a trial tile needs
+// the operand rows written by the stage-q epilogues of ALL population tiles of that trial tile -- a dependency between
+// the 4 CTAs of a group only -- so instead of a kernel boundary per stage the TMA producer waits on a per-trial-tile
+// counter in global memory (release/acquire + cross-proxy fence).  Consequences:
+//   * the epilogue of (stage q, tile A) overlaps the contraction of (stage q, tile B) AND the contraction of
+//     (stage q+1, tile A) overlaps the epilogue of (stage q, tile B): in steady state only the epilogues are exposed;
+//   * no per-launch prologue (barrier init, TMEM allocation, descriptor fetch) and no drain/fill bubble between stages;
+//   * 6,000 launches per forward solve become one.
+// All CTAs must be co-resident (they wait on each other), hence cudaLaunchCooperativeKernel with grid <= #SMs.
+#include "stage_tc.cuh"
+
+namespace odecol {
+namespace tc {
+
+struct PersistArgs {
+    DevProblem p;
+    TileGeom tg;
+    TileShape ts;
+    const float* t;
+    int T, out_every, KPa;
+    float* y_out;              // (rows, B, 3N)
+    float* YT[2];              // tile-major state, ping-pong per step
+    float* KT[3];
+    float* RT[2];              // r of the current / next stage, ping-pong per stage
+    float* Rhi[2]; float* Rlo[2];
+    unsigned int* done;        // [NT] cumulative count of finished (population-tile) epilogues per trial tile
+    float inv_tm, inv_ta, inv_ts;
+};
+
+ODECOL_DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int S>
+ODECOL_DEVINL void persist_epilogue(const PersistArgs& a, int n, int q, int m_tile, int row, int n0, int nt, int g, int TNq,
+                                    const float (&tot)[kMaxQ], int etid) {
+    FwdEpiT<S> e;
+    e.p = a.p; e.tg = a.tg; e.t = a.t; e.n = n; e.KPa = a.KPa;
+    e.Y0T = a.YT[n & 1]; e.Y1T = a.YT[(n + 1) & 1];
+    const int j = n + 1;
+    const bool emit = (j % a.out_every == 0) || (j == a.T - 1);
+    const size_t r = (j % a.out_every == 0) ? (size_t)(j / a.out_every) : (size_t)((a.T - 2) / a.out_every + 1);
+    e.traj_row = emit ? a.y_out + r * ((size_t)a.p.B * 3 * a.p.N) : nullptr;
+    e.K1T = a.KT[0]; e.K2T = a.KT[1]; e.K3T = a.KT[2];
+    e.RT_cur = a.RT[q & 1]; e.RT_nxt = a.RT[(q + 1) & 1];
+    e.Rhi_nxt = a.Rhi[(q + 1) & 1]; e.Rlo_nxt = a.Rlo[(q + 1) & 1];
+    e.DRT_nxt = nullptr; e.dbg_skip = 0;
+    e.inv_tm = a.inv_tm; e.inv_ta = a.inv_ta; e.inv_ts = a.inv_ts;
+    e.prepare();
+    e.rows(m_tile, row, n0, nt, g, TNq, tot);
+    e.tile_done(m_tile, n0, a.ts.TN, etid, kEpiWarps * 32);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant__ CUtensorMap mW_lo,
+                        const __grid_constant__ CUtensorMap mR_hi0, const __grid_constant__ CUtensorMap mR_lo0,
+                        const __grid_constant__ CUtensorMap mR_hi1, const __grid_constant__ CUtensorMap mR_lo1,
+                        PersistArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+    __shared__ uint32_t tmem_base_slot;
+    const TileShape ts = a.ts;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)ts.TN * BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * STAGES]), tempty = smem_u32(&bars[2 * STAGES + 1]);
+    const int tiles = ts.MT * ts.NT;
+    const uint32_t acc_stride = (uint32_t)ts.TN;
+    uint32_t ncols = 32;
+    while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
+    const int n_seq = 4 * (a.T - 1);                  // stage sequence numbers q = 4 n + (s - 1)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int q = 0; q < n_seq; ++q) {
+                const CUtensorMap* mb_hi = (q & 1) ? &mR_hi1 : &mR_hi0;
+                const CUtensorMap* mb_lo = (q & 1) ? &mR_lo1 : &mR_lo0;
+                for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                    const int nt = tile / ts.MT, m0 = (tile % ts.MT) * BM, n0 = nt * ts.TN;
+                    // operand rows of this trial tile are complete once every population tile finished stage q-1
+                    const unsigned int need = (unsigned int)ts.MT * (unsigned int)q;
+                    uint32_t spins = 0;
+                    while (ld_acquire_u32(a.done + nt) < need) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 26)) __trap();
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes -> TMA (async proxy) reads
+                    for (int kb = 0; kb < ts.KB; ++kb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, stage_bytes);
+                        tma_load_2d(base, &mW_hi, fb, kb * BK, m0);
+                        tma_load_2d(base + a_bytes, &mW_lo, fb, kb * BK, m0);
+                        tma_load_2d(base + 2 * a_bytes, mb_hi, fb, kb * BK, n0);
+                        tma_load_2d(base + 2 * a_bytes + b_bytes, mb_lo, fb, kb * BK, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(ts.TN);
+            const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int q = 0; q < n_seq; ++q) {
+                for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                    mbar_wait(tempty, tphase ^ 1);
+                    tc_fence_after();
+                    int j = 0;
+                    for (int kb = 0; kb < ts.KB; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t base = ring + stage * stage_bytes;
+                        const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
+                        const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k, ++j) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                            umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                        }
+                        umma_commit(empty0 + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(tfull);
+                    tphase ^= 1;
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int g = ew >> 2;
+        const int etid = ew * 32 + lane;
+        const int TNq = ts.TN >> 2;
+        uint32_t tphase = 0;
+        for (int q = 0; q < n_seq; ++q) {
+            const int n = q >> 2, s = (q & 3) + 1;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
+                const int row = m_tile * BM + quarter * 32 + lane;
+                float tot[kMaxQ];
+                mbar_wait(tfull, tphase);
+                tc_fence_after();
+                const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
+#pragma unroll
+                for (int qq = 0; qq < kMaxQ / 4; ++qq) {
+                    if (4 * qq < TNq) {
+                        uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                        for (int c = 0; c <= kMainAcc; ++c) tmem_ld4_issue(lane_base + c * acc_stride + 4 * qq, u[c]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float sum = __uint_as_float(u[kMainAcc][e]);
+#pragma unroll
+                            for (int c = 0; c < kMainAcc; ++c) sum += __uint_as_float(u[c][e]);
+                            tot[4 * qq + e] = sum;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
+                tphase ^= 1;
+                switch (s) {
+                    case 1: persist_epilogue<1>(a, n, q, m_tile, row, n0, nt, g, TNq, tot, etid); break;
+                    case 2: persist_epilogue<2>(a, n, q, m_tile, row, n0, nt, g, TNq, tot, etid); break;
+                    case 3: persist_epilogue<3>(a, n, q, m_tile, row, n0, nt, g, TNq, tot, etid); break;
+                    default: persist_epilogue<4>(a, n, q, m_tile, row, n0, nt, g, TNq, tot, etid); break;
+                }
+                // publish: all epilogue warps' writes of this tile, then one release increment
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+                if (etid == 0) atomicAdd(a.done + nt, 1u);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// workspace = the per-stage forward layout plus the dependency counters; reuses tc_fwd_layout's buffers
+int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
+                          float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
+                          float* const YT[2], float* const RT[2], unsigned int* done, int Np, int Bp, int KPa, int TN,
+                          cudaStream_t s) {
+    using namespace tc;
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+    const TileGeom tg{Bp / TN, Np, TN, TN / 4};
+    const TileShape tsh{Np / BM, Bp / TN, TN, KPa / BK, 0, nullptr};
+    const int tiles = tsh.MT * tsh.NT;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    // every trial tile's population tiles must be owned by co-resident CTAs: guaranteed by the cooperative launch
+
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, Np, KPa);
+    extern void tc_launch_init(const DevProblem&, const TileGeom&, const float*, const float*, float*, float*, float*, float*,
+                               float*, float*, int, int, cudaStream_t);
+    tc_launch_init(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], RT[0], KPa, Bp, s);
+    count_launch(2);
+    if (cudaMemsetAsync(done, 0, sizeof(unsigned int) * tsh.NT, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    CUtensorMap mWhi, mWlo, mRhi[2], mRlo[2];
+    bool ok = make_map(&mWhi, Whi, Np, KPa, KPa, BM) && make_map(&mWlo, Wlo, Np, KPa, KPa, BM);
+    for (int i = 0; i < 2; ++i)
+        ok = ok && make_map(&mRhi[i], Rhi[i], Bp, KPa, KPa, TN) && make_map(&mRlo[i], Rlo[i], Bp, KPa, KPa, TN);
+    if (!ok) return ODECOL_E_CUDA;
+
+    PersistArgs a;
+    a.p = p; a.tg = tg; a.ts = tsh; a.t = t_dev; a.T = T; a.out_every = out_every; a.KPa = KPa; a.y_out = y_out;
+    for (int i = 0; i < 2; ++i) { a.YT[i] = YT[i]; a.RT[i] = RT[i]; a.Rhi[i] = Rhi[i]; a.Rlo[i] = Rlo[i]; }
+    for (int i = 0; i < 3; ++i) a.KT[i] = KT[i];
+    a.done = done;
+    a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
+    const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)TN * BK * 4) + 1024;
+    if (cudaFuncSetAttribute(k_tc_rk4_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return ODECOL_E_CUDA;
+    int max_blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_tc_rk4_fwd_persistent, kThreads, smem) != cudaSuccess || max_blocks < 1)
+        return ODECOL_E_CUDA;
+    if (grid > max_blocks * num_sms()) grid = max_blocks * num_sms();
+    void* args[] = {&mWhi, &mWlo, &mRhi[0], &mRlo[0], &mRhi[1], &mRlo[1], &a};
+    if (cudaLaunchCooperativeKernel((const void*)k_tc_rk4_fwd_persistent, dim3(grid), dim3(kThreads), args, smem, s) != cudaSuccess)
+        return ODECOL_E_CUDA;
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+}  // namespace odecol
