@@ -44,6 +44,7 @@ struct RhsEpi {
             fb[2 * N] = (r - yb[2 * N]) * inv_ts;
         }
     }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 

@@ -20,6 +20,7 @@ struct StoreEpi {
             if (j < TNq && b < N) C[(size_t)b * ldc + i] = tot[j];
         }
     }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 
@@ -80,7 +81,7 @@ __global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y
 
 struct TcFwdLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[2], off_done, total;
+    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[4], off_done, total;
 };
 
 static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
@@ -94,9 +95,9 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     L.off_Whi = take((size_t)L.Np * L.KPa); L.off_Wlo = take((size_t)L.Np * L.KPa);
     for (int i = 0; i < 2; ++i) { L.off_Rhi[i] = take((size_t)L.Bp * L.KPa); L.off_Rlo[i] = take((size_t)L.Bp * L.KPa); }
     const size_t plane = (size_t)L.Np * L.Bp;
-    for (int i = 0; i < 3; ++i) L.off_K[i] = take(3 * plane);
+    for (int i = 0; i < 3; ++i) L.off_K[i] = take(plane);            // V slope of stages 1..3
     for (int i = 0; i < 2; ++i) L.off_Y[i] = take(3 * plane);
-    for (int i = 0; i < 2; ++i) L.off_RT[i] = take(plane);
+    for (int i = 0; i < 4; ++i) L.off_RT[i] = take(plane);           // r of stages 1..4
     L.off_done = take((size_t)(L.Bp / L.TN) + 64);          // one uint32 per trial tile (floats == 4 bytes)
     L.total = o;
     return L;
@@ -111,7 +112,7 @@ void tc_launch_init(const DevProblem& p, const tc::TileGeom& tg, const float* y0
 
 int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
                           float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
-                          float* const YT[2], float* const RT[2], unsigned int* done, int Np, int Bp, int KPa, int TN,
+                          float* const YT[2], float* const RT[4], unsigned int* done, int Np, int Bp, int KPa, int TN,
                           cudaStream_t s);
 
 static bool persistent_enabled() {
@@ -134,7 +135,7 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     float* Rlo[2] = {F(L.off_Rlo[0]), F(L.off_Rlo[1])};
     float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
     float* YT[2] = {F(L.off_Y[0]), F(L.off_Y[1])};
-    float* RT[2] = {F(L.off_RT[0]), F(L.off_RT[1])};
+    float* RT[4] = {F(L.off_RT[0]), F(L.off_RT[1]), F(L.off_RT[2]), F(L.off_RT[3])};
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
     const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
@@ -153,6 +154,13 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     if (!ok) return ODECOL_E_CUDA;
     const TileShape ts0{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
 
+    // diagnostics only (ODECOL_TIMELINE=1): per-CTA globaltimer stamps of the eight launches of steps 2 and 3
+    unsigned long long* tl_buf = nullptr;
+    if (getenv("ODECOL_TIMELINE") && T > 5) {
+        cudaMalloc(&tl_buf, sizeof(unsigned long long) * 8 * 148 * 8);
+        cudaMemsetAsync(tl_buf, 0, sizeof(unsigned long long) * 8 * 148 * 8, s);
+    }
+    const int dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
     int cur = 0;
     for (int n = 0; n < T - 1; ++n) {
         const int j = n + 1;
@@ -162,44 +170,56 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
             e.Y0T = YT[n & 1]; e.Y1T = YT[(n + 1) & 1]; e.traj_row = emit ? y_out + r * st : nullptr;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
-            e.RT_cur = RT[cur]; e.RT_nxt = RT[cur ^ 1]; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1]; e.DRT_nxt = nullptr; e.dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
+            for (int q = 0; q < 4; ++q) e.RsT[q] = RT[q];
+            e.store_r = 1; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1]; e.DRT_nxt = nullptr; e.dbg_skip = dbg_skip;
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.t0 = e.t1 = e.dt = 0.f;
         };
         for (int S = 1; S <= 4; ++S) {
             int rc;
             TileShape ts = ts0;
-            unsigned long long* dbg = nullptr;
-            if (n == 2 && getenv("ODECOL_TIMELINE")) {          // diagnostics only: per-CTA timeline of one launch
-                cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 148);
-                cudaMemset(dbg, 0, sizeof(unsigned long long) * 8 * 148);
-                ts.dbg = dbg;
-            }
+            if (tl_buf && n >= 2 && n < 4) ts.dbg = tl_buf + (size_t)((n - 2) * 4 + (S - 1)) * 8 * 148;
             if (S == 1) { FwdEpiT<1> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else if (S == 2) { FwdEpiT<2> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else if (S == 3) { FwdEpiT<3> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             else { FwdEpiT<4> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
             if (rc != ODECOL_OK) return rc;
-            if (dbg) {
-                cudaStreamSynchronize(s);
-                unsigned long long h[8 * 148];
-                cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-                cudaFree(dbg);
-                double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-                int cnt = 0;
-                for (int c = 0; c < 148; ++c) {
-                    const unsigned long long* r = h + 8 * c;
-                    if (!r[0] || !r[6]) continue;
-                    ++cnt;
-                    acc[0] += (double)(r[1] - r[0]); acc[1] += (double)(r[2] - r[1]); acc[2] += (double)(r[3] - r[2]);
-                    acc[3] += (double)(r[4] - r[3]); acc[4] += (double)(r[5] - r[4]); acc[5] += (double)(r[6] - r[5]);
-                    acc[6] += (double)(r[6] - r[0]);
-                }
-                if (cnt) fprintf(stderr, "[odecol timeline] stage %d, %d CTAs, mean ns: mainloop1 %.0f | drain1 %.0f | epilogue1 %.0f | "
-                                 "wait2 %.0f | drain2 %.0f | epilogue2 %.0f | total %.0f\n", S, cnt, acc[0] / cnt, acc[1] / cnt,
-                                 acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt, acc[6] / cnt);
-            }
             cur ^= 1;
+        }
+    }
+    if (tl_buf) {
+        cudaStreamSynchronize(s);
+        static unsigned long long h[8 * 8 * 148];
+        cudaMemcpy(h, tl_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(tl_buf);
+        unsigned long long origin = ~0ull;
+        for (int c = 0; c < 148; ++c) if (h[8 * c] && h[8 * c] < origin) origin = h[8 * c];
+        for (int l = 0; l < 8; ++l) {
+            const unsigned long long* hl = h + (size_t)l * 8 * 148;
+            double seg[6] = {0, 0, 0, 0, 0, 0}, end_mean = 0;
+            unsigned long long s_min = ~0ull, s_max = 0, e_min = ~0ull, e_max = 0;
+            int cnt = 0;
+            for (int c = 0; c < 148; ++c) {
+                const unsigned long long* r = hl + 8 * c;
+                if (!r[0] || !r[6]) continue;
+                ++cnt;
+                for (int k = 0; k < 6; ++k) seg[k] += (double)(r[k + 1] - r[k]);
+                end_mean += (double)(r[6] - origin);
+                if (r[0] < s_min) s_min = r[0];
+                if (r[0] > s_max) s_max = r[0];
+                if (r[6] < e_min) e_min = r[6];
+                if (r[6] > e_max) e_max = r[6];
+            }
+            if (!cnt) continue;
+            if (atoi(getenv("ODECOL_TIMELINE")) >= 2 && l == 4)
+                for (int c = 0; c < 148; ++c) {
+                    const unsigned long long* r = hl + 8 * c;
+                    fprintf(stderr, "[odecol cta] %d sm %llu start %llu ml1 %llu epi1 %llu epi2 %llu end %llu\n", c, r[7], r[0] - s_min,
+                            r[1] - r[0], r[3] - r[2], r[6] - r[5], r[6] - s_min);
+                }
+            fprintf(stderr, "[odecol timeline] step %d stage %d (%d CTAs) ns: start %llu..%llu end %llu..%llu (mean %.0f) | mainloop1 %.0f drain1 %.0f "
+                            "epilogue1 %.0f wait2 %.0f drain2 %.0f epilogue2 %.0f\n", 2 + l / 4, 1 + l % 4, cnt, s_min - origin, s_max - origin,
+                    e_min - origin, e_max - origin, end_mean / cnt, seg[0] / cnt, seg[1] / cnt, seg[2] / cnt, seg[3] / cnt, seg[4] / cnt, seg[5] / cnt);
         }
     }
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;

@@ -97,6 +97,8 @@ struct TileShape {
     unsigned long long* dbg; // optional per-CTA timeline stamps (globaltimer ns): [cta][8], diagnostics only
 };
 
+ODECOL_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 ODECOL_DEVINL unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -109,6 +111,7 @@ constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4
 // the persistent warp-specialised contraction.  Epi supplies
 //   prepare()                                             once per epilogue thread
 //   rows(m_tile, i, n0, nt, g, tot)                       population i, trials n0 + g*TN/4 + [0, TN/4): tot[] = W_aug.r_aug
+//   pre_tile(row, nt, g, TNq)                             per tile, before the accumulator is ready (prefetch only)
 //   tile_done(m_tile, n0, tile_n, etid, nthreads)         per tile, all epilogue threads
 // ---------------------------------------------------------------------------------------------------------------
 template <class Epi>
@@ -143,7 +146,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    if (ts.dbg && threadIdx.x == 0) ts.dbg[blockIdx.x * 8 + 0] = gtimer();
+    if (ts.dbg && threadIdx.x == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        ts.dbg[blockIdx.x * 8 + 0] = gtimer();
+        ts.dbg[blockIdx.x * 8 + 7] = smid;
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -203,6 +211,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
             const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
             const int row = m_tile * BM + quarter * 32 + lane;
             float tot[kMaxQ];
+            epi.pre_tile(row, nt, g, TNq);            // warm L2 with the first groups' scratch while the contraction runs
             mbar_wait(tfull, tphase);
             tc_fence_after();
             const int tslot = (tile - blockIdx.x) / gridDim.x;
@@ -379,6 +388,11 @@ struct TileGeom {
     }
 };
 
+// Forward stage epilogue (3/8 rule, reference step: torchdiffeq rk_common.py rk4_alt_step_func).  Only what cannot be
+// recomputed crosses a stage boundary through HBM: the V slope of each stage (it carries the contraction) and r of each
+// stage.  The A and F slopes are linear in r, so every stage re-derives them in registers from A0 / F0 and r_1..r_S with
+// the same expressions, in the same order, as a kernel that had stored them; F is only touched at stage 4.
+// Bytes per (population, trial): 28 / 36 / 44 / 64 (+12 trajectory) for stages 1..4.
 template <int S>
 struct FwdEpiT {
     DevProblem p;
@@ -388,12 +402,12 @@ struct FwdEpiT {
     const float* Y0T;      // [3 planes] state at the start of the step (tile-major)
     float* Y1T;            // stage 4: state at the end of the step (tile-major)
     float* traj_row;       // stage 4: (B, 3N) row of the trajectory, or NULL
-    float* K1T; float* K2T; float* K3T;     // [3 planes] each
-    const float* RT_cur;   // [1 plane] r of this stage
-    float* RT_nxt;         // r of the next stage
+    float* K1T; float* K2T; float* K3T;     // [1 plane] each: V slope of stages 1..3
+    float* RsT[4];         // [1 plane] each: r of stages 1..4; stage S reads 0..S-1 and writes r of the next stage to S % 4
+    int store_r;           // 0: the next stage's r plane is not needed (last recomputed stage of the reverse sweep)
     float* Rhi_nxt; float* Rlo_nxt;         // [Bp][KPa] operand of the next contraction
     float* DRT_nxt;        // optional [1 plane]: phi'(x) of the next stage state (reverse-sweep recompute)
-    int dbg_skip;          // diagnostics: 1 skip trajectory stores, 2 skip operand stores, 4 skip phi, 8 skip k stores
+    int dbg_skip;          // diagnostics: 1 skip trajectory stores, 2 skip operand stores, 4 skip phi, 8 skip all stores
     float inv_tm, inv_ta, inv_ts;
     float t0, t1, dt;
 
@@ -402,119 +416,120 @@ struct FwdEpiT {
         dt = __fsub_rn(t1, t0);
     }
 
-    // everything one float4 group (4 trials) of population i needs from the scratch planes
-    struct Loaded {
-        float4 V0, A0, F0, R, k1V, k1A, k1F, k2V, k2A, k2F, k3V, k3A, k3F;
-    };
-    ODECOL_DEVINL void load(size_t oq, size_t pl, Loaded& L) const {
-        L.V0 = ld4(Y0T + oq); L.A0 = ld4(Y0T + pl + oq); L.F0 = ld4(Y0T + 2 * pl + oq);
-        L.R = ld4(RT_cur + oq);
-        if (S >= 2) { L.k1V = ld4(K1T + oq); L.k1A = ld4(K1T + pl + oq); L.k1F = ld4(K1T + 2 * pl + oq); }
-        if (S >= 3) { L.k2V = ld4(K2T + oq); L.k2A = ld4(K2T + pl + oq); L.k2F = ld4(K2T + 2 * pl + oq); }
-        if (S >= 4) { L.k3V = ld4(K3T + oq); L.k3A = ld4(K3T + pl + oq); L.k3F = ld4(K3T + 2 * pl + oq); }
+    // The epilogue is bound by the latency of its scratch loads (one float4 group in flight per thread), not by DRAM
+    // bandwidth: each group's planes are pulled into L2 kPrefetchAhead groups before they are loaded.
+    static constexpr int kPrefetchAhead = 2;
+    ODECOL_DEVINL void prefetch_group(size_t oq, size_t pl) const {
+        prefetch_l2(Y0T + oq); prefetch_l2(Y0T + pl + oq); prefetch_l2(RsT[0] + oq);
+        if (S >= 2) { prefetch_l2(K1T + oq); prefetch_l2(RsT[1] + oq); }
+        if (S >= 3) { prefetch_l2(K2T + oq); prefetch_l2(RsT[2] + oq); }
+        if (S >= 4) { prefetch_l2(K3T + oq); prefetch_l2(RsT[3] + oq); prefetch_l2(Y0T + 2 * pl + oq); }
+    }
+    ODECOL_DEVINL void pre_tile(int i, int nt, int g, int TNq) const {
+        if (i >= p.N) return;
+        const size_t pl = tg.plane();
+#pragma unroll
+        for (int q = 0; q < kPrefetchAhead; ++q)
+            if (4 * q < TNq) prefetch_group(tg.off(nt, g, q, i), pl);
     }
 
-    ODECOL_DEVINL void finish(const Loaded& L, size_t oq, size_t pl, int i, int b0, float kap, const float* tot4) const {
-        const int N = p.N, B = p.B;
-        const float third = kOneThirdL;
-        const float4 &V0 = L.V0, &A0 = L.A0, &F0 = L.F0, &R = L.R;
-        const float4 &k1V = L.k1V, &k1A = L.k1A, &k1F = L.k1F, &k2V = L.k2V, &k2A = L.k2A, &k2F = L.k2F;
-        const float4 &k3V = L.k3V, &k3A = L.k3A, &k3F = L.k3F;
-        float oKV[4], oKA[4], oKF[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float v0 = (&V0.x)[e], a0 = (&A0.x)[e], f0 = (&F0.x)[e], r = (&R.x)[e];
-            float V, A, F;
-            if (S == 1) { V = v0; A = a0; F = f0; }
-            if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * (&k1A.x)[e] * third; F = f0 + dt * (&k1F.x)[e] * third; }
-            if (S == 3) {
-                V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third);
-                A = a0 + dt * ((&k2A.x)[e] - (&k1A.x)[e] * third);
-                F = f0 + dt * ((&k2F.x)[e] - (&k1F.x)[e] * third);
-            }
-            if (S == 4) {
-                V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]);
-                A = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + (&k3A.x)[e]);
-                F = f0 + dt * ((&k1F.x)[e] - (&k2F.x)[e] + (&k3F.x)[e]);
-            }
-            const float total = tot4[e] * p.c.tau_s;
-            const float dV = (total * p.c.R - V) * inv_tm;
-            const float dA = (kap * r - A) * inv_ta;
-            const float dF = (r - F) * inv_ts;
-            oKV[e] = dV; oKA[e] = dA; oKF[e] = dF;
-            float nV, nA, nF = 0.f;
-            if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
-            if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - (&k1A.x)[e] * third); }
-            if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * ((&k1A.x)[e] - (&k2A.x)[e] + dA); }
-            if (S == 4) {
-                nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
-                nA = a0 + ((&k1A.x)[e] + 3.f * ((&k2A.x)[e] + (&k3A.x)[e]) + dA) * dt * 0.125f;
-                nF = f0 + ((&k1F.x)[e] + 3.f * ((&k2F.x)[e] + (&k3F.x)[e]) + dF) * dt * 0.125f;
-            }
-            oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
-            if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
-            else oR[e] = (dbg_skip & 4) ? (nV - nA) : phi_fast(nV - nA);
-        }
-        if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
-        const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
-        const float4 kA4 = make_float4(oKA[0], oKA[1], oKA[2], oKA[3]);
-        const float4 kF4 = make_float4(oKF[0], oKF[1], oKF[2], oKF[3]);
-        if (dbg_skip & 8) return;
-        if (S == 1) { st4(K1T + oq, kV4); st4(K1T + pl + oq, kA4); st4(K1T + 2 * pl + oq, kF4); }
-        if (S == 2) { st4(K2T + oq, kV4); st4(K2T + pl + oq, kA4); st4(K2T + 2 * pl + oq, kF4); }
-        if (S == 3) { st4(K3T + oq, kV4); st4(K3T + pl + oq, kA4); st4(K3T + 2 * pl + oq, kF4); }
-        if (S == 4) {
-            st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
-            st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
-            st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
-        }
-        st4(RT_nxt + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int b = b0 + e;
-            if (b < B) {
-                const float h = tf32_rna(oR[e]);
-                if (!(dbg_skip & 2)) {
-                    Rhi_nxt[(size_t)b * KPa + i] = h;
-                    Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
-                }
-                if (S == 4 && traj_row && !(dbg_skip & 1)) {
-                    float* yr = traj_row + (size_t)b * 3 * N + i;
-                    yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
-                }
-            }
-        }
-    }
-
-    // The scratch loads of a float4 group cost a full DRAM round trip; the early stages read few planes, so U groups are
-    // loaded before any is processed to keep enough requests in flight (U = 3, 2, 1, 1 for stages 1..4: register budget).
     ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
         if (i >= p.N) return;
-        constexpr int U = S == 1 ? 3 : (S == 2 ? 2 : 1);
+        const int N = p.N, B = p.B;
         const float kap = __ldg(p.kappa + i);
         const size_t pl = tg.plane();
-        const int nq = TNq >> 2;
+        const float third = kOneThirdL;
 #pragma unroll
-        for (int q0 = 0; q0 < kMaxQ / 4; q0 += U) {
-            if (q0 >= nq) break;
-            Loaded L[U];
+        for (int q4 = 0; q4 < kMaxQ; q4 += 4) {
+            if (q4 >= TNq) break;
+            const size_t oq = tg.off(nt, g, q4 >> 2, i);
+            if (q4 + 4 * kPrefetchAhead < TNq) prefetch_group(tg.off(nt, g, (q4 >> 2) + kPrefetchAhead, i), pl);
+            const float4 V0 = ld4(Y0T + oq), A0 = ld4(Y0T + pl + oq);
+            const float4 R1 = ld4(RsT[0] + oq);
+            float4 F0, R2, R3, R4, k1V, k2V, k3V;
+            if (S >= 2) { k1V = ld4(K1T + oq); R2 = ld4(RsT[1] + oq); }
+            if (S >= 3) { k2V = ld4(K2T + oq); R3 = ld4(RsT[2] + oq); }
+            if (S >= 4) { k3V = ld4(K3T + oq); R4 = ld4(RsT[3] + oq); F0 = ld4(Y0T + 2 * pl + oq); }
+            float oKV[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (q0 + u < nq) load(tg.off(nt, g, q0 + u, i), pl, L[u]);
+            for (int e = 0; e < 4; ++e) {
+                const float v0 = (&V0.x)[e], a0 = (&A0.x)[e];
+                // A (and at stage 4 F) slopes of the earlier stages, re-derived from r
+                float k1A = 0.f, k2A = 0.f, k3A = 0.f, A = a0, V = v0;
+                if (S >= 2) { k1A = (kap * (&R1.x)[e] - a0) * inv_ta; }
+                if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * k1A * third; }
+                if (S >= 3) { const float a2 = a0 + dt * k1A * third; k2A = (kap * (&R2.x)[e] - a2) * inv_ta; }
+                if (S == 3) { V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third); A = a0 + dt * (k2A - k1A * third); }
+                if (S >= 4) { const float a3 = a0 + dt * (k2A - k1A * third); k3A = (kap * (&R3.x)[e] - a3) * inv_ta; }
+                if (S == 4) { V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]); A = a0 + dt * (k1A - k2A + k3A); }
+                const float r = S == 1 ? (&R1.x)[e] : S == 2 ? (&R2.x)[e] : S == 3 ? (&R3.x)[e] : (&R4.x)[e];
+                const float total = tot[q4 + e] * p.c.tau_s;
+                const float dV = (total * p.c.R - V) * inv_tm;
+                const float dA = (kap * r - A) * inv_ta;
+                oKV[e] = dV;
+                float nV, nA, nF = 0.f;
+                if (S == 1) { nV = v0 + dt * dV * third; nA = a0 + dt * dA * third; }
+                if (S == 2) { nV = v0 + dt * (dV - (&k1V.x)[e] * third); nA = a0 + dt * (dA - k1A * third); }
+                if (S == 3) { nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + dV); nA = a0 + dt * (k1A - k2A + dA); }
+                if (S == 4) {
+                    nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
+                    nA = a0 + (k1A + 3.f * (k2A + k3A) + dA) * dt * 0.125f;
+                    const float f0 = (&F0.x)[e];
+                    const float k1F = ((&R1.x)[e] - f0) * inv_ts;
+                    const float f2 = f0 + dt * k1F * third;
+                    const float k2F = ((&R2.x)[e] - f2) * inv_ts;
+                    const float f3 = f0 + dt * (k2F - k1F * third);
+                    const float k3F = ((&R3.x)[e] - f3) * inv_ts;
+                    const float f4 = f0 + dt * (k1F - k2F + k3F);
+                    const float k4F = (r - f4) * inv_ts;
+                    nF = f0 + (k1F + 3.f * (k2F + k3F) + k4F) * dt * 0.125f;
+                }
+                oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
+                if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
+                else oR[e] = (dbg_skip & 4) ? (nV - nA) : phi_fast(nV - nA);
+            }
+            if (dbg_skip & 8) continue;
+            if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
+            const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
+            if (S == 1) st4(K1T + oq, kV4);
+            if (S == 2) st4(K2T + oq, kV4);
+            if (S == 3) st4(K3T + oq, kV4);
+            if (S == 4) {
+                st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+                st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+                st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+            }
+            if (store_r) st4(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+            const int b0 = n0 + g * TNq + q4;
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (q0 + u < nq) finish(L[u], tg.off(nt, g, q0 + u, i), pl, i, n0 + g * TNq + 4 * (q0 + u), kap, &tot[4 * (q0 + u)]);
+            for (int e = 0; e < 4; ++e) {
+                const int b = b0 + e;
+                if (b < B) {
+                    const float h = tf32_rna(oR[e]);
+                    if (!(dbg_skip & 2)) {
+                        Rhi_nxt[(size_t)b * KPa + i] = h;
+                        Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
+                    }
+                    if (S == 4 && traj_row && !(dbg_skip & 1)) {
+                        float* yr = traj_row + (size_t)b * 3 * N + i;
+                        yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
+                    }
+                }
+            }
         }
     }
 
-    // stimulus columns of the next operand, written once per trial tile (by the CTA that owns population tile 0)
+    // stimulus columns of the next operand, written once per trial tile: the population tiles of a trial tile share the
+    // entries evenly (one CTA doing all of them finished 25 us after the others and set the pace of every stage)
     ODECOL_DEVINL void tile_done(int m_tile, int n0, int tile_n, int etid, int nthr) const {
-        if (m_tile != 0 || p.n_in == 0) return;
+        if (p.n_in == 0) return;
         const float tn = S == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : S == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
         int idx = 1;
         const float tcl = knot_locate(p.knot_t, p.K, tn, idx);
         const int n_in = p.n_in, N = p.N;
-        for (int e = etid; e < tile_n * n_in; e += nthr) {
+        const int MT = tg.Np / BM, total = tile_n * n_in, share = (total + MT - 1) / MT;
+        const int e_end = min(total, (m_tile + 1) * share);
+        for (int e = m_tile * share + etid; e < e_end; e += nthr) {
             const int b = n0 + e / n_in, ch = e % n_in;
             if (b < p.B) {
                 const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);

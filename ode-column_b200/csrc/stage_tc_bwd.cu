@@ -112,6 +112,7 @@ struct BwdEpiT {
             }
         }
     }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 
@@ -381,7 +382,7 @@ __global__ void k_split_pad_T(const float* __restrict__ src, int n, int ld, floa
 struct TcBwdLayout {
     int Np, Bp, KPa, NPk, TN;
     size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo;   // stacked x4 operand buffers
-    size_t off_K[3], off_Y, off_RT, off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, total;
+    size_t off_K[3], off_Y, off_RT[3], off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, total;
 };
 
 static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
@@ -398,9 +399,9 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     L.off_Rhi = take(16ull * L.Bp * L.KPa); L.off_Rlo = take(16ull * L.Bp * L.KPa);
     L.off_AVhi = take(16ull * L.Bp * L.NPk); L.off_AVlo = take(16ull * L.Bp * L.NPk);
     const size_t plane = 4ull * L.Np * L.Bp;
-    for (int i = 0; i < 3; ++i) L.off_K[i] = take(3 * plane);
+    for (int i = 0; i < 3; ++i) L.off_K[i] = take(plane);
     L.off_Y = take(3 * plane);
-    L.off_RT = take(plane);
+    for (int i = 0; i < 3; ++i) L.off_RT[i] = take(plane);
     for (int i = 0; i < 4; ++i) L.off_DRT[i] = take(plane);
     L.off_lam = take(3 * plane); L.off_b4 = take(3 * plane); L.off_b3 = take(3 * plane); L.off_acur = take(3 * plane);
     L.off_inv = take(sizeof(int) * 3ull * p.N);
@@ -458,7 +459,8 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
     float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *WThi = F(L.off_WThi), *WTlo = F(L.off_WTlo);
     float *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo), *AVhi = F(L.off_AVhi), *AVlo = F(L.off_AVlo);
     float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
-    float *YT = F(L.off_Y), *RT = F(L.off_RT);
+    float* YT = F(L.off_Y);
+    float* RT[3] = {F(L.off_RT[0]), F(L.off_RT[1]), F(L.off_RT[2])};
     float* DRT[4] = {F(L.off_DRT[0]), F(L.off_DRT[1]), F(L.off_DRT[2]), F(L.off_DRT[3])};
     float *lamT = F(L.off_lam), *b4T = F(L.off_b4), *b3T = F(L.off_b3), *acurT = F(L.off_acur);
     int* inv = reinterpret_cast<int*>(w + L.off_inv);
@@ -510,14 +512,15 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
     for (int n = T - 2; n >= 0; --n) {
         const float* yn = y_traj + (size_t)n * st;
-        k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT, DRT[0], L.KPa);
+        k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT[0], DRT[0], L.KPa);
         count_launch();
         // recompute stages 1..3: operand s -> operand s+1, r and phi' of the next stage state
         auto fill_f = [&](auto& e, int S) {
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
             e.Y0T = YT; e.Y1T = nullptr; e.traj_row = nullptr;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
-            e.RT_cur = RT; e.RT_nxt = RT;                       // in place: each element is read then written by its owner
+            e.RsT[0] = RT[0]; e.RsT[1] = RT[1]; e.RsT[2] = RT[2]; e.RsT[3] = nullptr;
+            e.store_r = S < 3;                                  // r of stage 4 is only needed as the dW operand
             e.Rhi_nxt = Rhi + S * rstride; e.Rlo_nxt = Rlo + S * rstride; e.DRT_nxt = DRT[S]; e.dbg_skip = 0;
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.t0 = e.t1 = e.dt = 0.f;

@@ -23,7 +23,7 @@ struct PersistArgs {
     float* y_out;              // (rows, B, 3N)
     float* YT[2];              // tile-major state, ping-pong per step
     float* KT[3];
-    float* RT[2];              // r of the current / next stage, ping-pong per stage
+    float* RT[4];              // r of stages 1..4 of the current step
     float* Rhi[2]; float* Rlo[2];
     unsigned int* done;        // [NT] cumulative count of finished (population-tile) epilogues per trial tile
     float inv_tm, inv_ta, inv_ts;
@@ -36,8 +36,7 @@ ODECOL_DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 
 template <int S>
-ODECOL_DEVINL void persist_epilogue(const PersistArgs& a, int n, int q, int m_tile, int row, int n0, int nt, int g, int TNq,
-                                    const float (&tot)[kMaxQ], int etid) {
+ODECOL_DEVINL FwdEpiT<S> persist_epi(const PersistArgs& a, int n, int q) {
     FwdEpiT<S> e;
     e.p = a.p; e.tg = a.tg; e.t = a.t; e.n = n; e.KPa = a.KPa;
     e.Y0T = a.YT[n & 1]; e.Y1T = a.YT[(n + 1) & 1];
@@ -46,13 +45,27 @@ ODECOL_DEVINL void persist_epilogue(const PersistArgs& a, int n, int q, int m_ti
     const size_t r = (j % a.out_every == 0) ? (size_t)(j / a.out_every) : (size_t)((a.T - 2) / a.out_every + 1);
     e.traj_row = emit ? a.y_out + r * ((size_t)a.p.B * 3 * a.p.N) : nullptr;
     e.K1T = a.KT[0]; e.K2T = a.KT[1]; e.K3T = a.KT[2];
-    e.RT_cur = a.RT[q & 1]; e.RT_nxt = a.RT[(q + 1) & 1];
+    for (int k = 0; k < 4; ++k) e.RsT[k] = a.RT[k];
+    e.store_r = 1;
     e.Rhi_nxt = a.Rhi[(q + 1) & 1]; e.Rlo_nxt = a.Rlo[(q + 1) & 1];
     e.DRT_nxt = nullptr; e.dbg_skip = 0;
     e.inv_tm = a.inv_tm; e.inv_ta = a.inv_ta; e.inv_ts = a.inv_ts;
+    return e;
+}
+
+template <int S>
+ODECOL_DEVINL void persist_epilogue(const PersistArgs& a, int n, int q, int m_tile, int row, int n0, int nt, int g, int TNq,
+                                    const float (&tot)[kMaxQ], int etid) {
+    FwdEpiT<S> e = persist_epi<S>(a, n, q);
     e.prepare();
     e.rows(m_tile, row, n0, nt, g, TNq, tot);
     e.tile_done(m_tile, n0, a.ts.TN, etid, kEpiWarps * 32);
+}
+
+template <int S>
+ODECOL_DEVINL void persist_pre_tile(const PersistArgs& a, int n, int q, int row, int nt, int g, int TNq) {
+    const FwdEpiT<S> e = persist_epi<S>(a, n, q);
+    e.pre_tile(row, nt, g, TNq);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -164,6 +177,12 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
                 const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
                 const int row = m_tile * BM + quarter * 32 + lane;
                 float tot[kMaxQ];
+                switch (s) {                       // warm L2 with the first groups' scratch while the contraction runs
+                    case 1: persist_pre_tile<1>(a, n, q, row, nt, g, TNq); break;
+                    case 2: persist_pre_tile<2>(a, n, q, row, nt, g, TNq); break;
+                    case 3: persist_pre_tile<3>(a, n, q, row, nt, g, TNq); break;
+                    default: persist_pre_tile<4>(a, n, q, row, nt, g, TNq); break;
+                }
                 mbar_wait(tfull, tphase);
                 tc_fence_after();
                 const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
@@ -212,7 +231,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
 // workspace = the per-stage forward layout plus the dependency counters; reuses tc_fwd_layout's buffers
 int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
                           float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
-                          float* const YT[2], float* const RT[2], unsigned int* done, int Np, int Bp, int KPa, int TN,
+                          float* const YT[2], float* const RT[4], unsigned int* done, int Np, int Bp, int KPa, int TN,
                           cudaStream_t s) {
     using namespace tc;
     const int Kaug = p.N + p.n_in + 1;
@@ -238,7 +257,8 @@ int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const 
 
     PersistArgs a;
     a.p = p; a.tg = tg; a.ts = tsh; a.t = t_dev; a.T = T; a.out_every = out_every; a.KPa = KPa; a.y_out = y_out;
-    for (int i = 0; i < 2; ++i) { a.YT[i] = YT[i]; a.RT[i] = RT[i]; a.Rhi[i] = Rhi[i]; a.Rlo[i] = Rlo[i]; }
+    for (int i = 0; i < 2; ++i) { a.YT[i] = YT[i]; a.Rhi[i] = Rhi[i]; a.Rlo[i] = Rlo[i]; }
+    for (int i = 0; i < 4; ++i) a.RT[i] = RT[i];
     for (int i = 0; i < 3; ++i) a.KT[i] = KT[i];
     a.done = done;
     a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
