@@ -74,6 +74,10 @@ ODECOL_DEVINL void gemm_nt_core(const float* __restrict__ Ag, int ldA, const flo
 
 ODECOL_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 ODECOL_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// scratch that is streamed once per launch: L2 only.  (With ~200 KB of the SM's array carved out as shared memory the
+// remaining L1 is too small to hold a line for every outstanding load, and allocating loads stall on it.)
+ODECOL_DEVINL float4 ld4s(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+ODECOL_DEVINL void st4s(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
 
 // one state component of 4 consecutive populations
 struct C4 { float v[4]; };

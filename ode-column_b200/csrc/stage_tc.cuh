@@ -97,6 +97,7 @@ struct TileShape {
     unsigned long long* dbg; // optional per-CTA timeline stamps (globaltimer ns): [cta][8], diagnostics only
 };
 
+ODECOL_DEVINL void st_global(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 ODECOL_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 ODECOL_DEVINL unsigned long long gtimer() {
@@ -352,7 +353,10 @@ ODECOL_DEVINL float exp_fast(float x) {            // |x| < 87
     return p * __int_as_float(((int)n + 127) << 23);
 }
 ODECOL_DEVINL float tanh_small(float u) {          // Taylor through u^11: < 3e-8 relative for |u| <= 0.4
-    if (fabsf(u) > 0.4f) return tanhf(u);
+    if (fabsf(u) > 0.4f) {                         // never reached for physical states; kept small (no libdevice call)
+        const float e2 = exp_fast(fminf(2.0f * fabsf(u), 80.0f));
+        return copysignf(1.0f - __fdividef(2.0f, e2 + 1.0f), u);
+    }
     const float s = u * u;
     float p = fmaf(s, -8.8632355299021965e-3f, 2.1869488536155203e-2f);   // -1382/155925, 62/2835
     p = fmaf(s, p, -5.3968253968253968e-2f);                               // -17/315
@@ -416,40 +420,38 @@ struct FwdEpiT {
         dt = __fsub_rn(t1, t0);
     }
 
-    // The epilogue is bound by the latency of its scratch loads (one float4 group in flight per thread), not by DRAM
-    // bandwidth: each group's planes are pulled into L2 kPrefetchAhead groups before they are loaded.
-    static constexpr int kPrefetchAhead = 2;
-    ODECOL_DEVINL void prefetch_group(size_t oq, size_t pl) const {
-        prefetch_l2(Y0T + oq); prefetch_l2(Y0T + pl + oq); prefetch_l2(RsT[0] + oq);
-        if (S >= 2) { prefetch_l2(K1T + oq); prefetch_l2(RsT[1] + oq); }
-        if (S >= 3) { prefetch_l2(K2T + oq); prefetch_l2(RsT[2] + oq); }
-        if (S >= 4) { prefetch_l2(K3T + oq); prefetch_l2(RsT[3] + oq); prefetch_l2(Y0T + 2 * pl + oq); }
+    // One float4 group (4 trials) of population i: what stage S reads from the scratch planes.
+    struct Group { float4 V0, A0, R1, k1V, R2, k2V, R3, k3V, R4, F0; };
+    ODECOL_DEVINL void load_group(Group& L, size_t oq, size_t pl) const {
+        L.V0 = ld4s(Y0T + oq); L.A0 = ld4s(Y0T + pl + oq); L.R1 = ld4s(RsT[0] + oq);
+        if (S >= 2) { L.k1V = ld4s(K1T + oq); L.R2 = ld4s(RsT[1] + oq); }
+        if (S >= 3) { L.k2V = ld4s(K2T + oq); L.R3 = ld4s(RsT[2] + oq); }
+        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); L.F0 = ld4s(Y0T + 2 * pl + oq); }
     }
-    ODECOL_DEVINL void pre_tile(int i, int nt, int g, int TNq) const {
-        if (i >= p.N) return;
-        const size_t pl = tg.plane();
-#pragma unroll
-        for (int q = 0; q < kPrefetchAhead; ++q)
-            if (4 * q < TNq) prefetch_group(tg.off(nt, g, q, i), pl);
-    }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
 
+    // The group loop is rolled (its body is ~1000 instructions; seven unrolled copies missed the instruction cache) and
+    // software-pipelined: the loads of group q+1 are issued before group q is processed, so the memory system is never
+    // idle while a warp does arithmetic.  tot[] is indexed at run time and therefore lives in local memory (L1).
     ODECOL_DEVINL void rows(int, int i, int n0, int nt, int g, int TNq, const float (&tot)[kMaxQ]) const {
         if (i >= p.N) return;
         const int N = p.N, B = p.B;
         const float kap = __ldg(p.kappa + i);
         const size_t pl = tg.plane();
         const float third = kOneThirdL;
-#pragma unroll
-        for (int q4 = 0; q4 < kMaxQ; q4 += 4) {
-            if (q4 >= TNq) break;
-            const size_t oq = tg.off(nt, g, q4 >> 2, i);
-            if (q4 + 4 * kPrefetchAhead < TNq) prefetch_group(tg.off(nt, g, (q4 >> 2) + kPrefetchAhead, i), pl);
-            const float4 V0 = ld4(Y0T + oq), A0 = ld4(Y0T + pl + oq);
-            const float4 R1 = ld4(RsT[0] + oq);
-            float4 F0, R2, R3, R4, k1V, k2V, k3V;
-            if (S >= 2) { k1V = ld4(K1T + oq); R2 = ld4(RsT[1] + oq); }
-            if (S >= 3) { k2V = ld4(K2T + oq); R3 = ld4(RsT[2] + oq); }
-            if (S >= 4) { k3V = ld4(K3T + oq); R4 = ld4(RsT[3] + oq); F0 = ld4(Y0T + 2 * pl + oq); }
+        const int nq = TNq >> 2;
+        const size_t qstride = (size_t)tg.Np * 4;
+        const size_t o0 = tg.off(nt, g, 0, i);
+        Group nxt;
+        load_group(nxt, o0, pl);
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+            const size_t oq = o0 + q * qstride;
+            const Group L = nxt;
+            if (q + 1 < nq) load_group(nxt, oq + qstride, pl);
+            const float4 &V0 = L.V0, &A0 = L.A0, &R1 = L.R1, &R2 = L.R2, &R3 = L.R3, &R4 = L.R4, &F0 = L.F0;
+            const float4 &k1V = L.k1V, &k2V = L.k2V, &k3V = L.k3V;
+            const int q4 = 4 * q;
             float oKV[4], oNV[4], oNA[4], oNF[4], oR[4], oD[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -489,30 +491,32 @@ struct FwdEpiT {
                 else oR[e] = (dbg_skip & 4) ? (nV - nA) : phi_fast(nV - nA);
             }
             if (dbg_skip & 8) continue;
-            if (DRT_nxt) st4(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
+            if (DRT_nxt) st4s(DRT_nxt + oq, make_float4(oD[0], oD[1], oD[2], oD[3]));
             const float4 kV4 = make_float4(oKV[0], oKV[1], oKV[2], oKV[3]);
-            if (S == 1) st4(K1T + oq, kV4);
-            if (S == 2) st4(K2T + oq, kV4);
-            if (S == 3) st4(K3T + oq, kV4);
+            if (S == 1) st4s(K1T + oq, kV4);
+            if (S == 2) st4s(K2T + oq, kV4);
+            if (S == 3) st4s(K3T + oq, kV4);
             if (S == 4) {
-                st4(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
-                st4(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
-                st4(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+                st4s(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+                st4s(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+                st4s(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
             }
-            if (store_r) st4(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+            if (store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
             const int b0 = n0 + g * TNq + q4;
+            float* rh = Rhi_nxt + (size_t)b0 * KPa + i;
+            float* rl = Rlo_nxt + (size_t)b0 * KPa + i;
+            float* yr = (S == 4 && traj_row && !(dbg_skip & 1)) ? traj_row + (size_t)b0 * 3 * N + i : nullptr;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int b = b0 + e;
-                if (b < B) {
+                if (b0 + e < B) {
                     const float h = tf32_rna(oR[e]);
                     if (!(dbg_skip & 2)) {
-                        Rhi_nxt[(size_t)b * KPa + i] = h;
-                        Rlo_nxt[(size_t)b * KPa + i] = tf32_rna(oR[e] - h);
+                        st_global(rh + (size_t)e * KPa, h);
+                        st_global(rl + (size_t)e * KPa, tf32_rna(oR[e] - h));
                     }
-                    if (S == 4 && traj_row && !(dbg_skip & 1)) {
-                        float* yr = traj_row + (size_t)b * 3 * N + i;
-                        yr[0] = oNV[e]; yr[N] = oNA[e]; yr[2 * N] = oNF[e];
+                    if (S == 4 && yr) {
+                        float* y = yr + (size_t)e * 3 * N;
+                        st_global(y, oNV[e]); st_global(y + N, oNA[e]); st_global(y + 2 * N, oNF[e]);
                     }
                 }
             }

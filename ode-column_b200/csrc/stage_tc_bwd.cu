@@ -47,12 +47,12 @@ struct BwdEpiT {
         for (int q = 0; q < kMaxQ / 4; ++q) {
             if (4 * q >= TNq) break;
             const size_t oq = tg.off(nt, g, q, j);
-            const float4 aV = ld4(acurT + oq), aA = ld4(acurT + pl + oq), aF = ld4(acurT + 2 * pl + oq);
-            const float4 dr = ld4(DRT + oq);
-            const float4 lV = ld4(lamT + oq), lA = ld4(lamT + pl + oq), lF = ld4(lamT + 2 * pl + oq);
+            const float4 aV = ld4s(acurT + oq), aA = ld4s(acurT + pl + oq), aF = ld4s(acurT + 2 * pl + oq);
+            const float4 dr = ld4s(DRT + oq);
+            const float4 lV = ld4s(lamT + oq), lA = ld4s(lamT + pl + oq), lF = ld4s(lamT + 2 * pl + oq);
             float4 p4V, p4A, p4F, p3V, p3A, p3F;
-            if (S <= 3) { p4V = ld4(b4T + oq); p4A = ld4(b4T + pl + oq); p4F = ld4(b4T + 2 * pl + oq); }
-            if (S == 2) { p3V = ld4(b3T + oq); p3A = ld4(b3T + pl + oq); p3F = ld4(b3T + 2 * pl + oq); }
+            if (S <= 3) { p4V = ld4s(b4T + oq); p4A = ld4s(b4T + pl + oq); p4F = ld4s(b4T + 2 * pl + oq); }
+            if (S == 2) { p3V = ld4s(b3T + oq); p3A = ld4s(b3T + pl + oq); p3F = ld4s(b3T + 2 * pl + oq); }
             float nV[4], nA[4], nF[4], sV[4], sA[4], sF[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -94,12 +94,12 @@ struct BwdEpiT {
                 }
             }
             float* sdst = S == 4 ? b4T : S == 3 ? b3T : S == 2 ? b4T : lamT;
-            st4(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
-            st4(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
-            st4(sdst + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
-            st4(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
-            st4(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
-            st4(acurT + 2 * pl + oq, make_float4(nF[0], nF[1], nF[2], nF[3]));
+            st4s(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
+            st4s(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
+            st4s(sdst + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
+            st4s(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
+            st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
+            st4s(acurT + 2 * pl + oq, make_float4(nF[0], nF[1], nF[2], nF[3]));
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int b = n0 + g * TNq + 4 * q + e;
