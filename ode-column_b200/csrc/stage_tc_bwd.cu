@@ -13,16 +13,19 @@ namespace tc {
 // ---------------------------------------------------------------------------------------------------------------
 // reverse stage epilogue.  S = 4, 3, 2, 1: the stage whose Jacobian is applied (same algebra as stage_bwd.cu)
 // ---------------------------------------------------------------------------------------------------------------
+// The F component never feeds back into the dynamics, so its adjoint within a step is a fixed linear chain of lambda_F:
+// every stage re-derives its own kbar_F from lambda_F in registers (same expressions a stored version would use) and no
+// F plane of kbar / Ybar crosses a stage boundary.  Bytes per (population, trial): 48 / 56 / 64 / 60 for S = 4, 3, 2, 1.
 template <int S>
 struct BwdEpiT {
     DevProblem p;
     TileGeom tg;
     const float* t;
     int n, NPk, G;
-    float* acurT;          // [3 planes] kbar of this stage in, of the next reverse stage out
+    float* acurT;          // [2 planes: V, A] kbar of this stage in, of the next reverse stage out
     float* lamT;           // [3 planes]
-    float* b4T;            // [3 planes] Ybar_4, later Ybar_4 + Ybar_3 + Ybar_2
-    float* b3T;            // [3 planes]
+    float* b4T;            // [2 planes] Ybar_4, later Ybar_4 + Ybar_3 + Ybar_2
+    float* b3T;            // [2 planes]
     const float* DRT;      // [1 plane] phi'(x_s)
     float* AVhi_nxt; float* AVlo_nxt;   // [Bp][NPk] operand of the next reverse stage (and of dW)
     const float* grad_y;   // (T, B, G)
@@ -35,6 +38,29 @@ struct BwdEpiT {
         h8p = n > 0 ? __fsub_rn(__ldg(t + n), __ldg(t + n - 1)) * 0.125f : 0.f;
     }
 
+    struct Group { float4 aV, aA, dr, lV, lA, lF, p4V, p4A, p3V, p3A, gv, ga, gf; };
+    ODECOL_DEVINL void load_group(Group& L, size_t oq, size_t pl, int b0, int gV, int gA, int gF) const {
+        L.aV = ld4s(acurT + oq); L.aA = ld4s(acurT + pl + oq); L.dr = ld4s(DRT + oq);
+        L.lV = ld4s(lamT + oq); L.lA = ld4s(lamT + pl + oq); L.lF = ld4s(lamT + 2 * pl + oq);
+        if (S <= 3) { L.p4V = ld4s(b4T + oq); L.p4A = ld4s(b4T + pl + oq); }
+        if (S == 2) { L.p3V = ld4s(b3T + oq); L.p3A = ld4s(b3T + pl + oq); }
+        if (S == 1) {                       // loss gradient of the selected components at grid point n
+            L.gv = L.ga = L.gf = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = b0 + e;
+                if (b < p.B) {
+                    const float* gy = grad_y + ((size_t)n * p.B + b) * G;
+                    if (gV >= 0) (&L.gv.x)[e] = __ldg(gy + gV);
+                    if (gA >= 0) (&L.ga.x)[e] = __ldg(gy + gA);
+                    if (gF >= 0) (&L.gf.x)[e] = __ldg(gy + gF);
+                }
+            }
+        }
+    }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
+
+    // rolled, software-pipelined group loop (see FwdEpiT::rows)
     ODECOL_DEVINL void rows(int, int j, int n0, int nt, int g, int TNq, const float (&graw)[kMaxQ]) const {
         if (j >= p.N) return;
         const int N = p.N, B = p.B;
@@ -43,76 +69,74 @@ struct BwdEpiT {
         const float h8 = dt * 0.125f, h38 = 3.0f * h8, h3 = dt * kOneThirdL;
         int gV = -1, gA = -1, gF = -1;
         if (S == 1) { gV = inv[j]; gA = inv[N + j]; gF = inv[2 * N + j]; }
-#pragma unroll
-        for (int q = 0; q < kMaxQ / 4; ++q) {
-            if (4 * q >= TNq) break;
-            const size_t oq = tg.off(nt, g, q, j);
-            const float4 aV = ld4s(acurT + oq), aA = ld4s(acurT + pl + oq), aF = ld4s(acurT + 2 * pl + oq);
-            const float4 dr = ld4s(DRT + oq);
-            const float4 lV = ld4s(lamT + oq), lA = ld4s(lamT + pl + oq), lF = ld4s(lamT + 2 * pl + oq);
-            float4 p4V, p4A, p4F, p3V, p3A, p3F;
-            if (S <= 3) { p4V = ld4s(b4T + oq); p4A = ld4s(b4T + pl + oq); p4F = ld4s(b4T + 2 * pl + oq); }
-            if (S == 2) { p3V = ld4s(b3T + oq); p3A = ld4s(b3T + pl + oq); p3F = ld4s(b3T + 2 * pl + oq); }
-            float nV[4], nA[4], nF[4], sV[4], sA[4], sF[4];
+        const int nq = TNq >> 2;
+        const size_t qstride = (size_t)tg.Np * 4;
+        const size_t o0 = tg.off(nt, g, 0, j);
+        const int bg = n0 + g * TNq;
+        Group nxt;
+        load_group(nxt, o0, pl, bg, gV, gA, gF);
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+            const size_t oq = o0 + q * qstride;
+            const Group L = nxt;
+            if (q + 1 < nq) load_group(nxt, oq + qstride, pl, bg + 4 * (q + 1), gV, gA, gF);
+            float nV[4], nA[4], sV[4], sA[4], sF[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float av = (&aV.x)[e], aa = (&aA.x)[e], af = (&aF.x)[e], d = (&dr.x)[e];
+                const float av = (&L.aV.x)[e], aa = (&L.aA.x)[e], d = (&L.dr.x)[e];
+                const float lv = (&L.lV.x)[e], la = (&L.lA.x)[e], lf = (&L.lF.x)[e];
+                // kbar_F of this stage (and, at stage 1, the sum of the F slopes' adjoints) from lambda_F
+                const float bF4 = -(h8 * lf) * inv_ts;
+                float af = h8 * lf, bF3 = 0.f, bF2 = 0.f;
+                if (S <= 3) { af = h38 * lf + dt * bF4; bF3 = -af * inv_ts; }
+                if (S <= 2) { af = h38 * lf - dt * bF4 + dt * bF3; bF2 = -af * inv_ts; }
+                if (S == 1) { af = h8 * lf + dt * bF4 - h3 * bF3 + h3 * bF2; }
                 const float gg = graw[4 * q + e] + kap * aa * inv_ta + af * inv_ts;
                 const float bV = -av * inv_tm + d * gg;
                 const float bA = -aa * inv_ta - d * gg;
-                const float bF = -af * inv_ts;
                 if (S == 4) {
-                    sV[e] = bV; sA[e] = bA; sF[e] = bF;
-                    nV[e] = h38 * (&lV.x)[e] + dt * bV; nA[e] = h38 * (&lA.x)[e] + dt * bA; nF[e] = h38 * (&lF.x)[e] + dt * bF;
+                    sV[e] = bV; sA[e] = bA;
+                    nV[e] = h38 * lv + dt * bV; nA[e] = h38 * la + dt * bA;
                 }
                 if (S == 3) {
-                    sV[e] = bV; sA[e] = bA; sF[e] = bF;
-                    nV[e] = h38 * (&lV.x)[e] - dt * (&p4V.x)[e] + dt * bV;
-                    nA[e] = h38 * (&lA.x)[e] - dt * (&p4A.x)[e] + dt * bA;
-                    nF[e] = h38 * (&lF.x)[e] - dt * (&p4F.x)[e] + dt * bF;
+                    sV[e] = bV; sA[e] = bA;
+                    nV[e] = h38 * lv - dt * (&L.p4V.x)[e] + dt * bV;
+                    nA[e] = h38 * la - dt * (&L.p4A.x)[e] + dt * bA;
                 }
                 if (S == 2) {
-                    nV[e] = h8 * (&lV.x)[e] + dt * (&p4V.x)[e] - h3 * (&p3V.x)[e] + h3 * bV;
-                    nA[e] = h8 * (&lA.x)[e] + dt * (&p4A.x)[e] - h3 * (&p3A.x)[e] + h3 * bA;
-                    nF[e] = h8 * (&lF.x)[e] + dt * (&p4F.x)[e] - h3 * (&p3F.x)[e] + h3 * bF;
-                    sV[e] = (&p4V.x)[e] + (&p3V.x)[e] + bV; sA[e] = (&p4A.x)[e] + (&p3A.x)[e] + bA; sF[e] = (&p4F.x)[e] + (&p3F.x)[e] + bF;
+                    nV[e] = h8 * lv + dt * (&L.p4V.x)[e] - h3 * (&L.p3V.x)[e] + h3 * bV;
+                    nA[e] = h8 * la + dt * (&L.p4A.x)[e] - h3 * (&L.p3A.x)[e] + h3 * bA;
+                    sV[e] = (&L.p4V.x)[e] + (&L.p3V.x)[e] + bV; sA[e] = (&L.p4A.x)[e] + (&L.p3A.x)[e] + bA;
                 }
                 if (S == 1) {
-                    const int b = n0 + g * TNq + 4 * q + e;
-                    float gv = 0.f, ga = 0.f, gf = 0.f;
-                    if (b < B) {
-                        const float* gy = grad_y + ((size_t)n * B + b) * G;
-                        if (gV >= 0) gv = gy[gV];
-                        if (gA >= 0) ga = gy[gA];
-                        if (gF >= 0) gf = gy[gF];
-                    }
-                    const float LV = (&lV.x)[e] + (&p4V.x)[e] + bV + gv;
-                    const float LA = (&lA.x)[e] + (&p4A.x)[e] + bA + ga;
-                    const float LF = (&lF.x)[e] + (&p4F.x)[e] + bF + gf;
+                    const float bF1 = -af * inv_ts;
+                    const float LV = lv + (&L.p4V.x)[e] + bV + (&L.gv.x)[e];
+                    const float LA = la + (&L.p4A.x)[e] + bA + (&L.ga.x)[e];
+                    const float LF = lf + (bF4 + bF3 + bF2) + bF1 + (&L.gf.x)[e];
                     sV[e] = LV; sA[e] = LA; sF[e] = LF;
-                    nV[e] = h8p * LV; nA[e] = h8p * LA; nF[e] = h8p * LF;
+                    nV[e] = h8p * LV; nA[e] = h8p * LA;
                 }
             }
             float* sdst = S == 4 ? b4T : S == 3 ? b3T : S == 2 ? b4T : lamT;
             st4s(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
             st4s(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
-            st4s(sdst + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
+            if (S == 1) st4s(lamT + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
             st4s(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
             st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
-            st4s(acurT + 2 * pl + oq, make_float4(nF[0], nF[1], nF[2], nF[3]));
+            const int b0 = bg + 4 * q;
+            float* ah = AVhi_nxt + (size_t)b0 * NPk + j;
+            float* al = AVlo_nxt + (size_t)b0 * NPk + j;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int b = n0 + g * TNq + 4 * q + e;
-                if (b < B) {
+                if (b0 + e < B) {
                     const float v = gamma * nV[e];
                     const float h = tf32_rna(v);
-                    AVhi_nxt[(size_t)b * NPk + j] = h;
-                    AVlo_nxt[(size_t)b * NPk + j] = tf32_rna(v - h);
+                    st_global(ah + (size_t)e * NPk, h);
+                    st_global(al + (size_t)e * NPk, tf32_rna(v - h));
                 }
             }
         }
     }
-    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 
@@ -189,7 +213,7 @@ __global__ void k_tc_bwd_begin(DevProblem p, TileGeom tg, const float* __restric
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             st4(lamT + c * pl + o, make_float4(L[c][0], L[c][1], L[c][2], L[c][3]));
-            st4(acurT + c * pl + o, make_float4(h8 * L[c][0], h8 * L[c][1], h8 * L[c][2], h8 * L[c][3]));
+            if (c < 2) st4(acurT + c * pl + o, make_float4(h8 * L[c][0], h8 * L[c][1], h8 * L[c][2], h8 * L[c][3]));
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -403,7 +427,7 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     L.off_Y = take(3 * plane);
     for (int i = 0; i < 3; ++i) L.off_RT[i] = take(plane);
     for (int i = 0; i < 4; ++i) L.off_DRT[i] = take(plane);
-    L.off_lam = take(3 * plane); L.off_b4 = take(3 * plane); L.off_b3 = take(3 * plane); L.off_acur = take(3 * plane);
+    L.off_lam = take(3 * plane); L.off_b4 = take(2 * plane); L.off_b3 = take(2 * plane); L.off_acur = take(2 * plane);
     L.off_inv = take(sizeof(int) * 3ull * p.N);
     L.total = o;
     return L;
