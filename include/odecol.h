@@ -132,6 +132,25 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
                    float* grad_y0, float* grad_W_aug,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Checkpoint mode of the rk4 pair, for training on a selection of state components (the reference's losses read a few
+ * firing-rate components: scripts/xor_ode.py:119-177, scripts/parity_ode.py:238-250).  The forward sweep returns only
+ * y[:, :, sel] and leaves, per grid step, the V/A state and the three V slopes of the step in `ckpt` (20 bytes per
+ * population, trial and step, kernel-private layout); the reverse sweep re-derives every stage from them elementwise
+ * instead of recomputing three contractions per step.  Only the tensor family (N >= 256) implements it: other
+ * problems return ODECOL_E_UNSUPPORTED and the caller uses odecol_rk4_fwd / odecol_rk4_bwd.
+ *   odecol_rk4_ckpt_bytes   size of `ckpt` for (p, T); 0 if unsupported
+ *   y_sel       (T, B, G)  out: the selected components at every grid point (row 0 = y0[:, sel])
+ *   grad_y_sel  (T, B, G)  dL/dy_sel;  sel, G, grad_y0, grad_W_aug as in odecol_rk4_bwd
+ * Workspaces: odecol_workspace_bytes(p, ODECOL_OP_RK4_FWD / ODECOL_OP_RK4_BWD, T, 0). */
+size_t odecol_rk4_ckpt_bytes(const odecol_problem* p, int32_t T);
+int odecol_rk4_fwd_ckpt(const odecol_problem* p, const float* t, int32_t T, const float* y0,
+                        const int32_t* sel, int32_t G, float* y_sel, void* ckpt, size_t ckpt_bytes,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, const void* ckpt, size_t ckpt_bytes,
+                        const float* grad_y_sel, const int32_t* sel, int32_t G,
+                        float* grad_y0, float* grad_W_aug,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Adaptive Dormand-Prince 5(4) with per-trial step control and 4th-order dense output at t[0..T).
  * Replaces torchdiffeq.odeint(func, y0, t) with its default method (what the reference scripts get,
  * scripts/xor_ode.py:114, scripts/parity_ode.py:233; rtol 1e-7, atol 1e-9 are torchdiffeq's defaults).

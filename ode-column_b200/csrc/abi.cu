@@ -132,6 +132,43 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
     return stage_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
 }
 
+size_t odecol_rk4_ckpt_bytes(const odecol_problem* p, int32_t T) {
+    DevProblem d;
+    if (to_dev(p, d) != ODECOL_OK || T < 2) return 0;
+    if (use_small(p, d) || !use_tensor(p, d) || p->N % 4 != 0) return 0;
+    return tc_rk4_ckpt_bytes(d, T);
+}
+
+int odecol_rk4_fwd_ckpt(const odecol_problem* p, const float* t, int32_t T, const float* y0, const int32_t* sel, int32_t G,
+                        float* y_sel, void* ckpt, size_t ckpt_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y0 || !y_sel || !ckpt) return ODECOL_E_NULL;
+    if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
+    if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
+    if (misaligned(y0) || misaligned(ckpt) || misaligned(workspace)) return ODECOL_E_ALIGN;
+    g_launches.store(0, std::memory_order_relaxed);
+    return tc_rk4_fwd_ckpt(d, t, T, y0, sel, G, y_sel, ckpt, ckpt_bytes, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, const void* ckpt, size_t ckpt_bytes,
+                        const float* grad_y_sel, const int32_t* sel, int32_t G, float* grad_y0, float* grad_W_aug,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !ckpt || !grad_y_sel || !grad_W_aug) return ODECOL_E_NULL;
+    if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
+    if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
+    if (misaligned(ckpt) || misaligned(workspace) || misaligned(grad_W_aug)) return ODECOL_E_ALIGN;
+    g_launches.store(0, std::memory_order_relaxed);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+    return tc_rk4_bwd_ckpt(d, t, T, ckpt, ckpt_bytes, grad_y_sel, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
+}
+
 int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out, float rtol,
                       float atol, int32_t max_steps, int32_t* n_accept, int32_t* n_reject, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream) {

@@ -80,6 +80,12 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int T);
 int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
                int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
+// checkpoint mode (tensor family): V/A state + V slopes per step instead of the trajectory; see tc::CkptView
+size_t tc_rk4_ckpt_bytes(const DevProblem& p, int T);
+int tc_rk4_fwd_ckpt(const DevProblem& p, const float* t_dev, int T, const float* y0, const int* sel, int G, float* y_sel,
+                    void* ckpt, size_t ckpt_bytes, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_rk4_bwd_ckpt(const DevProblem& p, const float* t_dev, int T, const void* ckpt, size_t ckpt_bytes, const float* grad_y,
+                    const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_contract_tn_workspace_bytes(int M, int N, int K);
 int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_contract_workspace_bytes(int M, int N, int K);

@@ -43,17 +43,17 @@ static ContractLayout contract_layout(int M, int N, int K) {
 // and the tile-major copies of y0 and r.  One CTA per (padded) trial.
 __global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y, const float* __restrict__ t_ptr,
                           float* __restrict__ hi0, float* __restrict__ lo0, float* __restrict__ hi1, float* __restrict__ lo1,
-                          float* __restrict__ Y0T, float* __restrict__ RT, int KPa) {
+                          float* __restrict__ V0T, float* __restrict__ A0T, float* __restrict__ F0T, float* __restrict__ RT,
+                          int KPa) {
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
     const size_t ro = (size_t)b * KPa;
     const int nt = b / tg.TN, g = (b % tg.TN) / tg.TNq, jq = (b % tg.TN) % tg.TNq;
     const int q = jq >> 2, e4 = jq & 3;
-    const size_t pl = tg.plane();
     if (b >= p.B) {
         for (int k = threadIdx.x; k < KPa; k += blockDim.x) { hi0[ro + k] = 0.f; lo0[ro + k] = 0.f; hi1[ro + k] = 0.f; lo1[ro + k] = 0.f; }
         for (int i = threadIdx.x; i < tg.Np; i += blockDim.x) {
             const size_t o = tg.off(nt, g, q, i) + e4;
-            Y0T[o] = 0.f; Y0T[pl + o] = 0.f; Y0T[2 * pl + o] = 0.f; RT[o] = 0.f;
+            V0T[o] = 0.f; A0T[o] = 0.f; F0T[o] = 0.f; RT[o] = 0.f;
         }
         return;
     }
@@ -74,14 +74,14 @@ __global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y
         const size_t o = tg.off(nt, g, q, i) + e4;
         const bool in = i < N;
         const float V = in ? yb[i] : 0.f, A = in ? yb[N + i] : 0.f, F = in ? yb[2 * N + i] : 0.f;
-        Y0T[o] = V; Y0T[pl + o] = A; Y0T[2 * pl + o] = F;
+        V0T[o] = V; A0T[o] = A; F0T[o] = F;
         RT[o] = in ? phi_fast(V - A) : 0.f;
     }
 }
 
 struct TcFwdLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[4], off_done, total;
+    size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[4], off_done, off_inv, total;
 };
 
 static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
@@ -99,6 +99,7 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     for (int i = 0; i < 2; ++i) L.off_Y[i] = take(3 * plane);
     for (int i = 0; i < 4; ++i) L.off_RT[i] = take(plane);           // r of stages 1..4
     L.off_done = take((size_t)(L.Bp / L.TN) + 64);          // one uint32 per trial tile (floats == 4 bytes)
+    L.off_inv = take(3ull * p.N);                           // component -> selection position (checkpoint mode)
     L.total = o;
     return L;
 }
@@ -106,14 +107,14 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
 }  // namespace tc
 
 void tc_launch_init(const DevProblem& p, const tc::TileGeom& tg, const float* y0, const float* t_dev, float* hi0, float* lo0,
-                    float* hi1, float* lo1, float* Y0T, float* RT, int KPa, int Bp, cudaStream_t s) {
-    tc::k_tc_init<<<Bp, 128, 0, s>>>(p, tg, y0, t_dev, hi0, lo0, hi1, lo1, Y0T, RT, KPa);
+                    float* hi1, float* lo1, float* V0T, float* A0T, float* F0T, float* RT, int KPa, int Bp, cudaStream_t s) {
+    tc::k_tc_init<<<Bp, 128, 0, s>>>(p, tg, y0, t_dev, hi0, lo0, hi1, lo1, V0T, A0T, F0T, RT, KPa);
 }
 
 int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
                           float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
                           float* const YT[2], float* const RT[4], unsigned int* done, int Np, int Bp, int KPa, int TN,
-                          cudaStream_t s);
+                          const tc::CkptView* ck, cudaStream_t s);
 
 static bool persistent_enabled() {
     const char* v = getenv("ODECOL_PERSISTENT");
@@ -141,10 +142,11 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
     if (persistent_enabled())
         return tc_rk4_fwd_persistent(p, t_dev, T, y0, y_out, out_every, Whi, Wlo, Rhi, Rlo, KT, YT, RT,
-                                     reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, s);
+                                     reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, nullptr, s);
 
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    k_tc_init<<<L.Bp, 128, 0, s>>>(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], RT[0], L.KPa);
+    k_tc_init<<<L.Bp, 128, 0, s>>>(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], YT[0] + tg.plane(),
+                                   YT[0] + 2 * tg.plane(), RT[0], L.KPa);
     count_launch(2);
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi[2], mRlo[2];
@@ -168,7 +170,10 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
         const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
         auto fill = [&](auto& e) {
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
-            e.Y0T = YT[n & 1]; e.Y1T = YT[(n + 1) & 1]; e.traj_row = emit ? y_out + r * st : nullptr;
+            const size_t pl = tg.plane();
+            e.V0T = YT[n & 1]; e.A0T = YT[n & 1] + pl; e.F0T = YT[n & 1] + 2 * pl;
+            e.V1T = YT[(n + 1) & 1]; e.A1T = YT[(n + 1) & 1] + pl; e.F1T = YT[(n + 1) & 1] + 2 * pl;
+            e.traj_row = emit ? y_out + r * st : nullptr; e.ysel_row = nullptr; e.inv = nullptr; e.G = 0;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
             for (int q = 0; q < 4; ++q) e.RsT[q] = RT[q];
             e.store_r = 1; e.Rhi_nxt = Rhi[cur ^ 1]; e.Rlo_nxt = Rlo[cur ^ 1]; e.DRT_nxt = nullptr; e.dbg_skip = dbg_skip;
@@ -225,6 +230,41 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// checkpoint mode (training with a component selection): no (T, B, 3N) trajectory; the forward sweep leaves the V/A
+// state and the three V slopes of every step (20 bytes per population, trial and step) and the selected components
+// ---------------------------------------------------------------------------------------------------------------
+size_t tc_rk4_ckpt_bytes(const DevProblem& p, int T) {
+    const tc::TcFwdLayout L = tc::tc_fwd_layout(p);
+    const size_t plane = 4ull * L.Np * L.Bp;
+    return plane * (2ull * T + 3ull * (T - 1));
+}
+
+int tc_rk4_fwd_ckpt(const DevProblem& p, const float* t_dev, int T, const float* y0, const int* sel, int G, float* y_sel,
+                    void* ckpt, size_t ckpt_bytes, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const TcFwdLayout L = tc_fwd_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (!ckpt || ckpt_bytes < tc_rk4_ckpt_bytes(p, T)) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float* Rhi[2] = {F(L.off_Rhi[0]), F(L.off_Rhi[1])};
+    float* Rlo[2] = {F(L.off_Rlo[0]), F(L.off_Rlo[1])};
+    float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
+    float* YT[2] = {F(L.off_Y[0]), F(L.off_Y[1])};
+    float* RT[4] = {F(L.off_RT[0]), F(L.off_RT[1]), F(L.off_RT[2]), F(L.off_RT[3])};
+    int* inv = reinterpret_cast<int*>(w + L.off_inv);
+    const size_t plane = (size_t)L.Np * L.Bp;
+    k_tc_build_inv<<<1, 256, 0, s>>>(sel, G, 3 * p.N, inv);
+    k_tc_gather_sel<<<296, 256, 0, s>>>(y0, sel, G, p.B, 3 * p.N, y_sel);
+    count_launch(2);
+    CkptView ck;
+    ck.VA = static_cast<float*>(ckpt); ck.K = ck.VA + 2 * plane * (size_t)T; ck.y_sel = y_sel; ck.inv = inv; ck.G = G;
+    return tc_rk4_fwd_persistent(p, t_dev, T, y0, nullptr, 1, F(L.off_Whi), F(L.off_Wlo), Rhi, Rlo, KT, YT, RT,
+                                 reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, &ck, s);
+}
 
 size_t tc_contract_workspace_bytes(int M, int N, int K) { return tc::contract_layout(M, N, K).total; }
 

@@ -341,6 +341,33 @@ static __global__ void k_split_pad(const float* __restrict__ src, int rows, int 
     }
 }
 
+// component -> position in the selection (-1: not selected); sel == NULL selects everything in order
+static __global__ void k_tc_build_inv(const int* __restrict__ sel, int G, int n3, int* __restrict__ inv) {
+    for (int e = threadIdx.x; e < n3; e += blockDim.x) inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) inv[sel[g]] = g;
+}
+
+// out[b][g] = y[b][sel[g]]
+static __global__ void k_tc_gather_sel(const float* __restrict__ y, const int* __restrict__ sel, int G, int B, int n3,
+                                       float* __restrict__ out) {
+    const size_t total = (size_t)B * G;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / G), g = (int)(e % G);
+        out[e] = y[(size_t)b * n3 + (sel ? sel[g] : g)];
+    }
+}
+
+// checkpoints of the forward sweep for the reverse sweep (all tile-major planes of Np x Bp floats):
+//   VA: T slots x {V, A} at the grid points;  K: (T-1) slots x {k1V, k2V, k3V}, the V slopes of stages 1..3 of each step.
+// With them the reverse sweep re-derives every stage state elementwise (no contraction is recomputed).
+struct CkptView {
+    float* VA; float* K;
+    float* y_sel;          // (T, B, G) selected components of the trajectory (forward output), or NULL in the reverse sweep
+    const int* inv;        // [3N]
+    int G;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // fast, FP32-accurate (about 1e-7 relative) elementwise math for the tensor family's epilogue
 // ---------------------------------------------------------------------------------------------------------------
@@ -386,7 +413,7 @@ ODECOL_DEVINL void phi_dphi_fast(float x, float& r, float& dr) {
 // later and lost it from L2 in between: 6x the DRAM traffic, profiles/r1_tc_v2_ncu.txt).
 struct TileGeom {
     int NT, Np, TN, TNq;
-    ODECOL_DEVINL size_t plane() const { return (size_t)NT * 4 * Np * TNq; }
+    __host__ __device__ __forceinline__ size_t plane() const { return (size_t)NT * 4 * Np * TNq; }
     ODECOL_DEVINL size_t off(int nt, int g, int q, int i) const {
         return ((((size_t)nt * 4 + g) * (TNq >> 2) + q) * Np + i) * 4;
     }
@@ -403,9 +430,12 @@ struct FwdEpiT {
     TileGeom tg;
     const float* t;
     int n, KPa;
-    const float* Y0T;      // [3 planes] state at the start of the step (tile-major)
-    float* Y1T;            // stage 4: state at the end of the step (tile-major)
+    const float* V0T; const float* A0T; const float* F0T;   // [1 plane each] state at the start of the step (tile-major)
+    float* V1T; float* A1T; float* F1T;                      // stage 4: state at the end of the step (tile-major)
     float* traj_row;       // stage 4: (B, 3N) row of the trajectory, or NULL
+    float* ysel_row;       // stage 4: (B, G) row of the selected components (checkpoint mode), or NULL
+    const int* inv;        // [3N] component -> position in the selection, -1 if not selected (with ysel_row)
+    int G;
     float* K1T; float* K2T; float* K3T;     // [1 plane] each: V slope of stages 1..3
     float* RsT[4];         // [1 plane] each: r of stages 1..4; stage S reads 0..S-1 and writes r of the next stage to S % 4
     int store_r;           // 0: the next stage's r plane is not needed (last recomputed stage of the reverse sweep)
@@ -422,11 +452,11 @@ struct FwdEpiT {
 
     // One float4 group (4 trials) of population i: what stage S reads from the scratch planes.
     struct Group { float4 V0, A0, R1, k1V, R2, k2V, R3, k3V, R4, F0; };
-    ODECOL_DEVINL void load_group(Group& L, size_t oq, size_t pl) const {
-        L.V0 = ld4s(Y0T + oq); L.A0 = ld4s(Y0T + pl + oq); L.R1 = ld4s(RsT[0] + oq);
+    ODECOL_DEVINL void load_group(Group& L, size_t oq) const {
+        L.V0 = ld4s(V0T + oq); L.A0 = ld4s(A0T + oq); L.R1 = ld4s(RsT[0] + oq);
         if (S >= 2) { L.k1V = ld4s(K1T + oq); L.R2 = ld4s(RsT[1] + oq); }
         if (S >= 3) { L.k2V = ld4s(K2T + oq); L.R3 = ld4s(RsT[2] + oq); }
-        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); L.F0 = ld4s(Y0T + 2 * pl + oq); }
+        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); L.F0 = ld4s(F0T + oq); }
     }
     ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
 
@@ -437,18 +467,19 @@ struct FwdEpiT {
         if (i >= p.N) return;
         const int N = p.N, B = p.B;
         const float kap = __ldg(p.kappa + i);
-        const size_t pl = tg.plane();
         const float third = kOneThirdL;
         const int nq = TNq >> 2;
         const size_t qstride = (size_t)tg.Np * 4;
         const size_t o0 = tg.off(nt, g, 0, i);
+        int gV = -1, gA = -1, gF = -1;
+        if (S == 4 && ysel_row) { gV = __ldg(inv + i); gA = __ldg(inv + N + i); gF = __ldg(inv + 2 * N + i); }
         Group nxt;
-        load_group(nxt, o0, pl);
+        load_group(nxt, o0);
 #pragma unroll 1
         for (int q = 0; q < nq; ++q) {
             const size_t oq = o0 + q * qstride;
             const Group L = nxt;
-            if (q + 1 < nq) load_group(nxt, oq + qstride, pl);
+            if (q + 1 < nq) load_group(nxt, oq + qstride);
             const float4 &V0 = L.V0, &A0 = L.A0, &R1 = L.R1, &R2 = L.R2, &R3 = L.R3, &R4 = L.R4, &F0 = L.F0;
             const float4 &k1V = L.k1V, &k2V = L.k2V, &k3V = L.k3V;
             const int q4 = 4 * q;
@@ -497,9 +528,9 @@ struct FwdEpiT {
             if (S == 2) st4s(K2T + oq, kV4);
             if (S == 3) st4s(K3T + oq, kV4);
             if (S == 4) {
-                st4s(Y1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
-                st4s(Y1T + pl + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
-                st4s(Y1T + 2 * pl + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+                st4s(V1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
+                st4s(A1T + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
+                st4s(F1T + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
             }
             if (store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
             const int b0 = n0 + g * TNq + q4;
@@ -517,6 +548,12 @@ struct FwdEpiT {
                     if (S == 4 && yr) {
                         float* y = yr + (size_t)e * 3 * N;
                         st_global(y, oNV[e]); st_global(y + N, oNA[e]); st_global(y + 2 * N, oNF[e]);
+                    }
+                    if (S == 4 && ysel_row) {
+                        float* y = ysel_row + (size_t)(b0 + e) * G;
+                        if (gV >= 0) st_global(y + gV, oNV[e]);
+                        if (gA >= 0) st_global(y + gA, oNA[e]);
+                        if (gF >= 0) st_global(y + gF, oNF[e]);
                     }
                 }
             }

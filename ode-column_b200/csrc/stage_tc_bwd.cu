@@ -187,6 +187,66 @@ __global__ void k_tc_step_begin(DevProblem p, TileGeom tg, const float* __restri
     }
 }
 
+// checkpoint mode: every stage operand and phi' of step n from the saved V/A state and V slopes -- the forward stage
+// recurrences of FwdEpiT, elementwise, no contraction.  One CTA per group of four trials, threads over populations.
+__global__ void k_tc_replay(DevProblem p, TileGeom tg, const float* __restrict__ VA, const float* __restrict__ KV,
+                            const float* __restrict__ t, int n, float* __restrict__ Rhi, float* __restrict__ Rlo,
+                            size_t rstride, float* __restrict__ D0, float* __restrict__ D1, float* __restrict__ D2,
+                            float* __restrict__ D3, int KPa) {
+    const int b4 = blockIdx.x * 4, N = p.N;
+    const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
+    const size_t pl = tg.plane();
+    const float t0 = __ldg(t + n), t1 = __ldg(t + n + 1), dt = __fsub_rn(t1, t0);
+    const float third = kOneThirdL, inv_ta = 1.0f / p.c.tau_a;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const size_t o = tg.off(nt, g, q, i);
+        const float4 V0 = ld4s(VA + o), A0 = ld4s(VA + pl + o);
+        const float4 k1V = ld4s(KV + o), k2V = ld4s(KV + pl + o), k3V = ld4s(KV + 2 * pl + o);
+        const float kap = __ldg(p.kappa + i);
+        float R[4][4], D[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v0 = (&V0.x)[e], a0 = (&A0.x)[e];
+            phi_dphi_fast(v0 - a0, R[0][e], D[0][e]);
+            const float k1A = (kap * R[0][e] - a0) * inv_ta;
+            float nV = v0 + dt * (&k1V.x)[e] * third, nA = a0 + dt * k1A * third;
+            phi_dphi_fast(nV - nA, R[1][e], D[1][e]);
+            const float k2A = (kap * R[1][e] - nA) * inv_ta;
+            nV = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third); nA = a0 + dt * (k2A - k1A * third);
+            phi_dphi_fast(nV - nA, R[2][e], D[2][e]);
+            const float k3A = (kap * R[2][e] - nA) * inv_ta;
+            nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]); nA = a0 + dt * (k1A - k2A + k3A);
+            phi_dphi_fast(nV - nA, R[3][e], D[3][e]);
+        }
+        st4s(D0 + o, make_float4(D[0][0], D[0][1], D[0][2], D[0][3]));
+        st4s(D1 + o, make_float4(D[1][0], D[1][1], D[1][2], D[1][3]));
+        st4s(D2 + o, make_float4(D[2][0], D[2][1], D[2][2], D[2][3]));
+        st4s(D3 + o, make_float4(D[3][0], D[3][1], D[3][2], D[3][3]));
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (b4 + e < p.B) {
+                    const float h = tf32_rna(R[s][e]);
+                    const size_t at = s * rstride + (size_t)(b4 + e) * KPa + i;
+                    Rhi[at] = h; Rlo[at] = tf32_rna(R[s][e] - h);
+                }
+    }
+    // stimulus channels at the four stage times (the constant-one column is set once per sweep)
+    const int n_in = p.n_in;
+    for (int e = threadIdx.x; e < 16 * n_in; e += blockDim.x) {
+        const int s = e / (4 * n_in), b = b4 + (e / n_in) % 4, ch = e % n_in;
+        if (b >= p.B) continue;
+        const float ts = s == 0 ? t0 : s == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : s == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
+        int idx = 1;
+        const float tcl = knot_locate(p.knot_t, p.K, ts, idx);
+        const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
+        const float h = tf32_rna(v);
+        const size_t at = s * rstride + (size_t)b * KPa + N + ch;
+        Rhi[at] = h; Rlo[at] = tf32_rna(v - h);
+    }
+}
+
 // lam = dL/dy_out[T-1] (tile-major), kbar_4 of the last step, its operand
 __global__ void k_tc_bwd_begin(DevProblem p, TileGeom tg, const float* __restrict__ grad_y, const int* __restrict__ inv,
                                int G, const float* __restrict__ t, int T, float gamma, float* __restrict__ lamT,
@@ -252,11 +312,6 @@ __global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, in
     Rhi[((size_t)s * Bp + b) * KPa + col] = 1.0f;
 }
 
-__global__ void k_tc_build_inv(const int* __restrict__ sel, int G, int n3, int* __restrict__ inv) {
-    for (int e = threadIdx.x; e < n3; e += blockDim.x) inv[e] = sel ? -1 : e;
-    __syncthreads();
-    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) inv[sel[g]] = g;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // dW contraction: C[i][k] += sum_rows A[row][i] * B[row][k], rows = stacked (stage, trial); both operands MN-major.
@@ -472,8 +527,9 @@ int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K
 
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_bwd_layout(p).total; }
 
-int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
-               int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* ckVA,
+                           const float* ckK, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
+                           void* ws, size_t ws_bytes, cudaStream_t s) {
     using namespace tc;
     const TcBwdLayout L = tc_bwd_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -535,13 +591,21 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
 
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
     for (int n = T - 2; n >= 0; --n) {
+        int rc = ODECOL_OK;
+        if (ckVA) {
+            const size_t pl = (size_t)L.Np * L.Bp;
+            k_tc_replay<<<L.Bp / 4, 128, 0, s>>>(p, tg, ckVA + 2 * pl * (size_t)n, ckK + 3 * pl * (size_t)n, t_dev, n, Rhi, Rlo,
+                                                 rstride, DRT[0], DRT[1], DRT[2], DRT[3], L.KPa);
+            count_launch();
+        } else {
         const float* yn = y_traj + (size_t)n * st;
         k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT[0], DRT[0], L.KPa);
         count_launch();
         // recompute stages 1..3: operand s -> operand s+1, r and phi' of the next stage state
         auto fill_f = [&](auto& e, int S) {
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.KPa = L.KPa;
-            e.Y0T = YT; e.Y1T = nullptr; e.traj_row = nullptr;
+            e.V0T = YT; e.A0T = YT + tg.plane(); e.F0T = nullptr;       // stages 1..3 never touch F
+            e.V1T = e.A1T = e.F1T = nullptr; e.traj_row = nullptr; e.ysel_row = nullptr; e.inv = nullptr; e.G = 0;
             e.K1T = KT[0]; e.K2T = KT[1]; e.K3T = KT[2];
             e.RsT[0] = RT[0]; e.RsT[1] = RT[1]; e.RsT[2] = RT[2]; e.RsT[3] = nullptr;
             e.store_r = S < 3;                                  // r of stage 4 is only needed as the dW operand
@@ -549,10 +613,10 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
             e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
             e.t0 = e.t1 = e.dt = 0.f;
         };
-        int rc;
         { FwdEpiT<1> e; fill_f(e, 1); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         { FwdEpiT<2> e; fill_f(e, 2); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         { FwdEpiT<3> e; fill_f(e, 3); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        }
         // reverse stages 4, 3, 2, then dW, then stage 1 (which overwrites the stage-4 operand for the next step)
         auto fill_b = [&](auto& e, int S) {
             e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
@@ -575,6 +639,21 @@ int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_tr
         count_launch();
     }
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int tc_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* grad_y, const int* sel,
+               int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+    return tc_rk4_bwd_impl(p, t_dev, T, y_traj, nullptr, nullptr, grad_y, sel, G, grad_y0, grad_W, ws, ws_bytes, s);
+}
+
+// reverse sweep from the checkpoints of tc_rk4_fwd_ckpt (layout: tc::CkptView)
+int tc_rk4_bwd_ckpt(const DevProblem& p, const float* t_dev, int T, const void* ckpt, size_t ckpt_bytes, const float* grad_y,
+                    const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const tc::TcBwdLayout L = tc::tc_bwd_layout(p);
+    const size_t plane = (size_t)L.Np * L.Bp;
+    if (!ckpt || ckpt_bytes < 4 * plane * (2ull * T + 3ull * (T - 1))) return ODECOL_E_WORKSPACE;
+    const float* VA = static_cast<const float*>(ckpt);
+    return tc_rk4_bwd_impl(p, t_dev, T, nullptr, VA, VA + 2 * plane * (size_t)T, grad_y, sel, G, grad_y0, grad_W, ws, ws_bytes, s);
 }
 
 }  // namespace odecol

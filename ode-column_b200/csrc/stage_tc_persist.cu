@@ -26,6 +26,7 @@ struct PersistArgs {
     float* RT[4];              // r of stages 1..4 of the current step
     float* Rhi[2]; float* Rlo[2];
     unsigned int* done;        // [NT] cumulative count of finished (population-tile) epilogues per trial tile
+    CkptView ck;               // ck.VA != NULL: checkpoint mode (V/A state and V slopes per step, selected output)
     float inv_tm, inv_ta, inv_ts;
 };
 
@@ -39,12 +40,23 @@ template <int S>
 ODECOL_DEVINL FwdEpiT<S> persist_epi(const PersistArgs& a, int n, int q) {
     FwdEpiT<S> e;
     e.p = a.p; e.tg = a.tg; e.t = a.t; e.n = n; e.KPa = a.KPa;
-    e.Y0T = a.YT[n & 1]; e.Y1T = a.YT[(n + 1) & 1];
+    const size_t pl = a.tg.plane();
     const int j = n + 1;
-    const bool emit = (j % a.out_every == 0) || (j == a.T - 1);
-    const size_t r = (j % a.out_every == 0) ? (size_t)(j / a.out_every) : (size_t)((a.T - 2) / a.out_every + 1);
-    e.traj_row = emit ? a.y_out + r * ((size_t)a.p.B * 3 * a.p.N) : nullptr;
-    e.K1T = a.KT[0]; e.K2T = a.KT[1]; e.K3T = a.KT[2];
+    e.F0T = a.YT[n & 1] + 2 * pl; e.F1T = a.YT[j & 1] + 2 * pl;
+    if (a.ck.VA) {
+        e.V0T = a.ck.VA + 2 * pl * (size_t)n; e.A0T = e.V0T + pl;
+        e.V1T = a.ck.VA + 2 * pl * (size_t)j; e.A1T = e.V1T + pl;
+        e.K1T = a.ck.K + 3 * pl * (size_t)n; e.K2T = e.K1T + pl; e.K3T = e.K2T + pl;
+        e.traj_row = nullptr;
+        e.ysel_row = a.ck.y_sel + (size_t)j * a.p.B * a.ck.G; e.inv = a.ck.inv; e.G = a.ck.G;
+    } else {
+        e.V0T = a.YT[n & 1]; e.A0T = e.V0T + pl; e.V1T = a.YT[j & 1]; e.A1T = e.V1T + pl;
+        e.K1T = a.KT[0]; e.K2T = a.KT[1]; e.K3T = a.KT[2];
+        const bool emit = (j % a.out_every == 0) || (j == a.T - 1);
+        const size_t r = (j % a.out_every == 0) ? (size_t)(j / a.out_every) : (size_t)((a.T - 2) / a.out_every + 1);
+        e.traj_row = emit ? a.y_out + r * ((size_t)a.p.B * 3 * a.p.N) : nullptr;
+        e.ysel_row = nullptr; e.inv = nullptr; e.G = 0;
+    }
     for (int k = 0; k < 4; ++k) e.RsT[k] = a.RT[k];
     e.store_r = 1;
     e.Rhi_nxt = a.Rhi[(q + 1) & 1]; e.Rlo_nxt = a.Rlo[(q + 1) & 1];
@@ -60,12 +72,6 @@ ODECOL_DEVINL void persist_epilogue(const PersistArgs& a, int n, int q, int m_ti
     e.prepare();
     e.rows(m_tile, row, n0, nt, g, TNq, tot);
     e.tile_done(m_tile, n0, a.ts.TN, etid, kEpiWarps * 32);
-}
-
-template <int S>
-ODECOL_DEVINL void persist_pre_tile(const PersistArgs& a, int n, int q, int row, int nt, int g, int TNq) {
-    const FwdEpiT<S> e = persist_epi<S>(a, n, q);
-    e.pre_tile(row, nt, g, TNq);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -177,12 +183,6 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
                 const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
                 const int row = m_tile * BM + quarter * 32 + lane;
                 float tot[kMaxQ];
-                switch (s) {                       // warm L2 with the first groups' scratch while the contraction runs
-                    case 1: persist_pre_tile<1>(a, n, q, row, nt, g, TNq); break;
-                    case 2: persist_pre_tile<2>(a, n, q, row, nt, g, TNq); break;
-                    case 3: persist_pre_tile<3>(a, n, q, row, nt, g, TNq); break;
-                    default: persist_pre_tile<4>(a, n, q, row, nt, g, TNq); break;
-                }
                 mbar_wait(tfull, tphase);
                 tc_fence_after();
                 const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
@@ -232,7 +232,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
 int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
                           float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
                           float* const YT[2], float* const RT[4], unsigned int* done, int Np, int Bp, int KPa, int TN,
-                          cudaStream_t s) {
+                          const tc::CkptView* ck, cudaStream_t s) {
     using namespace tc;
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
@@ -244,11 +244,13 @@ int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const 
 
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, Np, KPa);
     extern void tc_launch_init(const DevProblem&, const TileGeom&, const float*, const float*, float*, float*, float*, float*,
-                               float*, float*, int, int, cudaStream_t);
-    tc_launch_init(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], RT[0], KPa, Bp, s);
+                               float*, float*, float*, float*, int, int, cudaStream_t);
+    const size_t pl = tg.plane();
+    float* V0 = ck ? ck->VA : YT[0];
+    tc_launch_init(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], V0, V0 + pl, YT[0] + 2 * pl, RT[0], KPa, Bp, s);
     count_launch(2);
     if (cudaMemsetAsync(done, 0, sizeof(unsigned int) * tsh.NT, s) != cudaSuccess) return ODECOL_E_CUDA;
-    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (!ck && cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi[2], mRlo[2];
     bool ok = make_map(&mWhi, Whi, Np, KPa, KPa, BM) && make_map(&mWlo, Wlo, Np, KPa, KPa, BM);
     for (int i = 0; i < 2; ++i)
@@ -261,6 +263,7 @@ int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const 
     for (int i = 0; i < 4; ++i) a.RT[i] = RT[i];
     for (int i = 0; i < 3; ++i) a.KT[i] = KT[i];
     a.done = done;
+    if (ck) a.ck = *ck; else a.ck = CkptView{nullptr, nullptr, nullptr, nullptr, 0};
     a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
     const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)TN * BK * 4) + 1024;
     if (cudaFuncSetAttribute(k_tc_rk4_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)

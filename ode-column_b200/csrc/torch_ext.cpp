@@ -118,6 +118,43 @@ std::vector<torch::Tensor> rk4_bwd(const Problem& pr, const torch::Tensor& t, co
     return {gy0, gW};
 }
 
+// checkpoint mode (include/odecol.h): bytes of the checkpoint buffer, 0 if the problem's kernel family has no such mode
+int64_t rk4_ckpt_bytes(const Problem& pr, int64_t T) { return (int64_t)odecol_rk4_ckpt_bytes(&pr.p, (int32_t)T); }
+
+std::vector<torch::Tensor> rk4_fwd_ckpt(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0,
+                                        const torch::Tensor& sel) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(t, "t"); want(sel, "sel", torch::kInt32);
+    const int64_t T = t.numel(), G = sel.numel();
+    const size_t cb = odecol_rk4_ckpt_bytes(&pr.p, (int32_t)T);
+    TORCH_CHECK(cb > 0, "odecol: checkpoint mode is not available for this problem");
+    auto y_sel = torch::empty({T, pr.B(), G}, pr.fopts());
+    auto ckpt = torch::empty({(int64_t)cb}, torch::TensorOptions().dtype(torch::kUInt8).device(pr.W_aug.device()));
+    auto ws = pr.workspace(ODECOL_OP_RK4_FWD, T);
+    check(odecol_rk4_fwd_ckpt(&pr.p, t.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), sel.data_ptr<int32_t>(), (int32_t)G,
+                              y_sel.data_ptr<float>(), ckpt.data_ptr(), cb, ws.data_ptr(), (size_t)ws.numel(), pr.stream()),
+          "rk4_fwd_ckpt");
+    return {y_sel, ckpt};
+}
+
+std::vector<torch::Tensor> rk4_bwd_ckpt(const Problem& pr, const torch::Tensor& t, const torch::Tensor& ckpt,
+                                        const torch::Tensor& grad_y, const torch::Tensor& sel) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    want(t, "t"); want(grad_y, "grad_y"); want(sel, "sel", torch::kInt32);
+    TORCH_CHECK(ckpt.is_cuda() && ckpt.is_contiguous() && ckpt.scalar_type() == torch::kUInt8, "odecol: bad checkpoint buffer");
+    const int64_t T = t.numel(), G = sel.numel();
+    TORCH_CHECK(grad_y.dim() == 3 && grad_y.size(0) == T && grad_y.size(1) == pr.B() && grad_y.size(2) == G,
+                "odecol: grad_y must be (T, B, G)");
+    auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
+    auto gW = torch::empty_like(pr.W_aug);
+    auto ws = pr.workspace(ODECOL_OP_RK4_BWD, T);
+    check(odecol_rk4_bwd_ckpt(&pr.p, t.data_ptr<float>(), (int32_t)T, ckpt.data_ptr(), (size_t)ckpt.numel(),
+                              grad_y.data_ptr<float>(), sel.data_ptr<int32_t>(), (int32_t)G, gy0.data_ptr<float>(),
+                              gW.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(), pr.stream()), "rk4_bwd_ckpt");
+    return {gy0, gW};
+}
+
 std::vector<torch::Tensor> dopri5_fwd(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0, double rtol,
                                       double atol, int64_t max_steps) {
     c10::cuda::CUDAGuard g(pr.W_aug.device());
@@ -293,6 +330,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rhs", &rhs);
     m.def("rk4_fwd", &rk4_fwd);
     m.def("rk4_bwd", &rk4_bwd);
+    m.def("rk4_ckpt_bytes", &rk4_ckpt_bytes);
+    m.def("rk4_fwd_ckpt", &rk4_fwd_ckpt);
+    m.def("rk4_bwd_ckpt", &rk4_bwd_ckpt);
     m.def("dopri5_fwd", &dopri5_fwd);
     m.def("dopri5_fwd_record", &dopri5_fwd_record);
     m.def("dopri5_bwd", &dopri5_bwd);

@@ -96,6 +96,32 @@ class _RK4Function(torch.autograd.Function):
         return gy0, gW, None, None, None
 
 
+def _ckpt_fits(nbytes: int, device) -> bool:
+    """Checkpoint mode trades memory for three contractions per reverse step; use it when the buffer fits in what the
+    device has free plus what the caching allocator already holds unused, with headroom for the loss graph."""
+    free, _total = torch.cuda.mem_get_info(device)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return nbytes <= 0.85 * (free + cached)
+
+
+class _RK4CkptFunction(torch.autograd.Function):
+    """rk4 on a component selection in checkpoint mode (include/odecol.h: odecol_rk4_fwd_ckpt / odecol_rk4_bwd_ckpt)."""
+
+    @staticmethod
+    def forward(ctx, y0, W_aug, setup: _Setup, sel_i32):
+        prob = setup.problem(W_aug)
+        y_sel, ckpt = setup.ext.rk4_fwd_ckpt(prob, setup.t, y0.detach().to(torch.float32).contiguous(), sel_i32)
+        ctx.setup, ctx.prob, ctx.sel_i32 = setup, prob, sel_i32
+        ctx.save_for_backward(ckpt)
+        return y_sel
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ckpt,) = ctx.saved_tensors
+        gy0, gW = ctx.setup.ext.rk4_bwd_ckpt(ctx.prob, ctx.setup.t, ckpt, grad.to(torch.float32).contiguous(), ctx.sel_i32)
+        return gy0, gW, None, None
+
+
 class _EMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, W_aug, setup: _Setup, dW, seed, trial_offset, dt, n_steps, sel_long, sel_i32, stats):
@@ -132,6 +158,14 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     if method == "rk4":
         if options.get("step_size") is not None:
             raise NotImplementedError("odecol rk4 integrates on the grid `t` (the reference passes no step_size)")
+        ckpt = options.get("checkpoint", "auto")      # 'auto' | True | False
+        needs_grad = torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad)
+        if sel_i32 is not None and needs_grad and ckpt is not False:
+            nbytes = setup.ext.rk4_ckpt_bytes(setup.problem(setup.lf.W_aug), setup.t.numel())
+            if nbytes > 0 and (ckpt is True or _ckpt_fits(nbytes, y0.device)):
+                return _RK4CkptFunction.apply(y0, setup.lf.W_aug, setup, sel_i32)
+            if ckpt is True:
+                raise RuntimeError("odecol: checkpoint mode is not available for this problem (tensor family only)")
         return _RK4Function.apply(y0, setup.lf.W_aug, setup, sel_long, sel_i32)
     if method == "dopri5":
         if torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad):
