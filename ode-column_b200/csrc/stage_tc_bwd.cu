@@ -15,14 +15,15 @@ namespace tc {
 // ---------------------------------------------------------------------------------------------------------------
 // The F component never feeds back into the dynamics, so its adjoint within a step is a fixed linear chain of lambda_F:
 // every stage re-derives its own kbar_F from lambda_F in registers (same expressions a stored version would use) and no
-// F plane of kbar / Ybar crosses a stage boundary.  Bytes per (population, trial): 48 / 56 / 64 / 60 for S = 4, 3, 2, 1.
+// F plane of kbar / Ybar crosses a stage boundary; kbar_V / kbar_A of stages 4, 3, 2 are re-derived the same way from
+// lambda and the stored Ybar.  Bytes per (population, trial): 32 / 40 / 56 / 52 for S = 4, 3, 2, 1.
 template <int S>
 struct BwdEpiT {
     DevProblem p;
     TileGeom tg;
     const float* t;
     int n, NPk, G;
-    float* acurT;          // [2 planes: V, A] kbar of this stage in, of the next reverse stage out
+    float* acurT;          // [2 planes: V, A] kbar of stage 1, written by stage 2 (the other stages re-derive theirs)
     float* lamT;           // [3 planes]
     float* b4T;            // [2 planes] Ybar_4, later Ybar_4 + Ybar_3 + Ybar_2
     float* b3T;            // [2 planes]
@@ -40,8 +41,9 @@ struct BwdEpiT {
 
     struct Group { float4 aV, aA, dr, lV, lA, lF, p4V, p4A, p3V, p3A, gv, ga, gf; };
     ODECOL_DEVINL void load_group(Group& L, size_t oq, size_t pl, int b0, int gV, int gA, int gF) const {
-        L.aV = ld4s(acurT + oq); L.aA = ld4s(acurT + pl + oq); L.dr = ld4s(DRT + oq);
+        L.dr = ld4s(DRT + oq);
         L.lV = ld4s(lamT + oq); L.lA = ld4s(lamT + pl + oq); L.lF = ld4s(lamT + 2 * pl + oq);
+        if (S == 1) { L.aV = ld4s(acurT + oq); L.aA = ld4s(acurT + pl + oq); }
         if (S <= 3) { L.p4V = ld4s(b4T + oq); L.p4A = ld4s(b4T + pl + oq); }
         if (S == 2) { L.p3V = ld4s(b3T + oq); L.p3A = ld4s(b3T + pl + oq); }
         if (S == 1) {                       // loss gradient of the selected components at grid point n
@@ -83,8 +85,18 @@ struct BwdEpiT {
             float nV[4], nA[4], sV[4], sA[4], sF[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float av = (&L.aV.x)[e], aa = (&L.aA.x)[e], d = (&L.dr.x)[e];
+                const float d = (&L.dr.x)[e];
                 const float lv = (&L.lV.x)[e], la = (&L.lA.x)[e], lf = (&L.lF.x)[e];
+                // kbar_V, kbar_A of this stage: the expression the previous reverse stage fed to its operand, re-derived
+                // from lambda and the stored Ybar (stage 1 reads what stage 2 stored: it only keeps the sum of Ybar)
+                float av, aa;
+                if (S == 4) { av = h8 * lv; aa = h8 * la; }
+                if (S == 3) { av = h38 * lv + dt * (&L.p4V.x)[e]; aa = h38 * la + dt * (&L.p4A.x)[e]; }
+                if (S == 2) {
+                    av = h38 * lv - dt * (&L.p4V.x)[e] + dt * (&L.p3V.x)[e];
+                    aa = h38 * la - dt * (&L.p4A.x)[e] + dt * (&L.p3A.x)[e];
+                }
+                if (S == 1) { av = (&L.aV.x)[e]; aa = (&L.aA.x)[e]; }
                 // kbar_F of this stage (and, at stage 1, the sum of the F slopes' adjoints) from lambda_F
                 const float bF4 = -(h8 * lf) * inv_ts;
                 float af = h8 * lf, bF3 = 0.f, bF2 = 0.f;
@@ -121,8 +133,10 @@ struct BwdEpiT {
             st4s(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
             st4s(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
             if (S == 1) st4s(lamT + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
-            st4s(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
-            st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
+            if (S == 2) {
+                st4s(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
+                st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
+            }
             const int b0 = bg + 4 * q;
             float* ah = AVhi_nxt + (size_t)b0 * NPk + j;
             float* al = AVlo_nxt + (size_t)b0 * NPk + j;
@@ -273,7 +287,6 @@ __global__ void k_tc_bwd_begin(DevProblem p, TileGeom tg, const float* __restric
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             st4(lamT + c * pl + o, make_float4(L[c][0], L[c][1], L[c][2], L[c][3]));
-            if (c < 2) st4(acurT + c * pl + o, make_float4(h8 * L[c][0], h8 * L[c][1], h8 * L[c][2], h8 * L[c][3]));
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
