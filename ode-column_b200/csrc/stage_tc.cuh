@@ -97,6 +97,12 @@ struct TileShape {
     unsigned long long* dbg; // optional per-CTA timeline stamps (globaltimer ns): [cta][8], diagnostics only
 };
 
+ODECOL_DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 ODECOL_DEVINL void st_global(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 ODECOL_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

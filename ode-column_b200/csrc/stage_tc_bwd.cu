@@ -155,6 +155,188 @@ struct BwdEpiT {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// The four reverse stages of one step (S = 4, 3, 2, 1) in ONE cooperative launch: same structure as the persistent
+// forward kernel (stage_tc_persist.cu).  Stage S reads operand slot S-1 of the current operand set and writes slot
+// S-2; stage 1 writes kbar_4 of the NEXT reverse step into slot 3 of the other set, so the dW contraction of this step
+// (which reads all four slots of the current set) can run after the chain.  A trial tile's next contraction waits on
+// a per-trial-tile counter of finished population-tile epilogues (cumulative over launches: `done_base`).
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdChainArgs {
+    DevProblem p;
+    TileGeom tg;
+    TileShape ts;              // MT, NT, TN, KB = NPk / BK
+    const float* t;
+    int n, NPk, G, Bp;
+    float* acurT; float* lamT; float* b4T; float* b3T;
+    const float* DRT[4];
+    float* AVhi; float* AVlo;  // [2 sets][4 slots][Bp][NPk]
+    int set;                   // operand set of this step
+    const float* grad_y; const int* inv;
+    float gamma, inv_tm, inv_ta, inv_ts;
+    unsigned int* done; unsigned int done_base;
+};
+
+template <int S>
+ODECOL_DEVINL void chain_epilogue(const BwdChainArgs& a, int m_tile, int row, int n0, int nt, int g, int TNq,
+                                  const float (&tot)[kMaxQ]) {
+    BwdEpiT<S> e;
+    e.p = a.p; e.tg = a.tg; e.t = a.t; e.n = a.n; e.NPk = a.NPk; e.G = a.G;
+    e.acurT = a.acurT; e.lamT = a.lamT; e.b4T = a.b4T; e.b3T = a.b3T; e.DRT = a.DRT[S - 1];
+    const size_t astride = (size_t)a.Bp * a.NPk;
+    const size_t nxt = S == 1 ? (size_t)((a.set ^ 1) * 4 + 3) : (size_t)(a.set * 4 + S - 2);
+    e.AVhi_nxt = a.AVhi + nxt * astride; e.AVlo_nxt = a.AVlo + nxt * astride;
+    e.grad_y = a.grad_y; e.inv = a.inv; e.gamma = a.gamma;
+    e.inv_tm = a.inv_tm; e.inv_ta = a.inv_ta; e.inv_ts = a.inv_ts;
+    e.prepare();
+    e.rows(m_tile, row, n0, nt, g, TNq, tot);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant__ CUtensorMap mW_lo,
+               const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo, BwdChainArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+    __shared__ uint32_t tmem_base_slot;
+    const TileShape ts = a.ts;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)ts.TN * BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * STAGES]), tempty = smem_u32(&bars[2 * STAGES + 1]);
+    const int tiles = ts.MT * ts.NT;
+    const uint32_t acc_stride = (uint32_t)ts.TN;
+    uint32_t ncols = 32;
+    while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int q = 0; q < 4; ++q) {                       // q = 0..3  <->  S = 4..1, operand slot 3 - q
+                const int row0 = (a.set * 4 + 3 - q) * a.Bp;
+                for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                    const int nt = tile / ts.MT, m0 = (tile % ts.MT) * BM, n0 = nt * ts.TN;
+                    const unsigned int need = a.done_base + (unsigned int)ts.MT * (unsigned int)q;
+                    uint32_t spins = 0;
+                    while ((int)(ld_acquire_u32(a.done + nt) - need) < 0) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 26)) __trap();
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    for (int kb = 0; kb < ts.KB; ++kb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, stage_bytes);
+                        tma_load_2d(base, &mW_hi, fb, kb * BK, m0);
+                        tma_load_2d(base + a_bytes, &mW_lo, fb, kb * BK, m0);
+                        tma_load_2d(base + 2 * a_bytes, &mA_hi, fb, kb * BK, n0 + row0);
+                        tma_load_2d(base + 2 * a_bytes + b_bytes, &mA_lo, fb, kb * BK, n0 + row0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(ts.TN);
+            const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int q = 0; q < 4; ++q) {
+                for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                    mbar_wait(tempty, tphase ^ 1);
+                    tc_fence_after();
+                    int j = 0;
+                    for (int kb = 0; kb < ts.KB; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t base = ring + stage * stage_bytes;
+                        const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
+                        const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k, ++j) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                            umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                        }
+                        umma_commit(empty0 + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(tfull);
+                    tphase ^= 1;
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int g = ew >> 2;
+        const int etid = ew * 32 + lane;
+        const int TNq = ts.TN >> 2;
+        uint32_t tphase = 0;
+        for (int q = 0; q < 4; ++q) {
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
+                const int row = m_tile * BM + quarter * 32 + lane;
+                float tot[kMaxQ];
+                mbar_wait(tfull, tphase);
+                tc_fence_after();
+                const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
+#pragma unroll
+                for (int qq = 0; qq < kMaxQ / 4; ++qq) {
+                    if (4 * qq < TNq) {
+                        uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                        for (int c = 0; c <= kMainAcc; ++c) tmem_ld4_issue(lane_base + c * acc_stride + 4 * qq, u[c]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float sum = __uint_as_float(u[kMainAcc][e]);
+#pragma unroll
+                            for (int c = 0; c < kMainAcc; ++c) sum += __uint_as_float(u[c][e]);
+                            tot[4 * qq + e] = sum;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
+                tphase ^= 1;
+                switch (q) {
+                    case 0: chain_epilogue<4>(a, m_tile, row, n0, nt, g, TNq, tot); break;
+                    case 1: chain_epilogue<3>(a, m_tile, row, n0, nt, g, TNq, tot); break;
+                    case 2: chain_epilogue<2>(a, m_tile, row, n0, nt, g, TNq, tot); break;
+                    default: chain_epilogue<1>(a, m_tile, row, n0, nt, g, TNq, tot); break;
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+                if (etid == 0) atomicAdd(a.done + nt, 1u);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // per-step operand setup: y_traj[n] (API layout) -> tile-major Y0T, r / phi' of stage 1, split operand with stimulus
 // One CTA per group of four trials (one float4 of the tile-major layout), threads over populations.
 // ---------------------------------------------------------------------------------------------------------------
@@ -474,7 +656,7 @@ __global__ void k_split_pad_T(const float* __restrict__ src, int n, int ld, floa
 struct TcBwdLayout {
     int Np, Bp, KPa, NPk, TN;
     size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo;   // stacked x4 operand buffers
-    size_t off_K[3], off_Y, off_RT[3], off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, total;
+    size_t off_K[3], off_Y, off_RT[3], off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, off_done, total;
 };
 
 static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
@@ -489,7 +671,7 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
     L.off_WThi = take(4ull * L.Np * L.NPk); L.off_WTlo = take(4ull * L.Np * L.NPk);
     L.off_Rhi = take(16ull * L.Bp * L.KPa); L.off_Rlo = take(16ull * L.Bp * L.KPa);
-    L.off_AVhi = take(16ull * L.Bp * L.NPk); L.off_AVlo = take(16ull * L.Bp * L.NPk);
+    L.off_AVhi = take(32ull * L.Bp * L.NPk); L.off_AVlo = take(32ull * L.Bp * L.NPk);     // two sets of four slots
     const size_t plane = 4ull * L.Np * L.Bp;
     for (int i = 0; i < 3; ++i) L.off_K[i] = take(plane);
     L.off_Y = take(3 * plane);
@@ -497,6 +679,7 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     for (int i = 0; i < 4; ++i) L.off_DRT[i] = take(plane);
     L.off_lam = take(3 * plane); L.off_b4 = take(2 * plane); L.off_b3 = take(2 * plane); L.off_acur = take(2 * plane);
     L.off_inv = take(sizeof(int) * 3ull * p.N);
+    L.off_done = take(sizeof(unsigned int) * (size_t)(L.Bp / L.TN) + 256);
     L.total = o;
     return L;
 }
@@ -569,17 +752,22 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     k_split_pad_T<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, WThi, WTlo, L.Np, L.NPk);
     k_tc_set_one<<<(4 * p.B + 255) / 256, 256, 0, s>>>(Rhi, L.Bp, p.B, L.KPa, Kaug - 1);
     k_tc_build_inv<<<1, 256, 0, s>>>(sel, G, 3 * p.N, inv);
-    k_tc_bwd_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, grad_y, inv, G, t_dev, T, gamma, lamT, acurT, AVhi + 3 * astride,
-                                           AVlo + 3 * astride, L.NPk);
+    const size_t first = (size_t)(((T - 2) & 1) * 4 + 3);       // operand sets alternate per step: step n uses set n & 1
+    k_tc_bwd_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, grad_y, inv, G, t_dev, T, gamma, lamT, acurT, AVhi + first * astride,
+                                           AVlo + first * astride, L.NPk);
+    unsigned int* done = reinterpret_cast<unsigned int*>(w + L.off_done);
+    if (cudaMemsetAsync(done, 0, sizeof(unsigned int) * (size_t)(L.Bp / L.TN), s) != cudaSuccess) return ODECOL_E_CUDA;
     count_launch(5);
 
-    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo, dAhi, dAlo, dBhi, dBlo;
+    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo, dAhi[2], dAlo[2], dBhi, dBlo;
     bool ok = make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) && make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) &&
               make_map(&mWThi, WThi, L.Np, L.NPk, L.NPk, BM) && make_map(&mWTlo, WTlo, L.Np, L.NPk, L.NPk, BM) &&
               make_map(&mRhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, L.TN) &&
-              make_map(&mAVhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, L.TN) && make_map(&mAVlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, L.TN) &&
-              make_map(&dAhi, AVhi, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-              make_map(&dAlo, AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&mAVhi, AVhi, 8ull * L.Bp, L.NPk, L.NPk, L.TN) && make_map(&mAVlo, AVlo, 8ull * L.Bp, L.NPk, L.NPk, L.TN) &&
+              make_map(&dAhi[0], AVhi, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dAlo[0], AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dAhi[1], AVhi + 4 * astride, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dAlo[1], AVlo + 4 * astride, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
               make_map(&dBhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
               make_map(&dBlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (!ok) return ODECOL_E_CUDA;
@@ -603,6 +791,17 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     }
 
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
+    // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
+    const char* pe = getenv("ODECOL_PERSISTENT");
+    bool use_chain = pe ? atoi(pe) != 0 : true;
+    const size_t chain_smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)L.TN * BK * 4) + 1024;
+    int chain_grid = MT * NT < num_sms() ? MT * NT : num_sms();
+    if (use_chain) {
+        int max_blocks = 0;
+        if (cudaFuncSetAttribute(k_tc_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_tc_bwd_chain, kThreads, chain_smem) != cudaSuccess || max_blocks < 1)
+            use_chain = false;
+    }
     for (int n = T - 2; n >= 0; --n) {
         int rc = ODECOL_OK;
         if (ckVA) {
@@ -630,22 +829,38 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         { FwdEpiT<2> e; fill_f(e, 2); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         { FwdEpiT<3> e; fill_f(e, 3); rc = launch_contract(mWhi, mWlo, mRhi, mRlo, TileShape{MT, NT, L.TN, L.KPa / BK, 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         }
-        // reverse stages 4, 3, 2, then dW, then stage 1 (which overwrites the stage-4 operand for the next step)
-        auto fill_b = [&](auto& e, int S) {
-            e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
-            e.acurT = acurT; e.lamT = lamT; e.b4T = b4T; e.b3T = b3T; e.DRT = DRT[S - 1];
-            const int nxt = S == 1 ? 3 : S - 2;                 // operand buffer the epilogue writes
-            e.AVhi_nxt = AVhi + nxt * astride; e.AVlo_nxt = AVlo + nxt * astride;
-            e.grad_y = grad_y; e.inv = inv; e.gamma = gamma;
-            e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
-            e.dt = e.h8p = 0.f;
-        };
-        { BwdEpiT<4> e; fill_b(e, 4); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 3 * L.Bp, nullptr}, e, s); if (rc) return rc; }
-        { BwdEpiT<3> e; fill_b(e, 3); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
-        { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
-        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi, dAlo, dBhi, dBlo, ds);
+        // reverse stages 4, 3, 2, 1 (stage 1 writes kbar_4 of the next step into the OTHER operand set), then dW
+        const int set = n & 1;
+        if (use_chain) {
+            BwdChainArgs a;
+            a.p = p; a.tg = tg; a.ts = TileShape{MT, NT, L.TN, L.NPk / BK, 0, nullptr}; a.t = t_dev; a.n = n; a.NPk = L.NPk; a.G = G;
+            a.Bp = L.Bp; a.acurT = acurT; a.lamT = lamT; a.b4T = b4T; a.b3T = b3T;
+            for (int k = 0; k < 4; ++k) a.DRT[k] = DRT[k];
+            a.AVhi = AVhi; a.AVlo = AVlo; a.set = set; a.grad_y = grad_y; a.inv = inv; a.gamma = gamma;
+            a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
+            a.done = done; a.done_base = (unsigned int)MT * 4u * (unsigned int)(T - 2 - n);
+            void* args[] = {&mWThi, &mWTlo, &mAVhi, &mAVlo, &a};
+            if (cudaLaunchCooperativeKernel((const void*)k_tc_bwd_chain, dim3(chain_grid), dim3(kThreads), args, chain_smem, s) != cudaSuccess)
+                return ODECOL_E_CUDA;
+            count_launch();
+        } else {
+            auto fill_b = [&](auto& e, int S) {
+                e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
+                e.acurT = acurT; e.lamT = lamT; e.b4T = b4T; e.b3T = b3T; e.DRT = DRT[S - 1];
+                const size_t nxt = S == 1 ? (size_t)((set ^ 1) * 4 + 3) : (size_t)(set * 4 + S - 2);   // slot the epilogue writes
+                e.AVhi_nxt = AVhi + nxt * astride; e.AVlo_nxt = AVlo + nxt * astride;
+                e.grad_y = grad_y; e.inv = inv; e.gamma = gamma;
+                e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+                e.dt = e.h8p = 0.f;
+            };
+            const int r0 = set * 4 * L.Bp;
+            { BwdEpiT<4> e; fill_b(e, 4); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 3 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+            { BwdEpiT<3> e; fill_b(e, 3); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 2 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+            { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+            { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
+        }
+        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi, dBlo, ds);
         count_launch();
-        { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
     }
     if (grad_y0) {
         k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);

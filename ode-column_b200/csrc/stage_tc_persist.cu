@@ -30,12 +30,6 @@ struct PersistArgs {
     float inv_tm, inv_ta, inv_ts;
 };
 
-ODECOL_DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 template <int S>
 ODECOL_DEVINL FwdEpiT<S> persist_epi(const PersistArgs& a, int n, int q) {
     FwdEpiT<S> e;
