@@ -71,7 +71,9 @@ enum {
     ODECOL_OP_RK4_BWD = 2,
     ODECOL_OP_DOPRI5_FWD = 3,
     ODECOL_OP_EM_FWD = 4,
-    ODECOL_OP_EM_BWD = 5
+    ODECOL_OP_EM_BWD = 5,
+    ODECOL_OP_SRK_FWD = 6,
+    ODECOL_OP_SRK_BWD = 7
 };
 
 /* The column network in linear form plus the stimulus of every trial.
@@ -204,6 +206,30 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
                   const float* grad_y, const int32_t* sel, int32_t G, float dt,
                   float* grad_y0, float* grad_W_aug,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* torchsde's method='srk' for scalar noise, fixed step: Roessler's SRI2 scheme ("SRID2" tableau, strong order 1.5) in
+ * the same integrate loop as odecol_em_fwd.  Replaces
+ *   torchsde.sdeint(sde, y0, ts, names={'drift':'forward','diffusion':'diffusion'}, method='srk')
+ * the call every committed SDE solve of the reference makes (scripts/wta_ode.py:174,200;
+ * scripts/plotting_results.py:391,506,594).  Per step the scheme consumes the Brownian increment W and the space-time
+ * Levy area U = int_{t0}^{t1} (W_r - W_{t0}) dr (torchsde: bm(t0, t1, return_U=True)):
+ *   dW, dU   (n_steps, B) host-supplied, both or neither (n_steps = odecol_em_num_steps()); NULL: in-kernel
+ *            Philox4x32-10, U | W ~ N(h W / 2, h^3 / 12); the W stream is the one odecol_em_fwd draws (fixed step)
+ *   status   per trial, may be NULL: ODECOL_ST_NONFINITE if the final state is not finite
+ *   y_steps  optional (n_steps+1, B, 3N): every solver state (needed by odecol_srk_bwd)
+ * Persistent on-chip family only (N <= 128: the reference's networks); larger problems: ODECOL_E_UNSUPPORTED. */
+int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out,
+                   const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, float dt,
+                   int32_t* status, float* y_steps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Discrete adjoint of odecol_srk_fwd -- what loss.backward() through torchsde's unrolled srk steps computes (reference
+ * scripts/wta_ode.py:174-181).  The noise is additive, but U enters the third drift stage, so the sweep needs the same
+ * (dW, dU) tables or the same (seed, trial_offset) as the forward call.  Workspace:
+ * odecol_workspace_bytes(p, ODECOL_OP_SRK_BWD, T, n_steps); grad_y / sel / G / grad_y0 / grad_W_aug as odecol_rk4_bwd. */
+int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
+                   const float* dW, const float* dU, uint64_t seed, int64_t trial_offset,
+                   const float* grad_y, const int32_t* sel, int32_t G, float dt,
+                   float* grad_y0, float* grad_W_aug, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in
  * tensor memory), C[n][m] = sum_k A[m][k] * B[n][k] for row-major A (M x K), B (N x K), C (N x M).  Lets the tests pin

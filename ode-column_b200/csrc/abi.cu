@@ -87,6 +87,8 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
         case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
+        case ODECOL_OP_SRK_FWD: return 0;
+        case ODECOL_OP_SRK_BWD: return em_schedule_layout(T, n_steps).total;
         default: return 0;
     }
 }
@@ -284,6 +286,48 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     int r2 = launch_em_schedule(ts, T, dt, step_of, wts, tk, s);
     if (r2) return r2;
     return launch_em_bwd_small(d, ts, T, y_steps, grad_y, sel, G, grad_y0, grad_W_aug, step_of, wts, tk, s);
+}
+
+int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out, const float* dW,
+                   const float* dU, uint64_t seed, int64_t trial_offset, float dt, int32_t* status, float* y_steps,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
+    if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
+    if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_srk_fwd_small(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
+                   const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, const float* grad_y,
+                   const int32_t* sel, int32_t G, float dt, float* grad_y0, float* grad_W_aug, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
+    if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
+    if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;
+    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    const EmScheduleLayout L = em_schedule_layout(T, n_steps);
+    if (!workspace || workspace_bytes < L.total) return ODECOL_E_WORKSPACE;
+    g_launches.store(0, std::memory_order_relaxed);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    int* step_of = reinterpret_cast<int*>(w + L.off_step);
+    float* wts = reinterpret_cast<float*>(w + L.off_w);
+    float* tk = reinterpret_cast<float*>(w + L.off_tk);
+    if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+    const int r2 = launch_em_schedule(ts, T, dt, step_of, wts, tk, s);
+    if (r2) return r2;
+    return launch_srk_bwd_small(d, T, y_steps, dW, dU, seed, trial_offset, grad_y, sel, G, grad_y0, grad_W_aug, step_of,
+                                wts, tk, s);
 }
 
 size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K) {

@@ -59,6 +59,12 @@ int launch_em_schedule(const float* ts, int T, float dt, int* step_of, float* w,
 int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float* y_steps, const float* grad_y,
                         const int* sel, int G, float* grad_y0, float* grad_W, const int* step_of, const float* w,
                         const float* tk, cudaStream_t s);
+int launch_srk_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
+                         const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps,
+                         cudaStream_t s);
+int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const float* dW, const float* dU, uint64_t seed,
+                         int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
+                         const int* step_of, const float* w, const float* tk, cudaStream_t s);
 
 // ---- family L (stage_kernels.cu): state in global memory, one fused contraction + epilogue per RK stage ------
 struct StageWorkspace;   // carved from the caller's workspace

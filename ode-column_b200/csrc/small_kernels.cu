@@ -983,4 +983,229 @@ int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// torchsde method='srk' for scalar noise: Roessler's SRI2 ("SRID2" tableau), fixed step, in torchsde's integrate loop.
+// What every committed sdeint call of the reference names (scripts/wta_ode.py:174,200; plotting_results.py:391,506,594).
+// The diffusion of the column networks is state independent (src/coupled_columns.py:239-249, 444-454, 790-800), so the
+// H1 stage values (which only feed g) are never needed and g_prod = sigma * g_weight; the drift sees the space-time
+// Levy area U through the third stage.  Every float32 operation of diagonal_or_scalar_step is replayed in its order.
+// The fourth stage has alpha = 0 and H0 = y0: its drift contributes an exact zero and is not evaluated.
+// ---------------------------------------------------------------------------------------------------------------
+struct Srid2 {
+    static constexpr float quarter = 0.25f, half = 0.5f;
+    static constexpr float a0 = (float)(1.0 / 6), a1 = (float)(1.0 / 6), a2 = (float)(2.0 / 3);
+};
+
+// (W, U) of step k for one trial: host tables or Philox (U | W ~ N(h W / 2, h^3 / 12)).  The W deviate is the one the
+// fixed-step Euler-Maruyama kernel draws for the same (seed, trial, step), so both methods see the same path.
+ODECOL_DEVINL void srk_increments(const float* __restrict__ dWs, const float* __restrict__ dUs, const Philox& px,
+                                  unsigned long long trial, long long k, int B, int b, float h, float& dw, float& du) {
+    if (dWs) {
+        dw = __ldg(dWs + (size_t)k * B + b);
+        du = __ldg(dUs + (size_t)k * B + b);
+    } else {
+        const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)k, 0x80000000u | (uint32_t)(k >> 32));
+        dw = sqrtf(h) * normal_from_bits(bits.x, bits.y);
+        du = 0.5f * h * dw + sqrtf(h * h * h * (1.0f / 12.0f)) * normal_from_bits(bits.z, bits.w);
+    }
+}
+
+// g_weight of the four stages (thread-uniform scalars)
+ODECOL_DEVINL void srk_g_weights(float h, float dw, float du, float gw[4]) {
+    const float rdt = __fdiv_rn(1.0f, h), sq = __fsqrt_rn(h);
+    const float i_kk = __fmul_rn(__fsub_rn(__fmul_rn(dw, dw), h), 0.5f);
+    const float i_kkk = __fdiv_rn(__fsub_rn(__fmul_rn(__fmul_rn(dw, dw), dw), __fmul_rn(__fmul_rn(3.0f, h), dw)), 6.0f);
+    // beta rows as float32 (torch multiplies a float32 tensor by the Python scalar cast to float32)
+    constexpr float b1[4] = {-1.f, (float)(4.0 / 3), (float)(2.0 / 3), 0.f};
+    constexpr float b2[4] = {1.f, (float)(-4.0 / 3), (float)(1.0 / 3), 0.f};
+    constexpr float b3[4] = {2.f, (float)(-4.0 / 3), (float)(-2.0 / 3), 0.f};
+    constexpr float b4[4] = {-2.f, (float)(5.0 / 3), (float)(-2.0 / 3), 1.f};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float w = __fadd_rn(__fmul_rn(b1[s], dw), __fdiv_rn(__fmul_rn(b2[s], i_kk), sq));
+        w = __fadd_rn(w, __fmul_rn(__fmul_rn(b3[s], du), rdt));
+        gw[s] = __fadd_rn(w, __fmul_rn(__fmul_rn(b4[s], i_kkk), rdt));
+    }
+}
+
+// H0 of stage 3 for one state component: y + (1/4 f0) h + ((1 g) U) / h + (1/4 f1) h + ((1/2 g) U) / h
+ODECOL_DEVINL float srk_h2(float y, float f0, float f1, float g, float h, float du, float rdt) {
+    float v = __fadd_rn(y, __fmul_rn(__fmul_rn(Srid2::quarter, f0), h));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(g, du), rdt));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::quarter, f1), h));
+    return __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(Srid2::half, g), du), rdt));
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) k_srk_fwd_small(DevProblem p, const float* __restrict__ ts, int T,
+                                                       const float* __restrict__ y0, float* __restrict__ y_out,
+                                                       const float* __restrict__ dWs, const float* __restrict__ dUs,
+                                                       unsigned long long seed, long long trial_offset, float dt0,
+                                                       int* __restrict__ status, float* __restrict__ y_steps) {
+    __shared__ __align__(16) float ra[2 * KP];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    RowRhs<KP> f;
+    f.init(p, ra, b);
+    const size_t row = (size_t)3 * N;
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    float sg[3] = {0.f, 0.f, 0.f};
+    float y[3] = {0.f, 0.f, 0.f};
+    if (f.act) {
+        const Y3 s = ld3(y0 + b * row, N, i);
+        y[0] = s.V; y[1] = s.A; y[2] = s.F;
+        st3(y_out + b * row, N, i, y[0], y[1], y[2]);
+        if (y_steps) st3(y_steps + b * row, N, i, y[0], y[1], y[2]);
+        if (p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+    }
+    const float t_end = __ldg(ts + T - 1);
+    float curr_t = __ldg(ts), prev_t = curr_t;
+    float py[3] = {y[0], y[1], y[2]};
+    long long kstep = 0;
+    for (int j = 1; j < T; ++j) {
+        const float out_t = __ldg(ts + j);
+        while (curr_t < out_t) {
+            const float next_t = fminf(__fadd_rn(curr_t, dt0), t_end);
+            const float h = __fsub_rn(next_t, curr_t), rdt = __fdiv_rn(1.0f, h);
+            float dw, du, gw[4];
+            srk_increments(dWs, dUs, px, trial, kstep, B, b, h, dw, du);
+            srk_g_weights(h, dw, du, gw);
+            float f0[3], f1[3], f2[3], H[3];
+            f.eval(curr_t, y[0], y[1], y[2], f0[0], f0[1], f0[2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[c] = __fadd_rn(y[c], __fmul_rn(f0[c], h));
+            f.eval(__fadd_rn(curr_t, h), H[0], H[1], H[2], f1[0], f1[1], f1[2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[c] = srk_h2(y[c], f0[c], f1[c], sg[c], h, du, rdt);
+            f.eval(__fadd_rn(curr_t, __fmul_rn(Srid2::half, h)), H[0], H[1], H[2], f2[0], f2[1], f2[2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                py[c] = y[c];
+                float v = __fadd_rn(__fadd_rn(y[c], __fmul_rn(__fmul_rn(Srid2::a0, f0[c]), h)), __fmul_rn(sg[c], gw[0]));
+                v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a1, f1[c]), h)), __fmul_rn(sg[c], gw[1]));
+                v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a2, f2[c]), h)), __fmul_rn(sg[c], gw[2]));
+                y[c] = __fadd_rn(v, __fmul_rn(sg[c], gw[3]));
+            }
+            prev_t = curr_t; curr_t = next_t;
+            ++kstep;
+            if (y_steps && f.act) st3(y_steps + ((size_t)kstep * B + b) * row, N, i, y[0], y[1], y[2]);
+        }
+        if (f.act) {
+            const float spn = __fsub_rn(curr_t, prev_t);
+            const float w0 = __fdiv_rn(__fsub_rn(curr_t, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, prev_t), spn);
+            st3(y_out + ((size_t)j * B + b) * row, N, i,
+                __fadd_rn(__fmul_rn(w0, py[0]), __fmul_rn(w1, y[0])),
+                __fadd_rn(__fmul_rn(w0, py[1]), __fmul_rn(w1, y[1])),
+                __fadd_rn(__fmul_rn(w0, py[2]), __fmul_rn(w1, y[2])));
+        }
+    }
+    const bool bad = block_any(f.act && !(isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2])));
+    if (i == 0 && status) status[b] = bad ? ODECOL_ST_NONFINITE : ODECOL_ST_OK;
+}
+
+// Discrete adjoint of the fixed-step SRI2 solve.  With additive noise the step is
+//   H1 = y + h f0,  H2 = y + h/4 (f0 + f1) + 3/2 sigma U / h,  y1 = y + h (f0/6 + f1/6 + 2/3 f2) + sigma sum(g_weight)
+// so the Brownian inputs enter the Jacobians only through H2: the reverse sweep recomputes the three stages from the
+// saved solver states and the same (W, U) (host tables or the same Philox stream) and pushes the adjoint through them.
+// Replaces loss.backward() through torchsde's unrolled srk steps (reference scripts/wta_ode.py:174-181).
+template <int KP>
+__global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, const float* __restrict__ y_steps,
+                                                       const float* __restrict__ dWs, const float* __restrict__ dUs,
+                                                       unsigned long long seed, long long trial_offset,
+                                                       const float* __restrict__ grad_y, const int* __restrict__ sel,
+                                                       int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
+                                                       const int* __restrict__ step_of, const float* __restrict__ w,
+                                                       const float* __restrict__ tk) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    BwdCtx<KP> cx;
+    cx.init(p, sm, b);
+    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    __syncthreads();
+    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    __syncthreads();
+    int gi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gi[c] = cx.act ? cx.s.inv[c * N + i] : -1;
+    const size_t row = (size_t)3 * N;
+    const int nsteps = step_of[T];
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    float sg[3] = {0.f, 0.f, 0.f};
+    if (cx.act && p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+    auto gcomp = [&](int j, int c) -> float { return gi[c] >= 0 ? grad_y[((size_t)j * B + b) * G + gi[c]] : 0.f; };
+    float lam[3] = {0.f, 0.f, 0.f};      // adjoint of solver state k+1 while processing step k
+    float pend[3] = {0.f, 0.f, 0.f};     // contributions destined for state k (from interpolated outputs)
+    int j = T - 1;
+    for (int k = nsteps - 1; k >= 0; --k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { lam[c] += pend[c]; pend[c] = 0.f; }
+        while (j >= 1 && step_of[j] == k + 1) {
+            const float w0 = w[2 * j], w1 = w[2 * j + 1];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float g = gcomp(j, c); lam[c] += w1 * g; pend[c] += w0 * g; }
+            --j;
+        }
+        const float t0 = tk[k], h = __fsub_rn(tk[k + 1], tk[k]), rdt = __fdiv_rn(1.0f, h);
+        float dw, du;
+        srk_increments(dWs, dUs, px, trial, (long long)k, B, b, h, dw, du);
+        float y[3] = {0.f, 0.f, 0.f};
+        if (cx.act) { const Y3 q = ld3(y_steps + ((size_t)k * B + b) * row, N, i); y[0] = q.V; y[1] = q.A; y[2] = q.F; }
+        // ---- recompute the stages (same arithmetic as the forward kernel)
+        float r, d0, d1, d2, tot, f0[3], f1[3], H[3];
+        tot = cx.stage_fwd(0, t0, y[0], y[1], r, d0, true);
+        drift(cx.c, y[0], y[1], y[2], r, cx.kappa, tot, f0[0], f0[1], f0[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[c] = __fadd_rn(y[c], __fmul_rn(f0[c], h));
+        tot = cx.stage_fwd(1, __fadd_rn(t0, h), H[0], H[1], r, d1, true);
+        drift(cx.c, H[0], H[1], H[2], r, cx.kappa, tot, f1[0], f1[1], f1[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[c] = srk_h2(y[c], f0[c], f1[c], sg[c], h, du, rdt);
+        (void)cx.stage_fwd(2, __fadd_rn(t0, __fmul_rn(Srid2::half, h)), H[0], H[1], r, d2, false);
+        // ---- reverse
+        const float h23 = h * Srid2::a2, h6 = h * Srid2::a0, h4 = h * 0.25f;
+        float Y2[3], Y1[3], Y0[3];
+        cx.stage_bwd(2, d2, h23 * lam[0], h23 * lam[1], h23 * lam[2], Y2[0], Y2[1], Y2[2]);
+        cx.stage_bwd(1, d1, h6 * lam[0] + h4 * Y2[0], h6 * lam[1] + h4 * Y2[1], h6 * lam[2] + h4 * Y2[2], Y1[0], Y1[1], Y1[2]);
+        cx.stage_bwd(0, d0, h6 * lam[0] + h4 * Y2[0] + h * Y1[0], h6 * lam[1] + h4 * Y2[1] + h * Y1[1],
+                     h6 * lam[2] + h4 * Y2[2] + h * Y1[2], Y0[0], Y0[1], Y0[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lam[c] += Y2[c] + Y1[c] + Y0[c];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lam[c] += pend[c];
+    if (j >= 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lam[c] += gcomp(0, c);      // output 0 is y0 itself
+    }
+    if (grad_y0 && cx.act) st3(grad_y0 + b * row, N, i, lam[0], lam[1], lam[2]);
+    cx.flush_dw(p, grad_W);
+}
+
+int launch_srk_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
+                         const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps,
+                         cudaStream_t s) {
+    const int kp = small_kp(p);
+    ODECOL_KP_SWITCH(kp, (k_srk_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(
+                             p, ts, T, y0, y_out, dW, dU, (unsigned long long)seed, (long long)trial_offset, dt, status, y_steps)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const float* dW, const float* dU, uint64_t seed,
+                         int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
+                         const int* step_of, const float* w, const float* tk, cudaStream_t s) {
+    const int kp = small_kp(p);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    ODECOL_KP_SWITCH(kp, {
+        cudaFuncSetAttribute(k_srk_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_srk_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, y_steps, dW, dU, (unsigned long long)seed,
+                                                                 (long long)trial_offset, grad_y, sel, G, grad_y0, grad_W,
+                                                                 step_of, w, tk);
+    });
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 }  // namespace odecol

@@ -283,6 +283,67 @@ std::vector<torch::Tensor> em_bwd(const Problem& pr, const torch::Tensor& ts, co
     return {gy0, gW};
 }
 
+// (dW, dU) tables of the srk entry points: both or neither
+static void srk_tables(const Problem& pr, const std::optional<torch::Tensor>& dW, const std::optional<torch::Tensor>& dU,
+                       const float*& dWp, const float*& dUp) {
+    dWp = dUp = nullptr;
+    TORCH_CHECK(dW.has_value() == dU.has_value(), "odecol: srk wants both dW and dU, or neither (Philox)");
+    if (!dW.has_value()) return;
+    want(*dW, "dW"); want(*dU, "dU");
+    TORCH_CHECK(dW->dim() == 2 && dW->size(1) == pr.B() && dU->sizes() == dW->sizes(), "odecol: dW and dU must be (n_steps, B)");
+    dWp = dW->data_ptr<float>();
+    dUp = dU->data_ptr<float>();
+}
+
+std::vector<torch::Tensor> srk_fwd(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y0,
+                                   std::optional<torch::Tensor> dW, std::optional<torch::Tensor> dU, int64_t seed,
+                                   int64_t trial_offset, double dt, int64_t save_steps) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(ts, "ts");
+    const int64_t T = ts.numel();
+    const float *dWp, *dUp;
+    srk_tables(pr, dW, dU, dWp, dUp);
+    auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto st = torch::zeros({pr.B()}, pr.iopts());
+    torch::Tensor ysteps = save_steps > 0 ? torch::empty({save_steps + 1, pr.B(), 3 * pr.N()}, pr.fopts()) : torch::empty({0}, pr.fopts());
+    check(odecol_srk_fwd(&pr.p, ts.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), dWp, dUp,
+                         (uint64_t)seed, trial_offset, (float)dt, st.data_ptr<int32_t>(),
+                         save_steps > 0 ? ysteps.data_ptr<float>() : nullptr, nullptr, 0, pr.stream()), "srk_fwd");
+    return {y, st, ysteps};
+}
+
+std::vector<torch::Tensor> srk_bwd(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y_steps,
+                                   std::optional<torch::Tensor> dW, std::optional<torch::Tensor> dU, int64_t seed,
+                                   int64_t trial_offset, const torch::Tensor& grad_y, std::optional<torch::Tensor> sel,
+                                   double dt) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    want(ts, "ts"); want(y_steps, "y_steps"); want(grad_y, "grad_y");
+    const int64_t T = ts.numel();
+    TORCH_CHECK(y_steps.dim() == 3 && y_steps.size(1) == pr.B() && y_steps.size(2) == 3 * pr.N(), "odecol: y_steps must be (n_steps+1, B, 3N)");
+    const int64_t n_steps = y_steps.size(0) - 1;
+    TORCH_CHECK(grad_y.dim() == 3 && grad_y.size(0) == T && grad_y.size(1) == pr.B(), "odecol: grad_y must be (T, B, G)");
+    const int64_t G = grad_y.size(2);
+    const float *dWp, *dUp;
+    srk_tables(pr, dW, dU, dWp, dUp);
+    TORCH_CHECK(dWp == nullptr || dW->size(0) == n_steps, "odecol: dW/dU must have n_steps rows");
+    const int32_t* selp = nullptr;
+    if (sel.has_value()) {
+        want(*sel, "sel", torch::kInt32);
+        TORCH_CHECK(sel->numel() == G, "odecol: sel must have G entries");
+        selp = sel->data_ptr<int32_t>();
+    } else {
+        TORCH_CHECK(G == 3 * pr.N(), "odecol: dense grad_y must have 3N components");
+    }
+    auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
+    auto gW = torch::empty_like(pr.W_aug);
+    auto ws = pr.workspace(ODECOL_OP_SRK_BWD, T, n_steps);
+    check(odecol_srk_bwd(&pr.p, ts.data_ptr<float>(), (int32_t)T, y_steps.data_ptr<float>(), n_steps, dWp, dUp, (uint64_t)seed,
+                         trial_offset, grad_y.data_ptr<float>(), selp, (int32_t)G, (float)dt, gy0.data_ptr<float>(),
+                         gW.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(), pr.stream()), "srk_bwd");
+    return {gy0, gW};
+}
+
 torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
     c10::cuda::CUDAGuard g(A.device());
     want(A, "A"); want(B, "B");
@@ -339,6 +400,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_num_steps", &em_num_steps);
     m.def("em_fwd", &em_fwd);
     m.def("em_bwd", &em_bwd);
+    m.def("srk_fwd", &srk_fwd);
+    m.def("srk_bwd", &srk_bwd);
     m.def("tc_contract", &tc_contract);
     m.def("tc_contract_tn", &tc_contract_tn);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;
@@ -347,6 +410,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.attr("OP_DOPRI5_FWD") = (int)ODECOL_OP_DOPRI5_FWD;
     m.attr("OP_EM_FWD") = (int)ODECOL_OP_EM_FWD;
     m.attr("OP_EM_BWD") = (int)ODECOL_OP_EM_BWD;
+    m.attr("OP_SRK_FWD") = (int)ODECOL_OP_SRK_FWD;
+    m.attr("OP_SRK_BWD") = (int)ODECOL_OP_SRK_BWD;
     m.attr("FLAG_FORCE_STAGED") = (int)ODECOL_FLAG_FORCE_STAGED;
     m.attr("FLAG_FORCE_TENSOR") = (int)ODECOL_FLAG_FORCE_TENSOR;
 }

@@ -142,6 +142,31 @@ class _EMFunction(torch.autograd.Function):
         return (gy0, gW) + (None,) * 9
 
 
+class _SRKFunction(torch.autograd.Function):
+    """torchsde method='srk' (SRI2, fixed step) and its discrete adjoint (include/odecol.h: odecol_srk_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, y0, W_aug, setup: _Setup, dW, dU, seed, trial_offset, dt, n_steps, sel_long, sel_i32, stats):
+        prob = setup.problem(W_aug)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        y, st, ysteps = setup.ext.srk_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), dW, dU, seed,
+                                          trial_offset, dt, n_steps if need_grad else 0)
+        if stats is not None:
+            stats.update(status=st)
+        ctx.setup, ctx.prob, ctx.sel_i32, ctx.dt = setup, prob, sel_i32, dt
+        ctx.noise = (dW, dU, seed, trial_offset)
+        ctx.save_for_backward(ysteps)
+        return y if sel_long is None else y.index_select(2, sel_long)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ysteps,) = ctx.saved_tensors
+        dW, dU, seed, trial_offset = ctx.noise
+        gy0, gW = ctx.setup.ext.srk_bwd(ctx.prob, ctx.setup.t, ysteps, dW, dU, seed, trial_offset,
+                                        grad.to(torch.float32).contiguous(), ctx.sel_i32, ctx.dt)
+        return (gy0, gW) + (None,) * 10
+
+
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
            components=None, stats: Optional[Dict] = None):
     """Fused replacement of ``torchdiffeq.odeint``.  ``method``: None/'dopri5' (adaptive, per-trial control, the
@@ -190,35 +215,56 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
                   components=components, stats=stats)
 
 
-def _tabulate_bm(bm, ts_cpu: torch.Tensor, dt: float, B: int, device) -> torch.Tensor:
-    """Increments of a torchsde-style Brownian object along the fixed-step schedule (float32 time loop)."""
-    out = []
+def _tabulate_bm(bm, ts_cpu: torch.Tensor, dt: float, B: int, device, with_u: bool = False):
+    """Increments of a torchsde-style Brownian object along the fixed-step schedule (float32 time loop); with_u also
+    tabulates the space-time Levy areas ``bm(t0, t1, return_U=True)`` hands to the srk scheme."""
+    out, out_u = [], []
     curr = ts_cpu[0].clone()
     t_end = ts_cpu[-1]
+    row = lambda v: (lambda w: w.expand(B) if w.numel() == 1 else w)(torch.as_tensor(v, dtype=torch.float32).reshape(-1))
     for out_t in ts_cpu[1:]:
         while curr < out_t:
             nxt = torch.minimum(curr + dt, t_end)
-            w = torch.as_tensor(bm(curr, nxt), dtype=torch.float32).reshape(-1)
-            out.append(w.expand(B) if w.numel() == 1 else w)
+            if with_u:
+                w, u = bm(curr, nxt, return_U=True)
+                out_u.append(row(u))
+            else:
+                w = bm(curr, nxt)
+            out.append(row(w))
             curr = nxt
-    return torch.stack(out).to(device).contiguous()
+    W = torch.stack(out).to(device).contiguous()
+    return (W, torch.stack(out_u).to(device).contiguous()) if with_u else W
+
+
+def _increment_table(x, n_steps: int, B: int, device) -> torch.Tensor:
+    x = x.detach().to(device, torch.float32).reshape(x.shape[0], -1)
+    if x.shape[1] == 1 and B > 1:
+        x = x.expand(-1, B)
+    if x.shape != (n_steps, B):
+        raise ValueError(f"odecol: need Brownian increments of shape ({n_steps}, {B}), got {tuple(x.shape)}")
+    return x.contiguous()
 
 
 def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5, atol=1e-4, dt_min=1e-5,
            options=None, names=None, logqp=False, extra=False, extra_solver_state=None,
            seed: Optional[int] = None, trial_offset: int = 0, components=None, stats: Optional[Dict] = None):
-    """Fused replacement of ``torchsde.sdeint`` for scalar-noise Ito SDEs integrated with Euler-Maruyama.
+    """Fused replacement of ``torchsde.sdeint`` for scalar-noise Ito SDEs: ``method='euler'`` (Euler-Maruyama) and
+    ``method='srk'`` (Roessler SRI2 with torchsde's SRID2 tableau -- what the reference scripts name; also torchsde's
+    default for this noise type, so ``method=None`` selects it).
 
     ``bm``: None -> in-kernel Philox4x32-10 noise keyed by (seed, trial_offset + trial index); a tensor (n_steps, B)
-    or (n_steps, B, 1) of increments in step order (bit-parity mode, fixed step); or a torchsde-style callable
-    ``bm(t0, t1)``, tabulated along the step schedule.  ``adaptive=True`` uses step doubling with torchsde's controller,
-    per trial, on a virtual Brownian tree (Philox only).  ``method='srk'`` (what the reference scripts name) is not
-    fused yet."""
+    or (n_steps, B, 1) of increments in step order (bit-parity mode, fixed step) -- for 'srk' a pair ``(W, U)`` of such
+    tensors, U the space-time Levy area of each step; or a torchsde-style callable ``bm(t0, t1)`` /
+    ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` (Euler only) uses step
+    doubling with torchsde's controller, per trial, on a virtual Brownian tree (Philox only)."""
     if logqp or extra or extra_solver_state is not None:
         raise NotImplementedError("odecol: logqp / extra solver state are not part of the fused path")
-    method = method or "euler"
-    if method != "euler":
-        raise NotImplementedError(f"odecol: sdeint method {method!r} is not fused (have 'euler'); see DESIGN.md, next rows")
+    method = method or "srk"
+    if method not in ("euler", "srk"):
+        raise NotImplementedError(f"odecol: sdeint method {method!r} is not fused (have 'euler', 'srk')")
+    if method == "srk" and adaptive:
+        raise NotImplementedError("odecol: adaptive stepping is fused for method='euler' only (srk needs a Levy-area "
+                                  "consistent Brownian tree); use adaptive=False or method='euler'")
     if getattr(sde, "noise_type", "scalar") != "scalar" or getattr(sde, "sde_type", "ito") != "ito":
         raise ValueError("odecol: only scalar-noise Ito SDEs (what the reference declares) are supported")
     options = dict(options or {})
@@ -239,15 +285,25 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
         return y if sel_long is None else y.index_select(2, sel_long)
     ts_cpu = setup.t.cpu()
     n_steps = int(ext.em_num_steps(ts_cpu, dt))
+    if method == "srk":
+        dW = dU = None
+        if bm is not None:
+            if isinstance(bm, (tuple, list)) and len(bm) == 2 and all(torch.is_tensor(x) for x in bm):
+                dW, dU = (_increment_table(x, n_steps, setup.B, y0.device) for x in bm)
+            elif torch.is_tensor(bm):
+                raise ValueError("odecol: method='srk' needs the pair (W, U) of increment tables, or a callable bm")
+            else:
+                dW, dU = _tabulate_bm(bm, ts_cpu, dt, setup.B, y0.device, with_u=True)
+                if dW.shape != (n_steps, setup.B):
+                    raise ValueError(f"odecol: bm produced increments of shape {tuple(dW.shape)}")
+        return _SRKFunction.apply(y0, setup.lf.W_aug, setup, dW, dU, seed, int(trial_offset), dt, n_steps, sel_long,
+                                  sel_i32, stats)
     dW = None
     if bm is not None:
         if torch.is_tensor(bm):
-            dW = bm.detach().to(y0.device, torch.float32).reshape(bm.shape[0], -1)
-            if dW.shape[1] == 1 and setup.B > 1:
-                dW = dW.expand(-1, setup.B)
-            dW = dW.contiguous()
+            dW = _increment_table(bm, n_steps, setup.B, y0.device)
         else:
             dW = _tabulate_bm(bm, ts_cpu, dt, setup.B, y0.device)
-        if dW.shape != (n_steps, setup.B):
-            raise ValueError(f"odecol: need Brownian increments of shape ({n_steps}, {setup.B}), got {tuple(dW.shape)}")
+            if dW.shape != (n_steps, setup.B):
+                raise ValueError(f"odecol: bm produced increments of shape {tuple(dW.shape)}")
     return _EMFunction.apply(y0, setup.lf.W_aug, setup, dW, seed, int(trial_offset), dt, n_steps, sel_long, sel_i32, stats)

@@ -315,9 +315,63 @@ def add_fp64_gradients():
     print("parity fp64 loss", float(loss), "vs fp32", float(g["rk4_loss"]))
 
 
+def add_srk():
+    """method='srk' fixtures (what scripts/wta_ode.py:174,200 call): the UNMODIFIED reference modules driven by the
+    restated SRI2 stepper with tabulated (W, U), seed 4321; for the WTA network also the script's Huber loss and its
+    autograd gradient (wta_ode.py:176-181).  Adds keys srk_* to the existing wta / xor files."""
+    from oracle import solvers, stimuli
+    cc, ru = _import_reference()
+    cfg = ru.load_config(os.path.join(REF, "config", "model.toml"))
+    torch.set_num_threads(1)
+    # wta: one trial, the full 1500-point grid, sigma = 100 on all 48 components
+    path = os.path.join(OUT, "wta.npz")
+    g = dict(np.load(path))
+    torch.manual_seed(0)
+    net = cc.ColumnAreaWTA(cfg, "mt")
+    assert np.array_equal(_np(net.recurrent_weights), g["recurrent_weights"])
+    tv = torch.tensor(g["time_vec"])
+    net.time_vec, net.stim = tv, torch.tensor(g["stim"])
+    n_steps = len(solvers.em_step_schedule(tv, 1e-3))
+    gen = torch.Generator().manual_seed(4321)
+    W, U = solvers.sample_w_u(n_steps, 1, 1e-3, gen)
+    W, U = 0.1 * W, 0.1 * U                       # sigma = 100: keep V - A away from the pole of phi
+    traj = solvers.sdeint_srk(net, torch.zeros(1, 48), tv, solvers.TabulatedBrownianU(W, U), dt=1e-3)
+    target = torch.tensor(g["rk4_target"])
+    loss = ru.huber_loss_wta(traj.unsqueeze(0), target, net)
+    loss.backward()
+    g.update(srk_dW=_np(W), srk_dU=_np(U), srk_traj=_np(traj), srk_loss=_np(loss),
+             srk_grad_recurrent_weights=_np(net.recurrent_weights.grad))
+    np.savez_compressed(path, **g)
+    print(f"wta srk: {n_steps} steps, loss {float(loss):.6f}, |V|max {float(traj[..., :16].abs().max()):.2f}")
+    # xor: the four patterns, sigma = 10 on V
+    path = os.path.join(OUT, "xor.npz")
+    g = dict(np.load(path))
+    torch.manual_seed(0)
+    nd = {"nr_areas": 2, "areas": ["mt", "mt"], "nr_columns_per_area": [2, 1], "nr_input_units": 2}
+    net = cc.ColumnNetworkXOR(cfg, nd)
+    assert np.array_equal(_np(net.feedforward_target_weights["0"][0]), g["ffw_0_0"])
+    tv = torch.tensor(g["time_vec"])
+    net.time_vec = tv
+    n_steps = len(solvers.em_step_schedule(tv, 1e-3))
+    W, U = solvers.sample_w_u(n_steps, 4, 1e-3, gen)
+    W, U = 0.3 * W, 0.3 * U
+    trajs = []
+    with torch.no_grad():
+        for b in range(4):
+            net.stim = torch.tensor(g["stims"][b])
+            trajs.append(solvers.sdeint_srk(net, torch.zeros(1, 72), tv, solvers.TabulatedBrownianU(W[:, b:b + 1], U[:, b:b + 1]), dt=1e-3))
+    tr = torch.stack(trajs)[:, ::5, 0, :]
+    g.update(srk_dW=_np(W), srk_dU=_np(U), srk_traj=_np(tr))
+    np.savez_compressed(path, **g)
+    print(f"xor srk: {n_steps} steps, |V|max {float(tr[..., :24].abs().max()):.2f}")
+
+
 def main():
     if "--fp64-only" in sys.argv:
         add_fp64_gradients()
+        return
+    if "--srk-only" in sys.argv:
+        add_srk()
         return
     if "--orig-weights-only" in sys.argv:      # cheap refresh of one key without re-running the solvers
         path = os.path.join(OUT, "wta.npz")
@@ -337,6 +391,7 @@ def main():
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in data.items()})
         print(f"  wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
     add_fp64_gradients()
+    add_srk()
 
 
 if __name__ == "__main__":

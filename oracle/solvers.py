@@ -15,7 +15,11 @@ Algorithms restated
     state tensor, step controller (safety .9, ifactor 10, dfactor .2), 4th-order dense output through y_mid;
     time kept in float64, state in the dtype of y0, coefficients cast to the dtype of y0;
   * ``odeint_adjoint``: continuous adjoint, augmented state integrated backwards between output times;
-  * torchsde integrate loop with the Euler-Maruyama step, fixed step and step-doubling adaptive.
+  * torchsde integrate loop with the Euler-Maruyama step, fixed step and step-doubling adaptive;
+  * torchsde ``method='srk'`` for scalar / diagonal noise: Roessler's SRI2 scheme ("SRID2" tableau, strong order
+    1.5) driven by the Brownian increment W and the space-time Levy area U = int (W_r - W_s) dr of every step --
+    what every committed sdeint call of the reference names (scripts/wta_ode.py:174,200,
+    plotting_results.py:391,506,594), fixed step.
 
 ``tests/test_oracle_selfcheck.py`` anchors them (order conditions, convergence order, analytic solutions).
 All functions take ``func(t, y)`` with y of shape (B, D); the reference modules are used with B = 1.
@@ -336,3 +340,87 @@ def em_step_schedule(ts: torch.Tensor, dt: float) -> List[Tuple[float, float]]:
             out.append((float(curr), float(nxt)))
             curr = nxt
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# torchsde method='srk' (diagonal / scalar noise): Roessler SRI2, tableau "SRID2" [memory: torchsde 0.2.x
+# _core/methods/srk.py::diagonal_or_scalar_step and _core/methods/tableaus/srid2.py; Roessler 2010, table 5.3 SRI2W1]
+# ----------------------------------------------------------------------------------------------------------------
+SRID2_STAGES = 4
+SRID2_C0 = (0, 1, 1 / 2, 0)
+SRID2_C1 = (0, 1 / 4, 1, 1 / 4)
+SRID2_A0 = ((), (1,), (1 / 4, 1 / 4), (0, 0, 0))
+SRID2_A1 = ((), (1 / 4,), (1, 0), (0, 0, 1 / 4))
+SRID2_B0 = ((), (0,), (1, 1 / 2), (0, 0, 0))
+SRID2_B1 = ((), (-1 / 2,), (1, 0), (2, -1, 1 / 2))
+SRID2_ALPHA = (1 / 6, 1 / 6, 2 / 3, 0)
+SRID2_BETA1 = (-1, 4 / 3, 2 / 3, 0)
+SRID2_BETA2 = (1, -4 / 3, 1 / 3, 0)
+SRID2_BETA3 = (2, -4 / 3, -2 / 3, 0)
+SRID2_BETA4 = (-2, 5 / 3, -2 / 3, 1)
+
+
+class TabulatedBrownianU(TabulatedBrownian):
+    """Deterministic (W, U) source: call k returns rows k of ``increments`` and ``levy_u`` (both (steps, B, 1));
+    U is torchsde's space-time Levy area of the step, U = int_{t0}^{t1} (W_r - W_{t0}) dr, U | W ~ N(h W / 2, h^3 / 12)."""
+
+    def __init__(self, increments: torch.Tensor, levy_u: torch.Tensor):
+        super().__init__(increments)
+        self.levy_u = levy_u
+
+    def __call__(self, t0, t1, return_U=False):
+        k = self.k
+        w = super().__call__(t0, t1)
+        return (w, self.levy_u[k]) if return_U else w
+
+
+def sample_w_u(n_steps: int, B: int, h: float, generator: torch.Generator):
+    """Joint draw of (W, U) for steps of size h: W = sqrt(h) z1, U = h W / 2 + sqrt(h^3 / 12) z2."""
+    z = torch.randn(2, n_steps, B, 1, generator=generator)
+    w = math.sqrt(h) * z[0]
+    return w, 0.5 * h * w + math.sqrt(h ** 3 / 12.0) * z[1]
+
+
+def _srk_step(sde, bm, t0, t1, y0):
+    dt = t1 - t0
+    rdt = 1 / dt
+    sqrt_dt = torch.sqrt(dt) if torch.is_tensor(dt) else math.sqrt(dt)
+    I_k, I_k0 = bm(t0, t1, return_U=True)            # (B, 1) each: broadcast over the state for scalar noise
+    I_kk = (I_k ** 2 - dt) / 2
+    I_kkk = (I_k ** 3 - 3 * dt * I_k) / 6
+    y1 = y0
+    H0, H1 = [], []
+    for s in range(SRID2_STAGES):
+        H0s, H1s = y0, y0
+        for j in range(s):
+            f = sde.forward(t0 + SRID2_C0[j] * dt, H0[j])
+            g = sde.diffusion(t0 + SRID2_C1[j] * dt, H1[j])
+            g = g.squeeze(2) if g.dim() == 3 else g
+            H0s = H0s + SRID2_A0[s][j] * f * dt + SRID2_B0[s][j] * g * I_k0 * rdt
+            H1s = H1s + SRID2_A1[s][j] * f * dt + SRID2_B1[s][j] * g * sqrt_dt
+        H0.append(H0s)
+        H1.append(H1s)
+        f = sde.forward(t0 + SRID2_C0[s] * dt, H0s)
+        g_weight = (SRID2_BETA1[s] * I_k + SRID2_BETA2[s] * I_kk / sqrt_dt + SRID2_BETA3[s] * I_k0 * rdt
+                    + SRID2_BETA4[s] * I_kkk * rdt)
+        g = sde.diffusion(t0 + SRID2_C1[s] * dt, H1s)
+        g = g.squeeze(2) if g.dim() == 3 else g
+        y1 = y1 + SRID2_ALPHA[s] * f * dt + g * g_weight            # g_prod for diagonal / scalar noise
+    return y1
+
+
+def sdeint_srk(sde, y0: torch.Tensor, ts: torch.Tensor, bm, dt: float = 1e-3):
+    """torchsde ``sdeint(..., method='srk')``, fixed step: the integrate loop of sdeint_euler with the SRI2 step.
+    ``bm(t0, t1, return_U=True)`` -> (W, U), each (B, 1) (see TabulatedBrownianU)."""
+    prev_t = curr_t = ts[0]
+    prev_y = curr_y = y0
+    ys = [y0]
+    for out_t in ts[1:]:
+        while curr_t < out_t:
+            next_t = torch.minimum(curr_t + dt, ts[-1])
+            prev_t, prev_y = curr_t, curr_y
+            curr_y = _srk_step(sde, bm, curr_t, next_t, curr_y)
+            curr_t = next_t
+        span = curr_t - prev_t
+        ys.append((curr_t - out_t) / span * prev_y + (out_t - prev_t) / span * curr_y)
+    return torch.stack(ys, dim=0)

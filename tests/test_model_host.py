@@ -137,8 +137,12 @@ def test_solvers_refuse_cpu_and_foreign_functions(cfg, golden):
         odecol.odeint(net, torch.zeros(1, 48), net.time_vec, method="rk4")
     with pytest.raises(TypeError, match="fallback"):
         odecol.odeint(lambda t, y: -y, torch.zeros(1, 48), net.time_vec)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="srk")
+    with pytest.raises(NotImplementedError):
+        odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="srk", adaptive=True)
+    with pytest.raises(NotImplementedError):
+        odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="milstein")
 
 
 def test_synthetic_sheet_matches_oracle_structure(cfg):

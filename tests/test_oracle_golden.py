@@ -93,3 +93,14 @@ def test_em_prefix_matches_reference_driven_solve(cfg, golden):
     dW = torch.tensor(g["em_dW"])
     y = S.sdeint_euler(ode, torch.zeros(1, 48), tv, S.TabulatedBrownian(dW), dt=1e-3)
     assert rel_err(y[:, 0], torch.tensor(g["em_traj"][:, 0])) < 5e-6
+
+
+def test_srk_matches_reference_driven_solve(cfg, golden):
+    # unified-form oracle under the restated SRI2 stepper vs the UNMODIFIED reference module under the same stepper
+    g = golden["wta"]
+    lf = oracle_form("wta", cfg, g)
+    tv = torch.tensor(g["time_vec"])
+    ode = orhs.UnifiedColumnODE(lf, tv, stim_table("wta", g["stim"]))
+    bm = S.TabulatedBrownianU(torch.tensor(g["srk_dW"]), torch.tensor(g["srk_dU"]))
+    y = S.sdeint_srk(ode, torch.zeros(1, 48), tv, bm, dt=1e-3)
+    assert rel_err(y[:, 0], torch.tensor(g["srk_traj"][:, 0])) < 5e-6

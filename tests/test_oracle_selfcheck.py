@@ -131,3 +131,82 @@ def test_adaptive_controller_limits():
     assert abs(s - 1.4) < 1e-12 and r == 0.9 / 1e-9
     s, _ = S.adaptive_update(0.95, 1.0, None)
     assert s == 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torchsde method='srk' (SRI2 / "SRID2" tableau) restatement
+# ---------------------------------------------------------------------------------------------------------------
+def test_srid2_tableau_order_conditions():
+    # Roessler 2010, conditions for strong order 1.5 (m = 1): the ones that pin the tableau's rows
+    al, b1, b2, b3, b4 = (np.array(x, dtype=float) for x in (S.SRID2_ALPHA, S.SRID2_BETA1, S.SRID2_BETA2, S.SRID2_BETA3, S.SRID2_BETA4))
+    full = lambda rows: np.array([list(r) + [0.0] * (4 - len(r)) for r in rows])
+    A0, A1, B0, B1 = (full(x) for x in (S.SRID2_A0, S.SRID2_A1, S.SRID2_B0, S.SRID2_B1))
+    e = np.ones(4)
+    assert abs(al.sum() - 1) < 1e-15 and abs(b1.sum() - 1) < 1e-15
+    assert abs(b2.sum()) < 1e-15 and abs(b3.sum()) < 1e-15 and abs(b4.sum()) < 1e-15
+    assert np.allclose(A0 @ e, S.SRID2_C0) and np.allclose(A1 @ e, S.SRID2_C1)
+    assert abs(al @ (A0 @ e) - 0.5) < 1e-15                 # deterministic order 2
+    assert abs(al @ (B0 @ e) - 1.0) < 1e-15                 # drift sees the space-time integral once
+    assert abs(al @ (B0 @ e) ** 2 - 1.5) < 1e-15
+    assert abs(b1 @ (B1 @ e)) < 1e-15 and abs(b2 @ (B1 @ e) - 1.0) < 1e-15
+    assert abs(b3 @ (B1 @ e)) < 1e-15 and abs(b4 @ (B1 @ e)) < 1e-15
+    assert abs(b1 @ (A1 @ e) - 1.0) < 1e-15 and abs(b3 @ (A1 @ e) + 1.0) < 1e-15
+    assert abs(b2 @ (A1 @ e)) < 1e-15 and abs(b4 @ (A1 @ e)) < 1e-15      # NB not the full set; the empirical
+    # strong-order test below is the anchor
+
+
+class _Logistic:
+    """dy = y (1 - y) dt + sigma dW (additive), a nonlinear drift for convergence-order checks."""
+    noise_type, sde_type = "scalar", "ito"
+
+    def __init__(self, sigma):
+        self.sigma = sigma
+
+    def forward(self, t, y):
+        return y * (1 - y)
+
+    def diffusion(self, t, y):
+        return torch.full_like(y, self.sigma).unsqueeze(-1)
+
+
+def test_srk_without_noise_is_third_order():
+    errs = []
+    for n in (10, 20, 40):
+        ts = torch.linspace(0, 2, 2, dtype=torch.float64)
+        z = torch.zeros(n + 2, 1, 1, dtype=torch.float64)
+        y = S.sdeint_srk(_Logistic(0.0), torch.full((1, 1), 0.1, dtype=torch.float64), ts, S.TabulatedBrownianU(z, z), dt=2.0 / n)
+        exact = 0.1 * math.exp(2) / (1 + 0.1 * (math.exp(2) - 1))
+        errs.append(abs(float(y[-1]) - exact))
+    assert 6.5 < errs[0] / errs[1] < 9.5 and 6.5 < errs[1] / errs[2] < 9.5, errs
+
+
+def _coarsen(w, u, delta, factor):
+    """(W, U) of steps of size delta -> steps of size factor * delta on the same Brownian path."""
+    n = w.shape[0] // factor
+    w = w[:n * factor].reshape(n, factor, *w.shape[1:])
+    u = u[:n * factor].reshape(n, factor, *u.shape[1:])
+    before = torch.cumsum(w, dim=1) - w                      # W(t_i) - W(t_0) at the start of each fine step
+    return w.sum(1), (u + delta * before).sum(1)
+
+
+def test_srk_strong_order_on_a_shared_brownian_path():
+    g = torch.Generator().manual_seed(3)
+    n_fine, B, T = 256, 2000, 1.0
+    delta = T / n_fine
+    w, u = S.sample_w_u(n_fine, B, delta, g)
+    w, u = w.double(), u.double()
+    ts = torch.tensor([0.0, T], dtype=torch.float64)
+    y0 = torch.full((B, 1), 0.3, dtype=torch.float64)
+    sde = _Logistic(0.4)
+    ref = S.sdeint_srk(sde, y0, ts, S.TabulatedBrownianU(w, u), dt=delta)[-1]
+    errs, errs_em = [], []
+    for factor in (16, 32):
+        wc, uc = _coarsen(w, u, delta, factor)
+        y = S.sdeint_srk(sde, y0, ts, S.TabulatedBrownianU(wc, uc), dt=delta * factor)[-1]
+        errs.append(float((y - ref).abs().mean()))
+        ye = S.sdeint_euler(sde, y0, ts, S.TabulatedBrownian(wc), dt=delta * factor)[-1]
+        errs_em.append(float((ye - ref).abs().mean()))
+    ratio, ratio_em = errs[1] / errs[0], errs_em[1] / errs_em[0]
+    # strong order 1.5 -> 2^1.5 = 2.83 per halving; Euler-Maruyama (additive noise, order 1) -> 2
+    assert 2.45 < ratio < 3.3, (errs, ratio)
+    assert 1.7 < ratio_em < 2.3 and errs[0] < 0.2 * errs_em[0], (errs_em, errs)
