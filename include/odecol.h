@@ -231,6 +231,21 @@ int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const fl
                    const float* grad_y, const int32_t* sel, int32_t G, float dt,
                    float* grad_y0, float* grad_W_aug, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched Wong-Wang (2006) decision model: the training targets of the WTA task, one sample per thread, float64.
+ * Replaces DM.run_sim / DM.simulate / DM.update (src/ww_model.py:92-127) inside the dataset loop make_ds_wwp
+ * (scripts/wta_ode.py:56-93): three phases (mu = 0, mu = (muA, muB), mu = 0) of `steps_per_phase` updates of dt = 1e-3
+ * each (the reference: int(5. / 1e-3) + 1 = 5001), firing rates recorded after every update.
+ *   mu        (B, 2) float64 stimulus-phase inputs (muA, muB)
+ *   i_noise0  (B, 2) float64 initial noise currents, or NULL for 0.  DM.reset() does not reset I_noise, so in the
+ *             reference every sample but the first starts from the converged current (oracle/ww.py)
+ *   states    (B, time_steps, 2) float32 out: r of update k for k = 0, every, 2 every, ... (first time_steps of them) --
+ *             the `states` tensor of the dataset (R[:, ::10][:, :time_steps] transposed, wta_ode.py:82-87)
+ *   sigma_noise  0 in the reference; otherwise the AMPA noise comes from Philox4x32-10 keyed by (seed, trial_offset + b)
+ * Constants are those of DM.__init__ (src/ww_model.py:57-71). */
+int odecol_ww_generate(const double* mu, const double* i_noise0, int32_t B, int32_t steps_per_phase, int32_t every,
+                       int32_t time_steps, double sigma_noise, uint64_t seed, int64_t trial_offset,
+                       float* states, void* stream);
+
 /* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in
  * tensor memory), C[n][m] = sum_k A[m][k] * B[n][k] for row-major A (M x K), B (N x K), C (N x M).  Lets the tests pin
  * the accuracy of the split-precision contraction the staged solver uses for large networks. */

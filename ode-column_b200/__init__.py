@@ -4,7 +4,8 @@ Drop-in surface (reference src/coupled_columns.py, src/utils.py; torchdiffeq / t
 
     ColumnArea, ColumnAreaWTA, ColumnNetworkXOR, ColumnNetwork, load_config,
     compute_firing_rate, soft_clamp, torch_interp, min_max, fr_to_binary, huber_loss_wta,
-    odeint, odeint_adjoint, sdeint
+    odeint, odeint_adjoint, sdeint,
+    make_ds_wwp, get_data            (Wong-Wang target generator, reference scripts/wta_ode.py:56-107)
 
 The solvers run only on CUDA through the C ABI in ``include/odecol.h``; importing the package does not need a GPU.
 """
@@ -14,7 +15,8 @@ from .losses import fr_to_binary, huber_loss_wta, min_max, parity_readout, xor_r
 from .solvers import odeint, odeint_adjoint, sdeint
 from .stimulus import compress_knots, step_knots
 from .synthetic import SyntheticColumnSheet
-from . import distributed
+from .wongwang import get_data, make_ds_wwp
+from . import distributed, wongwang
 from . import _native
 
 __all__ = [
@@ -22,5 +24,6 @@ __all__ = [
     "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug",
     "min_max", "fr_to_binary", "huber_loss_wta", "xor_readout", "parity_readout",
     "odeint", "odeint_adjoint", "sdeint", "compress_knots", "step_knots", "distributed",
+    "make_ds_wwp", "get_data", "wongwang",
 ]
 __version__ = "0.1.0"

@@ -330,6 +330,17 @@ int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const fl
                                 wts, tk, s);
 }
 
+int odecol_ww_generate(const double* mu, const double* i_noise0, int32_t B, int32_t steps_per_phase, int32_t every,
+                       int32_t time_steps, double sigma_noise, uint64_t seed, int64_t trial_offset, float* states,
+                       void* stream) {
+    if (!mu || !states) return ODECOL_E_NULL;
+    if (B < 1 || steps_per_phase < 1 || every < 1 || time_steps < 1) return ODECOL_E_SHAPE;
+    if ((int64_t)time_steps > (3LL * steps_per_phase + every - 1) / every) return ODECOL_E_SHAPE;   // more rows than recorded updates
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_ww_generate(mu, i_noise0, B, steps_per_phase, every, time_steps, sigma_noise, seed, trial_offset, states,
+                              static_cast<cudaStream_t>(stream));
+}
+
 size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return tc_contract_workspace_bytes(M, N, K);

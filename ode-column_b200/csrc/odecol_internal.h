@@ -66,6 +66,10 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
                          int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
                          const int* step_of, const float* w, const float* tk, cudaStream_t s);
 
+// ---- Wong-Wang target generator (ww_kernel.cu) -----------------------------------------------------------------
+int launch_ww_generate(const double* mu, const double* i_noise0, int B, int steps_per_phase, int every, int time_steps,
+                       double sigma_noise, uint64_t seed, int64_t trial_offset, float* states, cudaStream_t s);
+
 // ---- family L (stage_kernels.cu): state in global memory, one fused contraction + epilogue per RK stage ------
 struct StageWorkspace;   // carved from the caller's workspace
 size_t stage_rk4_fwd_workspace_bytes(const DevProblem& p, int T);

@@ -344,6 +344,24 @@ std::vector<torch::Tensor> srk_bwd(const Problem& pr, const torch::Tensor& ts, c
     return {gy0, gW};
 }
 
+torch::Tensor ww_generate(const torch::Tensor& mu, std::optional<torch::Tensor> i_noise0, int64_t steps_per_phase,
+                          int64_t every, int64_t time_steps, double sigma_noise, int64_t seed, int64_t trial_offset) {
+    c10::cuda::CUDAGuard g(mu.device());
+    want(mu, "mu", torch::kFloat64);
+    TORCH_CHECK(mu.dim() == 2 && mu.size(1) == 2, "odecol: mu must be (B, 2) float64");
+    const double* i0 = nullptr;
+    if (i_noise0.has_value()) {
+        want(*i_noise0, "i_noise0", torch::kFloat64);
+        TORCH_CHECK(i_noise0->sizes() == mu.sizes(), "odecol: i_noise0 must be (B, 2) float64");
+        i0 = i_noise0->data_ptr<double>();
+    }
+    auto states = torch::empty({mu.size(0), time_steps, 2}, mu.options().dtype(torch::kFloat32));
+    check(odecol_ww_generate(mu.data_ptr<double>(), i0, (int32_t)mu.size(0), (int32_t)steps_per_phase, (int32_t)every,
+                             (int32_t)time_steps, sigma_noise, (uint64_t)seed, trial_offset, states.data_ptr<float>(),
+                             at::cuda::getCurrentCUDAStream(mu.device().index()).stream()), "ww_generate");
+    return states;
+}
+
 torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
     c10::cuda::CUDAGuard g(A.device());
     want(A, "A"); want(B, "B");
@@ -402,6 +420,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_bwd", &em_bwd);
     m.def("srk_fwd", &srk_fwd);
     m.def("srk_bwd", &srk_bwd);
+    m.def("ww_generate", &ww_generate);
     m.def("tc_contract", &tc_contract);
     m.def("tc_contract_tn", &tc_contract_tn);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;

@@ -366,7 +366,41 @@ def add_srk():
     print(f"xor srk: {n_steps} steps, |V|max {float(tr[..., :24].abs().max()):.2f}")
 
 
+def add_ww():
+    """tests/golden/ww.npz: the UNMODIFIED reference Wong-Wang class (src/ww_model.py) inside the reference's dataset
+    loop (scripts/wta_ode.py:56-93, restated here only as far as the loop body: the script itself imports matplotlib),
+    numpy seed 7, 5 samples -- stimuli AND states, so that both the generator's arithmetic and its consumption of the
+    global random stream are pinned."""
+    sys.path.insert(0, REF)
+    from src.ww_model import DM
+    nr_samples, time_steps = 5, 1500
+    np.random.seed(7)
+    states = torch.Tensor(nr_samples, time_steps, 2)
+    stims = torch.Tensor(nr_samples, 2)
+    dm = DM()
+    full_first = None
+    for i in range(nr_samples):
+        muA = np.random.uniform(15.0, 25.0)
+        muB = muA + np.random.uniform(10., 20.)
+        mu_vals = [muA, muB]
+        np.random.shuffle(mu_vals)
+        muA, muB = mu_vals
+        R = dm.run_sim(muA, muB)
+        if full_first is None:
+            full_first = R.copy()
+        R = R[:, ::10]
+        R = R[:, :time_steps]
+        states[i, :, :] = torch.tensor(R).transpose(0, 1)
+        stims[i, :] = torch.tensor([muA, muB])
+    path = os.path.join(OUT, "ww.npz")
+    np.savez_compressed(path, states=_np(states), stims=_np(stims), first_full=full_first[:, ::25], seed=np.array(7))
+    print(f"wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB); r range {float(states.min()):.3f}..{float(states.max()):.3f}")
+
+
 def main():
+    if "--ww-only" in sys.argv:
+        add_ww()
+        return
     if "--fp64-only" in sys.argv:
         add_fp64_gradients()
         return
@@ -392,6 +426,7 @@ def main():
         print(f"  wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
     add_fp64_gradients()
     add_srk()
+    add_ww()
 
 
 if __name__ == "__main__":

@@ -156,3 +156,22 @@ def test_synthetic_sheet_matches_oracle_structure(cfg):
         assert np.array_equal(W[8 * c:8 * c + 8, 8 * c:8 * c + 8].numpy(), one.recurrent_weights)
     off = W[0:8, 8:16]
     assert (off[0, 1] < 0) and (off[4, 5] < 0) and int((off != 0).sum()) == 2
+
+
+def test_networks_pickle_like_the_reference_scripts_do(cfg, golden):
+    # the reference pickles whole networks (scripts/wta_ode.py:214-215, parity_ode.py:210-211,281-282): the drop-in
+    # modules hold no native handles, a round trip keeps parameters, masks, stimulus and the exported linear form
+    import pickle
+    for name in ("wta", "xor", "parity"):
+        net = product_network(name, cfg, golden[name])
+        key = "stim" if name == "wta" else "stims"
+        net.stim = torch.tensor(golden[name][key]) if name == "wta" else torch.tensor(golden[name][key][1])
+        clone = pickle.loads(pickle.dumps(net))
+        assert [n for n, _ in clone.named_parameters()] == [n for n, _ in net.named_parameters()]
+        for (_, a), (_, b) in zip(net.named_parameters(), clone.named_parameters()):
+            assert torch.equal(a, b) and b.requires_grad == a.requires_grad
+        assert torch.equal(clone.time_vec, net.time_vec) and torch.equal(clone.stim, net.stim)
+        a, b = net.export_linear_form(), clone.export_linear_form()
+        assert torch.equal(a.W_aug, b.W_aug) and torch.equal(a.sigma, b.sigma) and a.n_in == b.n_in
+        y = torch.zeros(1, 3 * a.N)
+        assert torch.equal(net.forward(net.time_vec[3], y), clone.forward(clone.time_vec[3], y))
