@@ -104,5 +104,7 @@ def test_cuda_generator_noise_mode_is_reproducible_and_sharding_invariant():
     clean = odecol.wongwang.generate_states(mu, 1500)
     assert torch.equal(a, b) and torch.equal(c, a[32:])
     assert not torch.equal(a[3], a[4])                         # trials draw different noise
-    assert float((a[1:].mean(0) - clean[1]).abs().max()) < 3.0  # the trial average follows the noise-free solution
+    # the stronger input (pool B) still wins the competition in (almost) every noisy trial, as in the clean solution
+    assert float(clean[1, 990, 1]) > 10 * float(clean[1, 990, 0])
+    assert float((a[:, 990, 1] > a[:, 990, 0]).float().mean()) > 0.9
     assert torch.isfinite(a).all()
