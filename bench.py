@@ -75,6 +75,10 @@ def loss_components(torch, columns):
 
 
 def huber_on_rates(torch, odecol, sel_traj, target, columns):
+    """Huber loss on the L2/3e firing rates over the whole trajectory.  On the GPU arm this is the product's fused
+    read-out (one kernel: loss + gradient w.r.t. the trajectory); the CPU arms evaluate the same expression in torch."""
+    if sel_traj.is_cuda:
+        return odecol.huber_rate_loss(sel_traj, target, pops_per_group=1)
     rate = odecol.compute_firing_rate(sel_traj[:, :, :columns] - sel_traj[:, :, columns:])
     return torch.nn.functional.smooth_l1_loss(rate, target.expand_as(rate), beta=1.0)
 
@@ -223,6 +227,7 @@ def run_ours(args):
         traj = odecol.odeint(net, y0, tv, method="rk4", components=sel, options=options)
         launches["n"] += ext.last_launch_count()
         loss = huber_on_rates(torch, odecol, traj, target, columns)
+        launches["n"] += ext.last_launch_count()
         loss.backward()
         launches["n"] += ext.last_launch_count()
         if world > 1:

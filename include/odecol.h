@@ -246,6 +246,20 @@ int odecol_ww_generate(const double* mu, const double* i_noise0, int32_t B, int3
                        int32_t time_steps, double sigma_noise, uint64_t seed, int64_t trial_offset,
                        float* states, void* stream);
 
+/* Fused read-out loss on a trajectory restricted to read-out populations, with its gradient, in one pass:
+ *     rate    = phi(V - A)                                    src/utils.py:13-25
+ *     pred_g  = sum_k w[k] * rate[g*P + k]                    src/utils.py:79-84 (output_weights over the 8 populations)
+ *     loss    = mean over (t, b, g) of smooth_l1(pred_g - target[t, b, g], beta)      src/utils.py:86-88
+ * Replaces huber_loss_wta (src/utils.py:74-88) and loss.backward() down to the trajectory (scripts/wta_ode.py:178-179).
+ *   y_sel    (T, B, 2*G*P): the V components of the G*P read-out populations, then their A components -- what
+ *            odecol_rk4_fwd_ckpt returns for sel = [pops | N + pops]
+ *   w        [P] or NULL (all ones);  target with element strides (st_t, st_b, st_g), 0 = broadcast along that axis
+ *   loss     device scalar out;  grad_y_sel (T, B, 2*G*P) out = d loss / d y_sel (feeds odecol_*_bwd as grad_y)
+ *   workspace  at least 8 bytes, 8-byte aligned */
+int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, int32_t P, const float* w,
+                           const float* target, int64_t st_t, int64_t st_b, int64_t st_g, float beta,
+                           float* loss, float* grad_y_sel, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in
  * tensor memory), C[n][m] = sum_k A[m][k] * B[n][k] for row-major A (M x K), B (N x K), C (N x M).  Lets the tests pin
  * the accuracy of the split-precision contraction the staged solver uses for large networks. */

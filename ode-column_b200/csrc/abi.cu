@@ -341,6 +341,18 @@ int odecol_ww_generate(const double* mu, const double* i_noise0, int32_t B, int3
                               static_cast<cudaStream_t>(stream));
 }
 
+int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, int32_t P, const float* w,
+                           const float* target, int64_t st_t, int64_t st_b, int64_t st_g, float beta, float* loss,
+                           float* grad_y_sel, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!y_sel || !target || !loss || !grad_y_sel) return ODECOL_E_NULL;
+    if (T < 1 || B < 1 || G < 1 || P < 1 || !(beta > 0.f) || st_t < 0 || st_b < 0 || st_g < 0) return ODECOL_E_SHAPE;
+    if (!workspace || workspace_bytes < sizeof(double)) return ODECOL_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7) return ODECOL_E_ALIGN;
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_huber_rate_loss(y_sel, T, B, G, P, w, target, st_t, st_b, st_g, beta, loss, grad_y_sel,
+                                  static_cast<double*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
 size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return tc_contract_workspace_bytes(M, N, K);

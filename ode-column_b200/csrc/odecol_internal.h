@@ -70,6 +70,11 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
 int launch_ww_generate(const double* mu, const double* i_noise0, int B, int steps_per_phase, int every, int time_steps,
                        double sigma_noise, uint64_t seed, int64_t trial_offset, float* states, cudaStream_t s);
 
+// ---- fused read-out losses (readout_kernels.cu) ------------------------------------------------------------------
+int launch_huber_rate_loss(const float* y_sel, int T, int B, int G, int P, const float* w, const float* target,
+                           long long st_t, long long st_b, long long st_g, float beta, float* loss, float* grad,
+                           double* acc, cudaStream_t s);
+
 // ---- family L (stage_kernels.cu): state in global memory, one fused contraction + epilogue per RK stage ------
 struct StageWorkspace;   // carved from the caller's workspace
 size_t stage_rk4_fwd_workspace_bytes(const DevProblem& p, int T);

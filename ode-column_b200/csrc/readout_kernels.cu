@@ -1,0 +1,77 @@
+// Fused read-out losses on solver output: firing rate of the read-out populations, the
+// script-level reduction and the loss, together with the gradient w.r.t. the trajectory, in ONE pass over the selected
+// components -- instead of the ~10 elementwise ATen kernels (and as many (T, B, C) temporaries) autograd needs for
+//   rate = compute_firing_rate(V - A); loss = smooth_l1_loss(sum_k w_k rate_k, target)
+// (reference src/utils.py:74-88 huber_loss_wta; the C4 benchmark applies it to the L2/3e population of every column).
+// HBM-bound by construction: reads y_sel once, writes grad_y_sel once.
+#include "odecol_common.cuh"
+
+namespace odecol {
+
+// y_sel rows are [V of the G*P read-out populations | A of the same populations]; thread = one (row, group).
+__global__ void __launch_bounds__(256) k_huber_rate_loss(const float* __restrict__ y, long long rows, int B, int G, int P,
+                                                         const float* __restrict__ w, const float* __restrict__ target,
+                                                         long long st_t, long long st_b, long long st_g, float beta,
+                                                         float inv_count, float* __restrict__ grad, double* __restrict__ acc) {
+    const long long total = rows * G;
+    const int GP = G * P;
+    double local = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / G;
+        const int g = (int)(e - row * G);
+        const float* yr = y + row * 2 * GP;
+        float* gr = grad + row * 2 * GP;
+        float pred = 0.f, drs[8];
+        for (int k = 0; k < P; ++k) {
+            float r, dr;
+            phi_dphi(__fsub_rn(__ldg(yr + g * P + k), __ldg(yr + GP + g * P + k)), r, dr);
+            if (k < 8) drs[k] = dr;
+            pred = __fadd_rn(pred, w ? __fmul_rn(r, __ldg(w + k)) : r);
+        }
+        const long long t = row / B, b = row - t * B;
+        const float d = __fsub_rn(pred, __ldg(target + t * st_t + b * st_b + g * st_g));
+        const float ad = fabsf(d);
+        float dl;
+        if (ad < beta) { local += 0.5 * (double)d * (double)d / (double)beta; dl = d / beta; }
+        else { local += (double)ad - 0.5 * (double)beta; dl = d > 0.f ? 1.f : -1.f; }
+        dl *= inv_count;
+        for (int k = 0; k < P; ++k) {
+            float dr;
+            if (k < 8) dr = drs[k];
+            else { float r; phi_dphi(__fsub_rn(__ldg(yr + g * P + k), __ldg(yr + GP + g * P + k)), r, dr); }
+            const float gv = dl * dr * (w ? __ldg(w + k) : 1.f);
+            gr[g * P + k] = gv;
+            gr[GP + g * P + k] = -gv;
+        }
+    }
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        atomicAdd(acc, s);
+    }
+}
+
+__global__ void k_loss_finalize(const double* __restrict__ acc, double inv_count, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *loss = (float)(*acc * inv_count);
+}
+
+int launch_huber_rate_loss(const float* y_sel, int T, int B, int G, int P, const float* w, const float* target,
+                           long long st_t, long long st_b, long long st_g, float beta, float* loss, float* grad,
+                           double* acc, cudaStream_t s) {
+    const long long rows = (long long)T * B;
+    const double count = (double)rows * G;
+    if (cudaMemsetAsync(acc, 0, sizeof(double), s) != cudaSuccess) return ODECOL_E_CUDA;
+    const long long want = (rows * G + 255) / 256;
+    const int blocks = (int)(want < 148LL * 16 ? (want < 1 ? 1 : want) : 148LL * 16);      // 16 resident CTAs on each of 148 SMs
+    k_huber_rate_loss<<<blocks, 256, 0, s>>>(y_sel, rows, B, G, P, w, target, st_t, st_b, st_g, beta, (float)(1.0 / count), grad, acc);
+    k_loss_finalize<<<1, 32, 0, s>>>(acc, 1.0 / count, loss);
+    count_launch(2);
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+}  // namespace odecol

@@ -362,6 +362,29 @@ torch::Tensor ww_generate(const torch::Tensor& mu, std::optional<torch::Tensor> 
     return states;
 }
 
+// fused read-out loss: returns {loss (0-d), grad_y_sel}
+std::vector<torch::Tensor> huber_rate_loss(const torch::Tensor& y_sel, const torch::Tensor& target, int64_t P,
+                                           std::optional<torch::Tensor> w, double beta) {
+    c10::cuda::CUDAGuard g(y_sel.device());
+    want(y_sel, "y_sel");
+    TORCH_CHECK(y_sel.dim() == 3 && P >= 1 && y_sel.size(2) % (2 * P) == 0, "odecol: y_sel must be (T, B, 2*G*P)");
+    const int64_t T = y_sel.size(0), B = y_sel.size(1), G = y_sel.size(2) / (2 * P);
+    TORCH_CHECK(target.is_cuda() && target.scalar_type() == torch::kFloat32 && target.dim() == 3, "odecol: target must be a 3-d float32 CUDA tensor");
+    TORCH_CHECK((target.size(0) == T || target.size(0) == 1) && (target.size(1) == B || target.size(1) == 1) &&
+                (target.size(2) == G || target.size(2) == 1), "odecol: target must broadcast to (T, B, G)");
+    const float* wp = nullptr;
+    if (w.has_value()) { want(*w, "w"); TORCH_CHECK(w->numel() == P, "odecol: w must have P entries"); wp = w->data_ptr<float>(); }
+    auto st = [&](int d) { return target.size(d) == 1 ? (int64_t)0 : target.stride(d); };
+    auto loss = torch::empty({}, y_sel.options());
+    auto grad = torch::empty_like(y_sel);
+    auto ws = torch::empty({1}, y_sel.options().dtype(torch::kFloat64));
+    check(odecol_huber_rate_loss(y_sel.data_ptr<float>(), (int32_t)T, (int32_t)B, (int32_t)G, (int32_t)P, wp,
+                                 target.data_ptr<float>(), st(0), st(1), st(2), (float)beta, loss.data_ptr<float>(),
+                                 grad.data_ptr<float>(), ws.data_ptr(), sizeof(double),
+                                 at::cuda::getCurrentCUDAStream(y_sel.device().index()).stream()), "huber_rate_loss");
+    return {loss, grad};
+}
+
 torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
     c10::cuda::CUDAGuard g(A.device());
     want(A, "A"); want(B, "B");
@@ -421,6 +444,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("srk_fwd", &srk_fwd);
     m.def("srk_bwd", &srk_bwd);
     m.def("ww_generate", &ww_generate);
+    m.def("huber_rate_loss", &huber_rate_loss);
     m.def("tc_contract", &tc_contract);
     m.def("tc_contract_tn", &tc_contract_tn);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;

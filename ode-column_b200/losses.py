@@ -28,6 +28,38 @@ def huber_loss_wta(pred_states: torch.Tensor, true: torch.Tensor, network) -> to
     return torch.nn.functional.smooth_l1_loss(both, true, beta=1.0)
 
 
+class _HuberRateLoss(torch.autograd.Function):
+    """loss and d loss / d trajectory in one fused pass (include/odecol.h: odecol_huber_rate_loss)."""
+
+    @staticmethod
+    def forward(ctx, y_sel, target, P, w, beta):
+        from . import _native
+        loss, grad = _native.ext().huber_rate_loss(y_sel.detach().contiguous(), target.detach(), int(P),
+                                                   None if w is None else w.detach().to(torch.float32).contiguous(), float(beta))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None, None, None
+
+
+def huber_rate_loss(y_sel: torch.Tensor, target: torch.Tensor, pops_per_group: int = 1, weights=None,
+                    beta: float = 1.0) -> torch.Tensor:
+    """Fused ``smooth_l1_loss(sum_k w_k phi(V - A), target)`` on a trajectory restricted to read-out populations.
+
+    ``y_sel`` (T, B, 2*G*P) as returned by ``odeint(..., components=cat(pops, N + pops))``: V of the G*P read-out
+    populations (G groups of P consecutive ones) followed by their A; ``target`` broadcastable to (T, B, G).  Equals
+    the reference's huber_loss_wta reduction (src/utils.py:74-88) -- one kernel computes the loss and its gradient
+    w.r.t. ``y_sel`` (no gradient flows to ``target`` / ``weights``).  CUDA only."""
+    if not y_sel.is_cuda:
+        raise RuntimeError("odecol: huber_rate_loss is a fused CUDA read-out (no CPU path)")
+    if target.dim() != 3:
+        raise ValueError("odecol: target must be 3-d and broadcastable to (T, B, G)")
+    return _HuberRateLoss.apply(y_sel, target.to(y_sel.device, torch.float32), pops_per_group, weights, beta)
+
+
 def xor_readout(traj: torch.Tensor, network) -> torch.Tensor:
     """traj (T, B, 72) -> final L2/3e rate of column C per trial (scripts/xor_ode.py:120-125)."""
     rate = compute_firing_rate(traj[-1, :, 16:24] - traj[-1, :, 40:48])
