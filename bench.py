@@ -392,7 +392,7 @@ def run_ours(args):
 
 def run_c5(args):
     """BASELINE.json configs[4]: 1,024-column network (N = 8192, dense W on the tensor cores), sweep of
-    8192 members differing in stimulus amplitude, stochastic adaptive Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3,
+    8192 members differing in stimulus amplitude and noise amplitude (sigma in [0, 20]), stochastic adaptive Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3,
     dt_min 1e-5, in-kernel Philox seed 0), members sharded over the GPUs (strong scaling, no collective).  One step =
     one solve over --c5-horizon simulated seconds; the unit is one population advanced by one ATTEMPTED step."""
     import torch
@@ -411,6 +411,8 @@ def run_c5(args):
     net = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device=dev)
     g = torch.Generator(device="cpu").manual_seed(2000)
     amp = (torch.rand(args.c5_trials, 1, generator=g) * 30.0)[lo:hi].expand(B, cols).contiguous()
+    # second sweep axis: the noise amplitude, sigma in [0, 20] (SyntheticColumnSheet carries sigma_V = 10)
+    sigma_scale = (torch.rand(args.c5_trials, generator=g) * 2.0)[lo:hi].contiguous().to(dev)
     kt = torch.tensor([0.0, 1.0], device=dev)
     ku = torch.stack((amp, amp), dim=1).to(dev)                  # constant stimulus, per-member amplitude
     net.set_knots(kt, ku)
@@ -421,7 +423,7 @@ def run_c5(args):
         st = {}
         with torch.no_grad():
             y = odecol.sdeint(net, y0, ts, method="euler", dt=1e-3, adaptive=True, rtol=1e-5, atol=1e-4, dt_min=1e-5,
-                              seed=0, trial_offset=lo, stats=st)
+                              seed=0, trial_offset=lo, stats=st, options={"sigma_scale": sigma_scale})
         return y, st, ext.last_launch_count()
 
     for _ in range(args.warmup):

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ODECOL_ABI_VERSION 1
+#define ODECOL_ABI_VERSION 2
 
 enum {
     ODECOL_OK = 0,
@@ -99,6 +99,9 @@ typedef struct odecol_problem {
                              between, held beyond the ends (src/utils.py:31-46)              */
     int64_t knot_stride_b;/* floats between consecutive trials in knot_u (0 = shared)        */
     float tau_s, tau_m, tau_a, resistance;
+    const float* sigma_scale; /* [B] per-trial factor on sigma, or NULL (1): the noise-amplitude axis of a
+                                 parameter sweep (each trial integrates with g = sigma_scale[b] * sigma);
+                                 read by the stochastic entry points only (ABI v2)                   */
 } odecol_problem;
 
 int odecol_abi_version(void);

@@ -17,6 +17,7 @@ struct DevProblem {
     const float* W_aug;
     const float* kappa;
     const float* sigma;
+    const float* sigma_scale;   // [B] or NULL
     const float* knot_t;
     const float* knot_u;
     long long knot_stride_b;

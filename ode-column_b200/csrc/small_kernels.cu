@@ -688,6 +688,7 @@ __global__ void __launch_bounds__(128) k_em_fwd_small(DevProblem p, const float*
         st3(y_out + b * row, N, i, y[0], y[1], y[2]);
         if (y_steps) st3(y_steps + b * row, N, i, y[0], y[1], y[2]);
         if (p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+        if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + b); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
     }
     const float t_begin = __ldg(ts), t_end = __ldg(ts + T - 1);
     const float span = t_end - t_begin;
@@ -1057,6 +1058,7 @@ __global__ void __launch_bounds__(128) k_srk_fwd_small(DevProblem p, const float
         st3(y_out + b * row, N, i, y[0], y[1], y[2]);
         if (y_steps) st3(y_steps + b * row, N, i, y[0], y[1], y[2]);
         if (p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+        if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + b); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
     }
     const float t_end = __ldg(ts + T - 1);
     float curr_t = __ldg(ts), prev_t = curr_t;
@@ -1133,6 +1135,7 @@ __global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, cons
     const unsigned long long trial = (unsigned long long)(trial_offset + b);
     float sg[3] = {0.f, 0.f, 0.f};
     if (cx.act && p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+    if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + b); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
     auto gcomp = [&](int j, int c) -> float { return gi[c] >= 0 ? grad_y[((size_t)j * B + b) * G + gi[c]] : 0.f; };
     float lam[3] = {0.f, 0.f, 0.f};      // adjoint of solver state k+1 while processing step k
     float pend[3] = {0.f, 0.f, 0.f};     // contributions destined for state k (from interpolated outputs)

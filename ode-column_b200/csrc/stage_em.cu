@@ -93,7 +93,7 @@ __global__ void k_em_step(EmStepArgs a) {
             const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)a.kstep, 0x80000000u | (uint32_t)(a.kstep >> 32));
             dw = sqrtf(h) * normal_from_bits(bits.x, bits.y);
         }
-        const float sg = a.p.sigma ? __ldg(a.p.sigma + comp) : 0.f;
+        const float sg = (a.p.sigma ? __ldg(a.p.sigma + comp) : 0.f) * (a.p.sigma_scale ? __ldg(a.p.sigma_scale + b) : 1.f);
         const float y0 = a.y[e];
         const float y1 = __fadd_rn(__fadd_rn(y0, __fmul_rn(a.f[e], h)), __fmul_rn(sg, dw));
         a.y_prev[e] = y0;
@@ -147,7 +147,7 @@ __global__ void k_ad_half1(DevProblem p, TrialState s, const float* __restrict__
         if (!s.active[b]) continue;
         const float tc = s.t_cur[b], tm = s.t_mid[b], tn = s.t_next[b];
         const float h = __fsub_rn(tn, tc), h1 = __fsub_rn(tm, tc);
-        const float sg = p.sigma ? __ldg(p.sigma + comp) : 0.f;
+        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * (p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f);
         const float y0 = y[e], f = f0[e];
         y_full[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, s.dw_full[b]));
         y_mid[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, s.dw_1[b]));
@@ -165,7 +165,7 @@ __global__ void k_ad_half2(DevProblem p, TrialState s, const float* __restrict__
     double acc = 0.0;
     for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
         const size_t e = (size_t)b * 3 * N + comp;
-        const float sg = p.sigma ? __ldg(p.sigma + comp) : 0.f;
+        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * (p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f);
         const float yh = __fadd_rn(__fadd_rn(y_mid[e], __fmul_rn(fm[e], h2)), __fmul_rn(sg, dw2));
         y_half[e] = yh;
         const float yf = y_full[e];

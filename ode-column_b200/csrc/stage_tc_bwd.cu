@@ -500,9 +500,9 @@ __global__ void k_tc_untile(DevProblem p, TileGeom tg, const float* __restrict__
 }
 
 // constant-one column (the bias input) of the four stacked operand buffers
-__global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, int col) {
+__global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, int col, int nslots) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 4 * B) return;
+    if (e >= nslots * B) return;
     const int s = e / B, b = e % B;
     Rhi[((size_t)s * Bp + b) * KPa + col] = 1.0f;
 }
@@ -656,7 +656,7 @@ __global__ void k_split_pad_T(const float* __restrict__ src, int n, int ld, floa
 struct TcBwdLayout {
     int Np, Bp, KPa, NPk, TN;
     size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo;   // stacked x4 operand buffers
-    size_t off_K[3], off_Y, off_RT[3], off_DRT[4], off_lam, off_b4, off_b3, off_acur, off_inv, off_done, total;
+    size_t off_K[3], off_Y, off_RT[3], off_DRT[8], off_lam, off_b4, off_b3, off_acur, off_inv, off_done, total;
 };
 
 static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
@@ -670,13 +670,15 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
     L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
     L.off_WThi = take(4ull * L.Np * L.NPk); L.off_WTlo = take(4ull * L.Np * L.NPk);
-    L.off_Rhi = take(16ull * L.Bp * L.KPa); L.off_Rlo = take(16ull * L.Bp * L.KPa);
+    // two sets of the four stacked r_aug operands and of the four phi' planes: in checkpoint mode the replay of step
+    // n-1 (side stream) fills one set while the reverse stages and the dW contraction of step n read the other
+    L.off_Rhi = take(32ull * L.Bp * L.KPa); L.off_Rlo = take(32ull * L.Bp * L.KPa);
     L.off_AVhi = take(32ull * L.Bp * L.NPk); L.off_AVlo = take(32ull * L.Bp * L.NPk);     // two sets of four slots
     const size_t plane = 4ull * L.Np * L.Bp;
     for (int i = 0; i < 3; ++i) L.off_K[i] = take(plane);
     L.off_Y = take(3 * plane);
     for (int i = 0; i < 3; ++i) L.off_RT[i] = take(plane);
-    for (int i = 0; i < 4; ++i) L.off_DRT[i] = take(plane);
+    for (int i = 0; i < 8; ++i) L.off_DRT[i] = take(plane);
     L.off_lam = take(3 * plane); L.off_b4 = take(2 * plane); L.off_b3 = take(2 * plane); L.off_acur = take(2 * plane);
     L.off_inv = take(sizeof(int) * 3ull * p.N);
     L.off_done = take(sizeof(unsigned int) * (size_t)(L.Bp / L.TN) + 256);
@@ -737,7 +739,8 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     float* KT[3] = {F(L.off_K[0]), F(L.off_K[1]), F(L.off_K[2])};
     float* YT = F(L.off_Y);
     float* RT[3] = {F(L.off_RT[0]), F(L.off_RT[1]), F(L.off_RT[2])};
-    float* DRT[4] = {F(L.off_DRT[0]), F(L.off_DRT[1]), F(L.off_DRT[2]), F(L.off_DRT[3])};
+    float* DRT[8];
+    for (int k = 0; k < 8; ++k) DRT[k] = F(L.off_DRT[k]);
     float *lamT = F(L.off_lam), *b4T = F(L.off_b4), *b3T = F(L.off_b3), *acurT = F(L.off_acur);
     int* inv = reinterpret_cast<int*>(w + L.off_inv);
     const int Kaug = p.N + p.n_in + 1;
@@ -750,7 +753,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_K[0] - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
     k_split_pad_T<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, WThi, WTlo, L.Np, L.NPk);
-    k_tc_set_one<<<(4 * p.B + 255) / 256, 256, 0, s>>>(Rhi, L.Bp, p.B, L.KPa, Kaug - 1);
+    k_tc_set_one<<<(8 * p.B + 255) / 256, 256, 0, s>>>(Rhi, L.Bp, p.B, L.KPa, Kaug - 1, 8);
     k_tc_build_inv<<<1, 256, 0, s>>>(sel, G, 3 * p.N, inv);
     const size_t first = (size_t)(((T - 2) & 1) * 4 + 3);       // operand sets alternate per step: step n uses set n & 1
     k_tc_bwd_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, grad_y, inv, G, t_dev, T, gamma, lamT, acurT, AVhi + first * astride,
@@ -759,7 +762,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     if (cudaMemsetAsync(done, 0, sizeof(unsigned int) * (size_t)(L.Bp / L.TN), s) != cudaSuccess) return ODECOL_E_CUDA;
     count_launch(5);
 
-    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo, dAhi[2], dAlo[2], dBhi, dBlo;
+    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo, dAhi[2], dAlo[2], dBhi[2], dBlo[2];
     bool ok = make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) && make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) &&
               make_map(&mWThi, WThi, L.Np, L.NPk, L.NPk, BM) && make_map(&mWTlo, WTlo, L.Np, L.NPk, L.NPk, BM) &&
               make_map(&mRhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, L.TN) &&
@@ -768,8 +771,10 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
               make_map(&dAlo[0], AVlo, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
               make_map(&dAhi[1], AVhi + 4 * astride, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
               make_map(&dAlo[1], AVlo + 4 * astride, 4ull * L.Bp, L.NPk, L.NPk, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-              make_map(&dBhi, Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-              make_map(&dBlo, Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+              make_map(&dBhi[0], Rhi, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dBlo[0], Rlo, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dBhi[1], Rhi + 4 * rstride, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+              make_map(&dBlo[1], Rlo + 4 * rstride, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (!ok) return ODECOL_E_CUDA;
 
     // dW launch shape: output tiles x splits of the stacked rows, about three waves of CTAs
@@ -802,13 +807,45 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_tc_bwd_chain, kThreads, chain_smem) != cudaSuccess || max_blocks < 1)
             use_chain = false;
     }
+    // Checkpoint mode: the replay of a step needs nothing but the checkpoints, so it runs one step AHEAD of the
+    // contractions on a side stream, into the other operand / phi' set: replay(n-1) overlaps the reverse stages and the
+    // dW contraction of step n (it fits next to their CTAs: 8 K registers and no shared memory per CTA).
+    //   side: wait(dW(n+1) done) -> replay(n-1) -> record          main: wait(replay(n) done) -> chain(n) -> dW(n) -> record
+    // ODECOL_OVERLAP=0 keeps everything on the caller's stream.
+    const char* ov = getenv("ODECOL_OVERLAP");
+    bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : true);
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_replay = nullptr, ev_dw = nullptr;
+    if (overlap) {
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_replay, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_dw, cudaEventDisableTiming) != cudaSuccess) {
+            if (side) cudaStreamDestroy(side);
+            if (ev_replay) cudaEventDestroy(ev_replay);
+            cudaGetLastError();
+            side = nullptr; overlap = false;
+        }
+    }
+    const size_t ckpl = (size_t)L.Np * L.Bp;
+    auto replay = [&](int n, cudaStream_t st_) {
+        const int rs = overlap ? (n & 1) : 0;
+        k_tc_replay<<<L.Bp / 4, 128, 0, st_>>>(p, tg, ckVA + 2 * ckpl * (size_t)n, ckK + 3 * ckpl * (size_t)n, t_dev, n,
+                                               Rhi + (size_t)rs * 4 * rstride, Rlo + (size_t)rs * 4 * rstride, rstride,
+                                               DRT[4 * rs + 0], DRT[4 * rs + 1], DRT[4 * rs + 2], DRT[4 * rs + 3], L.KPa);
+        count_launch();
+    };
+    if (overlap) {                                   // setup on the caller's stream first, then the first replay
+        cudaEventRecord(ev_dw, s);
+        cudaStreamWaitEvent(side, ev_dw, 0);
+        replay(T - 2, side);
+        cudaEventRecord(ev_replay, side);
+    }
     for (int n = T - 2; n >= 0; --n) {
         int rc = ODECOL_OK;
+        const int rset = overlap ? (n & 1) : 0;      // operand / phi' set of this step
         if (ckVA) {
-            const size_t pl = (size_t)L.Np * L.Bp;
-            k_tc_replay<<<L.Bp / 4, 128, 0, s>>>(p, tg, ckVA + 2 * pl * (size_t)n, ckK + 3 * pl * (size_t)n, t_dev, n, Rhi, Rlo,
-                                                 rstride, DRT[0], DRT[1], DRT[2], DRT[3], L.KPa);
-            count_launch();
+            if (overlap) cudaStreamWaitEvent(s, ev_replay, 0);
+            else replay(n, s);
         } else {
         const float* yn = y_traj + (size_t)n * st;
         k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT[0], DRT[0], L.KPa);
@@ -835,7 +872,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             BwdChainArgs a;
             a.p = p; a.tg = tg; a.ts = TileShape{MT, NT, L.TN, L.NPk / BK, 0, nullptr}; a.t = t_dev; a.n = n; a.NPk = L.NPk; a.G = G;
             a.Bp = L.Bp; a.acurT = acurT; a.lamT = lamT; a.b4T = b4T; a.b3T = b3T;
-            for (int k = 0; k < 4; ++k) a.DRT[k] = DRT[k];
+            for (int k = 0; k < 4; ++k) a.DRT[k] = DRT[4 * rset + k];
             a.AVhi = AVhi; a.AVlo = AVlo; a.set = set; a.grad_y = grad_y; a.inv = inv; a.gamma = gamma;
             a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
             a.done = done; a.done_base = (unsigned int)MT * 4u * (unsigned int)(T - 2 - n);
@@ -846,7 +883,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         } else {
             auto fill_b = [&](auto& e, int S) {
                 e.p = p; e.tg = tg; e.t = t_dev; e.n = n; e.NPk = L.NPk; e.G = G;
-                e.acurT = acurT; e.lamT = lamT; e.b4T = b4T; e.b3T = b3T; e.DRT = DRT[S - 1];
+                e.acurT = acurT; e.lamT = lamT; e.b4T = b4T; e.b3T = b3T; e.DRT = DRT[4 * rset + S - 1];
                 const size_t nxt = S == 1 ? (size_t)((set ^ 1) * 4 + 3) : (size_t)(set * 4 + S - 2);   // slot the epilogue writes
                 e.AVhi_nxt = AVhi + nxt * astride; e.AVlo_nxt = AVlo + nxt * astride;
                 e.grad_y = grad_y; e.inv = inv; e.gamma = gamma;
@@ -859,8 +896,19 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
             { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         }
-        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi, dBlo, ds);
+        if (overlap && n > 0) {                      // replay(n-1) may start once dW(n+1) has released its set
+            cudaStreamWaitEvent(side, ev_dw, 0);
+            replay(n - 1, side);
+            cudaEventRecord(ev_replay, side);
+        }
+        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds);
         count_launch();
+        if (overlap) cudaEventRecord(ev_dw, s);
+    }
+    if (side) {                                      // every replay has been awaited by the caller's stream
+        cudaEventDestroy(ev_replay);
+        cudaEventDestroy(ev_dw);
+        cudaStreamDestroy(side);
     }
     if (grad_y0) {
         k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);

@@ -21,7 +21,7 @@ void want(const torch::Tensor& t, const char* name, c10::ScalarType dt = torch::
 }
 
 struct Problem {
-    torch::Tensor W_aug, kappa, sigma, knot_t, knot_u;
+    torch::Tensor W_aug, kappa, sigma, knot_t, knot_u, sigma_scale;
     bool has_sigma = false;
     odecol_problem p{};
 
@@ -49,6 +49,15 @@ struct Problem {
         p.knot_t = knot_t.data_ptr<float>(); p.knot_u = knot_u.data_ptr<float>();
         p.knot_stride_b = knot_u.size(0) == 1 ? 0 : knot_u.size(1) * knot_u.size(2);
         p.tau_s = (float)tau_s; p.tau_m = (float)tau_m; p.tau_a = (float)tau_a; p.resistance = (float)R;
+    }
+
+    // per-trial factor on sigma (the noise axis of a parameter sweep); undefined tensor = none
+    void set_sigma_scale(std::optional<torch::Tensor> sc) {
+        if (!sc.has_value()) { sigma_scale = torch::Tensor(); p.sigma_scale = nullptr; return; }
+        want(*sc, "sigma_scale");
+        TORCH_CHECK(sc->numel() == p.B, "odecol: sigma_scale must have B entries");
+        sigma_scale = *sc;
+        p.sigma_scale = sigma_scale.data_ptr<float>();
     }
 
     torch::TensorOptions fopts() const { return W_aug.options(); }
@@ -420,6 +429,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                       int64_t, double, double, double, double, int64_t>(),
              py::arg("W_aug"), py::arg("kappa"), py::arg("sigma"), py::arg("knot_t"), py::arg("knot_u"), py::arg("n_in"),
              py::arg("B"), py::arg("tau_s"), py::arg("tau_m"), py::arg("tau_a"), py::arg("resistance"), py::arg("flags") = 0)
+        .def("set_sigma_scale", &Problem::set_sigma_scale)
         .def_property_readonly("N", &Problem::N)
         .def_property_readonly("B", &Problem::B)
         .def("kernel_family", [](const Problem& pr, int op) { return odecol_kernel_family(&pr.p, op); })

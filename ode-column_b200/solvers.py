@@ -64,11 +64,15 @@ class _Setup:
         self.flags = {None: 0, "staged": self.ext.FLAG_FORCE_STAGED, "tensor": self.ext.FLAG_FORCE_TENSOR}[family]
         self.kappa = self.lf.kappa.detach().to(dev, torch.float32).contiguous()
         self.sigma = self.lf.sigma.detach().to(dev, torch.float32).contiguous()
+        self.sigma_scale = None       # (B,) per-trial factor on sigma, set by sdeint(options={'sigma_scale': ...})
 
     def problem(self, W_aug: torch.Tensor):
         lf = self.lf
-        return self.ext.Problem(W_aug.detach().to(torch.float32).contiguous(), self.kappa, self.sigma, self.knot_t,
+        prob = self.ext.Problem(W_aug.detach().to(torch.float32).contiguous(), self.kappa, self.sigma, self.knot_t,
                                 self.knot_u, lf.n_in, self.B, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, self.flags)
+        if self.sigma_scale is not None:
+            prob.set_sigma_scale(self.sigma_scale)
+        return prob
 
 
 def _sel_tensors(components, N3, device):
@@ -256,7 +260,9 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     or (n_steps, B, 1) of increments in step order (bit-parity mode, fixed step) -- for 'srk' a pair ``(W, U)`` of such
     tensors, U the space-time Levy area of each step; or a torchsde-style callable ``bm(t0, t1)`` /
     ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` (Euler only) uses step
-    doubling with torchsde's controller, per trial, on a virtual Brownian tree (Philox only)."""
+    doubling with torchsde's controller, per trial, on a virtual Brownian tree (Philox only).
+    ``options['sigma_scale']``: (B,) per-trial factor on the diffusion -- the noise-amplitude axis of a parameter sweep
+    (trial b integrates with g = sigma_scale[b] * diffusion); ``options['family']`` as in ``odeint``."""
     if logqp or extra or extra_solver_state is not None:
         raise NotImplementedError("odecol: logqp / extra solver state are not part of the fused path")
     method = method or "srk"
@@ -268,7 +274,13 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     if getattr(sde, "noise_type", "scalar") != "scalar" or getattr(sde, "sde_type", "ito") != "ito":
         raise ValueError("odecol: only scalar-noise Ito SDEs (what the reference declares) are supported")
     options = dict(options or {})
+    sigma_scale = options.pop("sigma_scale", None)
     setup = _Setup(sde, y0, ts, options.pop("family", None))
+    if sigma_scale is not None:
+        sc = torch.as_tensor(sigma_scale, dtype=torch.float32).to(y0.device).reshape(-1).contiguous()
+        if sc.numel() != setup.B:
+            raise ValueError(f"odecol: options['sigma_scale'] needs {setup.B} entries (one per trial), got {sc.numel()}")
+        setup.sigma_scale = sc
     sel_long, sel_i32 = _sel_tensors(components, 3 * setup.lf.N, y0.device)
     ext = setup.ext
     if seed is None:

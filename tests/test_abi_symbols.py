@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.odecol_abi_version() == 1
+    assert lib.odecol_abi_version() == 2
     lib.odecol_strerror.restype = ctypes.c_char_p
     assert lib.odecol_strerror(0) == b"ok"
     assert b"workspace" in lib.odecol_strerror(-4)
@@ -61,7 +61,7 @@ def test_em_num_steps_matches_oracle_schedule(lib):
 def test_torch_extension_imports_without_gpu():
     import odecol
     e = odecol._native.ext()
-    assert e.abi_version() == 1
+    assert e.abi_version() == 2
     with pytest.raises(RuntimeError):
         # CPU tensors are refused: there is no CPU path
         e.Problem(torch.zeros(8, 12), torch.zeros(8), None, torch.zeros(2), torch.zeros(1, 2, 1), 1, 1, 5e-4, 0.02, 10.0, 80.0, 0)
