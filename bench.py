@@ -44,8 +44,10 @@ def parse():
     ap.add_argument("--cpu-time-points", type=int, default=41, help="grid points of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--family", default=None, help="force a kernel family (staged, tensor)")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
-                    help="c4 (default, the headline): N=512 rk4 forward+adjoint; c5: N=8192 adaptive Euler-Maruyama sweep")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "small"],
+                    help="c4 (default, the headline): N=512 rk4 forward+adjoint; c5: N=8192 adaptive Euler-Maruyama sweep; "
+                         "small: the reference's own WTA / parity networks at large batch (persistent on-chip family)")
+    ap.add_argument("--small-trials", type=int, default=65536, help="trials per GPU of the small workload (WTA; parity uses a quarter)")
     ap.add_argument("--c5-columns", type=int, default=1024)
     ap.add_argument("--c5-trials", type=int, default=8192, help="sweep members in total (strong scaling over GPUs)")
     ap.add_argument("--c5-horizon", type=float, default=0.004, help="simulated seconds per step of the c5 workload")
@@ -479,6 +481,129 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
+def run_small(args):
+    """The reference's own networks (BASELINE.json configs[0..2] sizes: WTA N=16, parity N=104) at large batch on the
+    persistent on-chip kernel family: one CTA integrates one trial through the whole time loop.  Reports, per case,
+    population-steps/s and the fraction of min(HBM with the (T,B,3N) trajectory materialised, FP32 FFMA) -- SURVEY.md 8d."""
+    import torch
+    import odecol
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ext = odecol._native.ext()
+    cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6457.0)
+    ffma_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    torch.manual_seed(0)
+
+    def move(net):
+        net = net.to(dev)
+        for m in [net] + list(net.modules()):
+            for k, v in list(vars(m).items()):
+                if torch.is_tensor(v) and not isinstance(v, torch.nn.Parameter):
+                    setattr(m, k, v.to(dev))
+        return net
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
+
+    cases = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = 0
+    for name in ("wta", "parity"):
+        if name == "wta":
+            net = move(odecol.ColumnAreaWTA(cfg, "mt"))
+            N, n_in, T, dt, B = 16, 16, 1500, 1e-4, args.small_trials
+            amp = torch.zeros(B, 16)
+            g = torch.Generator().manual_seed(3000)
+            a = torch.rand(B, 2, generator=g) * 30.0
+            amp[:, 2] = amp[:, 3] = a[:, 0]; amp[:, 10] = amp[:, 11] = a[:, 1]
+            read = torch.tensor([0, 8])                                   # L2/3e of both columns
+        else:
+            nd = {"nr_areas": 3, "areas": ["mt"] * 3, "nr_columns_per_area": [8, 4, 1], "nr_input_units": 4}
+            net = move(odecol.ColumnNetwork(cfg, nd, torch.device("cpu")))
+            N, n_in, T, dt, B = 104, 4, 1000, 1e-3, max(1, args.small_trials // 4)
+            g = torch.Generator().manual_seed(3001)
+            amp = (torch.rand(B, 4, generator=g) > 0.5).float() * 15.0
+            read = torch.tensor([96])                                     # L2/3e of the output column
+        t_end = T * dt
+        grid = t_end / (T - 1)
+        kt, ku = odecol.step_knots((T // 3) * grid, (2 * (T // 3)) * grid, t_end, amp, grid)
+        net.time_vec, net.stim = kt.to(dev), (ku.to(dev) if name == "wta" else ku.to(dev))
+        tv = torch.linspace(0.0, t_end, T, device=dev)
+        y0 = torch.zeros(B, 3 * N, device=dev)
+        sel = torch.cat((read, read + N)).to(dev)
+        target = torch.full((1, 1, len(read)), 0.5, device=dev)
+        params = [p for p in net.parameters() if p.requires_grad]
+        kaug = N + n_in + 1
+        res = {"populations": N, "trials": B, "time_points": T}
+
+        def fwd():
+            with torch.no_grad():
+                return odecol.odeint(net, y0, tv, method="rk4")
+
+        def fwd_adj():
+            for p in params:
+                p.grad = None
+            y = odecol.odeint(net, y0, tv, method="rk4", components=sel)
+            odecol.huber_rate_loss(y, target, 1).backward()
+
+        sec = timed(fwd, args.steps)
+        launches += ext.last_launch_count() * (args.steps + 1)
+        ps = N * B * (T - 1) / sec
+        flops = 4 * (2 * kaug + 24) + 48                                  # per population-step (SURVEY 8d)
+        res["rk4_forward"] = {"pop_steps_per_sec": ps, "ms": 1e3 * sec,
+                              "hbm_gbs_trajectory": 12.0 * ps / 1e9, "hbm_frac": 12.0 * ps / 1e9 / hbm_peak,
+                              "fp32_tflops": flops * ps / 1e12, "fp32_frac": flops * ps / 1e12 / ffma_peak}
+        sec = timed(fwd_adj, args.steps)
+        ps = N * B * (T - 1) / sec
+        res["rk4_forward_adjoint"] = {"pop_steps_per_sec": ps, "ms": 1e3 * sec}
+        if name == "wta":
+            def srk():
+                for p in params:
+                    p.grad = None
+                y = odecol.sdeint(net, y0, tv, method="srk", dt=1e-3, seed=0, components=sel,
+                                  options={"sigma_scale": torch.full((B,), 0.1)})
+                odecol.huber_rate_loss(y, target, 1).backward()
+            sec = timed(srk, args.steps)
+            n_steps = ext.em_num_steps(tv.cpu(), 1e-3)
+            res["srk_forward_adjoint"] = {"pop_steps_per_sec": N * B * n_steps / sec, "ms": 1e3 * sec, "solver_steps": n_steps}
+        cases[name] = res
+        del net
+        torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    w = cases["wta"]
+    bound = min(("hbm", w["rk4_forward"]["hbm_frac"]), ("fp32", w["rk4_forward"]["fp32_frac"]), key=lambda kv: -kv[1])
+    print(json.dumps({
+        "metric": METRIC, "value": w["rk4_forward_adjoint"]["pop_steps_per_sec"], "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": 1, "ms_per_step": w["rk4_forward_adjoint"]["ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "small: reference WTA network (N=16, T=1500) and parity network (N=104, T=1000) at large "
+                               "batch, persistent on-chip family (one CTA per trial, whole time loop in one launch)",
+                   "l2": "trajectories (18.9 GB / 20.4 GB) larger than L2"},
+        "clocks": clocks, "gpu_launches": launches, "cases": cases,
+        "roofline": {"bound": "hbm", "kernel": "k_rk4_fwd_small<40> (WTA, full (T,B,3N) trajectory written: 12 B per population-step)",
+                     "achieved": w["rk4_forward"]["hbm_gbs_trajectory"], "peak": hbm_peak, "unit": "GB/s",
+                     "frac": w["rk4_forward"]["hbm_frac"], "traffic": None,
+                     "fp32_view": {"achieved_tflops": w["rk4_forward"]["fp32_tflops"], "peak_tflops": ffma_peak,
+                                   "frac": w["rk4_forward"]["fp32_frac"]}, "binding": bound[0]},
+    }))
+
+
 def net_family(ext, odecol, net, y0, tv, args):
     from ode_column_b200.solvers import _Setup
     setup = _Setup(net, y0, tv, args.family)
@@ -492,6 +617,8 @@ def main():
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
+    elif args.workload == "small":
+        run_small(args)
     else:
         run_ours(args)
 
