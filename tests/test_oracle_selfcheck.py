@@ -210,3 +210,43 @@ def test_srk_strong_order_on_a_shared_brownian_path():
     # strong order 1.5 -> 2^1.5 = 2.83 per halving; Euler-Maruyama (additive noise, order 1) -> 2
     assert 2.45 < ratio < 3.3, (errs, ratio)
     assert 1.7 < ratio_em < 2.3 and errs[0] < 0.2 * errs_em[0], (errs_em, errs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# independent third-party anchor that IS installed: scipy's Dormand-Prince (scipy.integrate.RK45)
+# ---------------------------------------------------------------------------------------------------------------
+def test_dopri5_tableau_equals_scipy_rk45():
+    from scipy.integrate._ivp.rk import RK45
+    A = np.asarray(RK45.A)                       # (6, 5): stage rows 0..5 (row 0 empty)
+    for i, row in enumerate(S.DP_BETA[:5]):      # our rows 0..4 are scipy's rows 1..5
+        assert np.allclose(A[i + 1, :len(row)], row, rtol=0, atol=1e-16), i
+    assert np.allclose(RK45.C[1:], S.DP_ALPHA[:5], rtol=0, atol=1e-16)
+    assert np.allclose(RK45.B, S.DP_C_SOL[:6], rtol=0, atol=1e-16)       # 5th-order weights = the FSAL row
+    assert np.allclose(S.DP_BETA[5], S.DP_C_SOL[:6], rtol=0, atol=1e-16)
+    # scipy's E uses the classic 4th-order weights (5179/57600, ...), torchdiffeq's c_error Shampine's (1951/21600, ...):
+    # both embedded estimators point along the same direction, torchdiffeq's is exactly -2/3 of scipy's
+    assert np.allclose(np.asarray(RK45.E), -1.5 * np.asarray(S.DP_C_ERR), rtol=0, atol=1e-15)
+
+
+def test_dopri5_and_rk4_agree_with_scipy_on_the_column_model(cfg, golden):
+    # the reference-generated golden rk4 trajectory (WTA, dt = 1e-4) against scipy's adaptive RK45 / DOP853 at tight
+    # tolerance in float64 on the oracle's right-hand side: the restated fixed-step solver integrates the same ODE
+    from scipy.integrate import solve_ivp
+    from helpers import oracle_form, stim_table
+    from oracle import rhs as orhs
+    g = golden["wta"]
+    lf = oracle_form("wta", cfg, g)
+    tv = g["time_vec"].astype(np.float64)
+    ode = orhs.UnifiedColumnODE(lf, tv, stim_table("wta", g["stim"]), dtype=torch.float64)
+    T = 900                                       # through the stimulus onset (knot at T/3) and well into the response
+
+    def f(t, y):
+        with torch.no_grad():
+            return ode.forward(torch.tensor(t, dtype=torch.float64), torch.tensor(y)[None])[0].numpy()
+
+    sol = solve_ivp(f, (tv[0], tv[T]), np.zeros(48), method="DOP853", rtol=1e-10, atol=1e-12, t_eval=tv[[300, 600, T]],
+                    max_step=float(tv[1] - tv[0]) * 4)
+    assert sol.success
+    ref = g["rk4_traj"][[300, 600, T], 0].astype(np.float64)
+    err = np.abs(sol.y.T - ref).max() / np.abs(ref).max()
+    assert err < 5e-5, err                        # fp32 rk4 at dt = 1e-4 vs converged float64 solution
