@@ -56,6 +56,31 @@ ODECOL_DEVINL float knot_value(const float* __restrict__ kt, const float* __rest
     return __fadd_rn(y0, __fmul_rn(slope, __fsub_rn(tc, x0)));
 }
 
+// One stimulus channel per lane with the interval cached in registers: as long as the query time stays inside the knot
+// interval found last (the common case: four stage times per step, a handful of knots per trial) the lookup is two
+// compares and the interpolation y0 + slope (tc - x0); the arithmetic and its order are those of knot_value, so the
+// result is bit-identical to the uncached path.
+struct KnotLane {
+    float lo, hi;            // validity of the cached interval: lo <= tc < hi  (+-inf at the ends: held values)
+    float x0, y0, slope;
+    int idx;
+    ODECOL_DEVINL void reset() { lo = 1.0f; hi = 0.0f; idx = 1; x0 = y0 = slope = 0.0f; }   // empty interval: first query locates
+    ODECOL_DEVINL float value(const float* __restrict__ kt, const float* __restrict__ ku_trial, int K, int n_in, int ch, float t) {
+        const float tc = fminf(fmaxf(t, __ldg(kt)), __ldg(kt + K - 1));
+        if (!(lo <= tc && tc < hi)) {
+            (void)knot_locate(kt, K, t, idx);
+            x0 = __ldg(kt + idx - 1);
+            const float x1 = __ldg(kt + idx);
+            y0 = __ldg(ku_trial + (size_t)(idx - 1) * n_in + ch);
+            const float y1 = __ldg(ku_trial + (size_t)idx * n_in + ch);
+            slope = __fdiv_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+            lo = idx == 1 ? -INFINITY : x0;
+            hi = idx == K - 1 ? INFINITY : x1;
+        }
+        return __fadd_rn(y0, __fmul_rn(slope, __fsub_rn(tc, x0)));
+    }
+};
+
 // ---- elementwise drift given the total synaptic input ------------------------------------------------------------
 // total = (ff + bias + rec); reference: coupled_columns.py:225-233.
 ODECOL_DEVINL void drift(const Consts& c, float V, float A, float F, float r, float kappa, float total_raw,

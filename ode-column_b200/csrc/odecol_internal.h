@@ -40,7 +40,7 @@ void count_launch(int n = 1);
 
 // ---- family S (small_kernels.cu) ---------------------------------------------------------------------------
 int small_kp(const DevProblem& p);                 // 0 if the problem does not fit family S
-size_t small_bwd_smem_bytes(int N, int KP);
+size_t small_bwd_smem_bytes(int N, int KP, int trials_per_cta);
 int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, float* f, cudaStream_t s);
 int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
                          cudaStream_t s);

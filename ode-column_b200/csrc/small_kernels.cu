@@ -52,19 +52,28 @@ struct RowRhs {
     const float* kt;
     Consts c;
     bool act;
+    KnotLane kl;          // this lane's stimulus channel (when n_in <= blockDim.x)
 
-    ODECOL_DEVINL void init(const DevProblem& p, float* ra_smem, int b) {
-        const int i = threadIdx.x;
+    int li, lanes;        // population index of this lane within its trial; lanes per trial
+
+    // One trial per CTA (li = threadIdx.x), or -- packed mode, networks with N, n_in <= 16 -- two trials per warp:
+    // lanes 0..15 integrate trial 2*blockIdx.x, lanes 16..31 trial 2*blockIdx.x + 1, each with its own r_aug buffers.
+    ODECOL_DEVINL void init(const DevProblem& p, float* ra_smem, int b, int li_ = threadIdx.x, int sub = 0,
+                            int lanes_ = blockDim.x) {
+        li = li_; lanes = lanes_;
+        const int i = li;
         N = p.N; n_in = p.n_in; K = p.K; kt = p.knot_t; c = p.c;
-        act = i < N;
-        ra = ra_smem;
-        ku = p.knot_u + (size_t)b * p.knot_stride_b;
+        const bool row = i < N;
+        act = row && b < p.B;
+        ra = ra_smem + sub * 2 * KP;
+        ku = p.knot_u + (size_t)(b < p.B ? b : p.B - 1) * p.knot_stride_b;
         idx = 1; buf = 0;
+        kl.reset();
         const int Kaug = p.N + p.n_in + 1;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) w[k] = (act && k < Kaug) ? __ldg(p.W_aug + (size_t)i * p.ld_w + k) : 0.0f;
-        kappa = act ? __ldg(p.kappa + i) : 0.0f;
-        for (int k = i; k < 2 * KP; k += blockDim.x) ra[k] = 0.0f;
+        for (int k = 0; k < KP; ++k) w[k] = (row && k < Kaug) ? __ldg(p.W_aug + (size_t)i * p.ld_w + k) : 0.0f;
+        kappa = row ? __ldg(p.kappa + i) : 0.0f;
+        for (int k = i; k < 2 * KP; k += lanes) ra[k] = 0.0f;
         __syncthreads();
         if (i == 0) { ra[Kaug - 1] = 1.0f; ra[KP + Kaug - 1] = 1.0f; }
         __syncthreads();
@@ -74,10 +83,13 @@ struct RowRhs {
     ODECOL_DEVINL float input(float t, float r) {
         buf ^= 1;
         float* cur = ra + buf * KP;
-        if (act) cur[threadIdx.x] = r;
-        if ((int)threadIdx.x < n_in) {
-            const float tc = knot_locate(kt, K, t, idx);
-            for (int ch = threadIdx.x; ch < n_in; ch += blockDim.x) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+        if (act) cur[li] = r;
+        if (li < n_in) {
+            if (n_in <= lanes) cur[N + li] = kl.value(kt, ku, K, n_in, li, t);
+            else {
+                const float tc = knot_locate(kt, K, t, idx);
+                for (int ch = li; ch < n_in; ch += lanes) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+            }
         }
         __syncthreads();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -133,14 +145,22 @@ __global__ void k_rhs_generic(DevProblem p, const float* __restrict__ t, const f
 // ---------------------------------------------------------------------------------------------------------------
 // RK4 (3/8 rule) forward
 // ---------------------------------------------------------------------------------------------------------------
+// occupancy targets of the forward kernels: blocks are N rounded up to a warp (<= 64 threads for KP <= 64, ...); the weight
+// row alone takes KP registers, the bounds keep the compiler from trading resident CTAs for a few more
+template <int KP> struct FwdBounds {
+    static constexpr int threads = KP <= 64 ? 64 : (KP <= 96 ? 96 : 128);
+    static constexpr int blocks = KP <= 40 ? 12 : (KP <= 64 ? 8 : (KP <= 96 ? 4 : 3));
+};
+
 template <int KP>
-__global__ void __launch_bounds__(128) k_rk4_fwd_small(DevProblem p, const float* __restrict__ t, int T,
+__global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks) k_rk4_fwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y0, float* __restrict__ y_out,
-                                                       int out_every) {
-    __shared__ __align__(16) float ra[2 * KP];
-    const int b = blockIdx.x, i = threadIdx.x, N = p.N;
+                                                       int out_every, int packed) {
+    __shared__ __align__(16) float ra[4 * KP];
+    const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
+    const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N;
     RowRhs<KP> f;
-    f.init(p, ra, b);
+    f.init(p, ra, b, i, sub, packed ? 16 : (int)blockDim.x);
     const size_t row = (size_t)3 * N;
     float V = 0.f, A = 0.f, F = 0.f;
     if (f.act) {
@@ -148,6 +168,7 @@ __global__ void __launch_bounds__(128) k_rk4_fwd_small(DevProblem p, const float
         V = s.V; A = s.A; F = s.F;
         st3(y_out + b * row, N, i, V, A, F);
     }
+    int since_out = 0, out_row = 0;
     for (int n = 0; n < T - 1; ++n) {
         const float t0 = __ldg(t + n), t1 = __ldg(t + n + 1);
         const float dt = __fsub_rn(t1, t0);
@@ -173,8 +194,9 @@ __global__ void __launch_bounds__(128) k_rk4_fwd_small(DevProblem p, const float
         A = __fadd_rn(A, __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1A, __fmul_rn(3.f, __fadd_rn(k2A, k3A))), k4A), dt), 0.125f));
         F = __fadd_rn(F, __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1F, __fmul_rn(3.f, __fadd_rn(k2F, k3F))), k4F), dt), 0.125f));
         const int j = n + 1;
-        if (f.act && (j % out_every == 0 || j == T - 1)) {
-            const size_t r = (j % out_every == 0) ? (size_t)(j / out_every) : (size_t)((T - 2) / out_every + 1);
+        if (++since_out == out_every) { since_out = 0; ++out_row; }       // j % out_every == 0 without the division
+        if (f.act && (since_out == 0 || j == T - 1)) {
+            const size_t r = since_out == 0 ? (size_t)out_row : (size_t)((T - 2) / out_every + 1);
             st3(y_out + (r * p.B + b) * row, N, i, V, A, F);
         }
     }
@@ -194,18 +216,18 @@ struct BwdShared {
 };
 
 template <int KP>
-ODECOL_DEVINL BwdShared<KP> carve_bwd(float* sm, int N, int NP) {
+ODECOL_DEVINL BwdShared<KP> carve_bwd(float* sm, int N, int NP, int tpc) {
     BwdShared<KP> s;
-    s.ra = sm;                                   // 16-byte aligned
-    s.av = s.ra + kBwdSlots * KP;
-    s.Ws = s.av + 2 * NP;
+    s.ra = sm;                                   // 16-byte aligned; [tpc trials][kBwdSlots][KP]
+    s.av = s.ra + tpc * kBwdSlots * KP;          // [tpc][2][NP]
+    s.Ws = s.av + tpc * 2 * NP;
     s.inv = reinterpret_cast<int*>(s.Ws + (size_t)N * (KP + 1));
     return s;
 }
 
-size_t small_bwd_smem_bytes(int N, int KP) {
-    const int NP = (N + 31) / 32 * 32;
-    return sizeof(float) * ((size_t)kBwdSlots * KP + 2 * NP + (size_t)N * (KP + 1) + 3 * N);
+size_t small_bwd_smem_bytes(int N, int KP, int tpc) {
+    const int NP = (N + 31) / 32 * 32;           // >= the lanes per trial in either mode
+    return sizeof(float) * ((size_t)tpc * kBwdSlots * KP + (size_t)tpc * 2 * NP + (size_t)N * (KP + 1) + 3 * N);
 }
 
 template <int KP>
@@ -218,25 +240,34 @@ struct BwdCtx {
     int idx, abuf, N, n_in, K, NP;
     Consts c;
     bool act;
+    KnotLane kl;
+    int li, lanes;        // population index of this lane within its trial; lanes per trial (see RowRhs::init)
+    float* ra_t;          // this trial's [kBwdSlots][KP]
+    float* av_t;          // this trial's [2][NP]
 
-    ODECOL_DEVINL void init(const DevProblem& p, float* sm, int b) {
-        const int i = threadIdx.x;
+    ODECOL_DEVINL void init(const DevProblem& p, float* sm, int b, int li_ = threadIdx.x, int sub = 0,
+                            int lanes_ = blockDim.x, int tpc = 1) {
+        li = li_; lanes = lanes_;
+        const int i = li;
         N = p.N; n_in = p.n_in; K = p.K; kt = p.knot_t; c = p.c;
-        NP = blockDim.x;
-        act = i < N;
-        s = carve_bwd<KP>(sm, N, NP);
-        ku = p.knot_u + (size_t)b * p.knot_stride_b;
+        NP = (N + 31) / 32 * 32;
+        act = i < N && b < p.B;
+        s = carve_bwd<KP>(sm, N, NP, tpc);
+        ra_t = s.ra + sub * kBwdSlots * KP;
+        av_t = s.av + sub * 2 * NP;
+        ku = p.knot_u + (size_t)(b < p.B ? b : p.B - 1) * p.knot_stride_b;
         idx = 1; abuf = 0;
+        kl.reset();
         const int Kaug = N + n_in + 1;
-        for (int e = i; e < N * KP; e += blockDim.x) {
+        for (int e = threadIdx.x; e < N * KP; e += blockDim.x) {
             const int r = e / KP, k = e % KP;
             s.Ws[r * (KP + 1) + k] = k < Kaug ? __ldg(p.W_aug + (size_t)r * p.ld_w + k) : 0.0f;
         }
-        for (int e = i; e < kBwdSlots * KP; e += blockDim.x) s.ra[e] = (e % KP == Kaug - 1) ? 1.0f : 0.0f;
-        for (int e = i; e < 2 * NP; e += blockDim.x) s.av[e] = 0.0f;
+        for (int e = threadIdx.x; e < tpc * kBwdSlots * KP; e += blockDim.x) s.ra[e] = (e % KP == Kaug - 1) ? 1.0f : 0.0f;
+        for (int e = threadIdx.x; e < tpc * 2 * NP; e += blockDim.x) s.av[e] = 0.0f;
 #pragma unroll
         for (int k = 0; k < KP; ++k) dw[k] = 0.0f;
-        kappa = act ? __ldg(p.kappa + i) : 0.0f;
+        kappa = i < N ? __ldg(p.kappa + i) : 0.0f;
         gamma = c.tau_s * c.R / c.tau_m;
         inv_tau_m = 1.0f / c.tau_m; inv_tau_a = 1.0f / c.tau_a; inv_tau_s = 1.0f / c.tau_s;
         __syncthreads();
@@ -245,16 +276,19 @@ struct BwdCtx {
     // forward stage: publishes r_aug into ra[stage], returns total input (needs_dot) ; r, dr out
     ODECOL_DEVINL float stage_fwd(int stage, float t, float V, float A, float& r, float& dr, bool needs_dot) {
         phi_dphi(__fsub_rn(V, A), r, dr);
-        float* cur = s.ra + stage * KP;
-        if (act) cur[threadIdx.x] = r;
-        if ((int)threadIdx.x < n_in) {
-            const float tc = knot_locate(kt, K, t, idx);
-            for (int ch = threadIdx.x; ch < n_in; ch += blockDim.x) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+        float* cur = ra_t + stage * KP;
+        if (act) cur[li] = r;
+        if (li < n_in) {
+            if (n_in <= lanes) cur[N + li] = kl.value(kt, ku, K, n_in, li, t);
+            else {
+                const float tc = knot_locate(kt, K, t, idx);
+                for (int ch = li; ch < n_in; ch += lanes) cur[N + ch] = knot_value(kt, ku, n_in, idx, tc, ch);
+            }
         }
         __syncthreads();
         float acc = 0.f;
         if (needs_dot && act) {
-            const float* wr = s.Ws + threadIdx.x * (KP + 1);
+            const float* wr = s.Ws + li * (KP + 1);
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
             for (int k = 0; k < KP; k += 2) { a0 = fmaf(wr[k], cur[k], a0); a1 = fmaf(wr[k + 1], cur[k + 1], a1); }
@@ -266,20 +300,20 @@ struct BwdCtx {
     // (Yb) = J(stage)^T (aV, aA, aF);  accumulates dW_aug row
     ODECOL_DEVINL void stage_bwd(int stage, float dr, float aV, float aA, float aF, float& bV, float& bA, float& bF) {
         abuf ^= 1;
-        float* a = s.av + abuf * NP;
+        float* a = av_t + abuf * NP;
         const float ga = gamma * aV;
-        a[threadIdx.x] = act ? ga : 0.0f;
+        if (li < NP) a[li] = act ? ga : 0.0f;
         __syncthreads();
         float g = 0.f;
         if (act) {
-            const float* wc = s.Ws + threadIdx.x;
+            const float* wc = s.Ws + li;
             float g0 = 0.f, g1 = 0.f;
             int r = 0;
             for (; r + 1 < N; r += 2) { g0 = fmaf(wc[r * (KP + 1)], a[r], g0); g1 = fmaf(wc[(r + 1) * (KP + 1)], a[r + 1], g1); }
             if (r < N) g0 = fmaf(wc[r * (KP + 1)], a[r], g0);
             g = g0 + g1 + kappa * aA * inv_tau_a + aF * inv_tau_s;
         }
-        const float4* r4 = reinterpret_cast<const float4*>(s.ra + stage * KP);
+        const float4* r4 = reinterpret_cast<const float4*>(ra_t + stage * KP);
 #pragma unroll
         for (int k = 0; k < KP / 4; ++k) {
             const float4 v = r4[k];
@@ -298,7 +332,7 @@ struct BwdCtx {
         const int Kaug = N + n_in + 1;
 #pragma unroll
         for (int k = 0; k < KP; ++k)
-            if (k < Kaug) atomicAdd(grad_W + (size_t)threadIdx.x * p.ld_w + k, dw[k]);
+            if (k < Kaug) atomicAdd(grad_W + (size_t)li * p.ld_w + k, dw[k]);
     }
 };
 
@@ -306,14 +340,16 @@ template <int KP>
 __global__ void __launch_bounds__(128) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y_traj,
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
-                                                       int G, float* __restrict__ grad_y0, float* __restrict__ grad_W) {
+                                                       int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
+                                                       int packed) {
     extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
+    const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N, B = p.B;
     BwdCtx<KP> cx;
-    cx.init(p, sm, b);
-    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    cx.init(p, sm, b, i, sub, packed ? 16 : (int)blockDim.x, packed ? 2 : 1);
+    for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
     __syncthreads();
-    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
     __syncthreads();
     const int gV = cx.act ? cx.s.inv[i] : -1, gA = cx.act ? cx.s.inv[N + i] : -1, gF = cx.act ? cx.s.inv[2 * N + i] : -1;
     const size_t row = (size_t)3 * N;
@@ -910,10 +946,15 @@ int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, floa
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+// two trials per warp when a trial needs at most half a warp (the reference's two-column WTA network)
+static inline bool small_packed(const DevProblem& p) { return p.N <= 16 && p.n_in <= 16; }
+
 int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
                          cudaStream_t s) {
     const int kp = small_kp(p);
-    ODECOL_KP_SWITCH(kp, (k_rk4_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, out_every)));
+    const int packed = small_packed(p) ? 1 : 0;
+    const int grid = packed ? (p.B + 1) / 2 : p.B;
+    ODECOL_KP_SWITCH(kp, (k_rk4_fwd_small<KP><<<grid, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, out_every, packed)));
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
@@ -921,10 +962,12 @@ int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float
 int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float* y_traj, const float* grad_y,
                          const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s) {
     const int kp = small_kp(p);
-    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    const int packed = small_packed(p) ? 1 : 0;
+    const size_t smem = small_bwd_smem_bytes(p.N, kp, packed ? 2 : 1);
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_rk4_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_rk4_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W);
+        k_rk4_bwd_small<KP><<<packed ? (p.B + 1) / 2 : p.B, small_threads(p.N), smem, s>>>(p, t, T, y_traj, grad_y, sel, G,
+                                                                                        grad_y0, grad_W, packed);
     });
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
@@ -943,7 +986,7 @@ int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const fl
 int launch_dopri5_bwd_small(const DevProblem& p, int T, const Dopri5Record& rec, const int* n_accept, const float* grad_y,
                             const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s) {
     const int kp = small_kp(p);
-    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp, 1);
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_dopri5_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_dopri5_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, rec, n_accept, grad_y, sel, G, grad_y0, grad_W);
@@ -975,7 +1018,7 @@ int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float
                         const float* tk, cudaStream_t s) {
     (void)ts;
     const int kp = small_kp(p);
-    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp, 1);
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_em_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_em_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, y_steps, grad_y, sel, G, grad_y0, grad_W, step_of, w, tk);
@@ -1038,7 +1081,7 @@ ODECOL_DEVINL float srk_h2(float y, float f0, float f1, float g, float h, float 
 }
 
 template <int KP>
-__global__ void __launch_bounds__(128) k_srk_fwd_small(DevProblem p, const float* __restrict__ ts, int T,
+__global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks) k_srk_fwd_small(DevProblem p, const float* __restrict__ ts, int T,
                                                        const float* __restrict__ y0, float* __restrict__ y_out,
                                                        const float* __restrict__ dWs, const float* __restrict__ dUs,
                                                        unsigned long long seed, long long trial_offset, float dt0,
@@ -1200,7 +1243,7 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
                          int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
                          const int* step_of, const float* w, const float* tk, cudaStream_t s) {
     const int kp = small_kp(p);
-    const size_t smem = small_bwd_smem_bytes(p.N, kp);
+    const size_t smem = small_bwd_smem_bytes(p.N, kp, 1);
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_srk_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_srk_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, y_steps, dW, dU, (unsigned long long)seed,
