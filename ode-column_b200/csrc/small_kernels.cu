@@ -1085,11 +1085,13 @@ __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks)
                                                        const float* __restrict__ y0, float* __restrict__ y_out,
                                                        const float* __restrict__ dWs, const float* __restrict__ dUs,
                                                        unsigned long long seed, long long trial_offset, float dt0,
-                                                       int* __restrict__ status, float* __restrict__ y_steps) {
-    __shared__ __align__(16) float ra[2 * KP];
-    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+                                                       int* __restrict__ status, float* __restrict__ y_steps, int packed) {
+    __shared__ __align__(16) float ra[4 * KP];
+    const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
+    const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N, B = p.B;
+    const int bs = b < B ? b : B - 1;            // in-bounds trial index for the (uniform) increment loads of an idle half
     RowRhs<KP> f;
-    f.init(p, ra, b);
+    f.init(p, ra, b, i, sub, packed ? 16 : (int)blockDim.x);
     const size_t row = (size_t)3 * N;
     const Philox px(seed);
     const unsigned long long trial = (unsigned long long)(trial_offset + b);
@@ -1113,7 +1115,7 @@ __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks)
             const float next_t = fminf(__fadd_rn(curr_t, dt0), t_end);
             const float h = __fsub_rn(next_t, curr_t), rdt = __fdiv_rn(1.0f, h);
             float dw, du, gw[4];
-            srk_increments(dWs, dUs, px, trial, kstep, B, b, h, dw, du);
+            srk_increments(dWs, dUs, px, trial, kstep, B, bs, h, dw, du);
             srk_g_weights(h, dw, du, gw);
             float f0[3], f1[3], f2[3], H[3];
             f.eval(curr_t, y[0], y[1], y[2], f0[0], f0[1], f0[2]);
@@ -1144,8 +1146,15 @@ __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks)
                 __fadd_rn(__fmul_rn(w0, py[2]), __fmul_rn(w1, y[2])));
         }
     }
-    const bool bad = block_any(f.act && !(isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2])));
-    if (i == 0 && status) status[b] = bad ? ODECOL_ST_NONFINITE : ODECOL_ST_OK;
+    const bool bad_lane = f.act && !(isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]));
+    bool bad;
+    if (packed) {                                   // one warp, two trials: the verdict of this lane's half
+        const unsigned m = __ballot_sync(0xffffffffu, bad_lane);
+        bad = ((sub ? (m >> 16) : m) & 0xffffu) != 0u;
+    } else {
+        bad = block_any(bad_lane);
+    }
+    if (i == 0 && status && b < B) status[b] = bad ? ODECOL_ST_NONFINITE : ODECOL_ST_OK;
 }
 
 // Discrete adjoint of the fixed-step SRI2 solve.  With additive noise the step is
@@ -1160,14 +1169,16 @@ __global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, cons
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
                                                        int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
                                                        const int* __restrict__ step_of, const float* __restrict__ w,
-                                                       const float* __restrict__ tk) {
+                                                       const float* __restrict__ tk, int packed) {
     extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
+    const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N, B = p.B;
+    const int bs = b < B ? b : B - 1;
     BwdCtx<KP> cx;
-    cx.init(p, sm, b);
-    for (int e = i; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
+    cx.init(p, sm, b, i, sub, packed ? 16 : (int)blockDim.x, packed ? 2 : 1);
+    for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
     __syncthreads();
-    if (sel) for (int g = i; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
+    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) cx.s.inv[sel[g]] = g;
     __syncthreads();
     int gi[3];
 #pragma unroll
@@ -1178,7 +1189,7 @@ __global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, cons
     const unsigned long long trial = (unsigned long long)(trial_offset + b);
     float sg[3] = {0.f, 0.f, 0.f};
     if (cx.act && p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
-    if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + b); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
+    if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + bs); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
     auto gcomp = [&](int j, int c) -> float { return gi[c] >= 0 ? grad_y[((size_t)j * B + b) * G + gi[c]] : 0.f; };
     float lam[3] = {0.f, 0.f, 0.f};      // adjoint of solver state k+1 while processing step k
     float pend[3] = {0.f, 0.f, 0.f};     // contributions destined for state k (from interpolated outputs)
@@ -1194,7 +1205,7 @@ __global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, cons
         }
         const float t0 = tk[k], h = __fsub_rn(tk[k + 1], tk[k]), rdt = __fdiv_rn(1.0f, h);
         float dw, du;
-        srk_increments(dWs, dUs, px, trial, (long long)k, B, b, h, dw, du);
+        srk_increments(dWs, dUs, px, trial, (long long)k, B, bs, h, dw, du);
         float y[3] = {0.f, 0.f, 0.f};
         if (cx.act) { const Y3 q = ld3(y_steps + ((size_t)k * B + b) * row, N, i); y[0] = q.V; y[1] = q.A; y[2] = q.F; }
         // ---- recompute the stages (same arithmetic as the forward kernel)
@@ -1233,8 +1244,10 @@ int launch_srk_fwd_small(const DevProblem& p, const float* ts, int T, const floa
                          const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps,
                          cudaStream_t s) {
     const int kp = small_kp(p);
-    ODECOL_KP_SWITCH(kp, (k_srk_fwd_small<KP><<<p.B, small_threads(p.N), 0, s>>>(
-                             p, ts, T, y0, y_out, dW, dU, (unsigned long long)seed, (long long)trial_offset, dt, status, y_steps)));
+    const int packed = small_packed(p) ? 1 : 0;
+    ODECOL_KP_SWITCH(kp, (k_srk_fwd_small<KP><<<packed ? (p.B + 1) / 2 : p.B, small_threads(p.N), 0, s>>>(
+                             p, ts, T, y0, y_out, dW, dU, (unsigned long long)seed, (long long)trial_offset, dt, status, y_steps,
+                             packed)));
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
@@ -1243,12 +1256,13 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
                          int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
                          const int* step_of, const float* w, const float* tk, cudaStream_t s) {
     const int kp = small_kp(p);
-    const size_t smem = small_bwd_smem_bytes(p.N, kp, 1);
+    const int packed = small_packed(p) ? 1 : 0;
+    const size_t smem = small_bwd_smem_bytes(p.N, kp, packed ? 2 : 1);
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_srk_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_srk_bwd_small<KP><<<p.B, small_threads(p.N), smem, s>>>(p, T, y_steps, dW, dU, (unsigned long long)seed,
-                                                                 (long long)trial_offset, grad_y, sel, G, grad_y0, grad_W,
-                                                                 step_of, w, tk);
+        k_srk_bwd_small<KP><<<packed ? (p.B + 1) / 2 : p.B, small_threads(p.N), smem, s>>>(
+            p, T, y_steps, dW, dU, (unsigned long long)seed, (long long)trial_offset, grad_y, sel, G, grad_y0, grad_W, step_of, w,
+            tk, packed);
     });
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
