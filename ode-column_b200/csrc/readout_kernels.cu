@@ -16,9 +16,20 @@ __global__ void __launch_bounds__(256) k_huber_rate_loss(const float* __restrict
     const long long total = rows * G;
     const int GP = G * P;
     double local = 0.0;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / G;
-        const int g = (int)(e - row * G);
+    // (row, g) of this thread's first element by one division; when the grid stride is a multiple of G (it is for the
+    // launcher's grid whenever G divides 256) g never changes and row advances by a constant -- no division per element
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long row = e0 / G;
+    int g = (int)(e0 - row * G);
+    const bool fixed_g = stride % G == 0;
+    const long long row_step = stride / G;
+    const bool need_tb = (st_t | st_b) != 0;
+    for (long long e = e0; e < total; e += stride) {
+        if (e != e0) {
+            if (fixed_g) row += row_step;
+            else { row = e / G; g = (int)(e - row * G); }
+        }
         const float* yr = y + row * 2 * GP;
         float* gr = grad + row * 2 * GP;
         float pred = 0.f, drs[8];
@@ -28,8 +39,9 @@ __global__ void __launch_bounds__(256) k_huber_rate_loss(const float* __restrict
             if (k < 8) drs[k] = dr;
             pred = __fadd_rn(pred, w ? __fmul_rn(r, __ldg(w + k)) : r);
         }
-        const long long t = row / B, b = row - t * B;
-        const float d = __fsub_rn(pred, __ldg(target + t * st_t + b * st_b + g * st_g));
+        long long toff = (long long)g * st_g;
+        if (need_tb) { const long long t = row / B, b = row - t * B; toff += t * st_t + b * st_b; }
+        const float d = __fsub_rn(pred, __ldg(target + toff));
         const float ad = fabsf(d);
         float dl;
         if (ad < beta) { local += 0.5 * (double)d * (double)d / (double)beta; dl = d / beta; }
