@@ -336,8 +336,15 @@ struct BwdCtx {
     }
 };
 
+// reverse kernels: the dW row (KP registers) rides along; only the smallest configuration has room to trade registers
+// for resident CTAs
+template <int KP> struct BwdBounds {
+    static constexpr int threads = KP <= 40 ? 64 : 128;
+    static constexpr int blocks = KP <= 40 ? 10 : 0;      // 0 = unspecified
+};
+
 template <int KP>
-__global__ void __launch_bounds__(128) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
+__global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y_traj,
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
                                                        int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
@@ -1163,7 +1170,7 @@ __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks)
 // saved solver states and the same (W, U) (host tables or the same Philox stream) and pushes the adjoint through them.
 // Replaces loss.backward() through torchsde's unrolled srk steps (reference scripts/wta_ode.py:174-181).
 template <int KP>
-__global__ void __launch_bounds__(128) k_srk_bwd_small(DevProblem p, int T, const float* __restrict__ y_steps,
+__global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks) k_srk_bwd_small(DevProblem p, int T, const float* __restrict__ y_steps,
                                                        const float* __restrict__ dWs, const float* __restrict__ dUs,
                                                        unsigned long long seed, long long trial_offset,
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
