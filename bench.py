@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -44,9 +45,10 @@ def parse():
     ap.add_argument("--cpu-time-points", type=int, default=41, help="grid points of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--family", default=None, help="force a kernel family (staged, tensor)")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "small"],
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "small", "configs"],
                     help="c4 (default, the headline): N=512 rk4 forward+adjoint; c5: N=8192 adaptive Euler-Maruyama sweep; "
-                         "small: the reference's own WTA / parity networks at large batch (persistent on-chip family)")
+                         "small: the reference's own WTA / parity networks at large batch (persistent on-chip family); "
+                         "configs: BASELINE.json configs[0..2] as the scripts run them (latency, next to the CPU oracle)")
     ap.add_argument("--small-trials", type=int, default=65536, help="trials per GPU of the small workload (WTA; parity uses a quarter)")
     ap.add_argument("--c5-columns", type=int, default=1024)
     ap.add_argument("--c5-trials", type=int, default=8192, help="sweep members in total (strong scaling over GPUs)")
@@ -604,6 +606,142 @@ def run_small(args):
     }))
 
 
+def run_configs(args):
+    """BASELINE.json configs[0..2] exactly as the reference scripts run them -- C1: WTA network, one trial, 1500 grid points
+    (rk4 forward + Huber-loss backward, and the scripts' sdeint srk call); C2: XOR network, dopri5 (rtol 1e-7, atol 1e-9)
+    with discrete-adjoint training, the four input patterns; C3: parity network, Euler-Maruyama dt 1e-3 with one
+    Brownian path shared by the four patterns.  Latency-bound by construction (1..4 trials); reported as wall time per
+    solve next to the CPU oracle driving the same solve trial by trial (torch CPU, one thread -- the reference's loop)."""
+    import torch
+    import odecol
+    from oracle import column_model as cm, rhs as orhs, solvers as S, stimuli
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ext = odecol._native.ext()
+    cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
+
+    def move(net):
+        net = net.to(dev)
+        for m in [net] + list(net.modules()):
+            for k, v in list(vars(m).items()):
+                if torch.is_tensor(v) and not isinstance(v, torch.nn.Parameter):
+                    setattr(m, k, v.to(dev))
+        return net
+
+    def gpu_ms(fn, reps=5):
+        fn(); fn()
+        out = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return statistics.median(out)
+
+    def cpu_ms(fn):
+        torch.set_num_threads(1)
+        t0 = time.perf_counter(); fn()
+        return 1e3 * (time.perf_counter() - t0)
+
+    cases = {}
+    launches = 0
+    # ---- C1
+    torch.manual_seed(0)
+    net = odecol.ColumnAreaWTA(cfg, "mt")
+    tv = stimuli.time_vec(1500, 1e-4)
+    stim = stimuli.wta_stimulus(tv, (20.0, 30.0))
+    target = torch.linspace(0, 1, 1500).reshape(1, 1500, 1).repeat(1, 1, 2) * torch.tensor([0.6, 0.3])
+    lf = cm.wta_linear_form(cfg, net.recurrent_weights.detach().numpy())
+    def c1_cpu():
+        ode = orhs.UnifiedColumnODE(lf, tv, stim[None], requires_grad=True)
+        y = S.odeint_rk4(ode, torch.zeros(1, 48), tv)
+        r = orhs.phi(y[:, 0, :16] - y[:, 0, 16:32])
+        torch.nn.functional.smooth_l1_loss(torch.stack((r[:, 0], r[:, 8]), 1)[None], target).backward()
+    def c1_cpu_srk():
+        ode = orhs.UnifiedColumnODE(lf, tv, stim[None])
+        n = len(S.em_step_schedule(tv, 1e-3))
+        W, U = S.sample_w_u(n, 1, 1e-3, torch.Generator().manual_seed(0))
+        with torch.no_grad():
+            S.sdeint_srk(ode, torch.zeros(1, 48), tv, S.TabulatedBrownianU(0.1 * W, 0.1 * U), dt=1e-3)
+    netd = move(net)
+    netd.time_vec, netd.stim = tv.to(dev), stim.to(dev)
+    y0 = torch.zeros(1, 48, device=dev)
+    tgt = target.to(dev)
+    def c1_gpu():
+        netd.zero_grad()
+        y = odecol.odeint(netd, y0, netd.time_vec, method="rk4")
+        odecol.huber_loss_wta(y.unsqueeze(0), tgt, netd).backward()
+    def c1_gpu_srk():
+        with torch.no_grad():
+            odecol.sdeint(netd, y0, netd.time_vec, names={"drift": "forward", "diffusion": "diffusion"}, method="srk", seed=0,
+                          options={"sigma_scale": [0.1]})
+    cases["C1 wta rk4 forward+backward (1 trial, 1499 steps)"] = {"gpu_ms": gpu_ms(c1_gpu), "cpu_oracle_ms": cpu_ms(c1_cpu)}
+    cases["C1 wta sdeint srk forward (1 trial, 150 steps, 1500 outputs)"] = {"gpu_ms": gpu_ms(c1_gpu_srk), "cpu_oracle_ms": cpu_ms(c1_cpu_srk)}
+    # ---- C2
+    torch.manual_seed(0)
+    nd = {"nr_areas": 2, "areas": ["mt", "mt"], "nr_columns_per_area": [2, 1], "nr_input_units": 2}
+    net = odecol.ColumnNetworkXOR(cfg, nd)
+    tv = stimuli.time_vec(1000, 1e-3)
+    stims = torch.stack([stimuli.xor_stimulus(tv, c) for c in stimuli.XOR_CONDITIONS])
+    ffw = [[p.detach().numpy() for p in net.feedforward_target_weights[a]] for a in "01"]
+    lf = cm.xor_linear_form(cfg, ffw)
+    def c2_cpu():                                          # one of the four patterns; the loop is linear in the trial count
+        ode = orhs.UnifiedColumnODE(lf, tv, stims[1:2].reshape(1, 1000, 32), requires_grad=True)
+        y = S.odeint_dopri5(ode, torch.zeros(1, 72), tv)
+        orhs.phi(y[-1, :, 16:24] - y[-1, :, 40:48])[:, 0].sum().backward()
+    netd = move(net)
+    netd.time_vec, netd.stim = tv.to(dev), stims.to(dev)
+    y0x = torch.zeros(4, 72, device=dev)
+    st = {}
+    def c2_gpu():
+        netd.zero_grad()
+        y = odecol.odeint(netd, y0x, netd.time_vec, stats=st)
+        odecol.xor_readout(y, netd).sum().backward()
+    g2 = gpu_ms(c2_gpu, reps=3)
+    cases["C2 xor dopri5 forward+adjoint (4 patterns, rtol 1e-7 atol 1e-9)"] = {
+        "gpu_ms": g2, "cpu_oracle_ms": 4.0 * cpu_ms(c2_cpu), "cpu_note": "one pattern timed, x4",
+        "accepted_steps_per_trial": [int(v) for v in st["n_accept"].tolist()]}
+    # ---- C3
+    torch.manual_seed(0)
+    nd = {"nr_areas": 3, "areas": ["mt"] * 3, "nr_columns_per_area": [8, 4, 1], "nr_input_units": 4}
+    net = odecol.ColumnNetwork(cfg, nd, torch.device("cpu"))
+    stims = torch.stack([stimuli.parity_stimulus(tv, p) for p in stimuli.PARITY_PATTERNS])
+    lf = cm.parity_linear_form(cfg, [net.areas[k].lateral_weights.detach().numpy() for k in "012"],
+                               {1: net.areas["1"].feedforward_weights.detach().numpy(), 2: net.areas["2"].feedforward_weights.detach().numpy()},
+                               net.areas["0"].input_weights.detach().numpy())
+    nst = len(S.em_step_schedule(tv, 1e-3))
+    dW = torch.randn(nst, 1, 1, generator=torch.Generator().manual_seed(1234)) * math.sqrt(1e-3)
+    def c3_cpu():
+        with torch.no_grad():
+            for b in range(4):
+                ode = orhs.UnifiedColumnODE(lf, tv, stims[b:b + 1])
+                S.sdeint_euler(ode, torch.zeros(1, 312), tv, S.TabulatedBrownian(dW), dt=1e-3)
+    netd = move(net)
+    netd.time_vec, netd.stim = tv.to(dev), stims.to(dev)
+    y0p = torch.zeros(4, 312, device=dev)
+    dWd = dW[:, :, 0].to(dev)
+    def c3_gpu():
+        with torch.no_grad():
+            odecol.sdeint(netd, y0p, netd.time_vec, bm=dWd, method="euler", dt=1e-3)
+    cases["C3 parity Euler-Maruyama, shared Brownian path (4 patterns, 1000 steps)"] = {"gpu_ms": gpu_ms(c3_gpu), "cpu_oracle_ms": cpu_ms(c3_cpu)}
+    launches = ext.last_launch_count()
+    for v in cases.values():
+        v["speedup_vs_cpu_oracle"] = v["cpu_oracle_ms"] / v["gpu_ms"]
+    c1 = cases["C1 wta rk4 forward+backward (1 trial, 1499 steps)"]
+    print(json.dumps({
+        "metric": METRIC, "value": 16 * 1499 / (c1["gpu_ms"] / 1e3), "unit": UNIT, "n_gpus": 1, "steps": 5, "warmup": 2,
+        "ms_per_step": c1["gpu_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs: BASELINE.json configs[0..2] as the reference scripts run them (1..4 trials, latency bound); "
+                               "value = C1 (WTA, rk4 forward + backward, one trial)", "l2": "working sets of a few hundred kB"},
+        "gpu_launches": launches, "cases": cases,
+        "cpu_baseline": {"value": 16 * 1499 / (c1["cpu_oracle_ms"] / 1e3), "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "the same C1 solve, oracle rk4 + autograd, one trial"},
+    }))
+
+
 def net_family(ext, odecol, net, y0, tv, args):
     from ode_column_b200.solvers import _Setup
     setup = _Setup(net, y0, tv, args.family)
@@ -619,6 +757,8 @@ def main():
         run_c5(args)
     elif args.workload == "small":
         run_small(args)
+    elif args.workload == "configs":
+        run_configs(args)
     else:
         run_ours(args)
 
