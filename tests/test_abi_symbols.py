@@ -65,3 +65,102 @@ def test_torch_extension_imports_without_gpu():
     with pytest.raises(RuntimeError):
         # CPU tensors are refused: there is no CPU path
         e.Problem(torch.zeros(8, 12), torch.zeros(8), None, torch.zeros(2), torch.zeros(1, 2, 1), 1, 1, 5e-4, 0.02, 10.0, 80.0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# argument validation happens before anything touches the GPU: error codes, never a crash (edge cases: empty batch,
+# single grid point, ragged / misaligned buffers, inconsistent optional tables)
+# ---------------------------------------------------------------------------------------------------------------
+class _Problem(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int32), ("n_in", ctypes.c_int32), ("B", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("ld_w", ctypes.c_int32), ("flags", ctypes.c_int32), ("W_aug", ctypes.c_void_p),
+                ("kappa", ctypes.c_void_p), ("sigma", ctypes.c_void_p), ("knot_t", ctypes.c_void_p),
+                ("knot_u", ctypes.c_void_p), ("knot_stride_b", ctypes.c_int64), ("tau_s", ctypes.c_float),
+                ("tau_m", ctypes.c_float), ("tau_a", ctypes.c_float), ("resistance", ctypes.c_float),
+                ("sigma_scale", ctypes.c_void_p)]
+
+
+def _problem(**kw):
+    fake = 0x7F0000001000                      # never dereferenced on the host; 16-byte aligned
+    base = dict(N=16, n_in=16, B=4, K=6, ld_w=36, flags=0, W_aug=fake, kappa=fake, sigma=None, knot_t=fake, knot_u=fake,
+                knot_stride_b=96, tau_s=5e-4, tau_m=0.02, tau_a=10.0, resistance=80.0, sigma_scale=None)
+    base.update(kw)
+    return _Problem(**base)
+
+
+def test_struct_layout_matches_the_header(lib):
+    # 6 int32, 5 pointers, int64, 4 floats, 1 pointer (ABI v2) -- what a cgo / ctypes binding sees
+    assert ctypes.sizeof(_Problem) == 6 * 4 + 5 * 8 + 8 + 4 * 4 + 8
+    hdr = open(os.path.join(ROOT, "include", "odecol.h")).read()
+    body = hdr[hdr.index("typedef struct odecol_problem {"):hdr.index("} odecol_problem;")]
+    names = re.findall(r"\b(?:int32_t|int64_t|float|const float\*)\s+([a-z_A-Z, ]+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    flat = [n.strip() for group in names for n in group.split(",")]
+    assert flat == [f[0] for f in _Problem._fields_]
+
+
+def test_shape_and_pointer_validation_without_a_gpu(lib):
+    E_NULL, E_SHAPE, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN = -1, -2, -3, -4, -6
+    fake = ctypes.c_void_p(0x7F0000002000)
+    rk4 = lib.odecol_rk4_fwd
+    rk4.restype = ctypes.c_int
+    rk4.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    call = lambda p, T=10, every=1, y0=fake: rk4(ctypes.byref(p), fake, T, y0, fake, every, None, 0, None)
+    assert call(_problem(B=0)) == E_SHAPE                      # empty batch
+    assert call(_problem(N=0)) == E_SHAPE
+    assert call(_problem(K=1)) == E_SHAPE                      # a stimulus needs two knots
+    assert call(_problem(ld_w=32)) == E_SHAPE                  # row shorter than N + n_in + 1
+    assert call(_problem(ld_w=35)) == E_SHAPE                  # not a multiple of 4
+    assert call(_problem(W_aug=0x7F0000001004)) == E_ALIGN
+    assert call(_problem(kappa=None)) == E_NULL
+    assert call(_problem(), T=1) == E_SHAPE                    # a single grid point is not a solve
+    assert call(_problem(), every=0) == E_SHAPE
+    assert call(_problem(), y0=None) == E_NULL
+    # srk: increments come as a (W, U) pair or not at all; only the on-chip family implements it
+    srk = lib.odecol_srk_fwd
+    srk.restype = ctypes.c_int
+    srk.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    p = _problem()
+    assert srk(ctypes.byref(p), fake, 10, fake, fake, fake, None, 0, 0, 1e-3, None, None, None, 0, None) == E_NULL
+    assert srk(ctypes.byref(p), fake, 10, fake, fake, None, None, 0, 0, 0.0, None, None, None, 0, None) == E_SHAPE
+    big = _problem(N=512, n_in=64, ld_w=580)
+    assert srk(ctypes.byref(big), fake, 10, fake, fake, None, None, 0, 0, 1e-3, None, None, None, 0, None) == E_UNSUPPORTED
+    # reverse sweeps insist on their workspace and on a sane component selection
+    bwd = lib.odecol_em_bwd
+    bwd.restype = ctypes.c_int
+    bwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                    ctypes.c_size_t, ctypes.c_void_p]
+    assert bwd(ctypes.byref(p), fake, 10, fake, 9, fake, None, 48, 1e-3, fake, fake, None, 0, None) == E_WORKSPACE
+    assert bwd(ctypes.byref(p), fake, 10, fake, 9, fake, None, 49, 1e-3, fake, fake, None, 0, None) == E_SHAPE
+    assert bwd(ctypes.byref(p), fake, 10, fake, 0, fake, None, 48, 1e-3, fake, fake, None, 0, None) == E_SHAPE
+    # generators / read-outs
+    ww = lib.odecol_ww_generate
+    ww.restype = ctypes.c_int
+    ww.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                   ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    assert ww(fake, None, 0, 5001, 10, 1500, 0.0, 0, 0, fake, None) == E_SHAPE
+    assert ww(fake, None, 4, 5001, 10, 1502, 0.0, 0, 0, fake, None) == E_SHAPE      # more rows than recorded updates
+    assert ww(None, None, 4, 5001, 10, 1500, 0.0, 0, 0, fake, None) == E_NULL
+    hub = lib.odecol_huber_rate_loss
+    hub.restype = ctypes.c_int
+    hub.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    assert hub(fake, 10, 4, 2, 0, None, fake, 0, 0, 0, 1.0, fake, fake, fake, 8, None) == E_SHAPE
+    assert hub(fake, 10, 4, 2, 1, None, fake, 0, 0, 0, 0.0, fake, fake, fake, 8, None) == E_SHAPE
+    assert hub(fake, 10, 4, 2, 1, None, fake, 0, 0, 0, 1.0, fake, fake, None, 0, None) == E_WORKSPACE
+    # bookkeeping helpers answer without a device
+    wsb = lib.odecol_workspace_bytes
+    wsb.restype = ctypes.c_size_t
+    wsb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64]
+    assert wsb(ctypes.byref(p), 1, 1500, 0) == 0                 # on-chip family: no workspace
+    assert wsb(ctypes.byref(p), 7, 1500, 150) > 0                # srk reverse sweep: the step schedule
+    assert wsb(ctypes.byref(_problem(B=0)), 1, 1500, 0) == 0
+    fam = lib.odecol_kernel_family
+    fam.restype = ctypes.c_int
+    fam.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert fam(ctypes.byref(p), 1) == 0 and fam(ctypes.byref(big), 1) == 2 and fam(ctypes.byref(_problem(N=0)), 1) == -1
+    assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184)), 1) == 1
