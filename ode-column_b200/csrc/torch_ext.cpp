@@ -11,7 +11,11 @@
 namespace {
 
 void check(int rc, const char* what) {
-    TORCH_CHECK(rc == ODECOL_OK, "odecol ", what, " failed: ", odecol_strerror(rc), " (", rc, ")");
+    if (rc == ODECOL_OK) return;
+    // the message is assembled with std::string only: streaming an integer through an ostream from inside this module
+    // crashed (facet lookup across two copies of libstdc++ state), turning every error code into a segmentation fault
+    const std::string msg = std::string("odecol ") + what + " failed: " + odecol_strerror(rc) + " (" + std::to_string(rc) + ")";
+    TORCH_CHECK(false, msg);
 }
 
 void want(const torch::Tensor& t, const char* name, c10::ScalarType dt = torch::kFloat32) {
@@ -437,6 +441,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
             return (int64_t)odecol_workspace_bytes(&pr.p, op, (int32_t)T, n_steps);
         });
     m.def("abi_version", &odecol_abi_version);
+    m.def("check_code", [](int rc) { check(rc, "self-test"); }, "raise the RuntimeError a failing entry point would raise");
     m.def("strerror", [](int c) { return std::string(odecol_strerror(c)); });
     m.def("last_launch_count", &odecol_last_launch_count);
     m.def("rhs", &rhs);

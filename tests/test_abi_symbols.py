@@ -164,3 +164,15 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     fam.argtypes = [ctypes.c_void_p, ctypes.c_int]
     assert fam(ctypes.byref(p), 1) == 0 and fam(ctypes.byref(big), 1) == 2 and fam(ctypes.byref(_problem(N=0)), 1) == -1
     assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184)), 1) == 1
+
+
+def test_error_codes_become_python_exceptions_not_crashes():
+    # regression: the message of a failing entry point used to be assembled with an ostream << int, which crashed
+    # inside the extension module (every error code was a segmentation fault); CPU-testable through check_code
+    import odecol
+    e = odecol._native.ext()
+    e.check_code(0)
+    for code, text in ((-1, "NULL"), (-2, "out of range"), (-3, "no kernel"), (-4, "workspace"), (-5, "CUDA"), (-6, "aligned")):
+        with pytest.raises(RuntimeError, match=text) as ei:
+            e.check_code(code)
+        assert f"({code})" in str(ei.value) and "self-test" in str(ei.value)
