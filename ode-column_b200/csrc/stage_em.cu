@@ -325,10 +325,16 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
         !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
         return ODECOL_E_CUDA;
     const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    // CTA pairs (tcgen05 cta_group::2, ODECOL_PAIR=1): each SM stages half of the trial tile
+    const bool use_pair = pair_enabled() && tsh.MT % 2 == 0;
+    CUtensorMap mRhHi, mRhLo;
+    if (use_pair && (!make_map(&mRhHi, Rhi, L.Bp, L.KPa, L.KPa, L.TN / 2) || !make_map(&mRhLo, Rlo, L.Bp, L.KPa, L.KPa, L.TN / 2)))
+        return ODECOL_E_CUDA;
     auto rhs = [&](const float* ysrc, float* fdst) {
         RhsEpi e;
         e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi, mRhLo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
     const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);

@@ -155,6 +155,17 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
         ok = ok && make_map(&mRhi[i], Rhi[i], L.Bp, L.KPa, L.KPa, L.TN) && make_map(&mRlo[i], Rlo[i], L.Bp, L.KPa, L.KPa, L.TN);
     if (!ok) return ODECOL_E_CUDA;
     const TileShape ts0{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    // CTA pairs (tcgen05 cta_group::2, ODECOL_PAIR=1): maps of the same operands with half-tile boxes
+    const bool use_pair = pair_enabled() && ts0.MT % 2 == 0;
+    CUtensorMap mRhHi[2], mRhLo[2];
+    for (int i = 0; i < 2 && use_pair; ++i)
+        if (!make_map(&mRhHi[i], Rhi[i], L.Bp, L.KPa, L.KPa, L.TN / 2) || !make_map(&mRhLo[i], Rlo[i], L.Bp, L.KPa, L.KPa, L.TN / 2))
+            return ODECOL_E_CUDA;
+    int cur = 0;
+    auto launch = [&](auto& e, const TileShape& ts) {
+        return use_pair ? launch_contract_pair(mWhi, mWlo, mRhHi[cur], mRhLo[cur], ts, e, s)
+                        : launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s);
+    };
 
     // diagnostics only (ODECOL_TIMELINE=1): per-CTA globaltimer stamps of the eight launches of steps 2 and 3
     unsigned long long* tl_buf = nullptr;
@@ -163,7 +174,6 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
         cudaMemsetAsync(tl_buf, 0, sizeof(unsigned long long) * 8 * 148 * 8, s);
     }
     const int dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
-    int cur = 0;
     for (int n = 0; n < T - 1; ++n) {
         const int j = n + 1;
         const bool emit = (j % out_every == 0) || (j == T - 1);
@@ -184,10 +194,10 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
             int rc;
             TileShape ts = ts0;
             if (tl_buf && n >= 2 && n < 4) ts.dbg = tl_buf + (size_t)((n - 2) * 4 + (S - 1)) * 8 * 148;
-            if (S == 1) { FwdEpiT<1> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
-            else if (S == 2) { FwdEpiT<2> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
-            else if (S == 3) { FwdEpiT<3> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
-            else { FwdEpiT<4> e; fill(e); rc = launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s); }
+            if (S == 1) { FwdEpiT<1> e; fill(e); rc = launch(e, ts); }
+            else if (S == 2) { FwdEpiT<2> e; fill(e); rc = launch(e, ts); }
+            else if (S == 3) { FwdEpiT<3> e; fill(e); rc = launch(e, ts); }
+            else { FwdEpiT<4> e; fill(e); rc = launch(e, ts); }
             if (rc != ODECOL_OK) return rc;
             cur ^= 1;
         }
@@ -284,6 +294,12 @@ int tc_contract(const float* A, const float* B, float* C, int M, int N, int K, v
         return ODECOL_E_CUDA;
     TileShape ts{L.Mp / BM, L.Np / L.TN, L.TN, L.Kp / BK, 0, nullptr};
     StoreEpi epi{C, M, N, M};
+    if (pair_enabled() && ts.MT % 2 == 0) {          // CTA pairs (cta_group::2): half trial-tile boxes
+        CUtensorMap mbh_hi, mbh_lo;
+        if (!make_map(&mbh_hi, Bhi, L.Np, L.Kp, L.Kp, L.TN / 2) || !make_map(&mbh_lo, Blo, L.Np, L.Kp, L.Kp, L.TN / 2))
+            return ODECOL_E_CUDA;
+        return launch_contract_pair(ma_hi, ma_lo, mbh_hi, mbh_lo, ts, epi, s);
+    }
     return launch_contract(ma_hi, ma_lo, mb_hi, mb_lo, ts, epi, s);
 }
 

@@ -258,6 +258,179 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two population tiles 2m, 2m+1 of one trial tile run on the two SMs of a
+// TPC as ONE M = 256 contraction.  Each CTA stages its own W_aug tile and HALF of the trial tile (TN/2 rows), so the
+// operand bytes entering an SM per K block drop from (128 + TN) to (128 + TN/2) rows -- operand ingress is what binds
+// the single-CTA kernel.  Protocol:
+//   * both CTAs' TMA loads complete on the LEADER's `full` barrier (mbarrier address with the peer bit cleared); the
+//     leader alone posts arrive.expect_tx with the bytes of both;
+//   * the leader's elected thread issues every tcgen05.mma.cta_group::2 (A / B descriptors name the same shared-memory
+//     offsets in both CTAs) and releases ring slots / publishes accumulators with tcgen05.commit ... multicast::cluster
+//     to the `empty` / `tfull` barriers of both CTAs;
+//   * each CTA keeps its own 128 TMEM lanes x TN columns: the epilogues are those of the single-CTA kernel; the peer's
+//     epilogue warps arrive remotely on the leader's `tempty`.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PSTAGES = 4;                      // (32 KB + TN/2 * 256 B) per stage: four stages fit next to the barriers
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's leader (even) CTA
+
+ODECOL_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+ODECOL_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+ODECOL_DEVINL void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+ODECOL_DEVINL void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+ODECOL_DEVINL void umma_commit_pair(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+ODECOL_DEVINL void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_tc_contract_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+                   const __grid_constant__ CUtensorMap mBh_hi, const __grid_constant__ CUtensorMap mBh_lo, TileShape ts, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * PSTAGES + 2];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 4, bh_bytes = (uint32_t)(ts.TN >> 1) * BK * 4;     // half of the trial tile per CTA
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * bh_bytes;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[PSTAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * PSTAGES]), tempty = smem_u32(&bars[2 * PSTAGES + 1]);
+    const int MT2 = ts.MT >> 1;
+    const int tiles = MT2 * ts.NT;
+    const uint32_t acc_stride = (uint32_t)ts.TN;
+    uint32_t ncols = 32;
+    while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PSTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 2 * kEpiWarps);             // the epilogue warps of BOTH CTAs (only the leader's is waited on)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < tiles; tile += npairs) {
+                const int m0 = (2 * (tile % MT2) + (int)rank) * BM;
+                const int n0 = (tile / MT2) * ts.TN + (int)rank * (ts.TN >> 1);
+                for (int kb = 0; kb < ts.KB; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t base = ring + stage * stage_bytes;
+                    const uint32_t fb = (full0 + 8 * stage) & kPeerBitMask;      // the leader's barrier collects both CTAs' bytes
+                    if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
+                    tma_load_2d_pair(base, &mA_hi, fb, kb * BK, m0);
+                    tma_load_2d_pair(base + a_bytes, &mA_lo, fb, kb * BK, m0);
+                    tma_load_2d_pair(base + 2 * a_bytes, &mBh_hi, fb, kb * BK, n0 + ts.b_row0);
+                    tma_load_2d_pair(base + 2 * a_bytes + bh_bytes, &mBh_lo, fb, kb * BK, n0 + ts.b_row0);
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // M = 256 across the pair: (256 >> 4) at [24, 29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ts.TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int tile = pair; tile < tiles; tile += npairs) {
+                mbar_wait(tempty, tphase ^ 1);
+                tc_fence_after();
+                int j = 0;
+                for (int kb = 0; kb < ts.KB; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t base = ring + stage * stage_bytes;
+                    const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
+                    const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + bh_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k, ++j) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        umma_tf32_pair(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                        umma_tf32_pair(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32_pair(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                    }
+                    umma_commit_pair(empty0 + 8 * stage);
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(tfull);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int g = ew >> 2;
+        const int etid = ew * 32 + lane;
+        const int TNq = ts.TN >> 2;
+        epi.prepare();
+        uint32_t tphase = 0;
+        for (int tile = pair; tile < tiles; tile += npairs) {
+            const int m_tile = 2 * (tile % MT2) + (int)rank, nt = tile / MT2, n0 = nt * ts.TN;
+            const int row = m_tile * BM + quarter * 32 + lane;
+            float tot[kMaxQ];
+            epi.pre_tile(row, nt, g, TNq);
+            mbar_wait(tfull, tphase);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
+#pragma unroll
+            for (int q = 0; q < kMaxQ / 4; ++q) {
+                if (4 * q < TNq) {
+                    uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                    for (int a = 0; a <= kMainAcc; ++a) tmem_ld4_issue(lane_base + a * acc_stride + 4 * q, u[a]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float sum = __uint_as_float(u[kMainAcc][e]);
+#pragma unroll
+                        for (int a = 0; a < kMainAcc; ++a) sum += __uint_as_float(u[a][e]);
+                        tot[4 * q + e] = sum;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty);
+            tphase ^= 1;
+            epi.rows(m_tile, row, n0, nt, g, TNq, tot);
+            epi.tile_done(m_tile, n0, ts.TN, etid, kEpiWarps * 32);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();           // the peer's shared memory and barriers stay alive until the leader's last MMA / commit landed
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: tensor maps, tile shape, launch
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -328,6 +501,31 @@ static int launch_contract(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
     const int tiles = ts.MT * ts.NT;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     k_tc_contract<Epi><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// pair launch: bh_* are maps of the SAME operand with a box of TN/2 rows.  Needs an even number of population tiles.
+inline bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ODECOL_PAIR"); v = e ? (atoi(e) != 0) : 0; }
+    return v != 0;
+}
+
+template <class Epi>
+static int launch_contract_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& bh_hi, const CUtensorMap& bh_lo,
+                                const TileShape& ts, const Epi& epi, cudaStream_t s) {
+    if ((ts.MT & 1) || (ts.TN & 15)) return ODECOL_E_UNSUPPORTED;
+    const size_t smem = (size_t)PSTAGES * (2 * BM * BK * 4 + 2 * (size_t)(ts.TN / 2) * BK * 4) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tc_contract_pair<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return ODECOL_E_CUDA;
+        configured = true;
+    }
+    const int tiles = (ts.MT / 2) * ts.NT;
+    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    k_tc_contract_pair<Epi><<<2 * pairs, kThreads, smem, s>>>(a_hi, a_lo, bh_hi, bh_lo, ts, epi);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
