@@ -175,3 +175,27 @@ def test_networks_pickle_like_the_reference_scripts_do(cfg, golden):
         assert torch.equal(a.W_aug, b.W_aug) and torch.equal(a.sigma, b.sigma) and a.n_in == b.n_in
         y = torch.zeros(1, 3 * a.N)
         assert torch.equal(net.forward(net.time_vec[3], y), clone.forward(clone.time_vec[3], y))
+
+
+def test_compress_knots_property_random_tables():
+    # property: for ANY table, looking the stimulus up on the compressed knots equals looking it up on the full table,
+    # bit for bit, at any time (inside, on and outside the grid) -- the contract the kernels rely on
+    from hypothesis import given, settings, strategies as st
+    from oracle.rhs import interp_knots
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(3, 40), st.integers(1, 3), st.integers(1, 4), st.integers(0, 2 ** 31 - 1), st.floats(0.0, 1.0))
+    def check(T, B, n_in, seed, p_change):
+        g = torch.Generator().manual_seed(seed)
+        tv = torch.cumsum(torch.rand(T, generator=g) * 0.01 + 1e-4, 0)
+        # runs of constant values with occasional jumps / ramps: what step stimuli sampled on a grid look like
+        jumps = (torch.rand(T, generator=g) < p_change).float().cumsum(0).long()
+        levels = torch.randn(int(jumps.max()) + 1, B, n_in, generator=g) * 20
+        table = levels[jumps].permute(1, 0, 2).contiguous()                 # (B, T, n_in)
+        kt, ku = odecol.compress_knots(tv, table)
+        assert kt[0] == tv[0] and kt[-1] == tv[-1] and len(kt) <= T and ku.shape == (B, len(kt), n_in)
+        probes = torch.cat((tv, (tv[1:] + tv[:-1]) / 2, tv[:1] - 1.0, tv[-1:] + 1.0, tv[0] + torch.rand(16, generator=g) * (tv[-1] - tv[0])))
+        for t in probes:
+            assert torch.equal(interp_knots(t, tv, table), interp_knots(t, kt, ku))
+
+    check()
