@@ -69,7 +69,7 @@ def train(iters=3, batch_size=4, device="cuda", seed=0, verbose=True):
                     param.clamp_(min=0.0)
                 if "output" in name:
                     param.clamp_(min=0.0, max=float(network.output_scale))
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         if verbose:
             print("Iter {:02d} | Total Loss {:.5f}".format(it + 1, losses[-1]))
     return network, losses

@@ -64,7 +64,7 @@ def train(nr_samples=54, batch_size=16, iters=None, device="cuda", sigma_scale=1
             pred = sdeint(network, torch.zeros(1, 48, device=device), time_vec, method="srk", seed=10_000 + it,
                           options={"sigma_scale": [float(sigma_scale)]})
             test_loss = huber_loss_wta(pred.permute(1, 0, 2).unsqueeze(2), true_states[-1:], network)
-        losses.append((float(loss), float(test_loss)))
+        losses.append((float(loss.detach()), float(test_loss)))
         if verbose:
             print("Iter {:02d} | Total Loss {:.5f} | Validation {:.5f}".format(it + 1, *losses[-1]))
     return network, losses

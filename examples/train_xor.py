@@ -67,7 +67,7 @@ def train(iters=5, batch_size=4, device="cuda", seed=0, verbose=True):
             network.feedforward_target_weights["1"][1].grad *= network.ff_target_mask
         optimizer.step()
         scheduler.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         if verbose:
             print("Iter {:02d} | Total Loss {:.5f}".format(itr + 1, losses[-1]))
     return network, losses
