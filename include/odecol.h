@@ -159,7 +159,11 @@ int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
 /* Adaptive Dormand-Prince 5(4) with per-trial step control and 4th-order dense output at t[0..T).
  * Replaces torchdiffeq.odeint(func, y0, t) with its default method (what the reference scripts get,
  * scripts/xor_ode.py:114, scripts/parity_ode.py:233; rtol 1e-7, atol 1e-9 are torchdiffeq's defaults).
- * n_accept / n_reject / status are per trial, any of them may be NULL. */
+ * n_accept / n_reject / status are per trial, any of them may be NULL.
+ * Networks beyond the on-chip family (N > 128, or ODECOL_FLAG_FORCE_STAGED / _TENSOR) run the staged solver: the same
+ * per-trial controller, one attempted step of every unfinished trial per round with the six stage evaluations on the
+ * tensor cores; it needs odecol_workspace_bytes(p, ODECOL_OP_DOPRI5_FWD, T, 0) and synchronises the stream every 16
+ * rounds (like the adaptive Euler-Maruyama).  The record / reverse pair below exists for the on-chip family only. */
 int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
                       float rtol, float atol, int32_t max_steps,
                       int32_t* n_accept, int32_t* n_reject, int32_t* status,

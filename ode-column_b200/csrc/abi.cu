@@ -86,6 +86,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
         case ODECOL_OP_RK4_FWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
         case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
+        case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
         case ODECOL_OP_SRK_FWD: return 0;
         case ODECOL_OP_SRK_BWD: return em_schedule_layout(T, n_steps).total;
@@ -174,14 +175,17 @@ int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
 int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out, float rtol,
                       float atol, int32_t max_steps, int32_t* n_accept, int32_t* n_reject, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
     if (!t || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;   // per-trial dopri5 exists in the on-chip family only
+    if (!use_small(p, d)) {                              // beyond the on-chip family (or forced): staged solver, forward only
+        if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
+        return stage_dopri5_fwd(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
+    }
     const Dopri5Record none{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, none,
                                    static_cast<cudaStream_t>(stream));
@@ -198,7 +202,7 @@ int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T,
     if (!t || !y0 || !y_out || !n_accept || !rec_y || !rec_t0 || !rec_dt || !out_step || !out_x) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || cap < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    if (!use_small(p, d)) return ODECOL_E_UNSUPPORTED;   // recording (training) exists in the on-chip family only
     const Dopri5Record rec{rec_y, rec_t0, rec_dt, out_step, out_x, cap};
     return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec,
                                    static_cast<cudaStream_t>(stream));

@@ -163,4 +163,25 @@ ODECOL_DEVINL float brownian_tree(const Philox& px, uint64_t trial, float T0, fl
     });
 }
 
+// ---- Dormand-Prince 5(4) tableau (Shampine's variant, as torchdiffeq tabulates it) ---------------------------------
+struct DP {
+    // float32(coefficient), as torchdiffeq casts its float64 tableau to y0.dtype
+    static constexpr float a1 = (float)(1.0 / 5), a2 = (float)(3.0 / 10), a3 = (float)(4.0 / 5), a4 = (float)(8.0 / 9);
+    static constexpr float b10 = (float)(1.0 / 5);
+    static constexpr float b20 = (float)(3.0 / 40), b21 = (float)(9.0 / 40);
+    static constexpr float b30 = (float)(44.0 / 45), b31 = (float)(-56.0 / 15), b32 = (float)(32.0 / 9);
+    static constexpr float b40 = (float)(19372.0 / 6561), b41 = (float)(-25360.0 / 2187), b42 = (float)(64448.0 / 6561),
+                           b43 = (float)(-212.0 / 729);
+    static constexpr float b50 = (float)(9017.0 / 3168), b51 = (float)(-355.0 / 33), b52 = (float)(46732.0 / 5247),
+                           b53 = (float)(49.0 / 176), b54 = (float)(-5103.0 / 18656);
+    static constexpr float b60 = (float)(35.0 / 384), b62 = (float)(500.0 / 1113), b63 = (float)(125.0 / 192),
+                           b64 = (float)(-2187.0 / 6784), b65 = (float)(11.0 / 84);
+    static constexpr float e0 = (float)(35.0 / 384 - 1951.0 / 21600), e2 = (float)(500.0 / 1113 - 22642.0 / 50085),
+                           e3 = (float)(125.0 / 192 - 451.0 / 720), e4 = (float)(-2187.0 / 6784 + 12231.0 / 42400),
+                           e5 = (float)(11.0 / 84 - 649.0 / 6300), e6 = (float)(-1.0 / 60);
+    static constexpr float m0 = (float)(6025192743.0 / 30085553152.0 / 2), m2 = (float)(51252292925.0 / 65400821598.0 / 2),
+                           m3 = (float)(-2691868925.0 / 45128329728.0 / 2), m4 = (float)(187940372067.0 / 1594534317056.0 / 2),
+                           m5 = (float)(-1776094331.0 / 19743644256.0 / 2), m6 = (float)(11237099.0 / 235043384.0 / 2);
+};
+
 }  // namespace odecol

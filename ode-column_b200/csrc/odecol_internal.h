@@ -89,6 +89,11 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
                  uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
                  int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// staged Dormand-Prince 5(4), forward (stage_em.cu): per-trial control in rounds, drift on the tensor cores
+size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int T);
+int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
+                     int max_steps, int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
+
 // ---- family T (stage_tc.cu): the staged contraction on tcgen05 tensor cores (3xTF32) ------------------------------
 size_t tc_rk4_fwd_workspace_bytes(const DevProblem& p, int T);
 int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every, void* ws,

@@ -431,4 +431,299 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged Dormand-Prince 5(4): torchdiffeq's default solver for networks beyond the on-chip family.  Same structure as
+// the adaptive Euler-Maruyama above -- every trial carries its own (t, dt), one ROUND = one attempted step of every
+// unfinished trial: six stage evaluations (stage state elementwise -> operand -> tensor-core drift), then one kernel
+// per trial block that forms the embedded error, takes the accept / reject decision and runs the step-size controller
+// exactly like k_dopri5_fwd_small (RMS over the trial's whole state in float64, controller in float64, time in
+// float64, state and tableau in float32), emits every output time inside an accepted step through the quartic dense
+// output and commits the step.  Forward only: training through dopri5 needs the on-chip family (N <= 128).
+// ---------------------------------------------------------------------------------------------------------------
+namespace tc {
+
+struct DpState {
+    double* t; double* dt; double* red;      // (B) current time, step size, reduction scratch
+    float* t_stage;                          // (B) time of the stage being evaluated
+    int* next_out; int* n_acc; int* n_rej; int* status; int* active;
+    int* n_active;
+    float* k[7];                             // (B, 3N) stage slopes; k[0] = f(t, y) (FSAL)
+    float* y; float* ys;                     // (B, 3N) accepted state, stage state / candidate
+};
+
+ODECOL_DEVINL double dp_block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    __syncthreads();
+    return s;
+}
+
+// Hairer's initial step, part 1: d0, d1 -> h0; ys = y + h0 f0; stage time t0 + h0.   One CTA per trial.
+__global__ void k_dp_init1(DevProblem p, DpState s, const float* __restrict__ ts, float rtol, float atol) {
+    __shared__ double sh[8];
+    const int b = blockIdx.x, n3 = 3 * p.N;
+    const size_t o = (size_t)b * n3;
+    double a0 = 0.0, a1 = 0.0;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) {
+        const float y = s.y[o + c], f = s.k[0][o + c];
+        const float sc = __fadd_rn(atol, __fmul_rn(fabsf(y), rtol));
+        const float q0 = __fdiv_rn(y, sc), q1 = __fdiv_rn(f, sc);
+        a0 += (double)q0 * q0; a1 += (double)q1 * q1;
+    }
+    a0 = dp_block_sum(a0, sh); a1 = dp_block_sum(a1, sh);
+    const float d0 = (float)sqrt(a0 / n3), d1 = (float)sqrt(a1 / n3);
+    float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : __fdiv_rn(__fmul_rn(0.01f, d0), d1);
+    h0 = fabsf(h0);
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) s.ys[o + c] = __fadd_rn(s.y[o + c], __fmul_rn(h0, s.k[0][o + c]));
+    if (threadIdx.x == 0) {
+        const double t0 = (double)ts[0];
+        s.t[b] = t0;
+        s.t_stage[b] = (float)(t0 + (double)h0);
+        s.red[2 * b] = (double)h0; s.red[2 * b + 1] = (double)d1;
+        s.next_out[b] = 1; s.n_acc[b] = 0; s.n_rej[b] = 0; s.status[b] = ODECOL_ST_OK; s.active[b] = 1;
+        if (b == 0) *s.n_active = p.B;
+    }
+}
+
+// part 2: d2 from f1 = k[1] -> dt
+__global__ void k_dp_init2(DevProblem p, DpState s, float rtol, float atol) {
+    __shared__ double sh[8];
+    const int b = blockIdx.x, n3 = 3 * p.N;
+    const size_t o = (size_t)b * n3;
+    const float h0 = (float)s.red[2 * b], d1 = (float)s.red[2 * b + 1];
+    double a2 = 0.0;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) {
+        const float sc = __fadd_rn(atol, __fmul_rn(fabsf(s.y[o + c]), rtol));
+        const float q = __fdiv_rn(__fsub_rn(s.k[1][o + c], s.k[0][o + c]), sc);
+        a2 += (double)q * q;
+    }
+    a2 = dp_block_sum(a2, sh);
+    if (threadIdx.x == 0) {
+        const float d2 = fabsf(__fdiv_rn((float)sqrt(a2 / n3), h0));
+        float h1;
+        if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
+        else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 0.2f);
+        s.dt[b] = (double)fminf(__fmul_rn(100.f, h0), fabsf(h1));
+    }
+}
+
+// stage state of stage S (1..6) of the current attempt and its evaluation time
+template <int S>
+__global__ void k_dp_stage(DevProblem p, DpState s) {
+    const int n3 = 3 * p.N;
+    const size_t total = (size_t)p.B * n3;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n3);
+        if (!s.active[b]) continue;
+        const float dtf = (float)s.dt[b];
+        float acc;
+        if (S == 1) acc = s.k[0][e] * (DP::b10 * dtf);
+        if (S == 2) acc = fmaf(s.k[1][e], DP::b21 * dtf, s.k[0][e] * (DP::b20 * dtf));
+        if (S == 3) acc = fmaf(s.k[2][e], DP::b32 * dtf, fmaf(s.k[1][e], DP::b31 * dtf, s.k[0][e] * (DP::b30 * dtf)));
+        if (S == 4) acc = fmaf(s.k[3][e], DP::b43 * dtf, fmaf(s.k[2][e], DP::b42 * dtf, fmaf(s.k[1][e], DP::b41 * dtf, s.k[0][e] * (DP::b40 * dtf))));
+        if (S == 5) acc = fmaf(s.k[4][e], DP::b54 * dtf, fmaf(s.k[3][e], DP::b53 * dtf, fmaf(s.k[2][e], DP::b52 * dtf,
+                          fmaf(s.k[1][e], DP::b51 * dtf, s.k[0][e] * (DP::b50 * dtf)))));
+        if (S == 6) acc = fmaf(s.k[5][e], DP::b65 * dtf, fmaf(s.k[4][e], DP::b64 * dtf, fmaf(s.k[3][e], DP::b63 * dtf,
+                          fmaf(s.k[2][e], DP::b62 * dtf, s.k[0][e] * (DP::b60 * dtf)))));
+        s.ys[e] = __fadd_rn(s.y[e], acc);
+        if (e == (size_t)b * n3) {
+            const double t0 = s.t[b];
+            const float t0f = (float)t0;
+            const float al = S == 1 ? DP::a1 : S == 2 ? DP::a2 : S == 3 ? DP::a3 : DP::a4;
+            s.t_stage[b] = S <= 4 ? __fadd_rn(t0f, __fmul_rn(al, dtf)) : (float)(t0 + s.dt[b]);
+        }
+    }
+}
+
+// error ratio, accept / reject, controller, dense output of every output time inside an accepted step, commit
+__global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ ts, int T, float rtol, float atol,
+                            int max_steps, float* __restrict__ y_out) {
+    __shared__ double sh[8];
+    __shared__ int sh_acc, sh_j0, sh_j1;
+    const int b = blockIdx.x, n3 = 3 * p.N;
+    if (!s.active[b]) return;
+    const size_t o = (size_t)b * n3;
+    const size_t total = (size_t)p.B * n3;
+    const double t0 = s.t[b], dt = s.dt[b], t1 = t0 + dt;
+    const float dtf = (float)dt;
+    double acc = 0.0;
+    int bad = 0;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) {
+        const size_t e = o + c;
+        const float err = fmaf(s.k[6][e], DP::e6 * dtf, fmaf(s.k[5][e], DP::e5 * dtf, fmaf(s.k[4][e], DP::e4 * dtf,
+                          fmaf(s.k[3][e], DP::e3 * dtf, fmaf(s.k[2][e], DP::e2 * dtf, s.k[0][e] * (DP::e0 * dtf))))));
+        const float y0 = s.y[e], y1 = s.ys[e];
+        const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y0), fabsf(y1))));
+        const float q = __fdiv_rn(err, tol);
+        acc += (double)q * q;
+        bad |= !isfinite(y0);
+    }
+    acc = dp_block_sum(acc, sh);
+    bad = __syncthreads_or(bad);
+    const float ratio = (float)sqrt(acc / n3);
+    if (threadIdx.x == 0) {
+        int st = ODECOL_ST_OK, accept = 0;
+        if (bad || !(ratio == ratio)) st = ODECOL_ST_NONFINITE;
+        else if (!(t0 + dt > t0)) st = ODECOL_ST_UNDERFLOW;
+        else accept = ratio <= 1.0f;
+        int j0 = s.next_out[b], j1 = j0;
+        if (st == ODECOL_ST_OK) {
+            if (accept) {
+                while (j1 < T && (double)ts[j1] <= t1) ++j1;      // outputs reached by this step: next_t <= st_t1
+                s.n_acc[b] += 1;
+            } else {
+                s.n_rej[b] += 1;
+            }
+            const double r64 = (double)ratio;
+            double ndt;
+            if (r64 == 0.0) ndt = dt * 10.0;
+            else { const double df = r64 < 1.0 ? 1.0 : 0.2; ndt = dt * fmin(10.0, fmax(0.9 / pow(r64, 0.2), df)); }
+            s.dt[b] = ndt;
+            if (accept) { s.t[b] = t1; s.next_out[b] = j1; }
+            if (j1 >= T) { s.active[b] = 0; atomicSub(s.n_active, 1); }
+            else if (s.n_acc[b] + s.n_rej[b] >= max_steps) { st = ODECOL_ST_MAXSTEPS; }
+        }
+        if (st != ODECOL_ST_OK) { s.status[b] = st; s.active[b] = 0; atomicSub(s.n_active, 1); accept = 0; }
+        sh_acc = accept; sh_j0 = j0; sh_j1 = j1;
+    }
+    __syncthreads();
+    if (!sh_acc) return;
+    const int j0 = sh_j0, j1 = sh_j1;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) {
+        const size_t e = o + c;
+        const float f0 = s.k[0][e], f1 = s.k[6][e], y0c = s.y[e], y1c = s.ys[e];
+        if (j1 > j0) {
+            const float ymid = __fadd_rn(y0c, fmaf(s.k[6][e], DP::m6 * dtf, fmaf(s.k[5][e], DP::m5 * dtf, fmaf(s.k[4][e], DP::m4 * dtf,
+                               fmaf(s.k[3][e], DP::m3 * dtf, fmaf(s.k[2][e], DP::m2 * dtf, s.k[0][e] * (DP::m0 * dtf)))))));
+            const float ca = 2.f * dtf * (f1 - f0) - 8.f * (y1c + y0c) + 16.f * ymid;
+            const float cb = dtf * (5.f * f0 - 3.f * f1) + 18.f * y0c + 14.f * y1c - 32.f * ymid;
+            const float cc = dtf * (f1 - 4.f * f0) - 11.f * y0c - 5.f * y1c + 16.f * ymid;
+            const float cd = dtf * f0;
+            for (int j = j0; j < j1; ++j) {
+                const float x = (float)(((double)ts[j] - t0) / (t1 - t0));
+                float tot = __fadd_rn(y0c, __fmul_rn(x, cd));
+                float xp = __fmul_rn(x, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, cc));
+                xp = __fmul_rn(xp, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, cb));
+                xp = __fmul_rn(xp, x);
+                tot = __fadd_rn(tot, __fmul_rn(xp, ca));
+                y_out[(size_t)j * total + e] = tot;
+            }
+        }
+        s.y[e] = y1c;
+        s.k[0][e] = f1;
+    }
+}
+
+struct DpLayout {
+    int Np, Bp, KPa, TN;
+    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_k[7], off_y, off_ys, off_state, total;
+};
+
+static DpLayout dp_layout(const DevProblem& p) {
+    DpLayout L;
+    L.Np = round_up(p.N, BM);
+    L.KPa = round_up(p.N + p.n_in + 1, BK);
+    L.TN = pick_tile_n(L.Np / BM, p.B);
+    L.Bp = round_up(p.B, L.TN);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
+    L.off_Rhi = take(4ull * L.Bp * L.KPa); L.off_Rlo = take(4ull * L.Bp * L.KPa);
+    const size_t st = 4ull * p.B * 3 * p.N;
+    for (int i = 0; i < 7; ++i) L.off_k[i] = take(st);
+    L.off_y = take(st); L.off_ys = take(st);
+    L.off_state = take(64ull * p.B + 1024);
+    L.total = o;
+    return L;
+}
+
+}  // namespace tc
+
+size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int) { return tc::dp_layout(p).total; }
+
+int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
+                     int max_steps, int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const DpLayout L = dp_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo);
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+    const size_t B = p.B;
+    DpState S;
+    for (int i = 0; i < 7; ++i) S.k[i] = F(L.off_k[i]);
+    S.y = F(L.off_y); S.ys = F(L.off_ys);
+    char* sb = w + L.off_state;
+    auto grab = [&](size_t bytes) { char* r = sb; sb += (bytes + 15) / 16 * 16; return r; };
+    S.t = reinterpret_cast<double*>(grab(8 * B)); S.dt = reinterpret_cast<double*>(grab(8 * B));
+    S.red = reinterpret_cast<double*>(grab(16 * B));
+    S.t_stage = reinterpret_cast<float*>(grab(4 * B));
+    S.next_out = reinterpret_cast<int*>(grab(4 * B)); S.n_acc = reinterpret_cast<int*>(grab(4 * B));
+    S.n_rej = reinterpret_cast<int*>(grab(4 * B)); S.status = reinterpret_cast<int*>(grab(4 * B));
+    S.active = reinterpret_cast<int*>(grab(4 * B));
+    S.n_active = reinterpret_cast<int*>(grab(16));
+
+    if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_k[0] - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+    count_launch();
+    if (cudaMemcpyAsync(S.y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    CUtensorMap mWhi, mWlo, mRhi, mRlo;
+    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+        return ODECOL_E_CUDA;
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    // f(t_stage[b], ysrc[b]) -> fdst for every trial (finished trials compute along harmlessly: rows are independent)
+    auto rhs = [&](const float* ysrc, const float* t_trial, float t_shared, float* fdst) {
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, t_trial, t_shared, Rhi, Rlo, L.KPa);
+        count_launch();
+        RhsEpi e;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
+    };
+    const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
+    float t_first = 0.f;
+    if (cudaMemcpyAsync(&t_first, ts_dev, sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+    int rc = rhs(S.y, nullptr, t_first, S.k[0]);                    // f0 = f(t[0], y0)
+    if (rc != ODECOL_OK) return rc;
+    k_dp_init1<<<p.B, 256, 0, s>>>(p, S, ts_dev, rtol, atol);
+    rc = rhs(S.ys, S.t_stage, 0.f, S.k[1]);                         // f(t0 + h0, y0 + h0 f0)
+    if (rc != ODECOL_OK) return rc;
+    k_dp_init2<<<p.B, 256, 0, s>>>(p, S, rtol, atol);
+    count_launch(2);
+    int h_active = p.B;
+    for (long long round = 0; round < (long long)max_steps && h_active > 0; ++round) {
+        k_dp_stage<1><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[1]); if (rc) return rc;
+        k_dp_stage<2><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[2]); if (rc) return rc;
+        k_dp_stage<3><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[3]); if (rc) return rc;
+        k_dp_stage<4><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[4]); if (rc) return rc;
+        k_dp_stage<5><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[5]); if (rc) return rc;
+        k_dp_stage<6><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[6]); if (rc) return rc;
+        k_dp_finish<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, rtol, atol, max_steps, y_out);
+        count_launch(7);
+        if ((round & 15) == 15) {
+            if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        }
+    }
+    k_em_fill_nan<<<p.B, 128, 0, s>>>(p, S.status, S.next_out, T, y_out);
+    count_launch();
+    if (n_accept && cudaMemcpyAsync(n_accept, S.n_acc, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (n_reject && cudaMemcpyAsync(n_reject, S.n_rej, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (status && cudaMemcpyAsync(status, S.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 }  // namespace odecol
