@@ -88,7 +88,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
-        case ODECOL_OP_SRK_FWD: return 0;
+        case ODECOL_OP_SRK_FWD: return small ? 0 : stage_srk_fwd_workspace_bytes(d, T);
         case ODECOL_OP_SRK_BWD: return em_schedule_layout(T, n_steps).total;
         default: return 0;
     }
@@ -295,15 +295,19 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
 int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out, const float* dW,
                    const float* dU, uint64_t seed, int64_t trial_offset, float dt, int32_t* status, float* y_steps,
                    void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
     if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
     if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
     if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
     g_launches.store(0, std::memory_order_relaxed);
+    if (!use_small(p, d)) {                              // staged solver: forward only (no y_steps record)
+        if (y_steps) return ODECOL_E_UNSUPPORTED;
+        if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
+        return stage_srk_fwd(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+    }
     return launch_srk_fwd_small(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps,
                                 static_cast<cudaStream_t>(stream));
 }

@@ -94,6 +94,12 @@ size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int T);
 int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
                      int max_steps, int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// staged torchsde srk (fixed step), forward (stage_em.cu)
+size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int T);
+int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, void* ws, size_t ws_bytes,
+                  cudaStream_t s);
+
 // ---- family T (stage_tc.cu): the staged contraction on tcgen05 tensor cores (3xTF32) ------------------------------
 size_t tc_rk4_fwd_workspace_bytes(const DevProblem& p, int T);
 int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every, void* ws,

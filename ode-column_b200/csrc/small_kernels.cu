@@ -1024,50 +1024,7 @@ int launch_em_bwd_small(const DevProblem& p, const float* ts, int T, const float
 // Levy area U through the third stage.  Every float32 operation of diagonal_or_scalar_step is replayed in its order.
 // The fourth stage has alpha = 0 and H0 = y0: its drift contributes an exact zero and is not evaluated.
 // ---------------------------------------------------------------------------------------------------------------
-struct Srid2 {
-    static constexpr float quarter = 0.25f, half = 0.5f;
-    static constexpr float a0 = (float)(1.0 / 6), a1 = (float)(1.0 / 6), a2 = (float)(2.0 / 3);
-};
-
-// (W, U) of step k for one trial: host tables or Philox (U | W ~ N(h W / 2, h^3 / 12)).  The W deviate is the one the
-// fixed-step Euler-Maruyama kernel draws for the same (seed, trial, step), so both methods see the same path.
-ODECOL_DEVINL void srk_increments(const float* __restrict__ dWs, const float* __restrict__ dUs, const Philox& px,
-                                  unsigned long long trial, long long k, int B, int b, float h, float& dw, float& du) {
-    if (dWs) {
-        dw = __ldg(dWs + (size_t)k * B + b);
-        du = __ldg(dUs + (size_t)k * B + b);
-    } else {
-        const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)k, 0x80000000u | (uint32_t)(k >> 32));
-        dw = sqrtf(h) * normal_from_bits(bits.x, bits.y);
-        du = 0.5f * h * dw + sqrtf(h * h * h * (1.0f / 12.0f)) * normal_from_bits(bits.z, bits.w);
-    }
-}
-
-// g_weight of the four stages (thread-uniform scalars)
-ODECOL_DEVINL void srk_g_weights(float h, float dw, float du, float gw[4]) {
-    const float rdt = __fdiv_rn(1.0f, h), sq = __fsqrt_rn(h);
-    const float i_kk = __fmul_rn(__fsub_rn(__fmul_rn(dw, dw), h), 0.5f);
-    const float i_kkk = __fdiv_rn(__fsub_rn(__fmul_rn(__fmul_rn(dw, dw), dw), __fmul_rn(__fmul_rn(3.0f, h), dw)), 6.0f);
-    // beta rows as float32 (torch multiplies a float32 tensor by the Python scalar cast to float32)
-    constexpr float b1[4] = {-1.f, (float)(4.0 / 3), (float)(2.0 / 3), 0.f};
-    constexpr float b2[4] = {1.f, (float)(-4.0 / 3), (float)(1.0 / 3), 0.f};
-    constexpr float b3[4] = {2.f, (float)(-4.0 / 3), (float)(-2.0 / 3), 0.f};
-    constexpr float b4[4] = {-2.f, (float)(5.0 / 3), (float)(-2.0 / 3), 1.f};
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        float w = __fadd_rn(__fmul_rn(b1[s], dw), __fdiv_rn(__fmul_rn(b2[s], i_kk), sq));
-        w = __fadd_rn(w, __fmul_rn(__fmul_rn(b3[s], du), rdt));
-        gw[s] = __fadd_rn(w, __fmul_rn(__fmul_rn(b4[s], i_kkk), rdt));
-    }
-}
-
-// H0 of stage 3 for one state component: y + (1/4 f0) h + ((1 g) U) / h + (1/4 f1) h + ((1/2 g) U) / h
-ODECOL_DEVINL float srk_h2(float y, float f0, float f1, float g, float h, float du, float rdt) {
-    float v = __fadd_rn(y, __fmul_rn(__fmul_rn(Srid2::quarter, f0), h));
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(g, du), rdt));
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::quarter, f1), h));
-    return __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(Srid2::half, g), du), rdt));
-}
+// Srid2, srk_increments, srk_g_weights, srk_h2: odecol_common.cuh (shared with the staged family)
 
 template <int KP>
 __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks) k_srk_fwd_small(DevProblem p, const float* __restrict__ ts, int T,

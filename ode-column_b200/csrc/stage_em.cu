@@ -726,4 +726,154 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged torchsde srk (Roessler SRI2, fixed step) for networks beyond the on-chip family: three tensor-core drift
+// evaluations per step (stages at t0, t0 + h, t0 + h/2; the fourth has weight 0), the stage states, the step and the
+// interpolated outputs in elementwise kernels -- the arithmetic of k_srk_fwd_small.  The (W, U) of a step are formed
+// once per trial (host tables or Philox) together with the four g_weights.  Forward only.
+// ---------------------------------------------------------------------------------------------------------------
+namespace tc {
+
+struct SrkNoise { float* dw; float* du; float* gw; };    // (B), (B), (B, 4)
+
+__global__ void k_srk_noise(DevProblem p, SrkNoise nz, const float* __restrict__ dWs, const float* __restrict__ dUs,
+                            unsigned long long seed, long long trial_offset, long long kstep, float h) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const Philox px(seed);
+    float dw, du, gw[4];
+    srk_increments(dWs, dUs, px, (unsigned long long)(trial_offset + b), kstep, p.B, b, h, dw, du);
+    srk_g_weights(h, dw, du, gw);
+    nz.dw[b] = dw; nz.du[b] = du;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nz.gw[4 * b + q] = gw[q];
+}
+
+// which: 1 -> H = y + f0 h;  2 -> H = y + 1/4 (f0 + f1) h + 3/2 sigma U / h  (srk_h2's operation order)
+__global__ void k_srk_stage(DevProblem p, SrkNoise nz, int which, const float* __restrict__ y, const float* __restrict__ f0,
+                            const float* __restrict__ f1, float h, float* __restrict__ H) {
+    const int n3 = 3 * p.N;
+    const size_t total = (size_t)p.B * n3;
+    const float rdt = __fdiv_rn(1.0f, h);
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        if (which == 1) { H[e] = __fadd_rn(y[e], __fmul_rn(f0[e], h)); continue; }
+        const int b = (int)(e / n3), comp = (int)(e % n3);
+        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * (p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f);
+        H[e] = srk_h2(y[e], f0[e], f1[e], sg, h, nz.du[b], rdt);
+    }
+}
+
+struct SrkStepArgs {
+    DevProblem p; SrkNoise nz;
+    float* y; float* y_prev; const float* f0; const float* f1; const float* f2;
+    float t0, t1; float* y_out; int j_lo, j_hi; const float* ts;
+};
+
+__global__ void k_srk_step(SrkStepArgs a) {
+    const int n3 = 3 * a.p.N;
+    const size_t total = (size_t)a.p.B * n3;
+    const float h = __fsub_rn(a.t1, a.t0);
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n3), comp = (int)(e % n3);
+        const float sg = (a.p.sigma ? __ldg(a.p.sigma + comp) : 0.f) * (a.p.sigma_scale ? __ldg(a.p.sigma_scale + b) : 1.f);
+        const float* gw = a.nz.gw + 4 * b;
+        const float y0 = a.y[e];
+        float v = __fadd_rn(__fadd_rn(y0, __fmul_rn(__fmul_rn(Srid2::a0, a.f0[e]), h)), __fmul_rn(sg, gw[0]));
+        v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a1, a.f1[e]), h)), __fmul_rn(sg, gw[1]));
+        v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a2, a.f2[e]), h)), __fmul_rn(sg, gw[2]));
+        const float y1 = __fadd_rn(v, __fmul_rn(sg, gw[3]));
+        a.y_prev[e] = y0;
+        a.y[e] = y1;
+        for (int j = a.j_lo; j < a.j_hi; ++j) {
+            const float out_t = __ldg(a.ts + j);
+            const float w0 = __fdiv_rn(__fsub_rn(a.t1, out_t), h), w1 = __fdiv_rn(__fsub_rn(out_t, a.t0), h);
+            a.y_out[(size_t)j * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
+        }
+    }
+}
+
+__global__ void k_status_finite(DevProblem p, const float* __restrict__ y, int* __restrict__ status) {
+    const int b = blockIdx.x, n3 = 3 * p.N;
+    int bad = 0;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) bad |= !isfinite(y[(size_t)b * n3 + c]);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) status[b] = bad ? ODECOL_ST_NONFINITE : ODECOL_ST_OK;
+}
+
+}  // namespace tc
+
+size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_layout(p).total; }
+
+int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+    using namespace tc;
+    const EmLayout L = em_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo);
+    float *f0 = F(L.off_f), *f1 = F(L.off_fm), *f2 = F(L.off_yfull), *H = F(L.off_ymid);
+    float *y = F(L.off_y), *yprev = F(L.off_yprev);
+    SrkNoise nz;
+    nz.dw = F(L.off_state); nz.du = nz.dw + p.B; nz.gw = nz.du + p.B;          // 6 floats per trial of the 128-byte slot
+    const int Kaug = p.N + p.n_in + 1;
+    const size_t st = (size_t)p.B * 3 * p.N;
+    if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+    count_launch();
+    if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    CUtensorMap mWhi, mWlo, mRhi, mRlo;
+    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+        return ODECOL_E_CUDA;
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    auto rhs = [&](const float* ysrc, float tq, float* fdst) {
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, nullptr, tq, Rhi, Rlo, L.KPa);
+        count_launch();
+        RhsEpi e;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
+    };
+    const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
+    std::vector<float> ts(T);
+    if (cudaMemcpyAsync(ts.data(), ts_dev, sizeof(float) * T, cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+    volatile float curr = ts[0];
+    const float t_end = ts[T - 1];
+    long long k = 0;
+    int j = 1;
+    while (j < T) {
+        const float c0 = curr;
+        volatile float nx = c0 + dt;
+        const float next_t = nx < t_end ? nx : t_end;
+        volatile float hv = next_t - c0;
+        const float h = hv;
+        volatile float t1v = c0 + h, thv = c0 + 0.5f * h;           // stage times in float32, as the on-chip kernel forms them
+        int j_hi = j;
+        while (j_hi < T && ts[j_hi] <= next_t) ++j_hi;
+        k_srk_noise<<<(p.B + 127) / 128, 128, 0, s>>>(p, nz, dW, dU, (unsigned long long)seed, (long long)trial_offset, k, h);
+        int rc = rhs(y, c0, f0); if (rc) return rc;
+        k_srk_stage<<<ew_grid, 256, 0, s>>>(p, nz, 1, y, f0, f1, h, H);
+        rc = rhs(H, t1v, f1); if (rc) return rc;
+        k_srk_stage<<<ew_grid, 256, 0, s>>>(p, nz, 2, y, f0, f1, h, H);
+        rc = rhs(H, thv, f2); if (rc) return rc;
+        SrkStepArgs a;
+        a.p = p; a.nz = nz; a.y = y; a.y_prev = yprev; a.f0 = f0; a.f1 = f1; a.f2 = f2; a.t0 = c0; a.t1 = next_t;
+        a.y_out = y_out; a.j_lo = j; a.j_hi = j_hi; a.ts = ts_dev;
+        k_srk_step<<<ew_grid, 256, 0, s>>>(a);
+        count_launch(4);
+        curr = next_t;
+        j = j_hi;
+        ++k;
+        if (k > (1LL << 40)) return ODECOL_E_SHAPE;
+    }
+    if (status) { k_status_finite<<<p.B, 128, 0, s>>>(p, y, status); count_launch(); }
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 }  // namespace odecol

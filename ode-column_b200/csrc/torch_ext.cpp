@@ -320,9 +320,11 @@ std::vector<torch::Tensor> srk_fwd(const Problem& pr, const torch::Tensor& ts, c
     auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
     auto st = torch::zeros({pr.B()}, pr.iopts());
     torch::Tensor ysteps = save_steps > 0 ? torch::empty({save_steps + 1, pr.B(), 3 * pr.N()}, pr.fopts()) : torch::empty({0}, pr.fopts());
+    auto ws = pr.workspace(ODECOL_OP_SRK_FWD, T);
     check(odecol_srk_fwd(&pr.p, ts.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), dWp, dUp,
                          (uint64_t)seed, trial_offset, (float)dt, st.data_ptr<int32_t>(),
-                         save_steps > 0 ? ysteps.data_ptr<float>() : nullptr, nullptr, 0, pr.stream()), "srk_fwd");
+                         save_steps > 0 ? ysteps.data_ptr<float>() : nullptr, ws.data_ptr(), (size_t)ws.numel(), pr.stream()),
+          "srk_fwd");
     return {y, st, ysteps};
 }
 
