@@ -529,7 +529,8 @@ ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint3
     return d;
 }
 
-struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv; };
+struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv;
+                 int two_products; };     // 1: drop the A_hi . B_lo term and never stage B_lo (experiment, ODECOL_DW_2X=1)
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -571,14 +572,14 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, stage_bytes);
+                mbar_expect_tx(fb, ds.two_products ? 3 * op_bytes : stage_bytes);
                 const int row = r0 + kb * DW_BK;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     tma_load_2d(base + m * box_bytes, &mA_hi, fb, i0 + 32 * m, row);
                     tma_load_2d(base + op_bytes + m * box_bytes, &mA_lo, fb, i0 + 32 * m, row);
                     tma_load_2d(base + 2 * op_bytes + m * box_bytes, &mB_hi, fb, k0 + 32 * m, row);
-                    tma_load_2d(base + 3 * op_bytes + m * box_bytes, &mB_lo, fb, k0 + 32 * m, row);
+                    if (!ds.two_products) tma_load_2d(base + 3 * op_bytes + m * box_bytes, &mB_lo, fb, k0 + 32 * m, row);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -601,7 +602,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 for (int k = 0; k < DW_BK / 8; ++k, ++j) {
                     const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);   // next 8-row swizzle atom
                     umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
-                    umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                    if (!ds.two_products) umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
                     umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
                 }
                 umma_commit(empty0 + 8 * stage);
@@ -714,7 +715,7 @@ int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K
     int z = 2;
     int rows = (Kp / DW_BK + z - 1) / z * DW_BK;
     ds.rows_per_split = rows; ds.Z = (Kp + rows - 1) / rows;
-    ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C;
+    ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C; ds.two_products = 0;
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
     if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s) != cudaSuccess) return ODECOL_E_CUDA;
@@ -787,6 +788,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     if (rows < DW_BK) rows = DW_BK;
     ds.rows_per_split = rows; ds.Z = (ds.total_rows + rows - 1) / rows;
     ds.N = p.N; ds.Kaug = Kaug; ds.ld_w = p.ld_w; ds.grad_W = grad_W;
+    { const char* e2 = getenv("ODECOL_DW_2X"); ds.two_products = e2 ? (atoi(e2) != 0) : 0; }
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
     const size_t dw_smem = (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024;
     static bool dw_configured = false;
