@@ -12,7 +12,7 @@ The solvers run only on CUDA through the C ABI in ``include/odecol.h``; importin
 from .model import (ColumnArea, ColumnAreaWTA, ColumnNetwork, ColumnNetworkXOR, LinearForm, compute_firing_rate,
                     load_config, pack_w_aug, soft_clamp, torch_interp)
 from .losses import fr_to_binary, huber_loss_wta, huber_rate_loss, min_max, parity_readout, xor_readout
-from .solvers import odeint, odeint_adjoint, sdeint
+from .solvers import odeint, odeint_adjoint, sdeint, sdeint_adjoint
 from .stimulus import compress_knots, step_knots
 from .synthetic import SyntheticColumnSheet
 from .wongwang import get_data, make_ds_wwp
@@ -23,7 +23,7 @@ __all__ = [
     "ColumnArea", "ColumnAreaWTA", "ColumnNetwork", "ColumnNetworkXOR", "SyntheticColumnSheet", "LinearForm",
     "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug",
     "min_max", "fr_to_binary", "huber_loss_wta", "huber_rate_loss", "xor_readout", "parity_readout",
-    "odeint", "odeint_adjoint", "sdeint", "compress_knots", "step_knots", "distributed",
+    "odeint", "odeint_adjoint", "sdeint", "sdeint_adjoint", "compress_knots", "step_knots", "distributed",
     "make_ds_wwp", "get_data", "wongwang",
 ]
 __version__ = "0.1.0"

@@ -818,14 +818,19 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : true);
     cudaStream_t side = nullptr;
     cudaEvent_t ev_replay = nullptr, ev_dw = nullptr;
+    struct SideGuard {                               // released on every return path (work already enqueued completes first)
+        cudaStream_t& st; cudaEvent_t& a; cudaEvent_t& b;
+        ~SideGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); if (st) cudaStreamDestroy(st); }
+    } side_guard{side, ev_replay, ev_dw};
     if (overlap) {
         if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev_replay, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev_dw, cudaEventDisableTiming) != cudaSuccess) {
             if (side) cudaStreamDestroy(side);
             if (ev_replay) cudaEventDestroy(ev_replay);
+            if (ev_dw) cudaEventDestroy(ev_dw);
             cudaGetLastError();
-            side = nullptr; overlap = false;
+            side = nullptr; ev_replay = ev_dw = nullptr; overlap = false;
         }
     }
     const size_t ckpl = (size_t)L.Np * L.Bp;
@@ -907,11 +912,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         count_launch();
         if (overlap) cudaEventRecord(ev_dw, s);
     }
-    if (side) {                                      // every replay has been awaited by the caller's stream
-        cudaEventDestroy(ev_replay);
-        cudaEventDestroy(ev_dw);
-        cudaStreamDestroy(side);
-    }
+    // every replay has been awaited by the caller's stream; side_guard releases the stream and the events
     if (grad_y0) {
         k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);
         count_launch();

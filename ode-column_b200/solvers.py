@@ -327,3 +327,14 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
             if dW.shape != (n_steps, setup.B):
                 raise ValueError(f"odecol: bm produced increments of shape {tuple(dW.shape)}")
     return _EMFunction.apply(y0, setup.lf.W_aug, setup, dW, seed, int(trial_offset), dt, n_steps, sel_long, sel_i32, stats)
+
+
+def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e-3, adaptive=False, adjoint_adaptive=False,
+                   rtol=1e-5, adjoint_rtol=1e-5, atol=1e-4, adjoint_atol=1e-4, dt_min=1e-5, options=None,
+                   adjoint_options=None, adjoint_params=None, names=None, logqp=False, extra=False,
+                   extra_solver_state=None, **kwargs):
+    """Signature of ``torchsde.sdeint_adjoint`` (imported but never called by the reference scripts,
+    scripts/wta_ode.py:9, xor_ode.py:2, parity_ode.py:10).  The fused solvers already run their backward pass inside a
+    kernel from the saved solver states, so this is ``sdeint``; the adjoint_* arguments are accepted for compatibility."""
+    return sdeint(sde, y0, ts, bm=bm, method=method, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
+                  options=options, names=names, logqp=logqp, extra=extra, extra_solver_state=extra_solver_state, **kwargs)

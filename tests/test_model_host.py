@@ -199,3 +199,22 @@ def test_compress_knots_property_random_tables():
             assert torch.equal(interp_knots(t, tv, table), interp_knots(t, kt, ku))
 
     check()
+
+
+def test_the_reference_scripts_import_lines_work_against_odecol():
+    # scripts/wta_ode.py:9-14, xor_ode.py:2-7, parity_ode.py:10-16 with the package names swapped
+    from odecol import sdeint, sdeint_adjoint                      # from torchsde import sdeint, sdeint_adjoint
+    from odecol import odeint, odeint_adjoint                      # from torchdiffeq import odeint, odeint_adjoint
+    from odecol import ColumnAreaWTA, ColumnNetworkXOR, ColumnNetwork, ColumnArea      # from src.coupled_columns import ...
+    from odecol import load_config, compute_firing_rate, soft_clamp, torch_interp, min_max, fr_to_binary, huber_loss_wta  # src.utils
+    from odecol import make_ds_wwp, get_data                       # scripts/wta_ode.py:56-107 (uses src.ww_model.DM)
+    import inspect
+    for fn, names in ((odeint, ("func", "y0", "t", "rtol", "atol", "method", "options", "event_fn")),
+                      (odeint_adjoint, ("func", "y0", "t", "adjoint_rtol", "adjoint_atol", "adjoint_method", "adjoint_options", "adjoint_params")),
+                      (sdeint, ("sde", "y0", "ts", "bm", "method", "dt", "adaptive", "rtol", "atol", "dt_min", "options", "names",
+                                "logqp", "extra", "extra_solver_state")),
+                      (sdeint_adjoint, ("sde", "y0", "ts", "bm", "method", "adjoint_method", "dt", "adaptive", "adjoint_adaptive",
+                                        "adjoint_params", "names"))):
+        params = inspect.signature(fn).parameters
+        assert all(n in params for n in names), (fn.__name__, [n for n in names if n not in params])
+    assert list(inspect.signature(sdeint).parameters)[:4] == ["sde", "y0", "ts", "bm"]
