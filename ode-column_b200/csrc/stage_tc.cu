@@ -99,7 +99,7 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     for (int i = 0; i < 2; ++i) L.off_Y[i] = take(3 * plane);
     for (int i = 0; i < 4; ++i) L.off_RT[i] = take(plane);           // r of stages 1..4
     L.off_done = take((size_t)(L.Bp / L.TN) + 64);          // one uint32 per trial tile (floats == 4 bytes)
-    L.off_inv = take(3ull * p.N);                           // component -> selection position (checkpoint mode)
+    L.off_inv = take(3ull * p.N + 4);                       // component -> selection position (checkpoint mode) + F flag
     L.total = o;
     return L;
 }

@@ -546,10 +546,16 @@ static __global__ void k_split_pad(const float* __restrict__ src, int rows, int 
 }
 
 // component -> position in the selection (-1: not selected); sel == NULL selects everything in order
+// inv[n3] = 1 iff some F component (index >= 2 n3 / 3) is selected: F never feeds back into the dynamics, so when the
+// loss does not read it the forward sweep (checkpoint mode) need not advance it and its adjoint is identically zero
 static __global__ void k_tc_build_inv(const int* __restrict__ sel, int G, int n3, int* __restrict__ inv) {
     for (int e = threadIdx.x; e < n3; e += blockDim.x) inv[e] = sel ? -1 : e;
+    if (threadIdx.x == 0) inv[n3] = sel ? 0 : 1;
     __syncthreads();
-    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) inv[sel[g]] = g;
+    if (sel) for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        inv[sel[g]] = g;
+        if (sel[g] >= 2 * (n3 / 3)) inv[n3] = 1;
+    }
 }
 
 // out[b][g] = y[b][sel[g]]
@@ -648,10 +654,12 @@ struct FwdEpiT {
     int dbg_skip;          // diagnostics: 1 skip trajectory stores, 2 skip operand stores, 4 skip phi, 8 skip all stores
     float inv_tm, inv_ta, inv_ts;
     float t0, t1, dt;
+    int needF;             // stage 4: advance F (always, except in checkpoint mode when no F component is selected)
 
     ODECOL_DEVINL void prepare() {
         t0 = __ldg(t + n); t1 = __ldg(t + n + 1);
         dt = __fsub_rn(t1, t0);
+        needF = (S == 4 && ysel_row && inv && !traj_row) ? __ldg(inv + 3 * p.N) : 1;
     }
 
     // One float4 group (4 trials) of population i: what stage S reads from the scratch planes.
@@ -660,7 +668,7 @@ struct FwdEpiT {
         L.V0 = ld4s(V0T + oq); L.A0 = ld4s(A0T + oq); L.R1 = ld4s(RsT[0] + oq);
         if (S >= 2) { L.k1V = ld4s(K1T + oq); L.R2 = ld4s(RsT[1] + oq); }
         if (S >= 3) { L.k2V = ld4s(K2T + oq); L.R3 = ld4s(RsT[2] + oq); }
-        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); L.F0 = ld4s(F0T + oq); }
+        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); if (needF) L.F0 = ld4s(F0T + oq); }
     }
     ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
 
@@ -711,6 +719,7 @@ struct FwdEpiT {
                 if (S == 4) {
                     nV = v0 + ((&k1V.x)[e] + 3.f * ((&k2V.x)[e] + (&k3V.x)[e]) + dV) * dt * 0.125f;
                     nA = a0 + (k1A + 3.f * (k2A + k3A) + dA) * dt * 0.125f;
+                    if (needF) {
                     const float f0 = (&F0.x)[e];
                     const float k1F = ((&R1.x)[e] - f0) * inv_ts;
                     const float f2 = f0 + dt * k1F * third;
@@ -720,6 +729,7 @@ struct FwdEpiT {
                     const float f4 = f0 + dt * (k1F - k2F + k3F);
                     const float k4F = (r - f4) * inv_ts;
                     nF = f0 + (k1F + 3.f * (k2F + k3F) + k4F) * dt * 0.125f;
+                    }
                 }
                 oNV[e] = nV; oNA[e] = nA; oNF[e] = nF;
                 if (DRT_nxt) phi_dphi_fast(nV - nA, oR[e], oD[e]);
@@ -734,7 +744,7 @@ struct FwdEpiT {
             if (S == 4) {
                 st4s(V1T + oq, make_float4(oNV[0], oNV[1], oNV[2], oNV[3]));
                 st4s(A1T + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
-                st4s(F1T + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
+                if (needF) st4s(F1T + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
             }
             if (store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
             const int b0 = n0 + g * TNq + q4;

@@ -33,16 +33,19 @@ struct BwdEpiT {
     const int* inv;        // [3N]
     float gamma, inv_tm, inv_ta, inv_ts;
     float dt, h8p;
+    int needF;             // 0: no F component carries a loss gradient -> lambda_F is identically zero, its plane is never touched
 
     ODECOL_DEVINL void prepare() {
         dt = __fsub_rn(__ldg(t + n + 1), __ldg(t + n));
         h8p = n > 0 ? __fsub_rn(__ldg(t + n), __ldg(t + n - 1)) * 0.125f : 0.f;
+        needF = __ldg(inv + 3 * p.N);
     }
 
     struct Group { float4 aV, aA, dr, lV, lA, lF, p4V, p4A, p3V, p3A, gv, ga, gf; };
     ODECOL_DEVINL void load_group(Group& L, size_t oq, size_t pl, int b0, int gV, int gA, int gF) const {
         L.dr = ld4s(DRT + oq);
-        L.lV = ld4s(lamT + oq); L.lA = ld4s(lamT + pl + oq); L.lF = ld4s(lamT + 2 * pl + oq);
+        L.lV = ld4s(lamT + oq); L.lA = ld4s(lamT + pl + oq);
+        L.lF = needF ? ld4s(lamT + 2 * pl + oq) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (S == 1) { L.aV = ld4s(acurT + oq); L.aA = ld4s(acurT + pl + oq); }
         if (S <= 3) { L.p4V = ld4s(b4T + oq); L.p4A = ld4s(b4T + pl + oq); }
         if (S == 2) { L.p3V = ld4s(b3T + oq); L.p3A = ld4s(b3T + pl + oq); }
@@ -132,7 +135,7 @@ struct BwdEpiT {
             float* sdst = S == 4 ? b4T : S == 3 ? b3T : S == 2 ? b4T : lamT;
             st4s(sdst + oq, make_float4(sV[0], sV[1], sV[2], sV[3]));
             st4s(sdst + pl + oq, make_float4(sA[0], sA[1], sA[2], sA[3]));
-            if (S == 1) st4s(lamT + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
+            if (S == 1 && needF) st4s(lamT + 2 * pl + oq, make_float4(sF[0], sF[1], sF[2], sF[3]));
             if (S == 2) {
                 st4s(acurT + oq, make_float4(nV[0], nV[1], nV[2], nV[3]));
                 st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
@@ -681,7 +684,7 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     for (int i = 0; i < 3; ++i) L.off_RT[i] = take(plane);
     for (int i = 0; i < 8; ++i) L.off_DRT[i] = take(plane);
     L.off_lam = take(3 * plane); L.off_b4 = take(2 * plane); L.off_b3 = take(2 * plane); L.off_acur = take(2 * plane);
-    L.off_inv = take(sizeof(int) * 3ull * p.N);
+    L.off_inv = take(sizeof(int) * (3ull * p.N + 4));      // + the "an F component is selected" flag
     L.off_done = take(sizeof(unsigned int) * (size_t)(L.Bp / L.TN) + 256);
     L.total = o;
     return L;
