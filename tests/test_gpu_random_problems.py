@@ -1,0 +1,72 @@
+"""Differential test on problem shapes the reference networks do not reach: every register-tile size of the on-chip
+family (KP = 40 / 64 / 96 / 128), two trials per warp with and without it, more stimulus channels than lanes (the
+uncached knot path), ragged batches -- rk4 forward and reverse through the extension, against the CPU oracle's autograd;
+and the same problems forced through the staged FFMA and tensor families."""
+import numpy as np
+import pytest
+import torch
+
+import odecol
+from oracle import rhs as orhs, solvers as S
+from oracle.column_model import LinearForm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+#           N  n_in  B  K
+SHAPES = [(8, 1, 3, 2), (16, 16, 5, 4), (16, 20, 3, 3), (8, 40, 2, 3), (40, 8, 4, 5), (72, 10, 2, 3), (120, 7, 3, 4),
+          (24, 32, 1, 6)]
+
+
+def _problem(N, n_in, B, K, seed):
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal((N, N)) * 0.04).astype(np.float32)
+    U = (rng.standard_normal((N, n_in)) * 0.02).astype(np.float32)
+    bias = (rng.random(N) * 0.3).astype(np.float32)
+    kappa = (rng.random(N) * 1.5).astype(np.float32)
+    lf = LinearForm(W=W, U=U, bias=bias, kappa=kappa, sigma=np.zeros(3 * N, np.float32), tau_s=5e-4, tau_m=0.02, tau_a=10.0,
+                    resistance=80.0)
+    T = 48
+    tv = np.linspace(0, (T - 1) * 1e-4, T, dtype=np.float32)
+    kt = np.sort(rng.random(K).astype(np.float32)) * tv[-1] * 1.2 - 0.1 * tv[-1]      # knots partly outside the solve window
+    kt = np.unique(kt)
+    while len(kt) < K:
+        kt = np.unique(np.append(kt, kt[-1] + 1e-4 * (1 + len(kt))).astype(np.float32))
+    ku = (rng.random((B, K, n_in)) * 20).astype(np.float32)
+    y0 = np.concatenate((rng.random((B, N)) * 8 - 10, rng.random((B, N)), rng.random((B, N)) * 3), 1).astype(np.float32)
+    return lf, tv, kt, ku, y0
+
+
+@pytest.mark.parametrize("family", [0, "staged", "tensor"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "N%d_in%d_B%d_K%d" % s)
+def test_rk4_forward_and_reverse_on_random_problems(shape, family):
+    N, n_in, B, K = shape
+    lf, tv, kt, ku, y0 = _problem(N, n_in, B, K, seed=N * 1000 + n_in)
+    ext = odecol._native.ext()
+    # oracle
+    ode = orhs.UnifiedColumnODE(lf, kt, ku, requires_grad=True)
+    y0o = torch.tensor(y0, requires_grad=True)
+    yo = S.odeint_rk4(ode, y0o, torch.tensor(tv))
+    gen = torch.Generator().manual_seed(N)
+    wgt = torch.randn(yo.shape, generator=gen)
+    (yo * wgt).sum().backward()
+    assert torch.isfinite(yo).all() and float(yo[..., :N].abs().max()) < 200
+    # product, through the extension (arbitrary W_aug, not one of the module classes)
+    ld = (N + n_in + 1 + 3) // 4 * 4
+    W_aug = torch.zeros(N, ld)
+    W_aug[:, :N] = torch.tensor(lf.W); W_aug[:, N:N + n_in] = torch.tensor(lf.U); W_aug[:, N + n_in] = torch.tensor(lf.bias)
+    flags = {0: 0, "staged": ext.FLAG_FORCE_STAGED, "tensor": ext.FLAG_FORCE_TENSOR}[family]
+    prob = ext.Problem(W_aug.to(DEV), torch.tensor(lf.kappa).to(DEV), None, torch.tensor(kt).to(DEV), torch.tensor(ku).to(DEV),
+                       n_in, B, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, flags)
+    assert prob.kernel_family(ext.OP_RK4_FWD) == {0: 0, "staged": 1, "tensor": 2}[family]
+    t_dev = torch.tensor(tv).to(DEV)
+    y = ext.rk4_fwd(prob, t_dev, torch.tensor(y0).to(DEV), 1)
+    gy0, gW = ext.rk4_bwd(prob, t_dev, y, wgt.to(DEV).contiguous(), None)
+    scale = lambda a: float(a.abs().max().clamp_min(1e-30))
+    et = float((y.cpu() - yo.detach()).abs().max()) / scale(yo.detach())
+    e0 = float((gy0.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
+    gWo = torch.cat((ode.W.grad, ode.U.grad, ode.bias.grad[:, None]), 1)
+    eW = float((gW.cpu()[:, :N + n_in + 1] - gWo).abs().max()) / scale(gWo)
+    print(f"\n[{shape} family {family}] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W_aug {eW:.1e}")
+    assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5
+    assert float(gW.cpu()[:, N + n_in + 1:].abs().max()) == 0 if ld > N + n_in + 1 else True     # padding columns stay zero
