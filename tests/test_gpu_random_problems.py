@@ -70,3 +70,52 @@ def test_rk4_forward_and_reverse_on_random_problems(shape, family):
     print(f"\n[{shape} family {family}] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W_aug {eW:.1e}")
     assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5
     assert float(gW.cpu()[:, N + n_in + 1:].abs().max()) == 0 if ld > N + n_in + 1 else True     # padding columns stay zero
+
+
+@pytest.mark.parametrize("method", ["srk", "euler"])
+@pytest.mark.parametrize("shape", [(8, 1, 3, 2), (16, 20, 3, 3), (8, 40, 2, 3), (72, 10, 2, 3), (120, 7, 3, 4)],
+                         ids=lambda s: "N%d_in%d_B%d_K%d" % s)
+def test_sde_solvers_on_random_problems(shape, method):
+    """srk / Euler-Maruyama with supplied increments: forward + reverse on the on-chip family, forward on the staged one."""
+    N, n_in, B, K = shape
+    lf, tv, kt, ku, y0 = _problem(N, n_in, B, K, seed=N * 77 + n_in)
+    lf.sigma[:] = np.random.default_rng(N).random(3 * N).astype(np.float32) * 3.0
+    ext = odecol._native.ext()
+    tvt = torch.tensor(tv)
+    dt = 2.5e-4                                             # 2.5 grid intervals per solver step: interpolated outputs
+    n_steps = len(S.em_step_schedule(tvt, dt))
+    gen = torch.Generator().manual_seed(N + 5)
+    W, U = S.sample_w_u(n_steps, B, dt, gen)
+    ode = orhs.UnifiedColumnODE(lf, kt, ku, requires_grad=True)
+    y0o = torch.tensor(y0, requires_grad=True)
+    if method == "srk":
+        yo = S.sdeint_srk(ode, y0o, tvt, S.TabulatedBrownianU(W, U), dt=dt)
+    else:
+        yo = S.sdeint_euler(ode, y0o, tvt, S.TabulatedBrownian(W), dt=dt)
+    wgt = torch.randn(yo.shape, generator=gen)
+    (yo * wgt).sum().backward()
+    ld = (N + n_in + 1 + 3) // 4 * 4
+    W_aug = torch.zeros(N, ld)
+    W_aug[:, :N] = torch.tensor(lf.W); W_aug[:, N:N + n_in] = torch.tensor(lf.U); W_aug[:, N + n_in] = torch.tensor(lf.bias)
+    mk = lambda flags: ext.Problem(W_aug.to(DEV), torch.tensor(lf.kappa).to(DEV), torch.tensor(lf.sigma).to(DEV),
+                                   torch.tensor(kt).to(DEV), torch.tensor(ku).to(DEV), n_in, B, lf.tau_s, lf.tau_m, lf.tau_a,
+                                   lf.resistance, flags)
+    t_dev, y0d = tvt.to(DEV), torch.tensor(y0).to(DEV)
+    Wd, Ud = W[:, :, 0].contiguous().to(DEV), U[:, :, 0].contiguous().to(DEV)
+    scale = lambda a: float(a.abs().max().clamp_min(1e-30))
+    gWo = torch.cat((ode.W.grad, ode.U.grad, ode.bias.grad[:, None]), 1)
+    if method == "srk":
+        y, st, ysteps = ext.srk_fwd(mk(0), t_dev, y0d, Wd, Ud, 0, 0, dt, n_steps)
+        gy0, gW = ext.srk_bwd(mk(0), t_dev, ysteps, Wd, Ud, 0, 0, wgt.to(DEV).contiguous(), None, dt)
+        ys, _, _ = ext.srk_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, Ud, 0, 0, dt, 0)
+    else:
+        y, _, _, st, ysteps = ext.em_fwd(mk(0), t_dev, y0d, Wd, 0, 0, dt, False, 0.0, 0.0, 0.0, n_steps)
+        gy0, gW = ext.em_bwd(mk(0), t_dev, ysteps, wgt.to(DEV).contiguous(), None, dt)
+        ys, *_ = ext.em_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, 0, 0, dt, False, 0.0, 0.0, 0.0, 0)
+    et = float((y.cpu() - yo.detach()).abs().max()) / scale(yo.detach())
+    es = float((ys.cpu() - yo.detach()).abs().max()) / scale(yo.detach())
+    e0 = float((gy0.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
+    eW = float((gW.cpu()[:, :N + n_in + 1] - gWo).abs().max()) / scale(gWo)
+    print(f"\n[{method} {shape}] trajectory on-chip {et:.1e} staged {es:.1e}  grad y0 {e0:.1e}  grad W_aug {eW:.1e}")
+    assert int(st.abs().sum()) == 0
+    assert et < 1e-5 and es < 2e-5 and e0 < 5e-5 and eW < 5e-5
