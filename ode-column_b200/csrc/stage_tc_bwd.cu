@@ -164,6 +164,22 @@ struct BwdEpiT {
 // (which reads all four slots of the current set) can run after the chain.  A trial tile's next contraction waits on
 // a per-trial-tile counter of finished population-tile epilogues (cumulative over launches: `done_base`).
 // ---------------------------------------------------------------------------------------------------------------
+// (the dW contraction's shape and MN-major descriptor are defined further down, next to the stand-alone k_tc_dw; the
+// chain kernel can run the dW contraction of its step as a fifth phase, see k_tc_bwd_chain)
+constexpr int DW_BK = 32;        // rows (trials) per K block = four 8-row swizzle atoms
+constexpr int DW_T = 128;        // output tile: 128 x 128
+struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv;
+                 int two_products; };     // 1: drop the A_hi . B_lo term and never stage B_lo (experiment, ODECOL_DW_2X=1)
+ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;                  // leading byte offset: next 32-wide block along M/N
+    d |= (uint64_t)(sbo >> 4) << 32;                  // stride byte offset: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B: the only MN-major layout for 32-bit operands
+    return d;
+}
+
 struct BwdChainArgs {
     DevProblem p;
     TileGeom tg;
@@ -177,6 +193,8 @@ struct BwdChainArgs {
     const float* grad_y; const int* inv;
     float gamma, inv_tm, inv_ta, inv_ts;
     unsigned int* done; unsigned int done_base;
+    int fuse_dw;               // 1: run the dW contraction of this step as a fifth phase (maps dA_* / dB_*, shape ds)
+    DwShape ds;
 };
 
 template <int S>
@@ -196,7 +214,9 @@ ODECOL_DEVINL void chain_epilogue(const BwdChainArgs& a, int m_tile, int row, in
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant__ CUtensorMap mW_lo,
-               const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo, BwdChainArgs a) {
+               const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+               const __grid_constant__ CUtensorMap dA_hi, const __grid_constant__ CUtensorMap dA_lo,
+               const __grid_constant__ CUtensorMap dB_hi, const __grid_constant__ CUtensorMap dB_lo, BwdChainArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
     __shared__ uint32_t tmem_base_slot;
@@ -211,6 +231,17 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
     const uint32_t acc_stride = (uint32_t)ts.TN;
     uint32_t ncols = 32;
     while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
+    if (a.fuse_dw) ncols = 512;                                 // the dW phase uses (kMainAcc + 1) x 128 accumulator columns
+    // Fifth phase (fuse_dw): the dW contraction of this step, work item = (output tile, row split) as in k_tc_dw.  Its
+    // operands are complete long before the chain ends -- slot 3 was written by the previous step, slots 2 / 1 / 0 by the
+    // epilogues of stages 4 / 3 / 2 of this step -- so the MMA warp contracts dW while the stage-1 epilogues still
+    // stream their bookkeeping through HBM, and the step needs one launch instead of two.
+    const DwShape& ds = a.ds;
+    const int dw_tiles = ds.MT * ds.NT, dw_items = a.fuse_dw ? dw_tiles * ds.Z : 0;
+    constexpr uint32_t dw_box = DW_BK * 128, dw_op = 4 * dw_box, dw_stage = 4 * dw_op;
+    // both phases address the ring with the same stage stride, so that a ring slot means the same bytes before and after
+    // the transition (the `empty` barrier of slot s then covers exactly the bytes the next load overwrites)
+    const uint32_t stride = a.fuse_dw ? (stage_bytes > dw_stage ? stage_bytes : dw_stage) : stage_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -243,7 +274,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                     asm volatile("fence.proxy.async;" ::: "memory");
                     for (int kb = 0; kb < ts.KB; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
+                        const uint32_t base = ring + stage * stride, fb = full0 + 8 * stage;
                         mbar_expect_tx(fb, stage_bytes);
                         tma_load_2d(base, &mW_hi, fb, kb * BK, m0);
                         tma_load_2d(base + a_bytes, &mW_lo, fb, kb * BK, m0);
@@ -251,6 +282,45 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                         tma_load_2d(base + 2 * a_bytes + b_bytes, &mA_lo, fb, kb * BK, n0 + row0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                }
+            }
+            // ---- dW phase: rows = stacked (operand slot, trial) of this step's operand set
+            for (int item = blockIdx.x; item < dw_items; item += gridDim.x) {
+                const int tile = item % dw_tiles, z = ds.Z - 1 - item / dw_tiles;   // last rows (slots 3, 2: ready first) first
+                const int i0 = (tile % ds.MT) * DW_T, k0 = (tile / ds.MT) * DW_T;
+                const int r0 = z * ds.rows_per_split;
+                int r1 = r0 + ds.rows_per_split;
+                if (r1 > ds.total_rows) r1 = ds.total_rows;
+                const int KBd = (r1 - r0) / DW_BK;
+                // rows of slot s < 3 are written by the epilogues of stage s + 2 of this step (q = 2 - s): wait once, up
+                // front, for every trial tile the item's rows touch
+                for (int slot = r0 / a.Bp; slot <= (r1 - 1) / a.Bp && slot < 3 && KBd > 0; ++slot) {
+                    const int lo = (r0 > slot * a.Bp ? r0 - slot * a.Bp : 0) / ts.TN;
+                    const int hi = ((r1 < (slot + 1) * a.Bp ? r1 - slot * a.Bp : a.Bp) - 1) / ts.TN;
+                    const unsigned int need = a.done_base + (unsigned int)ts.MT * (unsigned int)(3 - slot);
+                    for (int nt = lo; nt <= hi; ++nt) {
+                        uint32_t spins = 0;
+                        while ((int)(ld_acquire_u32(a.done + nt) - need) < 0) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 26)) __trap();
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                for (int kb = 0; kb < KBd; ++kb) {
+                    const int row = r0 + kb * DW_BK;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t base = ring + stage * stride, fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, ds.two_products ? 3 * dw_op : dw_stage);
+                    const int arow = row;                             // dA_* are the maps of this step's operand set
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        tma_load_2d(base + m * dw_box, &dA_hi, fb, i0 + 32 * m, arow);
+                        tma_load_2d(base + dw_op + m * dw_box, &dA_lo, fb, i0 + 32 * m, arow);
+                        tma_load_2d(base + 2 * dw_op + m * dw_box, &dB_hi, fb, k0 + 32 * m, row);
+                        if (!ds.two_products) tma_load_2d(base + 3 * dw_op + m * dw_box, &dB_lo, fb, k0 + 32 * m, row);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -267,7 +337,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                     for (int kb = 0; kb < ts.KB; ++kb) {
                         mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
-                        const uint32_t base = ring + stage * stage_bytes;
+                        const uint32_t base = ring + stage * stride;
                         const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
                         const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
 #pragma unroll
@@ -283,6 +353,38 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                     umma_commit(tfull);
                     tphase ^= 1;
                 }
+            }
+            // ---- dW phase: both operands MN-major, 128 x 128 accumulators
+            const uint32_t idesc_dw = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
+                                      ((uint32_t)(DW_T >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t d_small_dw = tmem_base + kMainAcc * DW_T;
+            for (int item = blockIdx.x; item < dw_items; item += gridDim.x) {
+                const int z = ds.Z - 1 - item / dw_tiles;
+                const int r0 = z * ds.rows_per_split;
+                int r1 = r0 + ds.rows_per_split;
+                if (r1 > ds.total_rows) r1 = ds.total_rows;
+                const int KBd = (r1 - r0) / DW_BK;
+                mbar_wait(tempty, tphase ^ 1);
+                tc_fence_after();
+                int j = 0;
+                for (int kb = 0; kb < KBd; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t base = ring + stage * stride;
+                    const uint64_t a_hi = make_smem_desc_mn(base, ds.lbo, ds.sbo), a_lo = make_smem_desc_mn(base + dw_op, ds.lbo, ds.sbo);
+                    const uint64_t b_hi = make_smem_desc_mn(base + 2 * dw_op, ds.lbo, ds.sbo), b_lo = make_smem_desc_mn(base + 3 * dw_op, ds.lbo, ds.sbo);
+#pragma unroll
+                    for (int k = 0; k < DW_BK / 8; ++k, ++j) {
+                        const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);
+                        umma_tf32(d_small_dw, a_lo + adv, b_hi + adv, idesc_dw, j != 0);
+                        if (!ds.two_products) umma_tf32(d_small_dw, a_hi + adv, b_lo + adv, idesc_dw, 1);
+                        umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc_dw, j >= kMainAcc);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull);
+                tphase ^= 1;
             }
         }
     } else {
@@ -330,6 +432,38 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
                 if (etid == 0) atomicAdd(a.done + nt, 1u);
             }
+        }
+        // ---- dW phase: accumulate the finished 128 x 128 tile into grad_W (float atomics), as k_tc_dw does
+        for (int item = blockIdx.x; item < dw_items; item += gridDim.x) {
+            const int tile = item % dw_tiles, z = ds.Z - 1 - item / dw_tiles;   // last rows (slots 3, 2: ready first) first
+            const int i0 = (tile % ds.MT) * DW_T, k0 = (tile / ds.MT) * DW_T;
+            const int r0 = z * ds.rows_per_split;
+            int r1 = r0 + ds.rows_per_split;
+            if (r1 > ds.total_rows) r1 = ds.total_rows;
+            const bool any = (r1 - r0) / DW_BK > 0;
+            const int i = i0 + quarter * 32 + lane;
+            mbar_wait(tfull, tphase);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 32);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                uint32_t u[kMainAcc + 1][4];
+#pragma unroll
+                for (int c = 0; c <= kMainAcc; ++c) tmem_ld4_issue(lane_base + c * DW_T + 4 * qq, u[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float sum = __uint_as_float(u[kMainAcc][e]);
+#pragma unroll
+                    for (int c = 0; c < kMainAcc; ++c) sum += __uint_as_float(u[c][e]);
+                    const int k = k0 + g * 32 + 4 * qq + e;
+                    if (any && i < ds.N && k < ds.Kaug) atomicAdd(ds.grad_W + (size_t)i * ds.ld_w + k, sum);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            tphase ^= 1;
         }
     }
     tc_fence_before();
@@ -519,21 +653,6 @@ __global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, in
 // and one tcgen05.mma (K = 8) consumes two atoms, i.e. 1024 bytes.
 // Same warp roles as k_tc_contract; one output tile and one slice of the rows per CTA; epilogue = float atomics.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DW_BK = 32;        // rows (trials) per K block = four 8-row swizzle atoms
-constexpr int DW_T = 128;        // output tile: 128 x 128
-
-ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(lbo >> 4) << 16;                  // leading byte offset: next 32-wide block along M/N
-    d |= (uint64_t)(sbo >> 4) << 32;                  // stride byte offset: next 8-row group along K
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B: the only MN-major layout for 32-bit operands
-    return d;
-}
-
-struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv;
-                 int two_products; };     // 1: drop the A_hi . B_lo term and never stage B_lo (experiment, ODECOL_DW_2X=1)
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -804,7 +923,12 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
     const char* pe = getenv("ODECOL_PERSISTENT");
     bool use_chain = pe ? atoi(pe) != 0 : true;
-    const size_t chain_smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)L.TN * BK * 4) + 1024;
+    // ODECOL_FUSE_DW=1: the dW contraction as a fifth phase of the chain launch instead of its own launch.  Measured on
+    // par with the default (separate launch + replay one step ahead): profiles/r1_session2.md section 5.
+    const char* fe = getenv("ODECOL_FUSE_DW");
+    const bool fuse_dw = use_chain && (fe ? atoi(fe) != 0 : false);
+    const size_t chain_stage = 2 * BM * BK * 4 + 2 * (size_t)L.TN * BK * 4, dw_stage_b = 4 * 4 * DW_BK * 128;
+    const size_t chain_smem = (size_t)STAGES * (fuse_dw && dw_stage_b > chain_stage ? dw_stage_b : chain_stage) + 1024;
     int chain_grid = MT * NT < num_sms() ? MT * NT : num_sms();
     if (use_chain) {
         int max_blocks = 0;
@@ -886,7 +1010,8 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             a.AVhi = AVhi; a.AVlo = AVlo; a.set = set; a.grad_y = grad_y; a.inv = inv; a.gamma = gamma;
             a.inv_tm = 1.0f / p.c.tau_m; a.inv_ta = 1.0f / p.c.tau_a; a.inv_ts = 1.0f / p.c.tau_s;
             a.done = done; a.done_base = (unsigned int)MT * 4u * (unsigned int)(T - 2 - n);
-            void* args[] = {&mWThi, &mWTlo, &mAVhi, &mAVlo, &a};
+            a.fuse_dw = fuse_dw ? 1 : 0; a.ds = ds;
+            void* args[] = {&mWThi, &mWTlo, &mAVhi, &mAVlo, &dAhi[set], &dAlo[set], &dBhi[rset], &dBlo[rset], &a};
             if (cudaLaunchCooperativeKernel((const void*)k_tc_bwd_chain, dim3(chain_grid), dim3(kThreads), args, chain_smem, s) != cudaSuccess)
                 return ODECOL_E_CUDA;
             count_launch();
@@ -911,8 +1036,10 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             replay(n - 1, side);
             cudaEventRecord(ev_replay, side);
         }
-        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds);
-        count_launch();
+        if (!(use_chain && fuse_dw)) {
+            k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds);
+            count_launch();
+        }
         if (overlap) cudaEventRecord(ev_dw, s);
     }
     // every replay has been awaited by the caller's stream; side_guard releases the stream and the events
