@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--time-points", type=int, default=1500)
     ap.add_argument("--dt", type=float, default=1e-4)
     ap.add_argument("--cpu-trials", type=int, default=1024, help="trials of the bounded CPU sample")
-    ap.add_argument("--cpu-time-points", type=int, default=41, help="grid points of the bounded CPU sample")
+    ap.add_argument("--cpu-time-points", type=int, default=81, help="grid points of the bounded CPU sample (a few seconds of CPU work per pass, ~10 GB of autograd state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--family", default=None, help="force a kernel family (staged, tensor)")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5", "small", "configs"],

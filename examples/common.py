@@ -12,9 +12,5 @@ CONFIG = os.path.join(ROOT, "config", "model.toml")
 
 
 def to_device(net, device):
-    net = net.to(device)
-    for m in [net] + list(net.modules()):
-        for k, v in list(vars(m).items()):
-            if torch.is_tensor(v) and not isinstance(v, torch.nn.Parameter):
-                setattr(m, k, v.to(device))
-    return net
+    import odecol
+    return odecol.move_to(net, device)

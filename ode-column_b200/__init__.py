@@ -10,7 +10,7 @@ Drop-in surface (reference src/coupled_columns.py, src/utils.py; torchdiffeq / t
 The solvers run only on CUDA through the C ABI in ``include/odecol.h``; importing the package does not need a GPU.
 """
 from .model import (ColumnArea, ColumnAreaWTA, ColumnNetwork, ColumnNetworkXOR, LinearForm, compute_firing_rate,
-                    load_config, pack_w_aug, soft_clamp, torch_interp)
+                    load_config, move_to, pack_w_aug, soft_clamp, torch_interp)
 from .losses import fr_to_binary, huber_loss_wta, huber_rate_loss, min_max, parity_readout, xor_readout
 from .solvers import odeint, odeint_adjoint, sdeint, sdeint_adjoint
 from .stimulus import compress_knots, step_knots
@@ -21,7 +21,7 @@ from . import _native
 
 __all__ = [
     "ColumnArea", "ColumnAreaWTA", "ColumnNetwork", "ColumnNetworkXOR", "SyntheticColumnSheet", "LinearForm",
-    "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug",
+    "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug", "move_to",
     "min_max", "fr_to_binary", "huber_loss_wta", "huber_rate_loss", "xor_readout", "parity_readout",
     "odeint", "odeint_adjoint", "sdeint", "sdeint_adjoint", "compress_knots", "step_knots", "distributed",
     "make_ds_wwp", "get_data", "wongwang",

@@ -380,3 +380,14 @@ class ColumnNetwork(_LinearFormNetwork):
 
     def _channels(self, stim):
         return stim.reshape(-1, stim.shape[-2], stim.shape[-1])                              # (T,4) -> (1,T,4)
+
+
+def move_to(network, device):
+    """``network.to(device)`` plus the plain-tensor attributes: like the reference, the drop-in modules keep masks,
+    constants, ``stim`` and ``time_vec`` as ordinary attributes (not buffers), which ``Module.to`` does not move."""
+    network = network.to(device)
+    for m in [network] + list(network.modules()):
+        for k, v in list(vars(m).items()):
+            if torch.is_tensor(v) and not isinstance(v, torch.nn.Parameter):
+                setattr(m, k, v.to(device))
+    return network

@@ -218,3 +218,11 @@ def test_the_reference_scripts_import_lines_work_against_odecol():
         params = inspect.signature(fn).parameters
         assert all(n in params for n in names), (fn.__name__, [n for n in names if n not in params])
     assert list(inspect.signature(sdeint).parameters)[:4] == ["sde", "y0", "ts", "bm"]
+
+
+def test_move_to_moves_plain_tensor_attributes(cfg, golden):
+    net = product_network("xor", cfg, golden["xor"])
+    net.stim = torch.tensor(golden["xor"]["stims"][0])
+    moved = odecol.move_to(net, torch.device("cpu"))
+    assert moved is net and moved.ff_source_mask.device.type == "cpu" and moved.stim.device.type == "cpu"
+    assert all(torch.is_tensor(v) for v in (moved.time_vec, moved.ff_target_mask))
