@@ -225,7 +225,7 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
  *   status   per trial, may be NULL: ODECOL_ST_NONFINITE if the final state is not finite
  *   y_steps  optional (n_steps+1, B, 3N): every solver state (needed by odecol_srk_bwd)
  * Networks beyond the on-chip family (N > 128 or a forced staged family) run the staged solver: three tensor-core drift
- * evaluations per step, forward only (y_steps must be NULL), workspace odecol_workspace_bytes(p, ODECOL_OP_SRK_FWD, T, 0);
+ * evaluations per step, workspace odecol_workspace_bytes(p, ODECOL_OP_SRK_FWD, T, 0) (and ODECOL_OP_SRK_BWD for the reverse sweep);
  * like the staged Euler-Maruyama it replays the step schedule on the host (one stream synchronisation at entry). */
 int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out,
                    const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, float dt,

@@ -87,9 +87,9 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
         case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
-        case ODECOL_OP_EM_BWD: return em_schedule_layout(T, n_steps).total;
+        case ODECOL_OP_EM_BWD: return small ? em_schedule_layout(T, n_steps).total : stage_sde_bwd_workspace_bytes(d, T);
         case ODECOL_OP_SRK_FWD: return small ? 0 : stage_srk_fwd_workspace_bytes(d, T);
-        case ODECOL_OP_SRK_BWD: return em_schedule_layout(T, n_steps).total;
+        case ODECOL_OP_SRK_BWD: return small ? em_schedule_layout(T, n_steps).total : stage_sde_bwd_workspace_bytes(d, T);
         default: return 0;
     }
 }
@@ -263,10 +263,9 @@ int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const flo
         return launch_em_fwd_small(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min,
                                    n_accept, n_reject, status, y_steps, cap, s);
     }
-    if (y_steps) return ODECOL_E_UNSUPPORTED;          // no staged Euler-Maruyama adjoint yet
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
     return stage_em_fwd(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min, n_accept, n_reject,
-                        status, workspace, workspace_bytes, s);
+                        status, y_steps, workspace, workspace_bytes, s);
 }
 
 int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
@@ -277,7 +276,12 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     if (rc) return rc;
     if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    if (!use_small(p, d)) {                              // staged reverse sweep (tensor-core VJPs)
+        if (misaligned(workspace)) return ODECOL_E_ALIGN;
+        g_launches.store(0, std::memory_order_relaxed);
+        return stage_sde_bwd(0, d, ts, T, y_steps, n_steps, nullptr, nullptr, 0, 0, grad_y, sel, G, dt, grad_y0, grad_W_aug,
+                             workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    }
     const EmScheduleLayout L = em_schedule_layout(T, n_steps);
     if (!workspace || workspace_bytes < L.total) return ODECOL_E_WORKSPACE;
     g_launches.store(0, std::memory_order_relaxed);
@@ -302,10 +306,9 @@ int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const fl
     if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
     if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
-    if (!use_small(p, d)) {                              // staged solver: forward only (no y_steps record)
-        if (y_steps) return ODECOL_E_UNSUPPORTED;
+    if (!use_small(p, d)) {                              // staged solver
         if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
-        return stage_srk_fwd(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, workspace, workspace_bytes,
+        return stage_srk_fwd(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
     }
     return launch_srk_fwd_small(d, ts, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps,
@@ -322,7 +325,12 @@ int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const fl
     if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
+    if (!use_small(p, d)) {
+        if (misaligned(workspace)) return ODECOL_E_ALIGN;
+        g_launches.store(0, std::memory_order_relaxed);
+        return stage_sde_bwd(1, d, ts, T, y_steps, n_steps, dW, dU, seed, trial_offset, grad_y, sel, G, dt, grad_y0, grad_W_aug,
+                             workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    }
     const EmScheduleLayout L = em_schedule_layout(T, n_steps);
     if (!workspace || workspace_bytes < L.total) return ODECOL_E_WORKSPACE;
     g_launches.store(0, std::memory_order_relaxed);

@@ -87,7 +87,7 @@ int stage_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y
                   const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
 int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
                  uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
-                 int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
+                 int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // staged Dormand-Prince 5(4), forward (stage_em.cu): per-trial control in rounds, drift on the tensor cores
 size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int T);
@@ -97,8 +97,13 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
 // staged torchsde srk (fixed step), forward (stage_em.cu)
 size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int T);
 int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
-                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, void* ws, size_t ws_bytes,
-                  cudaStream_t s);
+                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps, void* ws,
+                  size_t ws_bytes, cudaStream_t s);
+// staged discrete adjoints of the fixed-step Euler-Maruyama (which = 0) and srk (which = 1) solves
+size_t stage_sde_bwd_workspace_bytes(const DevProblem& p, int T);
+int stage_sde_bwd(int which, const DevProblem& p, const float* ts_dev, int T, const float* y_steps, int64_t n_steps,
+                  const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, const float* grad_y, const int* sel,
+                  int G, float dt, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // ---- family T (stage_tc.cu): the staged contraction on tcgen05 tensor cores (3xTF32) ------------------------------
 size_t tc_rk4_fwd_workspace_bytes(const DevProblem& p, int T);
@@ -113,6 +118,8 @@ int tc_rk4_fwd_ckpt(const DevProblem& p, const float* t_dev, int T, const float*
                     void* ckpt, size_t ckpt_bytes, void* ws, size_t ws_bytes, cudaStream_t s);
 int tc_rk4_bwd_ckpt(const DevProblem& p, const float* t_dev, int T, const void* ckpt, size_t ckpt_bytes, const float* grad_y,
                     const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_dw_accumulate(const float* Ahi, const float* Alo, const float* Bhi, const float* Blo, int rows, int Np, int KPa, int N,
+                     int Kaug, int ld_w, float* grad_W, cudaStream_t s);
 size_t tc_contract_tn_workspace_bytes(int M, int N, int K);
 int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_contract_workspace_bytes(int M, int N, int K);

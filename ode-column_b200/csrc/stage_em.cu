@@ -301,7 +301,7 @@ size_t stage_em_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_la
 
 int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
                  uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
-                 int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s) {
+                 int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s) {
     using namespace tc;
     const EmLayout L = em_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -320,6 +320,7 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(yprev, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (y_steps && cudaMemcpyAsync(y_steps, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
     if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
         !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
@@ -366,6 +367,8 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
             curr = next_t;
             j = j_hi;
             ++k;
+            if (y_steps && cudaMemcpyAsync(y_steps + (size_t)k * st, y, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+                return ODECOL_E_CUDA;
             if (k > (1LL << 40)) return ODECOL_E_SHAPE;
         }
         if (n_accept || n_reject || status) {
@@ -806,8 +809,8 @@ __global__ void k_status_finite(DevProblem p, const float* __restrict__ y, int* 
 size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_layout(p).total; }
 
 int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
-                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, void* ws, size_t ws_bytes,
-                  cudaStream_t s) {
+                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps, void* ws,
+                  size_t ws_bytes, cudaStream_t s) {
     using namespace tc;
     const EmLayout L = em_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -826,6 +829,7 @@ int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* 
     count_launch();
     if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (y_steps && cudaMemcpyAsync(y_steps, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
     if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
         !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
@@ -870,9 +874,315 @@ int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* 
         curr = next_t;
         j = j_hi;
         ++k;
+        if (y_steps && cudaMemcpyAsync(y_steps + (size_t)k * st, y, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return ODECOL_E_CUDA;
         if (k > (1LL << 40)) return ODECOL_E_SHAPE;
     }
     if (status) { k_status_finite<<<p.B, 128, 0, s>>>(p, y, status); count_launch(); }
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged discrete adjoints of the fixed-step stochastic solvers (Euler-Maruyama, srk) for networks beyond the on-chip
+// family.  Building block: the vector-Jacobian product of ONE drift evaluation, b = J(Y, t)^T a, which also accumulates
+// grad_W_aug += (gamma a_V)^T r_aug(Y, t):
+//   prep        r, phi' of Y;  r_aug and gamma a_V split into hi / lo operands            (elementwise)
+//   W^T . (gamma a_V) on the tensor cores, epilogue  b_V = -a_V / tau_m + phi' g,  b_A = -a_A / tau_a - phi' g,
+//               b_F = -a_F / tau_s,  g = W^T (gamma a_V) + kappa a_A / tau_a + a_F / tau_s      (same algebra as
+//               BwdCtx::stage_bwd of the on-chip family)
+//   dW          the MN-major contraction of stage_tc_bwd.cu over the two operand buffers
+// The reverse loops around it are those of k_em_bwd_small / k_srk_bwd_small, replayed on the host schedule.
+// ---------------------------------------------------------------------------------------------------------------
+namespace tc {
+
+struct VjpEpi {
+    DevProblem p;
+    const float* a;        // (B, 3N) cotangent of the drift
+    const float* D;        // (B, N)  phi'(V - A)
+    float* b;              // (B, 3N) out
+    float inv_tm, inv_ta, inv_ts;
+    ODECOL_DEVINL void prepare() {}
+    ODECOL_DEVINL void rows(int, int j, int n0, int, int g, int TNq, const float (&tot)[kMaxQ]) const {
+        if (j >= p.N) return;
+        const int N = p.N;
+        const float kap = __ldg(p.kappa + j);
+#pragma unroll 4
+        for (int q = 0; q < kMaxQ; ++q) {
+            const int t = n0 + g * TNq + q;
+            if (q >= TNq || t >= p.B) break;
+            const float* at = a + (size_t)t * 3 * N + j;
+            const float aV = at[0], aA = at[N], aF = at[2 * N];
+            const float d = D[(size_t)t * N + j];
+            const float gg = tot[q] + kap * aA * inv_ta + aF * inv_ts;
+            float* bt = b + (size_t)t * 3 * N + j;
+            bt[0] = -aV * inv_tm + d * gg;
+            bt[N] = -aA * inv_ta - d * gg;
+            bt[2 * N] = -aF * inv_ts;
+        }
+    }
+    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
+    ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
+};
+
+// operands of one VJP: r_aug(Y, t) -> (Rhi, Rlo) rows of KPa, gamma a_V -> (AVhi, AVlo) rows of NPk, phi' -> D
+__global__ void k_vjp_prep(DevProblem p, const float* __restrict__ Y, float tq, const float* __restrict__ a, float gamma,
+                           float* __restrict__ Rhi, float* __restrict__ Rlo, int KPa, float* __restrict__ AVhi,
+                           float* __restrict__ AVlo, int NPk, float* __restrict__ D) {
+    const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
+    const float* yb = Y + (size_t)b * 3 * N;
+    int idx = 1;
+    const float tcl = knot_locate(p.knot_t, p.K, tq, idx);
+    const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
+    for (int k = threadIdx.x; k < Kaug; k += blockDim.x) {
+        float v;
+        if (k < N) {
+            float dr;
+            phi_dphi_fast(yb[k] - yb[N + k], v, dr);
+            D[(size_t)b * N + k] = dr;
+            const float av = gamma * a[(size_t)b * 3 * N + k];
+            const float h = tf32_rna(av);
+            AVhi[(size_t)b * NPk + k] = h;
+            AVlo[(size_t)b * NPk + k] = tf32_rna(av - h);
+        } else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N);
+        else v = 1.0f;
+        const float h = tf32_rna(v);
+        Rhi[(size_t)b * KPa + k] = h;
+        Rlo[(size_t)b * KPa + k] = tf32_rna(v - h);
+    }
+}
+
+// out = c0 x0 + c1 x1 + c2 x2 + c3 x3 (NULL terms skipped); out may alias any input
+__global__ void k_lincomb(size_t n, float* out, float c0, const float* x0, float c1, const float* x1, float c2,
+                          const float* x2, float c3, const float* x3) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (x0) v += c0 * x0[e];
+        if (x1) v += c1 * x1[e];
+        if (x2) v += c2 * x2[e];
+        if (x3) v += c3 * x3[e];
+        out[e] = v;
+    }
+}
+
+// lam += w1 g_j, pend += w0 g_j for the (selected) output gradient row j
+__global__ void k_add_out_grad(DevProblem p, const float* __restrict__ grad_row, const int* __restrict__ sel, int G, float w1,
+                               float w0, float* __restrict__ lam, float* __restrict__ pend) {
+    const size_t total = (size_t)p.B * G;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / G), g = (int)(e % G);
+        const int comp = sel ? sel[g] : g;
+        const float v = grad_row[e];
+        const size_t at = (size_t)b * 3 * p.N + comp;
+        lam[at] += w1 * v;
+        if (pend) pend[at] += w0 * v;
+    }
+}
+
+struct AdjLayout {
+    int Np, Bp, Bp32, KPa, NPk, TN;
+    size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo, off_D;
+    size_t off_lam, off_pend, off_a, off_b[3], off_f[2], off_H[2], off_noise, total;
+};
+
+static AdjLayout adj_layout(const DevProblem& p) {
+    AdjLayout L;
+    L.Np = round_up(p.N, BM);
+    L.NPk = L.Np;
+    L.KPa = round_up(p.N + p.n_in + 1, BK);
+    L.TN = pick_tile_n(L.Np / BM, p.B);
+    L.Bp = round_up(p.B, L.TN);
+    L.Bp32 = round_up(L.Bp, 32);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
+    L.off_WThi = take(4ull * L.Np * L.NPk); L.off_WTlo = take(4ull * L.Np * L.NPk);
+    L.off_Rhi = take(4ull * L.Bp32 * L.KPa); L.off_Rlo = take(4ull * L.Bp32 * L.KPa);
+    L.off_AVhi = take(4ull * L.Bp32 * L.NPk); L.off_AVlo = take(4ull * L.Bp32 * L.NPk);
+    L.off_D = take(4ull * p.B * p.N);
+    const size_t st = 4ull * p.B * 3 * p.N;
+    L.off_lam = take(st); L.off_pend = take(st); L.off_a = take(st);
+    for (int i = 0; i < 3; ++i) L.off_b[i] = take(st);
+    for (int i = 0; i < 2; ++i) L.off_f[i] = take(st);
+    for (int i = 0; i < 2; ++i) L.off_H[i] = take(st);
+    L.off_noise = take(32ull * p.B + 64);
+    L.total = o;
+    return L;
+}
+
+// transpose of the leading n x n block, split, padded (the W^T operand)
+static __global__ void k_split_pad_WT(const float* __restrict__ src, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
+                                      int rows_p, int cols_p) {
+    const size_t total = (size_t)rows_p * cols_p;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols_p), c = (int)(e % cols_p);
+        const float x = (r < n && c < n) ? src[(size_t)c * ld + r] : 0.0f;
+        const float h = tf32_rna(x);
+        hi[e] = h;
+        lo[e] = tf32_rna(x - h);
+    }
+}
+
+// shared state of a staged reverse sweep
+struct AdjCtx {
+    DevProblem p; AdjLayout L; cudaStream_t s; char* w;
+    CUtensorMap mWhi, mWlo, mWThi, mWTlo, mRhi, mRlo, mAVhi, mAVlo;
+    TileShape tsF, tsB;
+    float gamma;
+    float* grad_W;
+    float* F(size_t off) const { return reinterpret_cast<float*>(w + off); }
+
+    int init(const DevProblem& p_, void* ws, size_t ws_bytes, float* grad_W_, cudaStream_t s_) {
+        p = p_; L = adj_layout(p_); s = s_; w = static_cast<char*>(ws); grad_W = grad_W_;
+        if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+        if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+        gamma = p.c.tau_s * p.c.R / p.c.tau_m;
+        const int Kaug = p.N + p.n_in + 1;
+        if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_D - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaMemsetAsync(w + L.off_lam, 0, L.off_a - L.off_lam, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaMemsetAsync(grad_W, 0, sizeof(float) * (size_t)p.N * p.ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+        k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, F(L.off_Whi), F(L.off_Wlo), L.Np, L.KPa);
+        k_split_pad_WT<<<296, 256, 0, s>>>(p.W_aug, p.N, p.ld_w, F(L.off_WThi), F(L.off_WTlo), L.Np, L.NPk);
+        count_launch(2);
+        if (!make_map(&mWhi, F(L.off_Whi), L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, F(L.off_Wlo), L.Np, L.KPa, L.KPa, BM) ||
+            !make_map(&mWThi, F(L.off_WThi), L.Np, L.NPk, L.NPk, BM) || !make_map(&mWTlo, F(L.off_WTlo), L.Np, L.NPk, L.NPk, BM) ||
+            !make_map(&mRhi, F(L.off_Rhi), L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, F(L.off_Rlo), L.Bp, L.KPa, L.KPa, L.TN) ||
+            !make_map(&mAVhi, F(L.off_AVhi), L.Bp, L.NPk, L.NPk, L.TN) || !make_map(&mAVlo, F(L.off_AVlo), L.Bp, L.NPk, L.NPk, L.TN))
+            return ODECOL_E_CUDA;
+        tsF = TileShape{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+        tsB = TileShape{L.Np / BM, L.Bp / L.TN, L.TN, L.NPk / BK, 0, nullptr};
+        return ODECOL_OK;
+    }
+    int grid(size_t n) const { return (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16); }
+    size_t st() const { return (size_t)p.B * 3 * p.N; }
+
+    // f = drift(Y, t)
+    int rhs(const float* Y, float tq, float* f) {
+        k_em_operand<<<p.B, 128, 0, s>>>(p, Y, nullptr, tq, F(L.off_Rhi), F(L.off_Rlo), L.KPa);
+        count_launch();
+        RhsEpi e;
+        e.p = p; e.y = Y; e.Rhi = F(L.off_Rhi); e.Rlo = F(L.off_Rlo); e.f = f; e.KPa = L.KPa;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        return launch_contract(mWhi, mWlo, mRhi, mRlo, tsF, e, s);
+    }
+    // b = J(Y, t)^T a;  grad_W += (gamma a_V)^T r_aug(Y, t)
+    int vjp(const float* Y, float tq, const float* a, float* b) {
+        k_vjp_prep<<<p.B, 128, 0, s>>>(p, Y, tq, a, gamma, F(L.off_Rhi), F(L.off_Rlo), L.KPa, F(L.off_AVhi), F(L.off_AVlo), L.NPk,
+                                       F(L.off_D));
+        count_launch();
+        VjpEpi e;
+        e.p = p; e.a = a; e.D = F(L.off_D); e.b = b;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        int rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, tsB, e, s);
+        if (rc) return rc;
+        return tc_dw_accumulate(F(L.off_AVhi), F(L.off_AVlo), F(L.off_Rhi), F(L.off_Rlo), L.Bp32, L.Np, L.KPa, p.N,
+                                p.N + p.n_in + 1, p.ld_w, grad_W, s);
+    }
+    void lincomb(float* out, float c0, const float* x0, float c1 = 0.f, const float* x1 = nullptr, float c2 = 0.f,
+                 const float* x2 = nullptr, float c3 = 0.f, const float* x3 = nullptr) {
+        k_lincomb<<<grid(st()), 256, 0, s>>>(st(), out, c0, x0, c1, x1, c2, x2, c3, x3);
+        count_launch();
+    }
+};
+
+// the float32 step schedule of torchsde's integrate loop, on the host: step start times, and for every output the solver
+// state it ends on with its two interpolation weights (what k_em_schedule computes on the device)
+struct HostSchedule {
+    std::vector<float> tk, w0, w1;
+    std::vector<int> step_of;
+    int build(const float* ts_dev, int T, float dt, cudaStream_t s) {
+        std::vector<float> ts(T);
+        if (cudaMemcpyAsync(ts.data(), ts_dev, sizeof(float) * T, cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        const float t_end = ts[T - 1];
+        volatile float curr = ts[0], prev = ts[0];
+        step_of.assign(T, 0); w0.assign(T, 0.f); w1.assign(T, 1.f);
+        tk.assign(1, ts[0]);
+        int k = 0;
+        for (int j = 1; j < T; ++j) {
+            const float out_t = ts[j];
+            while (curr < out_t) {
+                volatile float nx = curr + dt;
+                const float next_t = nx < t_end ? nx : t_end;
+                prev = curr; curr = next_t;
+                tk.push_back(next_t);
+                ++k;
+            }
+            volatile float spn = curr - prev, a0 = curr - out_t, a1 = out_t - prev;
+            step_of[j] = k;
+            w0[j] = a0 / spn; w1[j] = a1 / spn;
+        }
+        return ODECOL_OK;
+    }
+};
+
+}  // namespace tc
+
+size_t stage_sde_bwd_workspace_bytes(const DevProblem& p, int) { return tc::adj_layout(p).total; }
+
+// which = 0: Euler-Maruyama, 1: srk (needs the increments: host tables or Philox)
+int stage_sde_bwd(int which, const DevProblem& p, const float* ts_dev, int T, const float* y_steps, int64_t n_steps,
+                  const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, const float* grad_y, const int* sel,
+                  int G, float dt, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    AdjCtx cx;
+    int rc = cx.init(p, ws, ws_bytes, grad_W, s);
+    if (rc) return rc;
+    HostSchedule sch;
+    rc = sch.build(ts_dev, T, dt, s);
+    if (rc) return rc;
+    const int nsteps = (int)sch.tk.size() - 1;
+    if (nsteps != (int)n_steps) return ODECOL_E_SHAPE;
+    const AdjLayout& L = cx.L;
+    const size_t st = cx.st();
+    float *lam = cx.F(L.off_lam), *pend = cx.F(L.off_pend), *a = cx.F(L.off_a);
+    float *b0 = cx.F(L.off_b[0]), *b1 = cx.F(L.off_b[1]), *b2 = cx.F(L.off_b[2]);
+    float *f0 = cx.F(L.off_f[0]), *f1 = cx.F(L.off_f[1]), *H1 = cx.F(L.off_H[0]), *H2 = cx.F(L.off_H[1]);
+    SrkNoise nz;
+    nz.dw = cx.F(L.off_noise); nz.du = nz.dw + p.B; nz.gw = nz.du + p.B;
+    const int gg = cx.grid((size_t)p.B * G);
+    int j = T - 1;
+    for (int k = nsteps - 1; k >= 0; --k) {
+        cx.lincomb(lam, 1.f, lam, 1.f, pend);                               // lam += pend
+        if (cudaMemsetAsync(pend, 0, sizeof(float) * st, s) != cudaSuccess) return ODECOL_E_CUDA;
+        while (j >= 1 && sch.step_of[j] == k + 1) {
+            k_add_out_grad<<<gg, 256, 0, s>>>(p, grad_y + (size_t)j * p.B * G, sel, G, sch.w1[j], sch.w0[j], lam, pend);
+            count_launch();
+            --j;
+        }
+        const float t0 = sch.tk[k];
+        volatile float hv = sch.tk[k + 1] - sch.tk[k];
+        const float h = hv;
+        const float* yk = y_steps + (size_t)k * st;
+        if (which == 0) {
+            cx.lincomb(a, h, lam);
+            rc = cx.vjp(yk, t0, a, b0); if (rc) return rc;
+            cx.lincomb(lam, 1.f, lam, 1.f, b0);
+        } else {
+            volatile float t1v = t0 + h, thv = t0 + 0.5f * h;
+            k_srk_noise<<<(p.B + 127) / 128, 128, 0, s>>>(p, nz, dW, dU, (unsigned long long)seed, (long long)trial_offset, k, h);
+            count_launch();
+            rc = cx.rhs(yk, t0, f0); if (rc) return rc;
+            k_srk_stage<<<cx.grid(st), 256, 0, s>>>(p, nz, 1, yk, f0, f1, h, H1);
+            rc = cx.rhs(H1, t1v, f1); if (rc) return rc;
+            k_srk_stage<<<cx.grid(st), 256, 0, s>>>(p, nz, 2, yk, f0, f1, h, H2);
+            count_launch(2);
+            const float h23 = h * Srid2::a2, h6 = h * Srid2::a0, h4 = h * 0.25f;
+            cx.lincomb(a, h23, lam);
+            rc = cx.vjp(H2, thv, a, b2); if (rc) return rc;
+            cx.lincomb(a, h6, lam, h4, b2);
+            rc = cx.vjp(H1, t1v, a, b1); if (rc) return rc;
+            cx.lincomb(a, h6, lam, h4, b2, h, b1);
+            rc = cx.vjp(yk, t0, a, b0); if (rc) return rc;
+            cx.lincomb(lam, 1.f, lam, 1.f, b2, 1.f, b1, 1.f, b0);
+        }
+    }
+    cx.lincomb(lam, 1.f, lam, 1.f, pend);
+    if (j >= 0) {                                                           // output 0 is y0 itself
+        k_add_out_grad<<<gg, 256, 0, s>>>(p, grad_y, sel, G, 1.f, 0.f, lam, nullptr);
+        count_launch();
+    }
+    if (grad_y0 && cudaMemcpyAsync(grad_y0, lam, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 

@@ -846,6 +846,36 @@ int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+// grad_W[i][k] += sum_rows A[row][i] * B[row][k] for split operands A (rows x Np) and B (rows x KPa), rows % 32 == 0:
+// the dW accumulation as a stand-alone step for the staged Euler-Maruyama / srk adjoints (stage_em.cu)
+int tc_dw_accumulate(const float* Ahi, const float* Alo, const float* Bhi, const float* Blo, int rows, int Np, int KPa, int N,
+                     int Kaug, int ld_w, float* grad_W, cudaStream_t s) {
+    using namespace tc;
+    if (rows % DW_BK) return ODECOL_E_SHAPE;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!make_map(&a_hi, Ahi, rows, Np, Np, DW_BK, sw) || !make_map(&a_lo, Alo, rows, Np, Np, DW_BK, sw) ||
+        !make_map(&b_hi, Bhi, rows, KPa, KPa, DW_BK, sw) || !make_map(&b_lo, Blo, rows, KPa, KPa, DW_BK, sw))
+        return ODECOL_E_CUDA;
+    DwShape ds;
+    ds.MT = Np / DW_T; ds.NT = (KPa + DW_T - 1) / DW_T; ds.total_rows = rows;
+    int z = (3 * num_sms()) / (ds.MT * ds.NT);
+    if (z < 1) z = 1;
+    int rps = (rows / DW_BK + z - 1) / z * DW_BK;
+    if (rps < DW_BK) rps = DW_BK;
+    ds.rows_per_split = rps; ds.Z = (rows + rps - 1) / rps;
+    ds.N = N; ds.Kaug = Kaug; ds.ld_w = ld_w; ds.grad_W = grad_W; ds.two_products = 0;
+    ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
+        configured = true;
+    }
+    k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_bwd_layout(p).total; }
 
 static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const float* y_traj, const float* ckVA,

@@ -312,10 +312,6 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
                 dW, dU = _tabulate_bm(bm, ts_cpu, dt, setup.B, y0.device, with_u=True)
                 if dW.shape != (n_steps, setup.B):
                     raise ValueError(f"odecol: bm produced increments of shape {tuple(dW.shape)}")
-        if (torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad)
-                and setup.problem(setup.lf.W_aug).kernel_family(ext.OP_SRK_FWD) != 0):
-            raise NotImplementedError("odecol: gradients through sdeint(method='srk') exist for the on-chip family "
-                                      "(N <= 128) only; wrap the solve in torch.no_grad() for larger networks")
         return _SRKFunction.apply(y0, setup.lf.W_aug, setup, dW, dU, seed, int(trial_offset), dt, n_steps, sel_long,
                                   sel_i32, stats)
     dW = None

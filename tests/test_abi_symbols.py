@@ -126,9 +126,9 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert srk(ctypes.byref(p), fake, 10, fake, fake, fake, None, 0, 0, 1e-3, None, None, None, 0, None) == E_NULL
     assert srk(ctypes.byref(p), fake, 10, fake, fake, None, None, 0, 0, 0.0, None, None, None, 0, None) == E_SHAPE
     big = _problem(N=512, n_in=64, ld_w=580)
-    # beyond the on-chip family the staged solver takes over: it wants its workspace, and cannot record solver states
+    # beyond the on-chip family the staged solver takes over: it wants its workspace (with or without a state record)
     assert srk(ctypes.byref(big), fake, 10, fake, fake, None, None, 0, 0, 1e-3, None, None, None, 0, None) == E_WORKSPACE
-    assert srk(ctypes.byref(big), fake, 10, fake, fake, None, None, 0, 0, 1e-3, None, fake, None, 0, None) == E_UNSUPPORTED
+    assert srk(ctypes.byref(big), fake, 10, fake, fake, None, None, 0, 0, 1e-3, None, fake, None, 0, None) == E_WORKSPACE
     # reverse sweeps insist on their workspace and on a sane component selection
     bwd = lib.odecol_em_bwd
     bwd.restype = ctypes.c_int
@@ -138,6 +138,7 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert bwd(ctypes.byref(p), fake, 10, fake, 9, fake, None, 48, 1e-3, fake, fake, None, 0, None) == E_WORKSPACE
     assert bwd(ctypes.byref(p), fake, 10, fake, 9, fake, None, 49, 1e-3, fake, fake, None, 0, None) == E_SHAPE
     assert bwd(ctypes.byref(p), fake, 10, fake, 0, fake, None, 48, 1e-3, fake, fake, None, 0, None) == E_SHAPE
+    assert bwd(ctypes.byref(big), fake, 10, fake, 9, fake, None, 3 * 512, 1e-3, fake, fake, None, 0, None) == E_WORKSPACE   # staged sweep
     # generators / read-outs
     ww = lib.odecol_ww_generate
     ww.restype = ctypes.c_int

@@ -76,7 +76,7 @@ def test_rk4_forward_and_reverse_on_random_problems(shape, family):
 @pytest.mark.parametrize("shape", [(8, 1, 3, 2), (16, 20, 3, 3), (8, 40, 2, 3), (72, 10, 2, 3), (120, 7, 3, 4)],
                          ids=lambda s: "N%d_in%d_B%d_K%d" % s)
 def test_sde_solvers_on_random_problems(shape, method):
-    """srk / Euler-Maruyama with supplied increments: forward + reverse on the on-chip family, forward on the staged one."""
+    """srk / Euler-Maruyama with supplied increments: forward + reverse sweep on the on-chip AND the staged family."""
     N, n_in, B, K = shape
     lf, tv, kt, ku, y0 = _problem(N, n_in, B, K, seed=N * 77 + n_in)
     lf.sigma[:] = np.random.default_rng(N).random(3 * N).astype(np.float32) * 3.0
@@ -107,15 +107,65 @@ def test_sde_solvers_on_random_problems(shape, method):
     if method == "srk":
         y, st, ysteps = ext.srk_fwd(mk(0), t_dev, y0d, Wd, Ud, 0, 0, dt, n_steps)
         gy0, gW = ext.srk_bwd(mk(0), t_dev, ysteps, Wd, Ud, 0, 0, wgt.to(DEV).contiguous(), None, dt)
-        ys, _, _ = ext.srk_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, Ud, 0, 0, dt, 0)
+        ys, _, yss = ext.srk_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, Ud, 0, 0, dt, n_steps)
+        gy0s, gWs = ext.srk_bwd(mk(ext.FLAG_FORCE_STAGED), t_dev, yss, Wd, Ud, 0, 0, wgt.to(DEV).contiguous(), None, dt)
     else:
         y, _, _, st, ysteps = ext.em_fwd(mk(0), t_dev, y0d, Wd, 0, 0, dt, False, 0.0, 0.0, 0.0, n_steps)
         gy0, gW = ext.em_bwd(mk(0), t_dev, ysteps, wgt.to(DEV).contiguous(), None, dt)
-        ys, *_ = ext.em_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, 0, 0, dt, False, 0.0, 0.0, 0.0, 0)
+        ys, _, _, _, yss = ext.em_fwd(mk(ext.FLAG_FORCE_STAGED), t_dev, y0d, Wd, 0, 0, dt, False, 0.0, 0.0, 0.0, n_steps)
+        gy0s, gWs = ext.em_bwd(mk(ext.FLAG_FORCE_STAGED), t_dev, yss, wgt.to(DEV).contiguous(), None, dt)
     et = float((y.cpu() - yo.detach()).abs().max()) / scale(yo.detach())
     es = float((ys.cpu() - yo.detach()).abs().max()) / scale(yo.detach())
     e0 = float((gy0.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
     eW = float((gW.cpu()[:, :N + n_in + 1] - gWo).abs().max()) / scale(gWo)
-    print(f"\n[{method} {shape}] trajectory on-chip {et:.1e} staged {es:.1e}  grad y0 {e0:.1e}  grad W_aug {eW:.1e}")
+    e0s = float((gy0s.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
+    eWs = float((gWs.cpu()[:, :N + n_in + 1] - gWo).abs().max()) / scale(gWo)
+    print(f"\n[{method} {shape}] trajectory on-chip {et:.1e} staged {es:.1e}  grad y0 {e0:.1e} / staged {e0s:.1e}  "
+          f"grad W_aug {eW:.1e} / staged {eWs:.1e}")
     assert int(st.abs().sum()) == 0
-    assert et < 1e-5 and es < 2e-5 and e0 < 5e-5 and eW < 5e-5
+    assert et < 1e-5 and es < 2e-5 and e0 < 5e-5 and eW < 5e-5 and e0s < 5e-5 and eWs < 5e-5
+
+
+@pytest.mark.parametrize("method", ["srk", "euler"])
+def test_large_network_sde_gradients_through_the_public_api(method):
+    """N = 256 (two population tiles, beyond the on-chip family): sdeint(...).backward() through the staged reverse sweep
+    against the oracle's autograd, with the sheet module (W, U trainable) and a component selection."""
+    import os
+    cfg = odecol.load_config(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "model.toml"))
+    sheet = odecol.SyntheticColumnSheet(cfg, 32, seed=1, device=DEV, sigma_v=2.0)
+    B, T, N = 3, 21, 256
+    gen = torch.Generator().manual_seed(4)
+    amp = torch.rand(B, 32, generator=gen) * 20
+    kt, ku = odecol.step_knots(5e-4, 1.5e-3, 2e-3, amp, 1e-4)
+    sheet.set_knots(kt.to(DEV), ku.to(DEV))
+    tv = torch.linspace(0, 2e-3, T)
+    dt = 2.5e-4
+    n_steps = len(S.em_step_schedule(tv, dt))
+    W, U = S.sample_w_u(n_steps, B, dt, gen)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen), torch.rand(B, N, generator=gen)), 1)
+    sel = [0, 9, 255, 256 + 17, 512 + 3]
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    # oracle on the sheet's linear form
+    lfp = sheet.export_linear_form()
+    Wa = lfp.W_aug.detach().cpu().numpy()
+    lf = LinearForm(W=Wa[:, :N], U=Wa[:, N:N + 32], bias=Wa[:, N + 32], kappa=lfp.kappa.cpu().numpy(), sigma=lfp.sigma.cpu().numpy(),
+                    tau_s=lfp.tau_s, tau_m=lfp.tau_m, tau_a=lfp.tau_a, resistance=lfp.resistance)
+    ode = orhs.UnifiedColumnODE(lf, kt.numpy(), ku.numpy(), requires_grad=True)
+    y0o = y0.clone().requires_grad_(True)
+    if method == "srk":
+        yo = S.sdeint_srk(ode, y0o, tv, S.TabulatedBrownianU(W, U), dt=dt)
+    else:
+        yo = S.sdeint_euler(ode, y0o, tv, S.TabulatedBrownian(W), dt=dt)
+    (yo[:, :, sel] * wgt).sum().backward()
+    # product
+    y0p = y0.to(DEV).requires_grad_(True)
+    bm = (W, U) if method == "srk" else W
+    yp = odecol.sdeint(sheet, y0p, tv.to(DEV), bm=bm, method=method, dt=dt, components=sel)
+    (yp * wgt.to(DEV)).sum().backward()
+    scale = lambda a: float(a.abs().max().clamp_min(1e-30))
+    et = float((yp.detach().cpu() - yo[:, :, sel].detach()).abs().max()) / scale(yo[:, :, sel].detach())
+    e0 = float((y0p.grad.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
+    eW = float((sheet.recurrent_weights.grad.cpu() - ode.W.grad).abs().max()) / scale(ode.W.grad)
+    eU = float((sheet.input_weights.grad.cpu() - ode.U.grad).abs().max()) / scale(ode.U.grad)
+    print(f"\n[{method} N=256] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W {eW:.1e}  grad U {eU:.1e}")
+    assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5 and eU < 5e-5
