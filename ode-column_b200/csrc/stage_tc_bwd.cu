@@ -654,29 +654,42 @@ __global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, in
 // Same warp roles as k_tc_contract; one output tile and one slice of the rows per CTA; epilogue = float atomics.
 // ---------------------------------------------------------------------------------------------------------------
 
+// Accumulation is CHUNKED: the tensor core truncates every accumulation into TMEM (round toward zero), which shrinks a
+// long sum of mostly same-signed terms by ~5e-8 per accumulation (measured on dW_aug of the C4 workload: -3e-6 with three
+// rotating accumulators over 1504 rows, -1e-5 over 4736 rows).  So an accumulator only ever sees DW_CHUNK K blocks
+// (32 MMA steps): the epilogue warps drain it into FP32 round-to-nearest registers and the MMA warp carries on in the
+// second of two TMEM accumulator sets (main + cross terms, 2 x 256 columns) -- which makes the bias independent of the
+// rows per work item, so one wave of long items (a third of the float atomics of the former three waves) is accurate.
+#ifndef ODECOL_DW_CHUNK
+#define ODECOL_DW_CHUNK 8
+#endif
+constexpr int DW_CHUNK = ODECOL_DW_CHUNK;
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
         const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t box_bytes = DW_BK * 128;                 // 32 rows x 32 floats
     constexpr uint32_t op_bytes = 4 * box_bytes;                // 128 columns
     constexpr uint32_t stage_bytes = 4 * op_bytes;              // A hi, A lo, B hi, B lo
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
-    constexpr uint32_t ncols = 512;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+    constexpr uint32_t ncols = 512;                             // two sets of (main, cross) x 128 columns
     const int tile = blockIdx.x % (ds.MT * ds.NT), z = blockIdx.x / (ds.MT * ds.NT);
     const int i0 = (tile % ds.MT) * DW_T, k0 = (tile / ds.MT) * DW_T;
     const int r0 = z * ds.rows_per_split;
     int r1 = r0 + ds.rows_per_split;
     if (r1 > ds.total_rows) r1 = ds.total_rows;
     const int KB = (r1 - r0) / DW_BK;
+    const int nchunks = (KB + DW_CHUNK - 1) / DW_CHUNK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -711,6 +724,144 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             // c=F32, a=b=TF32, both MN-major (bits 15, 16), N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
                                    ((uint32_t)(DW_T >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int c = 0, jj = 0;
+            uint32_t d_main = tmem_base, d_cross = tmem_base + DW_T;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (kb % DW_CHUNK == 0) {                       // next accumulator set, once the epilogue has drained it
+                    const int set = c & 1;
+                    mbar_wait(tempty0 + 8 * set, (uint32_t)((c >> 1) & 1) ^ 1u);
+                    tc_fence_after();
+                    d_main = tmem_base + (uint32_t)set * 2 * DW_T;
+                    d_cross = d_main + DW_T;
+                    jj = 0;
+                }
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t base = ring + stage * stage_bytes;
+                const uint64_t a_hi = make_smem_desc_mn(base, ds.lbo, ds.sbo), a_lo = make_smem_desc_mn(base + op_bytes, ds.lbo, ds.sbo);
+                const uint64_t b_hi = make_smem_desc_mn(base + 2 * op_bytes, ds.lbo, ds.sbo), b_lo = make_smem_desc_mn(base + 3 * op_bytes, ds.lbo, ds.sbo);
+#pragma unroll
+                for (int k = 0; k < DW_BK / 8; ++k, ++jj) {
+                    const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);   // next 8-row swizzle atom
+                    umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, jj != 0);
+                    if (!ds.two_products) umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, jj != 0);
+                }
+                umma_commit(empty0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (kb % DW_CHUNK == DW_CHUNK - 1 || kb == KB - 1) { umma_commit(tfull0 + 8 * (c & 1)); ++c; }
+            }
+        }
+    } else if (KB > 0) {
+        const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
+        const int i = i0 + quarter * 32 + lane;
+        float acc[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int set = c & 1;
+            mbar_wait(tfull0 + 8 * set, (uint32_t)((c >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 2 * DW_T + g * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint32_t um[4], ux[4];
+                tmem_ld4_issue(lane_base + 4 * q, um);
+                tmem_ld4_issue(lane_base + DW_T + 4 * q, ux);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[4 * q + e] += __uint_as_float(ux[e]) + __uint_as_float(um[e]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int k = k0 + g * 32 + q;
+            if (i < ds.N && k < ds.Kaug) atomicAdd(ds.grad_W + (size_t)i * ds.ld_w + k, acc[q]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// CTA-pair variant of the dW contraction (tcgen05 cta_group::2, ODECOL_DW_PAIR=1): the output tiles (2m, k) and
+// (2m+1, k) run as one M = 256 MMA on the two SMs of a TPC; each CTA stages its own 128 columns of the A panel and HALF
+// (64 columns = two 32-wide boxes) of the shared B panel, i.e. 192 instead of 256 operand columns per K block and SM.
+// dW is the one contraction here without a heavy epilogue, bound purely by operand panels coming out of L2.
+// Barrier protocol as in k_tc_contract_pair (stage_tc.cuh).  Four ring stages of 48 KB.
+constexpr int DW_PSTAGES = 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+             const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * DW_PSTAGES + 1];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t box_bytes = DW_BK * 128;                 // 32 rows x 32 floats
+    constexpr uint32_t a_bytes = 4 * box_bytes;                 // this CTA's 128 columns of A
+    constexpr uint32_t bh_bytes = 2 * box_bytes;                // this CTA's 64 of the 128 columns of B
+    constexpr uint32_t stage_bytes = 2 * a_bytes + 2 * bh_bytes;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_PSTAGES]), tfull = smem_u32(&bars[2 * DW_PSTAGES]);
+    constexpr uint32_t ncols = 512;
+    const int MT2 = ds.MT >> 1;
+    const int tile = pair % (MT2 * ds.NT), z = pair / (MT2 * ds.NT);
+    const int i0 = (2 * (tile % MT2) + (int)rank) * DW_T, k0 = (tile / MT2) * DW_T;
+    const int r0 = z * ds.rows_per_split;
+    int r1 = r0 + ds.rows_per_split;
+    if (r1 > ds.total_rows) r1 = ds.total_rows;
+    const int KB = (r1 - r0) / DW_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DW_PSTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t base = ring + stage * stage_bytes;
+                const uint32_t fb = (full0 + 8 * stage) & kPeerBitMask;
+                if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
+                const int row = r0 + kb * DW_BK;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    tma_load_2d_pair(base + m * box_bytes, &mA_hi, fb, i0 + 32 * m, row);
+                    tma_load_2d_pair(base + a_bytes + m * box_bytes, &mA_lo, fb, i0 + 32 * m, row);
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    tma_load_2d_pair(base + 2 * a_bytes + m * box_bytes, &mB_hi, fb, k0 + 64 * (int)rank + 32 * m, row);
+                    tma_load_2d_pair(base + 2 * a_bytes + bh_bytes + m * box_bytes, &mB_lo, fb, k0 + 64 * (int)rank + 32 * m, row);
+                }
+                if (++stage == DW_PSTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // c = F32, a = b = TF32, both MN-major, N = 128, M = 256 across the pair
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
+                                   ((uint32_t)(DW_T >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t d_small = tmem_base + kMainAcc * DW_T;
             int stage = 0; uint32_t phase = 0;
             int j = 0;
@@ -718,19 +869,20 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t base = ring + stage * stage_bytes;
-                const uint64_t a_hi = make_smem_desc_mn(base, ds.lbo, ds.sbo), a_lo = make_smem_desc_mn(base + op_bytes, ds.lbo, ds.sbo);
-                const uint64_t b_hi = make_smem_desc_mn(base + 2 * op_bytes, ds.lbo, ds.sbo), b_lo = make_smem_desc_mn(base + 3 * op_bytes, ds.lbo, ds.sbo);
+                const uint64_t a_hi = make_smem_desc_mn(base, ds.lbo, ds.sbo), a_lo = make_smem_desc_mn(base + a_bytes, ds.lbo, ds.sbo);
+                const uint64_t b_hi = make_smem_desc_mn(base + 2 * a_bytes, ds.lbo, ds.sbo);
+                const uint64_t b_lo = make_smem_desc_mn(base + 2 * a_bytes + bh_bytes, ds.lbo, ds.sbo);
 #pragma unroll
                 for (int k = 0; k < DW_BK / 8; ++k, ++j) {
-                    const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);   // next 8-row swizzle atom
-                    umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
-                    if (!ds.two_products) umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
-                    umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                    const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);
+                    umma_tf32_pair(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                    umma_tf32_pair(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32_pair(tmem_base + (uint32_t)(j % kMainAcc) * DW_T, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
                 }
-                umma_commit(empty0 + 8 * stage);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit_pair(empty0 + 8 * stage);
+                if (++stage == DW_PSTAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull);
+            umma_commit_pair(tfull);
         }
     } else if (KB > 0) {
         const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
@@ -755,10 +907,32 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
+}
+
+// launches the dW contraction (pair variant when enabled and the tile count allows)
+static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const DwShape& ds, cudaStream_t s) {
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* e = getenv("ODECOL_DW_PAIR"); use_pair = e ? (atoi(e) != 0) : 0; }
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dw_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return ODECOL_E_CUDA;
+        configured = true;
+    }
+    if (use_pair && ds.MT % 2 == 0 && !ds.two_products) {
+        const int pairs = (ds.MT / 2) * ds.NT * ds.Z;
+        k_tc_dw_pair<<<2 * pairs, kThreads, (size_t)DW_PSTAGES * (2 * 4 + 2 * 2) * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+    } else {
+        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+    }
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
 // rows x cols float32 matrix, box = box_rows x 32 floats (MN-major operand boxes reuse make_map with box_rows = 32)
@@ -839,11 +1013,9 @@ int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K
     ds.rows_per_split = rows; ds.Z = (Kp + rows - 1) / rows;
     ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C; ds.two_products = 0;
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
-    if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s) != cudaSuccess) return ODECOL_E_CUDA;
-    k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
-    count_launch(3);
-    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+    count_launch(2);
+    return launch_dw(a_hi, a_lo, b_hi, b_lo, ds, s);
 }
 
 // grad_W[i][k] += sum_rows A[row][i] * B[row][k] for split operands A (rows x Np) and B (rows x KPa), rows % 32 == 0:
@@ -859,21 +1031,14 @@ int tc_dw_accumulate(const float* Ahi, const float* Alo, const float* Bhi, const
         return ODECOL_E_CUDA;
     DwShape ds;
     ds.MT = Np / DW_T; ds.NT = (KPa + DW_T - 1) / DW_T; ds.total_rows = rows;
-    int z = (3 * num_sms()) / (ds.MT * ds.NT);
+    int z = num_sms() / (ds.MT * ds.NT);
     if (z < 1) z = 1;
     int rps = (rows / DW_BK + z - 1) / z * DW_BK;
     if (rps < DW_BK) rps = DW_BK;
     ds.rows_per_split = rps; ds.Z = (rows + rps - 1) / rps;
     ds.N = N; ds.Kaug = Kaug; ds.ld_w = ld_w; ds.grad_W = grad_W; ds.two_products = 0;
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
-        configured = true;
-    }
-    k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
-    count_launch();
-    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+    return launch_dw(a_hi, a_lo, b_hi, b_lo, ds, s);
 }
 
 size_t tc_rk4_bwd_workspace_bytes(const DevProblem& p, int) { return tc::tc_bwd_layout(p).total; }
@@ -930,11 +1095,12 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
               make_map(&dBlo[1], Rlo + 4 * rstride, 4ull * L.Bp, L.KPa, L.KPa, DW_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (!ok) return ODECOL_E_CUDA;
 
-    // dW launch shape: output tiles x splits of the stacked rows, about three waves of CTAs
+    // dW launch shape: output tiles x splits of the stacked rows, one wave of CTAs (ODECOL_DW_WAVES)
     DwShape ds;
     ds.MT = L.Np / DW_T; ds.NT = (L.KPa + DW_T - 1) / DW_T;
     ds.total_rows = 4 * L.Bp;
-    int z = (3 * num_sms()) / (ds.MT * ds.NT);
+    static const int dw_waves = getenv("ODECOL_DW_WAVES") ? atoi(getenv("ODECOL_DW_WAVES")) : 1;   // chunked accumulation: long items are accurate
+    int z = (dw_waves * num_sms()) / (ds.MT * ds.NT);
     if (z < 1) z = 1;
     int rows = (ds.total_rows / DW_BK + z - 1) / z * DW_BK;
     if (rows < DW_BK) rows = DW_BK;
@@ -1032,7 +1198,9 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         }
         // reverse stages 4, 3, 2, 1 (stage 1 writes kbar_4 of the next step into the OTHER operand set), then dW
         const int set = n & 1;
-        if (use_chain) {
+        if (use_chain && (getenv("ODECOL_DBG_BWD_SKIP") ? (atoi(getenv("ODECOL_DBG_BWD_SKIP")) & 2) : 0)) {
+            // diagnostics: chain skipped
+        } else if (use_chain) {
             BwdChainArgs a;
             a.p = p; a.tg = tg; a.ts = TileShape{MT, NT, L.TN, L.NPk / BK, 0, nullptr}; a.t = t_dev; a.n = n; a.NPk = L.NPk; a.G = G;
             a.Bp = L.Bp; a.acurT = acurT; a.lamT = lamT; a.b4T = b4T; a.b3T = b3T;
@@ -1066,9 +1234,10 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             replay(n - 1, side);
             cudaEventRecord(ev_replay, side);
         }
-        if (!(use_chain && fuse_dw)) {
-            k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, dw_smem, s>>>(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds);
-            count_launch();
+        static const int dbg_skip = getenv("ODECOL_DBG_BWD_SKIP") ? atoi(getenv("ODECOL_DBG_BWD_SKIP")) : 0;   // timing diagnostics only
+        if (!(use_chain && fuse_dw) && !(dbg_skip & 1)) {
+            const int rcd = launch_dw(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds, s);
+            if (rcd) return rcd;
         }
         if (overlap) cudaEventRecord(ev_dw, s);
     }
