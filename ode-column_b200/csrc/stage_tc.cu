@@ -140,7 +140,9 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
     const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
-    if (persistent_enabled())
+    // long contractions (K > 32 * kChunkMin) go through k_tc_contract, which accumulates in chunks (stage_tc.cuh); the
+    // persistent kernel keeps the rotating-accumulator scheme that is accurate up to that length
+    if (persistent_enabled() && L.KPa / BK <= kChunkMin)
         return tc_rk4_fwd_persistent(p, t_dev, T, y0, y_out, out_every, Whi, Wlo, Rhi, Rlo, KT, YT, RT,
                                      reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, nullptr, s);
 
@@ -247,6 +249,7 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
 // ---------------------------------------------------------------------------------------------------------------
 size_t tc_rk4_ckpt_bytes(const DevProblem& p, int T) {
     const tc::TcFwdLayout L = tc::tc_fwd_layout(p);
+    if (L.KPa / tc::BK > tc::kChunkMin) return 0;      // checkpoint mode lives in the persistent kernel: see tc_rk4_fwd
     const size_t plane = 4ull * L.Np * L.Bp;
     return plane * (2ull * T + 3ull * (T - 1));
 }
@@ -256,6 +259,7 @@ int tc_rk4_fwd_ckpt(const DevProblem& p, const float* t_dev, int T, const float*
     using namespace tc;
     const TcFwdLayout L = tc_fwd_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (L.KPa / BK > kChunkMin) return ODECOL_E_UNSUPPORTED;       // see tc_rk4_ckpt_bytes
     if (!ckpt || ckpt_bytes < tc_rk4_ckpt_bytes(p, T)) return ODECOL_E_WORKSPACE;
     if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
     char* w = static_cast<char*>(ws);

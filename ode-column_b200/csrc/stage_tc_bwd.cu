@@ -1118,7 +1118,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
     // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
     const char* pe = getenv("ODECOL_PERSISTENT");
-    bool use_chain = pe ? atoi(pe) != 0 : true;
+    bool use_chain = (pe ? atoi(pe) != 0 : true) && L.NPk / BK <= kChunkMin && L.KPa / BK <= kChunkMin;   // long K: chunked k_tc_contract
     // ODECOL_FUSE_DW=1: the dW contraction as a fifth phase of the chain launch instead of its own launch.  Measured on
     // par with the default (separate launch + replay one step ahead): profiles/r1_session2.md section 5.
     const char* fe = getenv("ODECOL_FUSE_DW");

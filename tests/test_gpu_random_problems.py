@@ -169,3 +169,38 @@ def test_large_network_sde_gradients_through_the_public_api(method):
     eU = float((sheet.input_weights.grad.cpu() - ode.U.grad).abs().max()) / scale(ode.U.grad)
     print(f"\n[{method} N=256] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W {eW:.1e}  grad U {eU:.1e}")
     assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5 and eU < 5e-5
+
+
+def test_rk4_and_adjoint_on_a_long_contraction():
+    """N = 1024 (K = 1153 > 768): the contraction accumulates in chunks (two accumulator sets drained into FP32 registers),
+    forward and reverse sweep run one launch per stage; against the oracle's autograd."""
+    import os
+    cfg = odecol.load_config(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "model.toml"))
+    cols, N, B, T = 128, 1024, 3, 7
+    sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=2, device=DEV)
+    gen = torch.Generator().manual_seed(8)
+    amp = torch.rand(B, cols, generator=gen) * 20
+    kt, ku = odecol.step_knots(1e-4, 4e-4, 6e-4, amp, 1e-4)
+    sheet.set_knots(kt.to(DEV), ku.to(DEV))
+    tv = torch.linspace(0, 6e-4, T)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen), torch.rand(B, N, generator=gen)), 1)
+    sel = list(range(0, N, 64)) + [N + 5, 2 * N + 9]
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    lfp = sheet.export_linear_form()
+    Wa = lfp.W_aug.detach().cpu().numpy()
+    lf = LinearForm(W=Wa[:, :N], U=Wa[:, N:N + cols], bias=Wa[:, N + cols], kappa=lfp.kappa.cpu().numpy(), sigma=lfp.sigma.cpu().numpy(),
+                    tau_s=lfp.tau_s, tau_m=lfp.tau_m, tau_a=lfp.tau_a, resistance=lfp.resistance)
+    ode = orhs.UnifiedColumnODE(lf, kt.numpy(), ku.numpy(), requires_grad=True)
+    y0o = y0.clone().requires_grad_(True)
+    yo = S.odeint_rk4(ode, y0o, tv)
+    (yo[:, :, sel] * wgt).sum().backward()
+    y0p = y0.to(DEV).requires_grad_(True)
+    yp = odecol.odeint(sheet, y0p, tv.to(DEV), method="rk4", components=sel)
+    assert "Ckpt" not in type(yp.grad_fn).__name__            # checkpoint mode belongs to the persistent kernel (K <= 768)
+    (yp * wgt.to(DEV)).sum().backward()
+    scale = lambda a: float(a.abs().max().clamp_min(1e-30))
+    et = float((yp.detach().cpu() - yo[:, :, sel].detach()).abs().max()) / scale(yo[:, :, sel].detach())
+    e0 = float((y0p.grad.cpu() - y0o.grad).abs().max()) / scale(y0o.grad)
+    eW = float((sheet.recurrent_weights.grad.cpu() - ode.W.grad).abs().max()) / scale(ode.W.grad)
+    print(f"\n[rk4 N=1024, chunked contraction] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W {eW:.1e}")
+    assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5
