@@ -123,7 +123,7 @@ constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4
 //   pre_tile(row, nt, g, TNq)                             per tile, before the accumulator is ready (prefetch only)
 //   tile_done(m_tile, n0, tile_n, etid, nthreads)         per tile, all epilogue threads
 // ---------------------------------------------------------------------------------------------------------------
-template <class Epi>
+template <class Epi, bool CHUNKED>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
               const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TileShape ts, Epi epi) {
@@ -141,7 +141,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
     // with three rotating accumulators over 258 K blocks).  In chunked mode the four accumulator planes are two SETS of
     // (main, cross terms); a set sees kChunkKB K blocks, then the epilogue warps drain it into FP32 round-to-nearest
     // registers while the MMA warp fills the other set -- the error no longer grows with K.
-    const bool chunked = ts.KB > kChunkMin;
+    constexpr bool chunked = CHUNKED;                      // compile-time: each variant keeps a tight MMA issue loop
     const uint32_t cfull0 = tfull, cempty0 = smem_u32(&bars[2 * STAGES + 2]);        // chunked: [set] = +8 * set; cfull[1] = bars[2S+1]
 
     const int tiles = ts.MT * ts.NT;
@@ -574,13 +574,16 @@ static int launch_contract(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
     const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * (size_t)ts.TN * BK * 4) + 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_tc_contract<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_tc_contract<Epi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_contract<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return ODECOL_E_CUDA;
         configured = true;
     }
     const int tiles = ts.MT * ts.NT;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    k_tc_contract<Epi><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    static const int nochunk = getenv("ODECOL_NOCHUNK") ? atoi(getenv("ODECOL_NOCHUNK")) : 0;    // diagnostics
+    if (ts.KB > kChunkMin && !nochunk) k_tc_contract<Epi, true><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    else k_tc_contract<Epi, false><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
