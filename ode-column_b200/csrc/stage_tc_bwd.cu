@@ -212,6 +212,7 @@ ODECOL_DEVINL void chain_epilogue(const BwdChainArgs& a, int m_tile, int row, in
     e.rows(m_tile, row, n0, nt, g, TNq, tot);
 }
 
+template <bool FUSE_DW>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant__ CUtensorMap mW_lo,
                const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -231,17 +232,17 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
     const uint32_t acc_stride = (uint32_t)ts.TN;
     uint32_t ncols = 32;
     while (ncols < (kMainAcc + 1) * acc_stride) ncols <<= 1;
-    if (a.fuse_dw) ncols = 512;                                 // the dW phase uses (kMainAcc + 1) x 128 accumulator columns
+    if (FUSE_DW) ncols = 512;                                 // the dW phase uses (kMainAcc + 1) x 128 accumulator columns
     // Fifth phase (fuse_dw): the dW contraction of this step, work item = (output tile, row split) as in k_tc_dw.  Its
     // operands are complete long before the chain ends -- slot 3 was written by the previous step, slots 2 / 1 / 0 by the
     // epilogues of stages 4 / 3 / 2 of this step -- so the MMA warp contracts dW while the stage-1 epilogues still
     // stream their bookkeeping through HBM, and the step needs one launch instead of two.
     const DwShape& ds = a.ds;
-    const int dw_tiles = ds.MT * ds.NT, dw_items = a.fuse_dw ? dw_tiles * ds.Z : 0;
+    const int dw_tiles = ds.MT * ds.NT, dw_items = FUSE_DW ? dw_tiles * ds.Z : 0;
     constexpr uint32_t dw_box = DW_BK * 128, dw_op = 4 * dw_box, dw_stage = 4 * dw_op;
     // both phases address the ring with the same stage stride, so that a ring slot means the same bytes before and after
     // the transition (the `empty` barrier of slot s then covers exactly the bytes the next load overwrites)
-    const uint32_t stride = a.fuse_dw ? (stage_bytes > dw_stage ? stage_bytes : dw_stage) : stage_bytes;
+    const uint32_t stride = FUSE_DW ? (stage_bytes > dw_stage ? stage_bytes : dw_stage) : stage_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -665,6 +666,7 @@ __global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, in
 #endif
 constexpr int DW_CHUNK = ODECOL_DW_CHUNK;
 
+template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
         const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds) {
@@ -707,14 +709,14 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, ds.two_products ? 3 * op_bytes : stage_bytes);
+                mbar_expect_tx(fb, TWO ? 3 * op_bytes : stage_bytes);
                 const int row = r0 + kb * DW_BK;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     tma_load_2d(base + m * box_bytes, &mA_hi, fb, i0 + 32 * m, row);
                     tma_load_2d(base + op_bytes + m * box_bytes, &mA_lo, fb, i0 + 32 * m, row);
                     tma_load_2d(base + 2 * op_bytes + m * box_bytes, &mB_hi, fb, k0 + 32 * m, row);
-                    if (!ds.two_products) tma_load_2d(base + 3 * op_bytes + m * box_bytes, &mB_lo, fb, k0 + 32 * m, row);
+                    if (!TWO) tma_load_2d(base + 3 * op_bytes + m * box_bytes, &mB_lo, fb, k0 + 32 * m, row);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -745,7 +747,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 for (int k = 0; k < DW_BK / 8; ++k, ++jj) {
                     const uint64_t adv = (uint64_t)((k * ds.kadv) >> 4);   // next 8-row swizzle atom
                     umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, jj != 0);
-                    if (!ds.two_products) umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                    if (!TWO) umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
                     umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, jj != 0);
                 }
                 umma_commit(empty0 + 8 * stage);
@@ -920,7 +922,8 @@ static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     if (use_pair < 0) { const char* e = getenv("ODECOL_DW_PAIR"); use_pair = e ? (atoi(e) != 0) : 0; }
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        if (cudaFuncSetAttribute(k_tc_dw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dw_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return ODECOL_E_CUDA;
         configured = true;
@@ -928,8 +931,10 @@ static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     if (use_pair && ds.MT % 2 == 0 && !ds.two_products) {
         const int pairs = (ds.MT / 2) * ds.NT * ds.Z;
         k_tc_dw_pair<<<2 * pairs, kThreads, (size_t)DW_PSTAGES * (2 * 4 + 2 * 2) * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+    } else if (ds.two_products) {
+        k_tc_dw<true><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
     } else {
-        k_tc_dw<<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+        k_tc_dw<false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
     }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
@@ -1108,12 +1113,6 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     ds.N = p.N; ds.Kaug = Kaug; ds.ld_w = p.ld_w; ds.grad_W = grad_W;
     { const char* e2 = getenv("ODECOL_DW_2X"); ds.two_products = e2 ? (atoi(e2) != 0) : 0; }
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
-    const size_t dw_smem = (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024;
-    static bool dw_configured = false;
-    if (!dw_configured) {
-        if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return ODECOL_E_CUDA;
-        dw_configured = true;
-    }
 
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
     // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
@@ -1128,8 +1127,9 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     int chain_grid = MT * NT < num_sms() ? MT * NT : num_sms();
     if (use_chain) {
         int max_blocks = 0;
-        if (cudaFuncSetAttribute(k_tc_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_tc_bwd_chain, kThreads, chain_smem) != cudaSuccess || max_blocks < 1)
+        if (cudaFuncSetAttribute(k_tc_bwd_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_bwd_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_tc_bwd_chain<true>, kThreads, chain_smem) != cudaSuccess || max_blocks < 1)
             use_chain = false;
     }
     // Checkpoint mode: the replay of a step needs nothing but the checkpoints, so it runs one step AHEAD of the
@@ -1210,7 +1210,8 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             a.done = done; a.done_base = (unsigned int)MT * 4u * (unsigned int)(T - 2 - n);
             a.fuse_dw = fuse_dw ? 1 : 0; a.ds = ds;
             void* args[] = {&mWThi, &mWTlo, &mAVhi, &mAVlo, &dAhi[set], &dAlo[set], &dBhi[rset], &dBlo[rset], &a};
-            if (cudaLaunchCooperativeKernel((const void*)k_tc_bwd_chain, dim3(chain_grid), dim3(kThreads), args, chain_smem, s) != cudaSuccess)
+            const void* chain_fn = fuse_dw ? (const void*)k_tc_bwd_chain<true> : (const void*)k_tc_bwd_chain<false>;
+            if (cudaLaunchCooperativeKernel(chain_fn, dim3(chain_grid), dim3(kThreads), args, chain_smem, s) != cudaSuccess)
                 return ODECOL_E_CUDA;
             count_launch();
         } else {
