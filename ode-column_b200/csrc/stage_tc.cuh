@@ -123,6 +123,20 @@ constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4
 //   pre_tile(row, nt, g, TNq)                             per tile, before the accumulator is ready (prefetch only)
 //   tile_done(m_tile, n0, tile_n, etid, nthreads)         per tile, all epilogue threads
 // ---------------------------------------------------------------------------------------------------------------
+// tile -> (population tile, trial tile).  Population tiles are taken in groups of kTileGroupM: consecutive tiles (= the
+// CTAs of a wave) walk the trial tiles of ONE group, so a wave touches kTileGroupM W_aug panels and ~148 / kTileGroupM
+// trial panels instead of all of W_aug (at N = 8192 every wave streamed the whole 539 MB of W_aug from HBM: 19 GB of DRAM
+// reads per drift evaluation), and the group's panels stay in L2 for the following waves.  With MT <= kTileGroupM this is
+// the plain "population tile fastest" order.
+constexpr int kTileGroupM = 12;
+ODECOL_DEVINL void tile_coords(int tile, int MT, int NT, int& m, int& nt) {
+    const int per_group = kTileGroupM * NT;
+    const int grp = tile / per_group, within = tile - grp * per_group;
+    const int gm = min(kTileGroupM, MT - grp * kTileGroupM);          // the last group may be smaller
+    nt = within / gm;
+    m = grp * kTileGroupM + (within - nt * gm);
+}
+
 template <class Epi, bool CHUNKED>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -176,7 +190,9 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile % ts.MT) * BM, n0 = (tile / ts.MT) * ts.TN;
+                int mt_, nt_;
+                tile_coords(tile, ts.MT, ts.NT, mt_, nt_);
+                const int m0 = mt_ * BM, n0 = nt_ * ts.TN;
                 for (int kb = 0; kb < ts.KB; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
@@ -258,7 +274,9 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
         uint32_t tphase = 0;
         int cchunk = 0;                               // chunk counter (chunked mode), runs on across tiles
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
+            int m_tile, nt;
+            tile_coords(tile, ts.MT, ts.NT, m_tile, nt);
+            const int n0 = nt * ts.TN;
             const int row = m_tile * BM + quarter * 32 + lane;
             float tot[kMaxQ];
             epi.pre_tile(row, nt, g, TNq);            // warm L2 with the first groups' scratch while the contraction runs
