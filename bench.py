@@ -463,6 +463,14 @@ def run_c5(args):
         pass
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 6.0
     kaug = n + cols + 1
+    # DRAM bytes of one drift evaluation from the committed ncu --set full capture of this kernel on this workload shape
+    traffic, traffic_src = None, None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_c5.json")))
+        if rec.get("populations") == n and rec.get("trials") == B and world == 1:
+            traffic, traffic_src = rec["dram_bytes_per_drift_evaluation"], rec["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     rhs_launches = args.steps * 2 * rounds                        # two drift evaluations per round, all members
     achieved = 2.0 * n * kaug * B * rhs_launches / sec / 1e12     # whole solve attributed to the contraction launches
     if rank == 0:
@@ -477,7 +485,8 @@ def run_c5(args):
             "attempted_steps_per_member": float(attempts) / args.steps / args.c5_trials, "rounds_per_solve": rounds,
             "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (3xTF32 tcgen05 drift evaluation)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": None, "note": "lower bound: the elementwise stepping kernels are inside the timed region"},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "note": "lower bound: the elementwise stepping kernels are inside the timed region"},
         }))
     if world > 1:
         dist.destroy_process_group()
