@@ -9,7 +9,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (128, 128, 64), (512, 300, 577), (200, 1000, 130), (1024, 2368, 608)])
+# the last three: more than 12 population tiles, so the grouped tile order (tile_coords in csrc/stage_tc.cuh) is walked with
+# a ragged last group (14 = 12 + 2, 25 = 12 + 12 + 1, 13 = 12 + 1 with chunked accumulation, K > 768)
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (128, 128, 64), (512, 300, 577), (200, 1000, 130), (1024, 2368, 608),
+                                   (1792, 300, 96), (3100, 1200, 64), (1664, 240, 800)])
 def test_tc_contract_matches_float64(M, N, K):
     ext = odecol._native.ext()
     g = torch.Generator().manual_seed(M + N + K)
