@@ -185,6 +185,24 @@ def workload_name(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def init_nccl(torch, dist, dev):
+    """One process per GPU over NCCL.  NCCL writes its version banner to STDOUT when the first communicator is created
+    (NCCL_DEBUG=VERSION / WARN on some boxes); stdout carries the ONE JSON line of the contract, so file descriptor 1
+    points at stderr while the communicator comes up."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -198,7 +216,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(torch, dist, dev)
     ext = odecol._native.ext()
 
     cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
@@ -406,7 +424,7 @@ def run_c5(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(torch, dist, dev)
     ext = odecol._native.ext()
     cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
     cols, n = args.c5_columns, 8 * args.c5_columns
