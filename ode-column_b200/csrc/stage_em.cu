@@ -50,8 +50,10 @@ struct RhsEpi {
 
 // operand r_aug(t_b, y_b) split hi/lo; one CTA per trial, per-trial time (NULL -> shared time *t_shared)
 __global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
-                             float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa) {
+                             float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa,
+                             const int* __restrict__ active = nullptr) {
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
+    if (active && !active[b]) return;          // adaptive sweeps: a finished trial's drift is never read again
     const size_t ro = (size_t)b * KPa;
     const float* yb = y + (size_t)b * 3 * N;
     const float tq = t_trial ? t_trial[b] : t_shared;
@@ -156,20 +158,40 @@ __global__ void k_ad_init(DevProblem p, TrialState s, const float* __restrict__ 
     if (b == 0) *s.n_active = p.B;
 }
 
-// full step and first half step from f0; writes y_full, y_mid
+// full step and first half step from f0; writes y_full, y_mid.  One CTA per trial (finished trials cost nothing), four
+// components per thread and iteration when the rows are 16-byte aligned; per element the same operations in the same order.
 __global__ void k_ad_half1(DevProblem p, TrialState s, const float* __restrict__ y, const float* __restrict__ f0,
                            float* __restrict__ y_full, float* __restrict__ y_mid) {
-    const int N = p.N;
-    const size_t total = (size_t)p.B * 3 * N;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(e / (3 * N)), comp = (int)(e % (3 * N));
-        if (!s.active[b]) continue;
-        const float tc = s.t_cur[b], tm = s.t_mid[b], tn = s.t_next[b];
-        const float h = __fsub_rn(tn, tc), h1 = __fsub_rn(tm, tc);
-        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * (p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f);
+    const int N = p.N, b = blockIdx.x;
+    if (!s.active[b]) return;
+    const float tc = s.t_cur[b], tm = s.t_mid[b], tn = s.t_next[b];
+    const float h = __fsub_rn(tn, tc), h1 = __fsub_rn(tm, tc);
+    const float dwf = s.dw_full[b], dw1 = s.dw_1[b];
+    const float sc = p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f;
+    const size_t base = (size_t)b * 3 * N;
+    const bool vec = (N & 3) == 0 && (((uintptr_t)y | (uintptr_t)f0 | (uintptr_t)y_full | (uintptr_t)y_mid | (uintptr_t)p.sigma) & 15) == 0;
+    if (vec) {
+        for (int comp = 4 * threadIdx.x; comp < 3 * N; comp += 4 * blockDim.x) {
+            const float4 Y = ld4(y + base + comp), F = ld4(f0 + base + comp);
+            const float4 S = p.sigma ? ld4(p.sigma + comp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 yf, ym;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float sg = (&S.x)[e] * sc, y0 = (&Y.x)[e], f = (&F.x)[e];
+                (&yf.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, dwf));
+                (&ym.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, dw1));
+            }
+            st4(y_full + base + comp, yf);
+            st4(y_mid + base + comp, ym);
+        }
+        return;
+    }
+    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
+        const size_t e = base + comp;
+        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * sc;
         const float y0 = y[e], f = f0[e];
-        y_full[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, s.dw_full[b]));
-        y_mid[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, s.dw_1[b]));
+        y_full[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, dwf));
+        y_mid[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, dw1));
     }
 }
 
@@ -431,14 +453,14 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     for (long long round = 0; round < max_attempts && h_active > 0; ++round) {
         int rc = rhs(y, f0);
         if (rc != ODECOL_OK) return rc;
-        k_ad_half1<<<ew_grid, 256, 0, s>>>(p, S, y, f0, yfull, ymid);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa);
+        k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa, S.active);
         rc = rhs(ymid, fm);
         if (rc != ODECOL_OK) return rc;
         k_ad_half2<<<p.B, 256, 0, s>>>(p, S, ymid, fm, yfull, yhalf, rtol, atol);
         k_ad_control<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt_min, seed, trial_offset, max_attempts);
         k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, S.active);
         count_launch(6);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
