@@ -204,15 +204,37 @@ __global__ void k_ad_half2(DevProblem p, TrialState s, const float* __restrict__
     const float h2 = __fsub_rn(s.t_next[b], s.t_mid[b]);
     const float dw2 = s.dw_2[b];
     double acc = 0.0;
-    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
-        const size_t e = (size_t)b * 3 * N + comp;
-        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * (p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f);
-        const float yh = __fadd_rn(__fadd_rn(y_mid[e], __fmul_rn(fm[e], h2)), __fmul_rn(sg, dw2));
-        y_half[e] = yh;
-        const float yf = y_full[e];
-        const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf), fabsf(yh))));
-        const float q = __fdiv_rn(__fsub_rn(yf, yh), tol);
-        acc += (double)q * q;
+    const float sc = p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f;
+    const size_t base = (size_t)b * 3 * N;
+    const bool vec = (N & 3) == 0 && (((uintptr_t)y_mid | (uintptr_t)fm | (uintptr_t)y_full | (uintptr_t)y_half | (uintptr_t)p.sigma) & 15) == 0;
+    if (vec) {                                  // four components per thread and iteration, 16-byte accesses
+        for (int comp = 4 * threadIdx.x; comp < 3 * N; comp += 4 * blockDim.x) {
+            const float4 YM = ld4(y_mid + base + comp), FM = ld4(fm + base + comp), YF = ld4(y_full + base + comp);
+            const float4 S = p.sigma ? ld4(p.sigma + comp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 YH;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float sg = (&S.x)[e] * sc;
+                const float yh = __fadd_rn(__fadd_rn((&YM.x)[e], __fmul_rn((&FM.x)[e], h2)), __fmul_rn(sg, dw2));
+                (&YH.x)[e] = yh;
+                const float yf = (&YF.x)[e];
+                const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf), fabsf(yh))));
+                const float q = __fdiv_rn(__fsub_rn(yf, yh), tol);
+                acc += (double)q * q;
+            }
+            st4(y_half + base + comp, YH);
+        }
+    } else {
+        for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
+            const size_t e = base + comp;
+            const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * sc;
+            const float yh = __fadd_rn(__fadd_rn(y_mid[e], __fmul_rn(fm[e], h2)), __fmul_rn(sg, dw2));
+            y_half[e] = yh;
+            const float yf = y_full[e];
+            const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf), fabsf(yh))));
+            const float q = __fdiv_rn(__fsub_rn(yf, yh), tol);
+            acc += (double)q * q;
+        }
     }
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -284,15 +306,33 @@ __global__ void k_ad_commit(DevProblem p, TrialState s, const float* __restrict_
     const float spn = __fsub_rn(t_cur, t_prev);
     int j = s.next_out[b];
     const size_t total = (size_t)p.B * 3 * N;
-    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
-        const size_t e = (size_t)b * 3 * N + comp;
-        const float y0 = y[e], y1 = y_half[e];
-        y_prev[e] = y0;
-        y[e] = y1;
-        for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
-            const float out_t = __ldg(ts + jj);
-            const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
-            y_out[(size_t)jj * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
+    const bool vec = (N & 3) == 0 && (((uintptr_t)y | (uintptr_t)y_prev | (uintptr_t)y_half | (uintptr_t)y_out) & 15) == 0;
+    if (vec) {                                  // four components per thread and iteration, 16-byte accesses
+        for (int comp = 4 * threadIdx.x; comp < 3 * N; comp += 4 * blockDim.x) {
+            const size_t e = (size_t)b * 3 * N + comp;
+            const float4 Y0 = ld4(y + e), Y1 = ld4(y_half + e);
+            st4(y_prev + e, Y0);
+            st4(y + e, Y1);
+            for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
+                const float out_t = __ldg(ts + jj);
+                const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
+                float4 O;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) (&O.x)[c] = __fadd_rn(__fmul_rn(w0, (&Y0.x)[c]), __fmul_rn(w1, (&Y1.x)[c]));
+                st4(y_out + (size_t)jj * total + e, O);
+            }
+        }
+    } else {
+        for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
+            const size_t e = (size_t)b * 3 * N + comp;
+            const float y0 = y[e], y1 = y_half[e];
+            y_prev[e] = y0;
+            y[e] = y1;
+            for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
+                const float out_t = __ldg(ts + jj);
+                const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
+                y_out[(size_t)jj * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
+            }
         }
     }
     __syncthreads();
