@@ -53,6 +53,12 @@ def parse():
     ap.add_argument("--c5-columns", type=int, default=1024)
     ap.add_argument("--c5-trials", type=int, default=8192, help="sweep members in total (strong scaling over GPUs)")
     ap.add_argument("--c5-horizon", type=float, default=0.004, help="simulated seconds per step of the c5 workload")
+    ap.add_argument("--trials-total", type=int, default=0,
+                    help="c4: total trials of the job (strong scaling): every rank integrates trials-total / gpus trials per step in "
+                         "chunks of --trials-per-gpu, accumulating dW; 65536 = the literal BASELINE.json configs[3] batch at any N")
+    ap.add_argument("--parity-trials", type=int, default=8, help="trials of the in-bench oracle parity check (0 = skip)")
+    ap.add_argument("--parity-steps", type=int, default=40)
+    ap.add_argument("--probe-trials", type=int, default=1024, help="global trials of the sharding-invariance probe (0 = skip)")
     return ap.parse_args()
 
 
@@ -70,6 +76,12 @@ def make_stimulus(torch, B, columns, T, dt, trial0, device):
     on, off = (T // 3) * grid, (2 * (T // 3)) * grid
     kt, ku = odecol.step_knots(on, off, t_end, amp, grid)
     return kt.to(device), ku.to(device), amp
+
+
+def probe_amplitudes(torch, n_trials, columns):
+    """Stimulus amplitudes of the sharding-invariance probe: ONE draw for the global trials [0, n_trials); ranks slice it."""
+    g = torch.Generator(device="cpu").manual_seed(4242)
+    return torch.rand(n_trials, columns, generator=g) * 30.0
 
 
 def loss_components(torch, columns):
@@ -180,9 +192,98 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if args.trials_total:
+        return (f"C4: synthetic {args.columns}-column network (N={8 * args.columns}), rk4 forward + discrete adjoint dW, "
+                f"T={args.time_points} grid points, {args.trials_total} trials in the job ({args.trials_total // args.gpus} per GPU, "
+                f"chunks of {args.trials_per_gpu})")
     return (f"C4: synthetic {args.columns}-column network (N={8 * args.columns}), rk4 forward + discrete adjoint dW, "
             f"T={args.time_points} grid points, {args.trials_per_gpu} trials/GPU (x{args.gpus} GPUs = {args.trials_per_gpu * args.gpus})")
 
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def parity_block(torch, odecol, net, args, kt, ku_local, tv, sel, dev, options):
+    """The timed configuration checked against the CPU oracle inside the bench run (rank 0): the SAME network, batch,
+    tiling and code path (persistent tcgen05 forward in checkpoint mode, reverse sweep) on a window of --parity-steps
+    grid steps straddling the stimulus onset, with a seeded linear loss on the first --parity-trials trials only -- so
+    trajectory and dW_aug of those trials are comparable with oracle.solvers.odeint_rk4 + autograd on them alone."""
+    from oracle import rhs as orhs, solvers as S
+    from oracle.column_model import LinearForm
+    nb, steps = args.parity_trials, args.parity_steps
+    columns, n = args.columns, 8 * args.columns
+    B = ku_local.shape[0]
+    j0 = max(0, args.time_points // 3 - steps // 2)
+    tvp = tv[j0:j0 + steps + 1].contiguous()
+    g = torch.Generator(device="cpu").manual_seed(99)
+    y0 = torch.zeros(B, 3 * n)
+    y0[:nb] = torch.cat((torch.rand(nb, n, generator=g) * 6 - 8, torch.rand(nb, n, generator=g), torch.rand(nb, n, generator=g)), 1)
+    wgt = torch.zeros(steps + 1, B, sel.numel())
+    wgt[:, :nb] = torch.randn(steps + 1, nb, sel.numel(), generator=g)
+    params = [net.recurrent_weights, net.input_weights]
+    for p in params:
+        p.grad = None
+    net.set_knots(kt.to(dev), ku_local.to(dev))
+    y0d = y0.to(dev).requires_grad_(True)
+    traj = odecol.odeint(net, y0d, tvp, method="rk4", components=sel, options=options)
+    ckpt_mode = "Ckpt" in type(traj.grad_fn).__name__
+    (traj * wgt.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    lfp = net.export_linear_form()
+    Wa = lfp.W_aug.detach().cpu().numpy()
+    lf = LinearForm(W=Wa[:, :n], U=Wa[:, n:n + columns], bias=Wa[:, n + columns], kappa=lfp.kappa.cpu().numpy(),
+                    sigma=lfp.sigma.cpu().numpy(), tau_s=lfp.tau_s, tau_m=lfp.tau_m, tau_a=lfp.tau_a, resistance=lfp.resistance)
+    ode = orhs.UnifiedColumnODE(lf, kt.cpu().numpy(), ku_local[:nb].cpu().numpy(), requires_grad=True)
+    y0o = y0[:nb].clone().requires_grad_(True)
+    yo = S.odeint_rk4(ode, y0o, tvp.cpu())
+    selc = sel.cpu()
+    (yo[:, :, selc] * wgt[:, :nb]).sum().backward()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    out = {"trials": nb, "steps": steps, "window_start_index": j0, "batch": B, "checkpoint_mode": ckpt_mode,
+           "y_sel_rel_err": rel(traj.detach().cpu()[:, :nb], yo[:, :, selc].detach()),
+           "dy0_rel_err": rel(y0d.grad.cpu()[:nb], y0o.grad),
+           "dW_rel_err": rel(net.recurrent_weights.grad.cpu(), ode.W.grad),
+           "dU_rel_err": rel(net.input_weights.grad.cpu(), ode.U.grad),
+           "against": "oracle.solvers.odeint_rk4 + torch autograd (CPU, fp32), same inputs", "bar": "1e-5 trajectory, 5e-5 gradients"}
+    out["ok"] = bool(out["y_sel_rel_err"] < 1e-5 and out["dy0_rel_err"] < 5e-5 and out["dW_rel_err"] < 5e-5 and out["dU_rel_err"] < 5e-5)
+    for p in params:
+        p.grad = None
+    return out
+
+
+def probe_block(torch, dist, odecol, net, args, tv, sel, dev, options, rank, world):
+    """Sharding invariance on hardware: the global trials [0, --probe-trials) are split over the ranks (amplitudes and loss
+    weights keyed by the GLOBAL trial index), every rank runs forward + adjoint on its share, loss and dW are all-reduced.
+    The printed checksums must agree between the N = 1, 2, 4, 8 lines (to float32 summation order)."""
+    P, steps = args.probe_trials, args.parity_steps
+    columns, n = args.columns, 8 * args.columns
+    lo, hi = odecol.distributed.shard_bounds(P, rank, world)
+    amp = probe_amplitudes(torch, P, columns)[lo:hi]
+    T, dt = args.time_points, args.dt
+    t_end = T * dt
+    grid = t_end / (T - 1)
+    kt, ku = odecol.step_knots((T // 3) * grid, (2 * (T // 3)) * grid, t_end, amp, grid)
+    j0 = max(0, T // 3 - steps // 2)
+    tvp = tv[j0:j0 + steps + 1].contiguous()
+    g = torch.Generator(device="cpu").manual_seed(4243)
+    wgt = torch.randn(P, steps + 1, sel.numel(), generator=g)[lo:hi].permute(1, 0, 2).contiguous().to(dev)
+    params = [net.recurrent_weights, net.input_weights]
+    for p in params:
+        p.grad = None
+    net.set_knots(kt.to(dev), ku.to(dev))
+    traj = odecol.odeint(net, torch.zeros(hi - lo, 3 * n, device=dev), tvp, method="rk4", components=sel, options=options)
+    loss = (traj * wgt).sum()
+    loss.backward()
+    loss = loss.detach().double()
+    if world > 1:
+        odecol.distributed.allreduce_gradients(params)
+        dist.all_reduce(loss)
+    gW = net.recurrent_weights.grad.double()
+    pos = torch.arange(gW.numel(), device=dev, dtype=torch.float64).reshape(gW.shape)
+    out = {"trials": P, "steps": steps, "loss": float(loss), "dW_sum": float(gW.sum()), "dW_abs_sum": float(gW.abs().sum()),
+           "dW_weighted_sum": float((gW * torch.cos(pos)).sum()), "dU_abs_sum": float(net.input_weights.grad.double().abs().sum())}
+    for p in params:
+        p.grad = None
+    return out
 
 # ----------------------------------------------------------------------------------------------------------------------
 def init_nccl(torch, dist, dev):
@@ -224,13 +325,22 @@ def run_ours(args):
     n = 8 * columns
     net = odecol.SyntheticColumnSheet(cfg, columns, seed=0, device=dev)
     params = [net.recurrent_weights, net.input_weights]
-    trial0 = rank * B
-    kt, ku, _ = make_stimulus(torch, B, columns, T, args.dt, trial0, "cpu")
+    # default: weak scaling, one chunk of B trials per rank and step.  --trials-total: the job's batch is fixed and every
+    # rank walks its share in chunks of B trials per step, dW accumulating over the chunks (strong scaling)
+    chunks = 1
+    if args.trials_total:
+        if args.trials_total % (world * B):
+            raise SystemExit("--trials-total must be a multiple of gpus x trials-per-gpu")
+        chunks = args.trials_total // (world * B)
+    trial0 = rank * B * chunks
+    stim = [make_stimulus(torch, B, columns, T, args.dt, trial0 + c * B, "cpu") for c in range(chunks)]
+    kt, ku = stim[0][0], stim[0][1]
     tv = torch.linspace(0.0, T * args.dt, T, device=dev)
     sel = loss_components(torch, columns).to(dev)
     target = torch.full((1, 1, columns), 0.5, device=dev)
     y0_host = torch.zeros(B, 3 * n).pin_memory()
-    ku_host = ku.pin_memory()
+    ku_hosts = [st[1].pin_memory() for st in stim]
+    ku_host = ku_hosts[0]
     kt_dev = kt.to(dev)
     options = {"family": args.family} if args.family else None
     launches = {"n": 0}
@@ -238,28 +348,36 @@ def run_ours(args):
     def step(from_host: bool):
         """One forward + adjoint pass through the public API.  from_host: inputs come from pinned host memory and the
         loss + dW go back to the host inside the pass (the e2e leg)."""
-        if from_host:
-            y0 = y0_host.to(dev, non_blocking=True)
-            ku_d = ku_host.to(dev, non_blocking=True)
-        else:
-            y0, ku_d = step.y0_dev, step.ku_dev
-        net.set_knots(kt_dev, ku_d)
         for p in params:
             p.grad = None
-        traj = odecol.odeint(net, y0, tv, method="rk4", components=sel, options=options)
-        launches["n"] += ext.last_launch_count()
-        loss = huber_on_rates(torch, odecol, traj, target, columns)
-        launches["n"] += ext.last_launch_count()
-        loss.backward()
-        launches["n"] += ext.last_launch_count()
+        total = None
+        for c in range(chunks):
+            if from_host:
+                y0 = y0_host.to(dev, non_blocking=True)
+                ku_d = ku_hosts[c].to(dev, non_blocking=True)
+            else:
+                y0, ku_d = step.y0_dev, step.ku_devs[c]
+            net.set_knots(kt_dev, ku_d)
+            traj = odecol.odeint(net, y0, tv, method="rk4", components=sel, options=options)
+            launches["n"] += ext.last_launch_count()
+            loss = huber_on_rates(torch, odecol, traj, target, columns)
+            launches["n"] += ext.last_launch_count()
+            loss.backward()
+            launches["n"] += ext.last_launch_count()
+            total = loss.detach() if total is None else total + loss.detach()
+            del traj, loss
+        total = total / chunks
         if world > 1:
             odecol.distributed.allreduce_gradients(params)
+            dist.all_reduce(total)
+            total = total / world                  # mean over the job's trials (equal shares per rank)
         if from_host:
-            return loss.detach().cpu(), net.recurrent_weights.grad.cpu()
-        return loss.detach(), None
+            return total.cpu(), net.recurrent_weights.grad.cpu()
+        return total, None
 
     step.y0_dev = y0_host.to(dev)
-    step.ku_dev = ku_host.to(dev)
+    step.ku_devs = [k.to(dev) for k in ku_hosts]
+    step.ku_dev = step.ku_devs[0]
 
     def timed(n_steps, from_host):
         if world > 1:
@@ -287,7 +405,7 @@ def run_ours(args):
     sec, (loss, _) = timed(args.steps, False)
     n_launch = launches["n"]
     clocks = sampler.stop() if rank == 0 else None
-    pop_steps_job = n * B * world * (T - 1)
+    pop_steps_job = n * B * chunks * world * (T - 1)
     value = pop_steps_job * args.steps / sec
 
     # where one pass spends its time (one extra, untimed-for-the-metric pass with events between the phases)
@@ -318,7 +436,7 @@ def run_ours(args):
     sec_e2e, (loss_h, gW_h) = timed(max(1, min(args.steps, 2)), True)
     e2e_steps = max(1, min(args.steps, 2))
     e2e_value = pop_steps_job * e2e_steps / sec_e2e
-    h2d = y0_host.numel() * 4 + ku_host.numel() * 4
+    h2d = (y0_host.numel() * 4 + ku_host.numel() * 4) * chunks
     d2h = gW_h.numel() * 4 + 4
 
     # roofline of the dominant kernel (the fused forward stage contraction): forward-only solve, CUDA events around it
@@ -382,6 +500,14 @@ def run_ours(args):
                     "cap_gbs": 6300.0 * sm_max * 1e6 / 1e9, "frac": l2_bytes / avg_launch / (6300.0 * sm_max * 1e6)},
     }
 
+    # correctness inside the bench run: oracle parity of the timed configuration (rank 0) and the sharding-invariance probe
+    parity = None
+    if rank == 0 and args.parity_trials > 0:
+        parity = parity_block(torch, odecol, net, args, kt, ku, tv, sel, dev, options)
+    probe = None
+    if args.probe_trials > 0:
+        probe = probe_block(torch, dist, odecol, net, args, tv, sel, dev, options, rank, world)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         one_pass, ps, threads, sample = cpu_sample(args)
@@ -395,9 +521,9 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong" if args.trials_total else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "populations": n, "trials_per_gpu": B, "time_points": T,
+            "config": {"workload": workload_name(args), "populations": n, "trials_per_gpu": B * chunks, "time_points": T,
                        "solver": "rk4 (3/8 rule) + exact discrete adjoint", "l2": "working set larger than L2: 126 GB of per-step checkpoints (or the 75 GB trajectory) stream through HBM every pass",
                        "parallelism": f"trial-parallel x{world}, allreduce(dW) per step" if world > 1 else "single GPU"},
             "clocks": clocks,
@@ -407,6 +533,8 @@ def run_ours(args):
             "phases": phases,
             "cpu_baseline": cpu,
             "loss": float(loss),
+            "parity": parity,
+            "probe": probe,
         }))
     if world > 1:
         dist.destroy_process_group()

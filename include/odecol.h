@@ -117,6 +117,14 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
  * (src/utils.py:13-46). */
 int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f, void* stream);
 
+/* The same evaluation through the staged tensor-core path the large-network solvers use (operand split, 3xTF32
+ * tcgen05 contraction with chunked accumulation for long rows, fast FP32-accurate phi): the unit the N = 8192 sweep
+ * (BASELINE.json configs[4]) spends its time in.  Any N that is a multiple of 4; workspace:
+ * odecol_workspace_bytes(p, ODECOL_OP_EM_FWD, 0, 0) sized for the STAGED family (set ODECOL_FLAG_FORCE_STAGED or
+ * ODECOL_FLAG_FORCE_TENSOR on problems that would otherwise pick the on-chip family). */
+int odecol_drift_staged(const odecol_problem* p, const float* t, const float* y, float* f,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fixed-grid RK4 (3/8 rule) on the grid t[0..T): y_out[0] = y0, y_out[j] = y(t[j]).
  * Replaces torchdiffeq.odeint(func, y0, t, method='rk4') plus the per-trial Python loop
  * (scripts/xor_ode.py:104-117, scripts/parity_ode.py:223-236, scripts/wta_ode.py:167-176).
@@ -202,6 +210,14 @@ int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const flo
                   float dt, int32_t adaptive, float rtol, float atol, float dt_min,
                   int32_t* n_accept, int32_t* n_reject, int32_t* status, float* y_steps,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* The Brownian path the adaptive solvers integrate against, for reproduction and validation: W(t[m]) - W(t_begin) of
+ * trial (trial_offset + b) on the virtual Brownian tree spanning [t_begin, t_end] (Philox4x32-10 keyed by seed; the
+ * solve over ts uses t_begin = ts[0], t_end = ts[T-1]).  Stands in for torchsde's BrownianInterval object, which a
+ * caller can query after sdeint returns (torchsde.sdeint(..., bm=bm); reference call sites scripts/wta_ode.py:174,200
+ * pass none and get a fresh one).  t[M] device pointer, w (M, B) out. */
+int odecol_brownian_query(uint64_t seed, int64_t trial_offset, int32_t B, float t_begin, float t_end, const float* t,
+                          int32_t M, float* w, void* stream);
 
 /* Number of fixed steps odecol_em_fwd takes for (ts, dt): the float32 time loop is data independent.
  * ts is a HOST pointer here. */

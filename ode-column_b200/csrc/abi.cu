@@ -103,6 +103,17 @@ int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f
     return launch_rhs_generic(d, t, y, f, static_cast<cudaStream_t>(stream));
 }
 
+int odecol_drift_staged(const odecol_problem* p, const float* t, const float* y, float* f, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (!t || !y || !f) return ODECOL_E_NULL;
+    if (misaligned(y) || misaligned(f) || misaligned(workspace)) return ODECOL_E_ALIGN;
+    g_launches.store(0, std::memory_order_relaxed);
+    return stage_drift(d, t, y, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
                    int32_t out_every, void* workspace, size_t workspace_bytes, void* stream) {
     DevProblem d;
@@ -344,6 +355,14 @@ int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const fl
     if (r2) return r2;
     return launch_srk_bwd_small(d, T, y_steps, dW, dU, seed, trial_offset, grad_y, sel, G, grad_y0, grad_W_aug, step_of,
                                 wts, tk, s);
+}
+
+int odecol_brownian_query(uint64_t seed, int64_t trial_offset, int32_t B, float t_begin, float t_end, const float* t,
+                          int32_t M, float* w, void* stream) {
+    if (!t || !w) return ODECOL_E_NULL;
+    if (B < 1 || M < 1 || !(t_end > t_begin)) return ODECOL_E_SHAPE;
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_brownian_query(seed, trial_offset, B, t_begin, t_end - t_begin, t, M, w, static_cast<cudaStream_t>(stream));
 }
 
 int odecol_ww_generate(const double* mu, const double* i_noise0, int32_t B, int32_t steps_per_phase, int32_t every,

@@ -67,6 +67,10 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
                          int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
                          const int* step_of, const float* w, const float* tk, cudaStream_t s);
 
+// W(t[m]) of the virtual Brownian tree of trial (trial_offset + b) on [t_begin, t_begin + span]: w[m][b]
+int launch_brownian_query(uint64_t seed, int64_t trial_offset, int B, float t_begin, float span, const float* t, int M,
+                          float* w, cudaStream_t s);
+
 // ---- Wong-Wang target generator (ww_kernel.cu) -----------------------------------------------------------------
 int launch_ww_generate(const double* mu, const double* i_noise0, int B, int steps_per_phase, int every, int time_steps,
                        double sigma_noise, uint64_t seed, int64_t trial_offset, float* states, cudaStream_t s);
@@ -88,6 +92,9 @@ int stage_rk4_bwd(const DevProblem& p, const float* t_dev, int T, const float* y
 int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
                  uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
                  int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// one drift evaluation through the staged tensor-core path (workspace of stage_em_fwd)
+int stage_drift(const DevProblem& p, const float* t_trial, const float* y, float* f, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // staged Dormand-Prince 5(4), forward (stage_em.cu): per-trial control in rounds, drift on the tensor cores
 size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int T);

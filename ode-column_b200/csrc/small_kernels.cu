@@ -1214,4 +1214,26 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// W(t) of the virtual Brownian tree the adaptive Euler-Maruyama solvers draw from (odecol_brownian_query): one thread
+// per (query time, trial), the sequential walk every kernel family uses.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_brownian_query(unsigned long long seed, long long trial_offset, int B, float t_begin, float span,
+                                 const float* __restrict__ t, int M, float* __restrict__ w) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)M * B) return;
+    const int m = (int)(e / B), b = (int)(e % B);
+    const Philox px(seed);
+    w[e] = brownian_tree(px, (unsigned long long)(trial_offset + b), t_begin, span, __ldg(t + m));
+}
+
+int launch_brownian_query(uint64_t seed, int64_t trial_offset, int B, float t_begin, float span, const float* t, int M,
+                          float* w, cudaStream_t s) {
+    const long long total = (long long)M * B;
+    k_brownian_query<<<(unsigned)((total + 127) / 128), 128, 0, s>>>((unsigned long long)seed, (long long)trial_offset, B, t_begin,
+                                                                      span, t, M, w);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 }  // namespace odecol

@@ -516,6 +516,33 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
 }
 
 
+// One drift evaluation of the staged solvers, f[b] = forward(t[b], y[b]), as the sweeps above run it: operand kernel,
+// tensor-core contraction, RhsEpi.  Lets callers (and the parity tests) reach the unit C5 spends its time in.
+int stage_drift(const DevProblem& p, const float* t_trial, const float* y, float* f, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const EmLayout L = em_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    if (p.N % 4 != 0) return ODECOL_E_UNSUPPORTED;
+    char* w = static_cast<char*>(ws);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
+    float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo);
+    const int Kaug = p.N + p.n_in + 1;
+    if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
+    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+    k_em_operand<<<p.B, 128, 0, s>>>(p, y, t_trial, 0.f, Rhi, Rlo, L.KPa);
+    count_launch(2);
+    CUtensorMap mWhi, mWlo, mRhi, mRlo;
+    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+        return ODECOL_E_CUDA;
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    RhsEpi e;
+    e.p = p; e.y = y; e.Rhi = Rhi; e.Rlo = Rlo; e.f = f; e.KPa = L.KPa;
+    e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+    return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // Staged Dormand-Prince 5(4): torchdiffeq's default solver for networks beyond the on-chip family.  Same structure as
 // the adaptive Euler-Maruyama above -- every trial carries its own (t, dt), one ROUND = one attempted step of every

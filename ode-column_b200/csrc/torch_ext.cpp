@@ -91,6 +91,20 @@ torch::Tensor rhs(const Problem& pr, const torch::Tensor& t, const torch::Tensor
     return f;
 }
 
+torch::Tensor drift_staged(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y, "y");
+    want(t, "t");
+    TORCH_CHECK(t.numel() == pr.B(), "odecol: t must have one entry per trial");
+    auto f = torch::empty_like(y);
+    Problem staged = pr;                                   // workspace of the staged family whatever the size
+    staged.p.flags |= ODECOL_FLAG_FORCE_STAGED;
+    auto ws = staged.workspace(ODECOL_OP_EM_FWD, 2);
+    check(odecol_drift_staged(&pr.p, t.data_ptr<float>(), y.data_ptr<float>(), f.data_ptr<float>(), ws.data_ptr(),
+                              (size_t)ws.numel(), pr.stream()), "drift_staged");
+    return f;
+}
+
 torch::Tensor rk4_fwd(const Problem& pr, const torch::Tensor& t, const torch::Tensor& y0, int64_t out_every) {
     c10::cuda::CUDAGuard g(pr.W_aug.device());
     check_state(pr, y0, "y0");
@@ -359,6 +373,17 @@ std::vector<torch::Tensor> srk_bwd(const Problem& pr, const torch::Tensor& ts, c
     return {gy0, gW};
 }
 
+// W(t) - W(t_begin) on the virtual Brownian tree of the adaptive solvers: t (M,) -> (M, B)
+torch::Tensor brownian_query(int64_t seed, int64_t trial_offset, int64_t B, double t_begin, double t_end, const torch::Tensor& t) {
+    c10::cuda::CUDAGuard g(t.device());
+    want(t, "t");
+    auto w = torch::empty({t.numel(), B}, t.options());
+    check(odecol_brownian_query((uint64_t)seed, trial_offset, (int32_t)B, (float)t_begin, (float)t_end, t.data_ptr<float>(),
+                                (int32_t)t.numel(), w.data_ptr<float>(), at::cuda::getCurrentCUDAStream(t.device().index()).stream()),
+          "brownian_query");
+    return w;
+}
+
 torch::Tensor ww_generate(const torch::Tensor& mu, std::optional<torch::Tensor> i_noise0, int64_t steps_per_phase,
                           int64_t every, int64_t time_steps, double sigma_noise, int64_t seed, int64_t trial_offset) {
     c10::cuda::CUDAGuard g(mu.device());
@@ -447,6 +472,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("strerror", [](int c) { return std::string(odecol_strerror(c)); });
     m.def("last_launch_count", &odecol_last_launch_count);
     m.def("rhs", &rhs);
+    m.def("drift_staged", &drift_staged);
     m.def("rk4_fwd", &rk4_fwd);
     m.def("rk4_bwd", &rk4_bwd);
     m.def("rk4_ckpt_bytes", &rk4_ckpt_bytes);
@@ -460,6 +486,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_bwd", &em_bwd);
     m.def("srk_fwd", &srk_fwd);
     m.def("srk_bwd", &srk_bwd);
+    m.def("brownian_query", &brownian_query);
     m.def("ww_generate", &ww_generate);
     m.def("huber_rate_loss", &huber_rate_loss);
     m.def("tc_contract", &tc_contract);

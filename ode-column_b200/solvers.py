@@ -75,6 +75,23 @@ class _Setup:
         return prob
 
 
+_STATUS_NAMES = {1: "state became non-finite", 2: "step budget (max_num_steps) exhausted", 3: "step size underflow"}
+
+
+def _check_status(status: torch.Tensor, options: dict, what: str):
+    """torchdiffeq / torchsde raise when a solve fails (max_num_steps exceeded, dt underflow); the kernels report a
+    per-trial status and fill the remaining output rows with NaN, so the default is to raise here too.
+    ``options={'check_status': False}`` skips the check (and the device synchronisation it costs)."""
+    if not options.get("check_status", True) or status is None or status.numel() == 0:
+        return
+    if bool((status != 0).any()):
+        bad = torch.nonzero(status != 0).flatten()[:8].tolist()
+        codes = [int(status[b]) for b in bad]
+        raise RuntimeError(f"odecol: {what} failed for trial(s) {bad} (first of {int((status != 0).sum())}): " +
+                           "; ".join(f"trial {b}: {_STATUS_NAMES.get(c, c)}" for b, c in zip(bad, codes)) +
+                           " -- pass options={'check_status': False} and stats={} to inspect the partial result")
+
+
 def _sel_tensors(components, N3, device):
     if components is None:
         return None, None
@@ -209,6 +226,7 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
                                              float(atol), int(options.get("max_num_steps", _DEFAULT_MAX_STEPS)))
         if stats is not None:
             stats.update(n_accept=na, n_reject=nr, status=st)
+        _check_status(st, options, "dopri5")
         return y if sel_long is None else y.index_select(2, sel_long)
     raise ValueError(f"odecol: method {method!r} is not fused (have 'rk4', 'dopri5')")
 
@@ -288,7 +306,9 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     sel_long, sel_i32 = _sel_tensors(components, 3 * setup.lf.N, y0.device)
     ext = setup.ext
     if seed is None:
-        seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        # torchsde builds a fresh BrownianInterval (new entropy) per call: draw a new key from torch's global generator, so
+        # successive calls see independent paths and torch.manual_seed still reproduces a run
+        seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
     dt = float(dt)
     if adaptive:
         if bm is not None:
@@ -298,6 +318,7 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
                                       int(trial_offset), dt, True, float(rtol), float(atol), float(dt_min), 0)
         if stats is not None:
             stats.update(n_accept=na, n_reject=nr, status=st)
+        _check_status(st, options, "adaptive Euler-Maruyama")
         return y if sel_long is None else y.index_select(2, sel_long)
     ts_cpu = setup.t.cpu()
     n_steps = int(ext.em_num_steps(ts_cpu, dt))

@@ -87,3 +87,14 @@ def block_errs(a, b):
 
 def rel_err(a, b):
     return max(block_errs(a, b))
+
+
+def sheet_oracle_form(sheet):
+    """Oracle LinearForm of a product SyntheticColumnSheet (its W_aug split back into W | U | bias)."""
+    from oracle.column_model import LinearForm
+    lfp = sheet.export_linear_form()
+    n, n_in = lfp.N, lfp.n_in
+    Wa = lfp.W_aug.detach().cpu().numpy()
+    return LinearForm(W=Wa[:, :n], U=Wa[:, n:n + n_in], bias=Wa[:, n + n_in], kappa=lfp.kappa.cpu().numpy(),
+                      sigma=lfp.sigma.cpu().numpy(), tau_s=lfp.tau_s, tau_m=lfp.tau_m, tau_a=lfp.tau_a,
+                      resistance=lfp.resistance)

@@ -1,0 +1,254 @@
+"""Oracle parity on the paths bench.py actually runs:
+
+  * C4: rk4 forward + exact discrete adjoint at N = 512, n_in = 64 (K_aug = 577, four population tiles), batches large enough
+    that the persistent tcgen05 kernels own SEVERAL (population tile, trial tile) pairs per CTA and more tiles than SMs --
+    the cross-CTA `done[nt]` counter protocol of stage_tc_persist.cu / k_tc_bwd_chain -- in checkpoint and recompute mode,
+    persistent and per-stage launches, with and without an F component in the selection;
+  * C5: the adaptive Euler-Maruyama controller (on-chip and staged) against oracle.solvers.sdeint_euler(adaptive=True)
+    trial by trial (torchsde controls the step of each solve on its own), first without noise, then on the SAME
+    Brownian path (odecol_brownian_query exposes the virtual tree the kernels draw from);
+  * C5: one drift evaluation at N = 8192 (K_aug = 9217: chunked accumulation, grouped tile order, 64 population tiles)
+    against the float64 oracle right-hand side.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import odecol
+from oracle import rhs as orhs, solvers as S
+from helpers import XOR_DICT, oracle_form, product_network, sheet_oracle_form
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scale(a):
+    return float(a.abs().max().clamp_min(1e-30))
+
+
+def _relmax(a, b):
+    return float((a - b).abs().max()) / _scale(b)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C4 shape
+# ----------------------------------------------------------------------------------------------------------------------
+def _c4_problem(cfg, B, T, seed):
+    cols, N = 64, 512
+    sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device=DEV)
+    gen = torch.Generator().manual_seed(seed)
+    amp = torch.rand(B, cols, generator=gen) * 30.0
+    dt = 1e-4
+    t_end = (T - 1) * dt
+    kt, ku = odecol.step_knots(0.3 * t_end, 0.7 * t_end, t_end, amp, dt)       # stimulus switches on and off inside the window
+    sheet.set_knots(kt.to(DEV), ku.to(DEV))
+    tv = torch.linspace(0.0, t_end, T)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen),
+                    torch.rand(B, N, generator=gen) * 2), 1)
+    return sheet, kt, ku, tv, y0, gen
+
+
+def _oracle_rk4_grads(lf, kt, ku, tv, y0, sel, wgt, chunk=256):
+    """Oracle rk4 + autograd, trial chunk by trial chunk (trials are independent; dW, dU, dbias add up)."""
+    B = y0.shape[0]
+    traj, gy0 = [], []
+    gW = gU = gb = None
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        ode = orhs.UnifiedColumnODE(lf, kt.numpy(), ku[lo:hi].numpy(), requires_grad=True)
+        y0c = y0[lo:hi].clone().requires_grad_(True)
+        yo = S.odeint_rk4(ode, y0c, tv)
+        ys = yo[:, :, sel]
+        (ys * wgt[:, lo:hi]).sum().backward()
+        traj.append(ys.detach())
+        gy0.append(y0c.grad)
+        gW = ode.W.grad if gW is None else gW + ode.W.grad
+        gU = ode.U.grad if gU is None else gU + ode.U.grad
+        gb = ode.bias.grad if gb is None else gb + ode.bias.grad
+    return torch.cat(traj, 1), torch.cat(gy0, 0), gW, gU, gb
+
+
+C4_CASES = [
+    # B,    T,  checkpoint, persistent, with_F
+    (4790, 10, True, "1", False),        # TN = 80: 240 tiles on 148 CTAs (92 CTAs own two), ragged last trial tile
+    (4790, 10, True, "1", True),
+    (4790, 10, False, "1", False),       # recompute mode: trajectory + three recomputed contractions per reverse step
+    (4790, 10, True, "0", False),        # one launch per stage instead of the cooperative kernels
+    (8192, 6, True, "1", False),         # the benched batch: TN = 112, 296 tiles = exactly two per CTA
+]
+
+
+@pytest.mark.parametrize("B,T,ckpt,persistent,with_f", C4_CASES,
+                         ids=lambda v: str(v))
+def test_rk4_adjoint_at_the_benchmarked_shape(cfg, B, T, ckpt, persistent, with_f):
+    sheet, kt, ku, tv, y0, gen = _c4_problem(cfg, B, T, seed=B + T)
+    N = 512
+    sel = list(range(0, N, 8)) + list(range(N, 2 * N, 8)) + [3, 130, 257, 511, N + 1, N + 300]     # the bench's read-out + strays
+    if with_f:
+        sel += [2 * N, 2 * N + 129, 3 * N - 1]
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    lf = sheet_oracle_form(sheet)
+    tro, gy0o, gWo, gUo, gbo = _oracle_rk4_grads(lf, kt, ku, tv, y0, sel, wgt)
+
+    old = os.environ.get("ODECOL_PERSISTENT")
+    os.environ["ODECOL_PERSISTENT"] = persistent
+    try:
+        y0p = y0.to(DEV).requires_grad_(True)
+        yp = odecol.odeint(sheet, y0p, tv.to(DEV), method="rk4", components=sel, options={"checkpoint": ckpt})
+        assert ("Ckpt" in type(yp.grad_fn).__name__) == ckpt
+        (yp * wgt.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("ODECOL_PERSISTENT", None)
+        else:
+            os.environ["ODECOL_PERSISTENT"] = old
+    nV = len([c for c in sel if c < N])
+    nA = len([c for c in sel if N <= c < 2 * N])
+    ypc = yp.detach().cpu()
+    blocks = {"V": slice(0, nV), "A": slice(nV, nV + nA)}
+    if with_f:
+        blocks["F"] = slice(nV + nA, len(sel))
+    et = max(_relmax(ypc[:, :, sl], tro[:, :, sl]) for sl in blocks.values())
+    e0 = _relmax(y0p.grad.cpu(), gy0o)
+    eW = _relmax(sheet.recurrent_weights.grad.cpu(), gWo)
+    eU = _relmax(sheet.input_weights.grad.cpu(), gUo)
+    print(f"\n[C4 shape B={B} T={T} ckpt={ckpt} persistent={persistent} F={with_f}] trajectory {et:.1e}  dy0 {e0:.1e}  "
+          f"dW {eW:.1e}  dU {eU:.1e}")
+    assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5 and eU < 5e-5
+    # worst single trial (a mis-addressed trial tile would hide in a max over the whole batch only if it were tiny)
+    per_trial = (ypc - tro).abs().amax(dim=(0, 2)) / tro.abs().amax(dim=(0, 2)).clamp_min(1e-6)
+    assert float(per_trial.max()) < 2e-5, int(per_trial.argmax())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# adaptive Euler-Maruyama vs the oracle's step-doubling loop
+# ----------------------------------------------------------------------------------------------------------------------
+class _TreeBrownian:
+    """bm(t0, t1) for the oracle, reading the virtual Brownian tree of ONE trial through odecol_brownian_query -- the
+    path the kernels integrate against.  shape = (1, 1) like a torchsde Brownian object for one scalar-noise solve."""
+
+    def __init__(self, seed, trial, t_begin, t_end):
+        self.ext = odecol._native.ext()
+        self.seed, self.trial, self.t_begin, self.t_end = seed, trial, float(t_begin), float(t_end)
+        self.shape = (1, 1)
+
+    def __call__(self, t0, t1):
+        q = torch.tensor([float(t0), float(t1)], dtype=torch.float32, device=DEV)
+        w = self.ext.brownian_query(self.seed, self.trial, 1, self.t_begin, self.t_end, q).cpu()
+        return (w[1] - w[0]).reshape(1, 1)
+
+
+class _NoBrownian:
+    shape = (1, 1)
+
+    def __call__(self, t0, t1):
+        return torch.zeros(1, 1)
+
+
+def _oracle_adaptive(lf, kt, ku, ts, y0, sigma_scale, bms, rtol, atol, dt, dt_min):
+    """One adaptive solve per trial, as the reference runs them (B = 1 per sdeint call)."""
+    ys, na, nr = [], [], []
+    for b in range(y0.shape[0]):
+        lfb = lf
+        if sigma_scale is not None:
+            import dataclasses
+            lfb = dataclasses.replace(lf, sigma=(lf.sigma * float(sigma_scale[b])).astype(np.float32))
+        ode = orhs.UnifiedColumnODE(lfb, kt.numpy(), ku[b:b + 1].numpy() if ku.shape[0] > 1 else ku.numpy())
+        st = {}
+        with torch.no_grad():
+            y = S.sdeint_euler(ode, y0[b:b + 1], ts, bms[b], dt=dt, adaptive=True, rtol=rtol, atol=atol, dt_min=dt_min, stats=st)
+        ys.append(y)
+        na.append(st["n_accept"]); nr.append(st["n_reject"])
+    return torch.cat(ys, 1), np.array(na), np.array(nr)
+
+
+def _adaptive_case(kind, cfg, golden):
+    gen = torch.Generator().manual_seed(11)
+    if kind == "xor":                                         # on-chip family, the reference's XOR network
+        net = product_network("xor", cfg, golden["xor"], DEV)
+        lf = oracle_form("xor", cfg, golden["xor"])
+        B, N = 4, 24
+        amp = torch.tensor([[20.0, 0.0], [0.0, 20.0], [20.0, 20.0], [0.0, 0.0]])
+        u = torch.zeros(B, 2, 16)
+        u[:, 0, 2] = u[:, 0, 3] = amp[:, 0]; u[:, 1, 10] = u[:, 1, 11] = amp[:, 1]
+        kt = torch.tensor([0.0, 0.01, 0.0101, 1.0])
+        ku = torch.stack((torch.zeros(B, 32), torch.zeros(B, 32), u.reshape(B, 32), u.reshape(B, 32)), 1)
+        net.time_vec, net.stim = kt.to(DEV), ku.reshape(B, 4, 2, 16).to(DEV)
+        ts = torch.linspace(0.0, 0.06, 7)
+        options = {}
+    else:                                                     # staged family: 32-column sheet, N = 256
+        net = odecol.SyntheticColumnSheet(cfg, 32, seed=3, device=DEV, sigma_v=4.0)
+        lf = sheet_oracle_form(net)
+        B, N = 3, 256
+        amp = torch.rand(B, 32, generator=gen) * 25
+        kt, ku = odecol.step_knots(1e-3, 5e-3, 8e-3, amp, 1e-4)
+        net.set_knots(kt.to(DEV), ku.to(DEV))
+        ts = torch.linspace(0.0, 6e-3, 5)
+        options = {}
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 4 - 6, torch.rand(B, N, generator=gen) * 0.5,
+                    torch.rand(B, N, generator=gen)), 1)
+    return net, lf, kt, ku, ts, y0, B, options
+
+
+@pytest.mark.parametrize("noise", [False, True], ids=["deterministic", "same_brownian_path"])
+@pytest.mark.parametrize("kind", ["xor", "sheet256"])
+def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg, golden):
+    net, lf, kt, ku, ts, y0, B, options = _adaptive_case(kind, cfg, golden)
+    rtol, atol, dt, dt_min = 1e-5, 1e-4, 1e-3, 1e-5
+    seed, trial_offset = 77, 5
+    sc = torch.tensor([0.0] * B) if not noise else torch.tensor([0.05, 0.1, 0.2, 0.15][:B])
+    bms = [(_TreeBrownian(seed, trial_offset + b, ts[0], ts[-1]) if noise else _NoBrownian()) for b in range(B)]
+    yo, nao, nro = _oracle_adaptive(lf, kt, ku, ts, y0, sc.numpy(), bms, rtol, atol, dt, dt_min)
+    st = {}
+    with torch.no_grad():
+        yp = odecol.sdeint(net, y0.to(DEV), ts.to(DEV), method="euler", dt=dt, adaptive=True, rtol=rtol, atol=atol,
+                           dt_min=dt_min, seed=seed, trial_offset=trial_offset, stats=st,
+                           options=dict(options, sigma_scale=sc))
+    torch.cuda.synchronize()
+    na, nr = st["n_accept"].cpu().numpy(), st["n_reject"].cpu().numpy()
+    assert int(st["status"].abs().sum()) == 0
+    N = y0.shape[1] // 3
+    eV = _relmax(yp.cpu()[..., :N], yo[..., :N]); eA = _relmax(yp.cpu()[..., N:2 * N], yo[..., N:2 * N])
+    eF = _relmax(yp.cpu()[..., 2 * N:], yo[..., 2 * N:])
+    print(f"\n[adaptive EM {kind} noise={noise}] accepted {na.tolist()} vs oracle {nao.tolist()}; rejected {nr.tolist()} vs "
+          f"{nro.tolist()}; outputs V {eV:.1e} A {eA:.1e} F {eF:.1e}")
+    assert np.all(np.abs(na - nao) <= 2) and np.all(np.abs(nr - nro) <= 2)
+    assert max(eV, eA, eF) < 1e-4
+    assert nao.min() > 10                                        # the controller really ran (not parked at one step)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C5: one drift evaluation at N = 8192
+# ----------------------------------------------------------------------------------------------------------------------
+def test_c5_drift_evaluation_matches_the_float64_oracle(cfg):
+    cols, N, B = 1024, 8192, 300
+    sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device=DEV)
+    gen = torch.Generator().manual_seed(5)
+    amp = torch.rand(B, cols, generator=gen) * 30.0
+    kt = torch.tensor([0.0, 1.0])
+    ku = torch.stack((amp, amp * 0.5), 1)                        # a ramp: the lookup interpolates
+    tq = torch.rand(B, generator=gen)
+    y = torch.cat((torch.rand(B, N, generator=gen) * 10 - 8, torch.rand(B, N, generator=gen) * 2,
+                   torch.rand(B, N, generator=gen) * 3), 1)
+    ext = odecol._native.ext()
+    lfp = sheet.export_linear_form()
+    prob = ext.Problem(lfp.W_aug.detach().contiguous(), lfp.kappa.contiguous(), lfp.sigma.contiguous(), kt.to(DEV), ku.to(DEV),
+                       lfp.n_in, B, lfp.tau_s, lfp.tau_m, lfp.tau_a, lfp.resistance, 0)
+    f = ext.drift_staged(prob, tq.to(DEV), y.to(DEV)).cpu()
+    torch.cuda.synchronize()
+    ode = orhs.UnifiedColumnODE(sheet_oracle_form(sheet), kt.numpy(), ku.numpy(), dtype=torch.float64)
+    fo = ode.forward(tq.double(), y.double())
+    # error scale of the V slope: the contraction's sum |w||r| times tau_s R / tau_m, plus |V| / tau_m
+    r = orhs.phi(y[:, :N].double() - y[:, N:2 * N].double())
+    s = orhs.interp_knots(tq.double(), ode.knot_t, ode.knot_u)
+    mag = (r.abs() @ ode.W.abs().T + s.abs() @ ode.U.abs().T + ode.bias.abs()) * float(ode.tau_s * ode.R / ode.tau_m) \
+        + y[:, :N].double().abs() / float(ode.tau_m)
+    eV = float(((f[:, :N].double() - fo[:, :N]).abs() / mag).max())
+    eA = _relmax(f[:, N:2 * N].double(), fo[:, N:2 * N]); eF = _relmax(f[:, 2 * N:].double(), fo[:, 2 * N:])
+    print(f"\n[C5 drift N={N} B={B}] dV err / (sum|w||r| scale) {eV:.2e}; dA {eA:.1e}; dF {eF:.1e}; "
+          f"dV rel to max|dV| {_relmax(f[:, :N].double(), fo[:, :N]):.1e}")
+    assert eV < 4e-6 and eA < 2e-6 and eF < 2e-6
