@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--c5-columns", type=int, default=1024)
     ap.add_argument("--c5-trials", type=int, default=8192, help="sweep members in total (strong scaling over GPUs)")
     ap.add_argument("--c5-horizon", type=float, default=0.004, help="simulated seconds per step of the c5 workload")
+    ap.add_argument("--c5-no-gain", action="store_true", help="c5 without the lateral-gain sweep axis (the round-1 workload)")
+    ap.add_argument("--no-secondary", action="store_true", help="c4: skip the compact C5 measurement embedded as `secondary`")
     ap.add_argument("--trials-total", type=int, default=0,
                     help="c4: total trials of the job (strong scaling): every rank integrates trials-total / gpus trials per step in "
                          "chunks of --trials-per-gpu, accumulating dW; 65536 = the literal BASELINE.json configs[3] batch at any N")
@@ -508,6 +510,18 @@ def run_ours(args):
     if args.probe_trials > 0:
         probe = probe_block(torch, dist, odecol, net, args, tv, sel, dev, options, rank, world)
 
+    # BASELINE.json configs[4] next to the headline: one short adaptive Euler-Maruyama sweep at N = 8192 (strong scaling)
+    secondary = None
+    if not args.no_secondary:
+        del net
+        step.ku_devs = step.ku_dev = step.y0_dev = None
+        torch.cuda.empty_cache()
+        sec_line = c5_measure(args, torch, dist, odecol, dev, rank, world, 1, 1, args.c5_horizon)
+        secondary = {k: sec_line[k] for k in ("metric", "value", "unit", "scaling", "ms_per_step", "config", "gpu_launches",
+                                               "attempted_steps_per_member", "accepted_steps_per_member", "rounds_per_solve",
+                                               "all_members_finite")}
+        secondary["roofline"] = {k: sec_line["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac")}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         one_pass, ps, threads, sample = cpu_sample(args)
@@ -535,24 +549,18 @@ def run_ours(args):
             "loss": float(loss),
             "parity": parity,
             "probe": probe,
+            "secondary": secondary,
         }))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_c5(args):
+def c5_measure(args, torch, dist, odecol, dev, rank, world, steps, warmup, horizon):
     """BASELINE.json configs[4]: 1,024-column network (N = 8192, dense W on the tensor cores), sweep of
-    8192 members differing in stimulus amplitude and noise amplitude (sigma in [0, 20]), stochastic adaptive Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3,
-    dt_min 1e-5, in-kernel Philox seed 0), members sharded over the GPUs (strong scaling, no collective).  One step =
-    one solve over --c5-horizon simulated seconds; the unit is one population advanced by one ATTEMPTED step."""
-    import torch
-    import torch.distributed as dist
-    import odecol
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        init_nccl(torch, dist, dev)
+    8192 members differing in stimulus amplitude, noise amplitude (sigma in [0, 20]) and global lateral gain (0.5 .. 1.5),
+    stochastic adaptive Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3, dt_min 1e-5, in-kernel Philox seed 0), members
+    sharded over the GPUs (strong scaling, no collective).  One step = one solve over `horizon` simulated seconds; the unit
+    is one population advanced by one ATTEMPTED step.  Returns the fields of the JSON line (rank 0 prints)."""
     ext = odecol._native.ext()
     cfg = odecol.load_config(os.path.join(ROOT, "config", "model.toml"))
     cols, n = args.c5_columns, 8 * args.c5_columns
@@ -563,44 +571,56 @@ def run_c5(args):
     amp = (torch.rand(args.c5_trials, 1, generator=g) * 30.0)[lo:hi].expand(B, cols).contiguous()
     # second sweep axis: the noise amplitude, sigma in [0, 20] (SyntheticColumnSheet carries sigma_V = 10)
     sigma_scale = (torch.rand(args.c5_trials, generator=g) * 2.0)[lo:hi].contiguous().to(dev)
+    # third sweep axis: the global lateral gain, 0.5 .. 1.5 times the network's between-column weights
+    lateral_gain = (0.5 + torch.rand(args.c5_trials, generator=g))[lo:hi].contiguous().to(dev)
     kt = torch.tensor([0.0, 1.0], device=dev)
     ku = torch.stack((amp, amp), dim=1).to(dev)                  # constant stimulus, per-member amplitude
     net.set_knots(kt, ku)
-    ts = torch.linspace(0.0, args.c5_horizon, 3, device=dev)
     y0 = torch.zeros(B, 3 * n, device=dev)
+    sweep = {"sigma_scale": sigma_scale}
+    if not args.c5_no_gain:
+        sweep["lateral_gain"] = lateral_gain
 
-    def step():
+    def step(h):
         st = {}
+        ts = torch.linspace(0.0, h, 3, device=dev)
         with torch.no_grad():
             y = odecol.sdeint(net, y0, ts, method="euler", dt=1e-3, adaptive=True, rtol=1e-5, atol=1e-4, dt_min=1e-5,
-                              seed=0, trial_offset=lo, stats=st, options={"sigma_scale": sigma_scale})
+                              seed=0, trial_offset=lo, stats=st, options=dict(sweep))
         return y, st, ext.last_launch_count()
 
-    for _ in range(args.warmup):
-        step()
+    for _ in range(warmup):
+        step(min(horizon, 2e-4))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     attempts = torch.zeros((), device=dev, dtype=torch.float64)
+    accepted = torch.zeros((), device=dev, dtype=torch.float64)
     launches = 0
-    for _ in range(args.steps):
-        y, st, nl = step()
+    for _ in range(steps):
+        y, st, nl = step(horizon)
         attempts += (st["n_accept"] + st["n_reject"]).double().sum()
+        accepted += st["n_accept"].double().sum()
         launches += nl
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    rounds_t = (st["n_accept"] + st["n_reject"]).max().double()
+    finite = torch.isfinite(y[-1]).all().double()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(attempts)
+        dist.all_reduce(accepted)
+        dist.all_reduce(rounds_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     clocks = sampler.stop() if rank == 0 else None
     sec = float(ms) / 1e3
-    rounds = int(st["n_accept"].max() + st["n_reject"].max())
+    rounds = int(rounds_t)
     value = n * float(attempts) / sec
     peaks = {}
     try:
@@ -617,23 +637,41 @@ def run_c5(args):
             traffic, traffic_src = rec["dram_bytes_per_drift_evaluation"], rec["source"]
     except (OSError, KeyError, ValueError):
         pass
-    rhs_launches = args.steps * 2 * rounds                        # two drift evaluations per round, all members
-    achieved = 2.0 * n * kaug * B * rhs_launches / sec / 1e12     # whole solve attributed to the contraction launches
+    # two drift evaluations per round, all resident members (max over ranks of the rounds: the slowest rank sets the time)
+    achieved = 2.0 * n * kaug * B * 2 * rounds * steps / sec / 1e12 if rounds else 0.0
+    del net, y0, y
+    torch.cuda.empty_cache()
+    return {
+        "metric": "population_steps_per_sec_adaptive_em", "value": value, "unit": "population-steps/s (attempted steps)",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5: synthetic {cols}-column network (N={n}), sweep of {args.c5_trials} members (stimulus amplitude, "
+                   f"sigma in [0, 20]" + ("" if args.c5_no_gain else ", global lateral gain in [0.5, 1.5]") + "), adaptive "
+                   f"Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3, dt_min 1e-5, Philox seed 0), {horizon}s horizon",
+                   "l2": "W_aug hi+lo (539 MB) larger than L2"},
+        "clocks": clocks, "gpu_launches": launches,
+        "attempted_steps_per_member": float(attempts) / steps / args.c5_trials,
+        "accepted_steps_per_member": float(accepted) / steps / args.c5_trials, "rounds_per_solve": rounds,
+        "all_members_finite": bool(finite > 0),
+        "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (3xTF32 tcgen05 drift evaluation)",
+                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "note": "lower bound: the elementwise stepping kernels are inside the timed region; per rank at N > 1"},
+    }
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    import odecol
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        init_nccl(torch, dist, dev)
+    line = c5_measure(args, torch, dist, odecol, dev, rank, world, args.steps, args.warmup, args.c5_horizon)
     if rank == 0:
-        print(json.dumps({
-            "metric": "population_steps_per_sec_adaptive_em", "value": value, "unit": "population-steps/s (attempted steps)",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5: synthetic {cols}-column network (N={n}), sweep of {args.c5_trials} members, adaptive "
-                       f"Euler-Maruyama (rtol 1e-5, atol 1e-4, dt 1e-3, dt_min 1e-5, Philox seed 0), {args.c5_horizon}s horizon",
-                       "l2": "W_aug hi+lo (539 MB) larger than L2"},
-            "clocks": clocks, "gpu_launches": launches,
-            "attempted_steps_per_member": float(attempts) / args.steps / args.c5_trials, "rounds_per_solve": rounds,
-            "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (3xTF32 tcgen05 drift evaluation)",
-                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "note": "lower bound: the elementwise stepping kernels are inside the timed region"},
-        }))
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

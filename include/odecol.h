@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ODECOL_ABI_VERSION 2
+#define ODECOL_ABI_VERSION 3
 
 enum {
     ODECOL_OK = 0,
@@ -102,6 +102,16 @@ typedef struct odecol_problem {
     const float* sigma_scale; /* [B] per-trial factor on sigma, or NULL (1): the noise-amplitude axis of a
                                  parameter sweep (each trial integrates with g = sigma_scale[b] * sigma);
                                  read by the stochastic entry points only (ABI v2)                   */
+    const float* lat_gain;    /* [B] per-trial gain g_b on the dense recurrent input, or NULL (ABI v3): the "global
+                                 lateral gain" axis of a parameter sweep (BASELINE.json configs[4]).  With it the
+                                 input current of trial b is
+                                     I_b = g_b * (W r_b) + W_local (*) r_b + U s_b(t) + bias
+                                 where W = W_aug[:, :N] then holds the between-column (lateral) weights only and
+                                 the within-column weights move to W_local.  g_b must be > 0.  Honoured by
+                                 odecol_em_fwd (staged family) and odecol_drift_staged; every other entry point
+                                 returns ODECOL_E_UNSUPPORTED when it is set                          */
+    const float* W_local;     /* [N][8] within-column weights (row i, source population 8*(i/8) + j), or NULL;
+                                 read only together with lat_gain                                     */
 } odecol_problem;
 
 int odecol_abi_version(void);

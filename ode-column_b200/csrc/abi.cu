@@ -18,7 +18,7 @@ static int to_dev(const odecol_problem* p, DevProblem& d) {
     if (p->ld_w < p->N + p->n_in + 1 || (p->ld_w & 3)) return ODECOL_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(p->W_aug) & 15) || (reinterpret_cast<uintptr_t>(p->kappa) & 15)) return ODECOL_E_ALIGN;
     d.N = p->N; d.n_in = p->n_in; d.B = p->B; d.K = p->K; d.ld_w = p->ld_w;
-    d.W_aug = p->W_aug; d.kappa = p->kappa; d.sigma = p->sigma; d.sigma_scale = p->sigma_scale; d.knot_t = p->knot_t; d.knot_u = p->knot_u;
+    d.W_aug = p->W_aug; d.kappa = p->kappa; d.sigma = p->sigma; d.sigma_scale = p->sigma_scale; d.lat_gain = p->lat_gain; d.W_local = p->lat_gain ? p->W_local : nullptr; d.knot_t = p->knot_t; d.knot_u = p->knot_u;
     d.knot_stride_b = p->knot_stride_b;
     d.c.tau_s = p->tau_s; d.c.tau_m = p->tau_m; d.c.tau_a = p->tau_a; d.c.R = p->resistance;
     return ODECOL_OK;
@@ -98,6 +98,7 @@ int odecol_rhs(const odecol_problem* p, const float* t, const float* y, float* f
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y || !f) return ODECOL_E_NULL;
     g_launches.store(0, std::memory_order_relaxed);
     return launch_rhs_generic(d, t, y, f, static_cast<cudaStream_t>(stream));
@@ -119,6 +120,7 @@ int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const flo
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || out_every < 1) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
@@ -135,6 +137,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y_traj || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
@@ -158,6 +161,7 @@ int odecol_rk4_fwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y0 || !y_sel || !ckpt) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
     if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
@@ -173,6 +177,7 @@ int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !ckpt || !grad_y_sel || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
     if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
@@ -189,6 +194,7 @@ int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const 
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y0 || !y_out) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
@@ -210,6 +216,7 @@ int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T,
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y0 || !y_out || !n_accept || !rec_y || !rec_t0 || !rec_dt || !out_step || !out_x) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || cap < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
@@ -227,6 +234,7 @@ int odecol_dopri5_bwd(const odecol_problem* p, int32_t T, const float* rec_y, co
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!rec_y || !rec_t0 || !rec_dt || !out_step || !out_x || !n_accept || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || cap < 1 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
     if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
@@ -269,6 +277,7 @@ int odecol_em_fwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_small(p, d)) {
+        if (d.lat_gain) return ODECOL_E_UNSUPPORTED;     // set ODECOL_FLAG_FORCE_STAGED to sweep the gain on a small network
         // attempts are bounded: a step at dt_min is always accepted
         const long long cap = adaptive ? (1LL << 34) : (1LL << 40);
         return launch_em_fwd_small(d, ts, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min,
@@ -285,6 +294,7 @@ int odecol_em_bwd(const odecol_problem* p, const float* ts, int32_t T, const flo
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;
     if (!use_small(p, d)) {                              // staged reverse sweep (tensor-core VJPs)
@@ -313,6 +323,7 @@ int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const fl
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
     if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
     if (T < 2 || !(dt > 0.f)) return ODECOL_E_SHAPE;
@@ -333,6 +344,7 @@ int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const fl
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!ts || !y_steps || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if ((dW == nullptr) != (dU == nullptr)) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N || n_steps < 1 || !(dt > 0.f)) return ODECOL_E_SHAPE;

@@ -18,6 +18,8 @@ struct DevProblem {
     const float* kappa;
     const float* sigma;
     const float* sigma_scale;   // [B] or NULL
+    const float* lat_gain;      // [B] or NULL: per-trial gain on the dense recurrent input (staged Euler-Maruyama only)
+    const float* W_local;       // [N][8] or NULL: within-column weights applied outside the contraction (with lat_gain)
     const float* knot_t;
     const float* knot_u;
     long long knot_stride_b;

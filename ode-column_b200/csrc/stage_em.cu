@@ -26,6 +26,7 @@ struct RhsEpi {
     float* f;              // (B, 3N)
     int KPa;
     float inv_tm, inv_ta, inv_ts;
+    const float* loc;      // (B, N) within-column input W_local (*) r, or NULL (lateral-gain sweeps: DevProblem::lat_gain)
     ODECOL_DEVINL void prepare() {}
     ODECOL_DEVINL void rows(int, int i, int n0, int, int g, int TNq, const float (&tot)[kMaxQ]) const {
         if (i >= p.N) return;
@@ -37,7 +38,10 @@ struct RhsEpi {
             if (j >= TNq || b >= p.B) break;
             const float* yb = y + (size_t)b * 3 * N + i;
             const float r = Rhi[(size_t)b * KPa + i] + Rlo[(size_t)b * KPa + i];
-            const float total = tot[j] * p.c.tau_s;
+            // lateral-gain sweep: the contraction holds g_b-scaled lateral input (its stimulus / bias columns were divided
+            // by g_b in the operand), the within-column input comes from the operand kernel
+            const float cur = loc ? fmaf(__ldg(p.lat_gain + b), tot[j], loc[(size_t)b * N + i]) : tot[j];
+            const float total = cur * p.c.tau_s;
             float* fb = f + (size_t)b * 3 * N + i;
             fb[0] = (total * p.c.R - yb[0]) * inv_tm;
             fb[N] = (kap * r - yb[N]) * inv_ta;
@@ -51,9 +55,12 @@ struct RhsEpi {
 // operand r_aug(t_b, y_b) split hi/lo; one CTA per trial, per-trial time (NULL -> shared time *t_shared)
 __global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
                              float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa,
-                             const int* __restrict__ active = nullptr) {
+                             const int* __restrict__ active = nullptr, float* __restrict__ loc = nullptr) {
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
     if (active && !active[b]) return;          // adaptive sweeps: a finished trial's drift is never read again
+    // lateral-gain sweep (loc != NULL): the stimulus and bias columns carry 1 / g_b, so that g_b * (W_aug . r_aug) scales the
+    // recurrent input only
+    const float ginv = loc ? __fdiv_rn(1.0f, __ldg(p.lat_gain + b)) : 1.0f;
     const size_t ro = (size_t)b * KPa;
     const float* yb = y + (size_t)b * 3 * N;
     const float tq = t_trial ? t_trial[b] : t_shared;
@@ -82,11 +89,25 @@ __global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const fl
     for (int k = k_scalar0 + threadIdx.x; k < Kaug; k += blockDim.x) {
         float v;
         if (k < N) v = phi_fast(yb[k] - yb[N + k]);
-        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N);
-        else v = 1.0f;
+        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N) * ginv;
+        else v = ginv;
         const float h = tf32_rna(v);
         hi[ro + k] = h;
         lo[ro + k] = tf32_rna(v - h);
+    }
+    if (loc) {
+        // within-column input of every population from the rates this CTA has just written (r = hi + lo, as RhsEpi reads it)
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int c0 = i & ~7;
+            float acc = 0.f;
+            if (p.W_local) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < N) acc = fmaf(__ldg(p.W_local + (size_t)i * 8 + j), hi[ro + c0 + j] + lo[ro + c0 + j], acc);
+            }
+            loc[(size_t)b * N + i] = acc;
+        }
     }
 }
 
@@ -355,7 +376,7 @@ __global__ void k_em_fill_nan(DevProblem p, const int* __restrict__ status, cons
 
 struct EmLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev, off_state, total;
+    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev, off_state, off_loc, total;
 };
 
 static EmLayout em_layout(const DevProblem& p) {
@@ -372,6 +393,7 @@ static EmLayout em_layout(const DevProblem& p) {
     L.off_f = take(st); L.off_fm = take(st); L.off_yfull = take(st); L.off_ymid = take(st); L.off_yhalf = take(st);
     L.off_y = take(st); L.off_yprev = take(st);
     L.off_state = take(128ull * p.B + 1024);
+    L.off_loc = take(p.lat_gain ? 4ull * p.B * p.N : 0);       // within-column input plane of the lateral-gain sweep
     L.total = o;
     return L;
 }
@@ -392,6 +414,7 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     float *Whi = F(L.off_Whi), *Wlo = F(L.off_Wlo), *Rhi = F(L.off_Rhi), *Rlo = F(L.off_Rlo);
     float *f0 = F(L.off_f), *fm = F(L.off_fm), *yfull = F(L.off_yfull), *ymid = F(L.off_ymid), *yhalf = F(L.off_yhalf);
     float *y = F(L.off_y), *yprev = F(L.off_yprev);
+    float* loc = p.lat_gain ? F(L.off_loc) : nullptr;
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
 
@@ -414,7 +437,7 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
         return ODECOL_E_CUDA;
     auto rhs = [&](const float* ysrc, float* fdst) {
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = loc;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
         if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi, mRhLo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
@@ -436,7 +459,7 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
             const float next_t = nx < t_end ? nx : t_end;
             int j_hi = j;
             while (j_hi < T && ts[j_hi] <= next_t) ++j_hi;            // outputs the loop emits once curr_t >= ts[j]
-            k_em_operand<<<p.B, 128, 0, s>>>(p, y, nullptr, c0, Rhi, Rlo, L.KPa);
+            k_em_operand<<<p.B, 128, 0, s>>>(p, y, nullptr, c0, Rhi, Rlo, L.KPa, nullptr, loc);
             count_launch();
             const int rc = rhs(y, f0);
             if (rc != ODECOL_OK) return rc;
@@ -487,20 +510,20 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     const long long max_attempts = (long long)(4.0 * span / dt_min) + 4LL * T + 1024;
     const int tb = (p.B + 127) / 128;
     k_ad_init<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt, seed, trial_offset);
-    k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa);
+    k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, nullptr, loc);
     count_launch(2);
     int h_active = p.B;
     for (long long round = 0; round < max_attempts && h_active > 0; ++round) {
         int rc = rhs(y, f0);
         if (rc != ODECOL_OK) return rc;
         k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa, S.active);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa, S.active, loc);
         rc = rhs(ymid, fm);
         if (rc != ODECOL_OK) return rc;
         k_ad_half2<<<p.B, 256, 0, s>>>(p, S, ymid, fm, yfull, yhalf, rtol, atol);
         k_ad_control<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt_min, seed, trial_offset, max_attempts);
         k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, S.active);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, S.active, loc);
         count_launch(6);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
@@ -529,7 +552,8 @@ int stage_drift(const DevProblem& p, const float* t_trial, const float* y, float
     const int Kaug = p.N + p.n_in + 1;
     if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    k_em_operand<<<p.B, 128, 0, s>>>(p, y, t_trial, 0.f, Rhi, Rlo, L.KPa);
+    float* loc = p.lat_gain ? F(L.off_loc) : nullptr;
+    k_em_operand<<<p.B, 128, 0, s>>>(p, y, t_trial, 0.f, Rhi, Rlo, L.KPa, nullptr, loc);
     count_launch(2);
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
     if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
@@ -537,7 +561,7 @@ int stage_drift(const DevProblem& p, const float* t_trial, const float* y, float
         return ODECOL_E_CUDA;
     const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
     RhsEpi e;
-    e.p = p; e.y = y; e.Rhi = Rhi; e.Rlo = Rlo; e.f = f; e.KPa = L.KPa;
+    e.p = p; e.y = y; e.Rhi = Rhi; e.Rlo = Rlo; e.f = f; e.KPa = L.KPa; e.loc = loc;
     e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
     return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
 }
@@ -799,7 +823,7 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
         k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, t_trial, t_shared, Rhi, Rlo, L.KPa);
         count_launch();
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
@@ -947,7 +971,7 @@ int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* 
         k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, nullptr, tq, Rhi, Rlo, L.KPa);
         count_launch();
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
@@ -1169,7 +1193,7 @@ struct AdjCtx {
         k_em_operand<<<p.B, 128, 0, s>>>(p, Y, nullptr, tq, F(L.off_Rhi), F(L.off_Rlo), L.KPa);
         count_launch();
         RhsEpi e;
-        e.p = p; e.y = Y; e.Rhi = F(L.off_Rhi); e.Rlo = F(L.off_Rlo); e.f = f; e.KPa = L.KPa;
+        e.p = p; e.y = Y; e.Rhi = F(L.off_Rhi); e.Rlo = F(L.off_Rlo); e.f = f; e.KPa = L.KPa; e.loc = nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsF, e, s);
     }

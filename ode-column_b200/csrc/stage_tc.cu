@@ -169,13 +169,17 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
                         : launch_contract(mWhi, mWlo, mRhi[cur], mRlo[cur], ts, e, s);
     };
 
-    // diagnostics only (ODECOL_TIMELINE=1): per-CTA globaltimer stamps of the eight launches of steps 2 and 3
+    // diagnostics (compiled in with -DODECOL_DIAG only; the shipped library never allocates, synchronises or skips work):
+    // ODECOL_TIMELINE=1 per-CTA globaltimer stamps of the eight launches of steps 2 and 3, ODECOL_DBG_SKIP partial epilogues
     unsigned long long* tl_buf = nullptr;
+    int dbg_skip = 0;
+#ifdef ODECOL_DIAG
     if (getenv("ODECOL_TIMELINE") && T > 5) {
         cudaMalloc(&tl_buf, sizeof(unsigned long long) * 8 * 148 * 8);
         cudaMemsetAsync(tl_buf, 0, sizeof(unsigned long long) * 8 * 148 * 8, s);
     }
-    const int dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
+    dbg_skip = getenv("ODECOL_DBG_SKIP") ? atoi(getenv("ODECOL_DBG_SKIP")) : 0;
+#endif
     for (int n = 0; n < T - 1; ++n) {
         const int j = n + 1;
         const bool emit = (j % out_every == 0) || (j == T - 1);
@@ -204,6 +208,7 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
             cur ^= 1;
         }
     }
+#ifdef ODECOL_DIAG
     if (tl_buf) {
         cudaStreamSynchronize(s);
         static unsigned long long h[8 * 8 * 148];
@@ -239,6 +244,7 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
                     e_min - origin, e_max - origin, end_mean / cnt, seg[0] / cnt, seg[1] / cnt, seg[2] / cnt, seg[3] / cnt, seg[4] / cnt, seg[5] / cnt);
         }
     }
+#endif
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 

@@ -599,7 +599,11 @@ static int launch_contract(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
     }
     const int tiles = ts.MT * ts.NT;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    static const int nochunk = getenv("ODECOL_NOCHUNK") ? atoi(getenv("ODECOL_NOCHUNK")) : 0;    // diagnostics
+#ifdef ODECOL_DIAG
+    static const int nochunk = getenv("ODECOL_NOCHUNK") ? atoi(getenv("ODECOL_NOCHUNK")) : 0;    // accuracy comparison only
+#else
+    constexpr int nochunk = 0;
+#endif
     if (ts.KB > kChunkMin && !nochunk) k_tc_contract<Epi, true><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
     else k_tc_contract<Epi, false><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
     count_launch();

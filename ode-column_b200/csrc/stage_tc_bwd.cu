@@ -1111,7 +1111,10 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     if (rows < DW_BK) rows = DW_BK;
     ds.rows_per_split = rows; ds.Z = (ds.total_rows + rows - 1) / rows;
     ds.N = p.N; ds.Kaug = Kaug; ds.ld_w = p.ld_w; ds.grad_W = grad_W;
-    { const char* e2 = getenv("ODECOL_DW_2X"); ds.two_products = e2 ? (atoi(e2) != 0) : 0; }
+    ds.two_products = 0;
+#ifdef ODECOL_DIAG
+    { const char* e2 = getenv("ODECOL_DW_2X"); ds.two_products = e2 ? (atoi(e2) != 0) : 0; }    // fails the gradient bar: experiment only
+#endif
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
 
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
@@ -1198,7 +1201,12 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         }
         // reverse stages 4, 3, 2, 1 (stage 1 writes kbar_4 of the next step into the OTHER operand set), then dW
         const int set = n & 1;
-        if (use_chain && (getenv("ODECOL_DBG_BWD_SKIP") ? (atoi(getenv("ODECOL_DBG_BWD_SKIP")) & 2) : 0)) {
+#ifdef ODECOL_DIAG
+        static const int dbg_skip = getenv("ODECOL_DBG_BWD_SKIP") ? atoi(getenv("ODECOL_DBG_BWD_SKIP")) : 0;   // timing diagnostics only
+#else
+        constexpr int dbg_skip = 0;
+#endif
+        if (use_chain && (dbg_skip & 2)) {
             // diagnostics: chain skipped
         } else if (use_chain) {
             BwdChainArgs a;
@@ -1235,7 +1243,6 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             replay(n - 1, side);
             cudaEventRecord(ev_replay, side);
         }
-        static const int dbg_skip = getenv("ODECOL_DBG_BWD_SKIP") ? atoi(getenv("ODECOL_DBG_BWD_SKIP")) : 0;   // timing diagnostics only
         if (!(use_chain && fuse_dw) && !(dbg_skip & 1)) {
             const int rcd = launch_dw(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds, s);
             if (rcd) return rcd;

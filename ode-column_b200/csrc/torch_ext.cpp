@@ -25,7 +25,7 @@ void want(const torch::Tensor& t, const char* name, c10::ScalarType dt = torch::
 }
 
 struct Problem {
-    torch::Tensor W_aug, kappa, sigma, knot_t, knot_u, sigma_scale;
+    torch::Tensor W_aug, kappa, sigma, knot_t, knot_u, sigma_scale, lat_gain, W_local;
     bool has_sigma = false;
     odecol_problem p{};
 
@@ -62,6 +62,22 @@ struct Problem {
         TORCH_CHECK(sc->numel() == p.B, "odecol: sigma_scale must have B entries");
         sigma_scale = *sc;
         p.sigma_scale = sigma_scale.data_ptr<float>();
+    }
+
+    // per-trial gain on the dense recurrent input + the within-column weights that stay outside it (include/odecol.h)
+    void set_lateral_gain(std::optional<torch::Tensor> gain, std::optional<torch::Tensor> w_local) {
+        if (!gain.has_value()) { lat_gain = torch::Tensor(); W_local = torch::Tensor(); p.lat_gain = nullptr; p.W_local = nullptr; return; }
+        want(*gain, "lateral_gain");
+        TORCH_CHECK(gain->numel() == p.B, "odecol: lateral_gain must have B entries");
+        lat_gain = *gain;
+        p.lat_gain = lat_gain.data_ptr<float>();
+        p.W_local = nullptr;
+        if (w_local.has_value()) {
+            want(*w_local, "W_local");
+            TORCH_CHECK(w_local->dim() == 2 && w_local->size(0) == p.N && w_local->size(1) == 8, "odecol: W_local must be (N, 8)");
+            W_local = *w_local;
+            p.W_local = W_local.data_ptr<float>();
+        }
     }
 
     torch::TensorOptions fopts() const { return W_aug.options(); }
@@ -461,6 +477,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
              py::arg("W_aug"), py::arg("kappa"), py::arg("sigma"), py::arg("knot_t"), py::arg("knot_u"), py::arg("n_in"),
              py::arg("B"), py::arg("tau_s"), py::arg("tau_m"), py::arg("tau_a"), py::arg("resistance"), py::arg("flags") = 0)
         .def("set_sigma_scale", &Problem::set_sigma_scale)
+        .def("set_lateral_gain", &Problem::set_lateral_gain)
         .def_property_readonly("N", &Problem::N)
         .def_property_readonly("B", &Problem::B)
         .def("kernel_family", [](const Problem& pr, int op) { return odecol_kernel_family(&pr.p, op); })

@@ -65,6 +65,28 @@ class _Setup:
         self.kappa = self.lf.kappa.detach().to(dev, torch.float32).contiguous()
         self.sigma = self.lf.sigma.detach().to(dev, torch.float32).contiguous()
         self.sigma_scale = None       # (B,) per-trial factor on sigma, set by sdeint(options={'sigma_scale': ...})
+        self.lateral_gain = None      # (B,) per-trial gain on the between-column recurrent input (sweeps), with
+        self.W_local = None           # (N, 8) the within-column weights that stay unscaled
+
+    def set_lateral_gain(self, func, gain):
+        """Per-trial global lateral gain (the third axis of BASELINE.json configs[4]'s sweep): trial b integrates the network
+        whose between-column weights are gain[b] times the module's.  The module says which weights those are."""
+        if not hasattr(func, "lateral_split"):
+            raise TypeError(f"odecol: options['lateral_gain'] needs a network with lateral_split(); {type(func).__name__} has none")
+        g = torch.as_tensor(gain, dtype=torch.float32).to(self.kappa.device).reshape(-1).contiguous()
+        if g.numel() != self.B:
+            raise ValueError(f"odecol: options['lateral_gain'] needs {self.B} entries (one per trial), got {g.numel()}")
+        if not bool((g > 0).all()):
+            raise ValueError("odecol: options['lateral_gain'] must be positive")
+        W_lat, W_loc = func.lateral_split()
+        lf = self.lf
+        n = lf.N
+        W_aug = torch.cat((W_lat.detach().to(torch.float32), lf.W_aug.detach()[:, n:]), dim=1).contiguous()
+        self.lf = type(lf)(W_aug=W_aug, kappa=lf.kappa, sigma=lf.sigma, n_in=lf.n_in, tau_s=lf.tau_s, tau_m=lf.tau_m,
+                           tau_a=lf.tau_a, resistance=lf.resistance)
+        self.lateral_gain, self.W_local = g, W_loc.detach().to(torch.float32).contiguous()
+        if not (self.flags & (self.ext.FLAG_FORCE_STAGED | self.ext.FLAG_FORCE_TENSOR)):
+            self.flags |= self.ext.FLAG_FORCE_STAGED      # the gain lives in the staged Euler-Maruyama kernels
 
     def problem(self, W_aug: torch.Tensor):
         lf = self.lf
@@ -72,6 +94,8 @@ class _Setup:
                                 self.knot_u, lf.n_in, self.B, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, self.flags)
         if self.sigma_scale is not None:
             prob.set_sigma_scale(self.sigma_scale)
+        if self.lateral_gain is not None:
+            prob.set_lateral_gain(self.lateral_gain, self.W_local)
         return prob
 
 
@@ -284,7 +308,9 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` (Euler only) uses step
     doubling with torchsde's controller, per trial, on a virtual Brownian tree (Philox only).
     ``options['sigma_scale']``: (B,) per-trial factor on the diffusion -- the noise-amplitude axis of a parameter sweep
-    (trial b integrates with g = sigma_scale[b] * diffusion); ``options['family']`` as in ``odeint``."""
+    (trial b integrates with g = sigma_scale[b] * diffusion); ``options['lateral_gain']``: (B,) positive per-trial gain on
+    the between-column recurrent weights (networks with ``lateral_split()``, e.g. ``SyntheticColumnSheet``; Euler-Maruyama,
+    under ``torch.no_grad()``) -- the lateral-gain axis of the same sweep; ``options['family']`` as in ``odeint``."""
     if logqp or extra or extra_solver_state is not None:
         raise NotImplementedError("odecol: logqp / extra solver state are not part of the fused path")
     method = method or "srk"
@@ -297,7 +323,14 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
         raise ValueError("odecol: only scalar-noise Ito SDEs (what the reference declares) are supported")
     options = dict(options or {})
     sigma_scale = options.pop("sigma_scale", None)
+    lateral_gain = options.pop("lateral_gain", None)
     setup = _Setup(sde, y0, ts, options.pop("family", None))
+    if lateral_gain is not None:
+        if method != "euler":
+            raise NotImplementedError("odecol: options['lateral_gain'] is fused for method='euler' (fixed step and adaptive)")
+        if torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad):
+            raise NotImplementedError("odecol: options['lateral_gain'] is a forward (sweep) feature; wrap the call in torch.no_grad()")
+        setup.set_lateral_gain(sde, lateral_gain)
     if sigma_scale is not None:
         sc = torch.as_tensor(sigma_scale, dtype=torch.float32).to(y0.device).reshape(-1).contiguous()
         if sc.numel() != setup.B:

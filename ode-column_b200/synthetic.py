@@ -1,7 +1,8 @@
 """Synthetic large networks of BASELINE.json configs 4 and 5: ``num_columns`` copies of the
 full-size ``mt`` column on the block diagonal plus dense lateral inhibition between all column pairs at the TOML's
-lateral-mask positions; one stimulus channel per column into L4e/L4i.  Built directly on the device (no O(N^2) Python
-loops, reference src/coupled_columns.py:125-140 would need them), with W, U, bias as trainable parameters."""
+lateral-mask positions; one stimulus channel per column into L4e/L4i.  Assembled with vectorised ``kron`` products on
+the host (no O(N^2) Python loops, reference src/coupled_columns.py:125-140 would need them) and moved to ``device``,
+with W and U as trainable parameters."""
 from __future__ import annotations
 
 import torch
@@ -41,6 +42,18 @@ class SyntheticColumnSheet(_LinearFormNetwork):
 
     def _channels(self, stim):
         return stim if stim.dim() == 3 else stim.unsqueeze(0)
+
+    def lateral_split(self):
+        """(W_lateral (N, N), W_local (N, 8)): the between-column part of the recurrent weights (what a sweep's global
+        lateral gain multiplies, BASELINE.json configs[4]) and the within-column 8 x 8 blocks, row by row."""
+        W = self.recurrent_weights
+        c = self.num_columns
+        blocks = W.reshape(c, POPS, c, POPS)
+        idx = torch.arange(c, device=W.device)
+        local = blocks[idx, :, idx, :].reshape(c * POPS, POPS)            # row i -> its own column's 8 sources
+        eye = torch.eye(c, device=W.device, dtype=W.dtype)
+        off = (1 - eye)[:, None, :, None].expand(c, POPS, c, POPS).reshape(c * POPS, c * POPS)
+        return W * off, local
 
     def set_knots(self, knot_t: torch.Tensor, knot_u: torch.Tensor):
         """Stimulus given directly as knots: time_vec = knot_t (K,), stim = knot_u (B, K, n_in)."""

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.odecol_abi_version() == 2
+    assert lib.odecol_abi_version() == 3
     lib.odecol_strerror.restype = ctypes.c_char_p
     assert lib.odecol_strerror(0) == b"ok"
     assert b"workspace" in lib.odecol_strerror(-4)
@@ -61,7 +61,7 @@ def test_em_num_steps_matches_oracle_schedule(lib):
 def test_torch_extension_imports_without_gpu():
     import odecol
     e = odecol._native.ext()
-    assert e.abi_version() == 2
+    assert e.abi_version() == 3
     with pytest.raises(RuntimeError):
         # CPU tensors are refused: there is no CPU path
         e.Problem(torch.zeros(8, 12), torch.zeros(8), None, torch.zeros(2), torch.zeros(1, 2, 1), 1, 1, 5e-4, 0.02, 10.0, 80.0, 0)
@@ -77,20 +77,20 @@ class _Problem(ctypes.Structure):
                 ("kappa", ctypes.c_void_p), ("sigma", ctypes.c_void_p), ("knot_t", ctypes.c_void_p),
                 ("knot_u", ctypes.c_void_p), ("knot_stride_b", ctypes.c_int64), ("tau_s", ctypes.c_float),
                 ("tau_m", ctypes.c_float), ("tau_a", ctypes.c_float), ("resistance", ctypes.c_float),
-                ("sigma_scale", ctypes.c_void_p)]
+                ("sigma_scale", ctypes.c_void_p), ("lat_gain", ctypes.c_void_p), ("W_local", ctypes.c_void_p)]
 
 
 def _problem(**kw):
     fake = 0x7F0000001000                      # never dereferenced on the host; 16-byte aligned
     base = dict(N=16, n_in=16, B=4, K=6, ld_w=36, flags=0, W_aug=fake, kappa=fake, sigma=None, knot_t=fake, knot_u=fake,
-                knot_stride_b=96, tau_s=5e-4, tau_m=0.02, tau_a=10.0, resistance=80.0, sigma_scale=None)
+                knot_stride_b=96, tau_s=5e-4, tau_m=0.02, tau_a=10.0, resistance=80.0, sigma_scale=None, lat_gain=None, W_local=None)
     base.update(kw)
     return _Problem(**base)
 
 
 def test_struct_layout_matches_the_header(lib):
-    # 6 int32, 5 pointers, int64, 4 floats, 1 pointer (ABI v2) -- what a cgo / ctypes binding sees
-    assert ctypes.sizeof(_Problem) == 6 * 4 + 5 * 8 + 8 + 4 * 4 + 8
+    # 6 int32, 5 pointers, int64, 4 floats, 1 pointer (ABI v2), 2 pointers (ABI v3) -- what a cgo / ctypes binding sees
+    assert ctypes.sizeof(_Problem) == 6 * 4 + 5 * 8 + 8 + 4 * 4 + 8 + 2 * 8
     hdr = open(os.path.join(ROOT, "include", "odecol.h")).read()
     body = hdr[hdr.index("typedef struct odecol_problem {"):hdr.index("} odecol_problem;")]
     names = re.findall(r"\b(?:int32_t|int64_t|float|const float\*)\s+([a-z_A-Z, ]+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
@@ -116,6 +116,7 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert call(_problem(), T=1) == E_SHAPE                    # a single grid point is not a solve
     assert call(_problem(), every=0) == E_SHAPE
     assert call(_problem(), y0=None) == E_NULL
+    assert call(_problem(lat_gain=0x7F0000003000)) == E_UNSUPPORTED   # the lateral-gain axis exists in the staged EM path only
     # srk: increments come as a (W, U) pair or not at all; only the on-chip family implements it
     srk = lib.odecol_srk_fwd
     srk.restype = ctypes.c_int

@@ -197,7 +197,18 @@ def _adaptive_case(kind, cfg, golden):
 @pytest.mark.parametrize("noise", [False, True], ids=["deterministic", "same_brownian_path"])
 @pytest.mark.parametrize("kind", ["xor", "sheet256"])
 def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg, golden):
+    """What can and cannot agree: both solvers run torchsde's controller in float32 state arithmetic, so wherever an error
+    ratio lands within rounding of 1 (or of a clipping bound of the step factor) the accept / reject decision may differ,
+    after which the two take different -- equally valid -- step sequences whose results differ at the level of the
+    solve's own discretisation error, not of float32 rounding.  Hence:
+      * the early window (dozens of controlled steps, before any borderline decision) must agree to rounding level;
+      * accepted / rejected counts per trial: +-3 without noise, 3 % with noise (the Brownian increments make the error
+        estimate rough, borderline decisions are frequent);
+      * whole-solve outputs within 5e-4, and without noise the product must be as close to a converged float64 solution
+        as the oracle is."""
     net, lf, kt, ku, ts, y0, B, options = _adaptive_case(kind, cfg, golden)
+    ts = torch.linspace(0.0, float(ts[-1]), 61 if kind == "xor" else 13)
+    early = 6 if kind == "xor" else 3                            # outputs inside the first 5 ms (xor) / 1 ms (sheet)
     rtol, atol, dt, dt_min = 1e-5, 1e-4, 1e-3, 1e-5
     seed, trial_offset = 77, 5
     sc = torch.tensor([0.0] * B) if not noise else torch.tensor([0.05, 0.1, 0.2, 0.15][:B])
@@ -209,16 +220,32 @@ def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg,
                            dt_min=dt_min, seed=seed, trial_offset=trial_offset, stats=st,
                            options=dict(options, sigma_scale=sc))
     torch.cuda.synchronize()
+    yp = yp.cpu()
     na, nr = st["n_accept"].cpu().numpy(), st["n_reject"].cpu().numpy()
     assert int(st["status"].abs().sum()) == 0
     N = y0.shape[1] // 3
-    eV = _relmax(yp.cpu()[..., :N], yo[..., :N]); eA = _relmax(yp.cpu()[..., N:2 * N], yo[..., N:2 * N])
-    eF = _relmax(yp.cpu()[..., 2 * N:], yo[..., 2 * N:])
+    blk = lambda a, c: a[..., c * N:(c + 1) * N]
+    errs = [_relmax(blk(yp, c), blk(yo, c)) for c in range(3)]
+    errs_early = [_relmax(blk(yp[:early], c), blk(yo[:early], c)) for c in range(3)]
     print(f"\n[adaptive EM {kind} noise={noise}] accepted {na.tolist()} vs oracle {nao.tolist()}; rejected {nr.tolist()} vs "
-          f"{nro.tolist()}; outputs V {eV:.1e} A {eA:.1e} F {eF:.1e}")
-    assert np.all(np.abs(na - nao) <= 2) and np.all(np.abs(nr - nro) <= 2)
-    assert max(eV, eA, eF) < 1e-4
+          f"{nro.tolist()}; outputs V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}; first {early} outputs "
+          f"{errs_early[0]:.1e} {errs_early[1]:.1e} {errs_early[2]:.1e}")
     assert nao.min() > 10                                        # the controller really ran (not parked at one step)
+    assert max(errs_early) < 2e-5
+    if noise:
+        assert np.all(np.abs(na - nao) <= 0.03 * nao + 2) and np.all(np.abs(nr - nro) <= 0.06 * nro + 3)
+        assert max(errs) < 1e-3
+    else:
+        assert np.all(np.abs(na - nao) <= 3) and np.all(np.abs(nr - nro) <= 3)
+        assert max(errs) < 5e-4
+        # converged solution: float64 Euler with a step far below what the controller picks
+        ode64 = orhs.UnifiedColumnODE(lf, kt.numpy(), ku.numpy(), dtype=torch.float64)
+        with torch.no_grad():
+            yt = S.sdeint_euler(ode64, y0.double(), ts.double(), lambda a, b: torch.zeros(B, 1, dtype=torch.float64), dt=2e-6)
+        for c in range(3):
+            ep, eo = _relmax(blk(yp.double(), c), blk(yt, c)), _relmax(blk(yo.double(), c), blk(yt, c))
+            print(f"    block {c}: distance to the converged solution: product {ep:.2e}, oracle {eo:.2e}")
+            assert ep < 1.25 * eo + 2e-5
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -252,3 +279,54 @@ def test_c5_drift_evaluation_matches_the_float64_oracle(cfg):
     print(f"\n[C5 drift N={N} B={B}] dV err / (sum|w||r| scale) {eV:.2e}; dA {eA:.1e}; dF {eF:.1e}; "
           f"dV rel to max|dV| {_relmax(f[:, :N].double(), fo[:, :N]):.1e}")
     assert eV < 4e-6 and eA < 2e-6 and eF < 2e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C5: the per-member global lateral gain (third sweep axis)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_lateral_gain_sweep_axis_matches_per_member_networks(cfg):
+    """options['lateral_gain']: trial b integrates the sheet whose between-column weights are gain[b] times the module's.
+    Oracle: one network per member with W = W_local + gain[b] * W_lateral, Euler-Maruyama on supplied increments."""
+    import dataclasses
+    sheet = odecol.SyntheticColumnSheet(cfg, 32, seed=4, device=DEV, sigma_v=3.0)
+    B, N, T = 5, 256, 17
+    gen = torch.Generator().manual_seed(21)
+    gain = torch.tensor([0.25, 0.5, 1.0, 2.0, 3.5])
+    amp = torch.rand(B, 32, generator=gen) * 25
+    kt, ku = odecol.step_knots(5e-4, 2.5e-3, 4e-3, amp, 1e-4)
+    sheet.set_knots(kt.to(DEV), ku.to(DEV))
+    ts = torch.linspace(0.0, 3.2e-3, T)
+    dt = 2e-4
+    n_steps = len(S.em_step_schedule(ts, dt))
+    W_inc = torch.randn(n_steps, B, 1, generator=gen) * dt ** 0.5
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 4 - 6, torch.rand(B, N, generator=gen) * 0.5, torch.rand(B, N, generator=gen)), 1)
+    lf = sheet_oracle_form(sheet)
+    W_lat, W_loc = (x.detach().cpu() for x in sheet.lateral_split())
+    W_loc_dense = torch.tensor(lf.W) - W_lat
+    assert float((W_loc_dense.reshape(32, 8, 32, 8)[torch.arange(32), :, torch.arange(32), :].reshape(N, 8) - W_loc).abs().max()) == 0
+    ys = []
+    for b in range(B):
+        lfb = dataclasses.replace(lf, W=(W_loc_dense + float(gain[b]) * W_lat).numpy())
+        ode = orhs.UnifiedColumnODE(lfb, kt.numpy(), ku[b:b + 1].numpy())
+        with torch.no_grad():
+            ys.append(S.sdeint_euler(ode, y0[b:b + 1], ts, S.TabulatedBrownian(W_inc[:, b:b + 1]), dt=dt))
+    yo = torch.cat(ys, 1)
+    with torch.no_grad():
+        yp = odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), bm=W_inc[:, :, 0], method="euler", dt=dt,
+                           options={"lateral_gain": gain}).cpu()
+        yp1 = odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), bm=W_inc[:, :, 0], method="euler", dt=dt, options={"family": "staged"}).cpu()
+    errs = [_relmax(yp[..., c * N:(c + 1) * N], yo[..., c * N:(c + 1) * N]) for c in range(3)]
+    print(f"\n[lateral gain sweep, N={N}] V/A/F vs per-member oracle networks {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}; "
+          f"gain 1 member vs the plain solve {_relmax(yp[:, 2], yp1[:, 2]):.1e}; gain 0.25 vs 3.5 differ by {_relmax(yp[:, 0, :N], yp[:, 4, :N]):.2f}")
+    assert max(errs) < 1e-5
+    assert _relmax(yp[:, 2], yp1[:, 2]) < 2e-6            # gain 1 reproduces the unsplit network
+    # adaptive mode takes the gain too, and refuses what it cannot honour
+    st = {}
+    with torch.no_grad():
+        ya = odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", adaptive=True, seed=3, stats=st,
+                           options={"lateral_gain": gain, "sigma_scale": torch.full((B,), 0.1)})
+    assert torch.isfinite(ya).all() and int(st["n_accept"].min()) > 3
+    with pytest.raises(ValueError):
+        odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", options={"lateral_gain": torch.zeros(B)})
+    with pytest.raises(NotImplementedError):
+        odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="srk", options={"lateral_gain": gain})
