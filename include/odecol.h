@@ -73,7 +73,8 @@ enum {
     ODECOL_OP_EM_FWD = 4,
     ODECOL_OP_EM_BWD = 5,
     ODECOL_OP_SRK_FWD = 6,
-    ODECOL_OP_SRK_BWD = 7
+    ODECOL_OP_SRK_BWD = 7,
+    ODECOL_OP_DOPRI5_BWD = 8
 };
 
 /* The column network in linear form plus the stimulus of every trial.
@@ -181,7 +182,9 @@ int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
  * Networks beyond the on-chip family (N > 128, or ODECOL_FLAG_FORCE_STAGED / _TENSOR) run the staged solver: the same
  * per-trial controller, one attempted step of every unfinished trial per round with the six stage evaluations on the
  * tensor cores; it needs odecol_workspace_bytes(p, ODECOL_OP_DOPRI5_FWD, T, 0) and synchronises the stream every 16
- * rounds (like the adaptive Euler-Maruyama).  The record / reverse pair below exists for the on-chip family only. */
+ * rounds (like the adaptive Euler-Maruyama).  The record / reverse pair below exists in both families (staged: the same
+ * workspaces, ODECOL_OP_DOPRI5_FWD / ODECOL_OP_DOPRI5_BWD; the reverse sweep runs in rounds over the accepted steps, from
+ * each trial's last to its first, with the drift evaluations and vector-Jacobian products on the tensor cores). */
 int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const float* y0, float* y_out,
                       float rtol, float atol, int32_t max_steps,
                       int32_t* n_accept, int32_t* n_reject, int32_t* status,

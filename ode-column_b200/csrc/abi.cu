@@ -87,6 +87,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
         case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
+        case ODECOL_OP_DOPRI5_BWD: return small ? 0 : stage_dopri5_bwd_workspace_bytes(d, T);
         case ODECOL_OP_EM_BWD: return small ? em_schedule_layout(T, n_steps).total : stage_sde_bwd_workspace_bytes(d, T);
         case ODECOL_OP_SRK_FWD: return small ? 0 : stage_srk_fwd_workspace_bytes(d, T);
         case ODECOL_OP_SRK_BWD: return small ? em_schedule_layout(T, n_steps).total : stage_sde_bwd_workspace_bytes(d, T);
@@ -200,7 +201,8 @@ int odecol_dopri5_fwd(const odecol_problem* p, const float* t, int32_t T, const 
     g_launches.store(0, std::memory_order_relaxed);
     if (!use_small(p, d)) {                              // beyond the on-chip family (or forced): staged solver, forward only
         if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
-        return stage_dopri5_fwd(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, workspace,
+        const Dopri5Record norec{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+        return stage_dopri5_fwd(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, norec, workspace,
                                 workspace_bytes, static_cast<cudaStream_t>(stream));
     }
     const Dopri5Record none{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
@@ -212,7 +214,6 @@ int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T,
                              float atol, int32_t max_steps, int32_t* n_accept, int32_t* n_reject, int32_t* status,
                              float* rec_y, double* rec_t0, double* rec_dt, int32_t* out_step, float* out_x, int32_t cap,
                              void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
@@ -220,8 +221,12 @@ int odecol_dopri5_fwd_record(const odecol_problem* p, const float* t, int32_t T,
     if (!t || !y0 || !y_out || !n_accept || !rec_y || !rec_t0 || !rec_dt || !out_step || !out_x) return ODECOL_E_NULL;
     if (T < 2 || max_steps < 1 || cap < 1 || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
-    if (!use_small(p, d)) return ODECOL_E_UNSUPPORTED;   // recording (training) exists in the on-chip family only
     const Dopri5Record rec{rec_y, rec_t0, rec_dt, out_step, out_x, cap};
+    if (!use_small(p, d)) {                              // staged solver: the same record, written by its commit kernel
+        if (misaligned(y0) || misaligned(y_out) || misaligned(workspace) || misaligned(rec_y)) return ODECOL_E_ALIGN;
+        return stage_dopri5_fwd(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec, workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
+    }
     return launch_dopri5_fwd_small(d, t, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec,
                                    static_cast<cudaStream_t>(stream));
 }
@@ -230,16 +235,20 @@ int odecol_dopri5_bwd(const odecol_problem* p, int32_t T, const float* rec_y, co
                       const int32_t* out_step, const float* out_x, int32_t cap, const int32_t* n_accept,
                       const float* grad_y, const int32_t* sel, int32_t G, float* grad_y0, float* grad_W_aug,
                       void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     DevProblem d;
     const int rc = to_dev(p, d);
     if (rc) return rc;
     if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!rec_y || !rec_t0 || !rec_dt || !out_step || !out_x || !n_accept || !grad_y || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || cap < 1 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
-    if (small_kp(d) == 0) return ODECOL_E_UNSUPPORTED;
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!use_small(p, d)) {                              // staged reverse sweep in rounds (tensor-core VJPs)
+        if (misaligned(workspace) || misaligned(rec_y)) return ODECOL_E_ALIGN;
+        const Dopri5Record recs{const_cast<float*>(rec_y), const_cast<double*>(rec_t0), const_cast<double*>(rec_dt),
+                                const_cast<int*>(out_step), const_cast<float*>(out_x), cap};
+        return stage_dopri5_bwd(d, T, recs, n_accept, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
+    }
     if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
     const Dopri5Record rec{const_cast<float*>(rec_y), const_cast<double*>(rec_t0), const_cast<double*>(rec_dt),
                            const_cast<int*>(out_step), const_cast<float*>(out_x), cap};

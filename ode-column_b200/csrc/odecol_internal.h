@@ -101,7 +101,12 @@ int stage_drift(const DevProblem& p, const float* t_trial, const float* y, float
 // staged Dormand-Prince 5(4), forward (stage_em.cu): per-trial control in rounds, drift on the tensor cores
 size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int T);
 int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
-                     int max_steps, int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s);
+                     int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec, void* ws,
+                     size_t ws_bytes, cudaStream_t s);
+// staged discrete adjoint over the recorded accepted steps (rounds over the steps from each trial's last to its first)
+size_t stage_dopri5_bwd_workspace_bytes(const DevProblem& p, int T);
+int stage_dopri5_bwd(const DevProblem& p, int T, const Dopri5Record& rec, const int* n_accept, const float* grad_y,
+                     const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // staged torchsde srk (fixed step), forward (stage_em.cu)
 size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int T);

@@ -676,10 +676,12 @@ __global__ void k_dp_stage(DevProblem p, DpState s) {
 }
 
 // error ratio, accept / reject, controller, dense output of every output time inside an accepted step, commit
+// rec.y != NULL (training mode): every accepted step leaves its start state, t0 and dt, and every output the index of the
+// accepted step it lies in with its dense-output abscissa -- what stage_dopri5_bwd differentiates through
 __global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ ts, int T, float rtol, float atol,
-                            int max_steps, float* __restrict__ y_out) {
+                            int max_steps, float* __restrict__ y_out, Dopri5Record rec) {
     __shared__ double sh[8];
-    __shared__ int sh_acc, sh_j0, sh_j1;
+    __shared__ int sh_acc, sh_j0, sh_j1, sh_n;
     const int b = blockIdx.x, n3 = 3 * p.N;
     if (!s.active[b]) return;
     const size_t o = (size_t)b * n3;
@@ -707,10 +709,13 @@ __global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ t
         else if (!(t0 + dt > t0)) st = ODECOL_ST_UNDERFLOW;
         else accept = ratio <= 1.0f;
         int j0 = s.next_out[b], j1 = j0;
+        sh_n = s.n_acc[b];
+        if (st == ODECOL_ST_OK && accept && rec.y && sh_n >= rec.cap) { st = ODECOL_ST_MAXSTEPS; accept = 0; }   // record full
         if (st == ODECOL_ST_OK) {
             if (accept) {
                 while (j1 < T && (double)ts[j1] <= t1) ++j1;      // outputs reached by this step: next_t <= st_t1
                 s.n_acc[b] += 1;
+                if (rec.y) { rec.t0[(size_t)b * rec.cap + sh_n] = t0; rec.dt[(size_t)b * rec.cap + sh_n] = dt; }
             } else {
                 s.n_rej[b] += 1;
             }
@@ -732,6 +737,7 @@ __global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ t
     for (int c = threadIdx.x; c < n3; c += blockDim.x) {
         const size_t e = o + c;
         const float f0 = s.k[0][e], f1 = s.k[6][e], y0c = s.y[e], y1c = s.ys[e];
+        if (rec.y) rec.y[((size_t)sh_n * p.B + b) * n3 + c] = y0c;
         if (j1 > j0) {
             const float ymid = __fadd_rn(y0c, fmaf(s.k[6][e], DP::m6 * dtf, fmaf(s.k[5][e], DP::m5 * dtf, fmaf(s.k[4][e], DP::m4 * dtf,
                                fmaf(s.k[3][e], DP::m3 * dtf, fmaf(s.k[2][e], DP::m2 * dtf, s.k[0][e] * (DP::m0 * dtf)))))));
@@ -741,6 +747,7 @@ __global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ t
             const float cd = dtf * f0;
             for (int j = j0; j < j1; ++j) {
                 const float x = (float)(((double)ts[j] - t0) / (t1 - t0));
+                if (rec.y && c == 0) { rec.out_step[(size_t)b * T + j] = sh_n; rec.out_x[(size_t)b * T + j] = x; }
                 float tot = __fadd_rn(y0c, __fmul_rn(x, cd));
                 float xp = __fmul_rn(x, x);
                 tot = __fadd_rn(tot, __fmul_rn(xp, cc));
@@ -784,7 +791,8 @@ static DpLayout dp_layout(const DevProblem& p) {
 size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int) { return tc::dp_layout(p).total; }
 
 int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
-                     int max_steps, int* n_accept, int* n_reject, int* status, void* ws, size_t ws_bytes, cudaStream_t s) {
+                     int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec, void* ws,
+                     size_t ws_bytes, cudaStream_t s) {
     using namespace tc;
     const DpLayout L = dp_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -846,7 +854,7 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
         k_dp_stage<4><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[4]); if (rc) return rc;
         k_dp_stage<5><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[5]); if (rc) return rc;
         k_dp_stage<6><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[6]); if (rc) return rc;
-        k_dp_finish<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, rtol, atol, max_steps, y_out);
+        k_dp_finish<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, rtol, atol, max_steps, y_out, rec);
         count_launch(7);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
@@ -1058,12 +1066,17 @@ struct VjpEpi {
 };
 
 // operands of one VJP: r_aug(Y, t) -> (Rhi, Rlo) rows of KPa, gamma a_V -> (AVhi, AVlo) rows of NPk, phi' -> D
+// t_trial != NULL: one evaluation time per trial; active != NULL: trials with active[b] == 0 contribute a zero cotangent
+// (their rows of the gamma a_V operand are zero, so they add nothing to grad_W_aug)
 __global__ void k_vjp_prep(DevProblem p, const float* __restrict__ Y, float tq, const float* __restrict__ a, float gamma,
                            float* __restrict__ Rhi, float* __restrict__ Rlo, int KPa, float* __restrict__ AVhi,
-                           float* __restrict__ AVlo, int NPk, float* __restrict__ D) {
+                           float* __restrict__ AVlo, int NPk, float* __restrict__ D,
+                           const float* __restrict__ t_trial = nullptr, const int* __restrict__ active = nullptr) {
     const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
     const float* yb = Y + (size_t)b * 3 * N;
     int idx = 1;
+    if (t_trial) tq = t_trial[b];
+    const bool on = !active || active[b] != 0;
     const float tcl = knot_locate(p.knot_t, p.K, tq, idx);
     const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
     for (int k = threadIdx.x; k < Kaug; k += blockDim.x) {
@@ -1072,7 +1085,7 @@ __global__ void k_vjp_prep(DevProblem p, const float* __restrict__ Y, float tq, 
             float dr;
             phi_dphi_fast(yb[k] - yb[N + k], v, dr);
             D[(size_t)b * N + k] = dr;
-            const float av = gamma * a[(size_t)b * 3 * N + k];
+            const float av = on ? gamma * a[(size_t)b * 3 * N + k] : 0.f;
             const float h = tf32_rna(av);
             AVhi[(size_t)b * NPk + k] = h;
             AVlo[(size_t)b * NPk + k] = tf32_rna(av - h);
@@ -1210,6 +1223,27 @@ struct AdjCtx {
         return tc_dw_accumulate(F(L.off_AVhi), F(L.off_AVlo), F(L.off_Rhi), F(L.off_Rlo), L.Bp32, L.Np, L.KPa, p.N,
                                 p.N + p.n_in + 1, p.ld_w, grad_W, s);
     }
+    // per-trial evaluation times (adaptive solvers): f = drift(Y, t[b]);  b = J(Y, t[b])^T a with inactive trials masked
+    int rhs_t(const float* Y, const float* t_trial, float* f) {
+        k_em_operand<<<p.B, 128, 0, s>>>(p, Y, t_trial, 0.f, F(L.off_Rhi), F(L.off_Rlo), L.KPa);
+        count_launch();
+        RhsEpi e;
+        e.p = p; e.y = Y; e.Rhi = F(L.off_Rhi); e.Rlo = F(L.off_Rlo); e.f = f; e.KPa = L.KPa; e.loc = nullptr;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        return launch_contract(mWhi, mWlo, mRhi, mRlo, tsF, e, s);
+    }
+    int vjp_t(const float* Y, const float* t_trial, const int* active, const float* a, float* b) {
+        k_vjp_prep<<<p.B, 128, 0, s>>>(p, Y, 0.f, a, gamma, F(L.off_Rhi), F(L.off_Rlo), L.KPa, F(L.off_AVhi), F(L.off_AVlo), L.NPk,
+                                       F(L.off_D), t_trial, active);
+        count_launch();
+        VjpEpi e;
+        e.p = p; e.a = a; e.D = F(L.off_D); e.b = b;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        int rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, tsB, e, s);
+        if (rc) return rc;
+        return tc_dw_accumulate(F(L.off_AVhi), F(L.off_AVlo), F(L.off_Rhi), F(L.off_Rlo), L.Bp32, L.Np, L.KPa, p.N,
+                                p.N + p.n_in + 1, p.ld_w, grad_W, s);
+    }
     void lincomb(float* out, float c0, const float* x0, float c1 = 0.f, const float* x1 = nullptr, float c2 = 0.f,
                  const float* x2 = nullptr, float c3 = 0.f, const float* x3 = nullptr) {
         k_lincomb<<<grid(st()), 256, 0, s>>>(st(), out, c0, x0, c1, x1, c2, x2, c3, x3);
@@ -1315,6 +1349,208 @@ int stage_sde_bwd(int which, const DevProblem& p, const float* ts_dev, int T, co
         count_launch();
     }
     if (grad_y0 && cudaMemcpyAsync(grad_y0, lam, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged discrete adjoint of dopri5 for networks beyond the on-chip family: the algebra of k_dopri5_bwd_small (reverse
+// sweep over the ACCEPTED steps the forward pass recorded; per step the seven stages are recomputed, then the adjoint
+// runs through the dense-output quartic, the FSAL row and the tableau) with the drift evaluations and their
+// vector-Jacobian products on the tensor cores.  Trials accept different numbers of steps, so the sweep runs in ROUNDS:
+// in round r trial b handles its accepted step n_accept[b] - 1 - r (finished trials idle, masked out of every update and
+// of grad_W_aug).  What it replaces: loss.backward() through torchdiffeq's unrolled adaptive solver
+// (reference scripts/xor_ode.py:114,177, scripts/parity_ode.py:233,250) for the synthetic large networks.
+// ---------------------------------------------------------------------------------------------------------------
+namespace tc {
+
+struct DpAdj {
+    int* nidx; int* act; int* first; int* jptr;      // (B) step index of this round, n >= 0, n == 0, next output to consume
+    float* dtf;                                      // (B)
+    float* tst[7];                                   // (B) stage times
+    float* Ys[7]; float* k[7]; float* kb[7];         // (B, 3N)
+    float* yb0; float* yb1; float* lam; float* carry; float* bout;
+};
+
+// per trial: which accepted step this round handles, its t0 / dt, its start state
+__global__ void k_dpb_begin(DevProblem p, DpAdj d, DpState s, Dopri5Record rec, const int* __restrict__ n_accept, int round) {
+    const int b = blockIdx.x, n3 = 3 * p.N;
+    const int n = n_accept[b] - 1 - round;
+    if (threadIdx.x == 0) {
+        d.nidx[b] = n; d.act[b] = n >= 0; d.first[b] = n == 0; s.active[b] = n >= 0;
+        if (n >= 0) {
+            const double t0 = rec.t0[(size_t)b * rec.cap + n], dt = rec.dt[(size_t)b * rec.cap + n];
+            s.t[b] = t0; s.dt[b] = dt;
+            d.dtf[b] = (float)dt; d.tst[0][b] = (float)t0;
+        }
+    }
+    if (n < 0) return;
+    const float* src = rec.y + ((size_t)n * p.B + b) * n3;
+    float* dst = d.Ys[0] + (size_t)b * n3;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) dst[c] = src[c];
+}
+
+// adjoint of the dense output for every output inside this step; initial kbar / ybar (k_dopri5_bwd_small, same order)
+__global__ void k_dpb_dense(DevProblem p, DpAdj d, Dopri5Record rec, int T, const float* __restrict__ grad_y,
+                            const int* __restrict__ inv, int G) {
+    const int b = blockIdx.x, n3 = 3 * p.N, B = p.B;
+    if (!d.act[b]) return;
+    const int n = d.nidx[b];
+    const float dtf = d.dtf[b];
+    const int j_hi = d.jptr[b];
+    int j_lo = j_hi;
+    while (j_lo >= 1 && rec.out_step[(size_t)b * T + j_lo] == n) --j_lo;          // outputs (j_lo, j_hi] lie in this step
+    const float cmid[7] = {DP::m0, 0.f, DP::m2, DP::m3, DP::m4, DP::m5, DP::m6};
+    const size_t o = (size_t)b * n3;
+    for (int c = threadIdx.x; c < n3; c += blockDim.x) {
+        const int gi = inv[c];
+        float ca = 0.f, cb = 0.f, cc = 0.f, cd = 0.f, ce = 0.f;
+        if (gi >= 0)
+            for (int j = j_hi; j > j_lo; --j) {
+                const float x = rec.out_x[(size_t)b * T + j];
+                const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+                const float g = grad_y[((size_t)j * B + b) * G + gi];
+                ce += g; cd += x * g; cc += x2 * g; cb += x3 * g; ca += x4 * g;
+            }
+        const float ymidb = 16.f * ca - 32.f * cb + 16.f * cc;
+        d.yb0[o + c] = ce - 8.f * ca + 18.f * cb - 11.f * cc + ymidb;
+        d.yb1[o + c] = d.lam[o + c] - 8.f * ca + 14.f * cb - 5.f * cc;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            float v = dtf * cmid[m] * ymidb;
+            if (m == 0) v += dtf * (-2.f * ca + 5.f * cb - 4.f * cc + cd);                    // f0 = k1
+            if (m == 6) v += dtf * (2.f * ca - 3.f * cb + cc) + d.carry[o + c];               // f1 = k7 (+ the next step's k1)
+            d.kb[m][o + c] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) d.jptr[b] = j_lo;
+}
+
+// Ybar_st = [st == 6] ybar1 + J(Y_st)^T kbar_st (in bout), pushed through tableau row st
+template <int ST>
+__global__ void k_dpb_push(DevProblem p, DpAdj d) {
+    const int n3 = 3 * p.N;
+    const size_t total = (size_t)p.B * n3;
+    const float beta[6][6] = {
+        {DP::b10, 0.f, 0.f, 0.f, 0.f, 0.f}, {DP::b20, DP::b21, 0.f, 0.f, 0.f, 0.f}, {DP::b30, DP::b31, DP::b32, 0.f, 0.f, 0.f},
+        {DP::b40, DP::b41, DP::b42, DP::b43, 0.f, 0.f}, {DP::b50, DP::b51, DP::b52, DP::b53, DP::b54, 0.f},
+        {DP::b60, 0.f, DP::b62, DP::b63, DP::b64, DP::b65}};
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n3);
+        if (!d.act[b]) continue;
+        const float dtf = d.dtf[b];
+        float Yb = d.bout[e];
+        if (ST == 6) Yb += d.yb1[e];
+        d.yb0[e] += Yb;
+#pragma unroll
+        for (int m = 0; m < 6; ++m)
+            if (m < ST) d.kb[m][e] += dtf * beta[ST - 1][m] * Yb;
+    }
+}
+
+// end of the round: hand kbar_1 to the previous step (its k7) or, at a trial's first step, add J(y0)^T kbar_1 (in bout)
+__global__ void k_dpb_end(DevProblem p, DpAdj d, int have_first) {
+    const int n3 = 3 * p.N;
+    const size_t total = (size_t)p.B * n3;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n3);
+        if (!d.act[b]) continue;
+        if (d.first[b]) { d.lam[e] = d.yb0[e] + (have_first ? d.bout[e] : 0.f); d.carry[e] = 0.f; }
+        else { d.lam[e] = d.yb0[e]; d.carry[e] = d.kb[0][e]; }
+    }
+}
+
+__global__ void k_dpb_init(DevProblem p, DpAdj d, int T) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < p.B) d.jptr[b] = T - 1;
+}
+
+struct DpAdjLayout { AdjLayout A; DpLayout D; size_t off_planes, off_small, off_inv, total; };
+static DpAdjLayout dp_adj_layout(const DevProblem& p) {
+    DpAdjLayout L;
+    L.A = adj_layout(p);
+    L.D = dp_layout(p);
+    size_t o = L.A.total;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    const size_t st = 4ull * p.B * 3 * p.N;
+    L.off_planes = take(26 * st);                                     // Ys, k, kb (7 each), yb0, yb1, lam, carry, bout
+    L.off_small = take(256ull * p.B + 4096);
+    L.off_inv = take(4ull * (3 * p.N + 4));
+    L.total = o;
+    return L;
+}
+
+}  // namespace tc
+
+size_t stage_dopri5_bwd_workspace_bytes(const DevProblem& p, int) { return tc::dp_adj_layout(p).total; }
+
+int stage_dopri5_bwd(const DevProblem& p, int T, const Dopri5Record& rec, const int* n_accept, const float* grad_y,
+                     const int* sel, int G, float* grad_y0, float* grad_W, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const DpAdjLayout L = dp_adj_layout(p);
+    if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
+    AdjCtx cx;
+    int rc = cx.init(p, ws, ws_bytes, grad_W, s);
+    if (rc) return rc;
+    char* w = static_cast<char*>(ws);
+    const size_t st = cx.st(), B = p.B;
+    if (cudaMemsetAsync(w + L.off_planes, 0, L.total - L.off_planes, s) != cudaSuccess) return ODECOL_E_CUDA;
+    float* pl = reinterpret_cast<float*>(w + L.off_planes);
+    DpAdj d;
+    for (int i = 0; i < 7; ++i) { d.Ys[i] = pl + (size_t)i * st; d.k[i] = pl + (size_t)(7 + i) * st; d.kb[i] = pl + (size_t)(14 + i) * st; }
+    d.yb0 = pl + 21 * st; d.yb1 = pl + 22 * st; d.lam = pl + 23 * st; d.carry = pl + 24 * st; d.bout = pl + 25 * st;
+    char* sb = w + L.off_small;
+    auto grab = [&](size_t bytes) { char* r = sb; sb += (bytes + 15) / 16 * 16; return r; };
+    d.nidx = reinterpret_cast<int*>(grab(4 * B)); d.act = reinterpret_cast<int*>(grab(4 * B));
+    d.first = reinterpret_cast<int*>(grab(4 * B)); d.jptr = reinterpret_cast<int*>(grab(4 * B));
+    d.dtf = reinterpret_cast<float*>(grab(4 * B));
+    for (int i = 0; i < 7; ++i) d.tst[i] = reinterpret_cast<float*>(grab(4 * B));
+    DpState S;                                        // the forward stage kernels (k_dp_stage) run on this view
+    S.t = reinterpret_cast<double*>(grab(8 * B)); S.dt = reinterpret_cast<double*>(grab(8 * B));
+    S.red = nullptr; S.next_out = S.n_acc = S.n_rej = S.status = nullptr; S.n_active = nullptr;
+    S.active = d.act;
+    for (int i = 0; i < 7; ++i) S.k[i] = d.k[i];
+    S.y = d.Ys[0];
+    int* inv = reinterpret_cast<int*>(w + L.off_inv);
+    k_tc_build_inv<<<1, 256, 0, s>>>(sel, G, 3 * p.N, inv);
+    k_dpb_init<<<(p.B + 127) / 128, 128, 0, s>>>(p, d, T);
+    count_launch(2);
+    // accepted-step counts decide the number of rounds and where first steps fall (one synchronisation, like the forward pass)
+    std::vector<int> nacc(p.B);
+    if (cudaMemcpyAsync(nacc.data(), n_accept, sizeof(int) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+    int rounds = 0;
+    for (int b = 0; b < p.B; ++b) { if (nacc[b] > rec.cap) return ODECOL_E_SHAPE; if (nacc[b] > rounds) rounds = nacc[b]; }
+    std::vector<char> has_first(rounds + 1, 0);
+    for (int b = 0; b < p.B; ++b) if (nacc[b] >= 1) has_first[nacc[b] - 1] = 1;
+    const int eg = cx.grid(st);
+    for (int r = 0; r < rounds; ++r) {
+        k_dpb_begin<<<p.B, 256, 0, s>>>(p, d, S, rec, n_accept, r);
+        count_launch();
+        // ---- recompute the seven stages (stage 0 = the recorded start state at t0)
+        rc = cx.rhs_t(d.Ys[0], d.tst[0], d.k[0]); if (rc) return rc;
+#define ODECOL_DPB_STAGE(ST)                                                        \
+        S.ys = d.Ys[ST]; S.t_stage = d.tst[ST];                                     \
+        k_dp_stage<ST><<<eg, 256, 0, s>>>(p, S); count_launch();                    \
+        rc = cx.rhs_t(d.Ys[ST], d.tst[ST], d.k[ST]); if (rc) return rc;
+        ODECOL_DPB_STAGE(1) ODECOL_DPB_STAGE(2) ODECOL_DPB_STAGE(3) ODECOL_DPB_STAGE(4) ODECOL_DPB_STAGE(5) ODECOL_DPB_STAGE(6)
+#undef ODECOL_DPB_STAGE
+        // ---- dense output adjoint, then stages 7 .. 2
+        k_dpb_dense<<<p.B, 256, 0, s>>>(p, d, rec, T, grad_y, inv, G);
+        count_launch();
+#define ODECOL_DPB_BACK(ST)                                                                            \
+        rc = cx.vjp_t(d.Ys[ST], d.tst[ST], d.act, d.kb[ST], d.bout); if (rc) return rc;               \
+        k_dpb_push<ST><<<eg, 256, 0, s>>>(p, d); count_launch();
+        ODECOL_DPB_BACK(6) ODECOL_DPB_BACK(5) ODECOL_DPB_BACK(4) ODECOL_DPB_BACK(3) ODECOL_DPB_BACK(2) ODECOL_DPB_BACK(1)
+#undef ODECOL_DPB_BACK
+        if (has_first[r]) { rc = cx.vjp_t(d.Ys[0], d.tst[0], d.first, d.kb[0], d.bout); if (rc) return rc; }
+        k_dpb_end<<<eg, 256, 0, s>>>(p, d, has_first[r] ? 1 : 0);
+        count_launch();
+    }
+    // output 0 is y0 itself
+    k_add_out_grad<<<cx.grid((size_t)p.B * G), 256, 0, s>>>(p, grad_y, sel, G, 1.f, 0.f, d.lam, nullptr);
+    count_launch();
+    if (grad_y0 && cudaMemcpyAsync(grad_y0, d.lam, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 

@@ -228,11 +228,13 @@ std::vector<torch::Tensor> dopri5_fwd_record(const Problem& pr, const torch::Ten
     auto rec_dt = torch::zeros({pr.B(), cap}, pr.fopts().dtype(torch::kFloat64));
     auto out_step = torch::zeros({pr.B(), T}, pr.iopts());
     auto out_x = torch::zeros({pr.B(), T}, pr.fopts());
+    auto ws = pr.workspace(ODECOL_OP_DOPRI5_FWD, T);
     check(odecol_dopri5_fwd_record(&pr.p, t.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), (float)rtol,
                                    (float)atol, (int32_t)std::min<int64_t>(max_steps, INT32_MAX), na.data_ptr<int32_t>(),
                                    nr.data_ptr<int32_t>(), st.data_ptr<int32_t>(), rec_y.data_ptr<float>(),
                                    rec_t0.data_ptr<double>(), rec_dt.data_ptr<double>(), out_step.data_ptr<int32_t>(),
-                                   out_x.data_ptr<float>(), (int32_t)cap, nullptr, 0, pr.stream()), "dopri5_fwd_record");
+                                   out_x.data_ptr<float>(), (int32_t)cap, ws.data_ptr(), (size_t)ws.numel(), pr.stream()),
+          "dopri5_fwd_record");
     return {y, na, nr, st, rec_y, rec_t0, rec_dt, out_step, out_x};
 }
 
@@ -256,10 +258,11 @@ std::vector<torch::Tensor> dopri5_bwd(const Problem& pr, int64_t T, const torch:
     }
     auto gy0 = torch::empty({pr.B(), 3 * pr.N()}, pr.fopts());
     auto gW = torch::empty_like(pr.W_aug);
+    auto ws = pr.workspace(ODECOL_OP_DOPRI5_BWD, T);
     check(odecol_dopri5_bwd(&pr.p, (int32_t)T, rec_y.data_ptr<float>(), rec_t0.data_ptr<double>(), rec_dt.data_ptr<double>(),
                             out_step.data_ptr<int32_t>(), out_x.data_ptr<float>(), (int32_t)cap, n_accept.data_ptr<int32_t>(),
-                            grad_y.data_ptr<float>(), selp, (int32_t)G, gy0.data_ptr<float>(), gW.data_ptr<float>(), nullptr, 0,
-                            pr.stream()), "dopri5_bwd");
+                            grad_y.data_ptr<float>(), selp, (int32_t)G, gy0.data_ptr<float>(), gW.data_ptr<float>(), ws.data_ptr(),
+                            (size_t)ws.numel(), pr.stream()), "dopri5_bwd");
     return {gy0, gW};
 }
 
@@ -516,6 +519,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.attr("OP_EM_BWD") = (int)ODECOL_OP_EM_BWD;
     m.attr("OP_SRK_FWD") = (int)ODECOL_OP_SRK_FWD;
     m.attr("OP_SRK_BWD") = (int)ODECOL_OP_SRK_BWD;
+    m.attr("OP_DOPRI5_BWD") = (int)ODECOL_OP_DOPRI5_BWD;
     m.attr("FLAG_FORCE_STAGED") = (int)ODECOL_FLAG_FORCE_STAGED;
     m.attr("FLAG_FORCE_TENSOR") = (int)ODECOL_FLAG_FORCE_TENSOR;
 }

@@ -215,8 +215,8 @@ class _SRKFunction(torch.autograd.Function):
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
            components=None, stats: Optional[Dict] = None):
     """Fused replacement of ``torchdiffeq.odeint``.  ``method``: None/'dopri5' (adaptive, per-trial control, the
-    default the reference scripts get; every network size, differentiable for N <= 128) or 'rk4' (3/8 rule on the grid
-    ``t``; every size, differentiable).  Extras beyond torchdiffeq:
+    default the reference scripts get) or 'rk4' (3/8 rule on the grid ``t``); both for every network size, both
+    differentiable (exact discrete adjoints).  Extras beyond torchdiffeq:
     ``components`` restricts the returned trajectory to those state components (T, B, len(components));
     ``stats`` (a dict) receives per-trial n_accept / n_reject / status tensors; ``options['family']='staged'`` forces
     the global-state kernel family, ``options['max_num_steps']`` bounds dopri5."""
@@ -240,10 +240,7 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         return _RK4Function.apply(y0, setup.lf.W_aug, setup, sel_long, sel_i32)
     if method == "dopri5":
         if torch.is_grad_enabled() and (y0.requires_grad or setup.lf.W_aug.requires_grad):
-            if setup.problem(setup.lf.W_aug).kernel_family(setup.ext.OP_DOPRI5_FWD) != 0:
-                raise NotImplementedError("odecol: gradients through dopri5 exist for the on-chip family (N <= 128) only; "
-                                          "use method='rk4' (differentiable in every family) or torch.no_grad()")
-            from .dopri5_adjoint import dopri5_with_grad   # discrete adjoint through the accepted steps
+            from .dopri5_adjoint import dopri5_with_grad   # discrete adjoint through the accepted steps (both families)
             return dopri5_with_grad(setup, y0, rtol, atol, options, sel_long, sel_i32, stats)
         prob = setup.problem(setup.lf.W_aug)
         y, na, nr, st = setup.ext.dopri5_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), float(rtol),

@@ -201,7 +201,8 @@ def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg,
     ratio lands within rounding of 1 (or of a clipping bound of the step factor) the accept / reject decision may differ,
     after which the two take different -- equally valid -- step sequences whose results differ at the level of the
     solve's own discretisation error, not of float32 rounding.  Hence:
-      * the early window (dozens of controlled steps, before any borderline decision) must agree to rounding level;
+      * the early window (dozens of controlled steps, before any borderline decision) must agree to rounding level
+        (2e-5 on V and A; 1e-4 on F, whose filter has |1 - h / tau_s| ~ 1 at these steps so rounding differences do not decay);
       * accepted / rejected counts per trial: +-3 without noise, 3 % with noise (the Brownian increments make the error
         estimate rough, borderline decisions are frequent);
       * whole-solve outputs within 5e-4, and without noise the product must be as close to a converged float64 solution
@@ -231,7 +232,7 @@ def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg,
           f"{nro.tolist()}; outputs V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}; first {early} outputs "
           f"{errs_early[0]:.1e} {errs_early[1]:.1e} {errs_early[2]:.1e}")
     assert nao.min() > 10                                        # the controller really ran (not parked at one step)
-    assert max(errs_early) < 2e-5
+    assert max(errs_early[:2]) < 2e-5 and errs_early[2] < 1e-4      # F sits on explicit Euler's stability boundary at h ~ tau_s: rounding differences persist
     if noise:
         assert np.all(np.abs(na - nao) <= 0.03 * nao + 2) and np.all(np.abs(nr - nro) <= 0.06 * nro + 3)
         assert max(errs) < 1e-3
@@ -330,3 +331,48 @@ def test_lateral_gain_sweep_axis_matches_per_member_networks(cfg):
         odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", options={"lateral_gain": torch.zeros(B)})
     with pytest.raises(NotImplementedError):
         odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="srk", options={"lateral_gain": gain})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# dopri5 + loss.backward() beyond the on-chip family (the reference's default training path, scripts/xor_ode.py:114,177)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_staged_dopri5_adjoint_matches_oracle_autograd(cfg):
+    """N = 256 sheet: odeint(default method).backward() through the staged reverse sweep against autograd through the
+    oracle's dopri5 (one solve per trial: torchdiffeq controls the step over the whole tensor of a B = 1 solve)."""
+    sheet = odecol.SyntheticColumnSheet(cfg, 32, seed=6, device=DEV)
+    B, N, T = 4, 256, 9
+    gen = torch.Generator().manual_seed(31)
+    amp = torch.rand(B, 32, generator=gen) * 25
+    amp[3] *= 0.1                                              # a quiet trial: fewer accepted steps than the others
+    kt, ku = odecol.step_knots(2e-3, 8e-3, 1.2e-2, amp, 5e-4)
+    sheet.set_knots(kt.to(DEV), ku.to(DEV))
+    tv = torch.linspace(0.0, 1e-2, T)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 4 - 6, torch.rand(B, N, generator=gen) * 0.5, torch.rand(B, N, generator=gen)), 1)
+    sel = list(range(0, N, 8)) + [N + 8 * k for k in range(32)] + [2 * N + 5]
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    rtol, atol = 1e-6, 1e-8
+    lf = sheet_oracle_form(sheet)
+    gW = gU = None
+    trs, g0s, nacc_o = [], [], []
+    for b in range(B):
+        ode = orhs.UnifiedColumnODE(lf, kt.numpy(), ku[b:b + 1].numpy(), requires_grad=True)
+        y0o = y0[b:b + 1].clone().requires_grad_(True)
+        st = {}
+        yo = S.odeint_dopri5(ode, y0o, tv, rtol=rtol, atol=atol, stats=st)
+        (yo[:, :, sel] * wgt[:, b:b + 1]).sum().backward()
+        trs.append(yo[:, :, sel].detach()); g0s.append(y0o.grad); nacc_o.append(st["n_accept"])
+        gW = ode.W.grad if gW is None else gW + ode.W.grad
+        gU = ode.U.grad if gU is None else gU + ode.U.grad
+    tro, g0o = torch.cat(trs, 1), torch.cat(g0s, 0)
+    y0p = y0.to(DEV).requires_grad_(True)
+    stp = {}
+    yp = odecol.odeint(sheet, y0p, tv.to(DEV), rtol=rtol, atol=atol, components=sel, stats=stp)
+    (yp * wgt.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    et = _relmax(yp.detach().cpu(), tro)
+    e0, eW, eU = _relmax(y0p.grad.cpu(), g0o), _relmax(sheet.recurrent_weights.grad.cpu(), gW), _relmax(sheet.input_weights.grad.cpu(), gU)
+    print(f"\n[staged dopri5 adjoint N={N}] accepted {stp['n_accept'].tolist()} vs oracle {nacc_o}; trajectory {et:.1e}  dy0 {e0:.1e}  "
+          f"dW {eW:.1e}  dU {eU:.1e}")
+    assert np.all(np.abs(stp["n_accept"].cpu().numpy() - np.array(nacc_o)) <= 0.1 * np.array(nacc_o) + 2)
+    assert et < 2e-5 and e0 < 1e-3 and eW < 1e-3 and eU < 1e-3
+    assert len(set(stp["n_accept"].tolist())) > 1              # trials really ran different numbers of rounds
