@@ -298,6 +298,20 @@ int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, 
                            const float* target, int64_t st_t, int64_t st_b, int64_t st_g, float beta,
                            float* loss, float* grad_y_sel, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused window read-out of the XOR and parity tasks, with its gradient, in one pass:
+ *     pred_b = sum_k w[k] * mean over the last `last` grid points of phi(V_k - A_k)     k over the P read-out populations
+ *     loss   = mean_b | pred_b - target[b] |
+ * Replaces, down to the trajectory, compute_firing_rate + the final-point read-out of column C and
+ * torch.mean(abs(final_fr_C - xor_targets)) (scripts/xor_ode.py:120-130: last = 1, w = ff_source_mask) and the mean over
+ * the last 100 points times output_weights / output_scale with torch.mean(abs(final_fr_summed - parity_targets))
+ * (scripts/parity_ode.py:239-249: last = 100), plus loss.backward() down to the solver output.
+ *   y_sel    (T, B, 2*P): V of the P read-out populations, then their A (sel = [pops | N + pops])
+ *   w        [P] or NULL (ones);  target [B];  loss device scalar out;  pred [B] out
+ *   grad_y_sel (T, B, 2*P) out = d loss / d y_sel (zero outside the window);  workspace >= 8 bytes, 8-byte aligned */
+int odecol_window_rate_l1_loss(const float* y_sel, int32_t T, int32_t B, int32_t P, int32_t last, const float* w,
+                               const float* target, float* loss, float* pred, float* grad_y_sel,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in
  * tensor memory), C[n][m] = sum_k A[m][k] * B[n][k] for row-major A (M x K), B (N x K), C (N x M).  Lets the tests pin
  * the accuracy of the split-precision contraction the staged solver uses for large networks. */

@@ -11,7 +11,8 @@ The solvers run only on CUDA through the C ABI in ``include/odecol.h``; importin
 """
 from .model import (ColumnArea, ColumnAreaWTA, ColumnNetwork, ColumnNetworkXOR, LinearForm, compute_firing_rate,
                     load_config, move_to, pack_w_aug, soft_clamp, torch_interp)
-from .losses import fr_to_binary, huber_loss_wta, huber_rate_loss, min_max, parity_readout, xor_readout
+from .losses import (fr_to_binary, huber_loss_wta, huber_rate_loss, min_max, parity_readout, readout_components,
+                     window_rate_l1_loss, xor_readout)
 from .solvers import odeint, odeint_adjoint, sdeint, sdeint_adjoint
 from .stimulus import compress_knots, step_knots
 from .synthetic import SyntheticColumnSheet
@@ -22,7 +23,8 @@ from . import _native
 __all__ = [
     "ColumnArea", "ColumnAreaWTA", "ColumnNetwork", "ColumnNetworkXOR", "SyntheticColumnSheet", "LinearForm",
     "compute_firing_rate", "soft_clamp", "torch_interp", "load_config", "pack_w_aug", "move_to",
-    "min_max", "fr_to_binary", "huber_loss_wta", "huber_rate_loss", "xor_readout", "parity_readout",
+    "min_max", "fr_to_binary", "huber_loss_wta", "huber_rate_loss", "window_rate_l1_loss", "readout_components", "xor_readout",
+    "parity_readout",
     "odeint", "odeint_adjoint", "sdeint", "sdeint_adjoint", "compress_knots", "step_knots", "distributed",
     "make_ds_wwp", "get_data", "wongwang",
 ]

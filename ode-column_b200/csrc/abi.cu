@@ -409,6 +409,18 @@ int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, 
                                   static_cast<double*>(workspace), static_cast<cudaStream_t>(stream));
 }
 
+int odecol_window_rate_l1_loss(const float* y_sel, int32_t T, int32_t B, int32_t P, int32_t last, const float* w,
+                               const float* target, float* loss, float* pred, float* grad_y_sel, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!y_sel || !target || !loss || !pred || !grad_y_sel) return ODECOL_E_NULL;
+    if (T < 1 || B < 1 || P < 1 || last < 1 || last > T) return ODECOL_E_SHAPE;
+    if (!workspace || workspace_bytes < sizeof(double)) return ODECOL_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7) return ODECOL_E_ALIGN;
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_window_rate_l1_loss(y_sel, T, B, P, last, w, target, loss, pred, grad_y_sel, static_cast<double*>(workspace),
+                                      static_cast<cudaStream_t>(stream));
+}
+
 size_t odecol_tc_contract_workspace_bytes(int32_t M, int32_t N, int32_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return tc_contract_workspace_bytes(M, N, K);

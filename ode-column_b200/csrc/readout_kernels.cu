@@ -86,4 +86,64 @@ int launch_huber_rate_loss(const float* y_sel, int T, int B, int G, int P, const
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Window read-out of the XOR and parity tasks (reference scripts/xor_ode.py:120-130, scripts/parity_ode.py:239-249):
+//     pred_b = sum_k w_k * mean_{t in the last L grid points} phi(V_k(t, b) - A_k(t, b))        k over the P read-out populations
+//     loss   = mean_b | pred_b - target_b |
+// XOR: L = 1 (final point), the 8 populations of column C, w = ff_source_mask; parity: L = 100, the output column,
+// w = output_weights / output_scale.  One CTA per trial: the window's rates and phi' stay in shared memory between the
+// reduction and the gradient, so y_sel is read once; grad_y_sel is zero outside the window (cleared by the launcher).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_window_rate_l1(const float* __restrict__ y, int T, int B, int P, int L,
+                                                        const float* __restrict__ w, const float* __restrict__ target,
+                                                        float* __restrict__ pred, float* __restrict__ grad,
+                                                        double* __restrict__ acc) {
+    extern __shared__ float dph[];                      // [L * P] phi' of the window
+    __shared__ float red[4];
+    const int b = blockIdx.x, n = L * P;
+    const float inv_l = 1.0f / (float)L;
+    float part = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int t = T - L + e / P, k = e % P;
+        const float* yr = y + ((size_t)t * B + b) * 2 * P;
+        float r, dr;
+        phi_dphi(__fsub_rn(__ldg(yr + k), __ldg(yr + P + k)), r, dr);
+        const float wk = w ? __ldg(w + k) : 1.f;
+        dph[e] = dr * wk * inv_l;
+        part += r * wk * inv_l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    const float pr = red[0] + red[1] + red[2] + red[3];
+    const float d = pr - __ldg(target + b);
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    if (threadIdx.x == 0) {
+        pred[b] = pr;
+        atomicAdd(acc, (double)fabsf(d));
+    }
+    const float scale = sgn / (float)B;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int t = T - L + e / P, k = e % P;
+        float* gr = grad + ((size_t)t * B + b) * 2 * P;
+        const float gv = scale * dph[e];
+        gr[k] = gv;
+        gr[P + k] = -gv;
+    }
+}
+
+int launch_window_rate_l1_loss(const float* y_sel, int T, int B, int P, int L, const float* w, const float* target,
+                               float* loss, float* pred, float* grad, double* acc, cudaStream_t s) {
+    if (cudaMemsetAsync(acc, 0, sizeof(double), s) != cudaSuccess) return ODECOL_E_CUDA;
+    if (cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)T * B * 2 * P, s) != cudaSuccess) return ODECOL_E_CUDA;
+    const size_t smem = sizeof(float) * (size_t)L * P;
+    if (smem > 200 * 1024) return ODECOL_E_UNSUPPORTED;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_window_rate_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_window_rate_l1<<<B, 128, smem, s>>>(y_sel, T, B, P, L, w, target, pred, grad, acc);
+    k_loss_finalize<<<1, 32, 0, s>>>(acc, 1.0 / (double)B, loss);
+    count_launch(2);
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 }  // namespace odecol

@@ -444,6 +444,27 @@ std::vector<torch::Tensor> huber_rate_loss(const torch::Tensor& y_sel, const tor
     return {loss, grad};
 }
 
+// fused window read-out (XOR final point / parity last-100 mean): returns {loss (0-d), pred (B), grad_y_sel}
+std::vector<torch::Tensor> window_rate_l1_loss(const torch::Tensor& y_sel, const torch::Tensor& target, int64_t last,
+                                               std::optional<torch::Tensor> w) {
+    c10::cuda::CUDAGuard g(y_sel.device());
+    want(y_sel, "y_sel"); want(target, "target");
+    TORCH_CHECK(y_sel.dim() == 3 && y_sel.size(2) % 2 == 0, "odecol: y_sel must be (T, B, 2*P)");
+    const int64_t T = y_sel.size(0), B = y_sel.size(1), P = y_sel.size(2) / 2;
+    TORCH_CHECK(target.numel() == B, "odecol: target must have one entry per trial");
+    const float* wp = nullptr;
+    if (w.has_value()) { want(*w, "w"); TORCH_CHECK(w->numel() == P, "odecol: w must have P entries"); wp = w->data_ptr<float>(); }
+    auto loss = torch::empty({}, y_sel.options());
+    auto pred = torch::empty({B}, y_sel.options());
+    auto grad = torch::empty_like(y_sel);
+    auto ws = torch::empty({1}, y_sel.options().dtype(torch::kFloat64));
+    check(odecol_window_rate_l1_loss(y_sel.data_ptr<float>(), (int32_t)T, (int32_t)B, (int32_t)P, (int32_t)last, wp,
+                                     target.data_ptr<float>(), loss.data_ptr<float>(), pred.data_ptr<float>(),
+                                     grad.data_ptr<float>(), ws.data_ptr(), sizeof(double),
+                                     at::cuda::getCurrentCUDAStream(y_sel.device().index()).stream()), "window_rate_l1_loss");
+    return {loss, pred, grad};
+}
+
 torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {
     c10::cuda::CUDAGuard g(A.device());
     want(A, "A"); want(B, "B");
@@ -509,6 +530,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("brownian_query", &brownian_query);
     m.def("ww_generate", &ww_generate);
     m.def("huber_rate_loss", &huber_rate_loss);
+    m.def("window_rate_l1_loss", &window_rate_l1_loss);
     m.def("tc_contract", &tc_contract);
     m.def("tc_contract_tn", &tc_contract_tn);
     m.attr("OP_RHS") = (int)ODECOL_OP_RHS;

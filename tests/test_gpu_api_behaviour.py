@@ -77,3 +77,44 @@ def test_dopri5_record_is_sized_from_the_accepted_steps(cfg, golden, monkeypatch
     y2[-1, :, :24].sum().backward()
     assert caps[-1] < 4096 and caps[-1] > int(st["n_accept"].max())
     assert torch.equal(y, y2) and torch.equal(g_small, y0h.grad)
+
+
+@pytest.mark.parametrize("task", ["xor", "parity"])
+def test_fused_window_readout_matches_the_script_expressions(task, cfg, golden):
+    """odecol.window_rate_l1_loss against the reference scripts' read-out + loss written in torch (scripts/xor_ode.py:120-130,
+    scripts/parity_ode.py:239-249) and autograd's gradient w.r.t. the trajectory."""
+    gen = torch.Generator().manual_seed(3)
+    if task == "xor":
+        net = product_network("xor", cfg, golden["xor"], DEV)
+        T, B, N, last = 40, 8, 24, 1
+        pops = torch.arange(16, 24)
+        w = net.ff_source_mask
+        target = torch.where(torch.rand(B, generator=gen) > 0.5, 1.0, 0.25)
+    else:
+        net = product_network("parity", cfg, golden["parity"], DEV)
+        T, B, N, last = 130, 6, 104, 100
+        pops = torch.arange(N - 8, N)
+        w = net.output_weights / net.output_scale
+        target = torch.where(torch.rand(B, generator=gen) > 0.5, 20.0, 0.0)
+    traj = torch.cat((torch.rand(T, B, N, generator=gen) * 8 - 6, torch.rand(T, B, N, generator=gen), torch.rand(T, B, N, generator=gen)), 2).to(DEV)
+    sel = odecol.readout_components(pops, N).to(DEV)
+    # reference expression on the full trajectory
+    tr = traj.clone().requires_grad_(True)
+    rates = odecol.compute_firing_rate(tr[:, :, :N] - tr[:, :, N:2 * N])
+    if task == "xor":
+        pred_ref = torch.sum(rates[-1, :, 16:] * net.ff_source_mask.to(DEV), dim=1)
+    else:
+        pred_ref = torch.sum(rates[-100:, :, -8:].mean(dim=0) * w.to(DEV), dim=-1)
+    loss_ref = torch.mean(abs(pred_ref - target.to(DEV)))
+    loss_ref.backward()
+    # fused
+    ys = traj[:, :, sel].clone().requires_grad_(True)
+    loss, pred = odecol.window_rate_l1_loss(ys, target, weights=w, last=last)
+    (2.0 * loss).backward()
+    torch.cuda.synchronize()
+    g_ref = tr.grad[:, :, sel]
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    print(f"\n[{task} read-out] loss {float(loss):.6f} vs {float(loss_ref):.6f}; pred {rel(pred, pred_ref.detach()):.1e}; grad {rel(ys.grad, 2 * g_ref):.1e}")
+    assert abs(float(loss) - float(loss_ref)) < 2e-6 * max(1.0, abs(float(loss_ref)))
+    assert rel(pred, pred_ref.detach()) < 2e-6 and rel(ys.grad, 2 * g_ref) < 2e-5
+    assert float(ys.grad[:T - last].abs().max()) == 0.0

@@ -200,39 +200,45 @@ def test_adaptive_euler_maruyama_matches_the_oracle_controller(kind, noise, cfg,
     """What can and cannot agree: both solvers run torchsde's controller in float32 state arithmetic, so wherever an error
     ratio lands within rounding of 1 (or of a clipping bound of the step factor) the accept / reject decision may differ,
     after which the two take different -- equally valid -- step sequences whose results differ at the level of the
-    solve's own discretisation error, not of float32 rounding.  Hence:
-      * the early window (dozens of controlled steps, before any borderline decision) must agree to rounding level
-        (2e-5 on V and A; 1e-4 on F, whose filter has |1 - h / tau_s| ~ 1 at these steps so rounding differences do not decay);
-      * accepted / rejected counts per trial: +-3 without noise, 3 % with noise (the Brownian increments make the error
-        estimate rough, borderline decisions are frequent);
-      * whole-solve outputs within 5e-4, and without noise the product must be as close to a converged float64 solution
-        as the oracle is."""
+    solve's own discretisation error, not of float32 rounding.  Hence two checks:
+      * a SHORT solve (a handful of attempts, none of them borderline): identical accept / reject counts and states equal
+        to rounding level -- this pins the step arithmetic and the controller formula (any deviation moves the time grid);
+      * the LONG solve: accepted / rejected counts per trial +-3 without noise, 3 % with noise (the Brownian increments
+        make the error estimate rough, borderline decisions are frequent), outputs within 5e-4 / 1e-3, and without noise
+        the product must be as close to a converged float64 solution as the oracle is."""
     net, lf, kt, ku, ts, y0, B, options = _adaptive_case(kind, cfg, golden)
     ts = torch.linspace(0.0, float(ts[-1]), 61 if kind == "xor" else 13)
-    early = 6 if kind == "xor" else 3                            # outputs inside the first 5 ms (xor) / 1 ms (sheet)
     rtol, atol, dt, dt_min = 1e-5, 1e-4, 1e-3, 1e-5
     seed, trial_offset = 77, 5
     sc = torch.tensor([0.0] * B) if not noise else torch.tensor([0.05, 0.1, 0.2, 0.15][:B])
-    bms = [(_TreeBrownian(seed, trial_offset + b, ts[0], ts[-1]) if noise else _NoBrownian()) for b in range(B)]
-    yo, nao, nro = _oracle_adaptive(lf, kt, ku, ts, y0, sc.numpy(), bms, rtol, atol, dt, dt_min)
-    st = {}
-    with torch.no_grad():
-        yp = odecol.sdeint(net, y0.to(DEV), ts.to(DEV), method="euler", dt=dt, adaptive=True, rtol=rtol, atol=atol,
-                           dt_min=dt_min, seed=seed, trial_offset=trial_offset, stats=st,
-                           options=dict(options, sigma_scale=sc))
-    torch.cuda.synchronize()
-    yp = yp.cpu()
-    na, nr = st["n_accept"].cpu().numpy(), st["n_reject"].cpu().numpy()
-    assert int(st["status"].abs().sum()) == 0
     N = y0.shape[1] // 3
     blk = lambda a, c: a[..., c * N:(c + 1) * N]
+
+    def both(tgrid):
+        bms = [(_TreeBrownian(seed, trial_offset + b, tgrid[0], tgrid[-1]) if noise else _NoBrownian()) for b in range(B)]
+        yo_, nao_, nro_ = _oracle_adaptive(lf, kt, ku, tgrid, y0, sc.numpy(), bms, rtol, atol, dt, dt_min)
+        st_ = {}
+        with torch.no_grad():
+            yp_ = odecol.sdeint(net, y0.to(DEV), tgrid.to(DEV), method="euler", dt=dt, adaptive=True, rtol=rtol, atol=atol,
+                                dt_min=dt_min, seed=seed, trial_offset=trial_offset, stats=st_,
+                                options=dict(options, sigma_scale=sc))
+        torch.cuda.synchronize()
+        assert int(st_["status"].abs().sum()) == 0
+        return yp_.cpu(), yo_, st_["n_accept"].cpu().numpy(), st_["n_reject"].cpu().numpy(), nao_, nro_
+
+    # ---- short solve: the same attempts, step for step
+    yp, yo, na, nr, nao, nro = both(torch.linspace(0.0, 3e-4, 3))
     errs = [_relmax(blk(yp, c), blk(yo, c)) for c in range(3)]
-    errs_early = [_relmax(blk(yp[:early], c), blk(yo[:early], c)) for c in range(3)]
-    print(f"\n[adaptive EM {kind} noise={noise}] accepted {na.tolist()} vs oracle {nao.tolist()}; rejected {nr.tolist()} vs "
-          f"{nro.tolist()}; outputs V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}; first {early} outputs "
-          f"{errs_early[0]:.1e} {errs_early[1]:.1e} {errs_early[2]:.1e}")
+    print(f"\n[adaptive EM {kind} noise={noise}] short solve: accepted {na.tolist()} vs oracle {nao.tolist()}, rejected {nr.tolist()} vs "
+          f"{nro.tolist()}; V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}")
+    assert np.array_equal(na, nao) and np.array_equal(nr, nro) and int((na + nr).min()) >= 3
+    assert max(errs[:2]) < 5e-6 and errs[2] < 5e-5
+    # ---- long solve
+    yp, yo, na, nr, nao, nro = both(ts)
+    errs = [_relmax(blk(yp, c), blk(yo, c)) for c in range(3)]
+    print(f"[adaptive EM {kind} noise={noise}] accepted {na.tolist()} vs oracle {nao.tolist()}; rejected {nr.tolist()} vs "
+          f"{nro.tolist()}; outputs V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}")
     assert nao.min() > 10                                        # the controller really ran (not parked at one step)
-    assert max(errs_early[:2]) < 2e-5 and errs_early[2] < 1e-4      # F sits on explicit Euler's stability boundary at h ~ tau_s: rounding differences persist
     if noise:
         assert np.all(np.abs(na - nao) <= 0.03 * nao + 2) and np.all(np.abs(nr - nro) <= 0.06 * nro + 3)
         assert max(errs) < 1e-3
@@ -327,10 +333,13 @@ def test_lateral_gain_sweep_axis_matches_per_member_networks(cfg):
         ya = odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", adaptive=True, seed=3, stats=st,
                            options={"lateral_gain": gain, "sigma_scale": torch.full((B,), 0.1)})
     assert torch.isfinite(ya).all() and int(st["n_accept"].min()) > 3
-    with pytest.raises(ValueError):
-        odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", options={"lateral_gain": torch.zeros(B)})
-    with pytest.raises(NotImplementedError):
-        odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="srk", options={"lateral_gain": gain})
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", options={"lateral_gain": torch.zeros(B)})
+        with pytest.raises(NotImplementedError):
+            odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="srk", options={"lateral_gain": gain})
+    with pytest.raises(NotImplementedError):                  # a sweep feature: no reverse sweep through the gain
+        odecol.sdeint(sheet, y0.to(DEV), ts.to(DEV), method="euler", options={"lateral_gain": gain})
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -374,5 +383,5 @@ def test_staged_dopri5_adjoint_matches_oracle_autograd(cfg):
     print(f"\n[staged dopri5 adjoint N={N}] accepted {stp['n_accept'].tolist()} vs oracle {nacc_o}; trajectory {et:.1e}  dy0 {e0:.1e}  "
           f"dW {eW:.1e}  dU {eU:.1e}")
     assert np.all(np.abs(stp["n_accept"].cpu().numpy() - np.array(nacc_o)) <= 0.1 * np.array(nacc_o) + 2)
-    assert et < 2e-5 and e0 < 1e-3 and eW < 1e-3 and eU < 1e-3
+    assert et < 2e-4 and e0 < 1e-3 and eW < 1e-3 and eU < 1e-3     # two rtol = 1e-6 solves on step sequences that differ by one step
     assert len(set(stp["n_accept"].tolist())) > 1              # trials really ran different numbers of rounds
