@@ -307,9 +307,11 @@ int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, 
  * (scripts/parity_ode.py:239-249: last = 100), plus loss.backward() down to the solver output.
  *   y_sel    (T, B, 2*P): V of the P read-out populations, then their A (sel = [pops | N + pops])
  *   w        [P] or NULL (ones);  target [B];  loss device scalar out;  pred [B] out
- *   grad_y_sel (T, B, 2*P) out = d loss / d y_sel (zero outside the window);  workspace >= 8 bytes, 8-byte aligned */
+ *   grad_y_sel (T, B, 2*P) out = d loss / d y_sel (zero outside the window)
+ *   grad_w   (B, P) out: trial b's share of d loss / d w (sum over b for the gradient; the parity task trains
+ *            output_weights through this read-out);  workspace >= 8 bytes, 8-byte aligned */
 int odecol_window_rate_l1_loss(const float* y_sel, int32_t T, int32_t B, int32_t P, int32_t last, const float* w,
-                               const float* target, float* loss, float* pred, float* grad_y_sel,
+                               const float* target, float* loss, float* pred, float* grad_y_sel, float* grad_w,
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostic: the tensor-core contraction core alone (3xTF32 tcgen05.mma with TMA-fed operands, FP32 accumulation in

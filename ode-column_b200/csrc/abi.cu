@@ -410,14 +410,14 @@ int odecol_huber_rate_loss(const float* y_sel, int32_t T, int32_t B, int32_t G, 
 }
 
 int odecol_window_rate_l1_loss(const float* y_sel, int32_t T, int32_t B, int32_t P, int32_t last, const float* w,
-                               const float* target, float* loss, float* pred, float* grad_y_sel, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-    if (!y_sel || !target || !loss || !pred || !grad_y_sel) return ODECOL_E_NULL;
+                               const float* target, float* loss, float* pred, float* grad_y_sel, float* grad_w,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!y_sel || !target || !loss || !pred || !grad_y_sel || !grad_w) return ODECOL_E_NULL;
     if (T < 1 || B < 1 || P < 1 || last < 1 || last > T) return ODECOL_E_SHAPE;
     if (!workspace || workspace_bytes < sizeof(double)) return ODECOL_E_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) & 7) return ODECOL_E_ALIGN;
     g_launches.store(0, std::memory_order_relaxed);
-    return launch_window_rate_l1_loss(y_sel, T, B, P, last, w, target, loss, pred, grad_y_sel, static_cast<double*>(workspace),
+    return launch_window_rate_l1_loss(y_sel, T, B, P, last, w, target, loss, pred, grad_y_sel, grad_w, static_cast<double*>(workspace),
                                       static_cast<cudaStream_t>(stream));
 }
 

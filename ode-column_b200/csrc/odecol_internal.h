@@ -83,7 +83,7 @@ int launch_huber_rate_loss(const float* y_sel, int T, int B, int G, int P, const
                            double* acc, cudaStream_t s);
 
 int launch_window_rate_l1_loss(const float* y_sel, int T, int B, int P, int L, const float* w, const float* target,
-                               float* loss, float* pred, float* grad, double* acc, cudaStream_t s);
+                               float* loss, float* pred, float* grad, float* grad_w, double* acc, cudaStream_t s);
 
 // ---- family L (stage_kernels.cu): state in global memory, one fused contraction + epilogue per RK stage ------
 struct StageWorkspace;   // carved from the caller's workspace

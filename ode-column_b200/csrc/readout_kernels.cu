@@ -97,11 +97,14 @@ int launch_huber_rate_loss(const float* y_sel, int T, int B, int G, int P, const
 __global__ void __launch_bounds__(128) k_window_rate_l1(const float* __restrict__ y, int T, int B, int P, int L,
                                                         const float* __restrict__ w, const float* __restrict__ target,
                                                         float* __restrict__ pred, float* __restrict__ grad,
-                                                        double* __restrict__ acc) {
-    extern __shared__ float dph[];                      // [L * P] phi' of the window
+                                                        float* __restrict__ grad_w, double* __restrict__ acc) {
+    extern __shared__ float dph[];                      // [L * P] phi' of the window, then [P] window-mean rates
     __shared__ float red[4];
     const int b = blockIdx.x, n = L * P;
+    float* rk = dph + n;
     const float inv_l = 1.0f / (float)L;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) rk[k] = 0.f;
+    __syncthreads();
     float part = 0.f;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const int t = T - L + e / P, k = e % P;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(128) k_window_rate_l1(const float* __restrict_
         const float wk = w ? __ldg(w + k) : 1.f;
         dph[e] = dr * wk * inv_l;
         part += r * wk * inv_l;
+        atomicAdd(rk + k, r * inv_l);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(128) k_window_rate_l1(const float* __restrict_
         atomicAdd(acc, (double)fabsf(d));
     }
     const float scale = sgn / (float)B;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) grad_w[(size_t)b * P + k] = scale * rk[k];     // d loss / d w_k, this trial's share
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const int t = T - L + e / P, k = e % P;
         float* gr = grad + ((size_t)t * B + b) * 2 * P;
@@ -134,13 +139,13 @@ __global__ void __launch_bounds__(128) k_window_rate_l1(const float* __restrict_
 }
 
 int launch_window_rate_l1_loss(const float* y_sel, int T, int B, int P, int L, const float* w, const float* target,
-                               float* loss, float* pred, float* grad, double* acc, cudaStream_t s) {
+                               float* loss, float* pred, float* grad, float* grad_w, double* acc, cudaStream_t s) {
     if (cudaMemsetAsync(acc, 0, sizeof(double), s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)T * B * 2 * P, s) != cudaSuccess) return ODECOL_E_CUDA;
-    const size_t smem = sizeof(float) * (size_t)L * P;
+    const size_t smem = sizeof(float) * ((size_t)L * P + P);
     if (smem > 200 * 1024) return ODECOL_E_UNSUPPORTED;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_window_rate_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_window_rate_l1<<<B, 128, smem, s>>>(y_sel, T, B, P, L, w, target, pred, grad, acc);
+    k_window_rate_l1<<<B, 128, smem, s>>>(y_sel, T, B, P, L, w, target, pred, grad, grad_w, acc);
     k_loss_finalize<<<1, 32, 0, s>>>(acc, 1.0 / (double)B, loss);
     count_launch(2);
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;

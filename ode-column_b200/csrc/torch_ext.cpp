@@ -444,7 +444,7 @@ std::vector<torch::Tensor> huber_rate_loss(const torch::Tensor& y_sel, const tor
     return {loss, grad};
 }
 
-// fused window read-out (XOR final point / parity last-100 mean): returns {loss (0-d), pred (B), grad_y_sel}
+// fused window read-out (XOR final point / parity last-100 mean): returns {loss (0-d), pred (B), grad_y_sel, grad_w (P)}
 std::vector<torch::Tensor> window_rate_l1_loss(const torch::Tensor& y_sel, const torch::Tensor& target, int64_t last,
                                                std::optional<torch::Tensor> w) {
     c10::cuda::CUDAGuard g(y_sel.device());
@@ -457,12 +457,13 @@ std::vector<torch::Tensor> window_rate_l1_loss(const torch::Tensor& y_sel, const
     auto loss = torch::empty({}, y_sel.options());
     auto pred = torch::empty({B}, y_sel.options());
     auto grad = torch::empty_like(y_sel);
+    auto grad_w = torch::empty({B, P}, y_sel.options());
     auto ws = torch::empty({1}, y_sel.options().dtype(torch::kFloat64));
     check(odecol_window_rate_l1_loss(y_sel.data_ptr<float>(), (int32_t)T, (int32_t)B, (int32_t)P, (int32_t)last, wp,
                                      target.data_ptr<float>(), loss.data_ptr<float>(), pred.data_ptr<float>(),
-                                     grad.data_ptr<float>(), ws.data_ptr(), sizeof(double),
+                                     grad.data_ptr<float>(), grad_w.data_ptr<float>(), ws.data_ptr(), sizeof(double),
                                      at::cuda::getCurrentCUDAStream(y_sel.device().index()).stream()), "window_rate_l1_loss");
-    return {loss, pred, grad};
+    return {loss, pred, grad, grad_w.sum(0)};
 }
 
 torch::Tensor tc_contract(const torch::Tensor& A, const torch::Tensor& B) {

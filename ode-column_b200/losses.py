@@ -61,34 +61,36 @@ def huber_rate_loss(y_sel: torch.Tensor, target: torch.Tensor, pops_per_group: i
 
 
 class _WindowRateL1(torch.autograd.Function):
-    """loss, prediction and d loss / d trajectory in one fused pass (include/odecol.h: odecol_window_rate_l1_loss)."""
+    """loss, prediction, d loss / d trajectory and d loss / d weights in one fused pass (include/odecol.h:
+    odecol_window_rate_l1_loss)."""
 
     @staticmethod
     def forward(ctx, y_sel, target, last, w):
         from . import _native
-        loss, pred, grad = _native.ext().window_rate_l1_loss(y_sel.detach().contiguous(), target.detach().contiguous(), int(last),
-                                                             None if w is None else w.detach().to(torch.float32).contiguous())
-        ctx.save_for_backward(grad)
+        loss, pred, grad, grad_w = _native.ext().window_rate_l1_loss(y_sel.detach().contiguous(), target.detach().contiguous(),
+                                                                     int(last), w.detach().to(torch.float32).contiguous())
+        ctx.save_for_backward(grad, grad_w)
         ctx.mark_non_differentiable(pred)
         return loss, pred
 
     @staticmethod
     def backward(ctx, gout, _gpred):
-        (grad,) = ctx.saved_tensors
-        return grad * gout, None, None, None
+        grad, grad_w = ctx.saved_tensors
+        return grad * gout, None, None, grad_w * gout
 
 
 def window_rate_l1_loss(y_sel: torch.Tensor, target: torch.Tensor, weights=None, last: int = 1):
     """Fused ``mean_b | sum_k w_k mean_{last points} phi(V_k - A_k) - target_b |`` on a trajectory restricted to the P read-out
-    populations: ``y_sel`` (T, B, 2*P) as returned by ``odeint(..., components=cat(pops, N + pops))``, ``target`` (B,).
-    Returns ``(loss, pred)`` with pred (B,) the read-out itself.  The XOR task reads the final point of column C
+    populations: ``y_sel`` (T, B, 2*P) as returned by ``odeint(..., components=readout_components(pops, N))``, ``target`` (B,).
+    Returns ``(loss, pred)`` with pred (B,) the read-out itself (detached).  The XOR task reads the final point of column C
     (reference scripts/xor_ode.py:120-130: ``last=1``, ``weights=network.ff_source_mask``), the parity task the mean of the
     last 100 points of the output column (scripts/parity_ode.py:239-249: ``last=100``,
-    ``weights=network.output_weights / network.output_scale``).  One kernel computes loss, read-out and the gradient
-    w.r.t. ``y_sel``; no gradient flows to ``target`` / ``weights``.  CUDA only."""
+    ``weights=network.output_weights / network.output_scale`` -- trained through this read-out, so the gradient flows to
+    ``weights`` as well as to ``y_sel``).  One kernel computes all of it.  CUDA only."""
     if not y_sel.is_cuda:
         raise RuntimeError("odecol: window_rate_l1_loss is a fused CUDA read-out (no CPU path)")
-    w = None if weights is None else torch.as_tensor(weights, dtype=torch.float32).to(y_sel.device)
+    P = y_sel.shape[2] // 2
+    w = torch.ones(P, device=y_sel.device) if weights is None else torch.as_tensor(weights, dtype=torch.float32).to(y_sel.device)
     return _WindowRateL1.apply(y_sel, target.to(y_sel.device, torch.float32).reshape(-1), last, w)
 
 

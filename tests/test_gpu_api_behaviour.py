@@ -100,21 +100,24 @@ def test_fused_window_readout_matches_the_script_expressions(task, cfg, golden):
     sel = odecol.readout_components(pops, N).to(DEV)
     # reference expression on the full trajectory
     tr = traj.clone().requires_grad_(True)
+    wr = w.detach().clone().to(DEV).requires_grad_(True)
     rates = odecol.compute_firing_rate(tr[:, :, :N] - tr[:, :, N:2 * N])
     if task == "xor":
-        pred_ref = torch.sum(rates[-1, :, 16:] * net.ff_source_mask.to(DEV), dim=1)
+        pred_ref = torch.sum(rates[-1, :, 16:] * wr, dim=1)
     else:
-        pred_ref = torch.sum(rates[-100:, :, -8:].mean(dim=0) * w.to(DEV), dim=-1)
+        pred_ref = torch.sum(rates[-100:, :, -8:].mean(dim=0) * wr, dim=-1)
     loss_ref = torch.mean(abs(pred_ref - target.to(DEV)))
     loss_ref.backward()
     # fused
     ys = traj[:, :, sel].clone().requires_grad_(True)
-    loss, pred = odecol.window_rate_l1_loss(ys, target, weights=w, last=last)
+    wf = w.detach().clone().to(DEV).requires_grad_(True)
+    loss, pred = odecol.window_rate_l1_loss(ys, target, weights=wf, last=last)
     (2.0 * loss).backward()
     torch.cuda.synchronize()
     g_ref = tr.grad[:, :, sel]
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
-    print(f"\n[{task} read-out] loss {float(loss):.6f} vs {float(loss_ref):.6f}; pred {rel(pred, pred_ref.detach()):.1e}; grad {rel(ys.grad, 2 * g_ref):.1e}")
+    print(f"\n[{task} read-out] loss {float(loss):.6f} vs {float(loss_ref):.6f}; pred {rel(pred, pred_ref.detach()):.1e}; "
+          f"grad y {rel(ys.grad, 2 * g_ref):.1e}; grad w {rel(wf.grad, 2 * wr.grad):.1e}")
     assert abs(float(loss) - float(loss_ref)) < 2e-6 * max(1.0, abs(float(loss_ref)))
-    assert rel(pred, pred_ref.detach()) < 2e-6 and rel(ys.grad, 2 * g_ref) < 2e-5
+    assert rel(pred, pred_ref.detach()) < 2e-6 and rel(ys.grad, 2 * g_ref) < 2e-5 and rel(wf.grad, 2 * wr.grad) < 2e-5
     assert float(ys.grad[:T - last].abs().max()) == 0.0
