@@ -260,6 +260,25 @@ int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const fl
                    const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, float dt,
                    int32_t* status, float* y_steps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* torchsde.sdeint(..., method='srk', adaptive=True, rtol=, atol=, dt_min=): step doubling with the SRI2 step and torchsde's
+ * controller, per trial -- literally the reference's "avoid the integration artefacts" option (scripts/parity_ode.py:234,
+ * README.md:28-29).  Full step and half steps see one Brownian path: (W, U) of every sub-interval come from a
+ * Levy-area-consistent virtual Brownian tree (Philox4x32-10 keyed by seed and trial_offset + b; see
+ * odecol_brownian_levy_query).  Outputs by linear interpolation between solver states; n_accept / n_reject / status per
+ * trial as in odecol_em_fwd.  On-chip family only (N <= 128: the reference's networks); larger networks return
+ * ODECOL_E_UNSUPPORTED.  No workspace. */
+int odecol_srk_fwd_adaptive(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out,
+                            uint64_t seed, int64_t trial_offset, float dt, float rtol, float atol, float dt_min,
+                            int32_t* n_accept, int32_t* n_reject, int32_t* status,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* The path odecol_srk_fwd_adaptive integrates against: for every query time t[m] and trial b the cumulative pair
+ *     w[m][b] = W(t) - W(t_begin),     iw[m][b] = int_{t_begin}^{t} (W(r) - W(t_begin)) dr         (float64)
+ * of the tree spanning [t_begin, t_end].  For a step [a, b]: W = w(b) - w(a), U = iw(b) - iw(a) - (b - a) w(a) -- what
+ * torchsde's bm(a, b, return_U=True) returns. */
+int odecol_brownian_levy_query(uint64_t seed, int64_t trial_offset, int32_t B, float t_begin, float t_end, const float* t,
+                               int32_t M, double* w, double* iw, void* stream);
+
 /* Discrete adjoint of odecol_srk_fwd -- what loss.backward() through torchsde's unrolled srk steps computes (reference
  * scripts/wta_ode.py:174-181).  The noise is additive, but U enters the third drift stage, so the sweep needs the same
  * (dW, dU) tables or the same (seed, trial_offset) as the forward call.  Workspace:

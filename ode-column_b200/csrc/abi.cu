@@ -346,6 +346,30 @@ int odecol_srk_fwd(const odecol_problem* p, const float* ts, int32_t T, const fl
                                 static_cast<cudaStream_t>(stream));
 }
 
+int odecol_srk_fwd_adaptive(const odecol_problem* p, const float* ts, int32_t T, const float* y0, float* y_out, uint64_t seed,
+                            int64_t trial_offset, float dt, float rtol, float atol, float dt_min, int32_t* n_accept,
+                            int32_t* n_reject, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    DevProblem d;
+    const int rc = to_dev(p, d);
+    if (rc) return rc;
+    if (d.lat_gain) return ODECOL_E_UNSUPPORTED;
+    if (!ts || !y0 || !y_out) return ODECOL_E_NULL;
+    if (T < 2 || !(dt > 0.f) || !(dt_min > 0.f) || !(rtol >= 0.f) || !(atol >= 0.f)) return ODECOL_E_SHAPE;
+    if (!use_small(p, d)) return ODECOL_E_UNSUPPORTED;   // the adaptive srk solve exists in the on-chip family (N <= 128)
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_srk_adaptive_small(d, ts, T, y0, y_out, seed, trial_offset, dt, rtol, atol, dt_min, n_accept, n_reject, status,
+                                     1LL << 34, static_cast<cudaStream_t>(stream));
+}
+
+int odecol_brownian_levy_query(uint64_t seed, int64_t trial_offset, int32_t B, float t_begin, float t_end, const float* t,
+                               int32_t M, double* w, double* iw, void* stream) {
+    if (!t || !w || !iw) return ODECOL_E_NULL;
+    if (B < 1 || M < 1 || !(t_end > t_begin)) return ODECOL_E_SHAPE;
+    g_launches.store(0, std::memory_order_relaxed);
+    return launch_brownian_levy_query(seed, trial_offset, B, t_begin, t_end - t_begin, t, M, w, iw, static_cast<cudaStream_t>(stream));
+}
+
 int odecol_srk_bwd(const odecol_problem* p, const float* ts, int32_t T, const float* y_steps, int64_t n_steps,
                    const float* dW, const float* dU, uint64_t seed, int64_t trial_offset, const float* grad_y,
                    const int32_t* sel, int32_t G, float dt, float* grad_y0, float* grad_W_aug, void* workspace,

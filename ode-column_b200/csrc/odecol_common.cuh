@@ -163,6 +163,67 @@ ODECOL_DEVINL float brownian_tree(const Philox& px, uint64_t trial, float T0, fl
     });
 }
 
+// ---- Levy-area-consistent virtual Brownian tree (adaptive srk) -----------------------------------------------------------
+// The srk scheme consumes, per step, the increment W and the space-time Levy area U = int (W_r - W_t0) dr; under step
+// rejection both must stay consistent on every sub-interval (W(a,c) = W(a,b) + W(b,c), U(a,c) = U(a,b) + U(b,c) +
+// (c - b) W(a,b)), which is what torchsde's BrownianInterval guarantees.  Here every dyadic interval of the tree carries
+// (W, H) with H = U / h - W / 2 the normalised space-time Levy area (H ~ N(0, h / 12), independent of W); bisecting an
+// interval of length h draws Z ~ N(0, h / 16), N ~ N(0, h / 12) (Foster, Lyons & Oberhauser 2020, Theorem 6; verified
+// against the conditional law of the four half-interval variables in tests/test_oracle_selfcheck.py):
+//     W_left = W/2 + 3/2 H + Z      H_left  = H/4 - Z/2 + N/2
+//     W_right = W/2 - 3/2 H - Z     H_right = H/4 - Z/2 - N/2
+// A query walks the 24 levels once and returns the CUMULATIVE pair W(t) = W(T0, t), I(t) = int_{T0}^{t} W(T0, r) dr in
+// double precision; for a step [a, b]:  W = W(b) - W(a),  U = I(b) - I(a) - (b - a) W(a)  (the difference of the I's
+// cancels to ~h^1.5, hence the doubles).  Node deviates are keyed by (seed, trial, level | 0x40000000, index): a stream
+// separate from the W-only tree of the Euler-Maruyama solvers.
+constexpr uint32_t kLevyLevelTag = 0x40000000u;
+constexpr uint32_t kLevyRootLevel = 0x7FFFFFFFu;
+
+ODECOL_DEVINL void levy_node(const Philox& px, uint64_t trial, uint32_t level, uint32_t index, float& z, float& n) {
+    const uint4 bits = px((uint32_t)trial, (uint32_t)(trial >> 32), level | kLevyLevelTag, index);
+    z = normal_from_bits(bits.x, bits.y);
+    n = normal_from_bits(bits.z, bits.w);
+}
+
+// zn(level, z, n) yields the two deviates of the node visited at `level` (level == kBrownianDepth: the root's W and H)
+template <typename ZN>
+ODECOL_DEVINL void levy_combine(float span, uint32_t q, float frac, ZN zn, double& W, double& I) {
+    float z, n;
+    zn(kBrownianDepth, z, n);
+    double h = (double)span;
+    double Wab = sqrt(h) * (double)z, Hab = sqrt(h / 12.0) * (double)n;
+    double Wa = 0.0, Ia = 0.0;
+#pragma unroll 1
+    for (int level = 0; level < kBrownianDepth; ++level) {
+        zn(level, z, n);
+        const double Z = 0.25 * sqrt(h) * (double)z, Nn = sqrt(h / 12.0) * (double)n;
+        const double W1 = 0.5 * Wab + 1.5 * Hab + Z, H1 = 0.25 * Hab - 0.5 * Z + 0.5 * Nn;
+        const double hh = 0.5 * h;
+        if ((q >> (kBrownianDepth - 1 - level)) & 1u) {          // right half: move the left edge to the midpoint
+            Ia += hh * Wa + hh * (H1 + 0.5 * W1);
+            Wa += W1;
+            Wab = 0.5 * Wab - 1.5 * Hab - Z;
+            Hab = 0.25 * Hab - 0.5 * Z - 0.5 * Nn;
+        } else {
+            Wab = W1; Hab = H1;
+        }
+        h = hh;
+    }
+    const double fr = (double)frac;                              // linear inside the leaf (span / 2^24 long)
+    W = Wa + fr * Wab;
+    I = Ia + fr * h * Wa + 0.5 * fr * fr * h * Wab;
+}
+
+// sequential version (one thread per query)
+ODECOL_DEVINL void levy_tree(const Philox& px, uint64_t trial, float T0, float span, float t, double& W, double& I) {
+    uint32_t q; float frac;
+    brownian_path(T0, span, t, q, frac);
+    levy_combine(span, q, frac, [&](int level, float& z, float& n) {
+        if (level == kBrownianDepth) levy_node(px, trial, kLevyRootLevel, 0u, z, n);
+        else levy_node(px, trial, (uint32_t)level, level == 0 ? 0u : (q >> (kBrownianDepth - level)), z, n);
+    }, W, I);
+}
+
 // ---- torchsde srk (Roessler SRI2, SRID2 tableau) pieces shared by the on-chip and the staged kernels ---------------
 struct Srid2 {
     static constexpr float quarter = 0.25f, half = 0.5f;

@@ -69,6 +69,13 @@ int launch_srk_bwd_small(const DevProblem& p, int T, const float* y_steps, const
                          int64_t trial_offset, const float* grad_y, const int* sel, int G, float* grad_y0, float* grad_W,
                          const int* step_of, const float* w, const float* tk, cudaStream_t s);
 
+int launch_srk_adaptive_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, uint64_t seed,
+                              int64_t trial_offset, float dt, float rtol, float atol, float dt_min, int* n_accept,
+                              int* n_reject, int* status, long long max_attempts, cudaStream_t s);
+// W(t[m]) and I(t[m]) = int W of the Levy-area-consistent tree (adaptive srk), double precision, (M, B) each
+int launch_brownian_levy_query(uint64_t seed, int64_t trial_offset, int B, float t_begin, float span, const float* t, int M,
+                               double* w, double* iw, cudaStream_t s);
+
 // W(t[m]) of the virtual Brownian tree of trial (trial_offset + b) on [t_begin, t_begin + span]: w[m][b]
 int launch_brownian_query(uint64_t seed, int64_t trial_offset, int B, float t_begin, float span, const float* t, int M,
                           float* w, cudaStream_t s);

@@ -1186,6 +1186,190 @@ __global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks)
     cx.flush_dw(p, grad_W);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// torchsde sdeint(method='srk', adaptive=True): step doubling with the SRI2 step on the Levy-area-consistent virtual
+// Brownian tree (odecol_common.cuh) and torchsde's controller, per trial -- what the reference's own "avoid the
+// artefacts" option literally is (scripts/parity_ode.py:234, README.md:28-29).  Per attempt: f(t0, y) once (shared by the
+// full step and the first half step), two more drift evaluations for the full step, two for the first and three for the
+// second half step; the error estimate, the controller and the interpolated outputs are those of k_em_fwd_small.
+// ---------------------------------------------------------------------------------------------------------------
+template <int KP>
+struct SrkStepper {
+    RowRhs<KP>& f;
+    const float (&sg)[3];
+    // y1 = SRI2 step from (t0, y) over h with increments (dw, du); f0 = f(t0, y) is given
+    ODECOL_DEVINL void step(float t0, float h, const float (&y)[3], const float (&f0)[3], float dw, float du, float (&y1)[3]) {
+        const float rdt = __fdiv_rn(1.0f, h);
+        float gw[4], f1[3], f2[3], H[3];
+        srk_g_weights(h, dw, du, gw);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[c] = __fadd_rn(y[c], __fmul_rn(f0[c], h));
+        f.eval(__fadd_rn(t0, h), H[0], H[1], H[2], f1[0], f1[1], f1[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[c] = srk_h2(y[c], f0[c], f1[c], sg[c], h, du, rdt);
+        f.eval(__fadd_rn(t0, __fmul_rn(Srid2::half, h)), H[0], H[1], H[2], f2[0], f2[1], f2[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __fadd_rn(__fadd_rn(y[c], __fmul_rn(__fmul_rn(Srid2::a0, f0[c]), h)), __fmul_rn(sg[c], gw[0]));
+            v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a1, f1[c]), h)), __fmul_rn(sg[c], gw[1]));
+            v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(Srid2::a2, f2[c]), h)), __fmul_rn(sg[c], gw[2]));
+            y1[c] = __fadd_rn(v, __fmul_rn(sg[c], gw[3]));
+        }
+    }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128) k_srk_adaptive_small(DevProblem p, const float* __restrict__ ts, int T,
+                                                            const float* __restrict__ y0, float* __restrict__ y_out,
+                                                            unsigned long long seed, long long trial_offset, float dt0,
+                                                            float rtol, float atol, float dt_min, int* __restrict__ n_accept,
+                                                            int* __restrict__ n_reject, int* __restrict__ status,
+                                                            long long max_attempts) {
+    __shared__ __align__(16) float ra[2 * KP];
+    __shared__ double red[4];
+    __shared__ float zs[2][kBrownianDepth + 1][2];
+    const int b = blockIdx.x, i = threadIdx.x, N = p.N, B = p.B;
+    RowRhs<KP> f;
+    f.init(p, ra, b);
+    const size_t row = (size_t)3 * N;
+    const double cnt = 3.0 * N;
+    const Philox px(seed);
+    const unsigned long long trial = (unsigned long long)(trial_offset + b);
+    float sg[3] = {0.f, 0.f, 0.f};
+    float y[3] = {0.f, 0.f, 0.f};
+    if (f.act) {
+        const Y3 s = ld3(y0 + b * row, N, i);
+        y[0] = s.V; y[1] = s.A; y[2] = s.F;
+        st3(y_out + b * row, N, i, y[0], y[1], y[2]);
+        if (p.sigma) { sg[0] = __ldg(p.sigma + i); sg[1] = __ldg(p.sigma + N + i); sg[2] = __ldg(p.sigma + 2 * N + i); }
+        if (p.sigma_scale) { const float sc = __ldg(p.sigma_scale + b); sg[0] *= sc; sg[1] *= sc; sg[2] *= sc; }
+    }
+    SrkStepper<KP> srk{f, sg};
+    const float t_begin = __ldg(ts), t_end = __ldg(ts + T - 1);
+    const float span = t_end - t_begin;
+    float curr_t = t_begin, prev_t = t_begin;
+    float py[3] = {y[0], y[1], y[2]};
+    double step = (double)dt0, prev_ratio = 0.0;
+    bool has_prev = false;
+    long long attempts = 0;
+    int nacc = 0, nrej = 0, st = ODECOL_ST_OK;
+    double w_curr = 0.0, i_curr = 0.0;          // W(curr_t), I(curr_t) on the Levy tree
+    // two tree queries per attempt, computed cooperatively: lanes 0..24 draw the node deviates of both paths
+    auto tree2 = [&](float ta, float tb, double& wa, double& ia, double& wb, double& ib) {
+        uint32_t qa, qb; float fa, fb;
+        brownian_path(t_begin, span, ta, qa, fa);
+        brownian_path(t_begin, span, tb, qb, fb);
+        if (i <= kBrownianDepth) {
+            const bool root = i == kBrownianDepth;
+            const uint32_t lvl = root ? kLevyRootLevel : (uint32_t)i;
+            levy_node(px, trial, lvl, root || i == 0 ? 0u : (qa >> (kBrownianDepth - i)), zs[0][i][0], zs[0][i][1]);
+            levy_node(px, trial, lvl, root || i == 0 ? 0u : (qb >> (kBrownianDepth - i)), zs[1][i][0], zs[1][i][1]);
+        }
+        __syncthreads();
+        levy_combine(span, qa, fa, [&](int l, float& z, float& n) { z = zs[0][l][0]; n = zs[0][l][1]; }, wa, ia);
+        levy_combine(span, qb, fb, [&](int l, float& z, float& n) { z = zs[1][l][0]; n = zs[1][l][1]; }, wb, ib);
+        __syncthreads();
+    };
+    int j = 1;
+    for (; j < T && st == ODECOL_ST_OK; ++j) {
+        const float out_t = __ldg(ts + j);
+        while (curr_t < out_t) {
+            if (++attempts > max_attempts) { st = ODECOL_ST_MAXSTEPS; break; }
+            const float next_t = fminf(__fadd_rn(curr_t, (float)step), t_end);
+            const float mid_t = __fmul_rn(0.5f, __fadd_rn(curr_t, next_t));
+            double w_mid, i_mid, w_next, i_next;
+            tree2(mid_t, next_t, w_mid, i_mid, w_next, i_next);
+            const float h = __fsub_rn(next_t, curr_t), h1 = __fsub_rn(mid_t, curr_t), h2 = __fsub_rn(next_t, mid_t);
+            // (W, U) of the full step and of the two halves: U(a, b) = I(b) - I(a) - (b - a) W(a)
+            const float dwf = (float)(w_next - w_curr), duf = (float)(i_next - i_curr - (double)h * w_curr);
+            const float dw1 = (float)(w_mid - w_curr), du1 = (float)(i_mid - i_curr - (double)h1 * w_curr);
+            const float dw2 = (float)(w_next - w_mid), du2 = (float)(i_next - i_mid - (double)h2 * w_mid);
+            float f0[3], fm[3], yf[3], ym[3], yh[3], q[3];
+            f.eval(curr_t, y[0], y[1], y[2], f0[0], f0[1], f0[2]);
+            srk.step(curr_t, h, y, f0, dwf, duf, yf);
+            srk.step(curr_t, h1, y, f0, dw1, du1, ym);
+            f.eval(mid_t, ym[0], ym[1], ym[2], fm[0], fm[1], fm[2]);
+            srk.step(mid_t, h2, ym, fm, dw2, du2, yh);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(yf[c]), fabsf(yh[c]))));
+                q[c] = __fdiv_rn(__fsub_rn(yf[c], yh[c]), tol);
+            }
+            double s = f.act ? ((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]) : 0.0;
+            s = block_sum(s, red);
+            const double err = (double)(float)sqrt(s / cnt);
+            if (!(err == err)) { st = ODECOL_ST_NONFINITE; break; }
+            {                                    // torchsde adaptive_stepping.update_step_size
+                const double pfac = err > 1.0 ? 0.0 : 0.13, ifac = err > 1.0 ? 1.0 / 1.5 : 1.0 / 4.5;
+                const double ratio = 0.9 / err;
+                const double pr = has_prev ? prev_ratio : ratio;
+                double factor = pow(ratio, ifac) * pow(ratio / pr, pfac);
+                double facmin = 0.2;
+                if (err <= 1.0) { prev_ratio = ratio; has_prev = true; facmin = 1.0; }
+                factor = fmin(1.4, fmax(facmin, factor));
+                step = step * factor;
+            }
+            if (step < (double)dt_min) { step = (double)dt_min; has_prev = false; }
+            if (err <= 1.0 || step <= (double)dt_min) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { py[c] = y[c]; y[c] = yh[c]; }
+                prev_t = curr_t; curr_t = next_t; w_curr = w_next; i_curr = i_next;
+                ++nacc;
+            } else {
+                ++nrej;
+            }
+        }
+        if (st != ODECOL_ST_OK) break;
+        if (f.act) {
+            const float spn = __fsub_rn(curr_t, prev_t);
+            const float w0 = __fdiv_rn(__fsub_rn(curr_t, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, prev_t), spn);
+            st3(y_out + ((size_t)j * B + b) * row, N, i,
+                __fadd_rn(__fmul_rn(w0, py[0]), __fmul_rn(w1, y[0])),
+                __fadd_rn(__fmul_rn(w0, py[1]), __fmul_rn(w1, y[1])),
+                __fadd_rn(__fmul_rn(w0, py[2]), __fmul_rn(w1, y[2])));
+        }
+    }
+    if (st != ODECOL_ST_OK && f.act) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int jj = j; jj < T; ++jj) st3(y_out + ((size_t)jj * B + b) * row, N, i, qnan, qnan, qnan);
+    }
+    if (i == 0) {
+        if (n_accept) n_accept[b] = nacc;
+        if (n_reject) n_reject[b] = nrej;
+        if (status) status[b] = st;
+    }
+}
+
+int launch_srk_adaptive_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, uint64_t seed,
+                              int64_t trial_offset, float dt, float rtol, float atol, float dt_min, int* n_accept,
+                              int* n_reject, int* status, long long max_attempts, cudaStream_t s) {
+    const int kp = small_kp(p);
+    ODECOL_KP_SWITCH(kp, (k_srk_adaptive_small<KP><<<p.B, small_threads(p.N), 0, s>>>(
+                             p, ts, T, y0, y_out, (unsigned long long)seed, (long long)trial_offset, dt, rtol, atol, dt_min,
+                             n_accept, n_reject, status, max_attempts)));
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// W(t[m]), I(t[m]) of the Levy-area-consistent tree (odecol_brownian_levy_query): one thread per (query time, trial)
+__global__ void k_brownian_levy_query(unsigned long long seed, long long trial_offset, int B, float t_begin, float span,
+                                      const float* __restrict__ t, int M, double* __restrict__ w, double* __restrict__ iw) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)M * B) return;
+    const int m = (int)(e / B), b = (int)(e % B);
+    const Philox px(seed);
+    levy_tree(px, (unsigned long long)(trial_offset + b), t_begin, span, __ldg(t + m), w[e], iw[e]);
+}
+
+int launch_brownian_levy_query(uint64_t seed, int64_t trial_offset, int B, float t_begin, float span, const float* t, int M,
+                               double* w, double* iw, cudaStream_t s) {
+    const long long total = (long long)M * B;
+    k_brownian_levy_query<<<(unsigned)((total + 127) / 128), 128, 0, s>>>((unsigned long long)seed, (long long)trial_offset, B,
+                                                                           t_begin, span, t, M, w, iw);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
 int launch_srk_fwd_small(const DevProblem& p, const float* ts, int T, const float* y0, float* y_out, const float* dW,
                          const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps,
                          cudaStream_t s) {

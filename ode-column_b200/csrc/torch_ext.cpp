@@ -361,6 +361,34 @@ std::vector<torch::Tensor> srk_fwd(const Problem& pr, const torch::Tensor& ts, c
     return {y, st, ysteps};
 }
 
+// adaptive srk (on-chip family): (y, n_accept, n_reject, status)
+std::vector<torch::Tensor> srk_fwd_adaptive(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y0, int64_t seed,
+                                            int64_t trial_offset, double dt, double rtol, double atol, double dt_min) {
+    c10::cuda::CUDAGuard g(pr.W_aug.device());
+    check_state(pr, y0, "y0");
+    want(ts, "ts");
+    const int64_t T = ts.numel();
+    auto y = torch::empty({T, pr.B(), 3 * pr.N()}, pr.fopts());
+    auto na = torch::zeros({pr.B()}, pr.iopts()), nr = torch::zeros({pr.B()}, pr.iopts()), st = torch::zeros({pr.B()}, pr.iopts());
+    check(odecol_srk_fwd_adaptive(&pr.p, ts.data_ptr<float>(), (int32_t)T, y0.data_ptr<float>(), y.data_ptr<float>(), (uint64_t)seed,
+                                  trial_offset, (float)dt, (float)rtol, (float)atol, (float)dt_min, na.data_ptr<int32_t>(),
+                                  nr.data_ptr<int32_t>(), st.data_ptr<int32_t>(), nullptr, 0, pr.stream()), "srk_fwd_adaptive");
+    return {y, na, nr, st};
+}
+
+// cumulative (W, int W) of the Levy-area-consistent tree: t (M,) -> two float64 tensors (M, B)
+std::vector<torch::Tensor> brownian_levy_query(int64_t seed, int64_t trial_offset, int64_t B, double t_begin, double t_end,
+                                               const torch::Tensor& t) {
+    c10::cuda::CUDAGuard g(t.device());
+    want(t, "t");
+    auto w = torch::empty({t.numel(), B}, t.options().dtype(torch::kFloat64));
+    auto iw = torch::empty_like(w);
+    check(odecol_brownian_levy_query((uint64_t)seed, trial_offset, (int32_t)B, (float)t_begin, (float)t_end, t.data_ptr<float>(),
+                                     (int32_t)t.numel(), w.data_ptr<double>(), iw.data_ptr<double>(),
+                                     at::cuda::getCurrentCUDAStream(t.device().index()).stream()), "brownian_levy_query");
+    return {w, iw};
+}
+
 std::vector<torch::Tensor> srk_bwd(const Problem& pr, const torch::Tensor& ts, const torch::Tensor& y_steps,
                                    std::optional<torch::Tensor> dW, std::optional<torch::Tensor> dU, int64_t seed,
                                    int64_t trial_offset, const torch::Tensor& grad_y, std::optional<torch::Tensor> sel,
@@ -528,6 +556,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("em_bwd", &em_bwd);
     m.def("srk_fwd", &srk_fwd);
     m.def("srk_bwd", &srk_bwd);
+    m.def("srk_fwd_adaptive", &srk_fwd_adaptive);
+    m.def("brownian_levy_query", &brownian_levy_query);
     m.def("brownian_query", &brownian_query);
     m.def("ww_generate", &ww_generate);
     m.def("huber_rate_loss", &huber_rate_loss);

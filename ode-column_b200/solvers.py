@@ -302,8 +302,9 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     ``bm``: None -> in-kernel Philox4x32-10 noise keyed by (seed, trial_offset + trial index); a tensor (n_steps, B)
     or (n_steps, B, 1) of increments in step order (bit-parity mode, fixed step) -- for 'srk' a pair ``(W, U)`` of such
     tensors, U the space-time Levy area of each step; or a torchsde-style callable ``bm(t0, t1)`` /
-    ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` (Euler only) uses step
-    doubling with torchsde's controller, per trial, on a virtual Brownian tree (Philox only).
+    ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` uses step doubling with
+    torchsde's controller, per trial, on a virtual Brownian tree (Philox only): 'euler' for every network size, 'srk' (on
+    a Levy-area-consistent tree) for the on-chip family.
     ``options['sigma_scale']``: (B,) per-trial factor on the diffusion -- the noise-amplitude axis of a parameter sweep
     (trial b integrates with g = sigma_scale[b] * diffusion); ``options['lateral_gain']``: (B,) positive per-trial gain on
     the between-column recurrent weights (networks with ``lateral_split()``, e.g. ``SyntheticColumnSheet``; Euler-Maruyama,
@@ -313,9 +314,6 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     method = method or "srk"
     if method not in ("euler", "srk"):
         raise NotImplementedError(f"odecol: sdeint method {method!r} is not fused (have 'euler', 'srk')")
-    if method == "srk" and adaptive:
-        raise NotImplementedError("odecol: adaptive stepping is fused for method='euler' only (srk needs a Levy-area "
-                                  "consistent Brownian tree); use adaptive=False or method='euler'")
     if getattr(sde, "noise_type", "scalar") != "scalar" or getattr(sde, "sde_type", "ito") != "ito":
         raise ValueError("odecol: only scalar-noise Ito SDEs (what the reference declares) are supported")
     options = dict(options or {})
@@ -344,6 +342,16 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
         if bm is not None:
             raise NotImplementedError("odecol: adaptive stepping draws from the in-kernel Brownian tree; pass bm=None")
         prob = setup.problem(setup.lf.W_aug)
+        if method == "srk":
+            if prob.kernel_family(ext.OP_SRK_FWD) != 0:
+                raise NotImplementedError("odecol: adaptive srk is fused for the on-chip family (N <= 128, the reference's "
+                                          "networks); larger networks: method='euler' with adaptive=True, or fixed-step srk")
+            y, na, nr, st = ext.srk_fwd_adaptive(prob, setup.t, y0.detach().to(torch.float32).contiguous(), seed, int(trial_offset),
+                                                 dt, float(rtol), float(atol), float(dt_min))
+            if stats is not None:
+                stats.update(n_accept=na, n_reject=nr, status=st)
+            _check_status(st, options, "adaptive srk")
+            return y if sel_long is None else y.index_select(2, sel_long)
         y, na, nr, st, _ = ext.em_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), None, seed,
                                       int(trial_offset), dt, True, float(rtol), float(atol), float(dt_min), 0)
         if stats is not None:

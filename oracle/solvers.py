@@ -19,7 +19,7 @@ Algorithms restated
   * torchsde ``method='srk'`` for scalar / diagonal noise: Roessler's SRI2 scheme ("SRID2" tableau, strong order
     1.5) driven by the Brownian increment W and the space-time Levy area U = int (W_r - W_s) dr of every step --
     what every committed sdeint call of the reference names (scripts/wta_ode.py:174,200,
-    plotting_results.py:391,506,594), fixed step.
+    plotting_results.py:391,506,594), fixed step and step-doubling adaptive (scripts/parity_ode.py:234).
 
 ``tests/test_oracle_selfcheck.py`` anchors them (order conditions, convergence order, analytic solutions).
 All functions take ``func(t, y)`` with y of shape (B, D); the reference modules are used with B = 1.
@@ -409,18 +409,47 @@ def _srk_step(sde, bm, t0, t1, y0):
     return y1
 
 
-def sdeint_srk(sde, y0: torch.Tensor, ts: torch.Tensor, bm, dt: float = 1e-3):
-    """torchsde ``sdeint(..., method='srk')``, fixed step: the integrate loop of sdeint_euler with the SRI2 step.
-    ``bm(t0, t1, return_U=True)`` -> (W, U), each (B, 1) (see TabulatedBrownianU)."""
+def sdeint_srk(sde, y0: torch.Tensor, ts: torch.Tensor, bm, dt: float = 1e-3, adaptive: bool = False, rtol: float = 1e-5,
+               atol: float = 1e-4, dt_min: float = 1e-5, stats: Optional[Dict] = None):
+    """torchsde ``sdeint(..., method='srk')``: the integrate loop of sdeint_euler with the SRI2 step, fixed step or
+    step-doubling adaptive (``adaptive=True``: what /root/reference/scripts/parity_ode.py:234 names).
+    ``bm(t0, t1, return_U=True)`` -> (W, U), each (B, 1) (see TabulatedBrownianU); the adaptive controller needs a source
+    whose (W, U) are consistent on sub-intervals (a Brownian interval / tree, not a table)."""
+    step = dt
     prev_t = curr_t = ts[0]
     prev_y = curr_y = y0
     ys = [y0]
+    prev_ratio = None
+    n_acc = n_rej = 0
     for out_t in ts[1:]:
         while curr_t < out_t:
-            next_t = torch.minimum(curr_t + dt, ts[-1])
-            prev_t, prev_y = curr_t, curr_y
-            curr_y = _srk_step(sde, bm, curr_t, next_t, curr_y)
-            curr_t = next_t
+            next_t = torch.minimum(curr_t + step, ts[-1])
+            if adaptive:
+                y_full = _srk_step(sde, bm, curr_t, next_t, curr_y)
+                mid_t = 0.5 * (curr_t + next_t)
+                y_mid = _srk_step(sde, bm, curr_t, mid_t, curr_y)
+                y_half = _srk_step(sde, bm, mid_t, next_t, y_mid)
+                with torch.no_grad():
+                    tol = atol + rtol * torch.max(y_full.abs(), y_half.abs())
+                    err = float(_rms((y_full - y_half) / tol))
+                    step, prev_ratio = adaptive_update(err, step, prev_ratio)
+                if step < dt_min:
+                    step = dt_min
+                    prev_ratio = None
+                if err <= 1 or step <= dt_min:
+                    prev_t, prev_y = curr_t, curr_y
+                    curr_t, curr_y = next_t, y_half
+                    n_acc += 1
+                else:
+                    n_rej += 1
+            else:
+                prev_t, prev_y = curr_t, curr_y
+                curr_y = _srk_step(sde, bm, curr_t, next_t, curr_y)
+                curr_t = next_t
+                n_acc += 1
         span = curr_t - prev_t
         ys.append((curr_t - out_t) / span * prev_y + (out_t - prev_t) / span * curr_y)
+    if stats is not None:
+        stats["n_accept"] = n_acc
+        stats["n_reject"] = n_rej
     return torch.stack(ys, dim=0)

@@ -388,3 +388,106 @@ def test_staged_dopri5_adjoint_matches_oracle_autograd(cfg):
     assert np.all(np.abs(stp["n_accept"].cpu().numpy() - np.array(nacc_o)) <= 0.1 * np.array(nacc_o) + 2)
     assert et < 2e-4 and e0 < 1e-3 and eW < 1e-3 and eU < 1e-3     # two rtol = 1e-6 solves on step sequences that differ by one step
     assert len(set(stp["n_accept"].tolist())) > 1              # trials really ran different numbers of rounds
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# adaptive srk (the reference's "avoid the artefacts" option, scripts/parity_ode.py:234) on the Levy-area-consistent tree
+# ----------------------------------------------------------------------------------------------------------------------
+class _LevyTreeBrownian:
+    """bm(t0, t1, return_U=True) for the oracle from odecol_brownian_levy_query: the path the adaptive srk kernel sees."""
+
+    def __init__(self, seed, trial, t_begin, t_end):
+        self.ext = odecol._native.ext()
+        self.seed, self.trial, self.t_begin, self.t_end = seed, trial, float(t_begin), float(t_end)
+        self.shape = (1, 1)
+
+    def __call__(self, t0, t1, return_U=False):
+        q = torch.tensor([float(t0), float(t1)], dtype=torch.float32, device=DEV)
+        w, iw = (x.cpu() for x in self.ext.brownian_levy_query(self.seed, self.trial, 1, self.t_begin, self.t_end, q))
+        W = (w[1] - w[0]).float().reshape(1, 1)
+        if not return_U:
+            return W
+        h = float(q[1].cpu()) - float(q[0].cpu())
+        return W, (iw[1] - iw[0] - h * w[0]).float().reshape(1, 1)
+
+
+def test_levy_tree_gives_w_and_u_with_the_right_law_and_is_consistent():
+    ext = odecol._native.ext()
+    B, span = 20000, 0.8
+    # consistency on sub-intervals is exact by construction (cumulative W and int W): check the law of (W, U) of steps
+    for a, b in ((0.0, 0.8), (0.1, 0.1007), (0.3, 0.55), (0.7999, 0.8)):
+        q = torch.tensor([a, b], dtype=torch.float32, device=DEV)
+        w, iw = ext.brownian_levy_query(11, 0, B, 0.0, span, q)
+        h = float(q[1] - q[0])
+        W = (w[1] - w[0]).cpu().numpy()
+        U = (iw[1] - iw[0] - h * w[0]).cpu().numpy()
+        vW, vU, cWU = W.var(), U.var(), np.mean(W * U)
+        print(f"\n[levy tree] step [{a}, {b}]: var W / h {vW / h:.3f}, var U / (h^3/3) {vU / (h ** 3 / 3):.3f}, cov / (h^2/2) {cWU / (h * h / 2):.3f}, "
+              f"means {W.mean() / h ** 0.5:+.3f} {U.mean() / h ** 1.5:+.3f}")
+        assert abs(vW / h - 1) < 0.04 and abs(vU / (h ** 3 / 3) - 1) < 0.05 and abs(cWU / (h * h / 2) - 1) < 0.05
+        assert abs(W.mean()) < 0.03 * h ** 0.5 and abs(U.mean()) < 0.03 * h ** 1.5
+    # chaining: U(a, c) = U(a, b) + U(b, c) + (c - b) W(a, b), W additive
+    q = torch.tensor([0.2, 0.2004, 0.2011], dtype=torch.float32, device=DEV)
+    w, iw = (x.cpu().double() for x in ext.brownian_levy_query(11, 0, 64, 0.0, span, q))
+    t = q.cpu().double()
+    Ust = lambda i, j: iw[j] - iw[i] - (t[j] - t[i]) * w[i]
+    assert float((Ust(0, 2) - (Ust(0, 1) + Ust(1, 2) + (t[2] - t[1]) * (w[1] - w[0]))).abs().max()) < 1e-12
+    # different trials and seeds are different paths; the same key reproduces
+    w2, _ = ext.brownian_levy_query(11, 0, 64, 0.0, span, q)
+    w3, _ = ext.brownian_levy_query(12, 0, 64, 0.0, span, q)
+    assert torch.equal(w2.cpu().double(), w) and not torch.equal(w3.cpu().double(), w)
+
+
+@pytest.mark.parametrize("noise", [False, True], ids=["deterministic", "same_brownian_path"])
+def test_adaptive_srk_matches_the_oracle(noise, cfg, golden):
+    """sdeint(method='srk', adaptive=True) on the parity network (the call of scripts/parity_ode.py:234) against the
+    oracle's step-doubling srk on the same Levy tree, trial by trial; criteria as for adaptive Euler-Maruyama."""
+    net = product_network("parity", cfg, golden["parity"], DEV)
+    lf = oracle_form("parity", cfg, golden["parity"])
+    B, N = 3, 104
+    gen = torch.Generator().manual_seed(17)
+    kt = torch.tensor([0.0, 0.005, 0.0051, 1.0])
+    amp = torch.tensor([[15.0, 0, 15.0, 0], [0, 15.0, 15.0, 15.0], [15.0, 15.0, 15.0, 15.0]])
+    ku = torch.stack((torch.zeros(B, 4), torch.zeros(B, 4), amp, amp), 1)
+    net.time_vec, net.stim = kt.to(DEV), ku.to(DEV)
+    ts = torch.linspace(0.0, 0.03, 16)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 4 - 6, torch.rand(B, N, generator=gen) * 0.5, torch.rand(B, N, generator=gen)), 1)
+    rtol, atol, dt, dt_min = 1e-5, 1e-4, 1e-3, 1e-5
+    seed, off = 5, 40
+    sc = torch.tensor([0.0] * B) if not noise else torch.tensor([0.02, 0.05, 0.1])
+    import dataclasses
+    ys, nao, nro = [], [], []
+    for b in range(B):
+        lfb = dataclasses.replace(lf, sigma=(lf.sigma * float(sc[b])).astype(np.float32))
+        ode = orhs.UnifiedColumnODE(lfb, kt.numpy(), ku[b:b + 1].numpy())
+        so = {}
+        with torch.no_grad():
+            ys.append(S.sdeint_srk(ode, y0[b:b + 1], ts, _LevyTreeBrownian(seed, off + b, ts[0], ts[-1]), dt=dt, adaptive=True,
+                                   rtol=rtol, atol=atol, dt_min=dt_min, stats=so))
+        nao.append(so["n_accept"]); nro.append(so["n_reject"])
+    yo, nao, nro = torch.cat(ys, 1), np.array(nao), np.array(nro)
+    st = {}
+    with torch.no_grad():
+        yp = odecol.sdeint(net, y0.to(DEV), ts.to(DEV), method="srk", dt=dt, adaptive=True, rtol=rtol, atol=atol, dt_min=dt_min,
+                           seed=seed, trial_offset=off, stats=st, options={"sigma_scale": sc}).cpu()
+    na, nr = st["n_accept"].cpu().numpy(), st["n_reject"].cpu().numpy()
+    blk = lambda a, c: a[..., c * N:(c + 1) * N]
+    errs = [_relmax(blk(yp, c), blk(yo, c)) for c in range(3)]
+    print(f"\n[adaptive srk parity noise={noise}] accepted {na.tolist()} vs oracle {nao.tolist()}; rejected {nr.tolist()} vs {nro.tolist()}; "
+          f"outputs V/A/F {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}")
+    assert nao.min() > 10
+    assert np.all(np.abs(na - nao) <= 0.03 * nao + 3) and np.all(np.abs(nr - nro) <= 0.06 * nro + 3)
+    assert max(errs) < (1e-3 if noise else 5e-4)
+    if not noise:
+        ode64 = orhs.UnifiedColumnODE(lf, kt.numpy(), ku.numpy(), dtype=torch.float64)
+        with torch.no_grad():
+            yt = S.odeint_rk4(ode64, y0.double(), torch.linspace(0.0, 0.03, 15 * 400 + 1, dtype=torch.float64))[::400]
+        for c in range(3):
+            ep, eo = _relmax(blk(yp.double(), c), blk(yt, c)), _relmax(blk(yo.double(), c), blk(yt, c))
+            print(f"    block {c}: distance to the converged solution: product {ep:.2e}, oracle {eo:.2e}")
+            assert ep < 1.25 * eo + 2e-5
+    # larger networks have no fused adaptive srk
+    sheet = odecol.SyntheticColumnSheet(cfg, 32, seed=1, device=DEV)
+    sheet.set_knots(torch.tensor([0.0, 1.0], device=DEV), torch.zeros(1, 2, 32, device=DEV))
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        odecol.sdeint(sheet, torch.zeros(1, 768, device=DEV), ts.to(DEV), method="srk", adaptive=True)

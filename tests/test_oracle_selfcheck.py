@@ -250,3 +250,25 @@ def test_dopri5_and_rk4_agree_with_scipy_on_the_column_model(cfg, golden):
     ref = g["rk4_traj"][[300, 600, T], 0].astype(np.float64)
     err = np.abs(sol.y.T - ref).max() / np.abs(ref).max()
     assert err < 5e-5, err                        # fp32 rk4 at dt = 1e-4 vs converged float64 solution
+
+
+def test_levy_area_bridge_matches_the_conditional_law():
+    """The midpoint bisection of the Levy-area-consistent Brownian tree (csrc/odecol_common.cuh): conditional on (W, H) of an
+    interval of length h, the half-interval variables (W1, H1, W2, H2) must have mean (W/2 + 3H/2, H/4, W/2 - 3H/2, H/4) and
+    the covariance generated by Z ~ N(0, h/16), N ~ N(0, h/12) through W1 = .. + Z, H1 = .. - Z/2 + N/2, W2 = .. - Z,
+    H2 = .. - Z/2 - N/2.  Checked against Gaussian conditioning of the four underlying variables (W1, U1, W2, U2)."""
+    import numpy as np
+    for h in (1.0, 0.037):
+        g = h / 2
+        C1 = np.array([[g, g * g / 2], [g * g / 2, g ** 3 / 3]])                 # cov of (W, U = int W) on a half
+        C = np.zeros((4, 4)); C[:2, :2] = C1; C[2:, 2:] = C1
+        A = np.array([[1, 0, 1, 0], [g, 1, 0, 1]])                               # W = W1 + W2;  U = U1 + U2 + g W1
+        A_WH = np.array([A[0], A[1] / h - A[0] / 2])                             # H = U / h - W / 2
+        Sg = A_WH @ C @ A_WH.T
+        assert np.allclose(Sg, np.diag([h, h / 12]))                             # H ~ N(0, h / 12), independent of W
+        K = C @ A_WH.T @ np.linalg.inv(Sg)
+        Cc = C - K @ A_WH @ C
+        Tm = np.array([[1, 0, 0, 0], [-0.5, 1 / g, 0, 0], [0, 0, 1, 0], [0, 0, -0.5, 1 / g]])     # (W1, H1, W2, H2)
+        assert np.allclose(Tm @ K, [[0.5, 1.5], [0, 0.25], [0.5, -1.5], [0, 0.25]])
+        Bm = np.array([[1, 0], [-0.5, 0.5], [-1, 0], [-0.5, -0.5]])
+        assert np.allclose(Tm @ Cc @ Tm.T, Bm @ np.diag([h / 16, h / 12]) @ Bm.T)
