@@ -139,7 +139,7 @@ def test_solvers_refuse_cpu_and_foreign_functions(cfg, golden):
         odecol.odeint(lambda t, y: -y, torch.zeros(1, 48), net.time_vec)
     with pytest.raises(RuntimeError, match="CUDA"):
         odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="srk")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):               # adaptive srk is fused too (on-chip family): same CPU refusal
         odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="srk", adaptive=True)
     with pytest.raises(NotImplementedError):
         odecol.sdeint(net, torch.zeros(1, 48), net.time_vec, method="milstein")
