@@ -52,51 +52,70 @@ struct RhsEpi {
     ODECOL_DEVINL void tile_done(int, int, int, int, int) const {}
 };
 
-// operand r_aug(t_b, y_b) split hi/lo; one CTA per trial, per-trial time (NULL -> shared time *t_shared)
-__global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
-                             float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa,
-                             const int* __restrict__ active = nullptr, float* __restrict__ loc = nullptr) {
-    const int b = blockIdx.x, N = p.N, Kaug = N + p.n_in + 1;
-    if (active && !active[b]) return;          // adaptive sweeps: a finished trial's drift is never read again
-    // lateral-gain sweep (loc != NULL): the stimulus and bias columns carry 1 / g_b, so that g_b * (W_aug . r_aug) scales the
-    // recurrent input only
-    const float ginv = loc ? __fdiv_rn(1.0f, __ldg(p.lat_gain + b)) : 1.0f;
-    const size_t ro = (size_t)b * KPa;
-    const float* yb = y + (size_t)b * 3 * N;
-    const float tq = t_trial ? t_trial[b] : t_shared;
+// ---- operand r_aug(t_b, y_b), split hi / lo --------------------------------------------------------------------------------
+// Destination of one trial's operand row (and, in lateral-gain sweeps, of its within-column input plane).
+struct OperandDst {
+    float* hi; float* lo; float* loc;       // loc == NULL unless DevProblem::lat_gain is set
+    int KPa;
+};
+
+// Populations k .. k+3 of trial b from their stage state: r = phi(V - A) -> hi / lo (16-byte stores).  In a lateral-gain sweep
+// the within-column input W_local (*) r of the four populations is formed here as well: the eight rates of a column sit in
+// the registers of two neighbouring lanes (lane pairs exchange their four by shuffle), so nothing is re-read.  Every lane
+// of the warp must call this (in_range = false for lanes past N); `pair8` says whether the shuffle path applies (N % 8 == 0).
+ODECOL_DEVINL void operand_block4(const DevProblem& p, const OperandDst& d, int b, int k, bool in_range, const float4& V,
+                                  const float4& A, bool pair8) {
+    float r[4], h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        r[e] = in_range ? phi_fast((&V.x)[e] - (&A.x)[e]) : 0.f;
+        h[e] = tf32_rna(r[e]);
+        l[e] = tf32_rna(r[e] - h[e]);
+    }
+    const size_t ro = (size_t)b * d.KPa;
+    if (in_range) {
+        st4(d.hi + ro + k, make_float4(h[0], h[1], h[2], h[3]));
+        st4(d.lo + ro + k, make_float4(l[0], l[1], l[2], l[3]));
+    }
+    if (d.loc && pair8) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = __shfl_xor_sync(0xffffffffu, h[e] + l[e], 1);      // r as RhsEpi reads it: hi + lo
+        if (in_range) {
+            const bool upper = (k & 4) != 0;                 // this lane holds populations 4..7 of its column
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.W_local) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 w0 = ld4(p.W_local + (size_t)(k + e) * 8), w1 = ld4(p.W_local + (size_t)(k + e) * 8 + 4);
+                    const float4& wm = upper ? w1 : w0;      // weights onto this lane's own four sources
+                    const float4& wo = upper ? w0 : w1;      // ... and onto the partner lane's
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[e] = fmaf((&wm.x)[j], h[j] + l[j], fmaf((&wo.x)[j], o[j], acc[e]));
+                }
+            }
+            st4(d.loc + (size_t)b * p.N + k, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        }
+    }
+}
+
+// stimulus channels at time tq, the constant-one column (both divided by g_b in a lateral-gain sweep, so that
+// g_b * (W_aug . r_aug) scales the recurrent input only), and -- when the lane-pair path does not apply -- the
+// within-column input from the rates just written.  Called by all threads of the trial's CTA after the population loop.
+ODECOL_DEVINL void operand_tail(const DevProblem& p, const OperandDst& d, int b, float tq, bool pair8) {
+    const int N = p.N, Kaug = N + p.n_in + 1;
+    const float ginv = d.loc ? __fdiv_rn(1.0f, __ldg(p.lat_gain + b)) : 1.0f;
+    const size_t ro = (size_t)b * d.KPa;
     int idx = 1;
     const float tcl = knot_locate(p.knot_t, p.K, tq, idx);
     const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
-    // populations: four per thread and iteration through 16-byte accesses when the rows allow it (with one scalar load
-    // pair in flight per thread the kernel ran at 3.7 TB/s, latency-bound); same arithmetic per element either way
-    const bool vec = (N & 3) == 0 && (((uintptr_t)y | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0 && (KPa & 3) == 0;
-    int k_scalar0 = 0;
-    if (vec) {
-        for (int k = 4 * threadIdx.x; k < N; k += 4 * blockDim.x) {
-            const float4 V = ld4(yb + k), A = ld4(yb + N + k);
-            float h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float v = phi_fast((&V.x)[e] - (&A.x)[e]);
-                h[e] = tf32_rna(v);
-                l[e] = tf32_rna(v - h[e]);
-            }
-            st4(hi + ro + k, make_float4(h[0], h[1], h[2], h[3]));
-            st4(lo + ro + k, make_float4(l[0], l[1], l[2], l[3]));
-        }
-        k_scalar0 = N;
-    }
-    for (int k = k_scalar0 + threadIdx.x; k < Kaug; k += blockDim.x) {
-        float v;
-        if (k < N) v = phi_fast(yb[k] - yb[N + k]);
-        else if (k < N + p.n_in) v = knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N) * ginv;
-        else v = ginv;
+    for (int k = N + threadIdx.x; k < Kaug; k += blockDim.x) {
+        const float v = k < N + p.n_in ? knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N) * ginv : ginv;
         const float h = tf32_rna(v);
-        hi[ro + k] = h;
-        lo[ro + k] = tf32_rna(v - h);
+        d.hi[ro + k] = h;
+        d.lo[ro + k] = tf32_rna(v - h);
     }
-    if (loc) {
-        // within-column input of every population from the rates this CTA has just written (r = hi + lo, as RhsEpi reads it)
+    if (d.loc && !pair8) {
         __syncthreads();
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const int c0 = i & ~7;
@@ -104,11 +123,34 @@ __global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const fl
             if (p.W_local) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (c0 + j < N) acc = fmaf(__ldg(p.W_local + (size_t)i * 8 + j), hi[ro + c0 + j] + lo[ro + c0 + j], acc);
+                    if (c0 + j < N) acc = fmaf(__ldg(p.W_local + (size_t)i * 8 + j), d.hi[ro + c0 + j] + d.lo[ro + c0 + j], acc);
             }
-            loc[(size_t)b * N + i] = acc;
+            d.loc[(size_t)b * N + i] = acc;
         }
     }
+}
+
+ODECOL_DEVINL bool aligned16(const void* q) { return ((uintptr_t)q & 15) == 0; }
+
+// one CTA per trial, per-trial time (NULL -> shared time t_shared); N must be a multiple of 4 (the staged entry points check)
+__global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
+                             float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa,
+                             const int* __restrict__ active = nullptr, float* __restrict__ loc = nullptr) {
+    const int b = blockIdx.x, N = p.N;
+    if (active && !active[b]) return;          // adaptive sweeps: a finished trial's drift is never read again
+    const OperandDst d{hi, lo, loc, KPa};
+    const float* yb = y + (size_t)b * 3 * N;
+    const bool pair8 = (N & 7) == 0 && (!p.W_local || aligned16(p.W_local));
+    // four populations per thread and iteration through 16-byte accesses (with one scalar load pair in flight per thread
+    // the kernel ran at 3.7 TB/s, latency-bound)
+    for (int k0 = 0; k0 < N; k0 += 4 * blockDim.x) {
+        const int k = k0 + 4 * threadIdx.x;
+        const bool in = k < N;
+        float4 V = make_float4(0.f, 0.f, 0.f, 0.f), A = V;
+        if (in) { V = ld4(yb + k); A = ld4(yb + N + k); }
+        operand_block4(p, d, b, k, in, V, A, pair8);
+    }
+    operand_tail(p, d, b, t_trial ? t_trial[b] : t_shared, pair8);
 }
 
 // ---- fixed step ---------------------------------------------------------------------------------------------------
@@ -179,10 +221,13 @@ __global__ void k_ad_init(DevProblem p, TrialState s, const float* __restrict__ 
     if (b == 0) *s.n_active = p.B;
 }
 
-// full step and first half step from f0; writes y_full, y_mid.  One CTA per trial (finished trials cost nothing), four
-// components per thread and iteration when the rows are 16-byte aligned; per element the same operations in the same order.
+// full step and first half step from f0; writes y_full, y_mid AND the operand of the drift evaluation at (t_mid, y_mid).
+// One CTA per trial (finished trials cost nothing); a thread handles four populations per iteration -- their V, A and F
+// components through 16-byte accesses -- so the rates of y_mid are formed from registers (the separate operand kernel
+// re-read y_mid: 8 bytes per population and a launch per round).  Per element the operations of torchsde's Euler step in
+// their order.
 __global__ void k_ad_half1(DevProblem p, TrialState s, const float* __restrict__ y, const float* __restrict__ f0,
-                           float* __restrict__ y_full, float* __restrict__ y_mid) {
+                           float* __restrict__ y_full, float* __restrict__ y_mid, OperandDst d) {
     const int N = p.N, b = blockIdx.x;
     if (!s.active[b]) return;
     const float tc = s.t_cur[b], tm = s.t_mid[b], tn = s.t_next[b];
@@ -190,30 +235,37 @@ __global__ void k_ad_half1(DevProblem p, TrialState s, const float* __restrict__
     const float dwf = s.dw_full[b], dw1 = s.dw_1[b];
     const float sc = p.sigma_scale ? __ldg(p.sigma_scale + b) : 1.f;
     const size_t base = (size_t)b * 3 * N;
-    const bool vec = (N & 3) == 0 && (((uintptr_t)y | (uintptr_t)f0 | (uintptr_t)y_full | (uintptr_t)y_mid | (uintptr_t)p.sigma) & 15) == 0;
-    if (vec) {
-        for (int comp = 4 * threadIdx.x; comp < 3 * N; comp += 4 * blockDim.x) {
-            const float4 Y = ld4(y + base + comp), F = ld4(f0 + base + comp);
-            const float4 S = p.sigma ? ld4(p.sigma + comp) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 yf, ym;
+    const bool sig_vec = p.sigma && aligned16(p.sigma);
+    const bool pair8 = (N & 7) == 0 && (!p.W_local || aligned16(p.W_local));
+    for (int k0 = 0; k0 < N; k0 += 4 * blockDim.x) {
+        const int k = k0 + 4 * threadIdx.x;
+        const bool in = k < N;
+        float4 ymV = make_float4(0.f, 0.f, 0.f, 0.f), ymA = ymV;
+        if (in) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float sg = (&S.x)[e] * sc, y0 = (&Y.x)[e], f = (&F.x)[e];
-                (&yf.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, dwf));
-                (&ym.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, dw1));
+            for (int c = 0; c < 3; ++c) {
+                const size_t e0 = base + (size_t)c * N + k;
+                const float4 Y = ld4(y + e0), F = ld4(f0 + e0);
+                float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sig_vec) S = ld4(p.sigma + c * N + k);
+                else if (p.sigma) S = make_float4(__ldg(p.sigma + c * N + k), __ldg(p.sigma + c * N + k + 1), __ldg(p.sigma + c * N + k + 2),
+                                                  __ldg(p.sigma + c * N + k + 3));
+                float4 yf, ym;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float sg = (&S.x)[e] * sc, y0 = (&Y.x)[e], f = (&F.x)[e];
+                    (&yf.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, dwf));
+                    (&ym.x)[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, dw1));
+                }
+                st4(y_full + e0, yf);
+                st4(y_mid + e0, ym);
+                if (c == 0) ymV = ym;
+                if (c == 1) ymA = ym;
             }
-            st4(y_full + base + comp, yf);
-            st4(y_mid + base + comp, ym);
         }
-        return;
+        operand_block4(p, d, b, k, in, ymV, ymA, pair8);
     }
-    for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
-        const size_t e = base + comp;
-        const float sg = (p.sigma ? __ldg(p.sigma + comp) : 0.f) * sc;
-        const float y0 = y[e], f = f0[e];
-        y_full[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h)), __fmul_rn(sg, dwf));
-        y_mid[e] = __fadd_rn(__fadd_rn(y0, __fmul_rn(f, h1)), __fmul_rn(sg, dw1));
-    }
+    operand_tail(p, d, b, tm, pair8);
 }
 
 // second half step from f(mid), error sums per trial
@@ -318,44 +370,45 @@ __global__ void k_ad_control(DevProblem p, TrialState s, const float* __restrict
     s.dw_full[b] = wn - w0; s.dw_1[b] = wm - w0; s.dw_2[b] = wn - wm;
 }
 
-// commit accepted steps: state, outputs reached by the new time, finished trials
+// commit accepted steps: state, outputs reached by the new time, finished trials -- and the operand of the next attempt's
+// first drift evaluation, f(t_cur, y), formed from the committed state in registers.  A rejected attempt leaves y, t_cur
+// and therefore that operand untouched (the attempt's midpoint evaluation uses the other operand set).
 __global__ void k_ad_commit(DevProblem p, TrialState s, const float* __restrict__ ts, int T, float* __restrict__ y,
-                            float* __restrict__ y_prev, const float* __restrict__ y_half, float* __restrict__ y_out) {
+                            float* __restrict__ y_prev, const float* __restrict__ y_half, float* __restrict__ y_out,
+                            OperandDst d) {
     const int N = p.N, b = blockIdx.x;
     if (!s.active[b] || !s.accept[b]) return;
     const float t_prev = s.t_prev[b], t_cur = s.t_cur[b];
     const float spn = __fsub_rn(t_cur, t_prev);
     int j = s.next_out[b];
     const size_t total = (size_t)p.B * 3 * N;
-    const bool vec = (N & 3) == 0 && (((uintptr_t)y | (uintptr_t)y_prev | (uintptr_t)y_half | (uintptr_t)y_out) & 15) == 0;
-    if (vec) {                                  // four components per thread and iteration, 16-byte accesses
-        for (int comp = 4 * threadIdx.x; comp < 3 * N; comp += 4 * blockDim.x) {
-            const size_t e = (size_t)b * 3 * N + comp;
-            const float4 Y0 = ld4(y + e), Y1 = ld4(y_half + e);
-            st4(y_prev + e, Y0);
-            st4(y + e, Y1);
-            for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
-                const float out_t = __ldg(ts + jj);
-                const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
-                float4 O;
+    const bool pair8 = (N & 7) == 0 && (!p.W_local || aligned16(p.W_local));
+    for (int k0 = 0; k0 < N; k0 += 4 * blockDim.x) {
+        const int k = k0 + 4 * threadIdx.x;
+        const bool in = k < N;
+        float4 V = make_float4(0.f, 0.f, 0.f, 0.f), A = V;
+        if (in) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) (&O.x)[c] = __fadd_rn(__fmul_rn(w0, (&Y0.x)[c]), __fmul_rn(w1, (&Y1.x)[c]));
-                st4(y_out + (size_t)jj * total + e, O);
+            for (int c = 0; c < 3; ++c) {
+                const size_t e = (size_t)b * 3 * N + (size_t)c * N + k;
+                const float4 Y0 = ld4(y + e), Y1 = ld4(y_half + e);
+                st4(y_prev + e, Y0);
+                st4(y + e, Y1);
+                for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
+                    const float out_t = __ldg(ts + jj);
+                    const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
+                    float4 O;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) (&O.x)[q] = __fadd_rn(__fmul_rn(w0, (&Y0.x)[q]), __fmul_rn(w1, (&Y1.x)[q]));
+                    st4(y_out + (size_t)jj * total + e, O);
+                }
+                if (c == 0) V = Y1;
+                if (c == 1) A = Y1;
             }
         }
-    } else {
-        for (int comp = threadIdx.x; comp < 3 * N; comp += blockDim.x) {
-            const size_t e = (size_t)b * 3 * N + comp;
-            const float y0 = y[e], y1 = y_half[e];
-            y_prev[e] = y0;
-            y[e] = y1;
-            for (int jj = j; jj < T && __ldg(ts + jj) <= t_cur; ++jj) {
-                const float out_t = __ldg(ts + jj);
-                const float w0 = __fdiv_rn(__fsub_rn(t_cur, out_t), spn), w1 = __fdiv_rn(__fsub_rn(out_t, t_prev), spn);
-                y_out[(size_t)jj * total + e] = __fadd_rn(__fmul_rn(w0, y0), __fmul_rn(w1, y1));
-            }
-        }
+        operand_block4(p, d, b, k, in, V, A, pair8);
     }
+    operand_tail(p, d, b, t_cur, pair8);
     __syncthreads();
     if (threadIdx.x == 0) {
         while (j < T && ts[j] <= t_cur) ++j;
@@ -376,7 +429,8 @@ __global__ void k_em_fill_nan(DevProblem p, const int* __restrict__ status, cons
 
 struct EmLayout {
     int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev, off_state, off_loc, total;
+    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_Rhi1, off_Rlo1, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev,
+           off_state, off_loc, off_loc1, total;
 };
 
 static EmLayout em_layout(const DevProblem& p) {
@@ -389,11 +443,15 @@ static EmLayout em_layout(const DevProblem& p) {
     auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
     L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
     L.off_Rhi = take(4ull * L.Bp * L.KPa); L.off_Rlo = take(4ull * L.Bp * L.KPa);
+    // second operand set: the adaptive sweep keeps the operand of f(t_cur, y) (set 0) across a rejected attempt while the
+    // midpoint evaluation f(t_mid, y_mid) uses set 1
+    L.off_Rhi1 = take(4ull * L.Bp * L.KPa); L.off_Rlo1 = take(4ull * L.Bp * L.KPa);
     const size_t st = 4ull * p.B * 3 * p.N;
     L.off_f = take(st); L.off_fm = take(st); L.off_yfull = take(st); L.off_ymid = take(st); L.off_yhalf = take(st);
     L.off_y = take(st); L.off_yprev = take(st);
     L.off_state = take(128ull * p.B + 1024);
-    L.off_loc = take(p.lat_gain ? 4ull * p.B * p.N : 0);       // within-column input plane of the lateral-gain sweep
+    L.off_loc = take(p.lat_gain ? 4ull * p.B * p.N : 0);       // within-column input planes of the lateral-gain sweep
+    L.off_loc1 = take(p.lat_gain ? 4ull * p.B * p.N : 0);
     L.total = o;
     return L;
 }
@@ -441,6 +499,23 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
         if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi, mRhLo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
+    };
+    // adaptive sweep: the midpoint evaluation f(t_mid, y_mid) reads operand set 1 (written by k_ad_half1), so that the
+    // operand of f(t_cur, y) in set 0 (written by k_ad_commit) survives a rejected attempt
+    float *Rhi1 = F(L.off_Rhi1), *Rlo1 = F(L.off_Rlo1);
+    float* loc1 = p.lat_gain ? F(L.off_loc1) : nullptr;
+    CUtensorMap mRhi1, mRlo1, mRhHi1, mRhLo1;
+    if (adaptive) {
+        if (!make_map(&mRhi1, Rhi1, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo1, Rlo1, L.Bp, L.KPa, L.KPa, L.TN)) return ODECOL_E_CUDA;
+        if (use_pair && (!make_map(&mRhHi1, Rhi1, L.Bp, L.KPa, L.KPa, L.TN / 2) || !make_map(&mRhLo1, Rlo1, L.Bp, L.KPa, L.KPa, L.TN / 2)))
+            return ODECOL_E_CUDA;
+    }
+    auto rhs_mid = [&](const float* ysrc, float* fdst) {
+        RhsEpi e;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi1; e.Rlo = Rlo1; e.f = fdst; e.KPa = L.KPa; e.loc = loc1;
+        e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi1, mRhLo1, tsh, e, s);
+        return launch_contract(mWhi, mWlo, mRhi1, mRlo1, tsh, e, s);
     };
     const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
 
@@ -516,15 +591,13 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     for (long long round = 0; round < max_attempts && h_active > 0; ++round) {
         int rc = rhs(y, f0);
         if (rc != ODECOL_OK) return rc;
-        k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, ymid, S.t_mid, 0.f, Rhi, Rlo, L.KPa, S.active, loc);
-        rc = rhs(ymid, fm);
+        k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid, OperandDst{Rhi1, Rlo1, loc1, L.KPa});
+        rc = rhs_mid(ymid, fm);
         if (rc != ODECOL_OK) return rc;
         k_ad_half2<<<p.B, 256, 0, s>>>(p, S, ymid, fm, yfull, yhalf, rtol, atol);
         k_ad_control<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt_min, seed, trial_offset, max_attempts);
-        k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out);
-        k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, S.active, loc);
-        count_launch(6);
+        k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out, OperandDst{Rhi, Rlo, loc, L.KPa});
+        count_launch(4);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
             if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
