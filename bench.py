@@ -165,6 +165,21 @@ def cpu_sample(args, threads=None):
         loss.backward()
         return float(loss.detach())
 
+    def literal_loop(n_trials=2, steps=20):
+        """The reference's own execution model (scripts/xor_ode.py:104-117, parity_ode.py:223-236): ONE trial per solve, a
+        Python loop over trials, one thread -- here with the oracle's unified-form module standing in for the reference
+        classes (they cannot build a 64-column network in reasonable time).  Returns population-steps/s."""
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        for b in range(n_trials):
+            ode = orhs.UnifiedColumnODE(lf, kt, ku[b:b + 1], requires_grad=True)
+            y = S.odeint_rk4(ode, torch.zeros(1, 3 * n), tv[:steps + 1])
+            huber_on_rates(torch, odecol, y[:, :, sel], target, args.columns).backward()
+        el = time.perf_counter() - t0
+        torch.set_num_threads(threads)
+        return n * n_trials * steps / el
+
+    one_pass.literal_loop = literal_loop
     return one_pass, n * B * (T - 1), threads, f"{B} trials x {T - 1} rk4 steps, N={n}, forward + autograd backward"
 
 
@@ -530,7 +545,11 @@ def run_ours(args):
         reps = 2
         for _ in range(reps):
             one_pass()
-        cpu = {"value": ps * reps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu = {"value": ps * reps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+               "note": "batched unified-form port on all host threads (BASELINE.md's 'strong CPU'), not the reference's B = 1 loop",
+               "literal_trial_loop": {"value": one_pass.literal_loop(), "unit": UNIT, "cores": 1,
+                                      "sample": "2 trials x 20 rk4 steps, ONE trial per solve in a Python loop (the reference's "
+                                                "execution model), forward + autograd backward, extrapolates linearly in trials"}}
 
     if rank == 0:
         print(json.dumps({
