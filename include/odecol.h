@@ -8,8 +8,16 @@
  *   - all data pointers are DEVICE pointers to float32 (int32 / uint8 where declared), caller-owned,
  *     never retained past the call; the library performs no hidden allocation -- scratch memory is a
  *     caller-provided workspace sized by odecol_workspace_bytes();
- *   - calls are asynchronous with respect to the host and ordered on `stream` (a cudaStream_t passed as
- *     void* so that the header needs no CUDA include);
+ *   - calls are ordered on `stream` (a cudaStream_t passed as void* so that the header needs no CUDA include) and
+ *     asynchronous with respect to the host, with these documented exceptions, all in the STAGED family (N > 128 or a
+ *     forced flag): the fixed-step stochastic entry points (odecol_em_fwd, odecol_srk_fwd, odecol_em_bwd, odecol_srk_bwd)
+ *     replay the data-independent float32 step schedule on the host and synchronise the stream once at entry; the
+ *     adaptive ones (odecol_em_fwd with adaptive = 1, odecol_dopri5_fwd / _fwd_record) poll an "all trials finished"
+ *     counter every 16 rounds; odecol_dopri5_bwd reads the accepted-step counts once.  None of them may be captured into
+ *     a CUDA graph; everything else (the on-chip family, all rk4 entry points, the read-outs) may;
+ *   - results are deterministic for a given problem and library build, except grad_W_aug of the tensor family (N >= 256):
+ *     its reduction over trials uses float atomics, so repeated runs agree to float32 rounding (~1e-7 relative), not bit
+ *     for bit;
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
