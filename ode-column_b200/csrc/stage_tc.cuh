@@ -115,6 +115,11 @@ ODECOL_DEVINL unsigned long long gtimer() {
 }
 
 constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4 <= 32
+#ifndef ODECOL_PREFETCH_AHEAD
+#define ODECOL_PREFETCH_AHEAD 2
+#endif
+constexpr bool kPrefetch = ODECOL_PREFETCH_AHEAD > 0;      // L2 prefetch of the epilogues' scratch planes, groups ahead of the loads
+constexpr int kPrefetchAhead = ODECOL_PREFETCH_AHEAD;
 
 // ---------------------------------------------------------------------------------------------------------------
 // the persistent warp-specialised contraction.  Epi supplies
@@ -775,7 +780,22 @@ struct FwdEpiT {
         if (S >= 3) { L.k2V = ld4s(K2T + oq); L.R3 = ld4s(RsT[2] + oq); }
         if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); if (needF) L.F0 = ld4s(F0T + oq); }
     }
-    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
+    // L2 prefetch of what load_group(oq) will read: the planes were written one stage pass (tens of microseconds, several
+    // hundred MB of traffic) ago and are mostly back in HBM; a prefetch two groups ahead turns the demand loads of the
+    // pipelined loop into L2 hits without holding registers (the loop keeps ONE group in flight in registers).
+    ODECOL_DEVINL void prefetch_group(size_t oq) const {
+        prefetch_l2(V0T + oq); prefetch_l2(A0T + oq); prefetch_l2(RsT[0] + oq);
+        if (S >= 2) { prefetch_l2(K1T + oq); prefetch_l2(RsT[1] + oq); }
+        if (S >= 3) { prefetch_l2(K2T + oq); prefetch_l2(RsT[2] + oq); }
+        if (S >= 4) { prefetch_l2(K3T + oq); prefetch_l2(RsT[3] + oq); if (needF) prefetch_l2(F0T + oq); }
+    }
+    // before the tile's accumulator is ready: the first groups of this thread
+    ODECOL_DEVINL void pre_tile(int i, int nt, int g, int TNq) const {
+        if (i >= p.N || !kPrefetch) return;
+        const size_t o0 = tg.off(nt, g, 0, i), qstride = (size_t)tg.Np * 4;
+        const int nq = TNq >> 2;
+        for (int q = 0; q < kPrefetchAhead + 1 && q < nq; ++q) prefetch_group(o0 + q * qstride);
+    }
 
     // The group loop is rolled (its body is ~1000 instructions; seven unrolled copies missed the instruction cache) and
     // software-pipelined: the loads of group q+1 are issued before group q is processed, so the memory system is never
@@ -797,6 +817,7 @@ struct FwdEpiT {
             const size_t oq = o0 + q * qstride;
             const Group L = nxt;
             if (q + 1 < nq) load_group(nxt, oq + qstride);
+            if (kPrefetch && q + 1 + kPrefetchAhead < nq) prefetch_group(oq + (1 + kPrefetchAhead) * qstride);
             const float4 &V0 = L.V0, &A0 = L.A0, &R1 = L.R1, &R2 = L.R2, &R3 = L.R3, &R4 = L.R4, &F0 = L.F0;
             const float4 &k1V = L.k1V, &k2V = L.k2V, &k3V = L.k3V;
             const int q4 = 4 * q;

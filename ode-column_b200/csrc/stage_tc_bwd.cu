@@ -63,7 +63,19 @@ struct BwdEpiT {
             }
         }
     }
-    ODECOL_DEVINL void pre_tile(int, int, int, int) const {}
+    ODECOL_DEVINL void prefetch_group(size_t oq, size_t pl) const {      // see FwdEpiT::prefetch_group
+        prefetch_l2(DRT + oq); prefetch_l2(lamT + oq); prefetch_l2(lamT + pl + oq);
+        if (needF) prefetch_l2(lamT + 2 * pl + oq);
+        if (S == 1) { prefetch_l2(acurT + oq); prefetch_l2(acurT + pl + oq); }
+        if (S <= 3) { prefetch_l2(b4T + oq); prefetch_l2(b4T + pl + oq); }
+        if (S == 2) { prefetch_l2(b3T + oq); prefetch_l2(b3T + pl + oq); }
+    }
+    ODECOL_DEVINL void pre_tile(int j, int nt, int g, int TNq) const {
+        if (j >= p.N || !kPrefetch) return;
+        const size_t o0 = tg.off(nt, g, 0, j), qstride = (size_t)tg.Np * 4, pl = tg.plane();
+        const int nq = TNq >> 2;
+        for (int q = 0; q < kPrefetchAhead + 1 && q < nq; ++q) prefetch_group(o0 + q * qstride, pl);
+    }
 
     // rolled, software-pipelined group loop (see FwdEpiT::rows)
     ODECOL_DEVINL void rows(int, int j, int n0, int nt, int g, int TNq, const float (&graw)[kMaxQ]) const {
@@ -85,6 +97,7 @@ struct BwdEpiT {
             const size_t oq = o0 + q * qstride;
             const Group L = nxt;
             if (q + 1 < nq) load_group(nxt, oq + qstride, pl, bg + 4 * (q + 1), gV, gA, gF);
+            if (kPrefetch && q + 1 + kPrefetchAhead < nq) prefetch_group(oq + (1 + kPrefetchAhead) * qstride, pl);
             float nV[4], nA[4], sV[4], sA[4], sF[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -210,6 +223,14 @@ ODECOL_DEVINL void chain_epilogue(const BwdChainArgs& a, int m_tile, int row, in
     e.inv_tm = a.inv_tm; e.inv_ta = a.inv_ta; e.inv_ts = a.inv_ts;
     e.prepare();
     e.rows(m_tile, row, n0, nt, g, TNq, tot);
+}
+
+template <int S>
+ODECOL_DEVINL void chain_pre_tile(const BwdChainArgs& a, int row, int nt, int g, int TNq) {
+    BwdEpiT<S> e;
+    e.p = a.p; e.tg = a.tg; e.acurT = a.acurT; e.lamT = a.lamT; e.b4T = a.b4T; e.b3T = a.b3T; e.DRT = a.DRT[S - 1];
+    e.needF = __ldg(a.inv + 3 * a.p.N);
+    e.pre_tile(row, nt, g, TNq);
 }
 
 template <bool FUSE_DW>
@@ -400,6 +421,12 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                 const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
                 const int row = m_tile * BM + quarter * 32 + lane;
                 float tot[kMaxQ];
+                switch (q) {                       // warm L2 with this thread's first scratch groups while the tile is contracted
+                    case 0: chain_pre_tile<4>(a, row, nt, g, TNq); break;
+                    case 1: chain_pre_tile<3>(a, row, nt, g, TNq); break;
+                    case 2: chain_pre_tile<2>(a, row, nt, g, TNq); break;
+                    default: chain_pre_tile<1>(a, row, nt, g, TNq); break;
+                }
                 mbar_wait(tfull, tphase);
                 tc_fence_after();
                 const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);

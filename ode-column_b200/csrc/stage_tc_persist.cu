@@ -177,6 +177,12 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
                 const int m_tile = tile % ts.MT, nt = tile / ts.MT, n0 = nt * ts.TN;
                 const int row = m_tile * BM + quarter * 32 + lane;
                 float tot[kMaxQ];
+                switch (s) {                       // warm L2 with this thread's first scratch groups while the tile is contracted
+                    case 1: { FwdEpiT<1> e = persist_epi<1>(a, n, q); e.needF = 1; e.pre_tile(row, nt, g, TNq); } break;
+                    case 2: { FwdEpiT<2> e = persist_epi<2>(a, n, q); e.needF = 1; e.pre_tile(row, nt, g, TNq); } break;
+                    case 3: { FwdEpiT<3> e = persist_epi<3>(a, n, q); e.needF = 1; e.pre_tile(row, nt, g, TNq); } break;
+                    default: { FwdEpiT<4> e = persist_epi<4>(a, n, q); e.needF = 0; e.pre_tile(row, nt, g, TNq); } break;
+                }
                 mbar_wait(tfull, tphase);
                 tc_fence_after();
                 const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
