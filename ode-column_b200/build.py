@@ -28,6 +28,10 @@ NVCC_FLAGS = [
 ]
 
 
+# experiments: extra nvcc flags (e.g. ODECOL_NVCC_EXTRA="-DODECOL_PREFETCH_AHEAD=0 -DODECOL_DIAG") for an A/B rebuild on the GPU box
+NVCC_FLAGS += os.environ.get("ODECOL_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
