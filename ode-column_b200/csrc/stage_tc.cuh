@@ -115,10 +115,15 @@ ODECOL_DEVINL unsigned long long gtimer() {
 }
 
 constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4 <= 32
+// L2 prefetch of the epilogues' scratch planes, this many groups ahead of the pipelined loads (0 = off, the default).
+// Measured on the C4 step, A/B on one box (scratch/ab_bench.sh, -DODECOL_PREFETCH_AHEAD=2 vs 0): forward 370 vs 352 ms,
+// reverse sweep 626 vs 615 ms -- SLOWER with the prefetch.  The stage passes are bound by L2 throughput, not by the latency
+// of the scratch loads: every extra L2 transaction (and every operand line a prefetched plane evicts) costs more than the
+// shorter load latency buys.
 #ifndef ODECOL_PREFETCH_AHEAD
-#define ODECOL_PREFETCH_AHEAD 2
+#define ODECOL_PREFETCH_AHEAD 0
 #endif
-constexpr bool kPrefetch = ODECOL_PREFETCH_AHEAD > 0;      // L2 prefetch of the epilogues' scratch planes, groups ahead of the loads
+constexpr bool kPrefetch = ODECOL_PREFETCH_AHEAD > 0;
 constexpr int kPrefetchAhead = ODECOL_PREFETCH_AHEAD;
 
 // ---------------------------------------------------------------------------------------------------------------
