@@ -31,6 +31,21 @@ from .stimulus import compress_knots
 _DEFAULT_MAX_STEPS = 4_000_000
 
 
+class _nvtx:
+    """NVTX range around a fused solve / reverse sweep (shows up in ncu / nsys timelines; a few hundred nanoseconds when
+    no profiler is attached).  The reference has no tracing of its own."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _require_linear_form(func):
     if not (hasattr(func, "export_linear_form") and hasattr(func, "stimulus_channels")):
         raise TypeError(
@@ -129,7 +144,8 @@ class _RK4Function(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, W_aug, setup: _Setup, sel_long, sel_i32):
         prob = setup.problem(W_aug)
-        y = setup.ext.rk4_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), 1)
+        with _nvtx("odecol.rk4_fwd"):
+            y = setup.ext.rk4_fwd(prob, setup.t, y0.detach().to(torch.float32).contiguous(), 1)
         ctx.setup, ctx.prob, ctx.sel_i32 = setup, prob, sel_i32
         ctx.save_for_backward(y)
         return y if sel_long is None else y.index_select(2, sel_long)
@@ -137,7 +153,8 @@ class _RK4Function(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (y,) = ctx.saved_tensors
-        gy0, gW = ctx.setup.ext.rk4_bwd(ctx.prob, ctx.setup.t, y, grad.to(torch.float32).contiguous(), ctx.sel_i32)
+        with _nvtx("odecol.rk4_bwd"):
+            gy0, gW = ctx.setup.ext.rk4_bwd(ctx.prob, ctx.setup.t, y, grad.to(torch.float32).contiguous(), ctx.sel_i32)
         return gy0, gW, None, None, None
 
 
@@ -155,7 +172,8 @@ class _RK4CkptFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, W_aug, setup: _Setup, sel_i32):
         prob = setup.problem(W_aug)
-        y_sel, ckpt = setup.ext.rk4_fwd_ckpt(prob, setup.t, y0.detach().to(torch.float32).contiguous(), sel_i32)
+        with _nvtx("odecol.rk4_fwd_ckpt"):
+            y_sel, ckpt = setup.ext.rk4_fwd_ckpt(prob, setup.t, y0.detach().to(torch.float32).contiguous(), sel_i32)
         ctx.setup, ctx.prob, ctx.sel_i32 = setup, prob, sel_i32
         ctx.save_for_backward(ckpt)
         return y_sel
@@ -163,7 +181,8 @@ class _RK4CkptFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (ckpt,) = ctx.saved_tensors
-        gy0, gW = ctx.setup.ext.rk4_bwd_ckpt(ctx.prob, ctx.setup.t, ckpt, grad.to(torch.float32).contiguous(), ctx.sel_i32)
+        with _nvtx("odecol.rk4_bwd_ckpt"):
+            gy0, gW = ctx.setup.ext.rk4_bwd_ckpt(ctx.prob, ctx.setup.t, ckpt, grad.to(torch.float32).contiguous(), ctx.sel_i32)
         return gy0, gW, None, None
 
 
