@@ -156,6 +156,55 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert hub(fake, 10, 4, 2, 0, None, fake, 0, 0, 0, 1.0, fake, fake, fake, 8, None) == E_SHAPE
     assert hub(fake, 10, 4, 2, 1, None, fake, 0, 0, 0, 0.0, fake, fake, fake, 8, None) == E_SHAPE
     assert hub(fake, 10, 4, 2, 1, None, fake, 0, 0, 0, 1.0, fake, fake, None, 0, None) == E_WORKSPACE
+    # round-2 entry points: window read-out, Brownian queries, adaptive srk, the dopri5 record / reverse pair, the staged drift
+    win = lib.odecol_window_rate_l1_loss
+    win.restype = ctypes.c_int
+    win.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                    ctypes.c_size_t, ctypes.c_void_p]
+    assert win(fake, 100, 4, 8, 101, None, fake, fake, fake, fake, fake, fake, 8, None) == E_SHAPE      # window longer than the solve
+    assert win(fake, 100, 4, 8, 0, None, fake, fake, fake, fake, fake, fake, 8, None) == E_SHAPE
+    assert win(fake, 100, 4, 8, 100, None, fake, fake, fake, fake, None, fake, 8, None) == E_NULL        # grad_w is not optional
+    assert win(fake, 100, 4, 8, 100, None, fake, fake, fake, fake, fake, None, 0, None) == E_WORKSPACE
+    for name in ("odecol_brownian_query", "odecol_brownian_levy_query"):
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        extra = [ctypes.c_void_p] if name.endswith("levy_query") else []
+        fn.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
+                       ctypes.c_int32, ctypes.c_void_p] + extra + [ctypes.c_void_p]
+        tail = [fake] * len(extra) + [None]
+        assert fn(0, 0, 4, 0.0, 0.0, fake, 3, fake, *tail) == E_SHAPE                # empty span
+        assert fn(0, 0, 0, 0.0, 1.0, fake, 3, fake, *tail) == E_SHAPE
+        assert fn(0, 0, 4, 0.0, 1.0, None, 3, fake, *tail) == E_NULL
+    asrk = lib.odecol_srk_fwd_adaptive
+    asrk.restype = ctypes.c_int
+    asrk.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                     ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
+                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    assert asrk(ctypes.byref(big), fake, 10, fake, fake, 0, 0, 1e-3, 1e-5, 1e-4, 1e-5, None, None, None, None, 0, None) == E_UNSUPPORTED
+    assert asrk(ctypes.byref(p), fake, 10, fake, fake, 0, 0, 1e-3, 1e-5, 1e-4, 0.0, None, None, None, None, 0, None) == E_SHAPE
+    assert asrk(ctypes.byref(p), fake, 10, None, fake, 0, 0, 1e-3, 1e-5, 1e-4, 1e-5, None, None, None, None, 0, None) == E_NULL
+    rec = lib.odecol_dopri5_fwd_record
+    rec.restype = ctypes.c_int
+    rec.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                    ctypes.c_float, ctypes.c_int32] + [ctypes.c_void_p] * 8 + [ctypes.c_int32, ctypes.c_void_p, ctypes.c_size_t,
+                                                                            ctypes.c_void_p]
+    assert rec(ctypes.byref(big), fake, 10, fake, fake, 1e-7, 1e-9, 100, fake, fake, fake, fake, fake, fake, fake, fake, 64,
+               None, 0, None) == E_WORKSPACE                                            # staged record pass wants its workspace
+    assert rec(ctypes.byref(big), fake, 10, fake, fake, 1e-7, 1e-9, 100, fake, fake, fake, fake, fake, fake, fake, fake, 0,
+               None, 0, None) == E_SHAPE
+    dbw = lib.odecol_dopri5_bwd
+    dbw.restype = ctypes.c_int
+    dbw.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                                                ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                                                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                                                ctypes.c_void_p]
+    assert dbw(ctypes.byref(big), 10, fake, fake, fake, fake, fake, 64, fake, fake, None, 3 * 512, fake, fake, None, 0, None) == E_WORKSPACE
+    drift = lib.odecol_drift_staged
+    drift.restype = ctypes.c_int
+    drift.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    assert drift(ctypes.byref(big), fake, fake, fake, None, 0, None) == E_WORKSPACE
+    assert drift(ctypes.byref(big), fake, None, fake, None, 0, None) == E_NULL
     # bookkeeping helpers answer without a device
     wsb = lib.odecol_workspace_bytes
     wsb.restype = ctypes.c_size_t
@@ -163,6 +212,9 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert wsb(ctypes.byref(p), 1, 1500, 0) == 0                 # on-chip family: no workspace
     assert wsb(ctypes.byref(p), 7, 1500, 150) > 0                # srk reverse sweep: the step schedule
     assert wsb(ctypes.byref(_problem(B=0)), 1, 1500, 0) == 0
+    assert wsb(ctypes.byref(big), 8, 100, 0) > wsb(ctypes.byref(big), 3, 100, 0) > 0      # dopri5 reverse / forward, staged family
+    gain = _problem(N=512, n_in=64, ld_w=580, lat_gain=0x7F0000003000)
+    assert wsb(ctypes.byref(gain), 4, 3, 0) > wsb(ctypes.byref(big), 4, 3, 0)              # lateral-gain sweeps: two more planes
     fam = lib.odecol_kernel_family
     fam.restype = ctypes.c_int
     fam.argtypes = [ctypes.c_void_p, ctypes.c_int]
