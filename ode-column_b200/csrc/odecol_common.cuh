@@ -35,6 +35,44 @@ ODECOL_DEVINL void phi_dphi(float x, float& r, float& dr) {
     dr = 48.0f * (inv + r * inv * e * dzp);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fast, FP32-accurate (about 1e-7 relative) elementwise math (the staged families' epilogues; the on-chip family on request)
+// ---------------------------------------------------------------------------------------------------------------
+ODECOL_DEVINL float exp_fast(float x) {            // |x| < 87
+    const float n = rintf(x * 1.4426950408889634f);
+    float f = fmaf(n, -0.693145751953125f, x);
+    f = fmaf(n, -1.42860682030941723212e-6f, f);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f * 1.4426950408889634f));
+    return p * __int_as_float(((int)n + 127) << 23);
+}
+ODECOL_DEVINL float tanh_small(float u) {          // Taylor through u^11: < 3e-8 relative for |u| <= 0.4
+    if (fabsf(u) > 0.4f) {                         // never reached for physical states; kept small (no libdevice call)
+        const float e2 = exp_fast(fminf(2.0f * fabsf(u), 80.0f));
+        return copysignf(1.0f - __fdividef(2.0f, e2 + 1.0f), u);
+    }
+    const float s = u * u;
+    float p = fmaf(s, -8.8632355299021965e-3f, 2.1869488536155203e-2f);   // -1382/155925, 62/2835
+    p = fmaf(s, p, -5.3968253968253968e-2f);                               // -17/315
+    p = fmaf(s, p, 1.3333333333333333e-1f);                                // 2/15
+    p = fmaf(s, p, -3.3333333333333333e-1f);                               // -1/3
+    return fmaf(u * s, p, u);
+}
+ODECOL_DEVINL float phi_fast(float x) {
+    const float x_nom = fmaf(48.0f, x, -981.0f);
+    const float zc = 80.0f * tanh_small(x_nom * (-0.0089f / 80.0f));
+    return __fdividef(x_nom, 1.0f - exp_fast(zc));
+}
+
+ODECOL_DEVINL void phi_dphi_fast(float x, float& r, float& dr) {
+    const float x_nom = fmaf(48.0f, x, -981.0f);
+    const float th = tanh_small(x_nom * (-0.0089f / 80.0f));
+    const float e = exp_fast(80.0f * th);
+    const float inv = __fdividef(1.0f, 1.0f - e);
+    r = x_nom * inv;
+    dr = 48.0f * (inv + r * inv * e * (1.0f - th * th) * (-0.0089f));
+}
+
 // ---- stimulus lookup (reference src/utils.py:31-46) ------------------------------------------------------------
 // Finds idx in [1, K-1] with searchsorted(right=True) semantics starting from a hint; returns clamped time.
 ODECOL_DEVINL float knot_locate(const float* __restrict__ kt, int K, float t, int& idx) {

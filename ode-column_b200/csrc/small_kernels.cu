@@ -41,6 +41,17 @@ ODECOL_DEVINL bool block_any(bool flag) { return __syncthreads_or(flag ? 1 : 0) 
 // ---------------------------------------------------------------------------------------------------------------
 // per-thread right-hand side with the weight row in registers
 // ---------------------------------------------------------------------------------------------------------------
+// Transfer function of the on-chip family: the reference's operations in their order with IEEE division, tanhf and expf
+// (bit-faithful up to the last ulp of the two libm calls), or -- built with -DODECOL_SMALL_FAST_PHI -- the staged families'
+// fast path (1e-7 relative).  Measured (bench.py --workload small, A/B on one box): see DESIGN.md section 5.
+#ifdef ODECOL_SMALL_FAST_PHI
+ODECOL_DEVINL float small_phi(float x) { return phi_fast(x); }
+ODECOL_DEVINL void small_phi_dphi(float x, float& r, float& dr) { phi_dphi_fast(x, r, dr); }
+#else
+ODECOL_DEVINL float small_phi(float x) { return phi(x); }
+ODECOL_DEVINL void small_phi_dphi(float x, float& r, float& dr) { phi_dphi(x, r, dr); }
+#endif
+
 template <int KP>
 struct RowRhs {
     float w[KP];
@@ -106,7 +117,7 @@ struct RowRhs {
     }
 
     ODECOL_DEVINL void eval(float t, float V, float A, float F, float& dV, float& dA, float& dF) {
-        const float r = phi(__fsub_rn(V, A));
+        const float r = small_phi(__fsub_rn(V, A));
         const float tot = input(t, r);
         drift(c, V, A, F, r, kappa, tot, dV, dA, dF);
     }
@@ -275,7 +286,7 @@ struct BwdCtx {
 
     // forward stage: publishes r_aug into ra[stage], returns total input (needs_dot) ; r, dr out
     ODECOL_DEVINL float stage_fwd(int stage, float t, float V, float A, float& r, float& dr, bool needs_dot) {
-        phi_dphi(__fsub_rn(V, A), r, dr);
+        small_phi_dphi(__fsub_rn(V, A), r, dr);
         float* cur = ra_t + stage * KP;
         if (act) cur[li] = r;
         if (li < n_in) {
