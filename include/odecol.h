@@ -15,9 +15,11 @@
  *     adaptive ones (odecol_em_fwd with adaptive = 1, odecol_dopri5_fwd / _fwd_record) poll an "all trials finished"
  *     counter every 16 rounds; odecol_dopri5_bwd reads the accepted-step counts once.  None of them may be captured into
  *     a CUDA graph; everything else (the on-chip family, all rk4 entry points, the read-outs) may;
- *   - results are deterministic for a given problem and library build, except grad_W_aug of the tensor family (N >= 256):
- *     its reduction over trials uses float atomics, so repeated runs agree to float32 rounding (~1e-7 relative), not bit
- *     for bit;
+ *   - forward results (trajectories, step counts, read-outs' predictions) are bit-reproducible for a given problem,
+ *     library build and device.  Sums OVER TRIALS -- grad_W_aug, the scalar losses -- are bit-reproducible only in the
+ *     tensor family's rk4 reverse sweep (N >= 256, the benchmarked path: every (tile, row split) accumulates into its own
+ *     copy, the copies are summed in a fixed order); the other reverse sweeps and the read-out losses add per-trial
+ *     contributions with float / double atomics, so repeated runs agree to rounding (~1e-7 relative), not bit for bit;
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);

@@ -182,7 +182,10 @@ struct BwdEpiT {
 constexpr int DW_BK = 32;        // rows (trials) per K block = four 8-row swizzle atoms
 constexpr int DW_T = 128;        // output tile: 128 x 128
 struct DwShape { int MT, NT, Z, rows_per_split, total_rows, N, Kaug, ld_w; float* grad_W; uint32_t lbo, sbo, major_bits, kadv;
-                 int two_products; };     // 1: drop the A_hi . B_lo term and never stage B_lo (experiment, ODECOL_DW_2X=1)
+                 int two_products;        // 1: drop the A_hi . B_lo term and never stage B_lo (experiment, ODECOL_DW_2X=1)
+                 float* partial; };       // [Z][N][ld_w] or NULL: row split z accumulates into its OWN copy with plain
+                                          // read-modify-writes (one CTA per (tile, z) and launch, launches stream-ordered), summed
+                                          // over z in a fixed order at the end of the sweep -- bit-reproducible, no float atomics
 ODECOL_DEVINL uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -806,16 +809,34 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * set);
         }
+        if (ds.partial) {
+            float* dst = ds.partial + (size_t)z * ds.N * ds.ld_w;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const int k = k0 + g * 32 + q;
-            if (i < ds.N && k < ds.Kaug) atomicAdd(ds.grad_W + (size_t)i * ds.ld_w + k, acc[q]);
+            for (int q = 0; q < 32; ++q) {
+                const int k = k0 + g * 32 + q;
+                if (i < ds.N && k < ds.Kaug) dst[(size_t)i * ds.ld_w + k] += acc[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int k = k0 + g * 32 + q;
+                if (i < ds.N && k < ds.Kaug) atomicAdd(ds.grad_W + (size_t)i * ds.ld_w + k, acc[q]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// grad_W[e] = sum_z partial[z][e] in the fixed order z = 0, 1, ... (the deterministic end of the dW reduction)
+__global__ void k_dw_reduce_partials(const float* __restrict__ partial, int Z, size_t n, float* __restrict__ grad_W) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < Z; ++z) s += partial[(size_t)z * n + e];
+        grad_W[e] = s;
     }
 }
 
@@ -943,10 +964,15 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
 }
 
 // launches the dW contraction (pair variant when enabled and the tile count allows)
-static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const DwShape& ds, cudaStream_t s) {
+static bool dw_pair_enabled() {
     static int use_pair = -1;
     if (use_pair < 0) { const char* e = getenv("ODECOL_DW_PAIR"); use_pair = e ? (atoi(e) != 0) : 0; }
+    return use_pair != 0;
+}
+
+static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const DwShape& ds, cudaStream_t s) {
+    const bool use_pair = dw_pair_enabled();
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(k_tc_dw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
@@ -985,7 +1011,8 @@ __global__ void k_split_pad_T(const float* __restrict__ src, int n, int ld, floa
 struct TcBwdLayout {
     int Np, Bp, KPa, NPk, TN;
     size_t off_Whi, off_Wlo, off_WThi, off_WTlo, off_Rhi, off_Rlo, off_AVhi, off_AVlo;   // stacked x4 operand buffers
-    size_t off_K[3], off_Y, off_RT[3], off_DRT[8], off_lam, off_b4, off_b3, off_acur, off_inv, off_done, total;
+    size_t off_K[3], off_Y, off_RT[3], off_DRT[8], off_lam, off_b4, off_b3, off_acur, off_inv, off_done, off_dwpart, total;
+    int dwZ;
 };
 
 static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
@@ -1011,6 +1038,14 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     L.off_lam = take(3 * plane); L.off_b4 = take(2 * plane); L.off_b3 = take(2 * plane); L.off_acur = take(2 * plane);
     L.off_inv = take(sizeof(int) * (3ull * p.N + 4));      // + the "an F component is selected" flag
     L.off_done = take(sizeof(unsigned int) * (size_t)(L.Bp / L.TN) + 256);
+    // per-row-split copies of grad_W_aug (deterministic dW reduction): the split count of the one-wave dW launch
+    {
+        const int tiles = (L.Np / DW_T) * ((L.KPa + DW_T - 1) / DW_T);
+        int z = num_sms() / tiles;
+        if (z < 1) z = 1;
+        L.dwZ = z;
+        L.off_dwpart = take(4ull * (size_t)z * p.N * p.ld_w);
+    }
     L.total = o;
     return L;
 }
@@ -1043,7 +1078,7 @@ int tc_contract_tn(const float* A, const float* B, float* C, int M, int N, int K
     int z = 2;
     int rows = (Kp / DW_BK + z - 1) / z * DW_BK;
     ds.rows_per_split = rows; ds.Z = (Kp + rows - 1) / rows;
-    ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C; ds.two_products = 0;
+    ds.N = M; ds.Kaug = N; ds.ld_w = N; ds.grad_W = C; ds.two_products = 0; ds.partial = nullptr;
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
     if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s) != cudaSuccess) return ODECOL_E_CUDA;
     count_launch(2);
@@ -1068,7 +1103,7 @@ int tc_dw_accumulate(const float* Ahi, const float* Alo, const float* Bhi, const
     int rps = (rows / DW_BK + z - 1) / z * DW_BK;
     if (rps < DW_BK) rps = DW_BK;
     ds.rows_per_split = rps; ds.Z = (rows + rps - 1) / rps;
-    ds.N = N; ds.Kaug = Kaug; ds.ld_w = ld_w; ds.grad_W = grad_W; ds.two_products = 0;
+    ds.N = N; ds.Kaug = Kaug; ds.ld_w = ld_w; ds.grad_W = grad_W; ds.two_products = 0; ds.partial = nullptr;
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
     return launch_dw(a_hi, a_lo, b_hi, b_lo, ds, s);
 }
@@ -1143,6 +1178,7 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     { const char* e2 = getenv("ODECOL_DW_2X"); ds.two_products = e2 ? (atoi(e2) != 0) : 0; }    // fails the gradient bar: experiment only
 #endif
     ds.lbo = DW_BK * 128; ds.sbo = 512; ds.major_bits = (1u << 15) | (1u << 16); ds.kadv = 1024;
+    ds.partial = nullptr;
 
     const int MT = L.Np / BM, NT = L.Bp / L.TN;
     // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
@@ -1152,6 +1188,15 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // par with the default (separate launch + replay one step ahead): profiles/r1_session2.md section 5.
     const char* fe = getenv("ODECOL_FUSE_DW");
     const bool fuse_dw = use_chain && (fe ? atoi(fe) != 0 : false);
+    // default dW path: every (output tile, row split) accumulates into its own copy of grad_W_aug across the whole sweep (plain
+    // read-modify-write: one CTA per (tile, split) and launch, launches ordered on the stream), the copies are summed in a
+    // fixed order at the end -- the gradient is bit-reproducible.  The opt-in variants (pair, fused) keep float atomics.
+    float* dw_partial = nullptr;
+    if (!fuse_dw && !(dw_pair_enabled() && ds.MT % 2 == 0) && ds.Z <= L.dwZ) {
+        dw_partial = reinterpret_cast<float*>(w + L.off_dwpart);
+        if (cudaMemsetAsync(dw_partial, 0, sizeof(float) * (size_t)ds.Z * p.N * p.ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
+        ds.partial = dw_partial;
+    }
     const size_t chain_stage = 2 * BM * BK * 4 + 2 * (size_t)L.TN * BK * 4, dw_stage_b = 4 * 4 * DW_BK * 128;
     const size_t chain_smem = (size_t)STAGES * (fuse_dw && dw_stage_b > chain_stage ? dw_stage_b : chain_stage) + 1024;
     int chain_grid = MT * NT < num_sms() ? MT * NT : num_sms();
@@ -1277,6 +1322,10 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
         if (overlap) cudaEventRecord(ev_dw, s);
     }
     // every replay has been awaited by the caller's stream; side_guard releases the stream and the events
+    if (dw_partial) {
+        k_dw_reduce_partials<<<296, 256, 0, s>>>(dw_partial, ds.Z, (size_t)p.N * p.ld_w, grad_W);
+        count_launch();
+    }
     if (grad_y0) {
         k_tc_untile<<<L.Bp / 4, 128, 0, s>>>(p, tg, lamT, grad_y0);
         count_launch();
