@@ -1192,7 +1192,12 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // read-modify-write: one CTA per (tile, split) and launch, launches ordered on the stream), the copies are summed in a
     // fixed order at the end -- the gradient is bit-reproducible.  The opt-in variants (pair, fused) keep float atomics.
     float* dw_partial = nullptr;
-    if (!fuse_dw && !(dw_pair_enabled() && ds.MT % 2 == 0) && ds.Z <= L.dwZ) {
+#ifdef ODECOL_DW_ATOMIC
+    const bool dw_fixed_order = false;              // comparison build: float atomics straight into grad_W_aug
+#else
+    const bool dw_fixed_order = true;
+#endif
+    if (dw_fixed_order && !fuse_dw && !(dw_pair_enabled() && ds.MT % 2 == 0) && ds.Z <= L.dwZ) {
         dw_partial = reinterpret_cast<float*>(w + L.off_dwpart);
         if (cudaMemsetAsync(dw_partial, 0, sizeof(float) * (size_t)ds.Z * p.N * p.ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
         ds.partial = dw_partial;
