@@ -789,8 +789,14 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
         const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
         float acc[32];
+        // fixed-order reduction: the running sum of this (tile, split) is fetched up front -- its latency hides behind the
+        // contraction -- and stored back with the new contribution at the end (no read-modify-write in the kernel's tail)
+        float* dst = ds.partial ? ds.partial + (size_t)z * ds.N * ds.ld_w : nullptr;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+        for (int q = 0; q < 32; ++q) {
+            const int k = k0 + g * 32 + q;
+            acc[q] = (dst && i < ds.N && k < ds.Kaug) ? __ldcg(dst + (size_t)i * ds.ld_w + k) : 0.f;
+        }
         for (int c = 0; c < nchunks; ++c) {
             const int set = c & 1;
             mbar_wait(tfull0 + 8 * set, (uint32_t)((c >> 1) & 1));
@@ -809,12 +815,11 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * set);
         }
-        if (ds.partial) {
-            float* dst = ds.partial + (size_t)z * ds.N * ds.ld_w;
+        if (dst) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
                 const int k = k0 + g * 32 + q;
-                if (i < ds.N && k < ds.Kaug) dst[(size_t)i * ds.ld_w + k] += acc[q];
+                if (i < ds.N && k < ds.Kaug) dst[(size_t)i * ds.ld_w + k] = acc[q];
             }
         } else {
 #pragma unroll
