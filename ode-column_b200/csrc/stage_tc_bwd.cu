@@ -552,20 +552,31 @@ __global__ void k_tc_step_begin(DevProblem p, TileGeom tg, const float* __restri
 }
 
 // checkpoint mode: every stage operand and phi' of step n from the saved V/A state and V slopes -- the forward stage
-// recurrences of FwdEpiT, elementwise, no contraction.  One CTA per group of four trials, threads over populations.
-__global__ void k_tc_replay(DevProblem p, TileGeom tg, const float* __restrict__ VA, const float* __restrict__ KV,
-                            const float* __restrict__ t, int n, float* __restrict__ Rhi, float* __restrict__ Rlo,
-                            size_t rstride, float* __restrict__ D0, float* __restrict__ D1, float* __restrict__ D2,
-                            float* __restrict__ D3, int KPa) {
-    const int b4 = blockIdx.x * 4, N = p.N;
+// recurrences of FwdEpiT, elementwise, no contraction.  Work unit = (group of four trials, slice of 128 populations), done by
+// 128 threads: the stand-alone kernel below walks all slices of one trial group per CTA; the dW contraction kernel hands
+// units of the NEXT step to its epilogue warps, which idle between accumulator drains (ReplayJob).
+struct ReplayJob {
+    int valid;                 // 0: nothing to replay
+    DevProblem p; TileGeom tg;
+    const float* VA; const float* KV; const float* t;
+    int n, KPa, nblocks, slices;             // step, operand row length, trial groups (Bp / 4), population slices (Np / 128)
+    float* Rhi; float* Rlo; size_t rstride;  // four stacked operand buffers of the step's set
+    float* D[4];                             // phi' planes of the step's set
+};
+
+ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) {
+    const DevProblem& p = j.p;
+    const TileGeom& tg = j.tg;
+    const int b4 = blk * 4, N = p.N;
     const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
     const size_t pl = tg.plane();
-    const float t0 = __ldg(t + n), t1 = __ldg(t + n + 1), dt = __fsub_rn(t1, t0);
+    const float t0 = __ldg(j.t + j.n), t1 = __ldg(j.t + j.n + 1), dt = __fsub_rn(t1, t0);
     const float third = kOneThirdL, inv_ta = 1.0f / p.c.tau_a;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int i = slice * 128 + tid;
+    if (i < N) {
         const size_t o = tg.off(nt, g, q, i);
-        const float4 V0 = ld4s(VA + o), A0 = ld4s(VA + pl + o);
-        const float4 k1V = ld4s(KV + o), k2V = ld4s(KV + pl + o), k3V = ld4s(KV + 2 * pl + o);
+        const float4 V0 = ld4s(j.VA + o), A0 = ld4s(j.VA + pl + o);
+        const float4 k1V = ld4s(j.KV + o), k2V = ld4s(j.KV + pl + o), k3V = ld4s(j.KV + 2 * pl + o);
         const float kap = __ldg(p.kappa + i);
         float R[4][4], D[4][4];
 #pragma unroll
@@ -582,23 +593,22 @@ __global__ void k_tc_replay(DevProblem p, TileGeom tg, const float* __restrict__
             nV = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]); nA = a0 + dt * (k1A - k2A + k3A);
             phi_dphi_fast(nV - nA, R[3][e], D[3][e]);
         }
-        st4s(D0 + o, make_float4(D[0][0], D[0][1], D[0][2], D[0][3]));
-        st4s(D1 + o, make_float4(D[1][0], D[1][1], D[1][2], D[1][3]));
-        st4s(D2 + o, make_float4(D[2][0], D[2][1], D[2][2], D[2][3]));
-        st4s(D3 + o, make_float4(D[3][0], D[3][1], D[3][2], D[3][3]));
+#pragma unroll
+        for (int s = 0; s < 4; ++s) st4s(j.D[s] + o, make_float4(D[s][0], D[s][1], D[s][2], D[s][3]));
 #pragma unroll
         for (int s = 0; s < 4; ++s)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (b4 + e < p.B) {
                     const float h = tf32_rna(R[s][e]);
-                    const size_t at = s * rstride + (size_t)(b4 + e) * KPa + i;
-                    Rhi[at] = h; Rlo[at] = tf32_rna(R[s][e] - h);
+                    const size_t at = s * j.rstride + (size_t)(b4 + e) * j.KPa + i;
+                    j.Rhi[at] = h; j.Rlo[at] = tf32_rna(R[s][e] - h);
                 }
     }
+    if (slice != 0) return;
     // stimulus channels at the four stage times (the constant-one column is set once per sweep)
     const int n_in = p.n_in;
-    for (int e = threadIdx.x; e < 16 * n_in; e += blockDim.x) {
+    for (int e = tid; e < 16 * n_in; e += 128) {
         const int s = e / (4 * n_in), b = b4 + (e / n_in) % 4, ch = e % n_in;
         if (b >= p.B) continue;
         const float ts = s == 0 ? t0 : s == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : s == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
@@ -606,9 +616,14 @@ __global__ void k_tc_replay(DevProblem p, TileGeom tg, const float* __restrict__
         const float tcl = knot_locate(p.knot_t, p.K, ts, idx);
         const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
         const float h = tf32_rna(v);
-        const size_t at = s * rstride + (size_t)b * KPa + N + ch;
-        Rhi[at] = h; Rlo[at] = tf32_rna(v - h);
+        const size_t at = s * j.rstride + (size_t)b * j.KPa + N + ch;
+        j.Rhi[at] = h; j.Rlo[at] = tf32_rna(v - h);
     }
+}
+
+// stand-alone: one CTA of 128 threads per group of four trials
+__global__ void __launch_bounds__(128) k_tc_replay(ReplayJob j) {
+    for (int slice = 0; slice < j.slices; ++slice) replay_unit(j, blockIdx.x, slice, threadIdx.x);
 }
 
 // lam = dL/dy_out[T-1] (tile-major), kbar_4 of the last step, its operand
@@ -699,7 +714,8 @@ constexpr int DW_CHUNK = ODECOL_DW_CHUNK;
 template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
-        const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds) {
+        const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds,
+        const __grid_constant__ ReplayJob rj) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_slot;
@@ -785,9 +801,17 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 if (kb % DW_CHUNK == DW_CHUNK - 1 || kb == KB - 1) { umma_commit(tfull0 + 8 * (c & 1)); ++c; }
             }
         }
-    } else if (KB > 0) {
+    } else {
         const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
+        // The epilogue warps only drain an accumulator set every DW_CHUNK K blocks; in between, each group of four warps (128
+        // threads) replays units of the NEXT reverse step (rj): elementwise work that needs nothing but the checkpoints and
+        // writes the other operand / phi' set, so it overlaps this contraction instead of running as a kernel of its own
+        // (which cannot share an SM with the 576-thread contraction CTAs: they hold the whole register file).
+        const int rtid = (ew & 3) * 32 + lane;
+        const int rtotal = rj.valid ? rj.nblocks * rj.slices : 0;
+        const int rstep = (int)gridDim.x * 4;
+        int ru = (int)blockIdx.x * 4 + g;
         float acc[32];
         // fixed-order reduction: the running sum of this (tile, split) is fetched up front -- its latency hides behind the
         // contraction -- and stored back with the new contribution at the end (no read-modify-write in the kernel's tail)
@@ -814,7 +838,9 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+            if (ru < rtotal) { replay_unit(rj, ru / rj.slices, ru % rj.slices, rtid); ru += rstep; }
         }
+        for (; ru < rtotal; ru += rstep) replay_unit(rj, ru / rj.slices, ru % rj.slices, rtid);
         if (dst) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
@@ -975,8 +1001,12 @@ static bool dw_pair_enabled() {
     return use_pair != 0;
 }
 
+// rj: replay units of the next reverse step for the epilogue warps (k_tc_dw only; *rj_done says whether they were taken)
 static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const DwShape& ds, cudaStream_t s) {
+                     const DwShape& ds, cudaStream_t s, const ReplayJob* rj = nullptr, bool* rj_done = nullptr) {
+    ReplayJob none;
+    none.valid = 0;
+    if (rj_done) *rj_done = false;
     const bool use_pair = dw_pair_enabled();
     static bool configured = false;
     if (!configured) {
@@ -990,9 +1020,13 @@ static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
         const int pairs = (ds.MT / 2) * ds.NT * ds.Z;
         k_tc_dw_pair<<<2 * pairs, kThreads, (size_t)DW_PSTAGES * (2 * 4 + 2 * 2) * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
     } else if (ds.two_products) {
-        k_tc_dw<true><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+        k_tc_dw<true><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds,
+                                                                                                       rj ? *rj : none);
+        if (rj_done) *rj_done = rj != nullptr;
     } else {
-        k_tc_dw<false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
+        k_tc_dw<false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds,
+                                                                                                        rj ? *rj : none);
+        if (rj_done) *rj_done = rj != nullptr;
     }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
@@ -1032,7 +1066,7 @@ static TcBwdLayout tc_bwd_layout(const DevProblem& p) {
     L.off_Whi = take(4ull * L.Np * L.KPa); L.off_Wlo = take(4ull * L.Np * L.KPa);
     L.off_WThi = take(4ull * L.Np * L.NPk); L.off_WTlo = take(4ull * L.Np * L.NPk);
     // two sets of the four stacked r_aug operands and of the four phi' planes: in checkpoint mode the replay of step
-    // n-1 (side stream) fills one set while the reverse stages and the dW contraction of step n read the other
+    // n-1 (done by the dW contraction kernel of step n) fills one set while the reverse stages of step n and that contraction read the other
     L.off_Rhi = take(32ull * L.Bp * L.KPa); L.off_Rlo = take(32ull * L.Bp * L.KPa);
     L.off_AVhi = take(32ull * L.Bp * L.NPk); L.off_AVlo = take(32ull * L.Bp * L.NPk);     // two sets of four slots
     const size_t plane = 4ull * L.Np * L.Bp;
@@ -1218,49 +1252,34 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             use_chain = false;
     }
     // Checkpoint mode: the replay of a step needs nothing but the checkpoints, so it runs one step AHEAD of the
-    // contractions on a side stream, into the other operand / phi' set: replay(n-1) overlaps the reverse stages and the
-    // dW contraction of step n (it fits next to their CTAs: 8 K registers and no shared memory per CTA).
-    //   side: wait(dW(n+1) done) -> replay(n-1) -> record          main: wait(replay(n) done) -> chain(n) -> dW(n) -> record
-    // ODECOL_OVERLAP=0 keeps everything on the caller's stream.
+    // contractions, into the other operand / phi' set -- INSIDE the dW contraction of the step before: its epilogue warps
+    // idle between accumulator drains and take the replay's units (k_tc_dw / ReplayJob).  A kernel of its own cannot
+    // overlap anything here: the 576-thread contraction CTAs hold an SM's whole register file, so a side-stream replay ran
+    // in the gaps between launches only (measured: ODECOL_OVERLAP=0 changed nothing; replay alone 81 us per step).
+    // ODECOL_OVERLAP=0 replays every step as a launch of its own on the caller's stream.
     const char* ov = getenv("ODECOL_OVERLAP");
-    bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : true);
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_replay = nullptr, ev_dw = nullptr;
-    struct SideGuard {                               // released on every return path (work already enqueued completes first)
-        cudaStream_t& st; cudaEvent_t& a; cudaEvent_t& b;
-        ~SideGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); if (st) cudaStreamDestroy(st); }
-    } side_guard{side, ev_replay, ev_dw};
-    if (overlap) {
-        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_replay, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_dw, cudaEventDisableTiming) != cudaSuccess) {
-            if (side) cudaStreamDestroy(side);
-            if (ev_replay) cudaEventDestroy(ev_replay);
-            if (ev_dw) cudaEventDestroy(ev_dw);
-            cudaGetLastError();
-            side = nullptr; ev_replay = ev_dw = nullptr; overlap = false;
-        }
-    }
+    const bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : true);
     const size_t ckpl = (size_t)L.Np * L.Bp;
-    auto replay = [&](int n, cudaStream_t st_) {
+    auto replay_job = [&](int n) {
+        ReplayJob j;
         const int rs = overlap ? (n & 1) : 0;
-        k_tc_replay<<<L.Bp / 4, 128, 0, st_>>>(p, tg, ckVA + 2 * ckpl * (size_t)n, ckK + 3 * ckpl * (size_t)n, t_dev, n,
-                                               Rhi + (size_t)rs * 4 * rstride, Rlo + (size_t)rs * 4 * rstride, rstride,
-                                               DRT[4 * rs + 0], DRT[4 * rs + 1], DRT[4 * rs + 2], DRT[4 * rs + 3], L.KPa);
+        j.valid = 1; j.p = p; j.tg = tg;
+        j.VA = ckVA + 2 * ckpl * (size_t)n; j.KV = ckK + 3 * ckpl * (size_t)n; j.t = t_dev;
+        j.n = n; j.KPa = L.KPa; j.nblocks = L.Bp / 4; j.slices = L.Np / 128;
+        j.Rhi = Rhi + (size_t)rs * 4 * rstride; j.Rlo = Rlo + (size_t)rs * 4 * rstride; j.rstride = rstride;
+        for (int k = 0; k < 4; ++k) j.D[k] = DRT[4 * rs + k];
+        return j;
+    };
+    auto replay = [&](int n) {
+        k_tc_replay<<<L.Bp / 4, 128, 0, s>>>(replay_job(n));
         count_launch();
     };
-    if (overlap) {                                   // setup on the caller's stream first, then the first replay
-        cudaEventRecord(ev_dw, s);
-        cudaStreamWaitEvent(side, ev_dw, 0);
-        replay(T - 2, side);
-        cudaEventRecord(ev_replay, side);
-    }
+    bool replayed_ahead = false;                     // step n's operands were produced inside dW(n+1)
     for (int n = T - 2; n >= 0; --n) {
         int rc = ODECOL_OK;
         const int rset = overlap ? (n & 1) : 0;      // operand / phi' set of this step
         if (ckVA) {
-            if (overlap) cudaStreamWaitEvent(s, ev_replay, 0);
-            else replay(n, s);
+            if (!replayed_ahead) replay(n);
         } else {
         const float* yn = y_traj + (size_t)n * st;
         k_tc_step_begin<<<L.Bp / 4, 128, 0, s>>>(p, tg, yn, t_dev + n, Rhi, Rlo, YT, RT[0], DRT[0], L.KPa);
@@ -1320,18 +1339,15 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
             { BwdEpiT<2> e; fill_b(e, 2); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 1 * L.Bp, nullptr}, e, s); if (rc) return rc; }
             { BwdEpiT<1> e; fill_b(e, 1); rc = launch_contract(mWThi, mWTlo, mAVhi, mAVlo, TileShape{MT, NT, L.TN, L.NPk / BK, r0 + 0 * L.Bp, nullptr}, e, s); if (rc) return rc; }
         }
-        if (overlap && n > 0) {                      // replay(n-1) may start once dW(n+1) has released its set
-            cudaStreamWaitEvent(side, ev_dw, 0);
-            replay(n - 1, side);
-            cudaEventRecord(ev_replay, side);
-        }
+        replayed_ahead = false;
         if (!(use_chain && fuse_dw) && !(dbg_skip & 1)) {
-            const int rcd = launch_dw(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds, s);
+            ReplayJob next;
+            const bool ahead = overlap && n > 0;      // replay(n-1) into the other set, inside this step's dW contraction
+            if (ahead) next = replay_job(n - 1);
+            const int rcd = launch_dw(dAhi[set], dAlo[set], dBhi[rset], dBlo[rset], ds, s, ahead ? &next : nullptr, &replayed_ahead);
             if (rcd) return rcd;
         }
-        if (overlap) cudaEventRecord(ev_dw, s);
     }
-    // every replay has been awaited by the caller's stream; side_guard releases the stream and the events
     if (dw_partial) {
         k_dw_reduce_partials<<<296, 256, 0, s>>>(dw_partial, ds.Z, (size_t)p.N * p.ld_w, grad_W);
         count_launch();
