@@ -564,19 +564,32 @@ struct ReplayJob {
     float* D[4];                             // phi' planes of the step's set
 };
 
-ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) {
-    const DevProblem& p = j.p;
+// the checkpoint values one thread needs for one unit: loaded ahead of their use where the caller pipelines units
+struct ReplayLoad { float4 V0, A0, k1V, k2V, k3V; };
+
+ODECOL_DEVINL size_t replay_offset(const ReplayJob& j, int blk, int i) {
+    const int b4 = blk * 4;
     const TileGeom& tg = j.tg;
+    return tg.off(b4 / tg.TN, (b4 % tg.TN) / tg.TNq, ((b4 % tg.TN) % tg.TNq) >> 2, i);
+}
+
+ODECOL_DEVINL void replay_load(const ReplayJob& j, int blk, int slice, int tid, ReplayLoad& L) {
+    const int i = slice * 128 + tid;
+    if (i >= j.p.N) return;
+    const size_t o = replay_offset(j, blk, i), pl = j.tg.plane();
+    L.V0 = ld4s(j.VA + o); L.A0 = ld4s(j.VA + pl + o);
+    L.k1V = ld4s(j.KV + o); L.k2V = ld4s(j.KV + pl + o); L.k3V = ld4s(j.KV + 2 * pl + o);
+}
+
+ODECOL_DEVINL void replay_compute(const ReplayJob& j, int blk, int slice, int tid, const ReplayLoad& L) {
+    const DevProblem& p = j.p;
     const int b4 = blk * 4, N = p.N;
-    const int nt = b4 / tg.TN, g = (b4 % tg.TN) / tg.TNq, q = ((b4 % tg.TN) % tg.TNq) >> 2;
-    const size_t pl = tg.plane();
     const float t0 = __ldg(j.t + j.n), t1 = __ldg(j.t + j.n + 1), dt = __fsub_rn(t1, t0);
     const float third = kOneThirdL, inv_ta = 1.0f / p.c.tau_a;
     const int i = slice * 128 + tid;
     if (i < N) {
-        const size_t o = tg.off(nt, g, q, i);
-        const float4 V0 = ld4s(j.VA + o), A0 = ld4s(j.VA + pl + o);
-        const float4 k1V = ld4s(j.KV + o), k2V = ld4s(j.KV + pl + o), k3V = ld4s(j.KV + 2 * pl + o);
+        const size_t o = replay_offset(j, blk, i);
+        const float4 &V0 = L.V0, &A0 = L.A0, &k1V = L.k1V, &k2V = L.k2V, &k3V = L.k3V;
         const float kap = __ldg(p.kappa + i);
         float R[4][4], D[4][4];
 #pragma unroll
@@ -619,6 +632,12 @@ ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) 
         const size_t at = s * j.rstride + (size_t)b * j.KPa + N + ch;
         j.Rhi[at] = h; j.Rlo[at] = tf32_rna(v - h);
     }
+}
+
+ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) {
+    ReplayLoad L;
+    replay_load(j, blk, slice, tid, L);
+    replay_compute(j, blk, slice, tid, L);
 }
 
 // stand-alone: one CTA of 128 threads per group of four trials
@@ -812,6 +831,15 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
         const int rtotal = rj.valid ? rj.nblocks * rj.slices : 0;
         const int rstep = (int)gridDim.x * 4;
         int ru = (int)blockIdx.x * 4 + g;
+        ReplayLoad rl;                                // the next unit's checkpoint values, in flight while this one is processed
+        if (ru < rtotal) replay_load(rj, ru / rj.slices, ru % rj.slices, rtid, rl);
+        auto replay_next = [&]() {
+            const ReplayLoad cur = rl;
+            const int u = ru;
+            ru += rstep;
+            if (ru < rtotal) replay_load(rj, ru / rj.slices, ru % rj.slices, rtid, rl);
+            replay_compute(rj, u / rj.slices, u % rj.slices, rtid, cur);
+        };
         float acc[32];
         // fixed-order reduction: the running sum of this (tile, split) is fetched up front -- its latency hides behind the
         // contraction -- and stored back with the new contribution at the end (no read-modify-write in the kernel's tail)
@@ -838,9 +866,9 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * set);
-            if (ru < rtotal) { replay_unit(rj, ru / rj.slices, ru % rj.slices, rtid); ru += rstep; }
+            if (ru < rtotal) replay_next();
         }
-        for (; ru < rtotal; ru += rstep) replay_unit(rj, ru / rj.slices, ru % rj.slices, rtid);
+        while (ru < rtotal) replay_next();
         if (dst) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
