@@ -274,7 +274,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
         mbar_init(tempty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -283,7 +283,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int q = 0; q < 4; ++q) {                       // q = 0..3  <->  S = 4..1, operand slot 3 - q
@@ -349,7 +349,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(ts.TN);
             const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
@@ -413,7 +413,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
             }
         }
     } else {
-        const int ew = warp - 2;
+        const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int g = ew >> 2;
         const int etid = ew * 32 + lane;
@@ -499,7 +499,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
@@ -759,7 +759,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
         for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -768,7 +768,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < KB; ++kb) {
@@ -786,7 +786,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             // c=F32, a=b=TF32, both MN-major (bits 15, 16), N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
@@ -821,7 +821,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             }
         }
     } else {
-        const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
+        const int ew = warp - kEpiWarp0, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
         // The epilogue warps only drain an accumulator set every DW_CHUNK K blocks; in between, each group of four warps (128
         // threads) replays units of the NEXT reverse step (rj): elementwise work that needs nothing but the checkpoints and
@@ -885,7 +885,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
@@ -935,7 +935,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
@@ -944,7 +944,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < KB; ++kb) {
@@ -966,7 +966,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
                 if (++stage == DW_PSTAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0 && rank == 0) {
             // c = F32, a = b = TF32, both MN-major, N = 128, M = 256 across the pair
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ds.major_bits |
@@ -994,7 +994,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
             umma_commit_pair(tfull);
         }
     } else if (KB > 0) {
-        const int ew = warp - 2, quarter = warp & 3, g = ew >> 2;
+        const int ew = warp - kEpiWarp0, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
         mbar_wait(tfull, 0);
         tc_fence_after();
@@ -1017,7 +1017,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
     }
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
@@ -1284,9 +1284,13 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // idle between accumulator drains and take the replay's units (k_tc_dw / ReplayJob).  A kernel of its own cannot
     // overlap anything here: the 576-thread contraction CTAs hold an SM's whole register file, so a side-stream replay ran
     // in the gaps between launches only (measured: ODECOL_OVERLAP=0 changed nothing; replay alone 81 us per step).
-    // ODECOL_OVERLAP=0 replays every step as a launch of its own on the caller's stream.
+    // Default: every step's replay is a launch of its own on the caller's stream.
+    // MEASURED (round 2, one box): reverse sweep 632-641 ms with the replay as its own launch per step, 685 ms with the replay
+    // inside the dW contraction, 721 ms with its loads pipelined there -- the sixteen epilogue warps' arithmetic delays the two
+    // single-thread issue loops of the contraction more than the saved launch is worth.  Hence OFF by default
+    // (ODECOL_OVERLAP=1 turns it on).
     const char* ov = getenv("ODECOL_OVERLAP");
-    const bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : true);
+    const bool overlap = ckVA != nullptr && (ov ? atoi(ov) != 0 : false);
     const size_t ckpl = (size_t)L.Np * L.Bp;
     auto replay_job = [&](int n) {
         ReplayJob j;

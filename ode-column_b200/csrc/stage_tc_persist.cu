@@ -95,7 +95,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
         mbar_init(tempty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -104,7 +104,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int q = 0; q < n_seq; ++q) {
@@ -133,7 +133,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(ts.TN);
             const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
@@ -165,7 +165,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
             }
         }
     } else {
-        const int ew = warp - 2;
+        const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int g = ew >> 2;
         const int etid = ew * 32 + lane;
@@ -221,7 +221,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
