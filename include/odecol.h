@@ -16,10 +16,9 @@
  *     counter every 16 rounds; odecol_dopri5_bwd reads the accepted-step counts once.  None of them may be captured into
  *     a CUDA graph; everything else (the on-chip family, all rk4 entry points, the read-outs) may;
  *   - forward results (trajectories, step counts, read-outs' predictions) are bit-reproducible for a given problem,
- *     library build and device.  Sums OVER TRIALS -- grad_W_aug, the scalar losses -- are bit-reproducible only in the
- *     tensor family's rk4 reverse sweep (N >= 256, the benchmarked path: every (tile, row split) accumulates into its own
- *     copy, the copies are summed in a fixed order); the other reverse sweeps and the read-out losses add per-trial
- *     contributions with float / double atomics, so repeated runs agree to rounding (~1e-7 relative), not bit for bit;
+ *     library build and device.  Sums OVER TRIALS -- grad_W_aug, the scalar losses -- add per-trial contributions with
+ *     float / double atomics, so repeated runs agree to rounding (~1e-7 relative), not bit for bit; the tensor family's rk4
+ *     reverse sweep (N >= 256, the benchmarked path) reduces in a fixed order when ODECOL_FLAG_DETERMINISTIC is set;
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
@@ -71,7 +70,10 @@ enum {
 enum {
     ODECOL_FLAG_FORCE_STAGED = 1,  /* use the staged (global-state) FP32-FFMA kernel family even when the
                                       problem fits the persistent on-chip family; for testing and measurement */
-    ODECOL_FLAG_FORCE_TENSOR = 2   /* use the staged tcgen05 (3xTF32) family regardless of size               */
+    ODECOL_FLAG_FORCE_TENSOR = 2,  /* use the staged tcgen05 (3xTF32) family regardless of size               */
+    ODECOL_FLAG_DETERMINISTIC = 4  /* tensor family, rk4 reverse sweep: reduce grad_W_aug over trials in a fixed order
+                                      (per-split copies summed at the end) instead of float atomics: bit-reproducible
+                                      gradients for ~2 % of the sweep's time                                      */
 };
 
 /* operations, for odecol_workspace_bytes() */

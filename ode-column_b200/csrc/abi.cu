@@ -17,7 +17,7 @@ static int to_dev(const odecol_problem* p, DevProblem& d) {
     if (p->N <= 0 || p->B <= 0 || p->n_in < 0 || p->K < 2) return ODECOL_E_SHAPE;
     if (p->ld_w < p->N + p->n_in + 1 || (p->ld_w & 3)) return ODECOL_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(p->W_aug) & 15) || (reinterpret_cast<uintptr_t>(p->kappa) & 15)) return ODECOL_E_ALIGN;
-    d.N = p->N; d.n_in = p->n_in; d.B = p->B; d.K = p->K; d.ld_w = p->ld_w;
+    d.N = p->N; d.n_in = p->n_in; d.B = p->B; d.K = p->K; d.ld_w = p->ld_w; d.flags = p->flags;
     d.W_aug = p->W_aug; d.kappa = p->kappa; d.sigma = p->sigma; d.sigma_scale = p->sigma_scale; d.lat_gain = p->lat_gain; d.W_local = p->lat_gain ? p->W_local : nullptr; d.knot_t = p->knot_t; d.knot_u = p->knot_u;
     d.knot_stride_b = p->knot_stride_b;
     d.c.tau_s = p->tau_s; d.c.tau_m = p->tau_m; d.c.tau_a = p->tau_a; d.c.R = p->resistance;

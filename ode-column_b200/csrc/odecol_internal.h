@@ -14,6 +14,7 @@ struct Consts {
 // device-side copy of odecol_problem (passed by value to kernels)
 struct DevProblem {
     int N, n_in, B, K, ld_w;
+    int flags;                  // ODECOL_FLAG_* of the caller's problem
     const float* W_aug;
     const float* kappa;
     const float* sigma;

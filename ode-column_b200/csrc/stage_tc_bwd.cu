@@ -1255,15 +1255,12 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // par with the default (separate launch + replay one step ahead): profiles/r1_session2.md section 5.
     const char* fe = getenv("ODECOL_FUSE_DW");
     const bool fuse_dw = use_chain && (fe ? atoi(fe) != 0 : false);
-    // default dW path: every (output tile, row split) accumulates into its own copy of grad_W_aug across the whole sweep (plain
-    // read-modify-write: one CTA per (tile, split) and launch, launches ordered on the stream), the copies are summed in a
-    // fixed order at the end -- the gradient is bit-reproducible.  The opt-in variants (pair, fused) keep float atomics.
+    // ODECOL_FLAG_DETERMINISTIC: every (output tile, row split) accumulates into its own copy of grad_W_aug across the whole
+    // sweep (one CTA per (tile, split) and launch, launches ordered on the stream; the running sum is fetched at kernel start
+    // and stored back at the end), the copies are summed in a fixed order after the last step -- the gradient is
+    // bit-reproducible.  Measured: reverse sweep 633-639 ms against 621-625 ms with float atomics (A/B on one box).
     float* dw_partial = nullptr;
-#ifdef ODECOL_DW_ATOMIC
-    const bool dw_fixed_order = false;              // comparison build: float atomics straight into grad_W_aug
-#else
-    const bool dw_fixed_order = true;
-#endif
+    const bool dw_fixed_order = (p.flags & ODECOL_FLAG_DETERMINISTIC) != 0;     // default: float atomics (2 % faster sweep)
     if (dw_fixed_order && !fuse_dw && !(dw_pair_enabled() && ds.MT % 2 == 0) && ds.Z <= L.dwZ) {
         dw_partial = reinterpret_cast<float*>(w + L.off_dwpart);
         if (cudaMemsetAsync(dw_partial, 0, sizeof(float) * (size_t)ds.Z * p.N * p.ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;

@@ -575,4 +575,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.attr("OP_DOPRI5_BWD") = (int)ODECOL_OP_DOPRI5_BWD;
     m.attr("FLAG_FORCE_STAGED") = (int)ODECOL_FLAG_FORCE_STAGED;
     m.attr("FLAG_FORCE_TENSOR") = (int)ODECOL_FLAG_FORCE_TENSOR;
+    m.attr("FLAG_DETERMINISTIC") = (int)ODECOL_FLAG_DETERMINISTIC;
 }
