@@ -730,7 +730,7 @@ __global__ void k_tc_set_one(float* __restrict__ Rhi, int Bp, int B, int KPa, in
 #endif
 constexpr int DW_CHUNK = ODECOL_DW_CHUNK;
 
-template <bool TWO>
+template <bool TWO, bool REPLAY>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
         const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, DwShape ds,
@@ -828,12 +828,13 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
         // writes the other operand / phi' set, so it overlaps this contraction instead of running as a kernel of its own
         // (which cannot share an SM with the 576-thread contraction CTAs: they hold the whole register file).
         const int rtid = (ew & 3) * 32 + lane;
-        const int rtotal = rj.valid ? rj.nblocks * rj.slices : 0;
+        const int rtotal = (REPLAY && rj.valid) ? rj.nblocks * rj.slices : 0;      // REPLAY = false: the lean default kernel
         const int rstep = (int)gridDim.x * 4;
         int ru = (int)blockIdx.x * 4 + g;
         ReplayLoad rl;                                // the next unit's checkpoint values, in flight while this one is processed
-        if (ru < rtotal) replay_load(rj, ru / rj.slices, ru % rj.slices, rtid, rl);
+        if (REPLAY && ru < rtotal) replay_load(rj, ru / rj.slices, ru % rj.slices, rtid, rl);
         auto replay_next = [&]() {
+            if (!REPLAY) return;
             const ReplayLoad cur = rl;
             const int u = ru;
             ru += rstep;
@@ -866,9 +867,9 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * set);
-            if (ru < rtotal) replay_next();
+            if (REPLAY && ru < rtotal) replay_next();
         }
-        while (ru < rtotal) replay_next();
+        while (REPLAY && ru < rtotal) replay_next();
         if (dst) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
@@ -1038,8 +1039,9 @@ static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     const bool use_pair = dw_pair_enabled();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_tc_dw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_dw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        if (cudaFuncSetAttribute(k_tc_dw<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dw<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dw<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dw_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return ODECOL_E_CUDA;
         configured = true;
@@ -1048,13 +1050,12 @@ static int launch_dw(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
         const int pairs = (ds.MT / 2) * ds.NT * ds.Z;
         k_tc_dw_pair<<<2 * pairs, kThreads, (size_t)DW_PSTAGES * (2 * 4 + 2 * 2) * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds);
     } else if (ds.two_products) {
-        k_tc_dw<true><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds,
-                                                                                                       rj ? *rj : none);
-        if (rj_done) *rj_done = rj != nullptr;
+        k_tc_dw<true, false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds, none);
+    } else if (rj) {
+        k_tc_dw<false, true><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds, *rj);
+        if (rj_done) *rj_done = true;
     } else {
-        k_tc_dw<false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds,
-                                                                                                        rj ? *rj : none);
-        if (rj_done) *rj_done = rj != nullptr;
+        k_tc_dw<false, false><<<ds.MT * ds.NT * ds.Z, kThreads, (size_t)STAGES * 4 * 4 * DW_BK * 128 + 1024, s>>>(a_hi, a_lo, b_hi, b_lo, ds, none);
     }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
