@@ -18,7 +18,7 @@
  *   - forward results (trajectories, step counts, read-outs' predictions) are bit-reproducible for a given problem,
  *     library build and device.  Sums OVER TRIALS -- grad_W_aug, the scalar losses -- add per-trial contributions with
  *     float / double atomics, so repeated runs agree to rounding (~1e-7 relative), not bit for bit; the tensor family's rk4
- *     reverse sweep (N >= 256, the benchmarked path) reduces in a fixed order when ODECOL_FLAG_DETERMINISTIC is set;
+ *     reverse sweep (N > 128, the benchmarked path) reduces in a fixed order when ODECOL_FLAG_DETERMINISTIC is set;
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
@@ -172,7 +172,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
  * firing-rate components: scripts/xor_ode.py:119-177, scripts/parity_ode.py:238-250).  The forward sweep returns only
  * y[:, :, sel] and leaves, per grid step, the V/A state and the three V slopes of the step in `ckpt` (20 bytes per
  * population, trial and step, kernel-private layout); the reverse sweep re-derives every stage from them elementwise
- * instead of recomputing three contractions per step.  Only the tensor family (N >= 256) implements it: other
+ * instead of recomputing three contractions per step.  Only the tensor family (every network beyond the on-chip family, N > 128) implements it: other
  * problems return ODECOL_E_UNSUPPORTED and the caller uses odecol_rk4_fwd / odecol_rk4_bwd.
  *   odecol_rk4_ckpt_bytes   size of `ckpt` for (p, T); 0 if unsupported
  *   y_sel       (T, B, G)  out: the selected components at every grid point (row 0 = y0[:, sel])

@@ -28,11 +28,14 @@ static bool use_small(const odecol_problem* p, const DevProblem& d) {
     return !(p->flags & (ODECOL_FLAG_FORCE_STAGED | ODECOL_FLAG_FORCE_TENSOR)) && small_kp(d) != 0;
 }
 
-// staged problems: the contraction runs on the tensor cores once it is a real dense one (N >= 256), or on request
+// staged problems (beyond the on-chip family): rk4 runs in the tensor family -- persistent tcgen05 forward solve, checkpoint
+// mode, chained reverse stages -- unless the FFMA family is forced or N is not a multiple of 4 (never the case for column
+// networks, N = 8 x columns).  Measured at 8192 trials (round 2): N = 136: 4.2e9 vs 1.1e9, N = 192: 5.5e9 vs 1.4e9
+// population-steps/s forward + adjoint; the former threshold (N >= 256) left a 4x on the table.
 static bool use_tensor(const odecol_problem* p, const DevProblem& d) {
     if (p->flags & ODECOL_FLAG_FORCE_TENSOR) return true;
     if (p->flags & ODECOL_FLAG_FORCE_STAGED) return false;
-    return d.N >= 256;
+    return d.N % 4 == 0;
 }
 
 static inline bool misaligned(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) != 0; }

@@ -219,7 +219,9 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     fam.restype = ctypes.c_int
     fam.argtypes = [ctypes.c_void_p, ctypes.c_int]
     assert fam(ctypes.byref(p), 1) == 0 and fam(ctypes.byref(big), 1) == 2 and fam(ctypes.byref(_problem(N=0)), 1) == -1
-    assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184)), 1) == 1
+    assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184)), 1) == 2            # beyond the on-chip family: tensor cores
+    assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184, flags=1)), 1) == 1   # ... unless the FFMA family is forced
+    assert fam(ctypes.byref(_problem(N=162, n_in=20, ld_w=184)), 1) == 1            # N not a multiple of 4
 
 
 def test_error_codes_become_python_exceptions_not_crashes():
