@@ -766,14 +766,16 @@ def run_small(args):
         kaug = N + n_in + 1
         res = {"populations": N, "trials": B, "time_points": T}
 
+        opts = {"family": args.family} if args.family else None
+
         def fwd():
             with torch.no_grad():
-                return odecol.odeint(net, y0, tv, method="rk4")
+                return odecol.odeint(net, y0, tv, method="rk4", options=opts)
 
         def fwd_adj():
             for p in params:
                 p.grad = None
-            y = odecol.odeint(net, y0, tv, method="rk4", components=sel)
+            y = odecol.odeint(net, y0, tv, method="rk4", components=sel, options=opts)
             odecol.huber_rate_loss(y, target, 1).backward()
 
         sec = timed(fwd, args.steps)
