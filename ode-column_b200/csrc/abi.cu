@@ -38,6 +38,16 @@ static bool use_tensor(const odecol_problem* p, const DevProblem& d) {
     return d.N % 4 == 0;
 }
 
+// rk4 of a network that FITS the on-chip family still goes to the tensor family when the batch is large enough to fill the
+// machine with 128-row tiles: measured on the reference's parity network (N = 104; bench.py --workload small, round 2) the
+// two families break even at ~2048 trials (forward + adjoint 1.77e9 vs 1.67e9 population-steps/s); at 4096 trials the
+// tensor family is 1.9x (3.47e9 vs 1.79e9), at 16,384 trials 3.4x (6.13e9 vs 1.82e9; forward only 1.68e10 vs 9.1e9).  Small
+// networks (WTA N = 16, XOR N = 24) would waste most of a 128-row tile and stay on chip at every batch size.
+static bool use_small_rk4(const odecol_problem* p, const DevProblem& d) {
+    if (!use_small(p, d)) return false;
+    return !(d.B >= 4096 && d.N >= 64 && d.N % 4 == 0);
+}
+
 static inline bool misaligned(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) != 0; }
 
 struct EmScheduleLayout { size_t off_step, off_w, off_tk, total; };
@@ -78,16 +88,18 @@ int odecol_kernel_family(const odecol_problem* p, int op) {
     DevProblem d;
     if (to_dev(p, d) != ODECOL_OK) return -1;
     (void)op;
-    return use_small(p, d) ? 0 : (use_tensor(p, d) && (op == ODECOL_OP_RK4_FWD || op == ODECOL_OP_RK4_BWD) ? 2 : 1);
+    const bool rk4 = op == ODECOL_OP_RK4_FWD || op == ODECOL_OP_RK4_BWD;
+    if (rk4 ? use_small_rk4(p, d) : use_small(p, d)) return 0;
+    return use_tensor(p, d) && rk4 ? 2 : 1;
 }
 
 size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_t n_steps) {
     DevProblem d;
     if (to_dev(p, d) != ODECOL_OK) return 0;
-    const bool small = use_small(p, d);
+    const bool small = use_small(p, d), small_rk4 = use_small_rk4(p, d);
     switch (op) {
-        case ODECOL_OP_RK4_FWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
-        case ODECOL_OP_RK4_BWD: return small ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
+        case ODECOL_OP_RK4_FWD: return small_rk4 ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
+        case ODECOL_OP_RK4_BWD: return small_rk4 ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_BWD: return small ? 0 : stage_dopri5_bwd_workspace_bytes(d, T);
@@ -129,7 +141,7 @@ int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const flo
     if (T < 2 || out_every < 1) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_small(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
+    if (use_small_rk4(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
     if (use_tensor(p, d)) return tc_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
     return stage_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
@@ -147,7 +159,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(grad_W_aug, 0, sizeof(float) * (size_t)p->N * p->ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;
-    if (use_small(p, d)) return launch_rk4_bwd_small(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, s);
+    if (use_small_rk4(p, d)) return launch_rk4_bwd_small(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, s);
     if (misaligned(y_traj) || misaligned(workspace) || misaligned(grad_W_aug)) return ODECOL_E_ALIGN;
     if (use_tensor(p, d)) return tc_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
     return stage_rk4_bwd(d, t, T, y_traj, grad_y, sel, G, grad_y0, grad_W_aug, workspace, workspace_bytes, s);
@@ -156,7 +168,7 @@ int odecol_rk4_bwd(const odecol_problem* p, const float* t, int32_t T, const flo
 size_t odecol_rk4_ckpt_bytes(const odecol_problem* p, int32_t T) {
     DevProblem d;
     if (to_dev(p, d) != ODECOL_OK || T < 2) return 0;
-    if (use_small(p, d) || !use_tensor(p, d) || p->N % 4 != 0) return 0;
+    if (use_small_rk4(p, d) || !use_tensor(p, d) || p->N % 4 != 0) return 0;
     return tc_rk4_ckpt_bytes(d, T);
 }
 
@@ -168,7 +180,7 @@ int odecol_rk4_fwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
     if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !y0 || !y_sel || !ckpt) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
-    if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
+    if (use_small_rk4(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
     if (misaligned(y0) || misaligned(ckpt) || misaligned(workspace)) return ODECOL_E_ALIGN;
     g_launches.store(0, std::memory_order_relaxed);
     return tc_rk4_fwd_ckpt(d, t, T, y0, sel, G, y_sel, ckpt, ckpt_bytes, workspace, workspace_bytes,
@@ -184,7 +196,7 @@ int odecol_rk4_bwd_ckpt(const odecol_problem* p, const float* t, int32_t T, cons
     if (d.lat_gain) return ODECOL_E_UNSUPPORTED;      // the lateral-gain axis exists in the staged Euler-Maruyama path only
     if (!t || !ckpt || !grad_y_sel || !grad_W_aug) return ODECOL_E_NULL;
     if (T < 2 || G < 1 || G > 3 * p->N) return ODECOL_E_SHAPE;
-    if (use_small(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
+    if (use_small_rk4(p, d) || !use_tensor(p, d)) return ODECOL_E_UNSUPPORTED;
     if (misaligned(ckpt) || misaligned(workspace) || misaligned(grad_W_aug)) return ODECOL_E_ALIGN;
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -222,6 +222,13 @@ def test_shape_and_pointer_validation_without_a_gpu(lib):
     assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184)), 1) == 2            # beyond the on-chip family: tensor cores
     assert fam(ctypes.byref(_problem(N=160, n_in=20, ld_w=184, flags=1)), 1) == 1   # ... unless the FFMA family is forced
     assert fam(ctypes.byref(_problem(N=162, n_in=20, ld_w=184)), 1) == 1            # N not a multiple of 4
+    # the parity network (N = 104) fits the on-chip family, but from 4096 trials its rk4 runs on the tensor cores; the adaptive
+    # and stochastic solvers stay on chip, and so do the small networks at any batch size
+    par = dict(N=104, n_in=4, ld_w=112)
+    assert fam(ctypes.byref(_problem(B=4095, **par)), 1) == 0 and fam(ctypes.byref(_problem(B=4096, **par)), 1) == 2
+    assert fam(ctypes.byref(_problem(B=4096, **par)), 2) == 2 and fam(ctypes.byref(_problem(B=4096, **par)), 3) == 0
+    assert fam(ctypes.byref(_problem(B=65536)), 1) == 0
+    assert wsb(ctypes.byref(_problem(B=4096, **par)), 1, 100, 0) > 0 and wsb(ctypes.byref(_problem(B=4095, **par)), 1, 100, 0) == 0
 
 
 def test_error_codes_become_python_exceptions_not_crashes():

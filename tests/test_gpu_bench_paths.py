@@ -515,3 +515,59 @@ def test_tensor_family_gradients_are_bit_reproducible(cfg):
         (yp * wgt).sum().backward()
         grads.append((y0p.grad.clone(), sheet.recurrent_weights.grad.clone(), sheet.input_weights.grad.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*grads))
+
+
+def test_large_batch_rk4_of_the_parity_network_runs_on_the_tensor_cores(cfg, golden):
+    """From 4096 trials the rk4 solve of a network that fits the on-chip family (N = 104) is routed to the tensor family
+    (1.9x - 3.4x faster there, csrc/abi.cu::use_small_rk4): same results -- trajectories and gradients of every trial
+    against the oracle, and against the on-chip kernels on a slice of the batch."""
+    net = product_network("parity", cfg, golden["parity"], DEV)
+    lf = oracle_form("parity", cfg, golden["parity"])
+    B, N, T = 4100, 104, 12
+    gen = torch.Generator().manual_seed(9)
+    tv = torch.linspace(0.0, 1.1e-3, T)
+    kt = torch.tensor([0.0, 3e-4, 4e-4, 1.0])
+    amp = (torch.rand(B, 4, generator=gen) > 0.5).float() * 15.0
+    ku = torch.stack((torch.zeros(B, 4), torch.zeros(B, 4), amp, amp), 1)
+    net.time_vec, net.stim = kt.to(DEV), ku.to(DEV)
+    y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen), torch.rand(B, N, generator=gen)), 1)
+    sel = list(range(96, 104)) + list(range(N + 96, N + 104)) + [5, N + 50, 2 * N + 7]
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    tro, g0o, gWo, gUo, _ = _oracle_rk4_grads(lf, kt, ku, tv, y0, sel, wgt, chunk=1025)
+    ext = odecol._native.ext()
+    from ode_column_b200.solvers import _Setup
+    setup = _Setup(net, y0.to(DEV), tv.to(DEV), None)
+    assert setup.problem(setup.lf.W_aug).kernel_family(ext.OP_RK4_FWD) == 2
+    y0p = y0.to(DEV).requires_grad_(True)
+    yp = odecol.odeint(net, y0p, tv.to(DEV), method="rk4", components=sel)
+    assert "Ckpt" in type(yp.grad_fn).__name__
+    (yp * wgt.to(DEV)).sum().backward()
+    lfp = net.export_linear_form()
+    g_aug = torch.autograd.grad(lfp.W_aug, [p for p in net.parameters() if p.requires_grad], torch.ones_like(lfp.W_aug), allow_unused=True)
+    et = _relmax(yp.detach().cpu(), tro)
+    e0 = _relmax(y0p.grad.cpu(), g0o)
+    # parameter gradients through the oracle's dW, dU mapped onto the module's parameters by the same autograd graph
+    net2 = product_network("parity", cfg, golden["parity"], DEV)
+    net2.time_vec, net2.stim = net.time_vec, net.stim
+    lf2 = net2.export_linear_form()
+    gaug = torch.zeros_like(lf2.W_aug)
+    gaug[:, :N] = gWo.to(DEV); gaug[:, N:N + 4] = gUo.to(DEV)
+    lf2.W_aug.backward(gaug)
+    errs = []
+    for (n1, p1), (n2, p2) in zip(net.named_parameters(), net2.named_parameters()):
+        if p1.grad is not None and p2.grad is not None and float(p2.grad.abs().max()) > 0:
+            errs.append((n1, _relmax(p1.grad.cpu(), p2.grad.cpu())))
+    print(f"\n[parity network, B={B}, tensor family] trajectory {et:.1e}  dy0 {e0:.1e}  parameter gradients "
+          f"{[(n, f'{e:.1e}') for n, e in errs]}")
+    assert et < 1e-5 and e0 < 5e-5 and all(e < 5e-5 for _, e in errs) and len(errs) >= 3
+    # the same trials through the on-chip kernels (a batch below the threshold)
+    with torch.no_grad():
+        ys = odecol.odeint(net_slice(net, slice(0, 64)), y0[:64].to(DEV), tv.to(DEV), method="rk4", components=sel)
+    assert _relmax(ys.cpu(), yp.detach().cpu()[:, :64]) < 5e-6
+
+
+def net_slice(net, sl):
+    import copy
+    other = copy.copy(net)
+    other.stim = net.stim[sl]
+    return other
