@@ -132,6 +132,15 @@ constexpr int kMaxQ = 32;    // accumulator columns per epilogue thread = TN / 4
 #define ODECOL_PREFETCH_AHEAD 0
 #endif
 constexpr bool kPrefetch = ODECOL_PREFETCH_AHEAD > 0;
+// Forward stage epilogues: the rates r_1 .. r_S of the earlier stages of the step (they feed the A and F slopes) are
+// RECOMPUTED from the step's start state and the stored V slopes -- the recurrences of the checkpoint replay -- instead of
+// being kept in four tile-major planes.  A stage pass costs about 1.45 us per byte per element, a phi evaluation about 2 us
+// per pass: dropping the r planes takes the epilogues from 28 / 36 / 44 / 56 to 20 / 24 / 28 / 36 bytes per element.
+// -DODECOL_R_PLANES=1 restores the planes (comparison build).
+#ifndef ODECOL_R_PLANES
+#define ODECOL_R_PLANES 0
+#endif
+constexpr bool kRPlanes = ODECOL_R_PLANES != 0;
 constexpr int kPrefetchAhead = ODECOL_PREFETCH_AHEAD;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -752,19 +761,20 @@ struct FwdEpiT {
     // One float4 group (4 trials) of population i: what stage S reads from the scratch planes.
     struct Group { float4 V0, A0, R1, k1V, R2, k2V, R3, k3V, R4, F0; };
     ODECOL_DEVINL void load_group(Group& L, size_t oq) const {
-        L.V0 = ld4s(V0T + oq); L.A0 = ld4s(A0T + oq); L.R1 = ld4s(RsT[0] + oq);
-        if (S >= 2) { L.k1V = ld4s(K1T + oq); L.R2 = ld4s(RsT[1] + oq); }
-        if (S >= 3) { L.k2V = ld4s(K2T + oq); L.R3 = ld4s(RsT[2] + oq); }
-        if (S >= 4) { L.k3V = ld4s(K3T + oq); L.R4 = ld4s(RsT[3] + oq); if (needF) L.F0 = ld4s(F0T + oq); }
+        L.V0 = ld4s(V0T + oq); L.A0 = ld4s(A0T + oq);
+        if (kRPlanes) L.R1 = ld4s(RsT[0] + oq);
+        if (S >= 2) { L.k1V = ld4s(K1T + oq); if (kRPlanes) L.R2 = ld4s(RsT[1] + oq); }
+        if (S >= 3) { L.k2V = ld4s(K2T + oq); if (kRPlanes) L.R3 = ld4s(RsT[2] + oq); }
+        if (S >= 4) { L.k3V = ld4s(K3T + oq); if (kRPlanes) L.R4 = ld4s(RsT[3] + oq); if (needF) L.F0 = ld4s(F0T + oq); }
     }
     // L2 prefetch of what load_group(oq) will read: the planes were written one stage pass (tens of microseconds, several
     // hundred MB of traffic) ago and are mostly back in HBM; a prefetch two groups ahead turns the demand loads of the
     // pipelined loop into L2 hits without holding registers (the loop keeps ONE group in flight in registers).
     ODECOL_DEVINL void prefetch_group(size_t oq) const {
-        prefetch_l2(V0T + oq); prefetch_l2(A0T + oq); prefetch_l2(RsT[0] + oq);
-        if (S >= 2) { prefetch_l2(K1T + oq); prefetch_l2(RsT[1] + oq); }
-        if (S >= 3) { prefetch_l2(K2T + oq); prefetch_l2(RsT[2] + oq); }
-        if (S >= 4) { prefetch_l2(K3T + oq); prefetch_l2(RsT[3] + oq); if (needF) prefetch_l2(F0T + oq); }
+        prefetch_l2(V0T + oq); prefetch_l2(A0T + oq);
+        if (S >= 2) prefetch_l2(K1T + oq);
+        if (S >= 3) prefetch_l2(K2T + oq);
+        if (S >= 4) { prefetch_l2(K3T + oq); if (needF) prefetch_l2(F0T + oq); }
     }
     // before the tile's accumulator is ready: the first groups of this thread
     ODECOL_DEVINL void pre_tile(int i, int nt, int g, int TNq) const {
@@ -802,15 +812,30 @@ struct FwdEpiT {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float v0 = (&V0.x)[e], a0 = (&A0.x)[e];
-                // A (and at stage 4 F) slopes of the earlier stages, re-derived from r
+                // A (and at stage 4 F) slopes of the earlier stages, re-derived from the rates r_1 .. r_{S-1}; the rates
+                // themselves from the stage states (kRPlanes: from their planes), which follow from V0, A0 and the V slopes
                 float k1A = 0.f, k2A = 0.f, k3A = 0.f, A = a0, V = v0;
-                if (S >= 2) { k1A = (kap * (&R1.x)[e] - a0) * inv_ta; }
-                if (S == 2) { V = v0 + dt * (&k1V.x)[e] * third; A = a0 + dt * k1A * third; }
-                if (S >= 3) { const float a2 = a0 + dt * k1A * third; k2A = (kap * (&R2.x)[e] - a2) * inv_ta; }
-                if (S == 3) { V = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third); A = a0 + dt * (k2A - k1A * third); }
-                if (S >= 4) { const float a3 = a0 + dt * (k2A - k1A * third); k3A = (kap * (&R3.x)[e] - a3) * inv_ta; }
-                if (S == 4) { V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]); A = a0 + dt * (k1A - k2A + k3A); }
-                const float r = S == 1 ? (&R1.x)[e] : S == 2 ? (&R2.x)[e] : S == 3 ? (&R3.x)[e] : (&R4.x)[e];
+                float r1 = 0.f, r2 = 0.f, r3 = 0.f, r;
+                if (kRPlanes) { r1 = (&R1.x)[e]; r2 = (&R2.x)[e]; r3 = (&R3.x)[e]; }
+                else r1 = phi_fast(v0 - a0);
+                r = r1;
+                if (S >= 2) {
+                    k1A = (kap * r1 - a0) * inv_ta;
+                    const float v2 = v0 + dt * (&k1V.x)[e] * third, a2 = a0 + dt * k1A * third;
+                    if (!kRPlanes) r2 = phi_fast(v2 - a2);
+                    if (S == 2) { V = v2; A = a2; r = r2; }
+                    if (S >= 3) {
+                        k2A = (kap * r2 - a2) * inv_ta;
+                        const float v3 = v0 + dt * ((&k2V.x)[e] - (&k1V.x)[e] * third), a3 = a0 + dt * (k2A - k1A * third);
+                        if (!kRPlanes) r3 = phi_fast(v3 - a3);
+                        if (S == 3) { V = v3; A = a3; r = r3; }
+                        if (S >= 4) {
+                            k3A = (kap * r3 - a3) * inv_ta;
+                            V = v0 + dt * ((&k1V.x)[e] - (&k2V.x)[e] + (&k3V.x)[e]); A = a0 + dt * (k1A - k2A + k3A);
+                            r = kRPlanes ? (&R4.x)[e] : phi_fast(V - A);
+                        }
+                    }
+                }
                 const float total = tot[q4 + e] * p.c.tau_s;
                 const float dV = (total * p.c.R - V) * inv_tm;
                 const float dA = (kap * r - A) * inv_ta;
@@ -824,11 +849,11 @@ struct FwdEpiT {
                     nA = a0 + (k1A + 3.f * (k2A + k3A) + dA) * dt * 0.125f;
                     if (needF) {
                     const float f0 = (&F0.x)[e];
-                    const float k1F = ((&R1.x)[e] - f0) * inv_ts;
+                    const float k1F = (r1 - f0) * inv_ts;
                     const float f2 = f0 + dt * k1F * third;
-                    const float k2F = ((&R2.x)[e] - f2) * inv_ts;
+                    const float k2F = (r2 - f2) * inv_ts;
                     const float f3 = f0 + dt * (k2F - k1F * third);
-                    const float k3F = ((&R3.x)[e] - f3) * inv_ts;
+                    const float k3F = (r3 - f3) * inv_ts;
                     const float f4 = f0 + dt * (k1F - k2F + k3F);
                     const float k4F = (r - f4) * inv_ts;
                     nF = f0 + (k1F + 3.f * (k2F + k3F) + k4F) * dt * 0.125f;
@@ -849,7 +874,7 @@ struct FwdEpiT {
                 st4s(A1T + oq, make_float4(oNA[0], oNA[1], oNA[2], oNA[3]));
                 if (needF) st4s(F1T + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
             }
-            if (store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+            if (kRPlanes && store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
             const int b0 = n0 + g * TNq + q4;
             float* rh = Rhi_nxt + (size_t)b0 * KPa + i;
             float* rl = Rlo_nxt + (size_t)b0 * KPa + i;
