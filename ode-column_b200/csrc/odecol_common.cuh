@@ -46,11 +46,13 @@ ODECOL_DEVINL float exp_fast(float x) {            // |x| < 87
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f * 1.4426950408889634f));
     return p * __int_as_float(((int)n + 127) << 23);
 }
-ODECOL_DEVINL float tanh_small(float u) {          // Taylor through u^11: < 3e-8 relative for |u| <= 0.4
-    if (fabsf(u) > 0.4f) {                         // never reached for physical states; kept small (no libdevice call)
-        const float e2 = exp_fast(fminf(2.0f * fabsf(u), 80.0f));
-        return copysignf(1.0f - __fdividef(2.0f, e2 + 1.0f), u);
-    }
+// tanh on the argument range of phi's soft clamp, z = 80 tanh(-0.0089 x_nom / 80): Taylor through u^11, < 3e-8 relative for
+// |u| <= 0.4 (x_nom within +-3595, i.e. V - A between -54 and +95), the argument CLAMPED beyond.  Out there exp(z) is below
+// 1e-13 or above 1e13 either way, so phi = x_nom / (1 - exp(z)) does not see the difference in float32 (|delta r| < 1e-9);
+// a branch to an exp-based formula cost every evaluation a divergence point and doubled the code (round-2 SASS: 45 static
+// instructions per phi, 16 BSSY / BSYNC pairs per four elements).
+ODECOL_DEVINL float tanh_small(float u) {
+    u = fminf(fmaxf(u, -0.4f), 0.4f);
     const float s = u * u;
     float p = fmaf(s, -8.8632355299021965e-3f, 2.1869488536155203e-2f);   // -1382/155925, 62/2835
     p = fmaf(s, p, -5.3968253968253968e-2f);                               // -17/315

@@ -95,10 +95,11 @@ ODECOL_DEVINL uint32_t make_idesc(int tile_n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// float32 -> TF32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 does): on the sign-magnitude bit
+// pattern that is "add half of the dropped field, clear it" -- two integer instructions; ptxas expands the cvt into more.
+// Exact for every finite value whose rounding does not overflow (|x| < 3.4e38 (1 - 2^-11)); NaN stays NaN.
 ODECOL_DEVINL float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 struct TileShape {
