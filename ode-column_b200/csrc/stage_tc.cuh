@@ -726,6 +726,61 @@ struct TileGeom {
     }
 };
 
+// Stimulus columns [N, N + n_in) of a K-major operand (hi / lo split) for the trials [n0, n0 + tile_n) at ONE query time
+// (knot interval idx, clamped time tcl: knot_locate): share `part` of `parts` equal shares of the entries, walked by
+// `nthr` threads.  Four consecutive channels per thread -- two 16-byte loads of the knot values, the interpolation in
+// knot_value's operations and order (bit-identical), two 16-byte stores -- when the rows allow it; the entry index is
+// carried incrementally (one integer division per thread instead of two per entry).
+ODECOL_DEVINL void stimulus_columns(const DevProblem& p, int KPa, int idx, float tcl, int n0, int tile_n, int part, int parts,
+                                    int tid, int nthr, float* __restrict__ Rhi, float* __restrict__ Rlo) {
+    const int n_in = p.n_in, N = p.N;
+    const float x0 = __ldg(p.knot_t + idx - 1), x1 = __ldg(p.knot_t + idx);
+    const float dx = __fsub_rn(x1, x0), dtc = __fsub_rn(tcl, x0);
+    const bool vec = ((n_in | N | KPa | (int)p.knot_stride_b) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(p.knot_u) | reinterpret_cast<uintptr_t>(Rhi) | reinterpret_cast<uintptr_t>(Rlo)) & 15) == 0;
+    if (vec) {
+        const int nq = n_in >> 2, total = tile_n * nq, share = (total + parts - 1) / parts;
+        const int e_end = min(total, (part + 1) * share);
+        int e = part * share + tid;
+        if (e >= e_end) return;
+        int bl = e / nq, c = e - bl * nq;                      // trial within the tile, channel quad
+        const int dbl = nthr / nq, dc = nthr - dbl * nq;
+        for (; e < e_end; e += nthr) {
+            const int b = n0 + bl;
+            if (b < p.B) {
+                const float* ku = p.knot_u + (size_t)b * p.knot_stride_b + 4 * c;
+                const float4 y0 = __ldg(reinterpret_cast<const float4*>(ku + (size_t)(idx - 1) * n_in));
+                const float4 y1 = __ldg(reinterpret_cast<const float4*>(ku + (size_t)idx * n_in));
+                float4 h, l;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float slope = __fdiv_rn(__fsub_rn((&y1.x)[k], (&y0.x)[k]), dx);
+                    const float v = __fadd_rn((&y0.x)[k], __fmul_rn(slope, dtc));
+                    (&h.x)[k] = tf32_rna(v);
+                    (&l.x)[k] = tf32_rna(v - (&h.x)[k]);
+                }
+                const size_t at = (size_t)b * KPa + N + 4 * c;
+                *reinterpret_cast<float4*>(Rhi + at) = h;
+                *reinterpret_cast<float4*>(Rlo + at) = l;
+            }
+            bl += dbl; c += dc;
+            if (c >= nq) { c -= nq; ++bl; }
+        }
+        return;
+    }
+    const int total = tile_n * n_in, share = (total + parts - 1) / parts;
+    const int e_end = min(total, (part + 1) * share);
+    for (int e = part * share + tid; e < e_end; e += nthr) {
+        const int b = n0 + e / n_in, ch = e % n_in;
+        if (b < p.B) {
+            const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
+            const float h = tf32_rna(v);
+            Rhi[(size_t)b * KPa + N + ch] = h;
+            Rlo[(size_t)b * KPa + N + ch] = tf32_rna(v - h);
+        }
+    }
+}
+
 // Forward stage epilogue (3/8 rule, reference step: torchdiffeq rk_common.py rk4_alt_step_func).  Only what cannot be
 // recomputed crosses a stage boundary through HBM: the V slope of each stage (it carries the contraction) and r of each
 // stage.  The A and F slopes are linear in r, so every stage re-derives them in registers from A0 / F0 and r_1..r_S with
@@ -910,18 +965,8 @@ struct FwdEpiT {
         const float tn = S == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : S == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
         int idx = 1;
         const float tcl = knot_locate(p.knot_t, p.K, tn, idx);
-        const int n_in = p.n_in, N = p.N;
-        const int MT = tg.Np / BM, total = tile_n * n_in, share = (total + MT - 1) / MT;
-        const int e_end = min(total, (m_tile + 1) * share);
-        for (int e = m_tile * share + etid; e < e_end; e += nthr) {
-            const int b = n0 + e / n_in, ch = e % n_in;
-            if (b < p.B) {
-                const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
-                const float h = tf32_rna(v);
-                Rhi_nxt[(size_t)b * KPa + N + ch] = h;
-                Rlo_nxt[(size_t)b * KPa + N + ch] = tf32_rna(v - h);
-            }
-        }
+        const int MT = tg.Np / BM;
+        stimulus_columns(p, KPa, idx, tcl, n0, tile_n, m_tile, MT, etid, nthr, Rhi_nxt, Rlo_nxt);
     }
 };
 

@@ -619,19 +619,14 @@ ODECOL_DEVINL void replay_compute(const ReplayJob& j, int blk, int slice, int ti
                 }
     }
     if (slice != 0) return;
-    // stimulus channels at the four stage times (the constant-one column is set once per sweep)
-    const int n_in = p.n_in;
-    for (int e = tid; e < 16 * n_in; e += 128) {
-        const int s = e / (4 * n_in), b = b4 + (e / n_in) % 4, ch = e % n_in;
-        if (b >= p.B) continue;
-        const float ts = s == 0 ? t0 : s == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : s == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
-        int idx = 1;
-        const float tcl = knot_locate(p.knot_t, p.K, ts, idx);
-        const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
-        const float h = tf32_rna(v);
-        const size_t at = s * j.rstride + (size_t)b * j.KPa + N + ch;
-        j.Rhi[at] = h; j.Rlo[at] = tf32_rna(v - h);
-    }
+    // stimulus channels at the four stage times (the constant-one column is set once per sweep): warp s of the unit's four
+    // warps writes the columns of stage s (one knot lookup per warp, four channels per lane and trip)
+    if (p.n_in == 0) return;
+    const int s = tid >> 5;
+    const float ts = s == 0 ? t0 : s == 1 ? __fadd_rn(t0, __fmul_rn(dt, kOneThirdL)) : s == 2 ? __fadd_rn(t0, __fmul_rn(dt, kTwoThirdsL)) : t1;
+    int idx = 1;
+    const float tcl = knot_locate(p.knot_t, p.K, ts, idx);
+    stimulus_columns(p, j.KPa, idx, tcl, b4, 4, 0, 1, tid & 31, 32, j.Rhi + s * j.rstride, j.Rlo + s * j.rstride);
 }
 
 ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) {
