@@ -19,6 +19,9 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libodecol.so"
+# variant builds (A/B experiments): ODECOL_LIB_OUT=path/to/variant.so with ODECOL_NVCC_EXTRA=... compiles into its own object
+# directory and leaves the shipped library, its objects and the extension alone
+VARIANT_OUT = os.environ.get("ODECOL_LIB_OUT")
 EXT = PKG / ("_odecol_ext" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 
 CUDA_SOURCES = ["abi.cu", "small_kernels.cu", "stage_kernels.cu", "stage_bwd.cu", "stage_em.cu", "stage_tc.cu", "stage_tc_bwd.cu", "stage_tc_persist.cu", "ww_kernel.cu", "readout_kernels.cu"]
@@ -59,27 +62,29 @@ def _run(cmd, verbose):
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
     deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "odecol.h"]
-    if force or _stale(LIB, deps):
-        LIBDIR.mkdir(exist_ok=True)
-        objs = []
-        procs = []
-        objdir = PKG / "build"
-        objdir.mkdir(exist_ok=True)
-        for s in srcs:                                   # compile translation units in parallel
-            o = objdir / (s.stem + ".o")
-            objs.append(o)
-            if force or _stale(o, deps):
-                cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
-                if verbose:
-                    print("+", " ".join(map(str, cmd)), flush=True)
-                procs.append((cmd, subprocess.Popen(list(map(str, cmd)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        for cmd, pr in procs:
-            out, _ = pr.communicate()
-            if pr.returncode != 0:
-                sys.stderr.write(out)
-                raise RuntimeError(f"nvcc failed on {cmd[-3]}")
-        _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcuda"], verbose)
-    return LIB
+    target = Path(VARIANT_OUT).resolve() if VARIANT_OUT else LIB
+    force = force or bool(VARIANT_OUT)
+    LIBDIR.mkdir(exist_ok=True)
+    objs = []
+    procs = []
+    objdir = PKG / ("build_variant" if VARIANT_OUT else "build")
+    objdir.mkdir(exist_ok=True)
+    for s in srcs:                                       # compile translation units in parallel
+        o = objdir / (s.stem + ".o")
+        objs.append(o)
+        if force or _stale(o, deps):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+            if verbose:
+                print("+", " ".join(map(str, cmd)), flush=True)
+            procs.append((cmd, subprocess.Popen(list(map(str, cmd)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, pr in procs:
+        log, _ = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(log)
+            raise RuntimeError(f"nvcc failed on {cmd[-3]}")
+    if procs or _stale(target, objs):
+        _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs, "-lcuda"], verbose)
+    return target
 
 
 def build_ext(force: bool = False, verbose: bool = False) -> Path:
@@ -107,6 +112,8 @@ def build_ext(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build(force: bool = False, verbose: bool = False):
+    if VARIANT_OUT:
+        return build_lib(force, verbose), EXT
     build_lib(force, verbose)
     build_ext(force, verbose)
     return LIB, EXT

@@ -60,17 +60,34 @@ ODECOL_DEVINL float tanh_small(float u) {
     p = fmaf(s, p, -3.3333333333333333e-1f);                               // -1/3
     return fmaf(u * s, p, u);
 }
+// exp(80 th) for phi's soft-clamped exponent as ONE multiply and ex2.approx (the SFU splits integer and fraction itself):
+// the exponent z = 80 th is only known to 2^-24 relative in float32 whichever way it is formed (|z| <= 30.4 -> up to 2e-6
+// relative in exp(z), in the reference's own arithmetic as well), and where exp(z) matters to phi -- |z| of order one, the
+// cancellation in 1 - exp(z) -- the error is the SFU's 2^-22, with or without a Cody-Waite reduction in front of it.  So the
+// reduction (rint, two fmas, int conversion, exponent insertion: 8 of phi's 25 instructions) bought no accuracy.
+ODECOL_DEVINL float exp80_fast(float th) {
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(th * 115.41560327111707f));      // 80 log2(e)
+    return p;
+}
+// 1 / x as the bare SFU instruction (__fdividef / div.approx wrap it in a range check and two conditional rescalings for
+// denominators below 2^-126: 1 - exp(z) only gets there AT phi's removable pole, where the reference itself returns NaN)
+ODECOL_DEVINL float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 ODECOL_DEVINL float phi_fast(float x) {
     const float x_nom = fmaf(48.0f, x, -981.0f);
-    const float zc = 80.0f * tanh_small(x_nom * (-0.0089f / 80.0f));
-    return __fdividef(x_nom, 1.0f - exp_fast(zc));
+    const float th = tanh_small(x_nom * (-0.0089f / 80.0f));
+    return x_nom * rcp_fast(1.0f - exp80_fast(th));
 }
 
 ODECOL_DEVINL void phi_dphi_fast(float x, float& r, float& dr) {
     const float x_nom = fmaf(48.0f, x, -981.0f);
     const float th = tanh_small(x_nom * (-0.0089f / 80.0f));
-    const float e = exp_fast(80.0f * th);
-    const float inv = __fdividef(1.0f, 1.0f - e);
+    const float e = exp80_fast(th);
+    const float inv = rcp_fast(1.0f - e);
     r = x_nom * inv;
     dr = 48.0f * (inv + r * inv * e * (1.0f - th * th) * (-0.0089f));
 }

@@ -24,7 +24,10 @@ namespace tc {
 
 constexpr int BM = 128;          // populations per tile = TMEM lanes
 constexpr int BK = 32;           // floats per K block = one 128-byte swizzle row
-constexpr int STAGES = 3;
+#ifndef ODECOL_TC_STAGES
+#define ODECOL_TC_STAGES 3
+#endif
+constexpr int STAGES = ODECOL_TC_STAGES;      // operand ring depth (stages of 2 x (128 + TN) x 128 bytes)
 constexpr int kEpiWarps = 16;
 constexpr int kMainAcc = 3;      // Whi.Rhi accumulators (rotated), plus one for the cross terms
 constexpr int kThreads = 32 * (2 + kEpiWarps);
@@ -115,6 +118,10 @@ ODECOL_DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 
 ODECOL_DEVINL void st_global(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// predicated store: no branch around it (the ragged last trial tile is the only place where the predicate is ever false)
+ODECOL_DEVINL void st_global_if(float* p, float v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+}
 ODECOL_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 ODECOL_DEVINL unsigned long long gtimer() {
@@ -931,19 +938,23 @@ struct FwdEpiT {
                 if (needF) st4s(F1T + oq, make_float4(oNF[0], oNF[1], oNF[2], oNF[3]));
             }
             if (kRPlanes && store_r) st4s(RsT[S & 3] + oq, make_float4(oR[0], oR[1], oR[2], oR[3]));
+            // operand rows of the next contraction: one 64-bit row address per group, the other seven stores at fixed
+            // offsets from it, predicated (the branchy form spent ~27 instructions per element on these two stores)
             const int b0 = n0 + g * TNq + q4;
             float* rh = Rhi_nxt + (size_t)b0 * KPa + i;
-            float* rl = Rlo_nxt + (size_t)b0 * KPa + i;
+            const ptrdiff_t lo_off = Rlo_nxt - Rhi_nxt;
             float* yr = (S == 4 && traj_row && !(dbg_skip & 1)) ? traj_row + (size_t)b0 * 3 * N + i : nullptr;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (b0 + e < B) {
+                const bool ok = b0 + e < B;
+                if (!(dbg_skip & 2)) {
                     const float h = tf32_rna(oR[e]);
-                    if (!(dbg_skip & 2)) {
-                        st_global(rh + (size_t)e * KPa, h);
-                        st_global(rl + (size_t)e * KPa, tf32_rna(oR[e] - h));
-                    }
-                    if (S == 4 && yr) {
+                    float* ph = rh + (size_t)e * KPa;
+                    st_global_if(ph, h, ok);
+                    st_global_if(ph + lo_off, tf32_rna(oR[e] - h), ok);
+                }
+                if (S == 4 && ok) {
+                    if (yr) {
                         float* y = yr + (size_t)e * 3 * N;
                         st_global(y, oNV[e]); st_global(y + N, oNA[e]); st_global(y + 2 * N, oNF[e]);
                     }

@@ -154,16 +154,15 @@ struct BwdEpiT {
                 st4s(acurT + pl + oq, make_float4(nA[0], nA[1], nA[2], nA[3]));
             }
             const int b0 = bg + 4 * q;
-            float* ah = AVhi_nxt + (size_t)b0 * NPk + j;
-            float* al = AVlo_nxt + (size_t)b0 * NPk + j;
+            float* ah = AVhi_nxt + (size_t)b0 * NPk + j;       // one row address per group, predicated stores (FwdEpiT::rows)
+            const ptrdiff_t lo_off = AVlo_nxt - AVhi_nxt;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (b0 + e < B) {
-                    const float v = gamma * nV[e];
-                    const float h = tf32_rna(v);
-                    st_global(ah + (size_t)e * NPk, h);
-                    st_global(al + (size_t)e * NPk, tf32_rna(v - h));
-                }
+                const float v = gamma * nV[e];
+                const float h = tf32_rna(v);
+                float* ph = ah + (size_t)e * NPk;
+                st_global_if(ph, h, b0 + e < B);
+                st_global_if(ph + lo_off, tf32_rna(v - h), b0 + e < B);
             }
         }
     }
@@ -608,15 +607,17 @@ ODECOL_DEVINL void replay_compute(const ReplayJob& j, int blk, int slice, int ti
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) st4s(j.D[s] + o, make_float4(D[s][0], D[s][1], D[s][2], D[s][3]));
+        float* rh = j.Rhi + (size_t)b4 * j.KPa + i;               // one row address per unit, predicated stores
+        const ptrdiff_t lo_off = j.Rlo - j.Rhi;
 #pragma unroll
         for (int s = 0; s < 4; ++s)
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (b4 + e < p.B) {
-                    const float h = tf32_rna(R[s][e]);
-                    const size_t at = s * j.rstride + (size_t)(b4 + e) * j.KPa + i;
-                    j.Rhi[at] = h; j.Rlo[at] = tf32_rna(R[s][e] - h);
-                }
+            for (int e = 0; e < 4; ++e) {
+                const float h = tf32_rna(R[s][e]);
+                float* ph = rh + s * j.rstride + (size_t)e * j.KPa;
+                st_global_if(ph, h, b4 + e < p.B);
+                st_global_if(ph + lo_off, tf32_rna(R[s][e] - h), b4 + e < p.B);
+            }
     }
     if (slice != 0) return;
     // stimulus channels at the four stage times (the constant-one column is set once per sweep): warp s of the unit's four
@@ -636,7 +637,7 @@ ODECOL_DEVINL void replay_unit(const ReplayJob& j, int blk, int slice, int tid) 
 }
 
 // stand-alone: one CTA of 128 threads per group of four trials
-__global__ void __launch_bounds__(128) k_tc_replay(ReplayJob j) {
+__global__ void __launch_bounds__(128, 8) k_tc_replay(ReplayJob j) {
     for (int slice = 0; slice < j.slices; ++slice) replay_unit(j, blockIdx.x, slice, threadIdx.x);
 }
 

@@ -85,6 +85,22 @@ def test_rk4_prefix_matches_reference_driven_solve(name, steps, cfg, golden):
     assert rel_err(y, ref) < 2e-6
 
 
+def test_parity_rk4_noise_floor(cfg, golden):
+    """How far two float32 CPU implementations of the same arithmetic drift apart over the WHOLE parity solve (1000 steps):
+    the oracle's unified linear form against the golden trajectory of the unmodified reference modules.  The GPU tests
+    quote this floor where they judge the tensor family on this network (tests/test_gpu_parity.py)."""
+    g = golden["parity"]
+    lf = oracle_form("parity", cfg, g)
+    tv = torch.tensor(g["time_vec"])
+    worst = 0.0
+    for b in (1, 3):                                    # the two patterns with the largest drift
+        ode = orhs.UnifiedColumnODE(lf, tv, stim_table("parity", g["stims"][b]))
+        y = S.odeint_rk4(ode, torch.zeros(1, 3 * lf.n), tv)[::10, 0]
+        worst = max(worst, rel_err(y, torch.tensor(g["rk4_traj"][b])))
+    print(f"\nparity rk4, float32 CPU oracle vs reference golden over 1000 steps: {worst:.2e}")
+    assert 2e-6 < worst < 8e-6
+
+
 def test_em_prefix_matches_reference_driven_solve(cfg, golden):
     g = golden["wta"]
     lf = oracle_form("wta", cfg, g)
