@@ -80,8 +80,9 @@ __global__ void k_tc_init(DevProblem p, TileGeom tg, const float* __restrict__ y
 }
 
 struct TcFwdLayout {
-    int Np, Bp, KPa, TN;
+    int Np, Bp, KPa, TN, KP16;
     size_t off_Whi, off_Wlo, off_Rhi[2], off_Rlo[2], off_K[3], off_Y[2], off_RT[4], off_done, off_inv, total;
+    size_t off_W16[2], off_R16[2], off_wscale;      // mixed 16-bit operand format of the persistent forward kernel
 };
 
 static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
@@ -100,6 +101,10 @@ static TcFwdLayout tc_fwd_layout(const DevProblem& p) {
     for (int i = 0; i < 4; ++i) L.off_RT[i] = take(plane);           // r of stages 1..4
     L.off_done = take((size_t)(L.Bp / L.TN) + 64);          // one uint32 per trial tile (floats == 4 bytes)
     L.off_inv = take(3ull * p.N + 4);                       // component -> selection position (checkpoint mode) + F flag
+    L.KP16 = round_up(p.N + p.n_in + 1, BK16);
+    for (int i = 0; i < 2; ++i) L.off_W16[i] = take(((size_t)L.Np * L.KP16 + 1) / 2);          // FP16: half a float each
+    for (int i = 0; i < 2; ++i) L.off_R16[i] = take((size_t)L.Bp * L.KP16);                    // two FP16 planes
+    L.off_wscale = take(4);
     L.total = o;
     return L;
 }
@@ -114,7 +119,17 @@ void tc_launch_init(const DevProblem& p, const tc::TileGeom& tg, const float* y0
 int tc_rk4_fwd_persistent(const DevProblem& p, const float* t_dev, int T, const float* y0, float* y_out, int out_every,
                           float* Whi, float* Wlo, float* const Rhi[2], float* const Rlo[2], float* const KT[3],
                           float* const YT[2], float* const RT[4], unsigned int* done, int Np, int Bp, int KPa, int TN,
-                          const tc::CkptView* ck, cudaStream_t s);
+                          const tc::CkptView* ck, const tc::Mixed16* mx, cudaStream_t s);
+
+namespace tc {
+static Mixed16 mixed16_view(const TcFwdLayout& L, char* w) {
+    Mixed16 m;
+    for (int i = 0; i < 2; ++i) { m.W16[i] = w + L.off_W16[i]; m.R16[i] = reinterpret_cast<uint16_t*>(w + L.off_R16[i]); }
+    m.wscale = reinterpret_cast<float*>(w + L.off_wscale);
+    m.KP16 = L.KP16;
+    return m;
+}
+}  // namespace tc
 
 static bool persistent_enabled() {
     const char* v = getenv("ODECOL_PERSISTENT");
@@ -142,9 +157,11 @@ int tc_rk4_fwd(const DevProblem& p, const float* t_dev, int T, const float* y0, 
     const TileGeom tg{L.Bp / L.TN, L.Np, L.TN, L.TN / 4};
     // long contractions (K > 32 * kChunkMin) go through k_tc_contract, which accumulates in chunks (stage_tc.cuh); the
     // persistent kernel keeps the rotating-accumulator scheme that is accurate up to that length
-    if (persistent_enabled() && L.KPa / BK <= kChunkMin)
+    if (persistent_enabled() && L.KPa / BK <= kChunkMin) {
+        const Mixed16 mx = mixed16_view(L, w);
         return tc_rk4_fwd_persistent(p, t_dev, T, y0, y_out, out_every, Whi, Wlo, Rhi, Rlo, KT, YT, RT,
-                                     reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, nullptr, s);
+                                     reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, nullptr, &mx, s);
+    }
 
     k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
     k_tc_init<<<L.Bp, 128, 0, s>>>(p, tg, y0, t_dev, Rhi[0], Rlo[0], Rhi[1], Rlo[1], YT[0], YT[0] + tg.plane(),
@@ -282,8 +299,9 @@ int tc_rk4_fwd_ckpt(const DevProblem& p, const float* t_dev, int T, const float*
     count_launch(2);
     CkptView ck;
     ck.VA = static_cast<float*>(ckpt); ck.K = ck.VA + 2 * plane * (size_t)T; ck.y_sel = y_sel; ck.inv = inv; ck.G = G;
+    const Mixed16 mx = mixed16_view(L, w);
     return tc_rk4_fwd_persistent(p, t_dev, T, y0, nullptr, 1, F(L.off_Whi), F(L.off_Wlo), Rhi, Rlo, KT, YT, RT,
-                                 reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, &ck, s);
+                                 reinterpret_cast<unsigned int*>(w + L.off_done), L.Np, L.Bp, L.KPa, L.TN, &ck, &mx, s);
 }
 
 size_t tc_contract_workspace_bytes(int M, int N, int K) { return tc::contract_layout(M, N, K).total; }

@@ -17,6 +17,7 @@
 // The trial tile is chosen so that the number of tiles is a multiple of the SM count (148) where possible.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "stage_common.cuh"
 
 namespace odecol {
@@ -104,6 +105,48 @@ ODECOL_DEVINL uint32_t make_idesc(int tile_n) {
 ODECOL_DEVINL float tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+
+// ---- 16-bit operand format of the persistent forward solve: every operand as two FP16 planes, x s = xh + xl / 2048
+//   xh = fp16(x s), xl = fp16((x s - xh) 2048): 11 + 11 mantissa bits like the TF32 split, the low plane kept in FP16's normal
+//   range by its 2^11 (Ootomo & Yokota's error-corrected tensor-core product).  s is a power of two: for W_aug the one
+//   that puts max|W_aug| into [2^13, 2^14) (found on the device, undone by the epilogues); for the trial operand s = 1.
+//   C s = wh.rh (rotating main accumulators) + 2^-11 [wl.rh + wh.rl] (cross accumulator); dropped: wl.rl ~ 2^-22.
+// Three kind::f16 products of K = 16 per 32 operand bytes against three kind::tf32 products of K = 8: half the tensor-core
+// instructions and half the operand bytes (4 + 4 against 8 + 8 per (row, k)).  The stage passes are bound by the bytes
+// that cross the L2 <-> SM port (operand tiles + epilogue planes), so bytes are what count.  (kind::f16 wants A and B
+// of ONE type -- FP16 weights against BF16 rates is an illegal instruction -- hence FP16 for the trial operand as well.)
+// FP16's range is the price: an operand value beyond +-6e4 (a firing rate of 60 kHz, a stimulus of that size) cannot be
+// represented.  The epilogues raise a device flag when they meet one, and the launch sequence then repeats the solve in
+// the TF32 format (a kernel that returns at once when the flag is clear): same results as before wherever the 16-bit
+// format cannot hold the data, no host synchronisation either way.
+constexpr int BK16 = 64;         // 16-bit elements per K block = one 128-byte swizzle row
+constexpr float kF16Limit = 6.0e4f;
+struct F16x2 { unsigned short h, l; };
+ODECOL_DEVINL F16x2 f16_split2(float x) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn((x - __half2float(h)) * 2048.0f);
+    return {__half_as_ushort(h), __half_as_ushort(l)};
+}
+// predicated 16-bit store
+ODECOL_DEVINL void st_global_u16_if(uint16_t* p, unsigned short v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b16 [%0], %1;\n\t}" ::"l"(p), "h"(v), "r"((int)ok) : "memory");
+}
+ODECOL_DEVINL void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+ODECOL_DEVINL uint32_t make_idesc16(int tile_n) {
+    // c=F32 (1<<4), a=b=F16 (0<<7, 0<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    return (1u << 4) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// buffers of the 16-bit operand format (host side view; carved out of the forward workspace)
+struct Mixed16 {
+    void* W16[2];          // [Np][KP16] FP16: wh, wl
+    uint16_t* R16[2];      // two operand buffers of [2 planes][Bp][KP16] FP16
+    float* wscale;         // [0] = 1 / weight scale, [1] = scratch of the max reduction, [2] = overflow flag (uint32)
+    int KP16;
+};
 
 struct TileShape {
     int MT, NT, TN, KB;      // m tiles, trial tiles, trials per tile (multiple of 16, <= 128), K blocks of 32
@@ -595,6 +638,19 @@ inline bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rows x cols matrix of 16-bit elements (FP16 or BF16), `ld` elements per row; box = box_rows x 64 elements, 128-byte swizzle
+inline bool make_map16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {BK16, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (!n) {
@@ -682,6 +738,49 @@ static __global__ void k_split_pad(const float* __restrict__ src, int rows, int 
         const float h = tf32_rna(x);
         hi[e] = h;
         lo[e] = tf32_rna(x - h);
+    }
+}
+
+// max |src| as a float bit pattern (non-negative floats order like unsigned integers); *out zeroed by the caller
+static __global__ void k_absmax(const float* __restrict__ src, int rows, int cols, int ld, unsigned int* __restrict__ out) {
+    unsigned int m = 0;
+    const size_t total = (size_t)rows * cols;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const float x = fabsf(src[(e / cols) * ld + (e % cols)]);
+        if (x == x && x < 3.0e38f) m = max(m, __float_as_uint(x));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+// W s = wh + wl / 2048 in FP16, zero padded; s = the power of two with max|W| s in [2^13, 2^14); wscale[0] = 1 / s
+static __global__ void k_split16_w(const float* __restrict__ src, int rows, int cols, int ld, __half* __restrict__ hi,
+                                   __half* __restrict__ lo, int rows_p, int cols_p, const unsigned int* __restrict__ amax,
+                                   float* __restrict__ wscale) {
+    const float m = __uint_as_float(*amax);
+    int ex = 0;
+    if (m > 0.f) frexpf(m, &ex);                       // m = f 2^ex, f in [0.5, 1)
+    const float sc = m > 0.f ? ldexpf(1.0f, 14 - ex) : 1.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wscale[0] = m > 0.f ? ldexpf(1.0f, ex - 14) : 1.0f;
+    const size_t total = (size_t)rows_p * cols_p;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols_p), c = (int)(e % cols_p);
+        const float x = (r < rows && c < cols) ? src[(size_t)r * ld + c] * sc : 0.0f;
+        const F16x2 t = f16_split2(x);
+        hi[e] = __ushort_as_half(t.h);
+        lo[e] = __ushort_as_half(t.l);
+    }
+}
+// r = hi + lo (a TF32-split K-major operand buffer) re-split into two FP16 planes of KP16 columns, zero padded
+static __global__ void k_r16_from32(const float* __restrict__ hi, const float* __restrict__ lo, int Bp, int KPa,
+                                    uint16_t* __restrict__ R16, int KP16, unsigned int* __restrict__ ovf) {
+    const size_t total = (size_t)Bp * KP16, plane = total;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / KP16), k = (int)(e % KP16);
+        const float x = k < KPa ? hi[(size_t)b * KPa + k] + lo[(size_t)b * KPa + k] : 0.0f;
+        if (!(fabsf(x) <= kF16Limit)) *ovf = 1u;
+        const F16x2 t = f16_split2(x);
+        R16[e] = t.h; R16[plane + e] = t.l;
     }
 }
 
@@ -788,17 +887,76 @@ ODECOL_DEVINL void stimulus_columns(const DevProblem& p, int KPa, int idx, float
     }
 }
 
+// the same for the two-plane FP16 operand (plane stride `plane` elements, KP16 columns per row); *ovf = 1 when a value does
+// not fit the format
+ODECOL_DEVINL void stimulus_columns16(const DevProblem& p, int KP16, size_t plane, int idx, float tcl, int n0, int tile_n, int part,
+                                      int parts, int tid, int nthr, uint16_t* __restrict__ R16, unsigned int* __restrict__ ovf) {
+    const int n_in = p.n_in, N = p.N;
+    const float x0 = __ldg(p.knot_t + idx - 1), x1 = __ldg(p.knot_t + idx);
+    const float dx = __fsub_rn(x1, x0), dtc = __fsub_rn(tcl, x0);
+    const bool vec = ((n_in | N | KP16 | (int)p.knot_stride_b) & 3) == 0 && (plane & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(p.knot_u) & 15) == 0 && (reinterpret_cast<uintptr_t>(R16) & 7) == 0;
+    if (vec) {
+        const int nq = n_in >> 2, total = tile_n * nq, share = (total + parts - 1) / parts;
+        const int e_end = min(total, (part + 1) * share);
+        int e = part * share + tid;
+        if (e >= e_end) return;
+        int bl = e / nq, c = e - bl * nq;
+        const int dbl = nthr / nq, dc = nthr - dbl * nq;
+        for (; e < e_end; e += nthr) {
+            const int b = n0 + bl;
+            if (b < p.B) {
+                const float* ku = p.knot_u + (size_t)b * p.knot_stride_b + 4 * c;
+                const float4 y0 = __ldg(reinterpret_cast<const float4*>(ku + (size_t)(idx - 1) * n_in));
+                const float4 y1 = __ldg(reinterpret_cast<const float4*>(ku + (size_t)idx * n_in));
+                F16x2 t[4];
+                bool big = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float slope = __fdiv_rn(__fsub_rn((&y1.x)[k], (&y0.x)[k]), dx);
+                    const float v = __fadd_rn((&y0.x)[k], __fmul_rn(slope, dtc));
+                    big |= !(fabsf(v) <= kF16Limit);
+                    t[k] = f16_split2(v);
+                }
+                if (big) *ovf = 1u;
+                uint16_t* at = R16 + (size_t)b * KP16 + N + 4 * c;
+                *reinterpret_cast<uint2*>(at) = make_uint2((uint32_t)t[0].h | ((uint32_t)t[1].h << 16), (uint32_t)t[2].h | ((uint32_t)t[3].h << 16));
+                *reinterpret_cast<uint2*>(at + plane) = make_uint2((uint32_t)t[0].l | ((uint32_t)t[1].l << 16), (uint32_t)t[2].l | ((uint32_t)t[3].l << 16));
+            }
+            bl += dbl; c += dc;
+            if (c >= nq) { c -= nq; ++bl; }
+        }
+        return;
+    }
+    const int total = tile_n * n_in, share = (total + parts - 1) / parts;
+    const int e_end = min(total, (part + 1) * share);
+    for (int e = part * share + tid; e < e_end; e += nthr) {
+        const int b = n0 + e / n_in, ch = e % n_in;
+        if (b < p.B) {
+            const float v = knot_value(p.knot_t, p.knot_u + (size_t)b * p.knot_stride_b, n_in, idx, tcl, ch);
+            if (!(fabsf(v) <= kF16Limit)) *ovf = 1u;
+            const F16x2 t = f16_split2(v);
+            uint16_t* at = R16 + (size_t)b * KP16 + N + ch;
+            at[0] = t.h; at[plane] = t.l;
+        }
+    }
+}
+
 // Forward stage epilogue (3/8 rule, reference step: torchdiffeq rk_common.py rk4_alt_step_func).  Only what cannot be
 // recomputed crosses a stage boundary through HBM: the V slope of each stage (it carries the contraction) and r of each
 // stage.  The A and F slopes are linear in r, so every stage re-derives them in registers from A0 / F0 and r_1..r_S with
 // the same expressions, in the same order, as a kernel that had stored them; F is only touched at stage 4.
 // Bytes per (population, trial): 28 / 36 / 44 / 64 (+12 trajectory) for stages 1..4.
-template <int S>
+template <int S, bool F16 = false>      // F16: the next operand is written in the 16-bit format (two FP16 planes)
 struct FwdEpiT {
     DevProblem p;
     TileGeom tg;
     const float* t;
     int n, KPa;
+    uint16_t* R16_nxt; size_t r16_plane; int KP16;     // F16: operand of the next contraction, [2 planes][Bp][KP16]
+    const float* wscale;                               // F16: [0] = 1 / (power-of-two scale of the FP16 weight planes)
+    unsigned int* ovf;                                 // F16: raised when an operand value does not fit FP16
+    float ws;
     const float* V0T; const float* A0T; const float* F0T;   // [1 plane each] state at the start of the step (tile-major)
     float* V1T; float* A1T; float* F1T;                      // stage 4: state at the end of the step (tile-major)
     float* traj_row;       // stage 4: (B, 3N) row of the trajectory, or NULL
@@ -819,6 +977,7 @@ struct FwdEpiT {
         t0 = __ldg(t + n); t1 = __ldg(t + n + 1);
         dt = __fsub_rn(t1, t0);
         needF = (S == 4 && ysel_row && inv && !traj_row) ? __ldg(inv + 3 * p.N) : 1;
+        ws = F16 ? __ldg(wscale) : 1.0f;
     }
 
     // One float4 group (4 trials) of population i: what stage S reads from the scratch planes.
@@ -899,7 +1058,7 @@ struct FwdEpiT {
                         }
                     }
                 }
-                const float total = tot[q4 + e] * p.c.tau_s;
+                const float total = (F16 ? tot[q4 + e] * ws : tot[q4 + e]) * p.c.tau_s;
                 const float dV = (total * p.c.R - V) * inv_tm;
                 const float dA = (kap * r - A) * inv_ta;
                 oKV[e] = dV;
@@ -944,10 +1103,17 @@ struct FwdEpiT {
             float* rh = Rhi_nxt + (size_t)b0 * KPa + i;
             const ptrdiff_t lo_off = Rlo_nxt - Rhi_nxt;
             float* yr = (S == 4 && traj_row && !(dbg_skip & 1)) ? traj_row + (size_t)b0 * 3 * N + i : nullptr;
+            uint16_t* r16 = F16 ? R16_nxt + (size_t)b0 * KP16 + i : nullptr;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const bool ok = b0 + e < B;
-                if (!(dbg_skip & 2)) {
+                if (F16) {
+                    const F16x2 t2 = f16_split2(oR[e]);
+                    uint16_t* ph = r16 + (size_t)e * KP16;
+                    st_global_u16_if(ph, t2.h, ok);
+                    st_global_u16_if(ph + r16_plane, t2.l, ok);
+                    if (ok && !(fabsf(oR[e]) <= kF16Limit)) *ovf = 1u;
+                } else if (!(dbg_skip & 2)) {
                     const float h = tf32_rna(oR[e]);
                     float* ph = rh + (size_t)e * KPa;
                     st_global_if(ph, h, ok);
@@ -977,7 +1143,8 @@ struct FwdEpiT {
         int idx = 1;
         const float tcl = knot_locate(p.knot_t, p.K, tn, idx);
         const int MT = tg.Np / BM;
-        stimulus_columns(p, KPa, idx, tcl, n0, tile_n, m_tile, MT, etid, nthr, Rhi_nxt, Rlo_nxt);
+        if (F16) stimulus_columns16(p, KP16, r16_plane, idx, tcl, n0, tile_n, m_tile, MT, etid, nthr, R16_nxt, ovf);
+        else stimulus_columns(p, KPa, idx, tcl, n0, tile_n, m_tile, MT, etid, nthr, Rhi_nxt, Rlo_nxt);
     }
 };
 

@@ -36,11 +36,11 @@ def _relmax(a, b):
 # ----------------------------------------------------------------------------------------------------------------------
 # C4 shape
 # ----------------------------------------------------------------------------------------------------------------------
-def _c4_problem(cfg, B, T, seed):
+def _c4_problem(cfg, B, T, seed, amp_scale=30.0):
     cols, N = 64, 512
     sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device=DEV)
     gen = torch.Generator().manual_seed(seed)
-    amp = torch.rand(B, cols, generator=gen) * 30.0
+    amp = torch.rand(B, cols, generator=gen) * amp_scale
     dt = 1e-4
     t_end = (T - 1) * dt
     kt, ku = odecol.step_knots(0.3 * t_end, 0.7 * t_end, t_end, amp, dt)       # stimulus switches on and off inside the window
@@ -122,6 +122,29 @@ def test_rk4_adjoint_at_the_benchmarked_shape(cfg, B, T, ckpt, persistent, with_
     # worst single trial (a mis-addressed trial tile would hide in a max over the whole batch only if it were tiny)
     per_trial = (ypc - tro).abs().amax(dim=(0, 2)) / tro.abs().amax(dim=(0, 2)).clamp_min(1e-6)
     assert float(per_trial.max()) < 2e-5, int(per_trial.argmax())
+
+
+def test_rk4_forward_repeats_in_tf32_when_fp16_cannot_hold_the_operand(cfg):
+    """The persistent forward kernel keeps its operands as FP16 pairs; a stimulus of 2e5 does not fit.  The epilogues raise a
+    device flag and the launch sequence repeats the solve in the TF32 format (stage_tc_persist.cu): the result has to
+    match the oracle exactly as well as an ordinary problem does."""
+    B, T, N = 300, 6, 512
+    sheet, kt, ku, tv, y0, gen = _c4_problem(cfg, B, T, seed=77, amp_scale=2.0e5)
+    assert float(ku.abs().max()) > 6.0e4
+    sel = list(range(0, N, 8)) + list(range(N, 2 * N, 8))
+    wgt = torch.randn(T, B, len(sel), generator=gen)
+    lf = sheet_oracle_form(sheet)
+    tro, gy0o, gWo, gUo, gbo = _oracle_rk4_grads(lf, kt, ku, tv, y0, sel, wgt)
+    y0p = y0.to(DEV).requires_grad_(True)
+    yp = odecol.odeint(sheet, y0p, tv.to(DEV), method="rk4", components=sel, options={"checkpoint": True})
+    (yp * wgt.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(tro).all() and torch.isfinite(yp).all()
+    et = _relmax(yp.detach().cpu(), tro)
+    e0 = _relmax(y0p.grad.cpu(), gy0o)
+    eW = _relmax(sheet.recurrent_weights.grad.cpu(), gWo)
+    print(f"\n[C4 shape, stimulus beyond FP16] trajectory {et:.1e}  dy0 {e0:.1e}  dW {eW:.1e}")
+    assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5
 
 
 # ----------------------------------------------------------------------------------------------------------------------
