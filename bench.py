@@ -478,41 +478,50 @@ def run_ours(args):
     except OSError:
         pass
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-    tensor_peak = bf16 / 2.0 / 3.0                               # TF32 dense = bf16/2; 3xTF32 split keeps fp32 accuracy
+    # operand format of the persistent forward kernel: FP16 pairs, three kind::f16 products per K step (default), or the TF32
+    # split, three kind::tf32 products at half the rate (ODECOL_FWD16=0); either keeps float32 accuracy
+    fmt16 = os.environ.get("ODECOL_FWD16", "1") != "0"
+    tensor_peak = bf16 / 3.0 if fmt16 else bf16 / 2.0 / 3.0
+    tf32_peak = bf16 / 2.0 / 3.0
     sm_max = peaks.get("sm_max_mhz", 1965.0)
     ffma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     family = net_family(ext, odecol, net, step.y0_dev, tv, args)
     # DRAM bytes per stage pass from the committed ncu --set full capture of this kernel on this workload shape
     traffic, traffic_src = None, None
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if rec.get("populations") == n and rec.get("trials") == B:
             traffic, traffic_src = rec["dram_bytes_per_stage_pass"], rec["source"]
     except (OSError, KeyError, ValueError):
         pass
-    # the same pass seen from HBM: algorithmic bytes of the stage epilogues + the trial operand
-    hbm_bytes = (28 + 36 + 44 + 76) / 4.0 * n * B + 8.0 * kaug * B
+    # the same pass seen from HBM: algorithmic bytes of the stage epilogues (20 / 24 / 28 / 36 bytes per
+    # population and trial for stages 1..4) + the next operand written and read once (two FP16 or two TF32 planes)
+    kpa = (kaug + 63) // 64 * 64 if fmt16 else (kaug + 31) // 32 * 32
+    op_bytes = 4.0 if fmt16 else 8.0
+    hbm_bytes = (20 + 24 + 28 + 36) / 4.0 * n * B + op_bytes * n * B + op_bytes * kpa * B
     hbm_peak = peaks.get("hbm_gbs", 6457.0)
-    # operand tiles pulled by the contraction: every 128-population tile re-reads its trial tile (hi+lo) and every trial
-    # tile re-reads the W_aug tile (hi+lo); plus the bookkeeping bytes above
-    kpa = (kaug + 31) // 32 * 32
-    l2_bytes = (n // 128) * B * kpa * 8.0 + ((B + 111) // 112) * n * kpa * 8.0 + hbm_bytes
+    # what crosses the L2 <-> SM ports: every 128-population tile re-reads its trial tile and every trial tile re-reads the
+    # W_aug tile (both planes), plus the bookkeeping bytes above
+    l2_bytes = (n // 128) * B * kpa * op_bytes + ((B + 111) // 112) * n * kpa * op_bytes + hbm_bytes
     roofline = {
         "bound": "tensor",
         "kernel": "k_tc_rk4_fwd_persistent, per RK stage pass (fused W_aug.r_aug contraction + stage epilogue; one "
                   "cooperative launch runs all 4(T-1) passes, 'launch' below = one stage pass)",
         "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tflops / tensor_peak,
         "traffic": traffic,
-        "peak_source": ("measured bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split) from MEASURED_PEAKS.json" if peaks else
-                        "fallback 1.4 PFLOP/s bf16 sustained /6"),
+        "peak_source": (("measured bf16_tflops_sustained (FP16 runs at the BF16 rate) /3 (hi/lo FP16 pairs: three products) "
+                         if fmt16 else "measured bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split) ") + "from MEASURED_PEAKS.json"
+                        if peaks else "fallback 1.4 PFLOP/s bf16 sustained / products"),
+        "operand_format": "fp16 pairs (x = xh + xl/2048), 3 kind::f16 products" if fmt16 else "tf32 pairs, 3 kind::tf32 products",
+        "frac_of_3xtf32_peak": achieved_tflops / tf32_peak,
         "flops_per_launch": flops_per_launch, "avg_launch_ms": 1e3 * avg_launch, "kernel_family": family,
         "fp32_ffma_peak_tflops": ffma_peak, "frac_of_fp32_ffma_peak": achieved_tflops / ffma_peak,
         "forward_only_pop_steps_per_sec": n * B * (T - 1) / fwd_sec,
         "traffic_source": traffic_src,
         "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / avg_launch / 1e9,
                      "peak_gbs": hbm_peak, "frac": hbm_bytes / avg_launch / 1e9 / hbm_peak},
-        # what actually binds at N=512: every byte of operand tile and of bookkeeping crosses L2,
-        # whose full-chip throughput is ~6300 B/cycle (B300_MICROARCH.md, LTS cap)
+        # what binds at N=512: every byte of operand tile and of bookkeeping crosses the L2 <-> SM
+        # ports, whose full-chip throughput is ~6300 B/cycle (B300_MICROARCH.md, LTS cap)
         "l2_view": {"bytes_per_launch": l2_bytes, "achieved_gbs": l2_bytes / avg_launch / 1e9,
                     "cap_gbs": 6300.0 * sm_max * 1e6 / 1e9, "frac": l2_bytes / avg_launch / (6300.0 * sm_max * 1e6)},
     }
