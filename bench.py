@@ -655,7 +655,10 @@ def c5_measure(args, torch, dist, odecol, dev, rank, world, steps, warmup, horiz
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 6.0
+    # operand format of the drift contraction: FP16 pairs (three kind::f16 products per K step, default) or the TF32 split
+    # (ODECOL_EM16=0: three kind::tf32 products at half the rate); float32 accuracy either way
+    em16 = os.environ.get("ODECOL_EM16", "1") != "0"
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0) / (3.0 if em16 else 6.0)
     kaug = n + cols + 1
     # DRAM bytes of one drift evaluation from the committed ncu --set full capture of this kernel on this workload shape
     traffic, traffic_src = None, None
@@ -681,8 +684,10 @@ def c5_measure(args, torch, dist, odecol, dev, rank, world, steps, warmup, horiz
         "attempted_steps_per_member": float(attempts) / steps / args.c5_trials,
         "accepted_steps_per_member": float(accepted) / steps / args.c5_trials, "rounds_per_solve": rounds,
         "all_members_finite": bool(finite > 0),
-        "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (3xTF32 tcgen05 drift evaluation)",
+        "roofline": {"bound": "tensor", "kernel": "k_tc_contract<RhsEpi> (tcgen05 drift evaluation, " +
+                               ("FP16 pairs: 3 kind::f16 products)" if em16 else "TF32 pairs: 3 kind::tf32 products)"),
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                     "frac_of_3xtf32_peak": achieved / (peaks.get("bf16_tflops_sustained", 1400.0) / 6.0),
                      "traffic": traffic, "traffic_source": traffic_src,
                      "note": "lower bound: the elementwise stepping kernels are inside the timed region; per rank at N > 1"},
     }

@@ -22,14 +22,18 @@ namespace tc {
 struct RhsEpi {
     DevProblem p;
     const float* y;        // (B, 3N)
-    const float* Rhi; const float* Rlo;   // operand of this evaluation (r = hi + lo)
+    const float* Rhi; const float* Rlo;   // operand of this evaluation (r = hi + lo); FP16 pairs when wscale != NULL
     float* f;              // (B, 3N)
-    int KPa;
+    int KPa;               // elements per operand row (KP16 in the 16-bit format)
+    const float* wscale = nullptr;   // 16-bit operand format: [0] = 1 / (power-of-two scale of the FP16 weight planes); NULL = TF32
+    float ws;
     float inv_tm, inv_ta, inv_ts;
     const float* loc;      // (B, N) within-column input W_local (*) r, or NULL (lateral-gain sweeps: DevProblem::lat_gain)
-    ODECOL_DEVINL void prepare() {}
+    ODECOL_DEVINL void prepare() { ws = wscale ? __ldg(wscale) : 1.0f; }
     ODECOL_DEVINL void rows(int, int i, int n0, int, int g, int TNq, const float (&tot)[kMaxQ]) const {
         if (i >= p.N) return;
+        const __half* Rh16 = reinterpret_cast<const __half*>(Rhi);
+        const __half* Rl16 = reinterpret_cast<const __half*>(Rlo);
         const int N = p.N;
         const float kap = __ldg(p.kappa + i);
 #pragma unroll 4
@@ -37,10 +41,12 @@ struct RhsEpi {
             const int b = n0 + g * TNq + j;
             if (j >= TNq || b >= p.B) break;
             const float* yb = y + (size_t)b * 3 * N + i;
-            const float r = Rhi[(size_t)b * KPa + i] + Rlo[(size_t)b * KPa + i];
+            const float r = wscale ? __half2float(Rh16[(size_t)b * KPa + i]) + __half2float(Rl16[(size_t)b * KPa + i]) * 4.8828125e-4f
+                                   : Rhi[(size_t)b * KPa + i] + Rlo[(size_t)b * KPa + i];
             // lateral-gain sweep: the contraction holds g_b-scaled lateral input (its stimulus / bias columns were divided
             // by g_b in the operand), the within-column input comes from the operand kernel
-            const float cur = loc ? fmaf(__ldg(p.lat_gain + b), tot[j], loc[(size_t)b * N + i]) : tot[j];
+            const float tj = tot[j] * ws;
+            const float cur = loc ? fmaf(__ldg(p.lat_gain + b), tj, loc[(size_t)b * N + i]) : tj;
             const float total = cur * p.c.tau_s;
             float* fb = f + (size_t)b * 3 * N + i;
             fb[0] = (total * p.c.R - yb[0]) * inv_tm;
@@ -56,8 +62,22 @@ struct RhsEpi {
 // Destination of one trial's operand row (and, in lateral-gain sweeps, of its within-column input plane).
 struct OperandDst {
     float* hi; float* lo; float* loc;       // loc == NULL unless DevProblem::lat_gain is set
-    int KPa;
+    int KPa;                                // elements per operand row
+    unsigned int* ovf;                      // != NULL: 16-bit operand format -- hi / lo are planes of FP16 (x = xh + xl / 2048) with
+                                            // KPa halves per row; *ovf is raised when a value does not fit FP16
 };
+
+// one operand value in the destination's format: (hi, lo) as the floats the contraction will see
+ODECOL_DEVINL void operand_split(const OperandDst& d, float x, float& h, float& l, F16x2& t) {
+    if (d.ovf) {
+        t = f16_split2(x);
+        h = __half2float(__ushort_as_half(t.h));
+        l = __half2float(__ushort_as_half(t.l)) * 4.8828125e-4f;
+    } else {
+        h = tf32_rna(x);
+        l = tf32_rna(x - h);
+    }
+}
 
 // Populations k .. k+3 of trial b from their stage state: r = phi(V - A) -> hi / lo (16-byte stores).  In a lateral-gain sweep
 // the within-column input W_local (*) r of the four populations is formed here as well: the eight rates of a column sit in
@@ -66,14 +86,22 @@ struct OperandDst {
 ODECOL_DEVINL void operand_block4(const DevProblem& p, const OperandDst& d, int b, int k, bool in_range, const float4& V,
                                   const float4& A, bool pair8) {
     float r[4], h[4], l[4];
+    F16x2 t[4];
+    bool big = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         r[e] = in_range ? phi_fast((&V.x)[e] - (&A.x)[e]) : 0.f;
-        h[e] = tf32_rna(r[e]);
-        l[e] = tf32_rna(r[e] - h[e]);
+        big |= !(fabsf(r[e]) <= kF16Limit);
+        operand_split(d, r[e], h[e], l[e], t[e]);
     }
     const size_t ro = (size_t)b * d.KPa;
-    if (in_range) {
+    if (in_range && d.ovf) {
+        if (big) *d.ovf = 1u;
+        uint16_t* h16 = reinterpret_cast<uint16_t*>(d.hi) + ro + k;
+        uint16_t* l16 = reinterpret_cast<uint16_t*>(d.lo) + ro + k;
+        *reinterpret_cast<uint2*>(h16) = make_uint2((uint32_t)t[0].h | ((uint32_t)t[1].h << 16), (uint32_t)t[2].h | ((uint32_t)t[3].h << 16));
+        *reinterpret_cast<uint2*>(l16) = make_uint2((uint32_t)t[0].l | ((uint32_t)t[1].l << 16), (uint32_t)t[2].l | ((uint32_t)t[3].l << 16));
+    } else if (in_range) {
         st4(d.hi + ro + k, make_float4(h[0], h[1], h[2], h[3]));
         st4(d.lo + ro + k, make_float4(l[0], l[1], l[2], l[3]));
     }
@@ -111,9 +139,16 @@ ODECOL_DEVINL void operand_tail(const DevProblem& p, const OperandDst& d, int b,
     const float* ku = p.knot_u + (size_t)b * p.knot_stride_b;
     for (int k = N + threadIdx.x; k < Kaug; k += blockDim.x) {
         const float v = k < N + p.n_in ? knot_value(p.knot_t, ku, p.n_in, idx, tcl, k - N) * ginv : ginv;
-        const float h = tf32_rna(v);
-        d.hi[ro + k] = h;
-        d.lo[ro + k] = tf32_rna(v - h);
+        if (d.ovf) {
+            if (!(fabsf(v) <= kF16Limit)) *d.ovf = 1u;
+            const F16x2 t = f16_split2(v);
+            reinterpret_cast<uint16_t*>(d.hi)[ro + k] = t.h;
+            reinterpret_cast<uint16_t*>(d.lo)[ro + k] = t.l;
+        } else {
+            const float h = tf32_rna(v);
+            d.hi[ro + k] = h;
+            d.lo[ro + k] = tf32_rna(v - h);
+        }
     }
     if (d.loc && !pair8) {
         __syncthreads();
@@ -123,7 +158,12 @@ ODECOL_DEVINL void operand_tail(const DevProblem& p, const OperandDst& d, int b,
             if (p.W_local) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (c0 + j < N) acc = fmaf(__ldg(p.W_local + (size_t)i * 8 + j), d.hi[ro + c0 + j] + d.lo[ro + c0 + j], acc);
+                    if (c0 + j < N) {
+                        const float rj = d.ovf ? __half2float(reinterpret_cast<const __half*>(d.hi)[ro + c0 + j]) +
+                                                     __half2float(reinterpret_cast<const __half*>(d.lo)[ro + c0 + j]) * 4.8828125e-4f
+                                               : d.hi[ro + c0 + j] + d.lo[ro + c0 + j];
+                        acc = fmaf(__ldg(p.W_local + (size_t)i * 8 + j), rj, acc);
+                    }
             }
             d.loc[(size_t)b * N + i] = acc;
         }
@@ -135,10 +175,11 @@ ODECOL_DEVINL bool aligned16(const void* q) { return ((uintptr_t)q & 15) == 0; }
 // one CTA per trial, per-trial time (NULL -> shared time t_shared); N must be a multiple of 4 (the staged entry points check)
 __global__ void k_em_operand(DevProblem p, const float* __restrict__ y, const float* __restrict__ t_trial,
                              float t_shared, float* __restrict__ hi, float* __restrict__ lo, int KPa,
-                             const int* __restrict__ active = nullptr, float* __restrict__ loc = nullptr) {
+                             const int* __restrict__ active = nullptr, float* __restrict__ loc = nullptr,
+                             unsigned int* __restrict__ ovf = nullptr) {
     const int b = blockIdx.x, N = p.N;
     if (active && !active[b]) return;          // adaptive sweeps: a finished trial's drift is never read again
-    const OperandDst d{hi, lo, loc, KPa};
+    const OperandDst d{hi, lo, loc, KPa, ovf};
     const float* yb = y + (size_t)b * 3 * N;
     const bool pair8 = (N & 7) == 0 && (!p.W_local || aligned16(p.W_local));
     // four populations per thread and iteration through 16-byte accesses (with one scalar load pair in flight per thread
@@ -430,7 +471,8 @@ __global__ void k_em_fill_nan(DevProblem p, const int* __restrict__ status, cons
 struct EmLayout {
     int Np, Bp, KPa, TN;
     size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_Rhi1, off_Rlo1, off_f, off_fm, off_yfull, off_ymid, off_yhalf, off_y, off_yprev,
-           off_state, off_loc, off_loc1, total;
+           off_state, off_loc, off_loc1, off_aux, total;
+    int KP16;
 };
 
 static EmLayout em_layout(const DevProblem& p) {
@@ -452,6 +494,8 @@ static EmLayout em_layout(const DevProblem& p) {
     L.off_state = take(128ull * p.B + 1024);
     L.off_loc = take(p.lat_gain ? 4ull * p.B * p.N : 0);       // within-column input planes of the lateral-gain sweep
     L.off_loc1 = take(p.lat_gain ? 4ull * p.B * p.N : 0);
+    L.off_aux = take(64);                                       // 16-bit operand format: 1 / weight scale, max|W| scratch, overflow flag
+    L.KP16 = round_up(p.N + p.n_in + 1, BK16);                  // its rows live in the same buffers (2 KP16 <= 4 KPa bytes)
     L.total = o;
     return L;
 }
@@ -460,9 +504,14 @@ static EmLayout em_layout(const DevProblem& p) {
 
 size_t stage_em_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_layout(p).total; }
 
-int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
-                 uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
-                 int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s) {
+// f16: the drift contractions read FP16 pairs (half the tensor-core instructions and operand bytes of the TF32 split: the
+// contraction is 93 % of a round at N = 8192 and runs at 0.89 of the tensor roofline).  Returns kRetryTf32 when an operand
+// value did not fit FP16 (the flag is read at the host's polls): the caller repeats the solve in the TF32 format.
+static constexpr int kRetryTf32 = 1 << 20;
+static int em_fwd_impl(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                       uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
+                       int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s,
+                       bool f16) {
     using namespace tc;
     const EmLayout L = em_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -477,26 +526,42 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     const size_t st = (size_t)p.B * 3 * p.N;
 
     if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
-    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    count_launch();
+    float* aux = F(L.off_aux);                                  // [0] 1 / weight scale, [1] max|W| bits, [2] overflow flag
+    unsigned int* ovf = f16 ? reinterpret_cast<unsigned int*>(aux + 2) : nullptr;
+    const int KPr = f16 ? L.KP16 : L.KPa;                       // elements per operand row in the format in use
+    if (f16) {
+        if (cudaMemsetAsync(aux, 0, 64, s) != cudaSuccess) return ODECOL_E_CUDA;
+        k_absmax<<<148, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<unsigned int*>(aux + 1));
+        k_split16_w<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<__half*>(Whi), reinterpret_cast<__half*>(Wlo),
+                                        L.Np, L.KP16, reinterpret_cast<unsigned int*>(aux + 1), aux);
+        count_launch(2);
+    } else {
+        k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+        count_launch();
+    }
     if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(yprev, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (y_steps && cudaMemcpyAsync(y_steps, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
-    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
-        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+    if (f16) {
+        if (!make_map16(&mWhi, Whi, L.Np, L.KP16, L.KP16, BM, false) || !make_map16(&mWlo, Wlo, L.Np, L.KP16, L.KP16, BM, false) ||
+            !make_map16(&mRhi, Rhi, L.Bp, L.KP16, L.KP16, L.TN, false) || !make_map16(&mRlo, Rlo, L.Bp, L.KP16, L.KP16, L.TN, false))
+            return ODECOL_E_CUDA;
+    } else if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+               !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
         return ODECOL_E_CUDA;
-    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, f16 ? L.KP16 / BK16 : L.KPa / BK, 0, nullptr};
     // CTA pairs (tcgen05 cta_group::2, ODECOL_PAIR=1): each SM stages half of the trial tile
-    const bool use_pair = pair_enabled() && tsh.MT % 2 == 0;
+    const bool use_pair = !f16 && pair_enabled() && tsh.MT % 2 == 0;
     CUtensorMap mRhHi, mRhLo;
     if (use_pair && (!make_map(&mRhHi, Rhi, L.Bp, L.KPa, L.KPa, L.TN / 2) || !make_map(&mRhLo, Rlo, L.Bp, L.KPa, L.KPa, L.TN / 2)))
         return ODECOL_E_CUDA;
     auto rhs = [&](const float* ysrc, float* fdst) {
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = loc;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = KPr; e.loc = loc; e.wscale = f16 ? aux : nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (f16) return launch_contract16(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
         if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi, mRhLo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
@@ -505,15 +570,19 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     float *Rhi1 = F(L.off_Rhi1), *Rlo1 = F(L.off_Rlo1);
     float* loc1 = p.lat_gain ? F(L.off_loc1) : nullptr;
     CUtensorMap mRhi1, mRlo1, mRhHi1, mRhLo1;
-    if (adaptive) {
+    if (adaptive && f16) {
+        if (!make_map16(&mRhi1, Rhi1, L.Bp, L.KP16, L.KP16, L.TN, false) || !make_map16(&mRlo1, Rlo1, L.Bp, L.KP16, L.KP16, L.TN, false))
+            return ODECOL_E_CUDA;
+    } else if (adaptive) {
         if (!make_map(&mRhi1, Rhi1, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo1, Rlo1, L.Bp, L.KPa, L.KPa, L.TN)) return ODECOL_E_CUDA;
         if (use_pair && (!make_map(&mRhHi1, Rhi1, L.Bp, L.KPa, L.KPa, L.TN / 2) || !make_map(&mRhLo1, Rlo1, L.Bp, L.KPa, L.KPa, L.TN / 2)))
             return ODECOL_E_CUDA;
     }
     auto rhs_mid = [&](const float* ysrc, float* fdst) {
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi1; e.Rlo = Rlo1; e.f = fdst; e.KPa = L.KPa; e.loc = loc1;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi1; e.Rlo = Rlo1; e.f = fdst; e.KPa = KPr; e.loc = loc1; e.wscale = f16 ? aux : nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (f16) return launch_contract16(mWhi, mWlo, mRhi1, mRlo1, tsh, e, s);
         if (use_pair) return launch_contract_pair(mWhi, mWlo, mRhHi1, mRhLo1, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi1, mRlo1, tsh, e, s);
     };
@@ -534,7 +603,7 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
             const float next_t = nx < t_end ? nx : t_end;
             int j_hi = j;
             while (j_hi < T && ts[j_hi] <= next_t) ++j_hi;            // outputs the loop emits once curr_t >= ts[j]
-            k_em_operand<<<p.B, 128, 0, s>>>(p, y, nullptr, c0, Rhi, Rlo, L.KPa, nullptr, loc);
+            k_em_operand<<<p.B, 128, 0, s>>>(p, y, nullptr, c0, Rhi, Rlo, KPr, nullptr, loc, ovf);
             count_launch();
             const int rc = rhs(y, f0);
             if (rc != ODECOL_OK) return rc;
@@ -549,6 +618,12 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
             if (y_steps && cudaMemcpyAsync(y_steps + (size_t)k * st, y, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
                 return ODECOL_E_CUDA;
             if (k > (1LL << 40)) return ODECOL_E_SHAPE;
+        }
+        if (f16) {                                            // did every operand value fit FP16?
+            unsigned int h_ovf = 0;
+            if (cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (h_ovf) return kRetryTf32;
         }
         if (n_accept || n_reject || status) {
             std::vector<int> hk(p.B, (int)k), hz(p.B, 0);
@@ -585,23 +660,31 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     const long long max_attempts = (long long)(4.0 * span / dt_min) + 4LL * T + 1024;
     const int tb = (p.B + 127) / 128;
     k_ad_init<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt, seed, trial_offset);
-    k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, L.KPa, nullptr, loc);
+    k_em_operand<<<p.B, 128, 0, s>>>(p, y, S.t_cur, 0.f, Rhi, Rlo, KPr, nullptr, loc, ovf);
     count_launch(2);
     int h_active = p.B;
+    unsigned int h_ovf = 0;
     for (long long round = 0; round < max_attempts && h_active > 0; ++round) {
         int rc = rhs(y, f0);
         if (rc != ODECOL_OK) return rc;
-        k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid, OperandDst{Rhi1, Rlo1, loc1, L.KPa});
+        k_ad_half1<<<p.B, 256, 0, s>>>(p, S, y, f0, yfull, ymid, OperandDst{Rhi1, Rlo1, loc1, KPr, ovf});
         rc = rhs_mid(ymid, fm);
         if (rc != ODECOL_OK) return rc;
         k_ad_half2<<<p.B, 256, 0, s>>>(p, S, ymid, fm, yfull, yhalf, rtol, atol);
         k_ad_control<<<tb, 128, 0, s>>>(p, S, ts_dev, T, dt_min, seed, trial_offset, max_attempts);
-        k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out, OperandDst{Rhi, Rlo, loc, L.KPa});
+        k_ad_commit<<<p.B, 256, 0, s>>>(p, S, ts_dev, T, y, yprev, yhalf, y_out, OperandDst{Rhi, Rlo, loc, KPr, ovf});
         count_launch(4);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (f16 && cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
             if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (h_ovf) return kRetryTf32;
         }
+    }
+    if (f16) {                                                // rounds since the last poll
+        if (cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (h_ovf) return kRetryTf32;
     }
     k_em_fill_nan<<<p.B, 128, 0, s>>>(p, S.status, S.next_out, T, y_out);
     count_launch();
@@ -609,6 +692,18 @@ int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y
     if (n_reject && cudaMemcpyAsync(n_reject, S.n_rej, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (status && cudaMemcpyAsync(status, S.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int stage_em_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                 uint64_t seed, int64_t trial_offset, float dt, int adaptive, float rtol, float atol, float dt_min,
+                 int* n_accept, int* n_reject, int* status, float* y_steps, void* ws, size_t ws_bytes, cudaStream_t s) {
+    static const bool f16_env = [] { const char* e = getenv("ODECOL_EM16"); return e ? atoi(e) != 0 : true; }();
+    int rc = em_fwd_impl(p, ts_dev, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min, n_accept, n_reject,
+                         status, y_steps, ws, ws_bytes, s, f16_env);
+    if (rc == kRetryTf32)
+        rc = em_fwd_impl(p, ts_dev, T, y0, y_out, dW, seed, trial_offset, dt, adaptive, rtol, atol, dt_min, n_accept, n_reject,
+                         status, y_steps, ws, ws_bytes, s, false);
+    return rc;
 }
 
 

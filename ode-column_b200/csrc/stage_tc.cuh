@@ -215,7 +215,9 @@ ODECOL_DEVINL void tile_coords(int tile, int MT, int NT, int& m, int& nt) {
     m = grp * kTileGroupM + (within - nt * gm);
 }
 
-template <class Epi, bool CHUNKED>
+// F16: both operands as FP16 pairs (see "16-bit operand format" above): K blocks of 64 elements, kind::f16 products, the
+// cross sums scaled by 2^-11 on the way out of tensor memory; ts.KB counts 64-element blocks then.
+template <class Epi, bool CHUNKED, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
               const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TileShape ts, Epi epi) {
@@ -224,7 +226,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)ts.TN * BK * 4;
+    constexpr int KEL = F16 ? BK16 : BK;               // operand elements per K block (one 128-byte row either way)
+    constexpr int CKB = F16 ? kChunkKB / 2 : kChunkKB; // K blocks per accumulator chunk (512 elements of K)
+    constexpr float XS = F16 ? 4.8828125e-4f : 1.0f;   // scale of the cross sums (the low FP16 planes carry 2^11)
+    const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)ts.TN * 128;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
     const uint32_t tfull = smem_u32(&bars[2 * STAGES]), tempty = smem_u32(&bars[2 * STAGES + 1]);
@@ -275,17 +280,17 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t base = ring + stage * stage_bytes, fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, stage_bytes);
-                    tma_load_2d(base, &mA_hi, fb, kb * BK, m0);
-                    tma_load_2d(base + a_bytes, &mA_lo, fb, kb * BK, m0);
-                    tma_load_2d(base + 2 * a_bytes, &mB_hi, fb, kb * BK, n0 + ts.b_row0);
-                    tma_load_2d(base + 2 * a_bytes + b_bytes, &mB_lo, fb, kb * BK, n0 + ts.b_row0);
+                    tma_load_2d(base, &mA_hi, fb, kb * KEL, m0);
+                    tma_load_2d(base + a_bytes, &mA_lo, fb, kb * KEL, m0);
+                    tma_load_2d(base + 2 * a_bytes, &mB_hi, fb, kb * KEL, n0 + ts.b_row0);
+                    tma_load_2d(base + 2 * a_bytes + b_bytes, &mB_lo, fb, kb * KEL, n0 + ts.b_row0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(ts.TN);
+            const uint32_t idesc = F16 ? make_idesc16(ts.TN) : make_idesc(ts.TN);
             const uint32_t d_small = tmem_base + kMainAcc * acc_stride;
             int stage = 0; uint32_t phase = 0, tphase = 0;
             int c = 0;                                    // chunk counter (chunked mode), runs on across tiles
@@ -293,7 +298,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                 int jj = 0;
                 uint32_t d_main = tmem_base, d_cross = tmem_base + acc_stride;
                 for (int kb = 0; kb < ts.KB; ++kb) {
-                    if (kb % kChunkKB == 0) {
+                    if (kb % CKB == 0) {
                         const int set = c & 1;
                         mbar_wait(cempty0 + 8 * set, (uint32_t)((c >> 1) & 1) ^ 1u);
                         tc_fence_after();
@@ -307,15 +312,21 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
                     const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k, ++jj) {
+                    for (int k = 0; k < 4; ++k, ++jj) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, jj != 0);
-                        umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, jj != 0);
+                        if (F16) {
+                            umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, jj != 0);
+                            umma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, jj != 0);
+                        } else {
+                            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, jj != 0);
+                            umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, jj != 0);
+                        }
                     }
                     umma_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    if (kb % kChunkKB == kChunkKB - 1 || kb == ts.KB - 1) { umma_commit(cfull0 + 8 * (c & 1)); ++c; }
+                    if (kb % CKB == CKB - 1 || kb == ts.KB - 1) { umma_commit(cfull0 + 8 * (c & 1)); ++c; }
                 }
             }
             for (int tile = blockIdx.x; !chunked && tile < tiles; tile += gridDim.x) {
@@ -329,11 +340,18 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + a_bytes);
                     const uint64_t b_hi = make_smem_desc(base + 2 * a_bytes), b_lo = make_smem_desc(base + 2 * a_bytes + b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k, ++j) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 TF32 = 32 bytes along the swizzled row
-                        umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
-                        umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
-                        umma_tf32(tmem_base + (uint32_t)(j % kMainAcc) * acc_stride, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                    for (int k = 0; k < 4; ++k, ++j) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 TF32 / 16 FP16 = 32 bytes along the swizzled row
+                        const uint32_t d_main = tmem_base + (uint32_t)(j % kMainAcc) * acc_stride;
+                        if (F16) {
+                            umma_f16(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                            umma_f16(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                        } else {
+                            umma_tf32(d_small, a_lo + adv, b_hi + adv, idesc, j != 0);
+                            umma_tf32(d_small, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, j >= kMainAcc);
+                        }
                     }
                     umma_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -362,7 +380,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                 const uint32_t lb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TNq);
 #pragma unroll
                 for (int q = 0; q < kMaxQ; ++q) tot[q] = 0.f;
-                const int nchunks = (ts.KB + kChunkKB - 1) / kChunkKB;
+                const int nchunks = (ts.KB + CKB - 1) / CKB;
                 for (int cc = 0; cc < nchunks; ++cc, ++cchunk) {
                     const int set = cchunk & 1;
                     mbar_wait(cfull0 + 8 * set, (uint32_t)((cchunk >> 1) & 1));
@@ -383,7 +401,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                         for (int d = 0; d < 4; ++d) {
                             if (4 * (q0 + d) < TNq) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) tot[4 * (q0 + d) + e] += __uint_as_float(ux[d][e]) + __uint_as_float(um[d][e]);
+                                for (int e = 0; e < 4; ++e) tot[4 * (q0 + d) + e] += __uint_as_float(ux[d][e]) * XS + __uint_as_float(um[d][e]);
                             }
                         }
                     }
@@ -409,7 +427,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float sum = __uint_as_float(u[kMainAcc][e]);                 // cross terms first (small)
+                        float sum = __uint_as_float(u[kMainAcc][e]) * XS;            // cross terms first (small)
 #pragma unroll
                         for (int a = 0; a < kMainAcc; ++a) sum += __uint_as_float(u[a][e]);
                         tot[4 * q + e] = sum;
@@ -697,6 +715,26 @@ static int launch_contract(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
 #endif
     if (ts.KB > kChunkMin && !nochunk) k_tc_contract<Epi, true><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
     else k_tc_contract<Epi, false><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+// the same with both operands as FP16 pairs (maps from make_map16; ts.KB = K / 64)
+template <class Epi>
+static int launch_contract16(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                             const TileShape& ts, const Epi& epi, cudaStream_t s) {
+    const size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * (size_t)ts.TN * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tc_contract<Epi, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_contract<Epi, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return ODECOL_E_CUDA;
+        configured = true;
+    }
+    const int tiles = ts.MT * ts.NT;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (ts.KB > kChunkMin / 2) k_tc_contract<Epi, true, true><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
+    else k_tc_contract<Epi, false, true><<<grid, kThreads, smem, s>>>(a_hi, a_lo, b_hi, b_lo, ts, epi);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }
