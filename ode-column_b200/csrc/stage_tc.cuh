@@ -1157,17 +1157,15 @@ struct FwdEpiT {
                     st_global_if(ph, h, ok);
                     st_global_if(ph + lo_off, tf32_rna(oR[e] - h), ok);
                 }
-                if (S == 4 && ok) {
-                    if (yr) {
-                        float* y = yr + (size_t)e * 3 * N;
-                        st_global(y, oNV[e]); st_global(y + N, oNA[e]); st_global(y + 2 * N, oNF[e]);
-                    }
-                    if (S == 4 && ysel_row) {
-                        float* y = ysel_row + (size_t)(b0 + e) * G;
-                        if (gV >= 0) st_global(y + gV, oNV[e]);
-                        if (gA >= 0) st_global(y + gA, oNA[e]);
-                        if (gF >= 0) st_global(y + gF, oNF[e]);
-                    }
+                if (S == 4 && yr && ok) {
+                    float* y = yr + (size_t)e * 3 * N;
+                    st_global(y, oNV[e]); st_global(y + N, oNA[e]); st_global(y + 2 * N, oNF[e]);
+                }
+                if (S == 4 && ysel_row) {          // selected components: predicated stores (most populations select nothing)
+                    float* y = ysel_row + (size_t)(b0 + e) * G;
+                    st_global_if(y + gV, oNV[e], ok && gV >= 0);
+                    st_global_if(y + gA, oNA[e], ok && gA >= 0);
+                    st_global_if(y + gF, oNF[e], ok && gF >= 0);
                 }
             }
         }

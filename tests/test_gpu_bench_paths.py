@@ -172,6 +172,49 @@ def test_rk4_forward_repeats_in_tf32_when_fp16_cannot_hold_the_operand(tmp_path)
     assert float((c["y"] - d["y"]).abs().max()) <= 2e-6 * float(d["y"].abs().max())
 
 
+_EM_RETRY_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import odecol
+cfg = odecol.load_config(sys.argv[1] + "/config/model.toml")
+B, cols = 5, 32
+N = 8 * cols
+sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device="cuda")
+gen = torch.Generator().manual_seed(5)
+amp = torch.rand(B, cols, generator=gen) * 30.0
+kt, ku = odecol.step_knots(0.002, 0.006, 0.01, amp, 1e-3)
+sheet.set_knots(kt.cuda(), ku.cuda())
+ts = torch.linspace(0.0, 0.01, 6).cuda()
+y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen), torch.rand(B, N, generator=gen) * 2), 1)
+y0[:, 3] = float(sys.argv[3])
+adaptive = sys.argv[4] == "1"
+with torch.no_grad():
+    y = odecol.sdeint(sheet, y0.cuda(), ts, method="euler", dt=1e-3 if adaptive else 1e-4, adaptive=adaptive, rtol=1e-4, atol=1e-3, dt_min=1e-5, seed=3,
+                      options={"sigma_scale": torch.full((B,), 0.1)})
+torch.save(y.cpu(), sys.argv[2])
+"""
+
+
+@pytest.mark.parametrize("adaptive", ["0", "1"])
+def test_staged_euler_maruyama_repeats_in_tf32_when_fp16_cannot_hold_the_operand(tmp_path, adaptive):
+    """The drift contractions of the staged Euler-Maruyama solvers read FP16 pairs; the host reads the overflow flag at its
+    polls and repeats the solve in the TF32 format.  Same criterion as for the rk4 forward kernel above."""
+    import subprocess
+    import sys
+
+    def run(em16, v_hot):
+        out = tmp_path / f"e_{em16}_{int(v_hot)}.pt"
+        env = dict(os.environ, ODECOL_EM16=em16)
+        subprocess.run([sys.executable, "-c", _EM_RETRY_SCRIPT, ROOT, str(out), str(v_hot), adaptive], env=env, check=True, timeout=600)
+        return torch.load(out)
+
+    a, b = run("1", 1400.0), run("0", 1400.0)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    c, d = run("1", 4.0), run("0", 4.0)
+    assert not torch.equal(c, d)
+    assert float((c - d).abs().max()) <= (2e-4 if adaptive == "1" else 2e-6) * float(d.abs().max())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # adaptive Euler-Maruyama vs the oracle's step-doubling loop
 # ----------------------------------------------------------------------------------------------------------------------
