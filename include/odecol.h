@@ -22,7 +22,13 @@
  *   - return value: 0 (ODECOL_OK) or a negative error code, see odecol_strerror(); nothing throws;
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
- *   - there is NO CPU implementation behind this ABI.
+ *   - there is NO CPU implementation behind this ABI;
+ *   - arithmetic of the staged tensor-core family (N > 128): float32 state, contractions as error-corrected split
+ *     products on tcgen05 (operand = high + low half, three products, FP32 accumulation: 2^-22 relative).  The halves are
+ *     TF32 numbers, or -- in the persistent rk4 forward kernel and the Euler-Maruyama drift -- FP16 numbers.  FP16 cannot
+ *     hold an operand value (a firing rate, a stimulus) beyond +-6e4: the kernels detect that on the device and the same
+ *     call then repeats the solve on TF32 halves (rk4: a second kernel of the same launch sequence that returns at once
+ *     otherwise; Euler-Maruyama: at the host polls these entry points already have), so results never depend on it.
  *
  * The problem integrated (all three reference networks reduce to it):
  *
@@ -70,7 +76,7 @@ enum {
 enum {
     ODECOL_FLAG_FORCE_STAGED = 1,  /* use the staged (global-state) FP32-FFMA kernel family even when the
                                       problem fits the persistent on-chip family; for testing and measurement */
-    ODECOL_FLAG_FORCE_TENSOR = 2,  /* use the staged tcgen05 (3xTF32) family regardless of size               */
+    ODECOL_FLAG_FORCE_TENSOR = 2,  /* use the staged tcgen05 (split-operand, FP32-accurate) family regardless of size */
     ODECOL_FLAG_DETERMINISTIC = 4  /* tensor family, rk4 reverse sweep: reduce grad_W_aug over trials in a fixed order
                                       (per-split copies summed at the end) instead of float atomics: bit-reproducible
                                       gradients for ~2 % of the sweep's time                                      */

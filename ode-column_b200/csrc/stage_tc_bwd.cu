@@ -1248,16 +1248,19 @@ static int tc_rk4_bwd_impl(const DevProblem& p, const float* t_dev, int T, const
     // the four reverse stages of a step as one cooperative launch (ODECOL_PERSISTENT=0: one launch per stage)
     const char* pe = getenv("ODECOL_PERSISTENT");
     bool use_chain = (pe ? atoi(pe) != 0 : true) && L.NPk / BK <= kChunkMin && L.KPa / BK <= kChunkMin;   // long K: chunked k_tc_contract
-    // ODECOL_FUSE_DW=1: the dW contraction as a fifth phase of the chain launch instead of its own launch.  Measured on
-    // par with the default (separate launch + replay one step ahead): profiles/r1_session2.md section 5.
+    // The dW contraction runs as a fifth phase of the chain launch (its operands are complete long before the chain ends, so
+    // the MMA warp contracts dW while the stage-1 epilogues still stream): two launches per reverse step instead of three.
+    // Round 1 measured it on par with a launch of its own; since the epilogues got leaner it is 2.6 % of the sweep
+    // (577 against 592 ms, profiles/r2_session3_ab.md).  ODECOL_FUSE_DW=0: separate launch (always so for the fixed-order
+    // reduction, whose per-split copies live in the stand-alone kernel).
     const char* fe = getenv("ODECOL_FUSE_DW");
-    const bool fuse_dw = use_chain && (fe ? atoi(fe) != 0 : false);
+    const bool dw_fixed_order = (p.flags & ODECOL_FLAG_DETERMINISTIC) != 0;     // default: float atomics (2 % faster sweep)
+    const bool fuse_dw = use_chain && !dw_fixed_order && !dw_pair_enabled() && (fe ? atoi(fe) != 0 : true);
     // ODECOL_FLAG_DETERMINISTIC: every (output tile, row split) accumulates into its own copy of grad_W_aug across the whole
     // sweep (one CTA per (tile, split) and launch, launches ordered on the stream; the running sum is fetched at kernel start
     // and stored back at the end), the copies are summed in a fixed order after the last step -- the gradient is
     // bit-reproducible.  Measured: reverse sweep 633-639 ms against 621-625 ms with float atomics (A/B on one box).
     float* dw_partial = nullptr;
-    const bool dw_fixed_order = (p.flags & ODECOL_FLAG_DETERMINISTIC) != 0;     // default: float atomics (2 % faster sweep)
     if (dw_fixed_order && !fuse_dw && !(dw_pair_enabled() && ds.MT % 2 == 0) && ds.Z <= L.dwZ) {
         dw_partial = reinterpret_cast<float*>(w + L.off_dwpart);
         if (cudaMemsetAsync(dw_partial, 0, sizeof(float) * (size_t)ds.Z * p.N * p.ld_w, s) != cudaSuccess) return ODECOL_E_CUDA;

@@ -78,6 +78,7 @@ C4_CASES = [
     (4790, 10, False, "1", False),       # recompute mode: trajectory + three recomputed contractions per reverse step
     (4790, 10, True, "0", False),        # one launch per stage instead of the cooperative kernels
     (8192, 6, True, "1", False),         # the benched batch: TN = 112, 296 tiles = exactly two per CTA
+    (4790, 10, True, "1:nofuse", False), # dW as a launch of its own (ODECOL_FUSE_DW=0) instead of the chain's fifth phase
 ]
 
 
@@ -94,7 +95,10 @@ def test_rk4_adjoint_at_the_benchmarked_shape(cfg, B, T, ckpt, persistent, with_
     tro, gy0o, gWo, gUo, gbo = _oracle_rk4_grads(lf, kt, ku, tv, y0, sel, wgt)
 
     old = os.environ.get("ODECOL_PERSISTENT")
+    persistent, _, variant = persistent.partition(":")
     os.environ["ODECOL_PERSISTENT"] = persistent
+    if variant == "nofuse":
+        os.environ["ODECOL_FUSE_DW"] = "0"
     try:
         y0p = y0.to(DEV).requires_grad_(True)
         yp = odecol.odeint(sheet, y0p, tv.to(DEV), method="rk4", components=sel, options={"checkpoint": ckpt})
@@ -102,6 +106,7 @@ def test_rk4_adjoint_at_the_benchmarked_shape(cfg, B, T, ckpt, persistent, with_
         (yp * wgt.to(DEV)).sum().backward()
         torch.cuda.synchronize()
     finally:
+        os.environ.pop("ODECOL_FUSE_DW", None)
         if old is None:
             os.environ.pop("ODECOL_PERSISTENT", None)
         else:
