@@ -106,6 +106,14 @@ ODECOL_DEVINL float tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// predicated read-only load: 0 when the predicate is false (no branch, the address is never formed into an access then)
+ODECOL_DEVINL float ldg_if(const float* p, bool ok) {
+    float v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+                 : "=f"(v) : "l"(p), "r"((int)ok));
+    return v;
+}
+
 // ---- 16-bit operand format of the persistent forward solve: every operand as two FP16 planes, x s = xh + xl / 2048
 //   xh = fp16(x s), xl = fp16((x s - xh) 2048): 11 + 11 mantissa bits like the TF32 split, the low plane kept in FP16's normal
 //   range by its 2^11 (Ootomo & Yokota's error-corrected tensor-core product).  s is a power of two: for W_aug the one

@@ -33,12 +33,14 @@ struct BwdEpiT {
     const int* inv;        // [3N]
     float gamma, inv_tm, inv_ta, inv_ts;
     float dt, h8p;
+    const float* gy_step;  // row n of grad_y
     int needF;             // 0: no F component carries a loss gradient -> lambda_F is identically zero, its plane is never touched
 
     ODECOL_DEVINL void prepare() {
         dt = __fsub_rn(__ldg(t + n + 1), __ldg(t + n));
         h8p = n > 0 ? __fsub_rn(__ldg(t + n), __ldg(t + n - 1)) * 0.125f : 0.f;
         needF = __ldg(inv + 3 * p.N);
+        gy_step = grad_y + (size_t)n * p.B * G;
     }
 
     struct Group { float4 aV, aA, dr, lV, lA, lF, p4V, p4A, p3V, p3A, gv, ga, gf; };
@@ -49,17 +51,15 @@ struct BwdEpiT {
         if (S == 1) { L.aV = ld4s(acurT + oq); L.aA = ld4s(acurT + pl + oq); }
         if (S <= 3) { L.p4V = ld4s(b4T + oq); L.p4A = ld4s(b4T + pl + oq); }
         if (S == 2) { L.p3V = ld4s(b3T + oq); L.p3A = ld4s(b3T + pl + oq); }
-        if (S == 1) {                       // loss gradient of the selected components at grid point n
-            L.gv = L.ga = L.gf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (S == 1) {                       // loss gradient of the selected components at grid point n: predicated loads off
+            const float* gy = gy_step + (size_t)b0 * G;      // one row address (most populations select nothing)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int b = b0 + e;
-                if (b < p.B) {
-                    const float* gy = grad_y + ((size_t)n * p.B + b) * G;
-                    if (gV >= 0) (&L.gv.x)[e] = __ldg(gy + gV);
-                    if (gA >= 0) (&L.ga.x)[e] = __ldg(gy + gA);
-                    if (gF >= 0) (&L.gf.x)[e] = __ldg(gy + gF);
-                }
+                const bool ok = b0 + e < p.B;
+                (&L.gv.x)[e] = ldg_if(gy + gV, ok && gV >= 0);
+                (&L.ga.x)[e] = ldg_if(gy + gA, ok && gA >= 0);
+                (&L.gf.x)[e] = ldg_if(gy + gF, ok && gF >= 0);
+                gy += G;
             }
         }
     }
