@@ -974,7 +974,7 @@ def net_family(ext, odecol, net, y0, tv, args):
     from ode_column_b200.solvers import _Setup
     setup = _Setup(net, y0, tv, args.family)
     fam = setup.problem(setup.lf.W_aug).kernel_family(ext.OP_RK4_FWD)
-    return {0: "persistent on-chip (FP32 FFMA)", 1: "staged FP32-FFMA", 2: "staged tcgen05 3xTF32"}.get(fam, str(fam))
+    return {0: "persistent on-chip (FP32 FFMA)", 1: "staged FP32-FFMA", 2: "staged tcgen05, split operands (FP16 pairs forward / TF32 pairs reverse)"}.get(fam, str(fam))
 
 
 def main():

@@ -281,6 +281,7 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (kEpiRegs && warp < kEpiWarp0) setmaxnreg_dec<32>();
 
     if (warp == kTmaWarp) {
         if (lane == 0) {
@@ -411,7 +412,8 @@ k_tc_bwd_chain(const __grid_constant__ CUtensorMap mW_hi, const __grid_constant_
                 tphase ^= 1;
             }
         }
-    } else {
+    } else if (warp >= kEpiWarp0) {
+        if (kEpiRegs) setmaxnreg_inc<(kEpiRegs ? kEpiRegs : 96)>();
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int g = ew >> 2;
@@ -816,7 +818,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUten
                 if (kb % DW_CHUNK == DW_CHUNK - 1 || kb == KB - 1) { umma_commit(tfull0 + 8 * (c & 1)); ++c; }
             }
         }
-    } else {
+    } else if (warp >= kEpiWarp0) {
         const int ew = warp - kEpiWarp0, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
         // The epilogue warps only drain an accumulator set every DW_CHUNK K blocks; in between, each group of four warps (128
@@ -990,7 +992,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ 
             }
             umma_commit_pair(tfull);
         }
-    } else if (KB > 0) {
+    } else if (KB > 0 && warp >= kEpiWarp0) {
         const int ew = warp - kEpiWarp0, quarter = warp & 3, g = ew >> 2;
         const int i = i0 + quarter * 32 + lane;
         mbar_wait(tfull, 0);

@@ -113,6 +113,7 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (kEpiRegs && warp < kEpiWarp0) setmaxnreg_dec<32>();
 
     if (warp == kTmaWarp) {
         if (lane == 0) {
@@ -181,7 +182,8 @@ k_tc_rk4_fwd_persistent(const __grid_constant__ CUtensorMap mW_hi, const __grid_
                 }
             }
         }
-    } else {
+    } else if (warp >= kEpiWarp0) {
+        if (kEpiRegs) setmaxnreg_inc<(kEpiRegs ? kEpiRegs : 96)>();
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int g = ew >> 2;
