@@ -818,12 +818,15 @@ static __global__ void k_split16_w(const float* __restrict__ src, int rows, int 
     const float m = __uint_as_float(*amax);
     int ex = 0;
     if (m > 0.f) frexpf(m, &ex);                       // m = f 2^ex, f in [0.5, 1)
-    const float sc = m > 0.f ? ldexpf(1.0f, 14 - ex) : 1.0f;
-    if (blockIdx.x == 0 && threadIdx.x == 0) wscale[0] = m > 0.f ? ldexpf(1.0f, ex - 14) : 1.0f;
+    const int sh = m > 0.f ? max(-100, min(100, 14 - ex)) : 0;      // shifts beyond +-100: weights of 1e-35 / 1e+35
+    const float sc = ldexpf(1.0f, sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0) wscale[0] = ldexpf(1.0f, -sh);
+    unsigned int* ovf = reinterpret_cast<unsigned int*>(wscale + 2);   // the format's overflow flag (Mixed16::wscale)
     const size_t total = (size_t)rows_p * cols_p;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(e / cols_p), c = (int)(e % cols_p);
         const float x = (r < rows && c < cols) ? src[(size_t)r * ld + c] * sc : 0.0f;
+        if (!(fabsf(x) <= kF16Limit)) *ovf = 1u;       // non-finite weights, or a clamped shift: the TF32 repeat takes over
         const F16x2 t = f16_split2(x);
         hi[e] = __ushort_as_half(t.h);
         lo[e] = __ushort_as_half(t.l);
