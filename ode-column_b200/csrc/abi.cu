@@ -98,7 +98,7 @@ size_t odecol_workspace_bytes(const odecol_problem* p, int op, int32_t T, int64_
     if (to_dev(p, d) != ODECOL_OK) return 0;
     const bool small = use_small(p, d), small_rk4 = use_small_rk4(p, d);
     switch (op) {
-        case ODECOL_OP_RK4_FWD: return small_rk4 ? 0 : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
+        case ODECOL_OP_RK4_FWD: return small_rk4 ? (tiny_rk4_applicable(d) ? 256 : 0) : (use_tensor(p, d) ? tc_rk4_fwd_workspace_bytes(d, T) : stage_rk4_fwd_workspace_bytes(d, T));
         case ODECOL_OP_RK4_BWD: return small_rk4 ? 0 : (use_tensor(p, d) ? tc_rk4_bwd_workspace_bytes(d, T) : stage_rk4_bwd_workspace_bytes(d, T));
         case ODECOL_OP_EM_FWD: return small ? 0 : stage_em_fwd_workspace_bytes(d, T);
         case ODECOL_OP_DOPRI5_FWD: return small ? 0 : stage_dopri5_fwd_workspace_bytes(d, T);
@@ -141,7 +141,17 @@ int odecol_rk4_fwd(const odecol_problem* p, const float* t, int32_t T, const flo
     if (T < 2 || out_every < 1) return ODECOL_E_SHAPE;
     g_launches.store(0, std::memory_order_relaxed);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_small_rk4(p, d)) return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
+    if (use_small_rk4(p, d)) {
+        // tens of thousands of trials of a network of <= 16 populations: trials on the M axis of the tensor core (FP16 pairs),
+        // followed by the on-chip kernel, which returns at once unless the 16-bit solve raised its overflow flag
+        if (tiny_rk4_applicable(d) && workspace && workspace_bytes >= 256 && !misaligned(workspace)) {
+            unsigned int* ovf = static_cast<unsigned int*>(workspace);
+            const int rt = launch_rk4_fwd_tiny(d, t, T, y0, y_out, out_every, ovf, s);
+            if (rt != ODECOL_OK) return rt;
+            return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s, ovf);
+        }
+        return launch_rk4_fwd_small(d, t, T, y0, y_out, out_every, s);
+    }
     if (misaligned(y0) || misaligned(y_out) || misaligned(workspace)) return ODECOL_E_ALIGN;
     if (use_tensor(p, d)) return tc_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);
     return stage_rk4_fwd(d, t, T, y0, y_out, out_every, workspace, workspace_bytes, s);

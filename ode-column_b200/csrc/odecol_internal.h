@@ -46,7 +46,11 @@ int small_kp(const DevProblem& p);                 // 0 if the problem does not 
 size_t small_bwd_smem_bytes(int N, int KP, int trials_per_cta);
 int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, float* f, cudaStream_t s);
 int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
-                         cudaStream_t s);
+                         cudaStream_t s, const unsigned int* run_if = nullptr);      // run_if: device flag, 0 -> the kernel returns at once
+// large batches of the smallest networks on the tensor cores, trials on the M axis (tiny_tc.cu); *ovf: 4 bytes of device memory
+bool tiny_rk4_applicable(const DevProblem& p);
+int launch_rk4_fwd_tiny(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
+                        unsigned int* ovf, cudaStream_t s);
 int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float* y_traj, const float* grad_y,
                          const int* sel, int G, float* grad_y0, float* grad_W, cudaStream_t s);
 int launch_dopri5_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, float rtol,

@@ -166,8 +166,9 @@ template <int KP> struct FwdBounds {
 template <int KP>
 __global__ void __launch_bounds__(FwdBounds<KP>::threads, FwdBounds<KP>::blocks) k_rk4_fwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y0, float* __restrict__ y_out,
-                                                       int out_every, int packed) {
+                                                       int out_every, int packed, const unsigned int* __restrict__ run_if) {
     __shared__ __align__(16) float ra[4 * KP];
+    if (run_if && *run_if == 0u) return;      // repeat of a 16-bit tensor-core solve (tiny_tc.cu) that met no overflow
     const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
     const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N;
     RowRhs<KP> f;
@@ -950,11 +951,11 @@ int launch_rhs_generic(const DevProblem& p, const float* t, const float* y, floa
 static inline bool small_packed(const DevProblem& p) { return p.N <= 16 && p.n_in <= 16; }
 
 int launch_rk4_fwd_small(const DevProblem& p, const float* t, int T, const float* y0, float* y_out, int out_every,
-                         cudaStream_t s) {
+                         cudaStream_t s, const unsigned int* run_if) {
     const int kp = small_kp(p);
     const int packed = small_packed(p) ? 1 : 0;
     const int grid = packed ? (p.B + 1) / 2 : p.B;
-    ODECOL_KP_SWITCH(kp, (k_rk4_fwd_small<KP><<<grid, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, out_every, packed)));
+    ODECOL_KP_SWITCH(kp, (k_rk4_fwd_small<KP><<<grid, small_threads(p.N), 0, s>>>(p, t, T, y0, y_out, out_every, packed, run_if)));
     count_launch();
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
 }

@@ -204,3 +204,42 @@ def test_rk4_and_adjoint_on_a_long_contraction():
     eW = float((sheet.recurrent_weights.grad.cpu() - ode.W.grad).abs().max()) / scale(ode.W.grad)
     print(f"\n[rk4 N=1024, chunked contraction] trajectory {et:.1e}  grad y0 {e0:.1e}  grad W {eW:.1e}")
     assert et < 1e-5 and e0 < 5e-5 and eW < 5e-5
+
+
+@pytest.mark.parametrize("hot", [False, True], ids=["ordinary", "beyond_fp16"])
+@pytest.mark.parametrize("shape", [(16, 16, 1), (8, 3, 1), (12, 16, 3), (16, 5, 2)], ids=lambda s: "N%d_in%d_every%d" % s)
+def test_tensor_core_path_of_the_smallest_networks_matches_the_on_chip_kernel(shape, hot):
+    """From 4096 trials on, rk4 forward solves of networks with N <= 16, n_in <= 16 run with the trials on the M axis of the
+    tensor core (csrc/tiny_tc.cu, FP16 pairs).  The same trials in batches below the threshold run the on-chip kernel: the
+    two must agree to float32 rounding (ragged last CTA, padded populations / channels, subsampled outputs) -- and be
+    IDENTICAL when a rate does not fit FP16, because the launch sequence then repeats the solve with the on-chip kernel."""
+    N, n_in, every = shape
+    B, K = 4100, 4
+    lf, tv, kt, ku, y0 = _problem(N, n_in, B, K, seed=7 * N + n_in)
+    if hot:
+        y0[::37, 3] = 1400.0                                   # phi(1400 - A) = 6.6e4
+    ext = odecol._native.ext()
+    ld = (N + n_in + 1 + 3) // 4 * 4
+    W_aug = torch.zeros(N, ld)
+    W_aug[:, :N] = torch.tensor(lf.W); W_aug[:, N:N + n_in] = torch.tensor(lf.U); W_aug[:, N + n_in] = torch.tensor(lf.bias)
+    t_dev = torch.tensor(tv).to(DEV)
+
+    def solve(lo, hi):
+        prob = ext.Problem(W_aug.to(DEV), torch.tensor(lf.kappa).to(DEV), None, torch.tensor(kt).to(DEV),
+                           torch.tensor(ku[lo:hi]).contiguous().to(DEV), n_in, hi - lo, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, 0)
+        assert prob.kernel_family(ext.OP_RK4_FWD) == 0
+        assert (prob.workspace_bytes(ext.OP_RK4_FWD, len(tv), 0) > 0) == (hi - lo >= 4096)
+        return ext.rk4_fwd(prob, t_dev, torch.tensor(y0[lo:hi]).to(DEV), every)
+
+    big = solve(0, B)
+    ref = torch.cat([solve(lo, min(B, lo + 1500)) for lo in range(0, B, 1500)], 1)
+    torch.cuda.synchronize()
+    assert big.shape == ref.shape and torch.isfinite(ref).all()
+    if hot:
+        assert torch.equal(big, ref)
+        return
+    errs = [float((big[..., c * N:(c + 1) * N] - ref[..., c * N:(c + 1) * N]).abs().max() / ref[..., c * N:(c + 1) * N].abs().max())
+            for c in range(3)]
+    print(f"\n[tiny tensor-core path {shape}] V/A/F vs the on-chip kernel {errs[0]:.1e} {errs[1]:.1e} {errs[2]:.1e}")
+    assert not torch.equal(big, ref)                           # it is the other kernel that ran
+    assert max(errs) < 5e-6
