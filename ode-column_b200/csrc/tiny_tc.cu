@@ -43,13 +43,12 @@ ODECOL_DEVINL void tmem_ld8(uint32_t taddr, float (&f)[8]) {
     for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(u[i]);
 }
 
-// eight values -> one chunk of the high plane and one of the low plane; m = running max |x| (overflow check)
-ODECOL_DEVINL void pack8(const float (&x)[8], uint4& hi, uint4& lo, float& m) {
+// eight values -> one chunk of the high plane and one of the low plane
+ODECOL_DEVINL void pack8(const float (&x)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = x[2 * j], b = x[2 * j + 1];
-        m = fmaxf(m, fmaxf(fabsf(a), fabsf(b)));
         const __half2 hh = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(hh);
         const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
@@ -137,18 +136,23 @@ k_rk4_fwd_tiny(DevProblem p, const float* __restrict__ t, int T, const float* __
     }
     const float inv_tm = 1.0f / p.c.tau_m, inv_ta = 1.0f / p.c.tau_a, inv_ts = 1.0f / p.c.tau_s, gain = p.c.tau_s * p.c.R;
     const float* ku = p.knot_u + (size_t)(live ? b : 0) * p.knot_stride_b;
-    int kidx = 1, cached = -1;
+    int kidx = 1;
+    const float kt_lo = __ldg(p.knot_t), kt_hi = __ldg(p.knot_t + p.K - 1);
+    float kx0 = 1.0f, kx1 = 0.0f, kbase = 0.0f;                 // empty interval: the first evaluation locates
     uint32_t phase = 0;
-    float vmax = 0.f;
+    float vmax = 0.f, nanchk = 0.f;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // F16 x F16 -> F32, N = 16, M = 128
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)i0;
 
     // one right-hand side: r = phi(Vs - As) -> operand -> contraction -> tot; returns r and tot of this thread's populations
     auto rhs = [&](float tq, const float (&Vs)[8], const float (&As)[8], float (&r)[8], float (&tot)[8]) {
-        const float tc = knot_locate(p.knot_t, p.K, tq, kidx);
-        if (kidx != cached) {                                   // new knot interval (all threads at once: tq is shared)
-            cached = kidx;
+        const float tc = fminf(fmaxf(tq, kt_lo), kt_hi);
+        if (!(tc >= kx0 && tc < kx1)) {                         // new knot interval (all threads at once: tq is shared)
+            knot_locate(p.knot_t, p.K, tq, kidx);
             const float x0 = __ldg(p.knot_t + kidx - 1), x1 = __ldg(p.knot_t + kidx);
+            kx0 = kidx == 1 ? -INFINITY : x0;                   // the interval the lookup stays valid on (searchsorted right)
+            kx1 = kidx == p.K - 1 ? INFINITY : x1;
+            kbase = x0;
             const float dx = __fsub_rn(x1, x0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -156,24 +160,28 @@ k_rk4_fwd_tiny(DevProblem p, const float* __restrict__ t, int T, const float* __
                 float yl = 0.f, sl = 0.f;
                 if (live && ch < n_in) {
                     yl = __ldg(ku + (size_t)(kidx - 1) * n_in + ch);
-                    sl = __fdiv_rn(__fsub_rn(__ldg(ku + (size_t)kidx * n_in + ch), yl), dx);
+                    const float yh = __ldg(ku + (size_t)kidx * n_in + ch);
+                    sl = __fdiv_rn(__fsub_rn(yh, yl), dx);
+                    vmax = fmaxf(vmax, fmaxf(fabsf(yl), fabsf(yh)));      // the interpolant stays between its knots
                 }
                 stim[ch * TY_TRIALS + tr] = make_float2(yl, sl);
             }
         }
-        const float dtc = __fsub_rn(tc, __ldg(p.knot_t + kidx - 1));
+        const float dtc = __fsub_rn(tc, kbase);
         float xr[8], xu[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             r[j] = (live && i0 + j < N) ? phi_fast(Vs[j] - As[j]) : 0.f;
             xr[j] = r[j];
+            vmax = fmaxf(vmax, fabsf(r[j]));                     // overflow check; fmaxf drops a NaN, the product with zero keeps it
+            nanchk = fmaf(r[j], 0.0f, nanchk);
             const float2 s2 = stim[(i0 + j) * TY_TRIALS + tr];
             xu[j] = __fadd_rn(s2.x, __fmul_rn(s2.y, dtc));       // knot_value's arithmetic
         }
         uint4 hi, lo;
-        pack8(xr, hi, lo, vmax);
+        pack8(xr, hi, lo);
         sts128(a_hi + sw128(tr, half), hi); sts128(a_lo + sw128(tr, half), lo);
-        pack8(xu, hi, lo, vmax);
+        pack8(xu, hi, lo);
         sts128(a_hi + sw128(tr, 2 + half), hi); sts128(a_lo + sw128(tr, 2 + half), lo);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> tensor-core (async proxy) reads
         tc_fence_before();
@@ -239,12 +247,19 @@ k_rk4_fwd_tiny(DevProblem p, const float* __restrict__ t, int T, const float* __
         if (since_out == 0 || jn == T - 1) {
             const size_t ro = since_out == 0 ? (size_t)out_row : (size_t)((T - 2) / out_every + 1);
             float* yo = y_out + (ro * p.B + b) * row;
+            if (N == 16 && live && (reinterpret_cast<uintptr_t>(y_out) & 15) == 0) {        // 8 consecutive floats per component
+                float4* yv = reinterpret_cast<float4*>(yo + i0);
+                yv[0] = make_float4(V[0], V[1], V[2], V[3]); yv[1] = make_float4(V[4], V[5], V[6], V[7]);
+                yv[4] = make_float4(A[0], A[1], A[2], A[3]); yv[5] = make_float4(A[4], A[5], A[6], A[7]);
+                yv[8] = make_float4(F[0], F[1], F[2], F[3]); yv[9] = make_float4(F[4], F[5], F[6], F[7]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (live && i0 + j < N) { yo[i0 + j] = V[j]; yo[N + i0 + j] = A[j]; yo[2 * N + i0 + j] = F[j]; }
+                for (int j = 0; j < 8; ++j)
+                    if (live && i0 + j < N) { yo[i0 + j] = V[j]; yo[N + i0 + j] = A[j]; yo[2 * N + i0 + j] = F[j]; }
+            }
         }
     }
-    if (big || !(vmax <= kF16Limit)) *ovf = 1u;
+    if (big || !(vmax <= kF16Limit) || !(nanchk == 0.0f)) *ovf = 1u;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
