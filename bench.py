@@ -823,10 +823,10 @@ def run_small(args):
         "steps": args.steps, "warmup": 1, "ms_per_step": w["rk4_forward_adjoint"]["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "small: reference WTA network (N=16, T=1500) and parity network (N=104, T=1000) at large "
-                               "batch, persistent on-chip family (one CTA per trial, whole time loop in one launch)",
+                               "batch, persistent on-chip family (whole time loop in one launch; WTA forward: 128 trials per CTA on the tensor core)",
                    "l2": "trajectories (18.9 GB / 20.4 GB) larger than L2"},
         "clocks": clocks, "gpu_launches": launches, "cases": cases,
-        "roofline": {"bound": "hbm", "kernel": "k_rk4_fwd_small<40> (WTA, full (T,B,3N) trajectory written: 12 B per population-step)",
+        "roofline": {"bound": "hbm", "kernel": "k_rk4_fwd_tiny (WTA from 4096 trials: trials on the M axis of tcgen05, FP16 pairs; k_rk4_fwd_small<40> below that or with ODECOL_TINY_TC=0); full (T,B,3N) trajectory written: 12 B per population-step",
                      "achieved": w["rk4_forward"]["hbm_gbs_trajectory"], "peak": hbm_peak, "unit": "GB/s",
                      "frac": w["rk4_forward"]["hbm_frac"], "traffic": None,
                      "fp32_view": {"achieved_tflops": w["rk4_forward"]["fp32_tflops"], "peak_tflops": ffma_peak,

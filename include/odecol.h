@@ -23,7 +23,8 @@
  *   - re-entrant across streams, no global state that affects results, one GPU per call (multi-GPU orchestration is
  *     the caller's: shard trials, then all-reduce grad_W_aug);
  *   - there is NO CPU implementation behind this ABI;
- *   - arithmetic of the staged tensor-core family (N > 128): float32 state, contractions as error-corrected split
+ *   - arithmetic of the tensor-core paths (the staged family, N > 128; rk4 forward of N <= 16 networks from 4096 trials,
+ *     which asks for 256 bytes of workspace and falls back to the on-chip kernel without them): float32 state, contractions as error-corrected split
  *     products on tcgen05 (operand = high + low half, three products, FP32 accumulation: 2^-22 relative).  The halves are
  *     TF32 numbers, or -- in the persistent rk4 forward kernel and the Euler-Maruyama drift -- FP16 numbers.  FP16 cannot
  *     hold an operand value (a firing rate, a stimulus) beyond +-6e4: the kernels detect that on the device and the same
