@@ -224,16 +224,32 @@ def test_tensor_core_path_of_the_smallest_networks_matches_the_on_chip_kernel(sh
     W_aug[:, :N] = torch.tensor(lf.W); W_aug[:, N:N + n_in] = torch.tensor(lf.U); W_aug[:, N + n_in] = torch.tensor(lf.bias)
     t_dev = torch.tensor(tv).to(DEV)
 
+    gen = torch.Generator().manual_seed(3)
+    n_rows = (len(tv) - 2) // every + 2 if every > 1 else len(tv)
+    wgt = torch.randn(n_rows, B, 3 * N, generator=gen).to(DEV)
+    grads = []
+
     def solve(lo, hi):
         prob = ext.Problem(W_aug.to(DEV), torch.tensor(lf.kappa).to(DEV), None, torch.tensor(kt).to(DEV),
                            torch.tensor(ku[lo:hi]).contiguous().to(DEV), n_in, hi - lo, lf.tau_s, lf.tau_m, lf.tau_a, lf.resistance, 0)
         assert prob.kernel_family(ext.OP_RK4_FWD) == 0
         assert (prob.workspace_bytes(ext.OP_RK4_FWD, len(tv), 0) > 0) == (hi - lo >= 4096)
-        return ext.rk4_fwd(prob, t_dev, torch.tensor(y0[lo:hi]).to(DEV), every)
+        y = ext.rk4_fwd(prob, t_dev, torch.tensor(y0[lo:hi]).to(DEV), every)
+        if every == 1 and not hot:                             # the on-chip reverse sweep on top of either forward solve
+            grads.append(ext.rk4_bwd(prob, t_dev, y, wgt[:, lo:hi].contiguous(), None))
+        return y
 
     big = solve(0, B)
+    g_big = grads.pop() if grads else None
     ref = torch.cat([solve(lo, min(B, lo + 1500)) for lo in range(0, B, 1500)], 1)
     torch.cuda.synchronize()
+    if g_big is not None:
+        gy_ref = torch.cat([g[0] for g in grads], 0)
+        gW_ref = sum(g[1] for g in grads)
+        e0 = float((g_big[0] - gy_ref).abs().max() / gy_ref.abs().max())
+        eW = float((g_big[1] - gW_ref).abs().max() / gW_ref.abs().max())
+        print(f"\n[tiny tensor-core path {shape}] reverse sweep on its trajectory vs on the on-chip one: dy0 {e0:.1e}  dW {eW:.1e}")
+        assert e0 < 2e-5 and eW < 2e-5
     assert big.shape == ref.shape and torch.isfinite(ref).all()
     if hot:
         assert torch.equal(big, ref)
