@@ -242,7 +242,9 @@ size_t small_bwd_smem_bytes(int N, int KP, int tpc) {
     return sizeof(float) * ((size_t)tpc * kBwdSlots * KP + (size_t)tpc * 2 * NP + (size_t)N * (KP + 1) + 3 * N);
 }
 
-template <int KP>
+// FAST: the transfer function through the staged families' fast path (used for the large batches whose forward solve already
+// ran on the tensor cores: tiny_tc.cu -- bit-faithfulness to the reference's libm calls is not the point there)
+template <int KP, bool FAST = false>
 struct BwdCtx {
     BwdShared<KP> s;
     float dw[KP];
@@ -287,7 +289,8 @@ struct BwdCtx {
 
     // forward stage: publishes r_aug into ra[stage], returns total input (needs_dot) ; r, dr out
     ODECOL_DEVINL float stage_fwd(int stage, float t, float V, float A, float& r, float& dr, bool needs_dot) {
-        small_phi_dphi(__fsub_rn(V, A), r, dr);
+        if (FAST) phi_dphi_fast(__fsub_rn(V, A), r, dr);
+        else small_phi_dphi(__fsub_rn(V, A), r, dr);
         float* cur = ra_t + stage * KP;
         if (act) cur[li] = r;
         if (li < n_in) {
@@ -355,7 +358,7 @@ template <int KP> struct BwdBounds {
     static constexpr int blocks = KP <= 40 ? 10 : 0;      // 0 = unspecified
 };
 
-template <int KP>
+template <int KP, bool FAST = false>
 __global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y_traj,
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks)
     extern __shared__ __align__(16) float sm[];
     const int sub = packed ? (int)(threadIdx.x >> 4) : 0, i = packed ? (int)(threadIdx.x & 15) : (int)threadIdx.x;
     const int b = packed ? 2 * (int)blockIdx.x + sub : (int)blockIdx.x, N = p.N, B = p.B;
-    BwdCtx<KP> cx;
+    BwdCtx<KP, FAST> cx;
     cx.init(p, sm, b, i, sub, packed ? 16 : (int)blockDim.x, packed ? 2 : 1);
     for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) cx.s.inv[e] = sel ? -1 : e;
     __syncthreads();
@@ -965,6 +968,13 @@ int launch_rk4_bwd_small(const DevProblem& p, const float* t, int T, const float
     const int kp = small_kp(p);
     const int packed = small_packed(p) ? 1 : 0;
     const size_t smem = small_bwd_smem_bytes(p.N, kp, packed ? 2 : 1);
+    if (kp == 40 && tiny_rk4_applicable(p)) {       // the batches whose forward solve ran on the tensor cores (tiny_tc.cu)
+        cudaFuncSetAttribute(k_rk4_bwd_small<40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_rk4_bwd_small<40, true><<<packed ? (p.B + 1) / 2 : p.B, small_threads(p.N), smem, s>>>(p, t, T, y_traj, grad_y, sel, G,
+                                                                                              grad_y0, grad_W, packed);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+    }
     ODECOL_KP_SWITCH(kp, {
         cudaFuncSetAttribute(k_rk4_bwd_small<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_rk4_bwd_small<KP><<<packed ? (p.B + 1) / 2 : p.B, small_threads(p.N), smem, s>>>(p, t, T, y_traj, grad_y, sel, G,
