@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--trials-total", type=int, default=0,
                     help="c4: total trials of the job (strong scaling): every rank integrates trials-total / gpus trials per step in "
                          "chunks of --trials-per-gpu, accumulating dW; 65536 = the literal BASELINE.json configs[3] batch at any N")
+    ap.add_argument("--integrate-f", action="store_true",
+                    help="c4: also select the F (synaptic) component of the read-out populations, so that the solve integrates and "
+                         "returns F as torchdiffeq would (default: F feeds nothing back and no loss reads it, so the kernels skip it)")
     ap.add_argument("--parity-trials", type=int, default=8, help="trials of the in-bench oracle parity check (0 = skip)")
     ap.add_argument("--parity-steps", type=int, default=40)
     ap.add_argument("--probe-trials", type=int, default=1024, help="global trials of the sharding-invariance probe (0 = skip)")
@@ -86,15 +89,19 @@ def probe_amplitudes(torch, n_trials, columns):
     return torch.rand(n_trials, columns, generator=g) * 30.0
 
 
-def loss_components(torch, columns):
+def loss_components(torch, columns, with_f=False):
     n = 8 * columns
     v = torch.arange(columns) * 8                       # L2/3e of every column: V and A components
+    if with_f:                                          # --integrate-f: their F components ride along (the loss ignores them)
+        return torch.cat((v, v + n, v + 2 * n)).to(torch.int64)
     return torch.cat((v, v + n)).to(torch.int64)
 
 
 def huber_on_rates(torch, odecol, sel_traj, target, columns):
     """Huber loss on the L2/3e firing rates over the whole trajectory.  On the GPU arm this is the product's fused
     read-out (one kernel: loss + gradient w.r.t. the trajectory); the CPU arms evaluate the same expression in torch."""
+    if sel_traj.shape[2] == 3 * columns:                # --integrate-f: V, A, F selected; the read-out takes V and A
+        sel_traj = sel_traj[:, :, :2 * columns]
     if sel_traj.is_cuda:
         return odecol.huber_rate_loss(sel_traj, target, pops_per_group=1)
     rate = odecol.compute_firing_rate(sel_traj[:, :, :columns] - sel_traj[:, :, columns:])
@@ -209,6 +216,11 @@ def run_reference(args):
 
 
 def workload_name(args):
+    name = _workload_name(args)
+    return name + ("; F of the read-out populations selected, so F is integrated and returned" if args.integrate_f else "")
+
+
+def _workload_name(args):
     if args.trials_total:
         return (f"C4: synthetic {args.columns}-column network (N={8 * args.columns}), rk4 forward + discrete adjoint dW, "
                 f"T={args.time_points} grid points, {args.trials_total} trials in the job ({args.trials_total // args.gpus} per GPU, "
@@ -353,7 +365,7 @@ def run_ours(args):
     stim = [make_stimulus(torch, B, columns, T, args.dt, trial0 + c * B, "cpu") for c in range(chunks)]
     kt, ku = stim[0][0], stim[0][1]
     tv = torch.linspace(0.0, T * args.dt, T, device=dev)
-    sel = loss_components(torch, columns).to(dev)
+    sel = loss_components(torch, columns, args.integrate_f).to(dev)
     target = torch.full((1, 1, columns), 0.5, device=dev)
     y0_host = torch.zeros(B, 3 * n).pin_memory()
     ku_hosts = [st[1].pin_memory() for st in stim]
@@ -450,8 +462,8 @@ def run_ours(args):
 
     # e2e leg: same pass, inputs from pinned host memory, loss and dW read back every step
     step(True)
-    sec_e2e, (loss_h, gW_h) = timed(max(1, min(args.steps, 2)), True)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
+    sec_e2e, (loss_h, gW_h) = timed(e2e_steps, True)
     e2e_value = pop_steps_job * e2e_steps / sec_e2e
     h2d = (y0_host.numel() * 4 + ku_host.numel() * 4) * chunks
     d2h = gW_h.numel() * 4 + 4
