@@ -11,7 +11,8 @@
  *   - calls are ordered on `stream` (a cudaStream_t passed as void* so that the header needs no CUDA include) and
  *     asynchronous with respect to the host, with these documented exceptions, all in the STAGED family (N > 128 or a
  *     forced flag): the fixed-step stochastic entry points (odecol_em_fwd, odecol_srk_fwd, odecol_em_bwd, odecol_srk_bwd)
- *     replay the data-independent float32 step schedule on the host and synchronise the stream once at entry; the
+ *     replay the data-independent float32 step schedule on the host and synchronise the stream once at entry (the two
+ *     forward ones once more at exit, to read the overflow flag of the FP16 operand format, see "operand formats"); the
  *     adaptive ones (odecol_em_fwd with adaptive = 1, odecol_dopri5_fwd / _fwd_record) poll an "all trials finished"
  *     counter every 16 rounds; odecol_dopri5_bwd reads the accepted-step counts once.  None of them may be captured into
  *     a CUDA graph; everything else (the on-chip family, all rk4 entry points, the read-outs) may;

@@ -932,8 +932,8 @@ __global__ void k_dp_finish(DevProblem p, DpState s, const float* __restrict__ t
 }
 
 struct DpLayout {
-    int Np, Bp, KPa, TN;
-    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_k[7], off_y, off_ys, off_state, total;
+    int Np, Bp, KPa, KP16, TN;
+    size_t off_Whi, off_Wlo, off_Rhi, off_Rlo, off_k[7], off_y, off_ys, off_state, off_aux, total;
 };
 
 static DpLayout dp_layout(const DevProblem& p) {
@@ -950,6 +950,8 @@ static DpLayout dp_layout(const DevProblem& p) {
     for (int i = 0; i < 7; ++i) L.off_k[i] = take(st);
     L.off_y = take(st); L.off_ys = take(st);
     L.off_state = take(64ull * p.B + 1024);
+    L.off_aux = take(64);                                       // 16-bit operand format: 1 / weight scale, max|W| scratch, overflow flag
+    L.KP16 = round_up(p.N + p.n_in + 1, BK16);                  // its rows live in the same buffers (2 KP16 <= 4 KPa bytes)
     L.total = o;
     return L;
 }
@@ -958,9 +960,10 @@ static DpLayout dp_layout(const DevProblem& p) {
 
 size_t stage_dopri5_fwd_workspace_bytes(const DevProblem& p, int) { return tc::dp_layout(p).total; }
 
-int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
-                     int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec, void* ws,
-                     size_t ws_bytes, cudaStream_t s) {
+// f16: the six drift contractions of a round read FP16 pairs, as in em_fwd_impl (kRetryTf32 when a value did not fit).
+static int dopri5_fwd_impl(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
+                           int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec, void* ws,
+                           size_t ws_bytes, cudaStream_t s, bool f16) {
     using namespace tc;
     const DpLayout L = dp_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -985,22 +988,38 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
     S.n_active = reinterpret_cast<int*>(grab(16));
 
     if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_k[0] - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
-    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    count_launch();
+    float* aux = F(L.off_aux);                                  // [0] 1 / weight scale, [1] max|W| bits, [2] overflow flag
+    unsigned int* ovf = f16 ? reinterpret_cast<unsigned int*>(aux + 2) : nullptr;
+    const int KPr = f16 ? L.KP16 : L.KPa;                       // elements per operand row in the format in use
+    if (f16) {
+        if (cudaMemsetAsync(aux, 0, 64, s) != cudaSuccess) return ODECOL_E_CUDA;
+        k_absmax<<<148, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<unsigned int*>(aux + 1));
+        k_split16_w<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<__half*>(Whi), reinterpret_cast<__half*>(Wlo),
+                                        L.Np, L.KP16, reinterpret_cast<unsigned int*>(aux + 1), aux);
+        count_launch(2);
+    } else {
+        k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+        count_launch();
+    }
     if (cudaMemcpyAsync(S.y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
-    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
-        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+    if (f16) {
+        if (!make_map16(&mWhi, Whi, L.Np, L.KP16, L.KP16, BM, false) || !make_map16(&mWlo, Wlo, L.Np, L.KP16, L.KP16, BM, false) ||
+            !make_map16(&mRhi, Rhi, L.Bp, L.KP16, L.KP16, L.TN, false) || !make_map16(&mRlo, Rlo, L.Bp, L.KP16, L.KP16, L.TN, false))
+            return ODECOL_E_CUDA;
+    } else if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+               !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
         return ODECOL_E_CUDA;
-    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, f16 ? L.KP16 / BK16 : L.KPa / BK, 0, nullptr};
     // f(t_stage[b], ysrc[b]) -> fdst for every trial (finished trials compute along harmlessly: rows are independent)
     auto rhs = [&](const float* ysrc, const float* t_trial, float t_shared, float* fdst) {
-        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, t_trial, t_shared, Rhi, Rlo, L.KPa);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, t_trial, t_shared, Rhi, Rlo, KPr, nullptr, nullptr, ovf);
         count_launch();
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = nullptr;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = KPr; e.loc = nullptr; e.wscale = f16 ? aux : nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (f16) return launch_contract16(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
     const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
@@ -1015,6 +1034,7 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
     k_dp_init2<<<p.B, 256, 0, s>>>(p, S, rtol, atol);
     count_launch(2);
     int h_active = p.B;
+    unsigned int h_ovf = 0;
     for (long long round = 0; round < (long long)max_steps && h_active > 0; ++round) {
         k_dp_stage<1><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[1]); if (rc) return rc;
         k_dp_stage<2><<<ew_grid, 256, 0, s>>>(p, S); rc = rhs(S.ys, S.t_stage, 0.f, S.k[2]); if (rc) return rc;
@@ -1026,8 +1046,15 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
         count_launch(7);
         if ((round & 15) == 15) {
             if (cudaMemcpyAsync(&h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (f16 && cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
             if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+            if (h_ovf) return kRetryTf32;
         }
+    }
+    if (f16) {                                                // rounds since the last poll
+        if (cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (h_ovf) return kRetryTf32;
     }
     k_em_fill_nan<<<p.B, 128, 0, s>>>(p, S.status, S.next_out, T, y_out);
     count_launch();
@@ -1035,6 +1062,20 @@ int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const floa
     if (n_reject && cudaMemcpyAsync(n_reject, S.n_rej, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (status && cudaMemcpyAsync(status, S.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int stage_dopri5_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, float rtol, float atol,
+                     int max_steps, int* n_accept, int* n_reject, int* status, const Dopri5Record& rec, void* ws,
+                     size_t ws_bytes, cudaStream_t s) {
+    static const bool f16_env = [] { const char* e = getenv("ODECOL_DP16"); return e ? atoi(e) != 0 : true; }();
+    // Forward-only solves take the 16-bit format.  Training (rec.y != NULL) stays on TF32 pairs: on the stiff parity network the
+    // discrete adjoint through a stability-limited step sequence is ill-conditioned (on-chip and staged TF32 gradients already
+    // differ by 2e-2 there), and the step sequence the FP16 rounding produced amplified it 300-fold (profiles/r2_session4.md).
+    const bool f16 = f16_env && rec.y == nullptr;
+    int rc = dopri5_fwd_impl(p, ts_dev, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec, ws, ws_bytes, s, f16);
+    if (rc == kRetryTf32)
+        rc = dopri5_fwd_impl(p, ts_dev, T, y0, y_out, rtol, atol, max_steps, n_accept, n_reject, status, rec, ws, ws_bytes, s, false);
+    return rc;
 }
 
 
@@ -1116,9 +1157,11 @@ __global__ void k_status_finite(DevProblem p, const float* __restrict__ y, int* 
 
 size_t stage_srk_fwd_workspace_bytes(const DevProblem& p, int) { return tc::em_layout(p).total; }
 
-int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
-                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps, void* ws,
-                  size_t ws_bytes, cudaStream_t s) {
+// f16: the three drift contractions of a step read FP16 pairs, as in em_fwd_impl (kRetryTf32 when a value did not fit: the
+// flag is read once, after the last step).
+static int srk_fwd_impl(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                        const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps, void* ws,
+                        size_t ws_bytes, cudaStream_t s, bool f16) {
     using namespace tc;
     const EmLayout L = em_layout(p);
     if (!ws || ws_bytes < L.total) return ODECOL_E_WORKSPACE;
@@ -1133,22 +1176,38 @@ int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* 
     const int Kaug = p.N + p.n_in + 1;
     const size_t st = (size_t)p.B * 3 * p.N;
     if (cudaMemsetAsync(w + L.off_Rhi, 0, L.off_f - L.off_Rhi, s) != cudaSuccess) return ODECOL_E_CUDA;
-    k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
-    count_launch();
+    float* aux = F(L.off_aux);                                  // [0] 1 / weight scale, [1] max|W| bits, [2] overflow flag
+    unsigned int* ovf = f16 ? reinterpret_cast<unsigned int*>(aux + 2) : nullptr;
+    const int KPr = f16 ? L.KP16 : L.KPa;                       // elements per operand row in the format in use
+    if (f16) {
+        if (cudaMemsetAsync(aux, 0, 64, s) != cudaSuccess) return ODECOL_E_CUDA;
+        k_absmax<<<148, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<unsigned int*>(aux + 1));
+        k_split16_w<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, reinterpret_cast<__half*>(Whi), reinterpret_cast<__half*>(Wlo),
+                                        L.Np, L.KP16, reinterpret_cast<unsigned int*>(aux + 1), aux);
+        count_launch(2);
+    } else {
+        k_split_pad<<<296, 256, 0, s>>>(p.W_aug, p.N, Kaug, p.ld_w, Whi, Wlo, L.Np, L.KPa);
+        count_launch();
+    }
     if (cudaMemcpyAsync(y, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (cudaMemcpyAsync(y_out, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     if (y_steps && cudaMemcpyAsync(y_steps, y0, sizeof(float) * st, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return ODECOL_E_CUDA;
     CUtensorMap mWhi, mWlo, mRhi, mRlo;
-    if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
-        !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
+    if (f16) {
+        if (!make_map16(&mWhi, Whi, L.Np, L.KP16, L.KP16, BM, false) || !make_map16(&mWlo, Wlo, L.Np, L.KP16, L.KP16, BM, false) ||
+            !make_map16(&mRhi, Rhi, L.Bp, L.KP16, L.KP16, L.TN, false) || !make_map16(&mRlo, Rlo, L.Bp, L.KP16, L.KP16, L.TN, false))
+            return ODECOL_E_CUDA;
+    } else if (!make_map(&mWhi, Whi, L.Np, L.KPa, L.KPa, BM) || !make_map(&mWlo, Wlo, L.Np, L.KPa, L.KPa, BM) ||
+               !make_map(&mRhi, Rhi, L.Bp, L.KPa, L.KPa, L.TN) || !make_map(&mRlo, Rlo, L.Bp, L.KPa, L.KPa, L.TN))
         return ODECOL_E_CUDA;
-    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, L.KPa / BK, 0, nullptr};
+    const TileShape tsh{L.Np / BM, L.Bp / L.TN, L.TN, f16 ? L.KP16 / BK16 : L.KPa / BK, 0, nullptr};
     auto rhs = [&](const float* ysrc, float tq, float* fdst) {
-        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, nullptr, tq, Rhi, Rlo, L.KPa);
+        k_em_operand<<<p.B, 128, 0, s>>>(p, ysrc, nullptr, tq, Rhi, Rlo, KPr, nullptr, nullptr, ovf);
         count_launch();
         RhsEpi e;
-        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = L.KPa; e.loc = nullptr;
+        e.p = p; e.y = ysrc; e.Rhi = Rhi; e.Rlo = Rlo; e.f = fdst; e.KPa = KPr; e.loc = nullptr; e.wscale = f16 ? aux : nullptr;
         e.inv_tm = 1.0f / p.c.tau_m; e.inv_ta = 1.0f / p.c.tau_a; e.inv_ts = 1.0f / p.c.tau_s;
+        if (f16) return launch_contract16(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
         return launch_contract(mWhi, mWlo, mRhi, mRlo, tsh, e, s);
     };
     const int ew_grid = (int)((st + 255) / 256 < 148 * 16 ? (st + 255) / 256 : 148 * 16);
@@ -1186,8 +1245,24 @@ int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* 
             return ODECOL_E_CUDA;
         if (k > (1LL << 40)) return ODECOL_E_SHAPE;
     }
+    if (f16) {                                                // did every operand value fit FP16?
+        unsigned int h_ovf = 0;
+        if (cudaMemcpyAsync(&h_ovf, ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return ODECOL_E_CUDA;
+        if (h_ovf) return kRetryTf32;
+    }
     if (status) { k_status_finite<<<p.B, 128, 0, s>>>(p, y, status); count_launch(); }
     return cudaGetLastError() == cudaSuccess ? ODECOL_OK : ODECOL_E_CUDA;
+}
+
+int stage_srk_fwd(const DevProblem& p, const float* ts_dev, int T, const float* y0, float* y_out, const float* dW,
+                  const float* dU, uint64_t seed, int64_t trial_offset, float dt, int* status, float* y_steps, void* ws,
+                  size_t ws_bytes, cudaStream_t s) {
+    static const bool f16_env = [] { const char* e = getenv("ODECOL_SRK16"); return e ? atoi(e) != 0 : true; }();
+    int rc = srk_fwd_impl(p, ts_dev, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps, ws, ws_bytes, s, f16_env);
+    if (rc == kRetryTf32)
+        rc = srk_fwd_impl(p, ts_dev, T, y0, y_out, dW, dU, seed, trial_offset, dt, status, y_steps, ws, ws_bytes, s, false);
+    return rc;
 }
 
 

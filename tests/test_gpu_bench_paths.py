@@ -220,6 +220,55 @@ def test_staged_euler_maruyama_repeats_in_tf32_when_fp16_cannot_hold_the_operand
     assert float((c - d).abs().max()) <= (2e-4 if adaptive == "1" else 2e-6) * float(d.abs().max())
 
 
+_DP_SRK_RETRY_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import odecol
+cfg = odecol.load_config(sys.argv[1] + "/config/model.toml")
+B, cols = 5, 32
+N = 8 * cols
+sheet = odecol.SyntheticColumnSheet(cfg, cols, seed=0, device="cuda")
+gen = torch.Generator().manual_seed(5)
+amp = torch.rand(B, cols, generator=gen) * 30.0
+kt, ku = odecol.step_knots(0.002, 0.006, 0.01, amp, 1e-3)
+sheet.set_knots(kt.cuda(), ku.cuda())
+ts = torch.linspace(0.0, 0.01, 6).cuda()
+y0 = torch.cat((torch.rand(B, N, generator=gen) * 6 - 8, torch.rand(B, N, generator=gen), torch.rand(B, N, generator=gen) * 2), 1)
+out = {}
+for tag, v_hot in (("hot", 1400.0), ("plain", 4.0)):
+    y0[:, 3] = v_hot
+    st = {}
+    with torch.no_grad():
+        out["dopri5_" + tag] = odecol.odeint(sheet, y0.cuda(), ts, rtol=1e-5, atol=1e-6, stats=st).cpu()      # N = 256: staged family
+        out["srk_" + tag] = odecol.sdeint(sheet, y0.cuda(), ts, method="srk", dt=1e-4, seed=3,
+                                          options={"sigma_scale": torch.full((B,), 0.1)}).cpu()
+    out["n_accept_" + tag] = st["n_accept"].cpu()
+torch.save(out, sys.argv[2])
+"""
+
+
+def test_staged_dopri5_and_srk_repeat_in_tf32_when_fp16_cannot_hold_the_operand(tmp_path):
+    """The drift contractions of the staged srk forward solve and of the forward-only staged dopri5 solve (no record: training
+    keeps TF32 pairs) read FP16 pairs as well (stage_em.cu: dopri5_fwd_impl, srk_fwd_impl); same overflow protocol and same
+    criterion as for Euler-Maruyama above."""
+    import subprocess
+    import sys
+
+    def run(f16):
+        out = tmp_path / f"d_{f16}.pt"
+        env = dict(os.environ, ODECOL_DP16=f16, ODECOL_SRK16=f16)
+        subprocess.run([sys.executable, "-c", _DP_SRK_RETRY_SCRIPT, ROOT, str(out)], env=env, check=True, timeout=600)
+        return torch.load(out)
+
+    a, b = run("1"), run("0")
+    for k in ("dopri5_hot", "srk_hot", "n_accept_hot"):
+        assert torch.isfinite(a[k].float()).all() and torch.equal(a[k], b[k]), k
+    for k, bar in (("dopri5_plain", 5e-4), ("srk_plain", 1e-5)):        # srk: 100 noisy steps, F components of a few hundred
+        assert not torch.equal(a[k], b[k]), k
+        assert float((a[k] - b[k]).abs().max()) <= bar * float(b[k].abs().max()), k
+    assert float((a["n_accept_plain"] - b["n_accept_plain"]).abs().max()) <= 2
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # adaptive Euler-Maruyama vs the oracle's step-doubling loop
 # ----------------------------------------------------------------------------------------------------------------------
