@@ -72,7 +72,8 @@ def parse():
 # ----------------------------------------------------------------------------------------------------------------------
 def make_stimulus(torch, B, columns, T, dt, trial0, device):
     """Three-phase stimulus (off / on / off, thirds of the window) with per-trial, per-column amplitudes U(0, 30) Hz,
-    as knots; amplitudes are keyed by the GLOBAL trial index so that results do not depend on the sharding."""
+    as knots; the draw of a chunk of trials is seeded by the GLOBAL index of its first trial, so a rank's chunk is the same
+    whatever else runs (the sharding-invariance `probe` uses probe_amplitudes: one draw for the whole job, sliced)."""
     import odecol
     g = torch.Generator(device="cpu").manual_seed(1000 + trial0)
     amp = torch.rand(B, columns, generator=g) * 30.0
