@@ -248,6 +248,8 @@ template <int KP, bool FAST = false>
 struct BwdCtx {
     BwdShared<KP> s;
     float dw[KP];
+    float wrow[FAST ? KP : 1];   // FAST (N <= 16, two trials per warp): row li of W_aug and column li of its leading block in
+    float wcol[FAST ? 16 : 1];   // registers -- the dot products read only the broadcast operand from shared memory (16-byte loads)
     float kappa, gamma, inv_tau_m, inv_tau_a, inv_tau_s;
     const float* ku;
     const float* kt;
@@ -285,6 +287,12 @@ struct BwdCtx {
         gamma = c.tau_s * c.R / c.tau_m;
         inv_tau_m = 1.0f / c.tau_m; inv_tau_a = 1.0f / c.tau_a; inv_tau_s = 1.0f / c.tau_s;
         __syncthreads();
+        if constexpr (FAST) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) wrow[k] = i < N ? s.Ws[i * (KP + 1) + k] : 0.0f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) wcol[r] = (i < N && r < N) ? s.Ws[r * (KP + 1) + i] : 0.0f;
+        }
     }
 
     // forward stage: publishes r_aug into ra[stage], returns total input (needs_dot) ; r, dr out
@@ -302,6 +310,20 @@ struct BwdCtx {
         }
         __syncthreads();
         float acc = 0.f;
+        if constexpr (FAST) {
+            if (needs_dot && act) {                  // same two accumulators, same order as below
+                const float4* c4 = reinterpret_cast<const float4*>(cur);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < KP / 4; ++k) {
+                    const float4 v = c4[k];
+                    a0 = fmaf(wrow[4 * k], v.x, a0); a1 = fmaf(wrow[4 * k + 1], v.y, a1);
+                    a0 = fmaf(wrow[4 * k + 2], v.z, a0); a1 = fmaf(wrow[4 * k + 3], v.w, a1);
+                }
+                acc = a0 + a1;
+            }
+            return acc;
+        }
         if (needs_dot && act) {
             const float* wr = s.Ws + li * (KP + 1);
             float a0 = 0.f, a1 = 0.f;
@@ -320,7 +342,19 @@ struct BwdCtx {
         if (li < NP) a[li] = act ? ga : 0.0f;
         __syncthreads();
         float g = 0.f;
-        if (act) {
+        if constexpr (FAST) {
+            if (act) {                               // entries beyond N are zeros on both sides: the sums below are the ones further down
+                const float4* a4 = reinterpret_cast<const float4*>(a);
+                float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = a4[q];
+                    g0 = fmaf(wcol[4 * q], v.x, g0); g1 = fmaf(wcol[4 * q + 1], v.y, g1);
+                    g0 = fmaf(wcol[4 * q + 2], v.z, g0); g1 = fmaf(wcol[4 * q + 3], v.w, g1);
+                }
+                g = g0 + g1 + kappa * aA * inv_tau_a + aF * inv_tau_s;
+            }
+        } else if (act) {
             const float* wc = s.Ws + li;
             float g0 = 0.f, g1 = 0.f;
             int r = 0;
@@ -353,13 +387,13 @@ struct BwdCtx {
 
 // reverse kernels: the dW row (KP registers) rides along; only the smallest configuration has room to trade registers
 // for resident CTAs
-template <int KP> struct BwdBounds {
+template <int KP, bool FAST = false> struct BwdBounds {
     static constexpr int threads = KP <= 40 ? 64 : 128;
-    static constexpr int blocks = KP <= 40 ? 10 : 0;      // 0 = unspecified
+    static constexpr int blocks = KP <= 40 ? (FAST ? 6 : 10) : 0;      // 0 = unspecified; FAST keeps W in registers (BwdCtx)
 };
 
 template <int KP, bool FAST = false>
-__global__ void __launch_bounds__(BwdBounds<KP>::threads, BwdBounds<KP>::blocks) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
+__global__ void __launch_bounds__(BwdBounds<KP, FAST>::threads, BwdBounds<KP, FAST>::blocks) k_rk4_bwd_small(DevProblem p, const float* __restrict__ t, int T,
                                                        const float* __restrict__ y_traj,
                                                        const float* __restrict__ grad_y, const int* __restrict__ sel,
                                                        int G, float* __restrict__ grad_y0, float* __restrict__ grad_W,
