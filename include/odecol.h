@@ -27,10 +27,12 @@
  *   - arithmetic of the tensor-core paths (the staged family, N > 128; rk4 forward of N <= 16 networks from 4096 trials,
  *     which asks for 256 bytes of workspace and falls back to the on-chip kernel without them): float32 state, contractions as error-corrected split
  *     products on tcgen05 (operand = high + low half, three products, FP32 accumulation: 2^-22 relative).  The halves are
- *     TF32 numbers, or -- in the persistent rk4 forward kernel and the Euler-Maruyama drift -- FP16 numbers.  FP16 cannot
+ *     TF32 numbers, or -- in the persistent rk4 forward kernel and the drift evaluations of the staged Euler-Maruyama, srk
+ *     and forward-only (no record) dopri5 forward solves -- FP16 numbers.  FP16 cannot
  *     hold an operand value (a firing rate, a stimulus) beyond +-6e4: the kernels detect that on the device and the same
  *     call then repeats the solve on TF32 halves (rk4: a second kernel of the same launch sequence that returns at once
- *     otherwise; Euler-Maruyama: at the host polls these entry points already have), so results never depend on it.
+ *     otherwise; Euler-Maruyama / dopri5: at the host polls these entry points already have; srk: one read after the last
+ *     step), so results never depend on it.
  *
  * The problem integrated (all three reference networks reduce to it):
  *
