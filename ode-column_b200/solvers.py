@@ -329,6 +329,11 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     ``bm(t0, t1, return_U=True)``, tabulated along the step schedule.  ``adaptive=True`` uses step doubling with
     torchsde's controller, per trial, on a virtual Brownian tree (Philox only): 'euler' for every network size, 'srk' (on
     a Levy-area-consistent tree) for the on-chip family.
+    ``seed``: None -> a fresh key from torch's global generator on every call (independent paths per call, as torchsde's
+    fresh BrownianInterval gives; ``torch.manual_seed`` reproduces a run); an int fixes the paths.  ``trial_offset``: the
+    GLOBAL index of this call's first trial.  A job sharded over ranks or chunks passes ONE seed everywhere and
+    ``trial_offset = lo`` of its block (``distributed.shard_bounds``): trial t then sees the same Brownian path wherever
+    it runs, and results do not depend on the sharding.
     ``options['sigma_scale']``: (B,) per-trial factor on the diffusion -- the noise-amplitude axis of a parameter sweep
     (trial b integrates with g = sigma_scale[b] * diffusion); ``options['lateral_gain']``: (B,) positive per-trial gain on
     the between-column recurrent weights (networks with ``lateral_split()``, e.g. ``SyntheticColumnSheet``; Euler-Maruyama,
